@@ -1,0 +1,227 @@
+/* msig.h — C ABI of the B200-native operator library behind the drop-in
+ * Generator / StyleEncoder / Discriminator / VGG-loss modules.
+ *
+ * The reference (/root/reference) has no FFI: its arithmetic is issued through torch.nn
+ * (cuDNN / cuBLAS / ATen). Each entry point below names the reference call sites it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch caching allocator); the
+ *     library never allocates, frees or retains buffers;
+ *   - activations are bf16 NHWC ("pixel-major"), statistics / losses / gradients of parameters
+ *     are fp32; images at the module surface are fp32 NCHW like the reference's;
+ *   - every call is asynchronous on the cudaStream_t passed as `stream` (void*), never
+ *     synchronises the device, and is safe under CUDA-graph capture;
+ *   - return value: 0 = ok, negative = error (message: msig_last_error()). Unsupported shapes
+ *     fail loudly; there is no CPU or library fallback.
+ */
+#ifndef MSIG_H_
+#define MSIG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSIG_VERSION 100
+
+enum { MSIG_OK = 0, MSIG_ERR_ARG = -1, MSIG_ERR_CUDA = -2, MSIG_ERR_UNSUPPORTED = -3, MSIG_ERR_NCCL = -4 };
+
+enum { MSIG_ACT_NONE = 0, MSIG_ACT_RELU = 1, MSIG_ACT_LRELU = 2, MSIG_ACT_TANH = 3 };
+enum { MSIG_AUX_NONE = 0, MSIG_AUX_ADD = 1, MSIG_AUX_RELU_MASK = 2, MSIG_AUX_LRELU_MASK = 3 };
+enum { MSIG_OUT_BF16_NHWC = 0, MSIG_OUT_F32_NCHW = 1, MSIG_OUT_F32_NHWC = 2 };
+
+/* ---- context ------------------------------------------------------------------------ */
+int msig_init(int device);               /* binds the device, resolves cuTensorMapEncodeTiled */
+int msig_version(void);
+const char* msig_last_error(void);       /* thread-local */
+int msig_sm_count(void);
+long long msig_kernel_launches(void);    /* kernels launched by this library since load */
+
+/* ---- convolution geometry -------------------------------------------------------------
+ * x: [n,h,w,c] bf16 NHWC -> y: [n,oh,ow,k]. stride 1 or 2; pad_t/pad_l are the top/left zero
+ * padding (bottom/right follow from oh/ow; asymmetric padding as in ZeroPad2d((1,0,1,0)) +
+ * padding=1, model.py:182-183, is pad_t=pad_l=2). c must be a multiple of 64. */
+typedef struct msig_conv_geom {
+  int32_t n, h, w, c;
+  int32_t k;
+  int32_t r, s, stride, pad_t, pad_l;
+  int32_t oh, ow;
+} msig_conv_geom;
+
+/* Fused epilogue of every GEMM-shaped op:  y = act( aux_op( alpha*acc + bias ) ). */
+typedef struct msig_epilogue {
+  const float* bias;      /* [k] fp32 or NULL */
+  const void* aux;        /* bf16 tensor shaped like the bf16 NHWC output, or NULL */
+  int32_t aux_mode;       /* MSIG_AUX_* : residual add, or multiply by act'(aux) (ReLU / LeakyReLU) */
+  int32_t act;            /* MSIG_ACT_* */
+  float alpha;            /* 1.0f for plain convs */
+  const float* alpha_ptr; /* optional DEVICE scalar multiplied into alpha (upstream loss gradient) */
+  float slope;            /* LeakyReLU slope */
+  int32_t out_layout;     /* MSIG_OUT_* */
+} msig_epilogue;
+
+/* ---- weight packing --------------------------------------------------------------------
+ * Master weights stay fp32 in the reference's state_dict layout (OIHW; ConvTranspose2d IOHW;
+ * Linear [out,in]). Packed bf16 copies are derived caches, refreshed after each optimizer step. */
+enum {
+  MSIG_WPACK_FWD = 0,         /* OIHW -> [Opad][r*s][I]            conv fwd / Linear fwd (r=s=1)      */
+  MSIG_WPACK_DGRAD_S1 = 1,    /* OIHW -> [Ipad][flip(r*s)][O]      dgrad of stride-1 conv / Linear    */
+  MSIG_WPACK_DGRAD_S2 = 2,    /* OIHW(4x4,s2,p1) -> 4 x [Ipad][2*2][O]  dgrad as 4 output phases      */
+  MSIG_WPACK_CONVT_FWD = 3,   /* IOHW(4x4,s2,p1) -> 4 x [Opad][2*2][I]  transposed conv, 4 phases     */
+  MSIG_WPACK_CONVT_DGRAD = 4, /* IOHW -> [Ipad][4*4][O]            dgrad of transposed conv (s2 conv) */
+  MSIG_WPACK_IM2COL = 5,      /* OIHW (small I) -> [Opad][Kpad], k=(r*s)*I+i   gathered-patch GEMM    */
+  MSIG_WPACK_IM2COL_DGRAD = 6,/* OIHW (small I) -> [Kpad][O]                   its dgrad              */
+  MSIG_WPACK_IM2COL_FLIP = 7, /* OIHW (small O) -> [Ipad][Kpad], k=flip(r*s)*O+o  dgrad of a small-O conv via gathered dy */
+};
+typedef struct msig_wpack_desc {
+  int32_t kind;
+  int32_t o, i, r, s;     /* dims of the fp32 master weight as the reference stores it */
+} msig_wpack_desc;
+size_t msig_wpack_elems(const msig_wpack_desc* d);   /* bf16 elements of the packed buffer */
+int msig_wpack(const msig_wpack_desc* d, const float* w, void* packed, void* stream);
+
+/* ---- convolutions (tcgen05 implicit GEMM) ------------------------------------------------
+ * Replace nn.Conv2d (model.py:45,48,72-75,132-133,165,183; losses.py:15), nn.Linear
+ * (model.py:18; r=s=1 on a [1,1,M,K] view) and the 1x1 heads (model.py:84). */
+int msig_conv2d_fwd(const msig_conv_geom* g, const void* x, const void* w_fwd,
+                    const msig_epilogue* e, void* y, void* stream);
+/* dx = dgrad(dy): w_dgrad is MSIG_WPACK_DGRAD_S1 (stride 1) or MSIG_WPACK_DGRAD_S2 (stride 2). */
+int msig_conv2d_dgrad(const msig_conv_geom* g, const void* dy, const void* w_dgrad,
+                      const msig_epilogue* e, void* dx, void* stream);
+/* dw (fp32, reference layout OIHW) (+)= wgrad(x, dy). workspace holds split-K partials. */
+size_t msig_conv2d_wgrad_workspace(const msig_conv_geom* g);
+int msig_conv2d_wgrad(const msig_conv_geom* g, const void* x, const void* dy, float* dw,
+                      int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ConvTranspose2d(k=4, s=2, p=1) (model.py:139-140): x [n,h,w,c] -> y [n,2h,2w,k];
+ * geometry fields: n,h,w,c = input, k = output channels, oh=2h, ow=2w, r=s=4, stride=2. */
+int msig_convT2d_fwd(const msig_conv_geom* g, const void* x, const void* w_convt_fwd,
+                     const msig_epilogue* e, void* y, void* stream);
+int msig_convT2d_dgrad(const msig_conv_geom* g, const void* dy, const void* w_convt_dgrad,
+                       const msig_epilogue* e, void* dx, void* stream);
+size_t msig_convT2d_wgrad_workspace(const msig_conv_geom* g);
+int msig_convT2d_wgrad(const msig_conv_geom* g, const void* x, const void* dy, float* dw,
+                       int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- gathered-patch ("im2col") path for the narrow convs (3-channel images, few-channel
+ * gradients): model.py:131 (7x7 reflect, 3->64), :72/:165 (4x4 s2, 3->64), :141 (64->3 backward),
+ * :183 (head backward), losses.py conv_1_1. Source is fp32 NCHW [n,c,h,w]; patches go to a bf16
+ * [n*oh*ow][kpad] matrix with k = (r*S+s)*c + ch, kpad = roundup(r*s*c, 64); then the GEMM runs
+ * through msig_conv2d_fwd / msig_conv2d_wgrad with r=s=1. scale/shift (per channel, may be NULL)
+ * fold the VGG input renormalisation (losses.py:49-56) into the gather. */
+typedef struct msig_patch_geom {
+  int32_t n, c, h, w;
+  int32_t r, s, stride, pad_t, pad_l;
+  int32_t oh, ow;
+  int32_t reflect;        /* 1: reflect padding (padding_mode='reflect'), 0: zero padding */
+  int32_t kpad;
+} msig_patch_geom;
+int msig_patch_gather(const msig_patch_geom* g, const float* src_nchw, const float* scale,
+                      const float* shift, void* patches, void* stream);
+/* Adjoint: dsrc[n,c,h,w] (fp32, (+)=) = scale[c] * sum of the patch-gradient entries that read it. */
+int msig_patch_scatter(const msig_patch_geom* g, const void* dpatches, const float* scale,
+                       float* dsrc_nchw, int accumulate, void* stream);
+/* wgrad for a gathered-patch GEMM: dw (OIHW fp32, o x c x r x s) (+)= dy^T * patches.
+ * `flip`=1 is the MSIG_WPACK_IM2COL_FLIP arrangement (patches gathered from dy, `other` = input). */
+size_t msig_patch_wgrad_workspace(int64_t rows, int32_t m, int32_t ncols);
+int msig_patch_wgrad(const msig_wpack_desc* d, int64_t rows, const void* a_rows_m, const void* b_rows_n,
+                     float* dw, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- reflect padding of NHWC bf16 (7x7 reflect conv on 64 channels, model.py:141) -------- */
+int msig_reflect_pad_fwd(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad,
+                         void* y, void* stream);
+int msig_reflect_pad_bwd(const void* dy, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad,
+                         void* dx, void* stream);
+
+/* ---- InstanceNorm / AdaIN (model.py:16,20-36,131-133,139-140,167) -----------------------
+ * x: [n,hw,c] bf16. Statistics are biased, eps inside the sqrt, fp32.
+ * gamma/beta: fp32 with row stride `gb_stride` (NULL = plain InstanceNorm, gamma=1, beta=0);
+ * a row stride of 0 broadcasts one style code over the batch. */
+size_t msig_in_stats_workspace(int32_t n, int32_t hw, int32_t c);
+int msig_in_stats(const void* x, int32_t n, int32_t hw, int32_t c, float eps,
+                  const float* gamma, const float* beta, int64_t gb_stride,
+                  float* mean, float* rstd, float* scale, float* shift,
+                  void* workspace, size_t workspace_bytes, void* stream);
+/* y = act(x*scale + shift) (+ residual) */
+int msig_norm_act_fwd(const void* x, const float* scale, const float* shift, const void* residual,
+                      int32_t act, float slope, int32_t n, int32_t hw, int32_t c, void* y,
+                      void* stream);
+/* dx from dy (grad of y); also dgamma/dbeta [n,c] with row stride gb_stride (may be NULL). */
+int msig_norm_act_bwd(const void* dy, const void* x, const float* mean, const float* rstd,
+                      const float* scale, const float* shift, const float* gamma, int64_t gb_stride,
+                      int32_t act, float slope, int32_t n, int32_t hw, int32_t c, void* dx,
+                      float* dgamma, float* dbeta, int64_t dgb_stride, int accumulate_dgb,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- small bandwidth ops ------------------------------------------------------------------ */
+/* dz = dy * act'(y) (ReLU / LeakyReLU), bf16 */
+int msig_act_bwd(const void* dy, const void* y, int32_t act, float slope, int64_t numel, void* dz,
+                 void* stream);
+/* out = a + b (bf16) */
+int msig_add_bf16(const void* a, const void* b, int64_t numel, void* out, void* stream);
+/* bias gradient: db[c] (+)= sum over rows of dy[rows][c] (bf16 rows, fp32 out) */
+int msig_colsum(const void* dy, int64_t rows, int32_t c, float* db, int accumulate, void* stream);
+/* MaxPool2d(2) on NHWC bf16 (losses.py pool_2 / pool_4) */
+int msig_maxpool2_fwd(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* y, void* stream);
+int msig_maxpool2_bwd(const void* dy, const void* x, const void* y, int32_t n, int32_t h, int32_t w,
+                      int32_t c, void* dx, void* stream);
+/* AdaptiveAvgPool2d(1) (model.py:76): [n,hw,c] bf16 -> [n,c] bf16, and its backward */
+int msig_avgpool_fwd(const void* x, int32_t n, int32_t hw, int32_t c, void* y, void* stream);
+int msig_avgpool_bwd(const void* dy, int32_t n, int32_t hw, int32_t c, void* dx, void* stream);
+/* per-sample head selection (model.py:112-116, 208-212): out[b, :] = all[b, idx[b], :] over a
+ * [n, heads*per_head] fp32 row (SE) or [n, pix, heads_pad] (D); the backward writes zeros to the
+ * unselected heads. idx is int64 like the reference's domain_idx. */
+int msig_head_gather(const float* all, const int64_t* idx, int32_t n, int32_t pix, int32_t heads_ld,
+                     int32_t per_head, int32_t head_major, float* out, void* stream);
+int msig_head_scatter(const float* dout, const int64_t* idx, int32_t n, int32_t pix, int32_t heads_ld,
+                      int32_t per_head, int32_t head_major, float* dall, void* stream);
+/* dtype / layout converters at the module surface */
+int msig_f32_to_bf16(const float* x, int64_t numel, void* y, void* stream);
+int msig_bf16_to_f32(const void* x, int64_t numel, float* y, void* stream);
+int msig_tanh_bwd(const float* dy, const float* y, int64_t numel, float* dz, void* stream);
+/* sum over (n, h, w) of an fp32 NCHW tensor per channel (bias grad of the final conv) */
+int msig_nchw_chansum(const float* x, int32_t n, int32_t c, int64_t hw, float* out, int accumulate,
+                      void* stream);
+
+/* ---- losses (trainer.py:50-52, losses.py:70-98) ---------------------------------------------
+ * Forward kernels write the mean-reduced loss (fp32 device scalar). Backward kernels write
+ * d(loss)/da * (*gscale), where gscale is the upstream gradient as a DEVICE scalar, so no host
+ * synchronisation is needed anywhere in a training step. */
+int msig_l1_loss_f32_fwd(const float* a, const float* b, int64_t numel, float* loss, void* stream);
+int msig_l1_loss_f32_bwd(const float* a, const float* b, int64_t numel, const float* gscale,
+                         float* grad_a, void* stream);                   /* nn.L1Loss on images */
+int msig_l1_loss_bf16_fwd(const void* a, const void* b, int64_t numel, float* loss, void* stream);
+int msig_l1_loss_bf16_bwd(const void* a, const void* b, int64_t numel, const float* gscale,
+                          const void* aux, void* grad_a, void* stream);  /* F.l1_loss on VGG features; (+ aux) */
+int msig_mse_const_fwd(const float* a, float target, int64_t numel, float* loss, void* stream);
+int msig_mse_const_bwd(const float* a, float target, int64_t numel, const float* gscale,
+                       float* grad_a, void* stream);                     /* nn.MSELoss vs ones / zeros */
+/* Gram matrix (losses.py:70-78): f [n,h,w,c] bf16 -> G [n*c][n*c] fp32 = F F^T / (n*c*h*w), batch
+ * folded into rows exactly like the reference's view(a*b, c*d). */
+size_t msig_gram_workspace(int32_t n, int32_t h, int32_t w, int32_t c);
+int msig_gram_fwd(const void* f, int32_t n, int32_t h, int32_t w, int32_t c, float* gram,
+                  void* workspace, size_t workspace_bytes, void* stream);
+/* loss = mean |G_a - G_b|; ssym (bf16 [dim][dim]) = sign(D) + sign(D)^T, D = G_a - G_b. */
+int msig_gram_l1(const float* ga, const float* gb, int32_t dim, float* loss, void* ssym, void* stream);
+/* df = alpha * (*gscale) * ssym * F (+ aux): gradient of the style term w.r.t. the generated
+ * features; alpha = 1 / (dim^2 * n*c*h*w) supplied by the caller. */
+int msig_gram_bwd(const void* f, const void* ssym, int32_t n, int32_t h, int32_t w, int32_t c,
+                  float alpha, const float* gscale, const void* aux, void* df, void* stream);
+/* column sums of an fp32 [rows][c] matrix (bias gradients of the fp32 heads / style Linear) */
+int msig_colsum_f32(const float* x, int64_t rows, int32_t c, float* out, int accumulate, void* stream);
+
+/* ---- optimizer-side multi-tensor ops on flat fp32 buffers (trainer.py:127-134,152-153;
+ *      utils.py:80-91): global grad-norm clip + Adam + EMA + in one pass ------------------- */
+int msig_sumsq(const float* x, int64_t numel, float* out /* fp32 scalar, (+)= */, int accumulate,
+               void* stream);
+int msig_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                   float* ema /* may be NULL */, int64_t numel, const float* grad_sumsq, float max_norm,
+                   float grad_scale, float lr, float beta1, float beta2, float eps, int32_t step,
+                   float ema_beta, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSIG_H_ */

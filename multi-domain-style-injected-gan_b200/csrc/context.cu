@@ -1,0 +1,66 @@
+// Library context: device binding, error reporting, driver entry point for TMA descriptors.
+#include "common.h"
+#include "igemm.cuh"
+
+#include <cstring>
+#include <mutex>
+
+namespace msig {
+
+static thread_local char g_err[512] = "";
+static int g_sm_count = 0;
+static int g_device = -1;
+static EncodeTiledFn g_encode = nullptr;
+static std::mutex g_init_mu;
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int sm_count() { return g_sm_count; }
+bool context_ready() { return g_encode != nullptr; }
+EncodeTiledFn encode_tiled() { return g_encode; }
+
+}  // namespace msig
+
+using namespace msig;
+
+extern "C" {
+
+int msig_version(void) { return MSIG_VERSION; }
+const char* msig_last_error(void) { return g_err; }
+int msig_sm_count(void) { return g_sm_count; }
+long long msig_kernel_launches(void) { return igemm_kernel_launches(); }
+
+int msig_init(int device) {
+  std::lock_guard<std::mutex> lock(g_init_mu);
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0)
+    return set_error(MSIG_ERR_CUDA, "msig_init: no CUDA device (%s); this library has no CPU path",
+                     cudaGetErrorString(e));
+  if (device < 0 || device >= count) return set_error(MSIG_ERR_ARG, "msig_init: bad device %d", device);
+  MSIG_CHECK_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  MSIG_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return set_error(MSIG_ERR_UNSUPPORTED,
+                     "msig_init: device %d is sm_%d%d; this library is built for sm_100a only", device,
+                     prop.major, prop.minor);
+  g_sm_count = prop.multiProcessorCount;
+  g_device = device;
+  if (g_encode == nullptr) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    MSIG_CHECK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (fn == nullptr || qres != cudaDriverEntryPointSuccess)
+      return set_error(MSIG_ERR_CUDA, "msig_init: cuTensorMapEncodeTiled not available");
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  return MSIG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,743 @@
+// Host side of the convolution entry points: geometry -> TMA descriptors + tap tables -> the two
+// tcgen05 implicit-GEMM kernels; weight packing and the split-K reduce / un-pack of weight grads.
+#include "common.h"
+#include "igemm.cuh"
+
+#include <algorithm>
+#include <cstring>
+
+namespace msig {
+
+// ------------------------------------------------------------------------ phase tables
+// k=4, s=2, p=1: output row 2i+py of a transposed conv (or input row of a stride-2 conv's dgrad)
+// reads source row i+d through filter row r, for two (r, d) pairs per parity.
+__host__ __device__ inline int ph_r(int py, int ty) { return py == 0 ? (ty == 0 ? 1 : 3) : (ty == 0 ? 0 : 2); }
+__host__ __device__ inline int ph_d(int py, int ty) { return py == 0 ? (ty == 0 ? 0 : -1) : (ty == 0 ? 1 : 0); }
+// inverse: filter row r -> (parity, tap-in-phase)
+__host__ __device__ inline void r_to_ph(int r, int& py, int& ty) {
+  py = (r == 1 || r == 3) ? 0 : 1;
+  ty = (r == 1 || r == 0) ? 0 : 1;
+}
+
+// ------------------------------------------------------------------------ weight pack / unpack
+struct PackGeom {
+  int kind, O, I, R, S, OC, OOFF;
+  int RS, Ipad, Opad, Kpad;
+};
+
+static PackGeom make_pack_geom(const msig_wpack_desc* d, int oc, int ooff) {
+  PackGeom g;
+  g.kind = d->kind; g.O = d->o; g.I = d->i; g.R = d->r; g.S = d->s;
+  g.OC = oc > 0 ? oc : d->o;
+  g.OOFF = ooff;
+  g.RS = g.R * g.S;
+  g.Ipad = pad_rows(g.I);
+  g.Opad = pad_rows(g.OC);
+  if (g.kind == MSIG_WPACK_IM2COL_FLIP) g.Kpad = static_cast<int>(round_up(int64_t(g.RS) * g.OC, 64));
+  else g.Kpad = static_cast<int>(round_up(int64_t(g.RS) * g.I, 64));
+  return g;
+}
+
+static int64_t pack_elems(const PackGeom& g) {
+  switch (g.kind) {
+    case MSIG_WPACK_FWD: return int64_t(g.Opad) * g.RS * g.I;
+    case MSIG_WPACK_DGRAD_S1: return int64_t(g.Ipad) * g.RS * g.OC;
+    case MSIG_WPACK_DGRAD_S2: return int64_t(4) * g.Ipad * 4 * g.OC;
+    case MSIG_WPACK_CONVT_FWD: return int64_t(4) * g.Opad * 4 * g.I;
+    case MSIG_WPACK_CONVT_DGRAD: return int64_t(g.Ipad) * 16 * g.OC;
+    case MSIG_WPACK_IM2COL: return int64_t(g.Opad) * g.Kpad;
+    case MSIG_WPACK_IM2COL_DGRAD: return int64_t(g.Kpad) * g.OC;
+    case MSIG_WPACK_IM2COL_FLIP: return int64_t(g.Ipad) * g.Kpad;
+    default: return -1;
+  }
+}
+
+// (o, i, t) of the master weight -> linear index in the master tensor.
+__device__ __forceinline__ void decode_src(const PackGeom& g, int64_t idx, int& o, int& i, int& t) {
+  if (g.kind == MSIG_WPACK_CONVT_FWD || g.kind == MSIG_WPACK_CONVT_DGRAD) {  // [I][O][4][4]
+    t = static_cast<int>(idx % 16);
+    o = static_cast<int>((idx / 16) % g.O);
+    i = static_cast<int>(idx / (int64_t(16) * g.O));
+  } else {  // [O][I][R][S]
+    t = static_cast<int>(idx % g.RS);
+    i = static_cast<int>((idx / g.RS) % g.I);
+    o = static_cast<int>(idx / (int64_t(g.RS) * g.I));
+  }
+}
+
+// (o, i, t) -> offset in the packed bf16 matrix
+__device__ __forceinline__ int64_t packed_offset(const PackGeom& g, int o, int i, int t) {
+  const int oo = o + g.OOFF;
+  switch (g.kind) {
+    case MSIG_WPACK_FWD: return (int64_t(oo) * g.RS + t) * g.I + i;
+    case MSIG_WPACK_DGRAD_S1: return (int64_t(i) * g.RS + (g.RS - 1 - t)) * g.OC + oo;
+    case MSIG_WPACK_DGRAD_S2: {
+      int py, ty, px, tx;
+      r_to_ph(t / 4, py, ty);
+      r_to_ph(t % 4, px, tx);
+      return ((int64_t(py * 2 + px) * g.Ipad + i) * 4 + (ty * 2 + tx)) * g.OC + oo;
+    }
+    case MSIG_WPACK_CONVT_FWD: {
+      int py, ty, px, tx;
+      r_to_ph(t / 4, py, ty);
+      r_to_ph(t % 4, px, tx);
+      return ((int64_t(py * 2 + px) * g.Opad + oo) * 4 + (ty * 2 + tx)) * g.I + i;
+    }
+    case MSIG_WPACK_CONVT_DGRAD: return (int64_t(i) * 16 + t) * g.OC + oo;
+    case MSIG_WPACK_IM2COL: return int64_t(oo) * g.Kpad + t * g.I + i;
+    case MSIG_WPACK_IM2COL_DGRAD: return (int64_t(t) * g.I + i) * g.OC + oo;
+    case MSIG_WPACK_IM2COL_FLIP: return int64_t(i) * g.Kpad + (g.RS - 1 - t) * g.OC + oo;
+  }
+  return 0;
+}
+
+__global__ void wpack_kernel(PackGeom g, const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
+                             int64_t numel) {
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < numel;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    int o, i, t;
+    decode_src(g, idx, o, i, t);
+    out[packed_offset(g, o, i, t)] = __float2bfloat16(w[idx]);
+  }
+}
+
+// Layout of the fp32 split-K partials written by the wgrad kernel, per kind:
+//   FWD          [O][RS][I]            CONVT_FWD     [O][16 = phase*4+tap][I]
+//   IM2COL       [O][Kpad]             IM2COL_FLIP   [Kpad][I]
+__device__ __forceinline__ int64_t partial_offset(const PackGeom& g, int o, int i, int t) {
+  switch (g.kind) {
+    case MSIG_WPACK_FWD: return (int64_t(o) * g.RS + t) * g.I + i;
+    case MSIG_WPACK_CONVT_FWD: {
+      int py, ty, px, tx;
+      r_to_ph(t / 4, py, ty);
+      r_to_ph(t % 4, px, tx);
+      return (int64_t(o) * 16 + (py * 2 + px) * 4 + (ty * 2 + tx)) * g.I + i;
+    }
+    case MSIG_WPACK_IM2COL: return int64_t(o) * g.Kpad + t * g.I + i;
+    case MSIG_WPACK_IM2COL_FLIP: return (int64_t(g.RS - 1 - t) * g.OC + o + g.OOFF) * g.I + i;
+  }
+  return 0;
+}
+
+__global__ void wgrad_reduce_kernel(PackGeom g, const float* __restrict__ partial, int splits,
+                                    int64_t split_stride, float* __restrict__ dw, int accumulate,
+                                    int64_t numel) {
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < numel;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    int o, i, t;
+    decode_src(g, idx, o, i, t);
+    const int64_t off = partial_offset(g, o, i, t);
+    float acc = accumulate ? dw[idx] : 0.f;
+    for (int s = 0; s < splits; ++s) acc += partial[s * split_stride + off];
+    dw[idx] = acc;
+  }
+}
+
+static int launch_wgrad_reduce(const PackGeom& g, const float* partial, int splits,
+                               int64_t split_stride, float* dw, int accumulate, cudaStream_t st) {
+  const int64_t numel = int64_t(g.O) * g.I * g.RS;
+  const int threads = 256;
+  const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(numel, threads), 4096));
+  wgrad_reduce_kernel<<<blocks, threads, 0, st>>>(g, partial, splits, split_stride, dw, accumulate,
+                                                  numel);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
+// ------------------------------------------------------------------------ TMA descriptors
+struct ActView {
+  const void* base;
+  int64_t C, W, H, N;      // extents
+  int64_t sW, sH, sN;      // element strides (channel stride is 1)
+};
+
+static int make_act_map(CUtensorMap* m, const ActView& v, int boxW, int boxH) {
+  if ((reinterpret_cast<uintptr_t>(v.base) & 15) != 0)
+    return set_error(MSIG_ERR_ARG, "activation base %p is not 16-byte aligned", v.base);
+  cuuint64_t dims[4] = {cuuint64_t(v.C), cuuint64_t(v.W), cuuint64_t(v.H), cuuint64_t(v.N)};
+  cuuint64_t strides[3] = {cuuint64_t(v.sW) * 2, cuuint64_t(v.sH) * 2, cuuint64_t(v.sN) * 2};
+  cuuint32_t box[4] = {64, cuuint32_t(boxW), cuuint32_t(boxH), 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 3; ++i)
+    if (strides[i] % 16 != 0) return set_error(MSIG_ERR_ARG, "TMA stride %d not a multiple of 16 B", i);
+  CUresult r = encode_tiled()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.base), dims,
+                              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(MSIG_ERR_CUDA,
+                     "cuTensorMapEncodeTiled(act) failed: %d (dims %lld,%lld,%lld,%lld box %d,%d)", int(r),
+                     (long long)v.C, (long long)v.W, (long long)v.H, (long long)v.N, boxW, boxH);
+  return MSIG_OK;
+}
+
+static int make_w_map(CUtensorMap* m, const void* w, int64_t rows, int64_t K, int box_rows) {
+  if ((reinterpret_cast<uintptr_t>(w) & 15) != 0)
+    return set_error(MSIG_ERR_ARG, "packed weight base %p is not 16-byte aligned", w);
+  if (K % 64 != 0) return set_error(MSIG_ERR_ARG, "packed weight K=%lld is not a multiple of 64", (long long)K);
+  cuuint64_t dims[2] = {cuuint64_t(K), cuuint64_t(rows)};
+  cuuint64_t strides[1] = {cuuint64_t(K) * 2};
+  cuuint32_t box[2] = {64, cuuint32_t(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = encode_tiled()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(w), dims, strides,
+                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(MSIG_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d (rows %lld K %lld box %d)",
+                     int(r), (long long)rows, (long long)K, box_rows);
+  return MSIG_OK;
+}
+
+// 128-pixel output tile: TW x TH.
+static void pick_tile(int OW, int& TW, int& TH) {
+  if (OW == 64) { TW = 64; TH = 2; }
+  else if (OW == 32) { TW = 32; TH = 4; }
+  else if (OW == 16) { TW = 16; TH = 8; }
+  else { TW = 128; TH = 1; }
+}
+// 64-pixel K block of the wgrad kernel: PW x PH.
+static void pick_kblock(int OW, int& PW, int& PH) {
+  if (OW == 32) { PW = 32; PH = 2; }
+  else if (OW == 16) { PW = 16; PH = 4; }
+  else { PW = 64; PH = 1; }
+}
+
+struct OutView {
+  void* base;
+  int64_t sN, sH, sW, sC;
+  int f32;
+};
+
+// Output / aux views for a [n, OH, OW, k] result in the requested layout.
+static OutView make_out_view(void* y, int layout, int64_t OH, int64_t OW, int64_t k) {
+  OutView v;
+  v.base = y;
+  if (layout == MSIG_OUT_F32_NCHW) {
+    v.sN = k * OH * OW; v.sC = OH * OW; v.sH = OW; v.sW = 1; v.f32 = 1;
+  } else {
+    v.sN = OH * OW * k; v.sH = OW * k; v.sW = k; v.sC = 1; v.f32 = (layout == MSIG_OUT_F32_NHWC);
+  }
+  return v;
+}
+
+static int fill_epilogue(FpropParams& p, const msig_epilogue* e, const OutView& ov, int n_valid) {
+  p.out = ov.base;
+  p.o_sn = ov.sN; p.o_sh = ov.sH; p.o_sw = ov.sW; p.o_sc = ov.sC;
+  p.out_f32 = ov.f32;
+  p.n_valid = n_valid;
+  p.bias = e ? e->bias : nullptr;
+  p.alpha = e ? e->alpha : 1.f;
+  p.alpha_ptr = e ? e->alpha_ptr : nullptr;
+  p.act = e ? e->act : ACT_NONE;
+  p.slope = e ? e->slope : 0.f;
+  p.aux = e ? reinterpret_cast<const __nv_bfloat16*>(e->aux) : nullptr;
+  p.aux_mode = (e && e->aux) ? e->aux_mode : AUX_NONE;
+  p.a_sn = ov.sN; p.a_sh = ov.sH; p.a_sw = ov.sW;   // aux is congruent with a bf16 NHWC output
+  if (p.aux_mode != AUX_NONE && (ov.f32 || ov.sC != 1))
+    return set_error(MSIG_ERR_UNSUPPORTED, "epilogue aux needs a bf16 NHWC output");
+  if (!ov.f32 && ov.sC == 1 && (n_valid % 8) != 0)
+    return set_error(MSIG_ERR_UNSUPPORTED, "bf16 NHWC output needs k %% 8 == 0 (k=%d)", n_valid);
+  if ((p.bias != nullptr) && !ov.f32 && (reinterpret_cast<uintptr_t>(p.bias) & 15) != 0)
+    return set_error(MSIG_ERR_ARG, "bias pointer must be 16-byte aligned");
+  return MSIG_OK;
+}
+
+static void init_fprop(FpropParams& p) {
+  memset(&p, 0, sizeof(p));
+  p.phases = 1;
+  p.alpha = 1.f;
+}
+
+// Plain (stride 1 or 2) convolution of `in` [n,h,w,c] with a [rows][taps*c] packed matrix.
+static int run_conv(const void* in, int n, int h, int w, int c, int k, int R, int S, int stride,
+                    int pad_t, int pad_l, int OH, int OW, const void* wpk, const msig_epilogue* e,
+                    void* out, cudaStream_t st) {
+  MSIG_REQUIRE(context_ready(), "msig_init() has not been called");
+  MSIG_REQUIRE(c % 64 == 0, "conv: input channels (%d) must be a multiple of 64", c);
+  MSIG_REQUIRE(stride == 1 || stride == 2, "conv: stride %d unsupported", stride);
+  MSIG_REQUIRE(R * S <= kMaxTaps, "conv: %dx%d filter has too many taps", R, S);
+  FpropParams p;
+  init_fprop(p);
+  const int k_pad = pad_rows(k);
+  const int block_n = pick_block_n(k_pad);
+  pick_tile(OW, p.TW, p.TH);
+  p.OH = OH; p.OW = OW;
+  p.tiles_h = static_cast<int>(ceil_div(OH, p.TH));
+  p.tiles_w = static_cast<int>(ceil_div(OW, p.TW));
+  p.n_img = n;
+  p.n_blocks = k_pad / block_n;
+  p.taps = R * S;
+  p.cblocks = c / 64;
+  int rc;
+  if (stride == 1) {
+    ActView v{in, c, w, h, n, c, int64_t(w) * c, int64_t(h) * w * c};
+    if ((rc = make_act_map(&p.tmA[0], v, p.TW, p.TH)) != MSIG_OK) return rc;
+    for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+    for (int r = 0; r < R; ++r)
+      for (int s = 0; s < S; ++s) p.tap[r * S + s] = Tap{int8_t(r - pad_t), int8_t(s - pad_l), 0, 0};
+  } else {
+    MSIG_REQUIRE(h % 2 == 0 && w % 2 == 0, "stride-2 conv needs even input dims (%d x %d)", h, w);
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(in) + (int64_t(ph) * w + pw) * c;
+        ActView v{base, c, w / 2, h / 2, n, int64_t(2) * c, int64_t(2) * w * c, int64_t(h) * w * c};
+        if ((rc = make_act_map(&p.tmA[ph * 2 + pw], v, p.TW, p.TH)) != MSIG_OK) return rc;
+      }
+    for (int r = 0; r < R; ++r)
+      for (int s = 0; s < S; ++s) {
+        const int rr = r - pad_t, ss = s - pad_l;
+        const int ph = ((rr % 2) + 2) % 2, pw = ((ss % 2) + 2) % 2;
+        p.tap[r * S + s] = Tap{int8_t((rr - ph) / 2), int8_t((ss - pw) / 2), int8_t(ph * 2 + pw), 0};
+      }
+  }
+  if ((rc = make_w_map(&p.tmB, wpk, k_pad, int64_t(R) * S * c, block_n)) != MSIG_OK) return rc;
+  const OutView ov = make_out_view(out, e ? e->out_layout : MSIG_OUT_BF16_NHWC, OH, OW, k);
+  if ((rc = fill_epilogue(p, e, ov, k)) != MSIG_OK) return rc;
+  cudaError_t ce = launch_fprop(p, block_n, sm_count(), st);
+  if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "fprop launch: %s", cudaGetErrorString(ce));
+  return MSIG_OK;
+}
+
+// Phase-decomposed k4 s2 p1 transposed structure: `in` [n,h,w,c] -> out [n,2h,2w,k]; packed
+// weights are 4 slabs of [k_pad][4*c].
+static int run_phased(const void* in, int n, int h, int w, int c, int k, const void* wpk,
+                      const msig_epilogue* e, void* out, cudaStream_t st) {
+  MSIG_REQUIRE(context_ready(), "msig_init() has not been called");
+  MSIG_REQUIRE(c % 64 == 0, "transposed conv: input channels (%d) must be a multiple of 64", c);
+  MSIG_REQUIRE(k % 8 == 0, "transposed conv: output channels (%d) must be a multiple of 8", k);
+  const int layout = e ? e->out_layout : MSIG_OUT_BF16_NHWC;
+  MSIG_REQUIRE(layout == MSIG_OUT_BF16_NHWC, "transposed conv writes bf16 NHWC only");
+  FpropParams p;
+  init_fprop(p);
+  const int k_pad = pad_rows(k);
+  const int block_n = pick_block_n(k_pad);
+  pick_tile(w, p.TW, p.TH);
+  p.OH = h; p.OW = w;                      // per-phase output plane
+  p.tiles_h = static_cast<int>(ceil_div(h, p.TH));
+  p.tiles_w = static_cast<int>(ceil_div(w, p.TW));
+  p.n_img = n;
+  p.n_blocks = k_pad / block_n;
+  p.taps = 4;
+  p.cblocks = c / 64;
+  p.phases = 4;
+  p.b_row_per_phase = k_pad;
+  int rc;
+  ActView v{in, c, w, h, n, c, int64_t(w) * c, int64_t(h) * w * c};
+  if ((rc = make_act_map(&p.tmA[0], v, p.TW, p.TH)) != MSIG_OK) return rc;
+  for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+  const int64_t OW2 = 2 * int64_t(w);
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      const int ph = py * 2 + px;
+      for (int ty = 0; ty < 2; ++ty)
+        for (int tx = 0; tx < 2; ++tx)
+          p.tap[ph * 4 + ty * 2 + tx] = Tap{int8_t(ph_d(py, ty)), int8_t(ph_d(px, tx)), 0, 0};
+      p.o_ph[ph] = (py * OW2 + px) * k;
+      p.a_ph[ph] = p.o_ph[ph];
+    }
+  if ((rc = make_w_map(&p.tmB, wpk, int64_t(4) * k_pad, int64_t(4) * c, block_n)) != MSIG_OK) return rc;
+  OutView ov;
+  ov.base = out; ov.f32 = 0; ov.sC = 1;
+  ov.sN = int64_t(4) * h * w * k; ov.sH = 2 * OW2 * k; ov.sW = 2 * int64_t(k);
+  if ((rc = fill_epilogue(p, e, ov, k)) != MSIG_OK) return rc;
+  cudaError_t ce = launch_fprop(p, block_n, sm_count(), st);
+  if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "fprop(phased) launch: %s", cudaGetErrorString(ce));
+  return MSIG_OK;
+}
+
+// ------------------------------------------------------------------------ wgrad driver
+struct WgradPlan {
+  int block_n, m_blocks, n_blocks, splits, kb_per_split, kb_total;
+};
+
+static WgradPlan plan_wgrad(int M, int N, int taps, int64_t kb_total) {
+  WgradPlan pl;
+  pl.block_n = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
+  pl.m_blocks = static_cast<int>(ceil_div(M, 128));
+  pl.n_blocks = static_cast<int>(ceil_div(N, pl.block_n));
+  const int64_t base = int64_t(pl.m_blocks) * pl.n_blocks * taps;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  int64_t splits = ceil_div(2 * int64_t(sms), base);
+  splits = std::max<int64_t>(1, std::min<int64_t>(splits, ceil_div(kb_total, 8)));
+  splits = std::min<int64_t>(splits, 64);
+  pl.kb_per_split = static_cast<int>(ceil_div(kb_total, splits));
+  pl.splits = static_cast<int>(ceil_div(kb_total, pl.kb_per_split));
+  pl.kb_total = static_cast<int>(kb_total);
+  return pl;
+}
+
+
+__global__ void sum_splits_kernel(const float* __restrict__ partial, int splits, int64_t stride,
+                                  float* __restrict__ out, int64_t numel) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < numel;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += partial[s * stride + i];
+    out[i] = acc;
+  }
+}
+
+}  // namespace msig
+
+using namespace msig;
+
+extern "C" {
+
+size_t msig_wpack_elems(const msig_wpack_desc* d) {
+  if (!d) return 0;
+  PackGeom g = make_pack_geom(d, 0, 0);
+  const int64_t n = pack_elems(g);
+  return n < 0 ? 0 : static_cast<size_t>(n);
+}
+
+// Composite variant: this weight provides output channels [o_off, o_off + d->o) of a packed matrix
+// with `oc` output channels in total (per-domain heads, model.py:84,183). Padding rows/cols are
+// never written: the caller zero-initialises the packed buffer once.
+int msig_wpack_part(const msig_wpack_desc* d, int32_t oc, int32_t o_off, const float* w, void* packed,
+                    void* stream) {
+  MSIG_REQUIRE(d && w && packed, "msig_wpack: null argument");
+  PackGeom g = make_pack_geom(d, oc, o_off);
+  MSIG_REQUIRE(pack_elems(g) > 0, "msig_wpack: unknown kind %d", d->kind);
+  if (g.kind == MSIG_WPACK_DGRAD_S2 || g.kind == MSIG_WPACK_CONVT_FWD || g.kind == MSIG_WPACK_CONVT_DGRAD)
+    MSIG_REQUIRE(g.R == 4 && g.S == 4, "msig_wpack: kind %d needs a 4x4 filter", d->kind);
+  const int64_t numel = int64_t(g.O) * g.I * g.RS;
+  const int threads = 256;
+  const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(numel, threads), 4096));
+  wpack_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+      g, w, reinterpret_cast<__nv_bfloat16*>(packed), numel);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+size_t msig_wpack_part_elems(const msig_wpack_desc* d, int32_t oc) {
+  if (!d) return 0;
+  PackGeom g = make_pack_geom(d, oc, 0);
+  const int64_t n = pack_elems(g);
+  return n < 0 ? 0 : static_cast<size_t>(n);
+}
+
+int msig_wpack(const msig_wpack_desc* d, const float* w, void* packed, void* stream) {
+  return msig_wpack_part(d, 0, 0, w, packed, stream);
+}
+
+int msig_conv2d_fwd(const msig_conv_geom* g, const void* x, const void* w_fwd, const msig_epilogue* e,
+                    void* y, void* stream) {
+  MSIG_REQUIRE(g && x && w_fwd && y, "msig_conv2d_fwd: null argument");
+  return run_conv(x, g->n, g->h, g->w, g->c, g->k, g->r, g->s, g->stride, g->pad_t, g->pad_l, g->oh,
+                  g->ow, w_fwd, e, y, static_cast<cudaStream_t>(stream));
+}
+
+int msig_conv2d_dgrad(const msig_conv_geom* g, const void* dy, const void* w_dgrad,
+                      const msig_epilogue* e, void* dx, void* stream) {
+  MSIG_REQUIRE(g && dy && w_dgrad && dx, "msig_conv2d_dgrad: null argument");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (g->stride == 1) {
+    // dx[ih] = sum_r dy[ih + pad - r] w[r]  ==  conv of dy with the flipped filter, pad' = R-1-pad
+    return run_conv(dy, g->n, g->oh, g->ow, g->k, g->c, g->r, g->s, 1, g->r - 1 - g->pad_t,
+                    g->s - 1 - g->pad_l, g->h, g->w, w_dgrad, e, dx, st);
+  }
+  MSIG_REQUIRE(g->stride == 2 && g->r == 4 && g->s == 4 && g->pad_t == 1 && g->pad_l == 1 &&
+                   g->h == 2 * g->oh && g->w == 2 * g->ow,
+               "msig_conv2d_dgrad: stride-2 dgrad supports k=4,s=2,p=1 only");
+  return run_phased(dy, g->n, g->oh, g->ow, g->k, g->c, w_dgrad, e, dx, st);
+}
+
+int msig_convT2d_fwd(const msig_conv_geom* g, const void* x, const void* w, const msig_epilogue* e,
+                     void* y, void* stream) {
+  MSIG_REQUIRE(g && x && w && y, "msig_convT2d_fwd: null argument");
+  MSIG_REQUIRE(g->r == 4 && g->s == 4 && g->stride == 2 && g->oh == 2 * g->h && g->ow == 2 * g->w,
+               "msig_convT2d_fwd: supports k=4,s=2,p=1 only");
+  return run_phased(x, g->n, g->h, g->w, g->c, g->k, w, e, y, static_cast<cudaStream_t>(stream));
+}
+
+int msig_convT2d_dgrad(const msig_conv_geom* g, const void* dy, const void* w, const msig_epilogue* e,
+                       void* dx, void* stream) {
+  MSIG_REQUIRE(g && dy && w && dx, "msig_convT2d_dgrad: null argument");
+  // dx[ih, ci] = sum_{r,co} dy[2 ih - 1 + r, co] wT[ci][co][r]  ==  4x4 stride-2 pad-1 conv of dy
+  return run_conv(dy, g->n, g->oh, g->ow, g->k, g->c, 4, 4, 2, 1, 1, g->h, g->w, w, e, dx,
+                  static_cast<cudaStream_t>(stream));
+}
+
+// ---------------------------------------------------------------- weight gradients
+static size_t wgrad_ws_bytes(int M, int N, int taps, int64_t kb_total) {
+  WgradPlan pl = plan_wgrad(M, N, taps, kb_total);
+  return size_t(pl.splits) * size_t(M) * taps * N * sizeof(float);
+}
+
+size_t msig_conv2d_wgrad_workspace(const msig_conv_geom* g) {
+  if (!g) return 0;
+  int PW, PH;
+  pick_kblock(g->ow, PW, PH);
+  const int64_t kb = int64_t(g->n) * ceil_div(g->oh, PH) * ceil_div(g->ow, PW);
+  return wgrad_ws_bytes(g->k, g->c, g->r * g->s, kb);
+}
+
+int msig_conv2d_wgrad(const msig_conv_geom* g, const void* x, const void* dy, float* dw, int accumulate,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  MSIG_REQUIRE(g && x && dy && dw && workspace, "msig_conv2d_wgrad: null argument");
+  MSIG_REQUIRE(context_ready(), "msig_init() has not been called");
+  MSIG_REQUIRE(g->c % 64 == 0 && g->k % 64 == 0, "wgrad: c (%d) and k (%d) must be multiples of 64", g->c, g->k);
+  MSIG_REQUIRE(g->r * g->s <= kMaxTaps, "wgrad: too many taps");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  pick_kblock(g->ow, p.PW, p.PH);
+  p.blocks_w = static_cast<int>(ceil_div(g->ow, p.PW));
+  p.blocks_h = static_cast<int>(ceil_div(g->oh, p.PH));
+  p.n_img = g->n;
+  p.taps = g->r * g->s;
+  const int64_t kb_total = int64_t(g->n) * p.blocks_h * p.blocks_w;
+  WgradPlan pl = plan_wgrad(g->k, g->c, p.taps, kb_total);
+  const size_t need = size_t(pl.splits) * size_t(g->k) * p.taps * g->c * sizeof(float);
+  MSIG_REQUIRE(workspace_bytes >= need, "wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
+  p.m_blocks = pl.m_blocks; p.n_blocks = pl.n_blocks; p.splits = pl.splits;
+  p.kb_per_split = pl.kb_per_split; p.kb_total = pl.kb_total;
+  p.out = reinterpret_cast<float*>(workspace);
+  p.o_row = int64_t(p.taps) * g->c; p.o_tap = g->c;
+  p.o_split = int64_t(g->k) * p.taps * g->c;
+  p.alpha = 1.f; p.m_valid = g->k; p.n_valid = g->c;
+  int rc;
+  ActView va{dy, g->k, g->ow, g->oh, g->n, g->k, int64_t(g->ow) * g->k, int64_t(g->oh) * g->ow * g->k};
+  if ((rc = make_act_map(&p.tmA[0], va, p.PW, p.PH)) != MSIG_OK) return rc;
+  for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+  if (g->stride == 1) {
+    ActView vb{x, g->c, g->w, g->h, g->n, g->c, int64_t(g->w) * g->c, int64_t(g->h) * g->w * g->c};
+    if ((rc = make_act_map(&p.tmB[0], vb, p.PW, p.PH)) != MSIG_OK) return rc;
+    for (int i = 1; i < 4; ++i) p.tmB[i] = p.tmB[0];
+    for (int r = 0; r < g->r; ++r)
+      for (int s = 0; s < g->s; ++s) {
+        p.tapA[r * g->s + s] = Tap{0, 0, 0, 0};
+        p.tapB[r * g->s + s] = Tap{int8_t(r - g->pad_t), int8_t(s - g->pad_l), 0, 0};
+      }
+  } else {
+    MSIG_REQUIRE(g->stride == 2 && g->h % 2 == 0 && g->w % 2 == 0, "wgrad: stride-2 needs even dims");
+    for (int ph = 0; ph < 2; ++ph)
+      for (int pw = 0; pw < 2; ++pw) {
+        const __nv_bfloat16* base =
+            reinterpret_cast<const __nv_bfloat16*>(x) + (int64_t(ph) * g->w + pw) * g->c;
+        ActView vb{base, g->c, g->w / 2, g->h / 2, g->n, int64_t(2) * g->c, int64_t(2) * g->w * g->c,
+                   int64_t(g->h) * g->w * g->c};
+        if ((rc = make_act_map(&p.tmB[ph * 2 + pw], vb, p.PW, p.PH)) != MSIG_OK) return rc;
+      }
+    for (int r = 0; r < g->r; ++r)
+      for (int s = 0; s < g->s; ++s) {
+        const int rr = r - g->pad_t, ss = s - g->pad_l;
+        const int ph = ((rr % 2) + 2) % 2, pw = ((ss % 2) + 2) % 2;
+        p.tapA[r * g->s + s] = Tap{0, 0, 0, 0};
+        p.tapB[r * g->s + s] = Tap{int8_t((rr - ph) / 2), int8_t((ss - pw) / 2), int8_t(ph * 2 + pw), 0};
+      }
+  }
+  cudaError_t ce = launch_wgrad(p, pl.block_n, st);
+  if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(ce));
+  msig_wpack_desc d{MSIG_WPACK_FWD, g->k, g->c, g->r, g->s};
+  PackGeom pg = make_pack_geom(&d, 0, 0);
+  return launch_wgrad_reduce(pg, p.out, pl.splits, p.o_split, dw, accumulate, st);
+}
+
+size_t msig_convT2d_wgrad_workspace(const msig_conv_geom* g) {
+  if (!g) return 0;
+  int PW, PH;
+  pick_kblock(g->w, PW, PH);
+  const int64_t kb = int64_t(g->n) * ceil_div(g->h, PH) * ceil_div(g->w, PW);
+  return wgrad_ws_bytes(g->k, g->c, 16, kb);
+}
+
+// dW[ci][co][r][s] = sum x[n, i+dh, j+dw, ci] * dy[n, 2i+py, 2j+px, co] over the 4 phases x 4 taps.
+int msig_convT2d_wgrad(const msig_conv_geom* g, const void* x, const void* dy, float* dw, int accumulate,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  MSIG_REQUIRE(g && x && dy && dw && workspace, "msig_convT2d_wgrad: null argument");
+  MSIG_REQUIRE(context_ready(), "msig_init() has not been called");
+  MSIG_REQUIRE(g->c % 64 == 0 && g->k % 64 == 0, "convT wgrad: c and k must be multiples of 64");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  pick_kblock(g->w, p.PW, p.PH);
+  p.blocks_w = static_cast<int>(ceil_div(g->w, p.PW));
+  p.blocks_h = static_cast<int>(ceil_div(g->h, p.PH));
+  p.n_img = g->n;
+  p.taps = 16;
+  const int64_t kb_total = int64_t(g->n) * p.blocks_h * p.blocks_w;
+  WgradPlan pl = plan_wgrad(g->k, g->c, 16, kb_total);
+  const size_t need = size_t(pl.splits) * size_t(g->k) * 16 * g->c * sizeof(float);
+  MSIG_REQUIRE(workspace_bytes >= need, "convT wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
+  p.m_blocks = pl.m_blocks; p.n_blocks = pl.n_blocks; p.splits = pl.splits;
+  p.kb_per_split = pl.kb_per_split; p.kb_total = pl.kb_total;
+  p.out = reinterpret_cast<float*>(workspace);
+  p.o_row = int64_t(16) * g->c; p.o_tap = g->c;
+  p.o_split = int64_t(g->k) * 16 * g->c;
+  p.alpha = 1.f; p.m_valid = g->k; p.n_valid = g->c;
+  int rc;
+  const int64_t OH = 2 * int64_t(g->h), OW = 2 * int64_t(g->w);
+  for (int py = 0; py < 2; ++py)
+    for (int px = 0; px < 2; ++px) {
+      const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(dy) + (py * OW + px) * g->k;
+      ActView va{base, g->k, g->w, g->h, g->n, int64_t(2) * g->k, 2 * OW * g->k, OH * OW * g->k};
+      if ((rc = make_act_map(&p.tmA[py * 2 + px], va, p.PW, p.PH)) != MSIG_OK) return rc;
+      for (int ty = 0; ty < 2; ++ty)
+        for (int tx = 0; tx < 2; ++tx) {
+          const int T = (py * 2 + px) * 4 + ty * 2 + tx;
+          p.tapA[T] = Tap{0, 0, int8_t(py * 2 + px), 0};
+          p.tapB[T] = Tap{int8_t(ph_d(py, ty)), int8_t(ph_d(px, tx)), 0, 0};
+        }
+    }
+  ActView vb{x, g->c, g->w, g->h, g->n, g->c, int64_t(g->w) * g->c, int64_t(g->h) * g->w * g->c};
+  if ((rc = make_act_map(&p.tmB[0], vb, p.PW, p.PH)) != MSIG_OK) return rc;
+  for (int i = 1; i < 4; ++i) p.tmB[i] = p.tmB[0];
+  cudaError_t ce = launch_wgrad(p, pl.block_n, st);
+  if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "convT wgrad launch: %s", cudaGetErrorString(ce));
+  msig_wpack_desc d{MSIG_WPACK_CONVT_FWD, g->k, g->c, 4, 4};   // master weight [I=c][O=k][4][4]
+  PackGeom pg = make_pack_geom(&d, 0, 0);
+  return launch_wgrad_reduce(pg, p.out, pl.splits, p.o_split, dw, accumulate, st);
+}
+
+// Flat wgrad for gathered-patch GEMMs: a [rows][m] and b [rows][ncols] bf16 row-major,
+// result[m][ncols] = a^T b, un-packed into the master weight layout described by `d`.
+size_t msig_patch_wgrad_workspace(int64_t rows, int32_t m, int32_t ncols) {
+  return wgrad_ws_bytes(m, ncols, 1, ceil_div(rows, 64));
+}
+
+int msig_patch_wgrad_part(const msig_wpack_desc* d, int32_t oc, int32_t o_off, int64_t rows,
+                          const void* a_rows_m, int32_t m, const void* b_rows_n, int32_t ncols, float* dw,
+                          int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  MSIG_REQUIRE(d && a_rows_m && b_rows_n && dw && workspace, "msig_patch_wgrad: null argument");
+  MSIG_REQUIRE(context_ready(), "msig_init() has not been called");
+  MSIG_REQUIRE(m % 64 == 0 && ncols % 64 == 0, "patch wgrad: m (%d) and ncols (%d) must be multiples of 64", m, ncols);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PackGeom pg = make_pack_geom(d, oc, o_off);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.PW = 64; p.PH = 1;
+  p.blocks_w = static_cast<int>(ceil_div(rows, 64));
+  p.blocks_h = 1;
+  p.n_img = 1;
+  p.taps = 1;
+  const int64_t kb_total = p.blocks_w;
+  WgradPlan pl = plan_wgrad(m, ncols, 1, kb_total);
+  const size_t need = size_t(pl.splits) * size_t(m) * ncols * sizeof(float);
+  MSIG_REQUIRE(workspace_bytes >= need, "patch wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
+  p.m_blocks = pl.m_blocks; p.n_blocks = pl.n_blocks; p.splits = pl.splits;
+  p.kb_per_split = pl.kb_per_split; p.kb_total = pl.kb_total;
+  p.out = reinterpret_cast<float*>(workspace);
+  p.o_row = ncols; p.o_tap = 0; p.o_split = int64_t(m) * ncols;
+  p.alpha = 1.f; p.m_valid = m; p.n_valid = ncols;
+  int rc;
+  ActView va{a_rows_m, m, rows, 1, 1, m, int64_t(rows) * m, int64_t(rows) * m};
+  if ((rc = make_act_map(&p.tmA[0], va, 64, 1)) != MSIG_OK) return rc;
+  ActView vb{b_rows_n, ncols, rows, 1, 1, ncols, int64_t(rows) * ncols, int64_t(rows) * ncols};
+  if ((rc = make_act_map(&p.tmB[0], vb, 64, 1)) != MSIG_OK) return rc;
+  for (int i = 1; i < 4; ++i) { p.tmA[i] = p.tmA[0]; p.tmB[i] = p.tmB[0]; }
+  cudaError_t ce = launch_wgrad(p, pl.block_n, st);
+  if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "patch wgrad launch: %s", cudaGetErrorString(ce));
+  // partial layouts: IM2COL [O][Kpad] (a = dy, b = patches); IM2COL_FLIP [Kpad][I] (a = patches, b = x);
+  // FWD with r=s=1 [O][I] (Linear).
+  if (pg.kind == MSIG_WPACK_IM2COL) MSIG_REQUIRE(ncols == pg.Kpad && m >= pg.O, "patch wgrad: IM2COL shape mismatch");
+  if (pg.kind == MSIG_WPACK_IM2COL_FLIP) MSIG_REQUIRE(m >= pg.Kpad - 63 && ncols == pg.I, "patch wgrad: FLIP shape mismatch");
+  if (pg.kind == MSIG_WPACK_FWD) MSIG_REQUIRE(pg.RS == 1 && ncols == pg.I, "patch wgrad: FWD needs r=s=1");
+  return launch_wgrad_reduce(pg, p.out, pl.splits, p.o_split, dw, accumulate, st);
+}
+
+int msig_patch_wgrad(const msig_wpack_desc* d, int64_t rows, const void* a_rows_m, const void* b_rows_n,
+                     float* dw, int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  MSIG_REQUIRE(d, "msig_patch_wgrad: null desc");
+  PackGeom pg = make_pack_geom(d, 0, 0);
+  int m, ncols;
+  if (pg.kind == MSIG_WPACK_IM2COL) { m = static_cast<int>(round_up(pg.O, 64)); ncols = pg.Kpad; }
+  else if (pg.kind == MSIG_WPACK_IM2COL_FLIP) { m = pg.Kpad; ncols = pg.I; }
+  else { m = static_cast<int>(round_up(pg.O, 64)); ncols = pg.I; }
+  return msig_patch_wgrad_part(d, 0, 0, rows, a_rows_m, m, b_rows_n, ncols, dw, accumulate, workspace,
+                               workspace_bytes, stream);
+}
+
+
+// ---------------------------------------------------------------- Gram matrices (losses.py:70-78)
+static WgradPlan plan_gram(int n, int h, int w, int c, int& PW, int& PH) {
+  pick_kblock(w, PW, PH);
+  const int64_t kb = ceil_div(h, PH) * ceil_div(w, PW);
+  return plan_wgrad(n * c, n * c, 1, kb);
+}
+
+size_t msig_gram_workspace(int32_t n, int32_t h, int32_t w, int32_t c) {
+  int PW, PH;
+  WgradPlan pl = plan_gram(n, h, w, c, PW, PH);
+  return pl.splits > 1 ? size_t(pl.splits) * size_t(n) * c * size_t(n) * c * sizeof(float) : 16;
+}
+
+int msig_gram_fwd(const void* f, int32_t n, int32_t h, int32_t w, int32_t c, float* gram, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  MSIG_REQUIRE(f && gram, "msig_gram_fwd: null argument");
+  MSIG_REQUIRE(context_ready(), "msig_init() has not been called");
+  MSIG_REQUIRE(c % 64 == 0, "msig_gram_fwd: channels (%d) must be a multiple of 64", c);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  WgradPlan pl = plan_gram(n, h, w, c, p.PW, p.PH);
+  const int dim = n * c;
+  p.blocks_w = static_cast<int>(ceil_div(w, p.PW));
+  p.blocks_h = static_cast<int>(ceil_div(h, p.PH));
+  p.n_img = n; p.taps = 1; p.fold_img = 1; p.CA = c; p.CB = c;
+  p.m_blocks = pl.m_blocks; p.n_blocks = pl.n_blocks; p.splits = pl.splits;
+  p.kb_per_split = pl.kb_per_split; p.kb_total = pl.kb_total;
+  p.o_row = dim; p.o_tap = 0; p.o_split = int64_t(dim) * dim;
+  p.alpha = 1.f / (float(n) * float(c) * float(h) * float(w));
+  p.m_valid = dim; p.n_valid = dim;
+  if (pl.splits > 1) {
+    MSIG_REQUIRE(workspace && workspace_bytes >= size_t(pl.splits) * dim * size_t(dim) * sizeof(float),
+                 "msig_gram_fwd: workspace too small");
+    p.out = reinterpret_cast<float*>(workspace);
+  } else {
+    p.out = gram;
+  }
+  int rc;
+  ActView v{f, c, w, h, n, c, int64_t(w) * c, int64_t(h) * w * c};
+  if ((rc = make_act_map(&p.tmA[0], v, p.PW, p.PH)) != MSIG_OK) return rc;
+  for (int i = 0; i < 4; ++i) { p.tmA[i] = p.tmA[0]; p.tmB[i] = p.tmA[0]; }
+  cudaError_t ce = launch_wgrad(p, pl.block_n, st);
+  if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "gram launch: %s", cudaGetErrorString(ce));
+  if (pl.splits > 1) {
+    const int64_t numel = int64_t(dim) * dim;
+    sum_splits_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div(numel, 256), 4096)), 256, 0, st>>>(
+        p.out, pl.splits, p.o_split, gram, numel);
+    count_launch(1);
+    MSIG_CHECK_LAUNCH();
+  }
+  return MSIG_OK;
+}
+
+// df[b, p, c] = alpha * sum_{b', c'} ssym[(b,c)][(b',c')] * f[b', p, c']   (+ aux)
+int msig_gram_bwd(const void* f, const void* ssym, int32_t n, int32_t h, int32_t w, int32_t c, float alpha,
+                  const float* gscale, const void* aux, void* df, void* stream) {
+  MSIG_REQUIRE(f && ssym && df, "msig_gram_bwd: null argument");
+  MSIG_REQUIRE(context_ready(), "msig_init() has not been called");
+  MSIG_REQUIRE(c % 64 == 0, "msig_gram_bwd: channels (%d) must be a multiple of 64", c);
+  FpropParams p;
+  init_fprop(p);
+  const int block_n = pick_block_n(c);
+  pick_tile(w, p.TW, p.TH);
+  p.OH = h; p.OW = w;
+  p.tiles_h = static_cast<int>(ceil_div(h, p.TH));
+  p.tiles_w = static_cast<int>(ceil_div(w, p.TW));
+  p.n_img = n;
+  p.n_blocks = c / block_n;
+  p.taps = n;                 // one "tap" per source image
+  p.cblocks = c / 64;
+  p.tap_is_image = 1;
+  p.b_row_per_image = c;
+  int rc;
+  ActView v{f, c, w, h, n, c, int64_t(w) * c, int64_t(h) * w * c};
+  if ((rc = make_act_map(&p.tmA[0], v, p.TW, p.TH)) != MSIG_OK) return rc;
+  for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+  const int64_t dim = int64_t(n) * c;
+  if ((rc = make_w_map(&p.tmB, ssym, dim, dim, block_n)) != MSIG_OK) return rc;
+  msig_epilogue e;
+  memset(&e, 0, sizeof(e));
+  e.alpha = alpha; e.alpha_ptr = gscale; e.aux = aux; e.aux_mode = aux ? MSIG_AUX_ADD : MSIG_AUX_NONE;
+  e.out_layout = MSIG_OUT_BF16_NHWC;
+  const OutView ov = make_out_view(df, MSIG_OUT_BF16_NHWC, h, w, c);
+  if ((rc = fill_epilogue(p, &e, ov, c)) != MSIG_OK) return rc;
+  cudaError_t ce = launch_fprop(p, block_n, sm_count(), static_cast<cudaStream_t>(stream));
+  if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "gram bwd launch: %s", cudaGetErrorString(ce));
+  return MSIG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,511 @@
+// tcgen05 implicit-GEMM kernels for sm_100a.
+//
+//   fprop_kernel<BLOCK_N>: persistent, warp-specialised. Warp 0 = TMA producer, warp 1 = MMA
+//     issuer (one elected lane), warp 2 = TMEM allocator, warps 4..7 = epilogue. The fp32
+//     accumulator (128 pixels x BLOCK_N channels) lives in TMEM and is double buffered so the
+//     epilogue of tile i overlaps the main loop of tile i+1.
+//   wgrad_kernel<BLOCK_N>: one 128 x BLOCK_N output tile per CTA, K = pixels, both operands are
+//     pixel-major NHWC tiles consumed as MN-major UMMA operands; split-K over pixel blocks.
+//
+// Reference ops these replace: every nn.Conv2d / nn.ConvTranspose2d / nn.Linear in
+// /root/reference/model.py:18,45,48,72-75,84,131-141,165,183 and the VGG convs + torch.mm Gram of
+// /root/reference/losses.py:15,76 (forward, dgrad, wgrad).
+#include "igemm.cuh"
+#include "ptx.cuh"
+
+#include <atomic>
+
+namespace msig {
+
+static std::atomic<int> g_launches{0};
+int igemm_kernel_launches() { return g_launches.load(); }
+void count_launch(int n) { g_launches.fetch_add(n); }
+
+constexpr int kTileM = 128;
+constexpr int kBlockK = 64;                     // bf16 elements per K block = one 128 B swizzle row
+constexpr int kABytes = kTileM * kBlockK * 2;   // 16 KiB
+
+template <int BLOCK_N>
+struct FpropCfg {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act, float slope) {
+  if (act == ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == ACT_LRELU) return v > 0.f ? v : v * slope;
+  if (act == ACT_TANH) return tanhf(v);
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// Epilogue for NC accumulator columns of one output pixel (thread-per-row).
+template <int NC>
+__device__ __forceinline__ void fprop_epilogue_chunk(const FpropParams& p, const uint32_t (&r)[NC],
+                                                     int col0, bool row_valid, int64_t out_off,
+                                                     int64_t aux_off, float alpha) {
+  if (!row_valid) return;
+  if (!p.out_f32 && p.o_sc == 1) {
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+    for (int g = 0; g < NC / 8; ++g) {
+      const int c = col0 + 8 * g;
+      if (c + 8 > p.n_valid) continue;
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * g + j]) * alpha;
+      if (p.bias != nullptr) {
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + c));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + c + 4));
+        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+      }
+      if (p.aux_mode != AUX_NONE) {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.aux + aux_off + c));
+        const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(ah[j]);
+          if (p.aux_mode == AUX_ADD) {
+            v[2 * j] += f.x;
+            v[2 * j + 1] += f.y;
+          } else if (p.aux_mode == AUX_RELU_MASK) {
+            v[2 * j] = f.x > 0.f ? v[2 * j] : 0.f;
+            v[2 * j + 1] = f.y > 0.f ? v[2 * j + 1] : 0.f;
+          } else {
+            v[2 * j] = f.x > 0.f ? v[2 * j] : v[2 * j] * p.slope;
+            v[2 * j + 1] = f.y > 0.f ? v[2 * j + 1] : v[2 * j + 1] * p.slope;
+          }
+        }
+      }
+      if (p.act != ACT_NONE) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act, p.slope);
+      }
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]);
+      o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]);
+      o.w = pack_bf16x2(v[6], v[7]);
+      *reinterpret_cast<uint4*>(out + out_off + c) = o;
+    }
+  } else {
+    // generic strided path (fp32 outputs, narrow channel counts)
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const int c = col0 + j;
+      if (c < p.n_valid) {
+        float v = __uint_as_float(r[j]) * alpha;
+        if (p.bias != nullptr) v += __ldg(p.bias + c);
+        v = apply_act(v, p.act, p.slope);
+        if (p.out_f32)
+          reinterpret_cast<float*>(p.out)[out_off + c * p.o_sc] = v;
+        else
+          reinterpret_cast<__nv_bfloat16*>(p.out)[out_off + c * p.o_sc] = __float2bfloat16(v);
+      }
+    }
+  }
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(256, 1) fprop_kernel(const __grid_constant__ FpropParams p) {
+  using Cfg = FpropCfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) prefetch_tmap(&p.tmA[i]);
+    prefetch_tmap(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = p.n_img * p.tiles_h * p.tiles_w * p.phases;
+  const int total = m_tiles * p.n_blocks;
+  const int kblocks = p.taps * p.cblocks;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int n_blk = tile % p.n_blocks;
+        int mt = tile / p.n_blocks;
+        const int ph = mt % p.phases;
+        mt /= p.phases;
+        const int tw = mt % p.tiles_w;
+        mt /= p.tiles_w;
+        const int th = mt % p.tiles_h;
+        const int img = mt / p.tiles_h;
+        const int oh0 = th * p.TH, ow0 = tw * p.TW;
+        const int n_off =
+            n_blk * BLOCK_N + img * p.b_row_per_image + ph * p.b_row_per_phase;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          const int t = kb / p.cblocks;
+          const int cb = kb - t * p.cblocks;
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + stage * Cfg::kStageBytes;
+          uint8_t* sb = sa + kABytes;
+          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (p.tap_is_image) {
+            tma_load_4d(sa, &p.tmA[0], &full_bar[stage], cb * kBlockK, ow0, oh0, t);
+          } else {
+            const Tap tp = p.tap[ph * p.taps + t];
+            tma_load_4d(sa, &p.tmA[tp.map], &full_bar[stage], cb * kBlockK, ow0 + tp.dw,
+                        oh0 + tp.dh, img);
+          }
+          tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * kBlockK, n_off);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t aphase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[as], aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+          const uint32_t sb = sa + kABytes;
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint64_t da = make_smem_desc(sa + k * 32, 0, 1024);
+            const uint64_t db = make_smem_desc(sb + k * 32, 0, 1024);
+            umma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == Cfg::kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tfull_bar[as]);
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int n_blk = tile % p.n_blocks;
+      int mt = tile / p.n_blocks;
+      const int ph = mt % p.phases;
+      mt /= p.phases;
+      const int tw = mt % p.tiles_w;
+      mt /= p.tiles_w;
+      const int th = mt % p.tiles_h;
+      const int img = mt / p.tiles_h;
+      const int oh = th * p.TH + row / p.TW;
+      const int ow = tw * p.TW + row % p.TW;
+      const bool row_valid = (oh < p.OH) && (ow < p.OW);
+      const int64_t out_off = p.o_ph[ph] + img * p.o_sn + oh * p.o_sh + ow * p.o_sw;
+      const int64_t aux_off = p.a_ph[ph] + img * p.a_sn + oh * p.a_sh + ow * p.a_sw;
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
+      if constexpr (BLOCK_N == 16) {
+        uint32_t r[16];
+        tmem_ld_32x16(taddr, r);
+        tmem_ld_wait();
+        fprop_epilogue_chunk<16>(p, r, n_blk * BLOCK_N, row_valid, out_off, aux_off, alpha);
+      } else {
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c, r);
+          tmem_ld_wait();
+          fprop_epilogue_chunk<32>(p, r, n_blk * BLOCK_N + c, row_valid, out_off, aux_off, alpha);
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------ wgrad
+template <int BLOCK_N>
+struct WgradCfg {
+  static constexpr int kABytes = 2 * 8192;                 // 128 channels x 64 pixels
+  static constexpr int kBBytes = (BLOCK_N / 64) * 8192;    // BLOCK_N channels x 64 pixels
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int kTmemCols = BLOCK_N < 32 ? 32 : BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  using Cfg = WgradCfg<BLOCK_N>;
+  const int m_blk = blockIdx.x / p.n_blocks;
+  const int n_blk = blockIdx.x % p.n_blocks;
+  const int tap = blockIdx.y;
+  const int split = blockIdx.z;
+  if (p.upper_only && (n_blk + 1) * BLOCK_N <= m_blk * kTileM) return;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + Cfg::kStages;
+  uint64_t* tfull_bar = empty_bar + Cfg::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) {
+      prefetch_tmap(&p.tmA[i]);
+      prefetch_tmap(&p.tmB[i]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kb0 = split * p.kb_per_split;
+  int kb1 = kb0 + p.kb_per_split;
+  if (kb1 > p.kb_total) kb1 = p.kb_total;
+  const int nk = kb1 > kb0 ? kb1 - kb0 : 0;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const Tap ta = p.tapA[tap];
+      const Tap tb = p.tapB[tap];
+      const int per_img = p.blocks_h * p.blocks_w;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb0 + nk; ++kb) {
+        int img = 0, rem = kb;
+        if (!p.fold_img) {
+          img = kb / per_img;
+          rem = kb - img * per_img;
+        }
+        const int hb = rem / p.blocks_w;
+        const int wb = rem - hb * p.blocks_w;
+        const int oh0 = hb * p.PH, ow0 = wb * p.PW;
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sa = smem + stage * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          int vc = m_blk * kTileM + 64 * i;
+          int n_a = img;
+          if (p.fold_img) {
+            n_a = vc / p.CA;
+            vc -= n_a * p.CA;
+          }
+          tma_load_4d(sa + i * 8192, &p.tmA[ta.map], &full_bar[stage], vc, ow0 + ta.dw,
+                      oh0 + ta.dh, n_a);
+        }
+#pragma unroll
+        for (int i = 0; i < BLOCK_N / 64; ++i) {
+          int vc = n_blk * BLOCK_N + 64 * i;
+          int n_b = img;
+          if (p.fold_img) {
+            n_b = vc / p.CB;
+            vc -= n_b * p.CB;
+          }
+          tma_load_4d(sb + i * 8192, &p.tmB[tb.map], &full_bar[stage], vc, ow0 + tb.dw,
+                      oh0 + tb.dh, n_b);
+        }
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && nk > 0) {
+      const uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 1, 1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // 16 pixel rows (2 swizzle atoms of 8 rows) per MMA
+          const uint64_t da = make_smem_desc(sa + k * 2048, 8192, 1024);
+          const uint64_t db = make_smem_desc(sb + k * 2048, 8192, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int m = m_blk * kTileM + q * 32 + lane;
+    const bool row_valid = m < p.m_valid;
+    float* orow = p.out + split * p.o_split + tap * p.o_tap + static_cast<int64_t>(m) * p.o_row;
+    if (nk > 0) {
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      uint32_t r[32];
+      if (nk > 0) {
+        tmem_ld_32x32(taddr + c, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (row_valid) {
+        const int col0 = n_blk * BLOCK_N + c;
+        if (col0 + 32 <= p.n_valid && (p.o_row & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o;
+            o.x = __uint_as_float(r[j]) * p.alpha;
+            o.y = __uint_as_float(r[j + 1]) * p.alpha;
+            o.z = __uint_as_float(r[j + 2]) * p.alpha;
+            o.w = __uint_as_float(r[j + 3]) * p.alpha;
+            *reinterpret_cast<float4*>(orow + col0 + j) = o;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (col0 + j < p.n_valid) orow[col0 + j] = __uint_as_float(r[j]) * p.alpha;
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------ launch
+template <int BLOCK_N>
+static cudaError_t launch_fprop_t(const FpropParams& p, int num_sms, cudaStream_t stream) {
+  using Cfg = FpropCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fprop_kernel<BLOCK_N>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int total = p.n_img * p.tiles_h * p.tiles_w * p.phases * p.n_blocks;
+  const int grid = total < num_sms ? total : num_sms;
+  if (grid <= 0) return cudaSuccess;
+  fprop_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(p);
+  count_launch(1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fprop(const FpropParams& p, int block_n, int num_sms, cudaStream_t stream) {
+  switch (block_n) {
+    case 16: return launch_fprop_t<16>(p, num_sms, stream);
+    case 64: return launch_fprop_t<64>(p, num_sms, stream);
+    case 128: return launch_fprop_t<128>(p, num_sms, stream);
+    case 256: return launch_fprop_t<256>(p, num_sms, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+template <int BLOCK_N>
+static cudaError_t launch_wgrad_t(const WgradParams& p, cudaStream_t stream) {
+  using Cfg = WgradCfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BLOCK_N>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Cfg::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid(p.m_blocks * p.n_blocks, p.taps, p.splits);
+  wgrad_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(p);
+  count_launch(1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wgrad(const WgradParams& p, int block_n, cudaStream_t stream) {
+  switch (block_n) {
+    case 64: return launch_wgrad_t<64>(p, stream);
+    case 128: return launch_wgrad_t<128>(p, stream);
+    case 256: return launch_wgrad_t<256>(p, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace msig

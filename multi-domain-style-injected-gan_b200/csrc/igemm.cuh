@@ -1,0 +1,80 @@
+// Parameter blocks of the two tcgen05 implicit-GEMM kernels (see igemm.cu).
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+namespace msig {
+
+constexpr int kMaxTaps = 64;
+
+// One filter tap of an implicit GEMM: where the operand tile of this tap sits relative to the
+// output tile (in the coordinates of tensor map `map`).
+struct Tap {
+  int8_t dh, dw, map, pad_;
+};
+
+enum : int32_t { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_TANH = 3 };
+enum : int32_t { AUX_NONE = 0, AUX_ADD = 1, AUX_RELU_MASK = 2, AUX_LRELU_MASK = 3 };
+
+// ---- "fprop" kernel: D[pixels, N] = sum_{tap, c} A[pixel + tap, c] * B[n, (tap, c)]
+// A: bf16 NHWC activations read through 4-D TMA maps (dims C,W,H,N), one 128-pixel x 64-channel
+//    box per K block; out-of-bounds rows/cols are zero-filled by TMA (= zero padding).
+// B: bf16 [N_total][K_total] K-major packed weights (2-D TMA map).
+// Used for: conv forward, conv dgrad, transposed conv (4 output phases), 1x1 / Linear GEMMs,
+// Gram backward (taps = images).
+struct FpropParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB;
+  Tap tap[kMaxTaps];
+  int32_t taps, cblocks;          // K blocks = taps * cblocks, 64 channels each (taps per phase)
+  int32_t phases;                 // 1, or 4 output phases of a stride-2 transposed conv / dgrad:
+                                  //   phase ph uses taps [ph*taps, (ph+1)*taps), B rows offset by
+                                  //   ph*b_row_per_phase and the output / aux view offset o_ph/a_ph
+  int32_t b_row_per_phase;
+  int64_t o_ph[4], a_ph[4];
+  int32_t tap_is_image;           // Gram backward: tap t reads image t (not the tile's image)
+  int32_t b_row_per_image;        // B row offset added per output image (Gram backward)
+  int32_t OH, OW, TH, TW;         // output plane and the 128-pixel tile (TH*TW == 128)
+  int32_t tiles_h, tiles_w, n_img, n_blocks;
+  // epilogue
+  void* out;
+  int64_t o_sn, o_sh, o_sw, o_sc;  // element strides of the output view
+  int32_t out_f32, n_valid;
+  const float* bias;
+  float alpha;
+  const float* alpha_ptr;          // optional device scalar folded into alpha
+  int32_t act;
+  float slope;
+  const __nv_bfloat16* aux;        // channel-contiguous tensor congruent with the output tile
+  int64_t a_sn, a_sh, a_sw;
+  int32_t aux_mode;
+};
+
+// ---- "wgrad" kernel: D[m, n] = sum_{pixels} A[pixel + tapA, m] * B[pixel + tapB, n]
+// Both operands are pixel-major NHWC tiles (MN-major UMMA operands). Used for weight gradients
+// (A = dy, B = x), and for Gram matrices (A = B = features, channels folded with images).
+struct WgradParams {
+  CUtensorMap tmA[4];
+  CUtensorMap tmB[4];
+  Tap tapA[kMaxTaps];
+  Tap tapB[kMaxTaps];
+  int32_t taps;
+  int32_t PW, PH;                  // 64-pixel K block (PW*PH == 64)
+  int32_t blocks_w, blocks_h, n_img;
+  int32_t fold_img;                // 1: "channel" index = img*C + c, K loop stays inside an image
+  int32_t CA, CB;                  // channels per image of A / B (fold_img only)
+  int32_t m_blocks, n_blocks, splits, kb_per_split, kb_total;
+  float* out;                      // fp32 [split][tap][m][n]
+  int64_t o_split, o_tap, o_row;
+  float alpha;
+  int32_t m_valid, n_valid;
+  int32_t upper_only;              // Gram: skip tiles strictly below the diagonal
+};
+
+cudaError_t launch_fprop(const FpropParams& p, int block_n, int num_sms, cudaStream_t stream);
+cudaError_t launch_wgrad(const WgradParams& p, int block_n, cudaStream_t stream);
+int igemm_kernel_launches();  // launches issued since process start (bench: gpu_launches)
+
+}  // namespace msig

@@ -1,0 +1,870 @@
+// Bandwidth-bound kernels: gathered patches for the narrow convs, reflect padding, InstanceNorm /
+// AdaIN statistics + fused apply (+activation, +residual) and their backward, pooling, head
+// selection, dtype converters. All activations are bf16 NHWC, 16-byte vector accesses, one thread
+// per 8 channels, warp-shuffle / shared-memory reductions, fp32 statistics.
+//
+// Reference call sites: model.py:16,20-36 (AdaIN), :53-55 (ReLU, residual), :131-133,139-140,167
+// (InstanceNorm2d + ReLU/LeakyReLU), :76 (AdaptiveAvgPool2d), :112-116,208-212 (head selection),
+// :131,141 (reflect padding); losses.py:49-56 (VGG renorm), pool_2/pool_4 (MaxPool2d).
+#include "common.h"
+
+#include <algorithm>
+
+namespace msig {
+
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __bfloat1622float2(h[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 u;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+__device__ __forceinline__ float act_fwd(float v, int act, float slope) {
+  if (act == MSIG_ACT_RELU) return v > 0.f ? v : 0.f;
+  if (act == MSIG_ACT_LRELU) return v > 0.f ? v : v * slope;
+  return v;
+}
+__device__ __forceinline__ float act_grad(float u, int act, float slope) {
+  if (act == MSIG_ACT_RELU) return u > 0.f ? 1.f : 0.f;
+  if (act == MSIG_ACT_LRELU) return u > 0.f ? 1.f : slope;
+  return 1.f;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * (n - 1) - i;
+  return i;
+}
+
+static inline int grid_for(int64_t work, int threads, int cap = 148 * 16) {
+  return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(work, threads), cap)));
+}
+
+// ---------------------------------------------------------------- gathered patches
+__global__ void patch_gather_kernel(msig_patch_geom g, const float* __restrict__ src,
+                                    const float* __restrict__ scale, const float* __restrict__ shift,
+                                    __nv_bfloat16* __restrict__ out, int64_t groups_total) {
+  const int kg_per_row = g.kpad / 8;
+  const int kvalid = g.r * g.s * g.c;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < groups_total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int kg = static_cast<int>(idx % kg_per_row);
+    int64_t m = idx / kg_per_row;
+    const int ow = static_cast<int>(m % g.ow);
+    m /= g.ow;
+    const int oh = static_cast<int>(m % g.oh);
+    const int n = static_cast<int>(m / g.oh);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = kg * 8 + j;
+      float v = 0.f;
+      if (k < kvalid) {
+        const int t = k / g.c;
+        const int ch = k - t * g.c;
+        const int r = t / g.s;
+        const int s = t - r * g.s;
+        int ih = oh * g.stride + r - g.pad_t;
+        int iw = ow * g.stride + s - g.pad_l;
+        bool ok = true;
+        if (g.reflect) {
+          ih = reflect_idx(ih, g.h);
+          iw = reflect_idx(iw, g.w);
+        } else {
+          ok = (ih >= 0) && (ih < g.h) && (iw >= 0) && (iw < g.w);
+        }
+        if (ok) {
+          v = __ldg(src + ((int64_t(n) * g.c + ch) * g.h + ih) * g.w + iw);
+          if (scale != nullptr) v = v * scale[ch] + shift[ch];
+        }
+      }
+      f[j] = v;
+    }
+    store8(out + idx * 8, f);
+  }
+}
+
+// Adjoint of the gather: one thread per source element.
+__global__ void patch_scatter_kernel(msig_patch_geom g, const __nv_bfloat16* __restrict__ dp,
+                                     const float* __restrict__ scale, float* __restrict__ dsrc,
+                                     int accumulate, int64_t total) {
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int iw = static_cast<int>(idx % g.w);
+    int64_t rem = idx / g.w;
+    const int ih = static_cast<int>(rem % g.h);
+    rem /= g.h;
+    const int ch = static_cast<int>(rem % g.c);
+    const int n = static_cast<int>(rem / g.c);
+    // padded-domain positions that read this element
+    int ph[3], pw[3];
+    int nph = 0, npw = 0;
+    ph[nph++] = ih;
+    pw[npw++] = iw;
+    if (g.reflect) {
+      if (ih >= 1 && ih <= g.pad_t) ph[nph++] = -ih;
+      const int hi_h = 2 * (g.h - 1) - ih;   // mirrored position beyond the bottom edge
+      if (ih <= g.h - 2 && hi_h - (g.h - 1) <= (g.oh - 1) * g.stride + g.r - 1 - g.pad_t - (g.h - 1) &&
+          hi_h >= g.h)
+        ph[nph++] = hi_h;
+      if (iw >= 1 && iw <= g.pad_l) pw[npw++] = -iw;
+      const int hi_w = 2 * (g.w - 1) - iw;
+      if (iw <= g.w - 2 && hi_w - (g.w - 1) <= (g.ow - 1) * g.stride + g.s - 1 - g.pad_l - (g.w - 1) &&
+          hi_w >= g.w)
+        pw[npw++] = hi_w;
+    }
+    float acc = 0.f;
+    for (int a = 0; a < nph; ++a)
+      for (int r = 0; r < g.r; ++r) {
+        const int num_h = ph[a] + g.pad_t - r;
+        if (num_h < 0 || (num_h % g.stride) != 0) continue;
+        const int oh = num_h / g.stride;
+        if (oh >= g.oh) continue;
+        for (int b = 0; b < npw; ++b)
+          for (int s = 0; s < g.s; ++s) {
+            const int num_w = pw[b] + g.pad_l - s;
+            if (num_w < 0 || (num_w % g.stride) != 0) continue;
+            const int ow = num_w / g.stride;
+            if (ow >= g.ow) continue;
+            const int64_t m = (int64_t(n) * g.oh + oh) * g.ow + ow;
+            acc += __bfloat162float(dp[m * g.kpad + (r * g.s + s) * g.c + ch]);
+          }
+      }
+    if (scale != nullptr) acc *= scale[ch];
+    dsrc[idx] = accumulate ? dsrc[idx] + acc : acc;
+  }
+}
+
+// ---------------------------------------------------------------- reflect pad (NHWC bf16)
+__global__ void reflect_pad_fwd_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int c,
+                                       int pad, __nv_bfloat16* __restrict__ y, int64_t groups) {
+  const int cg = c / 8;
+  const int H2 = h + 2 * pad, W2 = w + 2 * pad;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < groups;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int g8 = static_cast<int>(idx % cg);
+    int64_t rem = idx / cg;
+    const int pw = static_cast<int>(rem % W2);
+    rem /= W2;
+    const int ph = static_cast<int>(rem % H2);
+    const int img = static_cast<int>(rem / H2);
+    const int ih = reflect_idx(ph - pad, h), iw = reflect_idx(pw - pad, w);
+    const uint4 v = *reinterpret_cast<const uint4*>(x + ((int64_t(img) * h + ih) * w + iw) * c + g8 * 8);
+    *reinterpret_cast<uint4*>(y + idx * 8) = v;
+  }
+}
+
+__global__ void reflect_pad_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int n, int h, int w, int c,
+                                       int pad, __nv_bfloat16* __restrict__ dx, int64_t groups) {
+  const int cg = c / 8;
+  const int H2 = h + 2 * pad, W2 = w + 2 * pad;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < groups;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int g8 = static_cast<int>(idx % cg);
+    int64_t rem = idx / cg;
+    const int iw = static_cast<int>(rem % w);
+    rem /= w;
+    const int ih = static_cast<int>(rem % h);
+    const int img = static_cast<int>(rem / h);
+    int ph[3], pw[3], nph = 0, npw = 0;
+    ph[nph++] = ih + pad;
+    pw[npw++] = iw + pad;
+    if (ih >= 1 && ih <= pad) ph[nph++] = pad - ih;
+    if (ih <= h - 2 && ih >= h - 1 - pad) ph[nph++] = pad + 2 * (h - 1) - ih;
+    if (iw >= 1 && iw <= pad) pw[npw++] = pad - iw;
+    if (iw <= w - 2 && iw >= w - 1 - pad) pw[npw++] = pad + 2 * (w - 1) - iw;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int a = 0; a < nph; ++a)
+      for (int b = 0; b < npw; ++b) {
+        float f[8];
+        load8(dy + ((int64_t(img) * H2 + ph[a]) * W2 + pw[b]) * c + g8 * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    store8(dx + idx * 8, acc);
+  }
+}
+
+// ---------------------------------------------------------------- per-(n,c) reductions
+// Block = 256 threads = (c/8) channel groups x (2048/c) pixel lanes; grid = (chunks, n).
+// MODE 0: sum x, sum x^2 (statistics)   MODE 1: sum g, sum g*xhat (norm backward), g = dy*act'(u)
+template <int MODE>
+__global__ void __launch_bounds__(256) nc_reduce_kernel(
+    const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
+    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
+    const float* __restrict__ shift, int act, float slope, int hw, int c, int pix_per_block,
+    float* __restrict__ partial) {
+  __shared__ float red[16][256 + 1];
+  const int cg = c / 8;
+  const int lanes = 256 / cg;
+  const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
+  const int img = blockIdx.y, chunk = blockIdx.x;
+  const int p0 = chunk * pix_per_block;
+  const int p1 = min(p0 + pix_per_block, hw);
+  float a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = b[j] = 0.f;
+  float mu[8], rs[8], sc[8], sh[8];
+  if (MODE == 1) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int ch = img * c + tx * 8 + j;
+      mu[j] = mean[ch]; rs[j] = rstd[ch]; sc[j] = scale[ch]; sh[j] = shift[ch];
+    }
+  }
+  const int64_t base = int64_t(img) * hw * c + tx * 8;
+  for (int p = p0 + ty; p < p1; p += lanes) {
+    float xf[8];
+    load8(x + base + int64_t(p) * c, xf);
+    if (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a[j] += xf[j];
+        b[j] += xf[j] * xf[j];
+      }
+    } else {
+      float df[8];
+      load8(dy + base + int64_t(p) * c, df);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float u = xf[j] * sc[j] + sh[j];
+        const float gq = df[j] * act_grad(u, act, slope);
+        a[j] += gq;
+        b[j] += gq * (xf[j] - mu[j]) * rs[j];
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[j][threadIdx.x] = a[j];
+    red[8 + j][threadIdx.x] = b[j];
+  }
+  __syncthreads();
+  // thread t < 2*c : quantity q = t / c (0: a, 1: b), channel ch = t % c
+  for (int t = threadIdx.x; t < 2 * c; t += 256) {
+    const int q = t / c, ch = t % c;
+    const int gx = ch / 8, j = ch % 8;
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[q * 8 + j][l * cg + gx];
+    partial[((int64_t(img) * gridDim.x + chunk) * 2 + q) * c + ch] = s;
+  }
+}
+
+__global__ void in_stats_finalize_kernel(const float* __restrict__ partial, int chunks, int hw, int c,
+                                         float eps, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, int64_t gb_stride,
+                                         float* __restrict__ mean, float* __restrict__ rstd,
+                                         float* __restrict__ scale, float* __restrict__ shift) {
+  const int img = blockIdx.y;
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double s = 0.0, ss = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    s += partial[((int64_t(img) * chunks + k) * 2 + 0) * c + ch];
+    ss += partial[((int64_t(img) * chunks + k) * 2 + 1) * c + ch];
+  }
+  const double m = s / hw;
+  double var = ss / hw - m * m;
+  if (var < 0.0) var = 0.0;
+  const float r = static_cast<float>(1.0 / sqrt(var + double(eps)));
+  const float gm = gamma ? gamma[img * gb_stride + ch] : 1.f;
+  const float bt = beta ? beta[img * gb_stride + ch] : 0.f;
+  const int o = img * c + ch;
+  mean[o] = static_cast<float>(m);
+  rstd[o] = r;
+  scale[o] = gm * r;
+  shift[o] = bt - static_cast<float>(m) * gm * r;
+}
+
+__global__ void norm_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, int hw, int c,
+                                         float* __restrict__ coef, float* __restrict__ dgamma,
+                                         float* __restrict__ dbeta, int64_t dgb_stride, int accumulate) {
+  const int img = blockIdx.y;
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int k = 0; k < chunks; ++k) {
+    s1 += partial[((int64_t(img) * chunks + k) * 2 + 0) * c + ch];
+    s2 += partial[((int64_t(img) * chunks + k) * 2 + 1) * c + ch];
+  }
+  coef[(int64_t(img) * 2 + 0) * c + ch] = static_cast<float>(s1 / hw);
+  coef[(int64_t(img) * 2 + 1) * c + ch] = static_cast<float>(s2 / hw);
+  if (dgamma != nullptr) {
+    const int64_t o = img * dgb_stride + ch;
+    dgamma[o] = (accumulate ? dgamma[o] : 0.f) + static_cast<float>(s2);
+    dbeta[o] = (accumulate ? dbeta[o] : 0.f) + static_cast<float>(s1);
+  }
+}
+
+// y = act(x*scale + shift) (+ residual)
+__global__ void __launch_bounds__(256) norm_act_fwd_kernel(
+    const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
+    const __nv_bfloat16* __restrict__ res, int act, float slope, int hw, int c, int pix_per_block,
+    __nv_bfloat16* __restrict__ y) {
+  const int cg = c / 8;
+  const int lanes = 256 / cg;
+  const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
+  const int img = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(p0 + pix_per_block, hw);
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[img * c + tx * 8 + j];
+    sh[j] = shift[img * c + tx * 8 + j];
+  }
+  const int64_t base = int64_t(img) * hw * c + tx * 8;
+  for (int p = p0 + ty; p < p1; p += lanes) {
+    float f[8];
+    load8(x + base + int64_t(p) * c, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = act_fwd(f[j] * sc[j] + sh[j], act, slope);
+    if (res != nullptr) {
+      float rf[8];
+      load8(res + base + int64_t(p) * c, rf);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += rf[j];
+    }
+    store8(y + base + int64_t(p) * c, f);
+  }
+}
+
+// dx = scale * (g - c1 - xhat*c2),  g = dy*act'(x*scale+shift)
+__global__ void __launch_bounds__(256) norm_act_bwd_kernel(
+    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
+    const float* __restrict__ shift, const float* __restrict__ coef, int act, float slope, int hw, int c,
+    int pix_per_block, __nv_bfloat16* __restrict__ dx) {
+  const int cg = c / 8;
+  const int lanes = 256 / cg;
+  const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
+  const int img = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(p0 + pix_per_block, hw);
+  float mu[8], rs[8], sc[8], sh[8], c1[8], c2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int ch = img * c + tx * 8 + j;
+    mu[j] = mean[ch]; rs[j] = rstd[ch]; sc[j] = scale[ch]; sh[j] = shift[ch];
+    c1[j] = coef[(int64_t(img) * 2 + 0) * c + tx * 8 + j];
+    c2[j] = coef[(int64_t(img) * 2 + 1) * c + tx * 8 + j];
+  }
+  const int64_t base = int64_t(img) * hw * c + tx * 8;
+  for (int p = p0 + ty; p < p1; p += lanes) {
+    float xf[8], df[8];
+    load8(x + base + int64_t(p) * c, xf);
+    load8(dy + base + int64_t(p) * c, df);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float u = xf[j] * sc[j] + sh[j];
+      const float gq = df[j] * act_grad(u, act, slope);
+      const float xh = (xf[j] - mu[j]) * rs[j];
+      df[j] = sc[j] * (gq - c1[j] - xh * c2[j]);
+    }
+    store8(dx + base + int64_t(p) * c, df);
+  }
+}
+
+static int pick_pix_per_block(int n, int hw) {
+  // aim for >= ~4 blocks per SM, at least 64 pixels per block
+  int ppb = 256;
+  while (ppb > 64 && int64_t(n) * ceil_div(hw, ppb) < 148 * 4) ppb /= 2;
+  return std::min(ppb, std::max(hw, 1));
+}
+
+// ---------------------------------------------------------------- simple elementwise kernels
+__global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                               int act, float slope, int64_t groups, __nv_bfloat16* __restrict__ dz) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < groups;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    float a[8], b[8];
+    load8(dy + i * 8, a);
+    load8(y + i * 8, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] *= act_grad(b[j], act, slope);
+    store8(dz + i * 8, a);
+  }
+}
+__global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
+                                int64_t groups, __nv_bfloat16* __restrict__ o) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < groups;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    float x[8], y[8];
+    load8(a + i * 8, x);
+    load8(b + i * 8, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += y[j];
+    store8(o + i * 8, x);
+  }
+}
+__global__ void f32_to_bf16_kernel(const float* __restrict__ x, int64_t n, __nv_bfloat16* __restrict__ y) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    y[i] = __float2bfloat16(x[i]);
+}
+__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, int64_t n, float* __restrict__ y) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    y[i] = __bfloat162float(x[i]);
+}
+__global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int64_t n,
+                                float* __restrict__ dz) {
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
+    dz[i] = dy[i] * (1.f - y[i] * y[i]);
+}
+
+// db[c] (+)= sum_rows dy[rows][c]; block = 256 threads = (c/8 groups) x lanes, atomics on fp32.
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ dy, int64_t rows,
+                                                     int c, int rows_per_block, float* __restrict__ db) {
+  __shared__ float red[8][256 + 1];
+  const int cg = c / 8;
+  const int lanes = 256 / cg;
+  const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
+  const int64_t r0 = int64_t(blockIdx.x) * rows_per_block;
+  const int64_t r1 = min(r0 + rows_per_block, rows);
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (threadIdx.x < cg * lanes) {
+    for (int64_t r = r0 + ty; r < r1; r += lanes) {
+      float f[8];
+      load8(dy + r * c + tx * 8, f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += f[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[j][threadIdx.x] = a[j];
+  __syncthreads();
+  for (int ch = threadIdx.x; ch < c; ch += 256) {
+    const int gx = ch / 8, j = ch % 8;
+    float s = 0.f;
+    for (int l = 0; l < lanes; ++l) s += red[j][l * cg + gx];
+    atomicAdd(db + ch, s);
+  }
+}
+
+__global__ void nchw_chansum_kernel(const float* __restrict__ x, int n, int c, int64_t hw,
+                                    float* __restrict__ out) {
+  // grid (blocks, c): each block reduces a slice of (n, hw) for channel blockIdx.y
+  const int ch = blockIdx.y;
+  const int64_t total = int64_t(n) * hw;
+  float s = 0.f;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int64_t img = i / hw, p = i - img * hw;
+    s += x[(img * c + ch) * hw + p];
+  }
+  s = warp_sum(s);
+  __shared__ float ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) t += ws[i];
+    atomicAdd(out + ch, t);
+  }
+}
+
+// ---------------------------------------------------------------- pooling
+__global__ void maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int c,
+                                    __nv_bfloat16* __restrict__ y, int64_t groups) {
+  const int cg = c / 8, oh = h / 2, ow = w / 2;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < groups;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int g8 = static_cast<int>(idx % cg);
+    int64_t rem = idx / cg;
+    const int x0 = static_cast<int>(rem % ow);
+    rem /= ow;
+    const int y0 = static_cast<int>(rem % oh);
+    const int img = static_cast<int>(rem / oh);
+    const __nv_bfloat16* p = x + ((int64_t(img) * h + 2 * y0) * w + 2 * x0) * c + g8 * 8;
+    float a[8], b[8];
+    load8(p, a);
+    load8(p + c, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], b[j]);
+    load8(p + int64_t(w) * c, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], b[j]);
+    load8(p + int64_t(w) * c + c, b);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], b[j]);
+    store8(y + idx * 8, a);
+  }
+}
+// dx = dy routed to the first max position in window order (torch's tie-break for equal values)
+__global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                                    int n, int h, int w, int c, __nv_bfloat16* __restrict__ dx,
+                                    int64_t groups) {
+  const int cg = c / 8, oh = h / 2, ow = w / 2;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < groups;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int g8 = static_cast<int>(idx % cg);
+    int64_t rem = idx / cg;
+    const int x0 = static_cast<int>(rem % ow);
+    rem /= ow;
+    const int y0 = static_cast<int>(rem % oh);
+    const int img = static_cast<int>(rem / oh);
+    const int64_t off = ((int64_t(img) * h + 2 * y0) * w + 2 * x0) * c + g8 * 8;
+    float v[4][8], d[8], o[4][8];
+    load8(x + off, v[0]);
+    load8(x + off + c, v[1]);
+    load8(x + off + int64_t(w) * c, v[2]);
+    load8(x + off + int64_t(w) * c + c, v[3]);
+    load8(dy + idx * 8, d);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int best = 0;
+      float bv = v[0][j];
+#pragma unroll
+      for (int k = 1; k < 4; ++k)
+        if (v[k][j] > bv) { bv = v[k][j]; best = k; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) o[k][j] = (k == best) ? d[j] : 0.f;
+    }
+    store8(dx + off, o[0]);
+    store8(dx + off + c, o[1]);
+    store8(dx + off + int64_t(w) * c, o[2]);
+    store8(dx + off + int64_t(w) * c + c, o[3]);
+  }
+}
+
+// [n,hw,c] -> [n,c] mean; one block per image, (c/8) x lanes threads
+__global__ void __launch_bounds__(256) avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int hw, int c,
+                                                          __nv_bfloat16* __restrict__ y) {
+  __shared__ float red[8][256 + 1];
+  const int img = blockIdx.x;
+  for (int c0 = 0; c0 < c; c0 += 512) {   // 64 groups of 8 channels per pass
+    const int cw = min(512, c - c0);
+    const int cg = cw / 8, lanes = 256 / cg;
+    const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (threadIdx.x < cg * lanes)
+      for (int p = ty; p < hw; p += lanes) {
+        float f[8];
+        load8(x + (int64_t(img) * hw + p) * c + c0 + tx * 8, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += f[j];
+      }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[j][threadIdx.x] = a[j];
+    __syncthreads();
+    for (int ch = threadIdx.x; ch < cw; ch += 256) {
+      const int gx = ch / 8, j = ch % 8;
+      float s = 0.f;
+      for (int l = 0; l < lanes; ++l) s += red[j][l * cg + gx];
+      y[int64_t(img) * c + c0 + ch] = __float2bfloat16(s / hw);
+    }
+    __syncthreads();
+  }
+}
+__global__ void avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int hw, int c,
+                                   __nv_bfloat16* __restrict__ dx, int64_t groups) {
+  const int cg = c / 8;
+  const float inv = 1.f / hw;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < groups;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int g8 = static_cast<int>(idx % cg);
+    const int64_t img = idx / (int64_t(cg) * hw);
+    float f[8];
+    load8(dy + img * c + g8 * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= inv;
+    store8(dx + idx * 8, f);
+  }
+}
+
+// ---------------------------------------------------------------- head selection
+// head_major = 1: all is [n][heads_ld*per_head], head k occupies [k*per_head, (k+1)*per_head) (SE).
+// head_major = 0: all is [n][pix][heads_ld], head k is channel k of every pixel (D, per_head = 1).
+__global__ void head_gather_kernel(const float* __restrict__ all, const int64_t* __restrict__ idx, int n,
+                                   int pix, int heads_ld, int per_head, int head_major,
+                                   float* __restrict__ out) {
+  const int64_t total = int64_t(n) * pix * per_head;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    const int e = static_cast<int>(i % per_head);
+    const int64_t rem = i / per_head;
+    const int p = static_cast<int>(rem % pix);
+    const int b = static_cast<int>(rem / pix);
+    const int k = idx ? static_cast<int>(idx[b]) : 0;
+    const int64_t src = head_major ? (int64_t(b) * pix + p) * heads_ld * per_head + int64_t(k) * per_head + e
+                                   : (int64_t(b) * pix + p) * heads_ld + k;
+    out[i] = all[src];
+  }
+}
+__global__ void head_scatter_kernel(const float* __restrict__ dout, const int64_t* __restrict__ idx, int n,
+                                    int pix, int heads_ld, int per_head, int head_major,
+                                    float* __restrict__ dall) {
+  const int64_t total = int64_t(n) * pix * heads_ld * per_head;
+  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total;
+       i += int64_t(gridDim.x) * blockDim.x) {
+    int b, p, k, e;
+    if (head_major) {
+      e = static_cast<int>(i % per_head);
+      int64_t rem = i / per_head;
+      k = static_cast<int>(rem % heads_ld);
+      rem /= heads_ld;
+      p = static_cast<int>(rem % pix);
+      b = static_cast<int>(rem / pix);
+    } else {
+      e = 0;
+      k = static_cast<int>(i % heads_ld);
+      const int64_t rem = i / heads_ld;
+      p = static_cast<int>(rem % pix);
+      b = static_cast<int>(rem / pix);
+    }
+    const int sel = idx ? static_cast<int>(idx[b]) : 0;
+    dall[i] = (k == sel) ? dout[(int64_t(b) * pix + p) * per_head + e] : 0.f;
+  }
+}
+
+}  // namespace msig
+
+using namespace msig;
+#define ST(s) static_cast<cudaStream_t>(s)
+#define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
+#define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
+
+extern "C" {
+
+int msig_patch_gather(const msig_patch_geom* g, const float* src, const float* scale, const float* shift,
+                      void* patches, void* stream) {
+  MSIG_REQUIRE(g && src && patches, "msig_patch_gather: null argument");
+  MSIG_REQUIRE(g->kpad % 64 == 0 && g->kpad >= g->r * g->s * g->c, "msig_patch_gather: bad kpad %d", g->kpad);
+  MSIG_REQUIRE((scale == nullptr) == (shift == nullptr), "msig_patch_gather: scale and shift go together");
+  const int64_t groups = int64_t(g->n) * g->oh * g->ow * (g->kpad / 8);
+  patch_gather_kernel<<<grid_for(groups, 256, 148 * 32), 256, 0, ST(stream)>>>(*g, src, scale, shift,
+                                                                              BF(patches), groups);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
+int msig_patch_scatter(const msig_patch_geom* g, const void* dpatches, const float* scale, float* dsrc,
+                       int accumulate, void* stream) {
+  MSIG_REQUIRE(g && dpatches && dsrc, "msig_patch_scatter: null argument");
+  const int64_t total = int64_t(g->n) * g->c * g->h * g->w;
+  patch_scatter_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, ST(stream)>>>(*g, CBF(dpatches), scale, dsrc,
+                                                                              accumulate, total);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
+int msig_reflect_pad_fwd(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad, void* y,
+                         void* stream) {
+  MSIG_REQUIRE(x && y && c % 8 == 0 && pad < h && pad < w, "msig_reflect_pad_fwd: bad argument");
+  const int64_t groups = int64_t(n) * (h + 2 * pad) * (w + 2 * pad) * (c / 8);
+  reflect_pad_fwd_kernel<<<grid_for(groups, 256, 148 * 32), 256, 0, ST(stream)>>>(CBF(x), n, h, w, c, pad,
+                                                                                 BF(y), groups);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+int msig_reflect_pad_bwd(const void* dy, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad, void* dx,
+                         void* stream) {
+  MSIG_REQUIRE(dy && dx && c % 8 == 0 && pad < h && pad < w, "msig_reflect_pad_bwd: bad argument");
+  const int64_t groups = int64_t(n) * h * w * (c / 8);
+  reflect_pad_bwd_kernel<<<grid_for(groups, 256, 148 * 32), 256, 0, ST(stream)>>>(CBF(dy), n, h, w, c, pad,
+                                                                                 BF(dx), groups);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
+static bool norm_c_ok(int c) { return c == 64 || c == 128 || c == 256 || c == 512; }
+
+size_t msig_in_stats_workspace(int32_t n, int32_t hw, int32_t c) {
+  const int ppb = pick_pix_per_block(n, hw);
+  const size_t chunks = static_cast<size_t>(ceil_div(hw, ppb));
+  return (size_t(n) * chunks * 2 * c + size_t(n) * 2 * c) * sizeof(float);
+}
+
+int msig_in_stats(const void* x, int32_t n, int32_t hw, int32_t c, float eps, const float* gamma,
+                  const float* beta, int64_t gb_stride, float* mean, float* rstd, float* scale, float* shift,
+                  void* workspace, size_t workspace_bytes, void* stream) {
+  MSIG_REQUIRE(x && mean && rstd && scale && shift && workspace, "msig_in_stats: null argument");
+  MSIG_REQUIRE(norm_c_ok(c), "msig_in_stats: channels %d unsupported (64/128/256/512)", c);
+  MSIG_REQUIRE(workspace_bytes >= msig_in_stats_workspace(n, hw, c), "msig_in_stats: workspace too small");
+  const int ppb = pick_pix_per_block(n, hw);
+  const int chunks = static_cast<int>(ceil_div(hw, ppb));
+  float* partial = reinterpret_cast<float*>(workspace);
+  nc_reduce_kernel<0><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), nullptr, nullptr, nullptr, nullptr,
+                                                              nullptr, 0, 0.f, hw, c, ppb, partial);
+  MSIG_CHECK_LAUNCH();
+  in_stats_finalize_kernel<<<dim3(static_cast<unsigned>(ceil_div(c, 128)), n), 128, 0, ST(stream)>>>(
+      partial, chunks, hw, c, eps, gamma, beta, gb_stride, mean, rstd, scale, shift);
+  count_launch(2);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
+int msig_norm_act_fwd(const void* x, const float* scale, const float* shift, const void* residual, int32_t act,
+                      float slope, int32_t n, int32_t hw, int32_t c, void* y, void* stream) {
+  MSIG_REQUIRE(x && scale && shift && y, "msig_norm_act_fwd: null argument");
+  MSIG_REQUIRE(norm_c_ok(c), "msig_norm_act_fwd: channels %d unsupported", c);
+  const int ppb = pick_pix_per_block(n, hw);
+  const int chunks = static_cast<int>(ceil_div(hw, ppb));
+  norm_act_fwd_kernel<<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), scale, shift, CBF(residual), act, slope,
+                                                              hw, c, ppb, BF(y));
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
+int msig_norm_act_bwd(const void* dy, const void* x, const float* mean, const float* rstd, const float* scale,
+                      const float* shift, const float* gamma, int64_t gb_stride, int32_t act, float slope,
+                      int32_t n, int32_t hw, int32_t c, void* dx, float* dgamma, float* dbeta,
+                      int64_t dgb_stride, int accumulate_dgb, void* workspace, size_t workspace_bytes,
+                      void* stream) {
+  (void)gamma; (void)gb_stride;   // gamma*rstd is already folded into `scale`
+  MSIG_REQUIRE(dy && x && mean && rstd && scale && shift && dx && workspace, "msig_norm_act_bwd: null argument");
+  MSIG_REQUIRE(norm_c_ok(c), "msig_norm_act_bwd: channels %d unsupported", c);
+  MSIG_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "msig_norm_act_bwd: dgamma/dbeta go together");
+  MSIG_REQUIRE(workspace_bytes >= msig_in_stats_workspace(n, hw, c), "msig_norm_act_bwd: workspace too small");
+  const int ppb = pick_pix_per_block(n, hw);
+  const int chunks = static_cast<int>(ceil_div(hw, ppb));
+  float* partial = reinterpret_cast<float*>(workspace);
+  float* coef = partial + size_t(n) * chunks * 2 * c;
+  nc_reduce_kernel<1><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), CBF(dy), mean, rstd, scale, shift, act,
+                                                              slope, hw, c, ppb, partial);
+  MSIG_CHECK_LAUNCH();
+  norm_bwd_finalize_kernel<<<dim3(static_cast<unsigned>(ceil_div(c, 128)), n), 128, 0, ST(stream)>>>(
+      partial, chunks, hw, c, coef, dgamma, dbeta, dgb_stride, accumulate_dgb);
+  MSIG_CHECK_LAUNCH();
+  norm_act_bwd_kernel<<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(dy), CBF(x), mean, rstd, scale, shift, coef,
+                                                              act, slope, hw, c, ppb, BF(dx));
+  count_launch(3);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
+int msig_act_bwd(const void* dy, const void* y, int32_t act, float slope, int64_t numel, void* dz, void* stream) {
+  MSIG_REQUIRE(dy && y && dz && numel % 8 == 0, "msig_act_bwd: bad argument");
+  act_bwd_kernel<<<grid_for(numel / 8, 256), 256, 0, ST(stream)>>>(CBF(dy), CBF(y), act, slope, numel / 8, BF(dz));
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+int msig_add_bf16(const void* a, const void* b, int64_t numel, void* out, void* stream) {
+  MSIG_REQUIRE(a && b && out && numel % 8 == 0, "msig_add_bf16: bad argument");
+  add_bf16_kernel<<<grid_for(numel / 8, 256), 256, 0, ST(stream)>>>(CBF(a), CBF(b), numel / 8, BF(out));
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+int msig_colsum(const void* dy, int64_t rows, int32_t c, float* db, int accumulate, void* stream) {
+  MSIG_REQUIRE(dy && db && c % 8 == 0 && c <= 2048 && (256 % (c / 8) == 0 || c / 8 > 256 || true),
+               "msig_colsum: bad argument");
+  MSIG_REQUIRE(c / 8 <= 256, "msig_colsum: c too large");
+  if (!accumulate) MSIG_CHECK_CUDA(cudaMemsetAsync(db, 0, size_t(c) * sizeof(float), ST(stream)));
+  const int rpb = 512;
+  const int blocks = static_cast<int>(ceil_div(rows, rpb));
+  colsum_kernel<<<std::max(blocks, 1), 256, 0, ST(stream)>>>(CBF(dy), rows, c, rpb, db);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+int msig_nchw_chansum(const float* x, int32_t n, int32_t c, int64_t hw, float* out, int accumulate, void* stream) {
+  MSIG_REQUIRE(x && out, "msig_nchw_chansum: null argument");
+  if (!accumulate) MSIG_CHECK_CUDA(cudaMemsetAsync(out, 0, size_t(c) * sizeof(float), ST(stream)));
+  const int blocks = grid_for(int64_t(n) * hw, 256, 256);
+  nchw_chansum_kernel<<<dim3(blocks, c), 256, 0, ST(stream)>>>(x, n, c, hw, out);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
+int msig_maxpool2_fwd(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* y, void* stream) {
+  MSIG_REQUIRE(x && y && h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "msig_maxpool2_fwd: bad argument");
+  const int64_t groups = int64_t(n) * (h / 2) * (w / 2) * (c / 8);
+  maxpool2_fwd_kernel<<<grid_for(groups, 256, 148 * 32), 256, 0, ST(stream)>>>(CBF(x), n, h, w, c, BF(y), groups);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+int msig_maxpool2_bwd(const void* dy, const void* x, const void* y, int32_t n, int32_t h, int32_t w, int32_t c,
+                      void* dx, void* stream) {
+  (void)y;
+  MSIG_REQUIRE(dy && x && dx && h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "msig_maxpool2_bwd: bad argument");
+  const int64_t groups = int64_t(n) * (h / 2) * (w / 2) * (c / 8);
+  maxpool2_bwd_kernel<<<grid_for(groups, 256, 148 * 32), 256, 0, ST(stream)>>>(CBF(dy), CBF(x), n, h, w, c, BF(dx),
+                                                                              groups);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+int msig_avgpool_fwd(const void* x, int32_t n, int32_t hw, int32_t c, void* y, void* stream) {
+  MSIG_REQUIRE(x && y && c % 64 == 0, "msig_avgpool_fwd: bad argument");
+  avgpool_fwd_kernel<<<n, 256, 0, ST(stream)>>>(CBF(x), hw, c, BF(y));
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+int msig_avgpool_bwd(const void* dy, int32_t n, int32_t hw, int32_t c, void* dx, void* stream) {
+  MSIG_REQUIRE(dy && dx && c % 8 == 0, "msig_avgpool_bwd: bad argument");
+  const int64_t groups = int64_t(n) * hw * (c / 8);
+  avgpool_bwd_kernel<<<grid_for(groups, 256), 256, 0, ST(stream)>>>(CBF(dy), hw, c, BF(dx), groups);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
+int msig_head_gather(const float* all, const int64_t* idx, int32_t n, int32_t pix, int32_t heads_ld,
+                     int32_t per_head, int32_t head_major, float* out, void* stream) {
+  MSIG_REQUIRE(all && out, "msig_head_gather: null argument");
+  const int64_t total = int64_t(n) * pix * per_head;
+  head_gather_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(all, idx, n, pix, heads_ld, per_head, head_major, out);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+int msig_head_scatter(const float* dout, const int64_t* idx, int32_t n, int32_t pix, int32_t heads_ld,
+                      int32_t per_head, int32_t head_major, float* dall, void* stream) {
+  MSIG_REQUIRE(dout && dall, "msig_head_scatter: null argument");
+  const int64_t total = int64_t(n) * pix * heads_ld * per_head;
+  head_scatter_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(dout, idx, n, pix, heads_ld, per_head, head_major, dall);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
+int msig_f32_to_bf16(const float* x, int64_t numel, void* y, void* stream) {
+  MSIG_REQUIRE(x && y, "msig_f32_to_bf16: null argument");
+  f32_to_bf16_kernel<<<grid_for(numel, 256), 256, 0, ST(stream)>>>(x, numel, BF(y));
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+int msig_bf16_to_f32(const void* x, int64_t numel, float* y, void* stream) {
+  MSIG_REQUIRE(x && y, "msig_bf16_to_f32: null argument");
+  bf16_to_f32_kernel<<<grid_for(numel, 256), 256, 0, ST(stream)>>>(CBF(x), numel, y);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+int msig_tanh_bwd(const float* dy, const float* y, int64_t numel, float* dz, void* stream) {
+  MSIG_REQUIRE(dy && y && dz, "msig_tanh_bwd: null argument");
+  tanh_bwd_kernel<<<grid_for(numel, 256), 256, 0, ST(stream)>>>(dy, y, numel, dz);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,386 @@
+"""Tensor-level wrappers over the C ABI (lib.py). torch provides device memory and the current
+stream; all arithmetic happens in libmsig.so. Activations are bf16 tensors shaped [n, h, w, c]
+(NHWC, contiguous)."""
+import ctypes
+
+import torch
+
+from . import lib as L
+from .lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, AUX_ADD, AUX_LRELU_MASK, AUX_NONE,
+                  AUX_RELU_MASK, OUT_BF16_NHWC, OUT_F32_NCHW, OUT_F32_NHWC, ConvGeom, Epilogue,
+                  PatchGeom, WpackDesc)
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def ensure_init(device=None):
+    if device is None:
+        device = torch.cuda.current_device()
+    elif isinstance(device, torch.device):
+        device = device.index if device.index is not None else torch.cuda.current_device()
+    return L.init(int(device))
+
+
+_ws_cache = {}
+
+
+def workspace(nbytes, device):
+    """Grow-only scratch buffer per (device, stream); stream-ordered reuse is safe because every
+    consumer of the scratch runs on the same stream as its producer."""
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+def conv_geom(n, h, w, c, k, r, s, stride, pad_t, pad_l, oh, ow):
+    return ConvGeom(n, h, w, c, k, r, s, stride, pad_t, pad_l, oh, ow)
+
+
+def epilogue(bias=None, aux=None, aux_mode=AUX_NONE, act=ACT_NONE, alpha=1.0, alpha_ptr=None,
+             slope=0.2, out_layout=OUT_BF16_NHWC):
+    return Epilogue(_p(bias), _p(aux), aux_mode if aux is not None else AUX_NONE, act, alpha,
+                    _p(alpha_ptr), slope, out_layout)
+
+
+# ------------------------------------------------------------------ weights
+def pad_rows(k):
+    return 16 if k <= 16 else (k + 63) // 64 * 64
+
+
+def wpack(kind, w, o, i, r, s, out=None, oc=0, o_off=0):
+    """Pack an fp32 master weight (reference layout) into the bf16 matrix the kernels read."""
+    d = WpackDesc(kind, o, i, r, s)
+    if out is None:
+        n = L.load().msig_wpack_part_elems(ctypes.byref(d), oc)
+        out = torch.zeros(n, dtype=BF16, device=w.device)
+    L.call("msig_wpack_part", ctypes.byref(d), oc, o_off, _p(w), _p(out), _stream())
+    return out
+
+
+# ------------------------------------------------------------------ convolutions
+def conv2d_fwd(x, wpk, g, e=None, out=None):
+    e = e or epilogue()
+    if out is None:
+        if e.out_layout == OUT_F32_NCHW:
+            out = torch.empty((g.n, g.k, g.oh, g.ow), dtype=F32, device=x.device)
+        elif e.out_layout == OUT_F32_NHWC:
+            out = torch.empty((g.n, g.oh, g.ow, g.k), dtype=F32, device=x.device)
+        else:
+            out = torch.empty((g.n, g.oh, g.ow, g.k), dtype=BF16, device=x.device)
+    L.call("msig_conv2d_fwd", ctypes.byref(g), _p(x), _p(wpk), ctypes.byref(e), _p(out), _stream())
+    return out
+
+
+def conv2d_dgrad(dy, wpk, g, e=None, out=None):
+    e = e or epilogue()
+    if out is None:
+        out = torch.empty((g.n, g.h, g.w, g.c), dtype=BF16, device=dy.device)
+    L.call("msig_conv2d_dgrad", ctypes.byref(g), _p(dy), _p(wpk), ctypes.byref(e), _p(out), _stream())
+    return out
+
+
+def conv2d_wgrad(x, dy, g, dw, accumulate=True):
+    nbytes = L.load().msig_conv2d_wgrad_workspace(ctypes.byref(g))
+    ws = workspace(nbytes, x.device)
+    L.call("msig_conv2d_wgrad", ctypes.byref(g), _p(x), _p(dy), _p(dw), int(accumulate), _p(ws),
+           ws.numel(), _stream())
+
+
+def convT2d_fwd(x, wpk, g, e=None, out=None):
+    e = e or epilogue()
+    if out is None:
+        out = torch.empty((g.n, g.oh, g.ow, g.k), dtype=BF16, device=x.device)
+    L.call("msig_convT2d_fwd", ctypes.byref(g), _p(x), _p(wpk), ctypes.byref(e), _p(out), _stream())
+    return out
+
+
+def convT2d_dgrad(dy, wpk, g, e=None, out=None):
+    e = e or epilogue()
+    if out is None:
+        out = torch.empty((g.n, g.h, g.w, g.c), dtype=BF16, device=dy.device)
+    L.call("msig_convT2d_dgrad", ctypes.byref(g), _p(dy), _p(wpk), ctypes.byref(e), _p(out), _stream())
+    return out
+
+
+def convT2d_wgrad(x, dy, g, dw, accumulate=True):
+    nbytes = L.load().msig_convT2d_wgrad_workspace(ctypes.byref(g))
+    ws = workspace(nbytes, x.device)
+    L.call("msig_convT2d_wgrad", ctypes.byref(g), _p(x), _p(dy), _p(dw), int(accumulate), _p(ws),
+           ws.numel(), _stream())
+
+
+def gemm_geom(rows, k_in, n_out):
+    """A [rows, k_in] x packed [n_out, k_in]^T GEMM expressed as a 1x1 conv on a [1,1,rows,k_in] view."""
+    return ConvGeom(1, 1, rows, k_in, n_out, 1, 1, 1, 0, 0, 1, rows)
+
+
+# ------------------------------------------------------------------ gathered patches
+def patch_geom(n, c, h, w, r, s, stride, pad_t, pad_l, oh, ow, reflect):
+    kpad = (r * s * c + 63) // 64 * 64
+    return PatchGeom(n, c, h, w, r, s, stride, pad_t, pad_l, oh, ow, int(reflect), kpad)
+
+
+def patch_gather(src, pg, scale=None, shift=None, out=None):
+    if out is None:
+        out = torch.empty((pg.n * pg.oh * pg.ow, pg.kpad), dtype=BF16, device=src.device)
+    L.call("msig_patch_gather", ctypes.byref(pg), _p(src), _p(scale), _p(shift), _p(out), _stream())
+    return out
+
+
+def patch_scatter(dpatches, pg, scale=None, out=None, accumulate=False):
+    if out is None:
+        out = torch.empty((pg.n, pg.c, pg.h, pg.w), dtype=F32, device=dpatches.device)
+    L.call("msig_patch_scatter", ctypes.byref(pg), _p(dpatches), _p(scale), _p(out), int(accumulate),
+           _stream())
+    return out
+
+
+def patch_wgrad(kind, o, i, r, s, rows, a, m, b, ncols, dw, accumulate=True, oc=0, o_off=0):
+    d = WpackDesc(kind, o, i, r, s)
+    nbytes = L.load().msig_patch_wgrad_workspace(rows, m, ncols)
+    ws = workspace(nbytes, a.device)
+    L.call("msig_patch_wgrad_part", ctypes.byref(d), oc, o_off, rows, _p(a), m, _p(b), ncols, _p(dw),
+           int(accumulate), _p(ws), ws.numel(), _stream())
+
+
+def reflect_pad_fwd(x, pad):
+    n, h, w, c = x.shape
+    y = torch.empty((n, h + 2 * pad, w + 2 * pad, c), dtype=BF16, device=x.device)
+    L.call("msig_reflect_pad_fwd", _p(x), n, h, w, c, pad, _p(y), _stream())
+    return y
+
+
+def reflect_pad_bwd(dy, pad):
+    n, h2, w2, c = dy.shape
+    h, w = h2 - 2 * pad, w2 - 2 * pad
+    dx = torch.empty((n, h, w, c), dtype=BF16, device=dy.device)
+    L.call("msig_reflect_pad_bwd", _p(dy), n, h, w, c, pad, _p(dx), _stream())
+    return dx
+
+
+# ------------------------------------------------------------------ InstanceNorm / AdaIN
+class NormStats:
+    """mean / rstd / scale / shift, each fp32 [n, c] (one allocation)."""
+    __slots__ = ("buf", "mean", "rstd", "scale", "shift")
+
+    def __init__(self, n, c, device):
+        self.buf = torch.empty((4, n, c), dtype=F32, device=device)
+        self.mean, self.rstd, self.scale, self.shift = self.buf[0], self.buf[1], self.buf[2], self.buf[3]
+
+
+def in_stats(x, gamma=None, beta=None, gb_stride=0, eps=1e-5):
+    n, h, w, c = x.shape
+    st = NormStats(n, c, x.device)
+    nbytes = L.load().msig_in_stats_workspace(n, h * w, c)
+    ws = workspace(nbytes, x.device)
+    L.call("msig_in_stats", _p(x), n, h * w, c, eps, _p(gamma), _p(beta), gb_stride, _p(st.mean),
+           _p(st.rstd), _p(st.scale), _p(st.shift), _p(ws), ws.numel(), _stream())
+    return st
+
+
+def norm_act_fwd(x, st, act=ACT_NONE, residual=None, slope=0.2, out=None):
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    L.call("msig_norm_act_fwd", _p(x), _p(st.scale), _p(st.shift), _p(residual), act, slope, n, h * w, c,
+           _p(out), _stream())
+    return out
+
+
+def norm_act_bwd(dy, x, st, act=ACT_NONE, slope=0.2, dgamma=None, dbeta=None, dgb_stride=0,
+                 accumulate_dgb=False, out=None):
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    nbytes = L.load().msig_in_stats_workspace(n, h * w, c)
+    ws = workspace(nbytes, x.device)
+    L.call("msig_norm_act_bwd", _p(dy), _p(x), _p(st.mean), _p(st.rstd), _p(st.scale), _p(st.shift),
+           None, 0, act, slope, n, h * w, c, _p(out), _p(dgamma), _p(dbeta), dgb_stride,
+           int(accumulate_dgb), _p(ws), ws.numel(), _stream())
+    return out
+
+
+# ------------------------------------------------------------------ small ops
+def act_bwd(dy, y, act, slope=0.2, out=None):
+    if out is None:
+        out = torch.empty_like(dy)
+    L.call("msig_act_bwd", _p(dy), _p(y), act, slope, dy.numel(), _p(out), _stream())
+    return out
+
+
+def add_bf16(a, b, out=None):
+    if out is None:
+        out = torch.empty_like(a)
+    L.call("msig_add_bf16", _p(a), _p(b), a.numel(), _p(out), _stream())
+    return out
+
+
+def colsum(dy2d_rows, c, db, accumulate=True, rows=None):
+    rows = dy2d_rows.numel() // c if rows is None else rows
+    L.call("msig_colsum", _p(dy2d_rows), rows, c, _p(db), int(accumulate), _stream())
+
+
+def colsum_f32(x, rows, c, out, accumulate=True):
+    L.call("msig_colsum_f32", _p(x), rows, c, _p(out), int(accumulate), _stream())
+
+
+def nchw_chansum(x, out, accumulate=True):
+    n, c, h, w = x.shape
+    L.call("msig_nchw_chansum", _p(x), n, c, h * w, _p(out), int(accumulate), _stream())
+
+
+def maxpool2_fwd(x):
+    n, h, w, c = x.shape
+    y = torch.empty((n, h // 2, w // 2, c), dtype=BF16, device=x.device)
+    L.call("msig_maxpool2_fwd", _p(x), n, h, w, c, _p(y), _stream())
+    return y
+
+
+def maxpool2_bwd(dy, x):
+    n, h, w, c = x.shape
+    dx = torch.empty_like(x)
+    L.call("msig_maxpool2_bwd", _p(dy), _p(x), None, n, h, w, c, _p(dx), _stream())
+    return dx
+
+
+def avgpool_fwd(x):
+    n, h, w, c = x.shape
+    y = torch.empty((n, c), dtype=BF16, device=x.device)
+    L.call("msig_avgpool_fwd", _p(x), n, h * w, c, _p(y), _stream())
+    return y
+
+
+def avgpool_bwd(dy, h, w):
+    n, c = dy.shape
+    dx = torch.empty((n, h, w, c), dtype=BF16, device=dy.device)
+    L.call("msig_avgpool_bwd", _p(dy), n, h * w, c, _p(dx), _stream())
+    return dx
+
+
+def head_gather(all_, idx, n, pix, heads_ld, per_head, head_major):
+    out = torch.empty((n, pix * per_head), dtype=F32, device=all_.device)
+    L.call("msig_head_gather", _p(all_), _p(idx), n, pix, heads_ld, per_head, int(head_major), _p(out),
+           _stream())
+    return out
+
+
+def head_scatter(dout, idx, n, pix, heads_ld, per_head, head_major):
+    dall = torch.empty((n, pix * heads_ld * per_head), dtype=F32, device=dout.device)
+    L.call("msig_head_scatter", _p(dout), _p(idx), n, pix, heads_ld, per_head, int(head_major), _p(dall),
+           _stream())
+    return dall
+
+
+def to_bf16(x, out=None):
+    if out is None:
+        out = torch.empty(x.shape, dtype=BF16, device=x.device)
+    L.call("msig_f32_to_bf16", _p(x), x.numel(), _p(out), _stream())
+    return out
+
+
+def to_f32(x, out=None):
+    if out is None:
+        out = torch.empty(x.shape, dtype=F32, device=x.device)
+    L.call("msig_bf16_to_f32", _p(x), x.numel(), _p(out), _stream())
+    return out
+
+
+def tanh_bwd(dy, y):
+    dz = torch.empty_like(dy)
+    L.call("msig_tanh_bwd", _p(dy), _p(y), dy.numel(), _p(dz), _stream())
+    return dz
+
+
+# ------------------------------------------------------------------ losses
+def _scalar(device):
+    return torch.empty((), dtype=F32, device=device)
+
+
+def l1_loss_f32_fwd(a, b):
+    loss = _scalar(a.device)
+    L.call("msig_l1_loss_f32_fwd", _p(a), _p(b), a.numel(), _p(loss), _stream())
+    return loss
+
+
+def l1_loss_f32_bwd(a, b, gscale):
+    g = torch.empty_like(a)
+    L.call("msig_l1_loss_f32_bwd", _p(a), _p(b), a.numel(), _p(gscale), _p(g), _stream())
+    return g
+
+
+def l1_loss_bf16_fwd(a, b):
+    loss = _scalar(a.device)
+    L.call("msig_l1_loss_bf16_fwd", _p(a), _p(b), a.numel(), _p(loss), _stream())
+    return loss
+
+
+def l1_loss_bf16_bwd(a, b, gscale, aux=None):
+    g = torch.empty_like(a)
+    L.call("msig_l1_loss_bf16_bwd", _p(a), _p(b), a.numel(), _p(gscale), _p(aux), _p(g), _stream())
+    return g
+
+
+def mse_const_fwd(a, target):
+    loss = _scalar(a.device)
+    L.call("msig_mse_const_fwd", _p(a), float(target), a.numel(), _p(loss), _stream())
+    return loss
+
+
+def mse_const_bwd(a, target, gscale):
+    g = torch.empty_like(a)
+    L.call("msig_mse_const_bwd", _p(a), float(target), a.numel(), _p(gscale), _p(g), _stream())
+    return g
+
+
+def gram_fwd(f):
+    n, h, w, c = f.shape
+    dim = n * c
+    gram = torch.empty((dim, dim), dtype=F32, device=f.device)
+    nbytes = L.load().msig_gram_workspace(n, h, w, c)
+    ws = workspace(nbytes, f.device)
+    L.call("msig_gram_fwd", _p(f), n, h, w, c, _p(gram), _p(ws), ws.numel(), _stream())
+    return gram
+
+
+def gram_l1(ga, gb):
+    dim = ga.shape[0]
+    loss = _scalar(ga.device)
+    ssym = torch.empty((dim, dim), dtype=BF16, device=ga.device)
+    L.call("msig_gram_l1", _p(ga), _p(gb), dim, _p(loss), _p(ssym), _stream())
+    return loss, ssym
+
+
+def gram_bwd(f, ssym, alpha, gscale=None, aux=None):
+    n, h, w, c = f.shape
+    df = torch.empty_like(f)
+    L.call("msig_gram_bwd", _p(f), _p(ssym), n, h, w, c, float(alpha), _p(gscale), _p(aux), _p(df),
+           _stream())
+    return df
+
+
+# ------------------------------------------------------------------ optimizer
+def sumsq(x, out, accumulate=False):
+    L.call("msig_sumsq", _p(x), x.numel(), _p(out), int(accumulate), _stream())
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, ema, grad_sumsq, max_norm, grad_scale, lr, beta1, beta2,
+              eps, step, ema_beta):
+    L.call("msig_adam_step", _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(ema), param.numel(),
+           _p(grad_sumsq), float(max_norm), float(grad_scale), float(lr), float(beta1), float(beta2),
+           float(eps), int(step), float(ema_beta), _stream())
+
+
+def kernel_launches():
+    return int(L.load().msig_kernel_launches())

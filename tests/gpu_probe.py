@@ -1,0 +1,54 @@
+"""Stand-alone GPU probe: runs every igemm parity case in its own subprocess (a device trap in one
+case must not poison the others) and writes one JSON line per case to gpurun_out/probe.jsonl.
+
+    python tests/gpu_probe.py [case_substring ...]
+"""
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def run_one(name):
+    import torch  # noqa: F401
+    import igemm_cases as C
+    t0 = time.time()
+    err, tol = C.CASES[name]()
+    print(json.dumps({"case": name, "err": err, "tol": tol, "ok": bool(err <= tol), "s": round(time.time() - t0, 2)}))
+
+
+def main():
+    if len(sys.argv) >= 3 and sys.argv[1] == "--one":
+        run_one(sys.argv[2])
+        return
+    import igemm_cases as C
+    pats = sys.argv[1:]
+    names = [n for n in C.CASES if not pats or any(p in n for p in pats)]
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    out = open(os.path.join(ROOT, "gpurun_out", "probe.jsonl"), "a")
+    nfail = 0
+    for n in names:
+        try:
+            r = subprocess.run([sys.executable, __file__, "--one", n], capture_output=True, text=True, timeout=180)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            if r.returncode == 0 and line:
+                rec = json.loads(line[-1])
+            else:
+                rec = {"case": n, "ok": False, "rc": r.returncode, "stderr": r.stderr[-600:]}
+        except subprocess.TimeoutExpired:
+            rec = {"case": n, "ok": False, "timeout": True}
+        nfail += 0 if rec.get("ok") else 1
+        print(json.dumps(rec), flush=True)
+        out.write(json.dumps(rec) + "\n")
+        out.flush()
+    print(f"probe: {len(names) - nfail}/{len(names)} ok")
+    sys.exit(1 if nfail else 0)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,182 @@
+"""Parity cases for the tcgen05 implicit-GEMM entry points, shared by pytest (-m gpu) and the
+stand-alone probe (tests/gpu_probe.py). Each case compares the C-ABI result with a plain
+PyTorch fp32 computation of the same op on the same bf16-rounded operands (so the only
+differences are fp32 accumulation order and the final bf16 rounding).
+
+Tolerance (stated): max|a-b| / max|b| <= 1e-2 for bf16 outputs, <= 2e-3 for fp32 outputs.
+"""
+import torch
+import torch.nn.functional as F
+
+import msig_b200  # noqa: F401
+from msig_b200 import lib as L
+from msig_b200 import ops
+
+DEV = "cuda"
+
+
+def rel_err(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def _rand(shape, seed, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale)
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+def nhwc(x_nchw):
+    return x_nchw.permute(0, 2, 3, 1).contiguous()
+
+
+def nchw(x_nhwc):
+    return x_nhwc.permute(0, 3, 1, 2).contiguous()
+
+
+# --------------------------------------------------------------------------- cases
+def case_conv_fwd(n, c, h, w, k, r, stride, pad, bias=True, act=L.ACT_NONE, seed=0):
+    ops.ensure_init()
+    x = _bf(_rand((n, c, h, w), seed)).to(DEV)
+    wt = _bf(_rand((k, c, r, r), seed + 1, 1.0 / (c * r * r) ** 0.5)).to(DEV)
+    b = _rand((k,), seed + 2).to(DEV) if bias else None
+    oh = (h + 2 * pad - r) // stride + 1
+    ow = (w + 2 * pad - r) // stride + 1
+    ref = F.conv2d(x.float(), wt.float(), b, stride=stride, padding=pad)
+    if act == L.ACT_RELU:
+        ref = F.relu(ref)
+    elif act == L.ACT_LRELU:
+        ref = F.leaky_relu(ref, 0.2)
+    wpk = ops.wpack(L.WPACK_FWD, wt.float().contiguous(), k, c, r, r)
+    g = ops.conv_geom(n, h, w, c, k, r, r, stride, pad, pad, oh, ow)
+    y = ops.conv2d_fwd(nhwc(x), wpk, g, ops.epilogue(bias=b, act=act))
+    torch.cuda.synchronize()
+    return rel_err(nchw(y), ref), 1e-2
+
+
+def case_conv_dgrad(n, c, h, w, k, r, stride, pad, seed=0):
+    ops.ensure_init()
+    oh = (h + 2 * pad - r) // stride + 1
+    ow = (w + 2 * pad - r) // stride + 1
+    dy = _bf(_rand((n, k, oh, ow), seed)).to(DEV)
+    wt = _bf(_rand((k, c, r, r), seed + 1, 1.0 / (k * r * r) ** 0.5)).to(DEV)
+    ref = torch.nn.grad.conv2d_input((n, c, h, w), wt.float(), dy.float(), stride=stride, padding=pad)
+    kind = L.WPACK_DGRAD_S1 if stride == 1 else L.WPACK_DGRAD_S2
+    wpk = ops.wpack(kind, wt.float().contiguous(), k, c, r, r)
+    g = ops.conv_geom(n, h, w, c, k, r, r, stride, pad, pad, oh, ow)
+    dx = ops.conv2d_dgrad(nhwc(dy), wpk, g)
+    torch.cuda.synchronize()
+    return rel_err(nchw(dx), ref), 1e-2
+
+
+def case_conv_wgrad(n, c, h, w, k, r, stride, pad, seed=0):
+    ops.ensure_init()
+    oh = (h + 2 * pad - r) // stride + 1
+    ow = (w + 2 * pad - r) // stride + 1
+    x = _bf(_rand((n, c, h, w), seed)).to(DEV)
+    dy = _bf(_rand((n, k, oh, ow), seed + 1)).to(DEV)
+    ref = torch.nn.grad.conv2d_weight(x.float(), (k, c, r, r), dy.float(), stride=stride, padding=pad)
+    g = ops.conv_geom(n, h, w, c, k, r, r, stride, pad, pad, oh, ow)
+    dw = torch.zeros((k, c, r, r), dtype=torch.float32, device=DEV)
+    ops.conv2d_wgrad(nhwc(x), nhwc(dy), g, dw, accumulate=False)
+    torch.cuda.synchronize()
+    return rel_err(dw, ref), 2e-3
+
+
+def case_convT(n, c, h, w, k, seed=0, which="fwd"):
+    ops.ensure_init()
+    x = _bf(_rand((n, c, h, w), seed)).to(DEV)
+    wt = _bf(_rand((c, k, 4, 4), seed + 1, 1.0 / (c * 4) ** 0.5)).to(DEV)   # ConvTranspose2d layout [in, out, 4, 4]
+    g = ops.conv_geom(n, h, w, c, k, 4, 4, 2, 1, 1, 2 * h, 2 * w)
+    if which == "fwd":
+        ref = F.conv_transpose2d(x.float(), wt.float(), None, stride=2, padding=1)
+        wpk = ops.wpack(L.WPACK_CONVT_FWD, wt.float().contiguous(), k, c, 4, 4)
+        y = ops.convT2d_fwd(nhwc(x), wpk, g)
+        torch.cuda.synchronize()
+        return rel_err(nchw(y), ref), 1e-2
+    dy = _bf(_rand((n, k, 2 * h, 2 * w), seed + 2)).to(DEV)
+    if which == "dgrad":
+        ref = F.conv2d(dy.float(), wt.float(), None, stride=2, padding=1)   # adjoint of conv_transpose
+        wpk = ops.wpack(L.WPACK_CONVT_DGRAD, wt.float().contiguous(), k, c, 4, 4)
+        dx = ops.convT2d_dgrad(nhwc(dy), wpk, g)
+        torch.cuda.synchronize()
+        return rel_err(nchw(dx), ref), 1e-2
+    # wgrad: d/dw of <conv_transpose(x, w), dy>
+    xf = x.float()
+    wf = wt.float().clone().requires_grad_(True)
+    (F.conv_transpose2d(xf, wf, None, stride=2, padding=1) * dy.float()).sum().backward()
+    dw = torch.zeros((c, k, 4, 4), dtype=torch.float32, device=DEV)
+    ops.convT2d_wgrad(nhwc(x), nhwc(dy), g, dw, accumulate=False)
+    torch.cuda.synchronize()
+    return rel_err(dw, wf.grad), 2e-3
+
+
+def case_gemm(rows, k_in, n_out, seed=0, f32_out=False):
+    """Linear layer as a 1x1 conv on a [1,1,rows,k_in] view."""
+    ops.ensure_init()
+    a = _bf(_rand((rows, k_in), seed)).to(DEV)
+    wt = _bf(_rand((n_out, k_in), seed + 1, 1.0 / k_in ** 0.5)).to(DEV)
+    b = _rand((n_out,), seed + 2).to(DEV)
+    ref = a.float() @ wt.float().t() + b
+    wpk = ops.wpack(L.WPACK_FWD, wt.float().contiguous(), n_out, k_in, 1, 1)
+    g = ops.gemm_geom(rows, k_in, n_out)
+    e = ops.epilogue(bias=b, out_layout=L.OUT_F32_NHWC if f32_out else L.OUT_BF16_NHWC)
+    y = ops.conv2d_fwd(a.view(1, 1, rows, k_in), wpk, g, e)
+    torch.cuda.synchronize()
+    return rel_err(y.reshape(rows, n_out), ref), (2e-3 if f32_out else 1e-2)
+
+
+def case_gram(n, c, h, w, seed=0):
+    ops.ensure_init()
+    f = _bf(_rand((n, h, w, c), seed)).to(DEV)
+    feat = nchw(f).float().reshape(n * c, h * w)
+    ref = feat @ feat.t() / (n * c * h * w)
+    gram = ops.gram_fwd(f)
+    torch.cuda.synchronize()
+    return rel_err(gram, ref), 2e-3
+
+
+def case_gram_bwd(n, c, h, w, seed=0):
+    ops.ensure_init()
+    f = _bf(_rand((n, h, w, c), seed)).to(DEV)
+    dim = n * c
+    g = torch.Generator().manual_seed(seed + 5)
+    s = torch.randint(-2, 3, (dim, dim), generator=g).float()
+    s = ((s + s.t()) / 2).round().clamp(-2, 2).to(DEV)
+    feat = nchw(f).float().reshape(dim, h * w)
+    alpha = 1.0 / dim
+    ref = (alpha * (s @ feat)).reshape(n, c, h, w)
+    df = ops.gram_bwd(f, s.to(torch.bfloat16).contiguous(), alpha)
+    torch.cuda.synchronize()
+    return rel_err(nchw(df), ref), 1e-2
+
+
+CASES = {
+    # forward convs: the shapes of the reference networks, reduced batch
+    "fwd_3x3_256_64": lambda: case_conv_fwd(2, 256, 64, 64, 256, 3, 1, 1),
+    "fwd_3x3_64_32_relu": lambda: case_conv_fwd(1, 64, 32, 32, 64, 3, 1, 1, act=L.ACT_RELU),
+    "fwd_3x3_128_128w": lambda: case_conv_fwd(1, 64, 128, 128, 128, 3, 1, 1),
+    "fwd_3x3_64_256w": lambda: case_conv_fwd(1, 64, 16, 256, 64, 3, 1, 1),
+    "fwd_4x4s2_64_128": lambda: case_conv_fwd(2, 64, 64, 64, 128, 4, 2, 1, act=L.ACT_LRELU),
+    "fwd_4x4s2_256_512": lambda: case_conv_fwd(2, 256, 32, 32, 512, 4, 2, 1),
+    "fwd_1x1_gemm": lambda: case_gemm(200, 256, 512),
+    "fwd_gemm_small_rows_f32": lambda: case_gemm(4, 512, 2560, f32_out=True),
+    "dgrad_3x3_256": lambda: case_conv_dgrad(2, 256, 64, 64, 256, 3, 1, 1),
+    "dgrad_4x4s2_128_256": lambda: case_conv_dgrad(2, 128, 64, 64, 256, 4, 2, 1),
+    "dgrad_4x4s2_64_128_w128": lambda: case_conv_dgrad(1, 64, 256, 256, 128, 4, 2, 1),
+    "convT_fwd_256_128": lambda: case_convT(2, 256, 32, 32, 128, which="fwd"),
+    "convT_fwd_128_64": lambda: case_convT(1, 128, 64, 64, 64, which="fwd"),
+    "convT_dgrad_256_128": lambda: case_convT(2, 256, 32, 32, 128, which="dgrad"),
+    "wgrad_3x3_256": lambda: case_conv_wgrad(2, 256, 64, 64, 256, 3, 1, 1),
+    "wgrad_3x3_64_128_w32": lambda: case_conv_wgrad(3, 64, 32, 32, 128, 3, 1, 1),
+    "wgrad_4x4s2_64_128": lambda: case_conv_wgrad(2, 64, 64, 64, 128, 4, 2, 1),
+    "wgrad_4x4s2_256_512_w16": lambda: case_conv_wgrad(2, 256, 32, 32, 512, 4, 2, 1),
+    "convT_wgrad_256_128": lambda: case_convT(2, 256, 32, 32, 128, which="wgrad"),
+    "gram_64": lambda: case_gram(2, 64, 64, 64),
+    "gram_256_b3": lambda: case_gram(3, 256, 16, 16),
+    "gram_bwd_128": lambda: case_gram_bwd(2, 128, 32, 32),
+}
