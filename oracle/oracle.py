@@ -1,0 +1,273 @@
+"""ORACLE — TEST INFRASTRUCTURE ONLY. Not part of the product path.
+
+CPU fp32 restatement (plain torch.nn.functional, no custom kernels) of the reference's hot path:
+the style-injected Generator, the multi-domain Style Encoder and Discriminator (model.py), the
+VGG style/content loss (losses.py) and one G+D optimisation step (trainer.py::train_step,
+utils.py EMA / DynamicWeightScheduler). Every function cites the reference lines it follows.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
+import this module, and only as the checker / the CPU baseline.
+
+Pinning: the reference ships no tests or golden vectors, so this restatement
+is pinned against the reference ITSELF: oracle/make_golden.py imports /root/reference in the build
+container, runs it on seeded inputs and writes small fixtures to tests/golden/; tests/test_oracle.py
+checks this module against them (and, when /root/reference is present, against the live reference).
+
+Weights are plain dicts of tensors keyed exactly like the reference's state_dict().
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+LRELU = 0.2
+IN_EPS = 1e-5
+
+
+# ----------------------------------------------------------------------------- building blocks
+def instance_norm(x):
+    """nn.InstanceNorm2d(affine=False): per-(n,c) biased variance, eps inside the sqrt
+    (model.py:16,131-133,139-140,167)."""
+    mu = x.mean(dim=(2, 3), keepdim=True)
+    var = x.var(dim=(2, 3), unbiased=False, keepdim=True)
+    return (x - mu) / torch.sqrt(var + IN_EPS)
+
+
+def adain(x, style, w, b):
+    """AdaIN.forward (model.py:20-36): gamma = first C outputs of the Linear, beta = last C."""
+    if style.dim() == 4:
+        style = style.squeeze(-1).squeeze(-1)
+    gb = F.linear(style, w, b)
+    c = x.shape[1]
+    gamma = gb[:, :c].reshape(-1, c, 1, 1)
+    beta = gb[:, c:].reshape(-1, c, 1, 1)
+    return gamma * instance_norm(x) + beta
+
+
+def reflect_conv7(x, w, b):
+    """nn.Conv2d(k=7, s=1, p=3, padding_mode='reflect') (model.py:131,141)."""
+    return F.conv2d(F.pad(x, (3, 3, 3, 3), mode="reflect"), w, b)
+
+
+def generator_forward(sd, img, style, n_res=8):
+    """StyleCycleGANGenerator.forward (model.py:145-151; layers :130-143)."""
+    x = F.relu(instance_norm(reflect_conv7(img, sd["content_encoder.0.weight"], sd["content_encoder.0.bias"])))
+    x = F.relu(instance_norm(F.conv2d(x, sd["content_encoder.3.weight"], sd["content_encoder.3.bias"], stride=2, padding=1)))
+    x = F.relu(instance_norm(F.conv2d(x, sd["content_encoder.6.weight"], sd["content_encoder.6.bias"], stride=2, padding=1)))
+    for i in range(n_res):  # ResidualBlockWithAdaIN.forward, model.py:51-55
+        p = f"decoder.{i}."
+        r = x
+        h = F.conv2d(x, sd[p + "conv1.weight"], sd[p + "conv1.bias"], padding=1)
+        h = F.relu(adain(h, style, sd[p + "adain1.style_modulation.weight"], sd[p + "adain1.style_modulation.bias"]))
+        h = F.conv2d(h, sd[p + "conv2.weight"], sd[p + "conv2.bias"], padding=1)
+        h = adain(h, style, sd[p + "adain2.style_modulation.weight"], sd[p + "adain2.style_modulation.bias"])
+        x = h + r
+    k = n_res
+    x = F.relu(instance_norm(F.conv_transpose2d(x, sd[f"decoder.{k}.weight"], sd[f"decoder.{k}.bias"], stride=2, padding=1)))
+    x = F.relu(instance_norm(F.conv_transpose2d(x, sd[f"decoder.{k + 3}.weight"], sd[f"decoder.{k + 3}.bias"], stride=2, padding=1)))
+    return torch.tanh(reflect_conv7(x, sd[f"decoder.{k + 6}.weight"], sd[f"decoder.{k + 6}.bias"]))
+
+
+def _select_heads(all_out, domain_idx):
+    """torch.stack(..., dim=1)[arange(B), domain_idx] (model.py:112-116, 208-212)."""
+    b = all_out.shape[0]
+    return all_out[torch.arange(b, device=all_out.device), domain_idx]
+
+
+def style_encoder_forward(sd, img, domain_idx, num_domains):
+    """MultiDomainStyleEncoder.forward (model.py:89-118): 4x (conv4x4 s2 + ReLU), global average
+    pool, one 1x1-conv head per domain, per-sample head selection."""
+    x = img
+    for i in (0, 2, 4, 6):
+        x = F.relu(F.conv2d(x, sd[f"shared_layers.{i}.weight"], sd[f"shared_layers.{i}.bias"], stride=2, padding=1))
+    x = x.mean(dim=(2, 3), keepdim=True)
+    if domain_idx is None:
+        return F.conv2d(x, sd["domain_branches.0.0.weight"], sd["domain_branches.0.0.bias"]).flatten(1)
+    outs = [F.conv2d(x, sd[f"domain_branches.{k}.0.weight"], sd[f"domain_branches.{k}.0.bias"]).flatten(1)
+            for k in range(num_domains)]
+    return _select_heads(torch.stack(outs, dim=1), domain_idx)
+
+
+def discriminator_forward(sd, img, domain_idx, num_domains):
+    """MultiDomainDiscriminator.forward (model.py:186-214): conv+LeakyReLU, 3x (conv + IN +
+    LeakyReLU), per-domain ZeroPad2d((1,0,1,0)) + conv4x4 p1 head, per-sample selection."""
+    x = F.leaky_relu(F.conv2d(img, sd["shared_layers.0.weight"], sd["shared_layers.0.bias"], stride=2, padding=1), LRELU)
+    for i in (2, 5, 8):
+        x = F.conv2d(x, sd[f"shared_layers.{i}.weight"], sd[f"shared_layers.{i}.bias"], stride=2, padding=1)
+        x = F.leaky_relu(instance_norm(x), LRELU)
+    xp = F.pad(x, (1, 0, 1, 0))
+    if domain_idx is None:
+        return F.conv2d(xp, sd["domain_branches.0.1.weight"], sd["domain_branches.0.1.bias"], padding=1)
+    outs = [F.conv2d(xp, sd[f"domain_branches.{k}.1.weight"], sd[f"domain_branches.{k}.1.bias"], padding=1)
+            for k in range(num_domains)]
+    return _select_heads(torch.stack(outs, dim=1), domain_idx)
+
+
+# ----------------------------------------------------------------------------- VGG loss
+VGG_MEAN = (0.485, 0.456, 0.406)
+VGG_STD = (0.229, 0.224, 0.225)
+# torchvision vgg19().features indices of the first five convs; max-pools sit after conv 2 and 4.
+VGG_CONV_IDX = (0, 2, 5, 7, 10)
+
+
+def vgg_features(vgg_sd, img):
+    """The five taps the reference actually uses (losses.py:23-35 names the ReLUs after the FIRST
+    FIVE convs 'relu_1_1'..'relu_5_1'; everything after conv 5 is dead).
+    Input renormalisation: losses.py:49-56."""
+    mean = torch.tensor(VGG_MEAN, device=img.device).view(1, 3, 1, 1)
+    std = torch.tensor(VGG_STD, device=img.device).view(1, 3, 1, 1)
+    x = ((img + 1) / 2 - mean) / std
+    feats = []
+    for j, idx in enumerate(VGG_CONV_IDX):
+        x = F.relu(F.conv2d(x, vgg_sd[f"{idx}.weight"], vgg_sd[f"{idx}.bias"], padding=1))
+        feats.append(x)
+        if j in (1, 3):
+            x = F.max_pool2d(x, 2)
+    return feats
+
+
+def gram(x):
+    """compute_gram_matrix (losses.py:70-78): batch folded into rows."""
+    a, b, c, d = x.shape
+    f = x.reshape(a * b, c * d)
+    return (f @ f.t()) / (a * b * c * d)
+
+
+def vgg_loss(vgg_sd, generated, real_style, real_content):
+    """VGGStyleContentLoss.forward (losses.py:100-115) -> (content_loss, style_loss)."""
+    fg = vgg_features(vgg_sd, generated)
+    fs = vgg_features(vgg_sd, real_style)
+    fc = vgg_features(vgg_sd, real_content)
+    style = sum(F.l1_loss(gram(a), gram(b)) for a, b in zip(fg, fs))
+    content = F.l1_loss(fg[3], fc[3])   # 'relu_4_1' = ReLU after the 4th conv
+    return content, style
+
+
+# ----------------------------------------------------------------------------- schedules
+def loss_weights(init_weights, epoch, warmup_epochs=10, decay_epochs=100):
+    """DynamicWeightScheduler.get_current_weights (utils.py:117-132): depends on epoch only."""
+    warm = min(1.0, (epoch + 1) / warmup_epochs)
+    decay = 1.0
+    if epoch >= warmup_epochs:
+        prog = min(1.0, (epoch - warmup_epochs) / decay_epochs)
+        decay = 0.1 + 0.9 * 0.5 * (1 + math.cos(math.pi * prog))
+    return {k: v * warm * decay for k, v in init_weights.items()}
+
+
+DEFAULT_LOSS_WEIGHTS = {"gan": 1.0, "cycle": 10.0, "identity": 5.0, "content": 1.0, "style": 1.0}  # config.py:27-33
+
+
+class AdamState:
+    """torch.optim.Adam defaults used by the reference (trainer.py:58,61): betas (0.5, 0.999),
+    eps 1e-8, no weight decay; preceded by clip_grad_norm_(params, 1.0) (trainer.py:127,152)."""
+
+    def __init__(self, params, lr, betas=(0.5, 0.999), eps=1e-8):
+        self.lr, self.betas, self.eps, self.t = lr, betas, eps, 0
+        self.m = [torch.zeros_like(p) for p in params]
+        self.v = [torch.zeros_like(p) for p in params]
+
+    def step(self, params, grads, max_norm=1.0):
+        total = torch.sqrt(sum((g.double() ** 2).sum() for g in grads)).float()
+        coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+        self.t += 1
+        b1, b2 = self.betas
+        bc1 = 1 - b1 ** self.t
+        bc2 = 1 - b2 ** self.t
+        for p, g, m, v in zip(params, grads, self.m, self.v):
+            g = g * coef
+            m.mul_(b1).add_(g, alpha=1 - b1)
+            v.mul_(b2).addcmul_(g, g, value=1 - b2)
+            denom = v.sqrt() / math.sqrt(bc2) + self.eps
+            p.sub_((self.lr / bc1) * m / denom)
+        return total
+
+
+class OracleTrainer:
+    """One G+D optimisation step, trainer.py:74-155, on dict-of-tensor weights."""
+
+    NETS = ("G_A2B", "G_B2A", "SE_A", "SE_B", "D_A", "D_B")
+
+    def __init__(self, state, vgg_sd, num_domains, lr_g=2e-4, lr_d=1e-4, loss_w=None, ema_beta=0.995):
+        self.sd = {k: {n: t.detach().clone().float() for n, t in state[k].items()} for k in self.NETS}
+        self.ema = {k: {n: t.clone() for n, t in self.sd[k].items()} for k in ("G_A2B", "G_B2A", "SE_A", "SE_B")}
+        self.vgg = {n: t.detach().clone().float() for n, t in vgg_sd.items()}
+        self.nd = num_domains
+        self.loss_w = dict(loss_w or DEFAULT_LOSS_WEIGHTS)
+        self.ema_beta = ema_beta
+        self.g_names = [(k, n) for k in ("G_A2B", "G_B2A", "SE_A", "SE_B") for n in self.sd[k]]
+        self.d_names = [(k, n) for k in ("D_A", "D_B") for n in self.sd[k]]
+        self.g_opt = AdamState([self.sd[k][n] for k, n in self.g_names], lr_g)
+        self.d_opt = AdamState([self.sd[k][n] for k, n in self.d_names], lr_d)
+
+    def _leaf(self, names):
+        for k, n in names:
+            self.sd[k][n] = self.sd[k][n].detach().requires_grad_(True)
+
+    def train_step(self, batch, epoch):
+        sd, nd = self.sd, self.nd
+        real_A, real_B = batch["source"].float(), batch["target"].float()
+        y_org, y_trg = batch["source_domain"], batch["target_domain"]
+        self._leaf(self.g_names + self.d_names)
+        # ---- generators (trainer.py:91-128)
+        style_A = style_encoder_forward(sd["SE_A"], real_A, y_org, nd)
+        style_B = style_encoder_forward(sd["SE_B"], real_B, y_trg, nd)
+        l_id = F.l1_loss(generator_forward(sd["G_A2B"], real_B, style_B), real_B)
+        fake_B = generator_forward(sd["G_A2B"], real_A, style_B)
+        d_fb = discriminator_forward(sd["D_B"], fake_B, y_trg, nd)
+        l_gan_ab = F.mse_loss(d_fb, torch.ones_like(d_fb))
+        c_b, s_b = vgg_loss(self.vgg, fake_B, real_B, real_A)
+        fake_A = generator_forward(sd["G_B2A"], real_B, style_A)
+        d_fa = discriminator_forward(sd["D_A"], fake_A, y_org, nd)
+        l_gan_ba = F.mse_loss(d_fa, torch.ones_like(d_fa))
+        c_a, s_a = vgg_loss(self.vgg, fake_A, real_A, real_B)
+        l_gan = (l_gan_ab + l_gan_ba) / 2
+        l_style = (s_a + s_b) / 2
+        l_content = (c_a + c_b) / 2
+        l_cycle = (F.l1_loss(generator_forward(sd["G_B2A"], fake_B, style_A), real_A) +
+                   F.l1_loss(generator_forward(sd["G_A2B"], fake_A, style_B), real_B)) / 2
+        indiv = {"gan": l_gan, "cycle": l_cycle, "identity": l_id, "style": l_style, "content": l_content}
+        w = loss_weights(self.loss_w, epoch)
+        g_loss = sum(indiv[k] * w[k] for k in indiv)
+        g_params = [sd[k][n] for k, n in self.g_names]
+        g_grads = torch.autograd.grad(g_loss, g_params, allow_unused=True)
+        g_grads = [torch.zeros_like(p) if g is None else g for p, g in zip(g_params, g_grads)]
+        fake_A_d, fake_B_d = fake_A.detach(), fake_B.detach()
+        with torch.no_grad():
+            g_norm = self.g_opt.step(g_params, g_grads)
+            for (k, n), p in zip(self.g_names, g_params):   # EMA, utils.py:80-91
+                self.ema[k][n].mul_(self.ema_beta).add_(p, alpha=1 - self.ema_beta)
+        # ---- discriminators (trainer.py:139-153)
+        def dl(net, x, y, target):
+            o = discriminator_forward(sd[net], x, y, nd)
+            return F.mse_loss(o, torch.full_like(o, target))
+        d_loss = (dl("D_A", real_A, y_org, 1.0) + dl("D_A", fake_A_d, y_org, 0.0) +
+                  dl("D_B", real_B, y_trg, 1.0) + dl("D_B", fake_B_d, y_trg, 0.0)) / 2
+        d_params = [sd[k][n] for k, n in self.d_names]
+        d_grads = torch.autograd.grad(d_loss, d_params, allow_unused=True)
+        d_grads = [torch.zeros_like(p) if g is None else g for p, g in zip(d_params, d_grads)]
+        with torch.no_grad():
+            d_norm = self.d_opt.step(d_params, d_grads)
+        losses = {"D_loss": d_loss.detach(), "G_loss": g_loss.detach(), **{k: v.detach() for k, v in indiv.items()}}
+        grads = {f"{k}.{n}": g.detach() for (k, n), g in zip(self.g_names + self.d_names, g_grads + d_grads)}
+        return {"losses": losses, "grads": grads, "g_grad_norm": g_norm, "d_grad_norm": d_norm,
+                "fake_A": fake_A_d, "fake_B": fake_B_d}
+
+
+def synthetic_batch(b, s, num_domains, seed=42):
+    """The seeded synthetic src/ref batch of SURVEY §8(d) / BASELINE.md §4."""
+    g = torch.Generator().manual_seed(seed)
+    src = torch.rand(b, 3, s, s, generator=g) * 2 - 1
+    tgt = torch.rand(b, 3, s, s, generator=g) * 2 - 1
+    return {"source": src, "target": tgt, "source_domain": torch.zeros(b, dtype=torch.int64),
+            "target_domain": 1 + (torch.arange(b) % max(num_domains - 1, 1))}
+
+
+def seeded_vgg_state(seed=1234):
+    """Random-init VGG19 feature weights under a fixed seed (the pretrained file cannot be
+    downloaded offline); RNG state is restored afterwards."""
+    import torchvision
+    st = torch.get_rng_state()
+    torch.manual_seed(seed)
+    sd = {k: v.clone() for k, v in torchvision.models.vgg19(weights=None).features.state_dict().items()}
+    torch.set_rng_state(st)
+    return sd

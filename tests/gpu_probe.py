@@ -16,19 +16,26 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def run_one(name):
     import torch  # noqa: F401
-    import igemm_cases as C
+    cases = all_cases()
     t0 = time.time()
-    err, tol = C.CASES[name]()
+    err, tol = cases[name]()
     print(json.dumps({"case": name, "err": err, "tol": tol, "ok": bool(err <= tol), "s": round(time.time() - t0, 2)}))
+
+
+def all_cases():
+    import igemm_cases
+    import ops_cases
+    d = dict(igemm_cases.CASES)
+    d.update(ops_cases.CASES)
+    return d
 
 
 def main():
     if len(sys.argv) >= 3 and sys.argv[1] == "--one":
         run_one(sys.argv[2])
         return
-    import igemm_cases as C
     pats = sys.argv[1:]
-    names = [n for n in C.CASES if not pats or any(p in n for p in pats)]
+    names = [n for n in all_cases() if not pats or any(p in n for p in pats)]
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     out = open(os.path.join(ROOT, "gpurun_out", "probe.jsonl"), "a")
     nfail = 0

@@ -1,0 +1,265 @@
+"""Parity cases for the bandwidth-bound entry points (through the C ABI) vs plain PyTorch fp32 on
+the same bf16-rounded inputs. Tolerances: bf16 outputs 1e-2 (max-rel), fp32 outputs 2e-3,
+loss scalars 1e-4 relative."""
+import torch
+import torch.nn.functional as F
+
+import msig_b200  # noqa: F401
+from msig_b200 import lib as L
+from msig_b200 import ops
+from igemm_cases import _bf, _rand, nchw, nhwc, rel_err
+
+DEV = "cuda"
+
+
+def case_patch_gather(n, c, h, w, r, stride, pad, reflect, affine=False, seed=0):
+    ops.ensure_init()
+    x = _rand((n, c, h, w), seed).to(DEV)
+    oh = (h + 2 * pad - r) // stride + 1
+    ow = (w + 2 * pad - r) // stride + 1
+    pg = ops.patch_geom(n, c, h, w, r, r, stride, pad, pad, oh, ow, reflect)
+    scale = shift = None
+    xs = x
+    if affine:
+        scale = torch.tensor([0.5, 2.0, -1.0][:c], device=DEV)
+        shift = torch.tensor([0.1, -0.2, 0.3][:c], device=DEV)
+        xs = x * scale.view(1, c, 1, 1) + shift.view(1, c, 1, 1)
+    xp = F.pad(xs, (pad,) * 4, mode="reflect" if reflect else "constant")
+    cols = F.unfold(xp, r, stride=stride)                      # [n, c*r*r, oh*ow], index (c, r, s)
+    cols = cols.view(n, c, r * r, oh * ow).permute(0, 3, 2, 1).reshape(n * oh * ow, r * r * c)
+    got = ops.patch_gather(x, pg, scale, shift)
+    torch.cuda.synchronize()
+    e1 = rel_err(got[:, :r * r * c], cols.to(torch.bfloat16))
+    e2 = got[:, r * r * c:].float().abs().max().item() if pg.kpad > r * r * c else 0.0
+    return max(e1, e2), 1e-6
+
+
+def case_patch_scatter(n, c, h, w, r, stride, pad, reflect, affine=False, seed=0):
+    ops.ensure_init()
+    oh = (h + 2 * pad - r) // stride + 1
+    ow = (w + 2 * pad - r) // stride + 1
+    pg = ops.patch_geom(n, c, h, w, r, r, stride, pad, pad, oh, ow, reflect)
+    dp = _bf(_rand((n * oh * ow, pg.kpad), seed)).to(DEV)
+    scale = torch.tensor([0.5, 2.0, -1.0][:c], device=DEV) if affine else None
+    x = torch.zeros((n, c, h, w), device=DEV, requires_grad=True)
+    xs = x * scale.view(1, c, 1, 1) if affine else x
+    xp = F.pad(xs, (pad,) * 4, mode="reflect" if reflect else "constant")
+    cols = F.unfold(xp, r, stride=stride).view(n, c, r * r, oh * ow).permute(0, 3, 2, 1).reshape(n * oh * ow, r * r * c)
+    (cols * dp[:, :r * r * c].float()).sum().backward()
+    got = ops.patch_scatter(dp, pg, scale)
+    torch.cuda.synchronize()
+    return rel_err(got, x.grad), 1e-5
+
+
+def case_reflect_pad(n, c, h, w, pad, seed=0):
+    ops.ensure_init()
+    x = _bf(_rand((n, c, h, w), seed)).to(DEV)
+    ref = F.pad(x.float(), (pad,) * 4, mode="reflect")
+    y = ops.reflect_pad_fwd(nhwc(x), pad)
+    dy = _bf(_rand(tuple(ref.shape), seed + 1)).to(DEV)
+    xr = x.float().clone().requires_grad_(True)
+    (F.pad(xr, (pad,) * 4, mode="reflect") * dy.float()).sum().backward()
+    dx = ops.reflect_pad_bwd(nhwc(dy), pad)
+    torch.cuda.synchronize()
+    return max(rel_err(nchw(y), ref), rel_err(nchw(dx), xr.grad)), 1e-2
+
+
+def case_norm(n, c, h, w, act, adain, residual, seed=0):
+    """InstanceNorm / AdaIN (+act, +residual) forward and backward (dx, dgamma, dbeta)."""
+    ops.ensure_init()
+    x = _bf(_rand((n, c, h, w), seed) * 2.0 + 0.5).to(DEV)
+    dy = _bf(_rand((n, c, h, w), seed + 1)).to(DEV)
+    res = _bf(_rand((n, c, h, w), seed + 2)).to(DEV) if residual else None
+    gb = (_rand((n, 2 * c), seed + 3) + 0.5).to(DEV) if adain else None
+
+    xr = x.float().clone().requires_grad_(True)
+    gbr = gb.clone().requires_grad_(True) if adain else None
+    xn = F.instance_norm(xr, eps=1e-5)
+    if adain:
+        z = gbr[:, :c].view(n, c, 1, 1) * xn + gbr[:, c:].view(n, c, 1, 1)
+    else:
+        z = xn
+    if act == L.ACT_RELU:
+        z = F.relu(z)
+    elif act == L.ACT_LRELU:
+        z = F.leaky_relu(z, 0.2)
+    if residual:
+        z = z + res.float()
+    (z * dy.float()).sum().backward()
+
+    xh = nhwc(x)
+    gamma = gb[:, :c] if adain else None
+    beta = gb[:, c:] if adain else None
+    st = ops.in_stats(xh, gamma, beta, 2 * c if adain else 0)
+    y = ops.norm_act_fwd(xh, st, act, nhwc(res) if residual else None)
+    dgb = torch.zeros((n, 2 * c), device=DEV) if adain else None
+    dx = ops.norm_act_bwd(nhwc(dy), xh, st, act, dgamma=dgb[:, :c] if adain else None,
+                          dbeta=dgb[:, c:] if adain else None, dgb_stride=2 * c if adain else 0)
+    torch.cuda.synchronize()
+    errs = [rel_err(nchw(y), z), rel_err(nchw(dx), xr.grad)]
+    if adain:
+        errs.append(rel_err(dgb, gbr.grad) / 5)   # fp32 sums of bf16 products: looser than 1e-2/5 is a bug
+    return max(errs), 1.2e-2
+
+
+def case_act_bwd(seed=0):
+    ops.ensure_init()
+    y = _bf(_rand((4, 32, 32, 64), seed)).to(DEV)
+    dy = _bf(_rand((4, 32, 32, 64), seed + 1)).to(DEV)
+    ref = dy.float() * torch.where(y.float() > 0, 1.0, 0.2)
+    got = ops.act_bwd(dy, y, L.ACT_LRELU)
+    s = ops.add_bf16(dy, y)
+    torch.cuda.synchronize()
+    return max(rel_err(got, ref), rel_err(s, dy.float() + y.float())), 1e-2
+
+
+def case_colsum(seed=0):
+    ops.ensure_init()
+    dy = _bf(_rand((3000, 256), seed)).to(DEV)
+    db = torch.ones(256, device=DEV)
+    ops.colsum(dy, 256, db, accumulate=True)
+    x = _rand((37, 2560), seed + 1).to(DEV)
+    o = torch.zeros(2560, device=DEV)
+    ops.colsum_f32(x, 37, 2560, o, accumulate=False)
+    img = _rand((3, 3, 40, 50), seed + 2).to(DEV)
+    cs = torch.zeros(3, device=DEV)
+    ops.nchw_chansum(img, cs, accumulate=False)
+    torch.cuda.synchronize()
+    return max(rel_err(db, dy.float().sum(0) + 1), rel_err(o, x.sum(0)), rel_err(cs, img.sum((0, 2, 3)))), 1e-4
+
+
+def case_pool(seed=0):
+    ops.ensure_init()
+    x = _bf(_rand((2, 64, 32, 48), seed)).to(DEV)
+    xr = x.float().clone().requires_grad_(True)
+    ref = F.max_pool2d(xr, 2)
+    dy = _bf(_rand(tuple(ref.shape), seed + 1)).to(DEV)
+    (ref * dy.float()).sum().backward()
+    y = ops.maxpool2_fwd(nhwc(x))
+    dx = ops.maxpool2_bwd(nhwc(dy), nhwc(x))
+    a = _bf(_rand((3, 512, 16, 16), seed + 2)).to(DEV)
+    pooled = ops.avgpool_fwd(nhwc(a))
+    dpool = _bf(_rand((3, 512), seed + 3)).to(DEV)
+    da = ops.avgpool_bwd(dpool, 16, 16)
+    torch.cuda.synchronize()
+    e = [rel_err(nchw(y), ref), rel_err(nchw(dx), xr.grad), rel_err(pooled, a.float().mean((2, 3))),
+         rel_err(nchw(da), (dpool.float() / 256).view(3, 512, 1, 1).expand(3, 512, 16, 16))]
+    return max(e), 1e-2
+
+
+def case_heads(seed=0):
+    ops.ensure_init()
+    n, nd, sd = 5, 10, 256
+    allv = _rand((n, nd * sd), seed).to(DEV)
+    idx = torch.tensor([0, 3, 9, 1, 3], device=DEV)
+    got = ops.head_gather(allv, idx, n, 1, nd, sd, True)
+    ref = allv.view(n, nd, sd)[torch.arange(n), idx]
+    dout = _rand((n, sd), seed + 1).to(DEV)
+    dall = ops.head_scatter(dout, idx, n, 1, nd, sd, True)
+    dref = torch.zeros(n, nd, sd, device=DEV)
+    dref[torch.arange(n), idx] = dout
+    # discriminator layout [n][pix][16] (heads padded to 16)
+    pix = 256
+    alld = _rand((n, pix, 16), seed + 2).to(DEV)
+    gd = ops.head_gather(alld, idx, n, pix, 16, 1, False)
+    refd = alld[torch.arange(n), :, idx]
+    dd = ops.head_scatter(gd, idx, n, pix, 16, 1, False).view(n, pix, 16)
+    drefd = torch.zeros(n, pix, 16, device=DEV)
+    drefd[torch.arange(n), :, idx] = refd
+    torch.cuda.synchronize()
+    e = [(got - ref).abs().max().item(), (dall.view(n, nd, sd) - dref).abs().max().item(),
+         (gd - refd).abs().max().item(), (dd - drefd).abs().max().item()]
+    return max(e), 0.0
+
+
+def case_losses(seed=0):
+    ops.ensure_init()
+    a = _rand((4, 3, 64, 64), seed).to(DEV)
+    b = _rand((4, 3, 64, 64), seed + 1).to(DEV)
+    gs = torch.tensor(0.37, device=DEV)
+    ar = a.clone().requires_grad_(True)
+    lref = F.l1_loss(ar, b)
+    (lref * gs).backward()
+    l1 = ops.l1_loss_f32_fwd(a, b)
+    g1 = ops.l1_loss_f32_bwd(a, b, gs)
+    fa = _bf(_rand((2, 16, 16, 128), seed + 2)).to(DEV)
+    fb = _bf(_rand((2, 16, 16, 128), seed + 3)).to(DEV)
+    far = fa.float().clone().requires_grad_(True)
+    lref2 = F.l1_loss(far, fb.float())
+    (lref2 * gs).backward()
+    l2 = ops.l1_loss_bf16_fwd(fa, fb)
+    g2 = ops.l1_loss_bf16_bwd(fa, fb, gs)
+    d = _rand((4, 1, 16, 16), seed + 4).to(DEV)
+    dr = d.clone().requires_grad_(True)
+    lref3 = F.mse_loss(dr, torch.ones_like(dr))
+    (lref3 * gs).backward()
+    l3 = ops.mse_const_fwd(d, 1.0)
+    g3 = ops.mse_const_bwd(d, 1.0, gs)
+    torch.cuda.synchronize()
+    e = [abs(l1.item() - lref.item()) / lref.item(), rel_err(g1, ar.grad),
+         abs(l2.item() - lref2.item()) / lref2.item(), rel_err(g2, far.grad) / 100,  # grads ~1e-5 in bf16
+         abs(l3.item() - lref3.item()) / lref3.item(), rel_err(g3, dr.grad)]
+    return max(e), 1e-4
+
+
+def case_gram_l1(seed=0):
+    ops.ensure_init()
+    dim = 200
+    ga = _rand((dim, dim), seed).to(DEV)
+    gb = _rand((dim, dim), seed + 1).to(DEV)
+    loss, ssym = ops.gram_l1(ga, gb)
+    d = ga - gb
+    ref = d.abs().mean()
+    sref = torch.sign(d) + torch.sign(d).t()
+    torch.cuda.synchronize()
+    return max(abs(loss.item() - ref.item()) / ref.item(), (ssym.float() - sref).abs().max().item()), 1e-5
+
+
+def case_adam(seed=0):
+    """clip_grad_norm_(1.0) + Adam(betas 0.5/0.999) + EMA(0.995) over a flat buffer, 3 steps."""
+    ops.ensure_init()
+    n = 100003
+    p0 = _rand((n,), seed).to(DEV)
+    ref_p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([ref_p], lr=2e-4, betas=(0.5, 0.999))
+    ema_ref = p0.clone()
+    p = p0.clone()
+    m = torch.zeros(n, device=DEV)
+    v = torch.zeros(n, device=DEV)
+    ema = p0.clone()
+    ss = torch.zeros((), device=DEV)
+    for step in range(1, 4):
+        g = (_rand((n,), seed + 10 + step) * (0.02 if step == 2 else 1.0)).to(DEV)   # step 2: norm < 1, no clipping
+        ref_p.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([ref_p], 1.0)
+        opt.step()
+        ema_ref = ema_ref * 0.995 + (1 - 0.995) * ref_p.data
+        ops.sumsq(g, ss, accumulate=False)
+        ops.adam_step(p, g, m, v, ema, ss, 1.0, 1.0, 2e-4, 0.5, 0.999, 1e-8, step, 0.995)
+    torch.cuda.synchronize()
+    return max(rel_err(p, ref_p.data), rel_err(ema, ema_ref), ((p - ref_p.data).abs().max() / 2e-4).item() * 1e-2), 1e-5
+
+
+CASES = {
+    "gather_7x7_reflect": lambda: case_patch_gather(2, 3, 32, 40, 7, 1, 3, True),
+    "gather_4x4s2_zero": lambda: case_patch_gather(2, 3, 32, 32, 4, 2, 1, False),
+    "gather_3x3_affine": lambda: case_patch_gather(1, 3, 16, 24, 3, 1, 1, False, affine=True),
+    "gather_7x7_full_c3": lambda: case_patch_gather(1, 3, 20, 20, 7, 1, 6, False),
+    "gather_4x4_c16": lambda: case_patch_gather(2, 16, 16, 16, 4, 1, 1, False),
+    "scatter_7x7_reflect": lambda: case_patch_scatter(2, 3, 32, 40, 7, 1, 3, True),
+    "scatter_4x4s2_zero": lambda: case_patch_scatter(2, 3, 32, 32, 4, 2, 1, False),
+    "scatter_3x3_affine": lambda: case_patch_scatter(1, 3, 16, 24, 3, 1, 1, False, affine=True),
+    "reflect_pad": lambda: case_reflect_pad(2, 64, 24, 32, 3),
+    "in_relu_64": lambda: case_norm(2, 64, 32, 32, L.ACT_RELU, False, False),
+    "in_lrelu_512": lambda: case_norm(3, 512, 16, 16, L.ACT_LRELU, False, False),
+    "adain_relu_256": lambda: case_norm(2, 256, 32, 32, L.ACT_RELU, True, False),
+    "adain_res_256": lambda: case_norm(2, 256, 64, 64, L.ACT_NONE, True, True),
+    "in_relu_128_big": lambda: case_norm(1, 128, 128, 128, L.ACT_RELU, False, False),
+    "act_bwd_add": case_act_bwd,
+    "colsum": case_colsum,
+    "pool": case_pool,
+    "heads": case_heads,
+    "losses": case_losses,
+    "gram_l1": case_gram_l1,
+    "adam": case_adam,
+}
