@@ -271,3 +271,58 @@ def seeded_vgg_state(seed=1234):
     sd = {k: v.clone() for k, v in torchvision.models.vgg19(weights=None).features.state_dict().items()}
     torch.set_rng_state(st)
     return sd
+
+
+# ----------------------------------------------------------------------------- seeded init
+def _conv(sd, key, cin, cout, k, transposed=False):
+    m = (torch.nn.ConvTranspose2d if transposed else torch.nn.Conv2d)(cin, cout, k)
+    sd[key + ".weight"], sd[key + ".bias"] = m.weight.detach().clone(), m.bias.detach().clone()
+
+
+def init_generator(n_res=8, style_dim=256):
+    """Consumes the global RNG exactly like StyleCycleGANGenerator.__init__ (model.py:127-143):
+    PyTorch default inits in module-construction order."""
+    sd = {}
+    _conv(sd, "content_encoder.0", 3, 64, 7)
+    _conv(sd, "content_encoder.3", 64, 128, 4)
+    _conv(sd, "content_encoder.6", 128, 256, 4)
+    for i in range(n_res):
+        for j in (1, 2):
+            _conv(sd, f"decoder.{i}.conv{j}", 256, 256, 3)
+            lin = torch.nn.Linear(style_dim, 512)
+            sd[f"decoder.{i}.adain{j}.style_modulation.weight"] = lin.weight.detach().clone()
+            sd[f"decoder.{i}.adain{j}.style_modulation.bias"] = lin.bias.detach().clone()
+    _conv(sd, f"decoder.{n_res}", 256, 128, 4, transposed=True)
+    _conv(sd, f"decoder.{n_res + 3}", 128, 64, 4, transposed=True)
+    _conv(sd, f"decoder.{n_res + 6}", 64, 3, 7)
+    # state_dict order of the reference: per block conv1, adain1, conv2, adain2
+    return sd
+
+
+def init_style_encoder(num_domains, style_dim=256):
+    sd = {}
+    for i, (a, b) in zip((0, 2, 4, 6), ((3, 64), (64, 128), (128, 256), (256, 512))):
+        _conv(sd, f"shared_layers.{i}", a, b, 4)
+    for k in range(num_domains):
+        _conv(sd, f"domain_branches.{k}.0", 512, style_dim, 1)
+    return sd
+
+
+def init_discriminator(num_domains):
+    sd = {}
+    for i, (a, b) in zip((0, 2, 5, 8), ((3, 64), (64, 128), (128, 256), (256, 512))):
+        _conv(sd, f"shared_layers.{i}", a, b, 4)
+    for k in range(num_domains):
+        _conv(sd, f"domain_branches.{k}.1", 512, 1, 4)
+    return sd
+
+
+def init_state(seed, num_domains):
+    """All six networks in the construction order of trainer.py:31-40 after torch.manual_seed(seed)."""
+    torch.manual_seed(seed)
+    st = {"G_A2B": init_generator(), "G_B2A": init_generator()}
+    st["SE_A"] = init_style_encoder(num_domains)
+    st["SE_B"] = init_style_encoder(num_domains)
+    st["D_A"] = init_discriminator(num_domains)
+    st["D_B"] = init_discriminator(num_domains)
+    return st
