@@ -1,0 +1,264 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: one full G+D training step (trainer.train_step) at 256x256.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0). Contract fields: metric/value/unit (BASELINE.json's metric: train
+images/sec at 256^2), e2e (same metric through the public trainer API with pinned HOST batches and a
+device->host loss read every step), roofline (dominant kernel: the 3x3 256->256 tcgen05 implicit
+GEMM, timed live with CUDA events), cpu_baseline (the oracle port of the reference's CPU path timed
+on the host cores, bounded sample), clocks, gpu_launches.
+
+`--impl reference` times the reference's CPU implementation of the same step (the oracle port;
+/root/reference is not present on the GPU box) with all host threads on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S = 256
+ND = 10
+WORKLOAD = "full G+D training step 256x256 batch 32 per GPU (BASELINE.json configs[2]; configs[3] at 8 GPUs)"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "source": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+def step_flops(b, s=S):
+    """Necessary algorithmic FLOPs of one train step: s*(1641.7*B + 21.47*B^2) GF."""
+    sc = (s / 256.0) ** 2
+    return sc * (1641.7 * b + 21.47 * b * b) * 1e9
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi during the timed region."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.max_mhz, self.reasons = [], None, set()
+        self._stop = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0]))
+                self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=5)
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline(sample_steps=2, threads=None):
+    """The reference's CPU path (oracle port, fp32, all host threads) on a bounded sample: B=1, 256^2."""
+    import torch
+    from oracle import oracle as O
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    state = O.init_state(0, ND)
+    tr = O.OracleTrainer(state, O.seeded_vgg_state(), ND)
+    batch = O.synthetic_batch(1, S, ND)
+    tr.train_step(batch, 0)                      # warm-up
+    ts = []
+    for _ in range(sample_steps):
+        t0 = time.time()
+        tr.train_step(batch, 0)
+        ts.append(time.time() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return {"value": 1.0 / med, "unit": "images/sec", "cores": threads, "kind": "port",
+            "sample": f"oracle port of trainer.train_step, B=1 256x256 nd={ND}, fp32, 1 warm-up + {sample_steps} timed steps "
+                      f"(median {med:.2f} s/step, min {ts[0]:.2f})"}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    state = O.init_state(0, ND)
+    tr = O.OracleTrainer(state, O.seeded_vgg_state(), ND)
+    batch = O.synthetic_batch(1, S, ND)
+    for _ in range(max(args.warmup, 0)):
+        tr.train_step(batch, 0)
+    t0 = time.time()
+    for _ in range(args.steps):
+        tr.train_step(batch, 0)
+    dt = time.time() - t0
+    v = args.steps * 1.0 / dt
+    line = {"impl": "reference", "metric": "train images/sec at 256^2", "value": v, "unit": "images/sec",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": "each step = B=1 256x256 train_step on the host CPU",
+                       "num_domains": ND},
+            "cpu_baseline": {"value": v, "unit": "images/sec", "cores": threads, "kind": "port",
+                             "sample": f"B=1 256x256 train_step x {args.steps} (oracle port of the reference CPU path)"},
+            "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def time_dominant_kernel(torch, ops, L, batch, iters=20):
+    """The dominant kernel: 3x3 s1 p1 256->256 implicit GEMM at 64x64 (80% of generator FLOPs)."""
+    dev = torch.device("cuda")
+    x = torch.randn(batch, 64, 64, 256, device=dev).to(torch.bfloat16)
+    w = torch.randn(256, 256, 3, 3, device=dev) * 0.02
+    wpk = ops.wpack(L.WPACK_FWD, w, 256, 256, 3, 3)
+    g = ops.conv_geom(batch, 64, 64, 256, 256, 3, 3, 1, 1, 1, 64, 64)
+    y = torch.empty(batch, 64, 64, 256, device=dev, dtype=torch.bfloat16)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > L2 (126 MB)
+    for _ in range(3):
+        ops.conv2d_fwd(x, wpk, g, out=y)
+    total = 0.0
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.conv2d_fwd(x, wpk, g, out=y)
+        e1.record()
+        e1.synchronize()
+        total += e0.elapsed_time(e1)
+    ms = total / iters
+    flops = 2.0 * batch * 4096 * 256 * 2304
+    return ms, flops
+
+
+def run_ours(args):
+    import torch
+    import msig_b200  # noqa: F401
+    from msig_b200 import lib as L
+    from msig_b200 import ops
+    from msig_b200 import trainer as T
+    from oracle import oracle as O   # only for cpu_baseline and the seeded synthetic batch / VGG weights
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    pk = peaks()
+
+    torch.manual_seed(0)
+    tr = T.MultiDomainStyleCycleGAN(dev, 200, 2e-4, 1e-4, dict(O.DEFAULT_LOSS_WEIGHTS), ND, vgg_state=O.seeded_vgg_state())
+    gb = O.synthetic_batch(B * world, S, ND)
+    host = {k: v[rank * B:(rank + 1) * B].contiguous().pin_memory() for k, v in gb.items()}
+    devb = {k: v.to(dev) for k, v in host.items()}
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        out = tr.train_step(devb, 0)
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    # ---- device-timed region: inputs resident in HBM
+    l0 = ops.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        out = tr.train_step(devb, 0)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.kernel_launches() - l0
+    # ---- end to end: pinned host batch in, loss scalar out, every step
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        out = tr.train_step(host, 0)
+        _ = float(out["G_loss"])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop() if sampler else None
+    t = torch.tensor([ms, e2e_s * 1000.0], device=dev, dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            torch.distributed.destroy_process_group()
+        return
+    value = B * world * args.steps / (ms / 1000.0)
+    e2e = B * world * args.steps / (e2e_ms / 1000.0)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    kms, kflops = time_dominant_kernel(torch, ops, L, B)
+    ach = kflops / (kms * 1e-3) / 1e12
+    step_tf = step_flops(B) / (ms / args.steps * 1e-3) / 1e12
+    line = {
+        "metric": "train images/sec at 256^2", "value": value, "unit": "images/sec", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "image": S, "num_domains": ND,
+                   "parallelism": f"dp{world}", "l2": "working set >> L2 (tens of GB of activations per step)",
+                   "accumulate": "fp32", "loss_epoch": 0},
+        "e2e": {"value": e2e, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": ach / pk["bf16_burst"],
+                     "traffic": None, "kernel": "fprop_kernel<256> conv3x3 256->256 @64x64, batch %d" % B,
+                     "kernel_ms": kms, "peak_source": pk["source"] + " (burst, kernel timed alone, L2 flushed)"},
+        "step_tflops": {"achieved": step_tf, "peak_sustained": pk["bf16_sustained"], "frac": step_tf / pk["bf16_sustained"],
+                        "flops_per_step": step_flops(B), "note": "necessary algorithmic FLOPs (SURVEY 8d) / step time"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

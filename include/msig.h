@@ -126,6 +126,19 @@ int msig_patch_scatter(const msig_patch_geom* g, const void* dpatches, const flo
 /* wgrad for a gathered-patch GEMM: dw (OIHW fp32, o x c x r x s) (+)= dy^T * patches.
  * `flip`=1 is the MSIG_WPACK_IM2COL_FLIP arrangement (patches gathered from dy, `other` = input). */
 size_t msig_patch_wgrad_workspace(int64_t rows, int32_t m, int32_t ncols);
+/* Two-step form for weights stored as several master tensors (per-domain heads model.py:84,183;
+ * the 16 AdaIN Linears model.py:18): one GEMM  partial[split][m][ncols] = a^T b  into the
+ * workspace, then one msig_wgrad_unpack per master tensor. */
+int msig_gemm_tn_partial(int64_t rows, const void* a_rows_m, int32_t m, const void* b_rows_n, int32_t ncols,
+                         void* workspace, size_t workspace_bytes, int32_t* splits_out, void* stream);
+int msig_wgrad_unpack(const msig_wpack_desc* d, int32_t oc, int32_t o_off, const float* partial,
+                      int32_t splits, int64_t split_stride, float* dw, int accumulate, void* stream);
+size_t msig_wpack_part_elems(const msig_wpack_desc* d, int32_t oc);
+int msig_wpack_part(const msig_wpack_desc* d, int32_t oc, int32_t o_off, const float* w, void* packed,
+                    void* stream);
+int msig_patch_wgrad_part(const msig_wpack_desc* d, int32_t oc, int32_t o_off, int64_t rows,
+                          const void* a_rows_m, int32_t m, const void* b_rows_n, int32_t ncols, float* dw,
+                          int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 int msig_patch_wgrad(const msig_wpack_desc* d, int64_t rows, const void* a_rows_m, const void* b_rows_n,
                      float* dw, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
@@ -182,8 +195,8 @@ int msig_f32_to_bf16(const float* x, int64_t numel, void* y, void* stream);
 int msig_bf16_to_f32(const void* x, int64_t numel, float* y, void* stream);
 int msig_tanh_bwd(const float* dy, const float* y, int64_t numel, float* dz, void* stream);
 /* sum over (n, h, w) of an fp32 NCHW tensor per channel (bias grad of the final conv) */
-int msig_nchw_chansum(const float* x, int32_t n, int32_t c, int64_t hw, float* out, int accumulate,
-                      void* stream);
+int msig_nchw_chansum(const float* x, int32_t n, int32_t c, int64_t hw, int64_t img_stride, float* out,
+                      int accumulate, void* stream);   /* img_stride: elements between images (c*hw if dense) */
 
 /* ---- losses (trainer.py:50-52, losses.py:70-98) ---------------------------------------------
  * Forward kernels write the mean-reduced loss (fp32 device scalar). Backward kernels write
@@ -204,13 +217,15 @@ size_t msig_gram_workspace(int32_t n, int32_t h, int32_t w, int32_t c);
 int msig_gram_fwd(const void* f, int32_t n, int32_t h, int32_t w, int32_t c, float* gram,
                   void* workspace, size_t workspace_bytes, void* stream);
 /* loss = mean |G_a - G_b|; ssym (bf16 [dim][dim]) = sign(D) + sign(D)^T, D = G_a - G_b. */
-int msig_gram_l1(const float* ga, const float* gb, int32_t dim, float* loss, void* ssym, void* stream);
+int msig_gram_l1(const float* ga, const float* gb, int32_t dim, float* loss, int accumulate, void* ssym,
+                 void* stream);   /* accumulate=1: loss += (sum over the five taps, losses.py:84-89) */
 /* df = alpha * (*gscale) * ssym * F (+ aux): gradient of the style term w.r.t. the generated
  * features; alpha = 1 / (dim^2 * n*c*h*w) supplied by the caller. */
 int msig_gram_bwd(const void* f, const void* ssym, int32_t n, int32_t h, int32_t w, int32_t c,
                   float alpha, const float* gscale, const void* aux, void* df, void* stream);
 /* column sums of an fp32 [rows][c] matrix (bias gradients of the fp32 heads / style Linear) */
-int msig_colsum_f32(const float* x, int64_t rows, int32_t c, float* out, int accumulate, void* stream);
+int msig_colsum_f32(const float* x, int64_t rows, int32_t c, int64_t ld, float* out, int accumulate,
+                    void* stream);   /* ld: elements between rows */
 
 /* ---- optimizer-side multi-tensor ops on flat fp32 buffers (trainer.py:127-134,152-153;
  *      utils.py:80-91): global grad-norm clip + Adam + EMA + in one pass ------------------- */

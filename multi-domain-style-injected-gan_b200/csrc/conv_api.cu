@@ -597,14 +597,12 @@ size_t msig_patch_wgrad_workspace(int64_t rows, int32_t m, int32_t ncols) {
   return wgrad_ws_bytes(m, ncols, 1, ceil_div(rows, 64));
 }
 
-int msig_patch_wgrad_part(const msig_wpack_desc* d, int32_t oc, int32_t o_off, int64_t rows,
-                          const void* a_rows_m, int32_t m, const void* b_rows_n, int32_t ncols, float* dw,
-                          int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
-  MSIG_REQUIRE(d && a_rows_m && b_rows_n && dw && workspace, "msig_patch_wgrad: null argument");
+int msig_gemm_tn_partial(int64_t rows, const void* a_rows_m, int32_t m, const void* b_rows_n, int32_t ncols,
+                         void* workspace, size_t workspace_bytes, int32_t* splits_out, void* stream) {
+  MSIG_REQUIRE(a_rows_m && b_rows_n && workspace && splits_out, "msig_gemm_tn_partial: null argument");
   MSIG_REQUIRE(context_ready(), "msig_init() has not been called");
-  MSIG_REQUIRE(m % 64 == 0 && ncols % 64 == 0, "patch wgrad: m (%d) and ncols (%d) must be multiples of 64", m, ncols);
+  MSIG_REQUIRE(m % 64 == 0 && ncols % 64 == 0, "gemm_tn: m (%d) and ncols (%d) must be multiples of 64", m, ncols);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  PackGeom pg = make_pack_geom(d, oc, o_off);
   WgradParams p;
   memset(&p, 0, sizeof(p));
   p.PW = 64; p.PH = 1;
@@ -615,7 +613,7 @@ int msig_patch_wgrad_part(const msig_wpack_desc* d, int32_t oc, int32_t o_off, i
   const int64_t kb_total = p.blocks_w;
   WgradPlan pl = plan_wgrad(m, ncols, 1, kb_total);
   const size_t need = size_t(pl.splits) * size_t(m) * ncols * sizeof(float);
-  MSIG_REQUIRE(workspace_bytes >= need, "patch wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
+  MSIG_REQUIRE(workspace_bytes >= need, "gemm_tn: workspace too small (%zu < %zu)", workspace_bytes, need);
   p.m_blocks = pl.m_blocks; p.n_blocks = pl.n_blocks; p.splits = pl.splits;
   p.kb_per_split = pl.kb_per_split; p.kb_total = pl.kb_total;
   p.out = reinterpret_cast<float*>(workspace);
@@ -628,13 +626,36 @@ int msig_patch_wgrad_part(const msig_wpack_desc* d, int32_t oc, int32_t o_off, i
   if ((rc = make_act_map(&p.tmB[0], vb, 64, 1)) != MSIG_OK) return rc;
   for (int i = 1; i < 4; ++i) { p.tmA[i] = p.tmA[0]; p.tmB[i] = p.tmB[0]; }
   cudaError_t ce = launch_wgrad(p, pl.block_n, st);
-  if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "patch wgrad launch: %s", cudaGetErrorString(ce));
-  // partial layouts: IM2COL [O][Kpad] (a = dy, b = patches); IM2COL_FLIP [Kpad][I] (a = patches, b = x);
-  // FWD with r=s=1 [O][I] (Linear).
+  if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "gemm_tn launch: %s", cudaGetErrorString(ce));
+  *splits_out = pl.splits;
+  return MSIG_OK;
+}
+
+// partial layouts: IM2COL [O][Kpad] (a = dy, b = patches); IM2COL_FLIP [Kpad][I] (a = patches of dy,
+// b = x); FWD with r=s=1 [O][I] (Linear; a = dy, b = x).
+int msig_wgrad_unpack(const msig_wpack_desc* d, int32_t oc, int32_t o_off, const float* partial,
+                      int32_t splits, int64_t split_stride, float* dw, int accumulate, void* stream) {
+  MSIG_REQUIRE(d && partial && dw && splits >= 1, "msig_wgrad_unpack: bad argument");
+  PackGeom pg = make_pack_geom(d, oc, o_off);
+  MSIG_REQUIRE(pg.kind == MSIG_WPACK_FWD || pg.kind == MSIG_WPACK_IM2COL || pg.kind == MSIG_WPACK_IM2COL_FLIP ||
+                   pg.kind == MSIG_WPACK_CONVT_FWD,
+               "msig_wgrad_unpack: kind %d has no weight-gradient layout", pg.kind);
+  return launch_wgrad_reduce(pg, partial, splits, split_stride, dw, accumulate, static_cast<cudaStream_t>(stream));
+}
+
+int msig_patch_wgrad_part(const msig_wpack_desc* d, int32_t oc, int32_t o_off, int64_t rows,
+                          const void* a_rows_m, int32_t m, const void* b_rows_n, int32_t ncols, float* dw,
+                          int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  MSIG_REQUIRE(d && dw, "msig_patch_wgrad: null argument");
+  PackGeom pg = make_pack_geom(d, oc, o_off);
   if (pg.kind == MSIG_WPACK_IM2COL) MSIG_REQUIRE(ncols == pg.Kpad && m >= pg.O, "patch wgrad: IM2COL shape mismatch");
-  if (pg.kind == MSIG_WPACK_IM2COL_FLIP) MSIG_REQUIRE(m >= pg.Kpad - 63 && ncols == pg.I, "patch wgrad: FLIP shape mismatch");
+  if (pg.kind == MSIG_WPACK_IM2COL_FLIP) MSIG_REQUIRE(m == pg.Kpad && ncols == pg.I, "patch wgrad: FLIP shape mismatch");
   if (pg.kind == MSIG_WPACK_FWD) MSIG_REQUIRE(pg.RS == 1 && ncols == pg.I, "patch wgrad: FWD needs r=s=1");
-  return launch_wgrad_reduce(pg, p.out, pl.splits, p.o_split, dw, accumulate, st);
+  int32_t splits = 0;
+  int rc = msig_gemm_tn_partial(rows, a_rows_m, m, b_rows_n, ncols, workspace, workspace_bytes, &splits, stream);
+  if (rc != MSIG_OK) return rc;
+  return msig_wgrad_unpack(d, oc, o_off, reinterpret_cast<const float*>(workspace), splits, int64_t(m) * ncols,
+                           dw, accumulate, stream);
 }
 
 int msig_patch_wgrad(const msig_wpack_desc* d, int64_t rows, const void* a_rows_m, const void* b_rows_n,

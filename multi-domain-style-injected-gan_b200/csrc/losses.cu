@@ -141,12 +141,12 @@ __global__ void gram_l1_kernel(const float* __restrict__ ga, const float* __rest
   }
 }
 
-__global__ void colsum_f32_kernel(const float* __restrict__ x, int64_t rows, int c, float* __restrict__ out,
-                                  int accumulate) {
+__global__ void colsum_f32_kernel(const float* __restrict__ x, int64_t rows, int c, int64_t ld,
+                                  float* __restrict__ out, int accumulate) {
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   float s = 0.f;
-  for (int64_t r = 0; r < rows; ++r) s += x[r * c + ch];
+  for (int64_t r = 0; r < rows; ++r) s += x[r * ld + ch];
   out[ch] = accumulate ? out[ch] + s : s;
 }
 
@@ -245,9 +245,10 @@ int msig_mse_const_bwd(const float* a, float target, int64_t numel, const float*
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
 }
-int msig_gram_l1(const float* ga, const float* gb, int32_t dim, float* loss, void* ssym, void* stream) {
+int msig_gram_l1(const float* ga, const float* gb, int32_t dim, float* loss, int accumulate, void* ssym,
+                 void* stream) {
   MSIG_REQUIRE(ga && gb && loss && ssym && dim > 0, "msig_gram_l1: bad argument");
-  MSIG_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), ST(stream)));
+  if (!accumulate) MSIG_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), ST(stream)));
   const unsigned t = static_cast<unsigned>(ceil_div(dim, 32));
   gram_l1_kernel<<<dim3(t, t), dim3(32, 8), 0, ST(stream)>>>(ga, gb, dim, 1.f / (float(dim) * float(dim)), loss,
                                                              BF(ssym));
@@ -255,9 +256,10 @@ int msig_gram_l1(const float* ga, const float* gb, int32_t dim, float* loss, voi
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
 }
-int msig_colsum_f32(const float* x, int64_t rows, int32_t c, float* out, int accumulate, void* stream) {
+int msig_colsum_f32(const float* x, int64_t rows, int32_t c, int64_t ld, float* out, int accumulate,
+                    void* stream) {
   MSIG_REQUIRE(x && out && c > 0, "msig_colsum_f32: bad argument");
-  colsum_f32_kernel<<<static_cast<unsigned>(ceil_div(c, 128)), 128, 0, ST(stream)>>>(x, rows, c, out, accumulate);
+  colsum_f32_kernel<<<static_cast<unsigned>(ceil_div(c, 128)), 128, 0, ST(stream)>>>(x, rows, c, ld, out, accumulate);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;

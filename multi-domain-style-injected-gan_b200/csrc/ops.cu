@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 }
 
 __global__ void nchw_chansum_kernel(const float* __restrict__ x, int n, int c, int64_t hw,
-                                    float* __restrict__ out) {
+                                    int64_t img_stride, float* __restrict__ out) {
   // grid (blocks, c): each block reduces a slice of (n, hw) for channel blockIdx.y
   const int ch = blockIdx.y;
   const int64_t total = int64_t(n) * hw;
@@ -467,7 +467,7 @@ __global__ void nchw_chansum_kernel(const float* __restrict__ x, int n, int c, i
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total;
        i += int64_t(gridDim.x) * blockDim.x) {
     const int64_t img = i / hw, p = i - img * hw;
-    s += x[(img * c + ch) * hw + p];
+    s += x[img * img_stride + ch * hw + p];
   }
   s = warp_sum(s);
   __shared__ float ws[8];
@@ -781,11 +781,12 @@ int msig_colsum(const void* dy, int64_t rows, int32_t c, float* db, int accumula
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
 }
-int msig_nchw_chansum(const float* x, int32_t n, int32_t c, int64_t hw, float* out, int accumulate, void* stream) {
+int msig_nchw_chansum(const float* x, int32_t n, int32_t c, int64_t hw, int64_t img_stride, float* out,
+                      int accumulate, void* stream) {
   MSIG_REQUIRE(x && out, "msig_nchw_chansum: null argument");
   if (!accumulate) MSIG_CHECK_CUDA(cudaMemsetAsync(out, 0, size_t(c) * sizeof(float), ST(stream)));
   const int blocks = grid_for(int64_t(n) * hw, 256, 256);
-  nchw_chansum_kernel<<<dim3(blocks, c), 256, 0, ST(stream)>>>(x, n, c, hw, out);
+  nchw_chansum_kernel<<<dim3(blocks, c), 256, 0, ST(stream)>>>(x, n, c, hw, img_stride, out);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;

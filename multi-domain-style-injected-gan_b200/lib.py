@@ -78,8 +78,10 @@ _SIGS = {
     "msig_act_bwd": (c_int, [_P, _P, c_int32, c_float, c_int64, _P, _P]),
     "msig_add_bf16": (c_int, [_P, _P, c_int64, _P, _P]),
     "msig_colsum": (c_int, [_P, c_int64, c_int32, _P, c_int, _P]),
-    "msig_colsum_f32": (c_int, [_P, c_int64, c_int32, _P, c_int, _P]),
-    "msig_nchw_chansum": (c_int, [_P, c_int32, c_int32, c_int64, _P, c_int, _P]),
+    "msig_colsum_f32": (c_int, [_P, c_int64, c_int32, c_int64, _P, c_int, _P]),
+    "msig_nchw_chansum": (c_int, [_P, c_int32, c_int32, c_int64, c_int64, _P, c_int, _P]),
+    "msig_gemm_tn_partial": (c_int, [c_int64, _P, c_int32, _P, c_int32, _P, c_size_t, POINTER(c_int32), _P]),
+    "msig_wgrad_unpack": (c_int, [POINTER(WpackDesc), c_int32, c_int32, _P, c_int32, c_int64, _P, c_int, _P]),
     "msig_maxpool2_fwd": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "msig_maxpool2_bwd": (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "msig_avgpool_fwd": (c_int, [_P, c_int32, c_int32, c_int32, _P, _P]),
@@ -97,7 +99,7 @@ _SIGS = {
     "msig_mse_const_bwd": (c_int, [_P, c_float, c_int64, _P, _P, _P]),
     "msig_gram_workspace": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "msig_gram_fwd": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, _P, _P, c_size_t, _P]),
-    "msig_gram_l1": (c_int, [_P, _P, c_int32, _P, _P, _P]),
+    "msig_gram_l1": (c_int, [_P, _P, c_int32, _P, c_int, _P, _P]),
     "msig_gram_bwd": (c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P, _P, _P]),
     "msig_sumsq": (c_int, [_P, c_int64, _P, c_int, _P]),
     "msig_adam_step": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float,

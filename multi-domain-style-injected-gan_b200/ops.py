@@ -232,13 +232,37 @@ def colsum(dy2d_rows, c, db, accumulate=True, rows=None):
     L.call("msig_colsum", _p(dy2d_rows), rows, c, _p(db), int(accumulate), _stream())
 
 
-def colsum_f32(x, rows, c, out, accumulate=True):
-    L.call("msig_colsum_f32", _p(x), rows, c, _p(out), int(accumulate), _stream())
+def colsum_f32(x, rows, c, out, accumulate=True, ld=None, offset=0):
+    """out[c] (+)= column sums of the fp32 matrix starting `offset` elements into x, row stride ld."""
+    ptr = ctypes.c_void_p(x.data_ptr() + 4 * offset)
+    L.call("msig_colsum_f32", ptr, rows, c, c if ld is None else ld, _p(out), int(accumulate), _stream())
 
 
-def nchw_chansum(x, out, accumulate=True):
-    n, c, h, w = x.shape
-    L.call("msig_nchw_chansum", _p(x), n, c, h * w, _p(out), int(accumulate), _stream())
+def nchw_chansum(x, out, accumulate=True, n=None, c=None, hw=None, img_stride=None, offset=0):
+    if n is None:
+        n, c, h, w = x.shape
+        hw = h * w
+    ptr = ctypes.c_void_p(x.data_ptr() + 4 * offset)
+    L.call("msig_nchw_chansum", ptr, n, c, hw, c * hw if img_stride is None else img_stride, _p(out),
+           int(accumulate), _stream())
+
+
+def gemm_tn_partial(rows, a, m, b, ncols):
+    """partial[split][m][ncols] = a^T b in the stream workspace; returns (workspace, splits)."""
+    nbytes = L.load().msig_patch_wgrad_workspace(rows, m, ncols)
+    ws = workspace(nbytes, a.device)
+    splits = ctypes.c_int32(0)
+    L.call("msig_gemm_tn_partial", rows, _p(a), m, _p(b), ncols, _p(ws), ws.numel(), ctypes.byref(splits),
+           _stream())
+    return ws, splits.value
+
+
+def wgrad_unpack(kind, o, i, r, s, ws, splits, split_stride, dw, accumulate=True, oc=0, o_off=0,
+                 partial_offset=0):
+    d = WpackDesc(kind, o, i, r, s)
+    ptr = ctypes.c_void_p(ws.data_ptr() + 4 * partial_offset)
+    L.call("msig_wgrad_unpack", ctypes.byref(d), oc, o_off, ptr, splits, split_stride, _p(dw),
+           int(accumulate), _stream())
 
 
 def maxpool2_fwd(x):
@@ -354,11 +378,14 @@ def gram_fwd(f):
     return gram
 
 
-def gram_l1(ga, gb):
+def gram_l1(ga, gb, loss=None):
+    """loss (+)= mean|ga - gb| (accumulates when `loss` is given); returns (loss, ssym)."""
     dim = ga.shape[0]
-    loss = _scalar(ga.device)
+    acc = loss is not None
+    if loss is None:
+        loss = _scalar(ga.device)
     ssym = torch.empty((dim, dim), dtype=BF16, device=ga.device)
-    L.call("msig_gram_l1", _p(ga), _p(gb), dim, _p(loss), _p(ssym), _stream())
+    L.call("msig_gram_l1", _p(ga), _p(gb), dim, _p(loss), int(acc), _p(ssym), _stream())
     return loss, ssym
 
 

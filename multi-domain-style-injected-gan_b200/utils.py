@@ -1,0 +1,172 @@
+"""Mirror of the hot-path-adjacent parts of the reference's utils.py: EMA (utils.py:71-91) and
+DynamicWeightScheduler (utils.py:94-134), plus the flat parameter / gradient buffers and the fused
+clip + Adam + EMA optimizer the trainer uses (trainer.py:56-65,127-134,152-153).
+
+Image-grid / plotting helpers of the reference (utils.py:9-68,136-155) are out of scope."""
+import math
+
+import torch
+
+from . import ops
+
+F32 = torch.float32
+_ALIGN = 64   # floats; keeps every parameter 256-byte aligned inside the flat buffers
+
+
+class FlatParams:
+    """Re-homes the parameters of several modules into ONE fp32 buffer (and their gradients into
+    another), in `module.parameters()` order, so that gradient all-reduce, global-norm clipping,
+    Adam and EMA each touch one contiguous buffer. Parameter tensors stay ordinary views:
+    state_dict() / load_state_dict() / checkpoints are unaffected."""
+
+    def __init__(self, modules, device):
+        self.modules = list(modules)
+        self.params = [p for m in self.modules for p in m.parameters()]
+        self.offsets = []
+        off = 0
+        for p in self.params:
+            self.offsets.append(off)
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.numel = off
+        self.data = torch.zeros(off, dtype=F32, device=device)
+        self.grad = torch.zeros(off, dtype=F32, device=device)
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                n = p.numel()
+                self.data[o:o + n].copy_(p.detach().reshape(-1))
+                p.data = self.data[o:o + n].view(p.shape)
+                p.grad = self.grad[o:o + n].view(p.shape)
+        for m in self.modules:
+            if hasattr(m, "mark_weights_dirty"):
+                m.mark_weights_dirty()
+
+    def views_of(self, flat):
+        return [flat[o:o + p.numel()].view(p.shape) for p, o in zip(self.params, self.offsets)]
+
+    def rebind_grads(self):
+        for p, o in zip(self.params, self.offsets):
+            p.grad = self.grad[o:o + p.numel()].view(p.shape)
+
+    def mark_dirty(self):
+        for m in self.modules:
+            if hasattr(m, "mark_weights_dirty"):
+                m.mark_weights_dirty()
+
+
+class FusedAdam(torch.optim.Optimizer):
+    """torch.optim.Adam(betas, eps) semantics (no weight decay / amsgrad) over a FlatParams buffer,
+    fused with clip_grad_norm_(max_norm) and the EMA update in one pass over memory
+    (msig_sumsq + msig_adam_step). `param_groups[0]['lr']` is honoured, so torch LR schedulers
+    (CosineAnnealingLR, trainer.py:64-65) work unchanged; state_dict() uses Adam's layout."""
+
+    def __init__(self, flat, lr, betas=(0.5, 0.999), eps=1e-8, ema_flat=None, ema_beta=0.995):
+        super().__init__(flat.params, dict(lr=lr, betas=betas, eps=eps))
+        self.flat = flat
+        self.ema_flat = ema_flat
+        self.ema_beta = ema_beta
+        self.exp_avg = torch.zeros_like(flat.data)
+        self.exp_avg_sq = torch.zeros_like(flat.data)
+        self.grad_sumsq = torch.zeros((), dtype=F32, device=flat.data.device)
+        self.step_count = 0
+        m_views, v_views = flat.views_of(self.exp_avg), flat.views_of(self.exp_avg_sq)
+        for p, m, v in zip(flat.params, m_views, v_views):
+            self.state[p] = {"step": torch.tensor(0.0), "exp_avg": m, "exp_avg_sq": v}
+
+    def zero_grad(self, set_to_none=False):
+        self.flat.grad.zero_()
+        self.flat.rebind_grads()
+
+    @torch.no_grad()
+    def step(self, closure=None, max_norm=None, grad_scale=1.0):
+        g = self.param_groups[0]
+        self.step_count += 1
+        use_clip = max_norm is not None and max_norm > 0
+        if use_clip:
+            ops.sumsq(self.flat.grad, self.grad_sumsq, accumulate=False)
+        ops.adam_step(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq,
+                      None if self.ema_flat is None else self.ema_flat.data,
+                      self.grad_sumsq if use_clip else None, max_norm if use_clip else 0.0, grad_scale,
+                      g["lr"], g["betas"][0], g["betas"][1], g["eps"], self.step_count, self.ema_beta)
+        self.flat.mark_dirty()
+        if self.ema_flat is not None:
+            self.ema_flat.mark_dirty()
+
+    def state_dict(self):
+        for st in self.state.values():
+            st["step"] = torch.tensor(float(self.step_count))
+        return super().state_dict()
+
+    def grad_norm(self):
+        """Pre-clip global gradient norm of the last step (device scalar)."""
+        return torch.sqrt(self.grad_sumsq)
+
+    def load_state_dict(self, state_dict):
+        # copy into the flat-backed state instead of replacing the tensors
+        groups = state_dict["param_groups"]
+        for g, sg in zip(self.param_groups, groups):
+            for k in ("lr", "betas", "eps", "initial_lr"):
+                if k in sg:
+                    g[k] = sg[k]
+        ids = [i for sg in groups for i in sg["params"]]
+        steps = []
+        for i, p in zip(ids, self.flat.params):
+            st = state_dict["state"].get(i)
+            if st is None:
+                continue
+            self.state[p]["exp_avg"].copy_(st["exp_avg"])
+            self.state[p]["exp_avg_sq"].copy_(st["exp_avg_sq"])
+            steps.append(int(float(st["step"])))
+        if steps:
+            self.step_count = max(steps)
+
+
+class EMA:
+    """Exponential moving average of model parameters (reference utils.py:71-91). The trainer folds
+    this update into the fused optimizer pass; this class keeps the reference's stand-alone API."""
+
+    def __init__(self, beta):
+        self.beta = beta
+
+    @torch.no_grad()
+    def update_model_average(self, ma_model, current_model):
+        for cur, ma in zip(current_model.parameters(), ma_model.parameters()):
+            ma.data.mul_(self.beta).add_(cur.data, alpha=1 - self.beta)
+        if hasattr(ma_model, "mark_weights_dirty"):
+            ma_model.mark_weights_dirty()
+
+    def update_average(self, old, new):
+        if old is None:
+            return new
+        return old * self.beta + (1 - self.beta) * new
+
+
+class DynamicWeightScheduler:
+    """Warm-up x cosine-decay loss weights (reference utils.py:94-134). The weights depend on the
+    epoch only; the reference's per-step `.item()` host syncs (utils.py:114) are replaced by keeping
+    the detached device scalars, materialised on demand through `loss_history_values()`."""
+
+    def __init__(self, init_weights, warmup_epochs=10, decay_epochs=100, total_epochs=200):
+        self.init_weights = init_weights
+        self.current_weights = init_weights.copy()
+        self.warmup_epochs = warmup_epochs
+        self.decay_end_epoch = warmup_epochs + decay_epochs
+        self.total_epochs = total_epochs
+        self.loss_history = {k: [] for k in init_weights.keys()}
+        self.weight_history = {k: [] for k in init_weights.keys()}
+
+    def get_current_weights(self, epoch, current_losses):
+        for k, v in current_losses.items():
+            if k in self.loss_history:
+                self.loss_history[k].append(v.detach() if hasattr(v, "detach") else v)
+        warmup_factor = min(1.0, (epoch + 1) / self.warmup_epochs)
+        decay_factor = 1.0
+        if epoch >= self.warmup_epochs:
+            progress = min(1.0, (epoch - self.warmup_epochs) / (self.decay_end_epoch - self.warmup_epochs))
+            decay_factor = 0.1 + 0.9 * 0.5 * (1 + math.cos(math.pi * progress))
+        for k in self.current_weights.keys():
+            self.current_weights[k] = self.init_weights[k] * warmup_factor * decay_factor
+            self.weight_history[k].append(self.current_weights[k])
+        return self.current_weights
+
+    def loss_history_values(self):
+        return {k: [float(x) for x in v] for k, v in self.loss_history.items()}

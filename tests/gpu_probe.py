@@ -14,19 +14,37 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 
+def _fmt(v):
+    if isinstance(v, float):
+        return round(v, 6)
+    if isinstance(v, (tuple, list)):
+        return [_fmt(x) for x in v]
+    if isinstance(v, dict):
+        return {k: _fmt(x) for k, x in v.items()}
+    return v
+
+
 def run_one(name):
     import torch  # noqa: F401
     cases = all_cases()
     t0 = time.time()
-    err, tol = cases[name]()
-    print(json.dumps({"case": name, "err": err, "tol": tol, "ok": bool(err <= tol), "s": round(time.time() - t0, 2)}))
+    r = cases[name]()
+    if isinstance(r[0], dict):     # network-level case: (details, ok)
+        rec = {"case": name, "ok": bool(r[1]), "s": round(time.time() - t0, 2)}
+        rec.update({k: _fmt(v) for k, v in r[0].items()})
+    else:
+        err, tol = r
+        rec = {"case": name, "err": err, "tol": tol, "ok": bool(err <= tol), "s": round(time.time() - t0, 2)}
+    print(json.dumps(rec))
 
 
 def all_cases():
     import igemm_cases
     import ops_cases
+    import net_cases
     d = dict(igemm_cases.CASES)
     d.update(ops_cases.CASES)
+    d.update(net_cases.CASES)
     return d
 
 
@@ -41,12 +59,12 @@ def main():
     nfail = 0
     for n in names:
         try:
-            r = subprocess.run([sys.executable, __file__, "--one", n], capture_output=True, text=True, timeout=180)
+            r = subprocess.run([sys.executable, __file__, "--one", n], capture_output=True, text=True, timeout=600)
             line = [l for l in r.stdout.splitlines() if l.startswith("{")]
             if r.returncode == 0 and line:
                 rec = json.loads(line[-1])
             else:
-                rec = {"case": n, "ok": False, "rc": r.returncode, "stderr": r.stderr[-600:]}
+                rec = {"case": n, "ok": False, "rc": r.returncode, "stderr": r.stderr[-1500:]}
         except subprocess.TimeoutExpired:
             rec = {"case": n, "ok": False, "timeout": True}
         nfail += 0 if rec.get("ok") else 1
