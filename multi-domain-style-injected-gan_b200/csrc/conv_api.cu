@@ -23,6 +23,7 @@ __host__ __device__ inline void r_to_ph(int r, int& py, int& ty) {
 struct PackGeom {
   int kind, O, I, R, S, OC, OOFF;
   int RS, Ipad, Opad, Kpad;
+  int partT;   // wgrad partials stored [I][RS][O] instead of [O][RS][I]
 };
 
 static PackGeom make_pack_geom(const msig_wpack_desc* d, int oc, int ooff) {
@@ -30,6 +31,7 @@ static PackGeom make_pack_geom(const msig_wpack_desc* d, int oc, int ooff) {
   g.kind = d->kind; g.O = d->o; g.I = d->i; g.R = d->r; g.S = d->s;
   g.OC = oc > 0 ? oc : d->o;
   g.OOFF = ooff;
+  g.partT = 0;
   g.RS = g.R * g.S;
   g.Ipad = pad_rows(g.I);
   g.Opad = pad_rows(g.OC);
@@ -106,7 +108,8 @@ __global__ void wpack_kernel(PackGeom g, const float* __restrict__ w, __nv_bfloa
 //   IM2COL       [O][Kpad]             IM2COL_FLIP   [Kpad][I]
 __device__ __forceinline__ int64_t partial_offset(const PackGeom& g, int o, int i, int t) {
   switch (g.kind) {
-    case MSIG_WPACK_FWD: return (int64_t(o) * g.RS + t) * g.I + i;
+    case MSIG_WPACK_FWD:
+      return g.partT ? (int64_t(i) * g.RS + t) * g.O + o : (int64_t(o) * g.RS + t) * g.I + i;
     case MSIG_WPACK_CONVT_FWD: {
       int py, ty, px, tx;
       r_to_ph(t / 4, py, ty);
@@ -358,9 +361,10 @@ static WgradPlan plan_wgrad(int M, int N, int taps, int64_t kb_total) {
   pl.n_blocks = static_cast<int>(ceil_div(N, pl.block_n));
   const int64_t base = int64_t(pl.m_blocks) * pl.n_blocks * taps;
   const int sms = sm_count() > 0 ? sm_count() : 148;
-  int64_t splits = ceil_div(2 * int64_t(sms), base);
-  splits = std::max<int64_t>(1, std::min<int64_t>(splits, ceil_div(kb_total, 8)));
-  splits = std::min<int64_t>(splits, 64);
+  // one CTA per SM is resident (192 KiB of smem): fill ONE wave as completely as possible
+  int64_t splits = std::max<int64_t>(1, int64_t(sms) / base);
+  splits = std::max<int64_t>(1, std::min<int64_t>(splits, ceil_div(kb_total, 4)));
+  splits = std::min<int64_t>(splits, 128);
   pl.kb_per_split = static_cast<int>(ceil_div(kb_total, splits));
   pl.splits = static_cast<int>(ceil_div(kb_total, pl.kb_per_split));
   pl.kb_total = static_cast<int>(kb_total);
@@ -470,7 +474,8 @@ size_t msig_conv2d_wgrad_workspace(const msig_conv_geom* g) {
   int PW, PH;
   pick_kblock(g->ow, PW, PH);
   const int64_t kb = int64_t(g->n) * ceil_div(g->oh, PH) * ceil_div(g->ow, PW);
-  return wgrad_ws_bytes(g->k, g->c, g->r * g->s, kb);
+  const bool swap = g->c >= 128;
+  return wgrad_ws_bytes(swap ? g->c : g->k, swap ? g->k : g->c, g->r * g->s, kb);
 }
 
 int msig_conv2d_wgrad(const msig_conv_geom* g, const void* x, const void* dy, float* dw, int accumulate,
@@ -488,27 +493,36 @@ int msig_conv2d_wgrad(const msig_conv_geom* g, const void* x, const void* dy, fl
   p.n_img = g->n;
   p.taps = g->r * g->s;
   const int64_t kb_total = int64_t(g->n) * p.blocks_h * p.blocks_w;
-  WgradPlan pl = plan_wgrad(g->k, g->c, p.taps, kb_total);
+  // Operand roles. All CTAs of one pixel range read the SAME dy tile (L2 serves it once) but a
+  // different shifted x window per tap, so the per-CTA-unique operand should be the 128-wide M side:
+  // with >= 128 input channels x is the M operand (partials come out [ci][tap-major][co]).
+  const bool swap = g->c >= 128;
+  const int M = swap ? g->c : g->k, N = swap ? g->k : g->c;
+  WgradPlan pl = plan_wgrad(M, N, p.taps, kb_total);
   const size_t need = size_t(pl.splits) * size_t(g->k) * p.taps * g->c * sizeof(float);
   MSIG_REQUIRE(workspace_bytes >= need, "wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
   p.m_blocks = pl.m_blocks; p.n_blocks = pl.n_blocks; p.splits = pl.splits;
   p.kb_per_split = pl.kb_per_split; p.kb_total = pl.kb_total;
   p.out = reinterpret_cast<float*>(workspace);
-  p.o_row = int64_t(p.taps) * g->c; p.o_tap = g->c;
+  p.o_row = int64_t(p.taps) * N; p.o_tap = N;
   p.o_split = int64_t(g->k) * p.taps * g->c;
-  p.alpha = 1.f; p.m_valid = g->k; p.n_valid = g->c;
+  p.alpha = 1.f; p.m_valid = M; p.n_valid = N;
   int rc;
+  CUtensorMap* tm_dy = swap ? p.tmB : p.tmA;
+  CUtensorMap* tm_x = swap ? p.tmA : p.tmB;
+  Tap* tap_dy = swap ? p.tapB : p.tapA;
+  Tap* tap_x = swap ? p.tapA : p.tapB;
   ActView va{dy, g->k, g->ow, g->oh, g->n, g->k, int64_t(g->ow) * g->k, int64_t(g->oh) * g->ow * g->k};
-  if ((rc = make_act_map(&p.tmA[0], va, p.PW, p.PH)) != MSIG_OK) return rc;
-  for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+  if ((rc = make_act_map(&tm_dy[0], va, p.PW, p.PH)) != MSIG_OK) return rc;
+  for (int i = 1; i < 4; ++i) tm_dy[i] = tm_dy[0];
   if (g->stride == 1) {
     ActView vb{x, g->c, g->w, g->h, g->n, g->c, int64_t(g->w) * g->c, int64_t(g->h) * g->w * g->c};
-    if ((rc = make_act_map(&p.tmB[0], vb, p.PW, p.PH)) != MSIG_OK) return rc;
-    for (int i = 1; i < 4; ++i) p.tmB[i] = p.tmB[0];
+    if ((rc = make_act_map(&tm_x[0], vb, p.PW, p.PH)) != MSIG_OK) return rc;
+    for (int i = 1; i < 4; ++i) tm_x[i] = tm_x[0];
     for (int r = 0; r < g->r; ++r)
       for (int s = 0; s < g->s; ++s) {
-        p.tapA[r * g->s + s] = Tap{0, 0, 0, 0};
-        p.tapB[r * g->s + s] = Tap{int8_t(r - g->pad_t), int8_t(s - g->pad_l), 0, 0};
+        tap_dy[r * g->s + s] = Tap{0, 0, 0, 0};
+        tap_x[r * g->s + s] = Tap{int8_t(r - g->pad_t), int8_t(s - g->pad_l), 0, 0};
       }
   } else {
     MSIG_REQUIRE(g->stride == 2 && g->h % 2 == 0 && g->w % 2 == 0, "wgrad: stride-2 needs even dims");
@@ -518,20 +532,21 @@ int msig_conv2d_wgrad(const msig_conv_geom* g, const void* x, const void* dy, fl
             reinterpret_cast<const __nv_bfloat16*>(x) + (int64_t(ph) * g->w + pw) * g->c;
         ActView vb{base, g->c, g->w / 2, g->h / 2, g->n, int64_t(2) * g->c, int64_t(2) * g->w * g->c,
                    int64_t(g->h) * g->w * g->c};
-        if ((rc = make_act_map(&p.tmB[ph * 2 + pw], vb, p.PW, p.PH)) != MSIG_OK) return rc;
+        if ((rc = make_act_map(&tm_x[ph * 2 + pw], vb, p.PW, p.PH)) != MSIG_OK) return rc;
       }
     for (int r = 0; r < g->r; ++r)
       for (int s = 0; s < g->s; ++s) {
         const int rr = r - g->pad_t, ss = s - g->pad_l;
         const int ph = ((rr % 2) + 2) % 2, pw = ((ss % 2) + 2) % 2;
-        p.tapA[r * g->s + s] = Tap{0, 0, 0, 0};
-        p.tapB[r * g->s + s] = Tap{int8_t((rr - ph) / 2), int8_t((ss - pw) / 2), int8_t(ph * 2 + pw), 0};
+        tap_dy[r * g->s + s] = Tap{0, 0, 0, 0};
+        tap_x[r * g->s + s] = Tap{int8_t((rr - ph) / 2), int8_t((ss - pw) / 2), int8_t(ph * 2 + pw), 0};
       }
   }
   cudaError_t ce = launch_wgrad(p, pl.block_n, st);
   if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "wgrad launch: %s", cudaGetErrorString(ce));
   msig_wpack_desc d{MSIG_WPACK_FWD, g->k, g->c, g->r, g->s};
   PackGeom pg = make_pack_geom(&d, 0, 0);
+  pg.partT = swap ? 1 : 0;
   return launch_wgrad_reduce(pg, p.out, pl.splits, p.o_split, dw, accumulate, st);
 }
 
@@ -702,6 +717,7 @@ int msig_gram_fwd(const void* f, int32_t n, int32_t h, int32_t w, int32_t c, flo
   p.o_row = dim; p.o_tap = 0; p.o_split = int64_t(dim) * dim;
   p.alpha = 1.f / (float(n) * float(c) * float(h) * float(w));
   p.m_valid = dim; p.n_valid = dim;
+  p.upper_only = 1;   // G is symmetric: tiles strictly below the diagonal are neither computed nor read
   if (pl.splits > 1) {
     MSIG_REQUIRE(workspace && workspace_bytes >= size_t(pl.splits) * dim * size_t(dim) * sizeof(float),
                  "msig_gram_fwd: workspace too small");

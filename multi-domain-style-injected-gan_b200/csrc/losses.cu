@@ -104,34 +104,36 @@ __global__ void mse_const_bwd_kernel(const float* __restrict__ a, float t, int64
     g[i] = (a[i] - t) * k;
 }
 
-// loss = mean |Ga - Gb|; ssym[i][j] = sign(D[i][j]) + sign(D[j][i])
+// loss = mean |Ga - Gb| over the full symmetric matrix; ssym = 2*sign(D) (= sign(D) + sign(D)^T).
+// Only 32x32 tiles on/above the diagonal are read (the Gram kernel skips tiles below it); a block
+// below the diagonal reads its mirror tile and transposes it through shared memory (coalesced).
 __global__ void gram_l1_kernel(const float* __restrict__ ga, const float* __restrict__ gb, int dim,
                                float inv_n, float* __restrict__ loss, __nv_bfloat16* __restrict__ ssym) {
   __shared__ float tile[32][33];
-  // 32x32 tiles; block (32, 8)
-  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int bx = blockIdx.x * 32, by = blockIdx.y * 32;   // this block: rows by.., cols bx..
+  const bool upper = blockIdx.x >= blockIdx.y;
   float s = 0.f;
-  // load the transposed tile D[bx.., by..] so that tile[tx][ty] = D[bx+ty'][by+tx']...
-  for (int r = threadIdx.y; r < 32; r += 8) {
-    const int i = bx + r, j = by + threadIdx.x;   // D[i][j] with i in the x-block rows: this is the mirror tile
-    float d = 0.f;
-    if (i < dim && j < dim) d = ga[int64_t(i) * dim + j] - gb[int64_t(i) * dim + j];
-    tile[r][threadIdx.x] = sgn(d);
+  if (!upper) {
+    for (int r = ty; r < 32; r += 8) {
+      const int i = bx + r, j = by + tx;                  // mirror tile (above the diagonal)
+      float d = 0.f;
+      if (i < dim && j < dim) d = ga[int64_t(i) * dim + j] - gb[int64_t(i) * dim + j];
+      tile[r][tx] = d;
+    }
+    __syncthreads();
   }
-  __syncthreads();
-  for (int r = threadIdx.y; r < 32; r += 8) {
-    const int i = by + r, j = bx + threadIdx.x;   // D[i][j] in this block's own tile
+  for (int r = ty; r < 32; r += 8) {
+    const int i = by + r, j = bx + tx;
     if (i < dim && j < dim) {
-      const float d = ga[int64_t(i) * dim + j] - gb[int64_t(i) * dim + j];
+      const float d = upper ? ga[int64_t(i) * dim + j] - gb[int64_t(i) * dim + j] : tile[tx][r];
       s += fabsf(d);
-      // mirror element D[j][i] sits at tile[j - bx][i - by] = tile[threadIdx.x][r]
-      ssym[int64_t(i) * dim + j] = __float2bfloat16(sgn(d) + tile[threadIdx.x][r]);
+      ssym[int64_t(i) * dim + j] = __float2bfloat16(2.f * sgn(d));
     }
   }
-  // block reduce (256 threads)
   __shared__ float ws[8];
   s = warp_sum_l(s);
-  const int tid = threadIdx.y * 32 + threadIdx.x;
+  const int tid = ty * 32 + tx;
   if ((tid & 31) == 0) ws[tid >> 5] = s;
   __syncthreads();
   if (tid == 0) {

@@ -59,46 +59,69 @@ static inline int grid_for(int64_t work, int threads, int cap = 148 * 16) {
 }
 
 // ---------------------------------------------------------------- gathered patches
-__global__ void patch_gather_kernel(msig_patch_geom g, const float* __restrict__ src,
-                                    const float* __restrict__ scale, const float* __restrict__ shift,
-                                    __nv_bfloat16* __restrict__ out, int64_t groups_total) {
-  const int kg_per_row = g.kpad / 8;
+// One block walks 32-output-pixel tiles of one output row; the k -> (channel, r, s) decode is a
+// shared-memory table built once per block (no integer division in the hot loop), stores are
+// 16-byte and contiguous along k, source reads hit L1 (a tile touches a tiny input window).
+constexpr int kGatherTile = 32;
+__global__ void __launch_bounds__(256) patch_gather_kernel(msig_patch_geom g, const float* __restrict__ src,
+                                                           const float* __restrict__ scale,
+                                                           const float* __restrict__ shift,
+                                                           __nv_bfloat16* __restrict__ out, int tiles_w,
+                                                           int64_t total_tiles) {
+  extern __shared__ uint32_t tab[];   // [8][kpad/8], transposed so that lanes read consecutive words
+  const int kgs = g.kpad / 8;
   const int kvalid = g.r * g.s * g.c;
-  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < groups_total;
-       idx += int64_t(gridDim.x) * blockDim.x) {
-    const int kg = static_cast<int>(idx % kg_per_row);
-    int64_t m = idx / kg_per_row;
-    const int ow = static_cast<int>(m % g.ow);
-    m /= g.ow;
-    const int oh = static_cast<int>(m % g.oh);
-    const int n = static_cast<int>(m / g.oh);
-    float f[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = kg * 8 + j;
-      float v = 0.f;
-      if (k < kvalid) {
-        const int t = k / g.c;
-        const int ch = k - t * g.c;
-        const int r = t / g.s;
-        const int s = t - r * g.s;
-        int ih = oh * g.stride + r - g.pad_t;
-        int iw = ow * g.stride + s - g.pad_l;
-        bool ok = true;
-        if (g.reflect) {
-          ih = reflect_idx(ih, g.h);
-          iw = reflect_idx(iw, g.w);
-        } else {
-          ok = (ih >= 0) && (ih < g.h) && (iw >= 0) && (iw < g.w);
-        }
-        if (ok) {
-          v = __ldg(src + ((int64_t(n) * g.c + ch) * g.h + ih) * g.w + iw);
-          if (scale != nullptr) v = v * scale[ch] + shift[ch];
-        }
-      }
-      f[j] = v;
+  for (int k = threadIdx.x; k < g.kpad; k += blockDim.x) {
+    uint32_t e = 0xFFFFFFFFu;
+    if (k < kvalid) {
+      const int t = k / g.c, ch = k - t * g.c;
+      const int r = t / g.s, s2 = t - r * g.s;
+      e = uint32_t(ch) | (uint32_t(r) << 8) | (uint32_t(s2) << 16);
     }
-    store8(out + idx * 8, f);
+    tab[(k & 7) * kgs + (k >> 3)] = e;
+  }
+  __syncthreads();
+  const int items = kGatherTile * kgs;
+  const int64_t plane = int64_t(g.h) * g.w;
+  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    const int tw = static_cast<int>(tile % tiles_w);
+    const int64_t rem = tile / tiles_w;
+    const int oh = static_cast<int>(rem % g.oh);
+    const int n = static_cast<int>(rem / g.oh);
+    const float* sn = src + int64_t(n) * g.c * plane;
+    const int ih0 = oh * g.stride - g.pad_t;
+    __nv_bfloat16* orow = out + (int64_t(n) * g.oh + oh) * g.ow * g.kpad;
+    for (int it = threadIdx.x; it < items; it += blockDim.x) {
+      const int p = it / kgs;
+      const int kg = it - p * kgs;
+      const int ow = tw * kGatherTile + p;
+      if (ow >= g.ow) continue;
+      const int iw0 = ow * g.stride - g.pad_l;
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const uint32_t e = tab[j * kgs + kg];
+        float v = 0.f;
+        if (e != 0xFFFFFFFFu) {
+          const int ch = e & 0xFF;
+          int ih = ih0 + int((e >> 8) & 0xFF);
+          int iw = iw0 + int(e >> 16);
+          bool ok = true;
+          if (g.reflect) {
+            ih = reflect_idx(ih, g.h);
+            iw = reflect_idx(iw, g.w);
+          } else {
+            ok = (ih >= 0) && (ih < g.h) && (iw >= 0) && (iw < g.w);
+          }
+          if (ok) {
+            v = __ldg(sn + ch * plane + int64_t(ih) * g.w + iw);
+            if (scale != nullptr) v = v * __ldg(scale + ch) + __ldg(shift + ch);
+          }
+        }
+        f[j] = v;
+      }
+      store8(orow + int64_t(ow) * g.kpad + kg * 8, f);
+    }
   }
 }
 
@@ -648,9 +671,12 @@ int msig_patch_gather(const msig_patch_geom* g, const float* src, const float* s
   MSIG_REQUIRE(g && src && patches, "msig_patch_gather: null argument");
   MSIG_REQUIRE(g->kpad % 64 == 0 && g->kpad >= g->r * g->s * g->c, "msig_patch_gather: bad kpad %d", g->kpad);
   MSIG_REQUIRE((scale == nullptr) == (shift == nullptr), "msig_patch_gather: scale and shift go together");
-  const int64_t groups = int64_t(g->n) * g->oh * g->ow * (g->kpad / 8);
-  patch_gather_kernel<<<grid_for(groups, 256, 148 * 32), 256, 0, ST(stream)>>>(*g, src, scale, shift,
-                                                                              BF(patches), groups);
+  MSIG_REQUIRE(g->c <= 255 && g->r <= 255 && g->s <= 255, "msig_patch_gather: channel / filter extent too large");
+  const int tiles_w = static_cast<int>(ceil_div(g->ow, kGatherTile));
+  const int64_t tiles = int64_t(g->n) * g->oh * tiles_w;
+  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(tiles, 148 * 8)));
+  patch_gather_kernel<<<blocks, 256, size_t(g->kpad) * sizeof(uint32_t), ST(stream)>>>(
+      *g, src, scale, shift, BF(patches), tiles_w, tiles);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;

@@ -89,7 +89,7 @@ class VGGStyleContentLoss(nn.Module):
         img = img.contiguous().float()
         B, _, H, W = img.shape
         pg = ops.patch_geom(B, 3, H, W, 3, 3, 1, 1, 1, H, W, False)
-        a = ops.patch_gather(img, pg, P["scale"], P["shift"])
+        a = ops.patch_gather_cached(img, pg, P["scale"], P["shift"])
         m0 = B * H * W
         f1 = ops.conv2d_fwd(a.view(1, 1, m0, pg.kpad), P["w0"], ops.gemm_geom(m0, pg.kpad, 64),
                             ops.epilogue(bias=P["b"][0], act=ACT_RELU)).view(B, H, W, 64)
@@ -112,6 +112,19 @@ class VGGStyleContentLoss(nn.Module):
                 feats.append(f5)
         return feats, g, pg
 
+    def features_of_real(self, img, upto):
+        """Features of a data image; inside a train_step they are computed once (all five levels)
+        and shared by the two perceptual-loss calls (trainer.py:104,109)."""
+        cache = ops.step_cache()
+        if cache is None:
+            return self.features(img, upto)[0]
+        key = ("vgg", img.data_ptr(), img._version, tuple(img.shape))
+        hit = cache.get(key)
+        if hit is None:
+            hit = (img, self.features(img, 5)[0])
+            cache[key] = hit
+        return hit[1]
+
     def forward(self, generated, real_style, real_content):
         return _VGGLossFn.apply(self, generated, real_style, real_content)
 
@@ -125,8 +138,8 @@ class _VGGLossFn(torch.autograd.Function):
         if gen.shape[2] % 4 or gen.shape[3] % 4:
             raise RuntimeError("VGG loss input height/width must be multiples of 4")
         fg, geoms, pg = mod.features(gen, 5)
-        fs, _, _ = mod.features(real_style, 5)
-        fc, _, _ = mod.features(real_content, 4)          # only relu_4_1 is used (losses.py:110)
+        fs = mod.features_of_real(real_style, 5)
+        fc = mod.features_of_real(real_content, 4)         # only relu_4_1 is used (losses.py:110)
         style = torch.zeros((), dtype=F32, device=gen.device)
         ssyms = []
         for a, b in zip(fg, fs):                            # losses.py:80-89

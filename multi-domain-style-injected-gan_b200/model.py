@@ -247,7 +247,7 @@ class _GeneratorFn(torch.autograd.Function):
         S = {}   # saved activations
         # ---- content encoder (model.py:130-134)
         pg0 = ops.patch_geom(B, 3, H, W, 7, 7, 1, 3, 3, H, W, True)
-        a0 = ops.patch_gather(img, pg0)
+        a0 = ops.patch_gather_cached(img, pg0)
         m0 = B * H * W
         z0 = ops.conv2d_fwd(a0.view(1, 1, m0, pg0.kpad), P["e0"], ops.gemm_geom(m0, pg0.kpad, 64)).view(B, H, W, 64)
         del a0
@@ -391,7 +391,7 @@ class _GeneratorFn(torch.autograd.Function):
         m0 = B * H * W
         pg0 = S["pg0"]
         if wg:
-            a0 = ops.patch_gather(S["img"], pg0)   # recomputed instead of saved (25 MB / image at 256^2)
+            a0 = ops.patch_gather_cached(S["img"], pg0)   # re-gathered (or step-cached), not saved: 25 MB / image
             ops.patch_wgrad(WPACK_IM2COL, 64, 3, 7, 7, m0, dz0, 64, a0, pg0.kpad, _grad_buf(enc[0].weight))
             del a0
             # conv biases that feed an InstanceNorm have an exactly-zero true gradient (the mean
@@ -488,7 +488,7 @@ class _StyleEncoderFn(torch.autograd.Function):
             raise RuntimeError("style encoder input height/width must be multiples of 16")
         idx = None if domain_idx is None else domain_idx.to(device=img.device, dtype=torch.int64).contiguous()
         pg = ops.patch_geom(B, 3, H, W, 4, 4, 2, 1, 1, H // 2, W // 2, False)
-        a = ops.patch_gather(img, pg)
+        a = ops.patch_gather_cached(img, pg)
         m0 = B * (H // 2) * (W // 2)
         y = ops.conv2d_fwd(a.view(1, 1, m0, pg.kpad), P["c0"], ops.gemm_geom(m0, pg.kpad, 64),
                            ops.epilogue(bias=convs[0].bias.detach(), act=ACT_RELU)).view(B, H // 2, W // 2, 64)
@@ -541,7 +541,7 @@ class _StyleEncoderFn(torch.autograd.Function):
         pg = S["pg"]
         m0 = dz.shape[0] * dz.shape[1] * dz.shape[2]
         ops.colsum(dz, 64, _grad_buf(convs[0].bias))
-        a = ops.patch_gather(S["img"], pg)
+        a = ops.patch_gather_cached(S["img"], pg)
         ops.patch_wgrad(WPACK_IM2COL, 64, 3, 4, 4, m0, dz, 64, a, pg.kpad, _grad_buf(convs[0].weight))
         ctx.saved = None
         # the style encoder only ever sees leaf images (trainer.py:94-95): no image gradient
@@ -617,7 +617,7 @@ class _DiscriminatorFn(torch.autograd.Function):
             raise RuntimeError("discriminator input height/width must be multiples of 16")
         idx = None if domain_idx is None else domain_idx.to(device=img.device, dtype=torch.int64).contiguous()
         pg = ops.patch_geom(B, 3, H, W, 4, 4, 2, 1, 1, H // 2, W // 2, False)
-        a = ops.patch_gather(img, pg)
+        a = ops.patch_gather_cached(img, pg)
         m0 = B * (H // 2) * (W // 2)
         y0 = ops.conv2d_fwd(a.view(1, 1, m0, pg.kpad), P["c0"], ops.gemm_geom(m0, pg.kpad, 64),
                             ops.epilogue(bias=convs[0].bias.detach(), act=ACT_LRELU)).view(B, H // 2, W // 2, 64)
@@ -682,7 +682,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         m0 = dz0.shape[0] * dz0.shape[1] * dz0.shape[2]
         if wg:
             ops.colsum(dz0, 64, _grad_buf(convs[0].bias))
-            a = ops.patch_gather(S["img"], pg)
+            a = ops.patch_gather_cached(S["img"], pg)
             ops.patch_wgrad(WPACK_IM2COL, 64, 3, 4, 4, m0, dz0, 64, a, pg.kpad, _grad_buf(convs[0].weight))
             del a
             for p in mod._dead_biases():

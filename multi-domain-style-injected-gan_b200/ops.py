@@ -139,6 +139,44 @@ def patch_gather(src, pg, scale=None, shift=None, out=None):
     return out
 
 
+# Within one train_step the same image is gathered many times with the same geometry (the generator's
+# forward and its wgrad re-gather, SE and D on the same real image, D on fake_B in both phases) and the
+# VGG features of the two real images are needed by both perceptual-loss calls. The step cache keeps
+# those results (and a reference to the source tensor, so its storage cannot be recycled) until the
+# step ends. Keys use (data_ptr, version): detach() shares both.
+_step_cache = None
+
+
+def step_cache_begin():
+    global _step_cache
+    _step_cache = {}
+
+
+def step_cache_end():
+    global _step_cache
+    _step_cache = None
+
+
+def step_cache():
+    return _step_cache
+
+
+def _pg_key(pg):
+    return (pg.n, pg.c, pg.h, pg.w, pg.r, pg.s, pg.stride, pg.pad_t, pg.pad_l, pg.oh, pg.ow, pg.reflect, pg.kpad)
+
+
+def patch_gather_cached(src, pg, scale=None, shift=None):
+    """patch_gather of an IMAGE (a tensor that stays unchanged for the rest of the step)."""
+    if _step_cache is None:
+        return patch_gather(src, pg, scale, shift)
+    key = ("pg", src.data_ptr(), src._version, _pg_key(pg), 0 if scale is None else scale.data_ptr())
+    hit = _step_cache.get(key)
+    if hit is None:
+        hit = (src, patch_gather(src, pg, scale, shift))
+        _step_cache[key] = hit
+    return hit[1]
+
+
 def patch_scatter(dpatches, pg, scale=None, out=None, accumulate=False):
     if out is None:
         out = torch.empty((pg.n, pg.c, pg.h, pg.w), dtype=F32, device=dpatches.device)

@@ -17,6 +17,7 @@ import os
 
 import torch
 
+from . import ops
 from .losses import L1Loss, MSELoss, VGGStyleContentLoss
 from .model import MultiDomainDiscriminator, MultiDomainStyleEncoder, StyleCycleGANGenerator
 from .parallel import FlatAllReduce
@@ -82,6 +83,13 @@ class MultiDomainStyleCycleGAN:
     def train_step(self, batch, epoch):
         """One G+D optimisation step (reference trainer.py:74-155). Returns the same dict of loss
         tensors: D_loss, G_loss, gan, cycle, identity, style, content."""
+        ops.step_cache_begin()
+        try:
+            return self._train_step(batch, epoch)
+        finally:
+            ops.step_cache_end()
+
+    def _train_step(self, batch, epoch):
         dev = self.device
         real_A = batch['source'].to(dev, non_blocking=True)
         real_B = batch['target'].to(dev, non_blocking=True)

@@ -220,7 +220,7 @@ def case_train_step(b=2, s=64, nd=3, steps=2, seed=0):
         ok = ok and res[f"s{it}.g_norm"] <= 5e-2 and res[f"s{it}.d_norm"] <= 5e-2
         if it == 0:
             # pre-clip gradients of step 1, per tensor
-            worst, wname, all_ok = (1.0, 0.0, 0.0), "", True
+            worst, wname, all_ok, bad = (1.0, 0.0, 0.0), "", True, []
             for net in O.OracleTrainer.NETS:
                 mod = getattr(tr, net)
                 dead = set()
@@ -232,11 +232,15 @@ def case_train_step(b=2, s=64, nd=3, steps=2, seed=0):
                         continue
                     m = grad_metrics(p.grad, rg)
                     # whole step: gradients cross two chained generators + D / VGG -> cosine >= 0.95
-                    all_ok = all_ok and m[0] >= 0.95 and m[1] <= GRAD_NORM and m[2] <= GRAD_MAXREL
+                    t_ok = m[0] >= 0.95 and m[1] <= GRAD_NORM and m[2] <= GRAD_MAXREL
+                    if not t_ok:
+                        bad.append((f"{net}.{n}", [round(x, 4) for x in m]))
+                    all_ok = all_ok and t_ok
                     if m[0] < worst[0]:
                         worst, wname = m, f"{net}.{n}"
             res["s0.wgrad"] = worst
             res["s0.wgrad_worst"] = wname
+            res["s0.wgrad_bad"] = bad[:8]
             ok = ok and all_ok
     # parameters after the steps: Adam moves each weight by ~lr per step regardless of gradient size
     worst = 0.0
