@@ -354,12 +354,18 @@ struct WgradPlan {
   int block_n, m_blocks, n_blocks, splits, kb_per_split, kb_total;
 };
 
-static WgradPlan plan_wgrad(int M, int N, int taps, int64_t kb_total) {
+static WgradPlan plan_wgrad(int M, int N, int taps, int64_t kb_total, bool upper_only = false) {
   WgradPlan pl;
   pl.block_n = (N % 256 == 0) ? 256 : (N % 128 == 0 ? 128 : 64);
   pl.m_blocks = static_cast<int>(ceil_div(M, 128));
   pl.n_blocks = static_cast<int>(ceil_div(N, pl.block_n));
-  const int64_t base = int64_t(pl.m_blocks) * pl.n_blocks * taps;
+  int64_t base = int64_t(pl.m_blocks) * pl.n_blocks * taps;
+  if (upper_only) {   // only tiles on/above the diagonal do work
+    base = 0;
+    for (int m = 0; m < pl.m_blocks; ++m)
+      for (int n = 0; n < pl.n_blocks; ++n)
+        if ((n + 1) * pl.block_n > m * 128) ++base;
+  }
   const int sms = sm_count() > 0 ? sm_count() : 148;
   // one CTA per SM is resident (192 KiB of smem): fill ONE wave as completely as possible
   int64_t splits = std::max<int64_t>(1, int64_t(sms) / base);
@@ -690,7 +696,7 @@ int msig_patch_wgrad(const msig_wpack_desc* d, int64_t rows, const void* a_rows_
 static WgradPlan plan_gram(int n, int h, int w, int c, int& PW, int& PH) {
   pick_kblock(w, PW, PH);
   const int64_t kb = ceil_div(h, PH) * ceil_div(w, PW);
-  return plan_wgrad(n * c, n * c, 1, kb);
+  return plan_wgrad(n * c, n * c, 1, kb, true);
 }
 
 size_t msig_gram_workspace(int32_t n, int32_t h, int32_t w, int32_t c) {

@@ -154,37 +154,43 @@ __global__ void __launch_bounds__(256, 1) fprop_kernel(const __grid_constant__ F
   const int total = m_tiles * p.n_blocks;
   const int kblocks = p.taps * p.cblocks;
 
+  // Both single-thread roles run warp-converged: every lane walks the loops and waits on the
+  // barriers, one elected lane issues TMA / MMA / commit. (Issuing from inside `if (lane == 0)`
+  // makes ptxas wrap every uniform-datapath instruction in an ELECT / BRA.U.ANY loop, which costs
+  // more than the MMA itself for narrow tiles.)
   if (warp == 0) {
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int n_blk = tile % p.n_blocks;
-        int mt = tile / p.n_blocks;
-        const int ph = mt % p.phases;
-        mt /= p.phases;
-        const int tw = mt % p.tiles_w;
-        mt /= p.tiles_w;
-        const int th = mt % p.tiles_h;
-        const int img = mt / p.tiles_h;
-        const int oh0 = th * p.TH, ow0 = tw * p.TW;
-        const int n_off =
-            n_blk * BLOCK_N + img * p.b_row_per_image + ph * p.b_row_per_phase;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          const int t = kb / p.cblocks;
-          const int cb = kb - t * p.cblocks;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      const int n_blk = tile % p.n_blocks;
+      int mt = tile / p.n_blocks;
+      const int ph = mt % p.phases;
+      mt /= p.phases;
+      const int tw = mt % p.tiles_w;
+      mt /= p.tiles_w;
+      const int th = mt % p.tiles_h;
+      const int img = mt / p.tiles_h;
+      const int oh0 = th * p.TH, ow0 = tw * p.TW;
+      const int n_off = n_blk * BLOCK_N + img * p.b_row_per_image + ph * p.b_row_per_phase;
+      int kb = 0;
+      for (int t = 0; t < p.taps; ++t) {
+        int map = 0, cw = ow0, chh = oh0, cn = t;
+        if (!p.tap_is_image) {
+          const Tap tp = p.tap[ph * p.taps + t];
+          map = tp.map;
+          cw = ow0 + tp.dw;
+          chh = oh0 + tp.dh;
+          cn = img;
+        }
+        for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
-          uint8_t* sa = smem + stage * Cfg::kStageBytes;
-          uint8_t* sb = sa + kABytes;
-          mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
-          if (p.tap_is_image) {
-            tma_load_4d(sa, &p.tmA[0], &full_bar[stage], cb * kBlockK, ow0, oh0, t);
-          } else {
-            const Tap tp = p.tap[ph * p.taps + t];
-            tma_load_4d(sa, &p.tmA[tp.map], &full_bar[stage], cb * kBlockK, ow0 + tp.dw,
-                        oh0 + tp.dh, img);
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * Cfg::kStageBytes;
+            mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            tma_load_4d(sa, &p.tmA[map], &full_bar[stage], cb * kBlockK, cw, chh, cn);
+            tma_load_2d(sa + kABytes, &p.tmB, &full_bar[stage], kb * kBlockK, n_off);
           }
-          tma_load_2d(sb, &p.tmB, &full_bar[stage], kb * kBlockK, n_off);
+          __syncwarp();
           if (++stage == Cfg::kStages) {
             stage = 0;
             phase ^= 1u;
@@ -193,35 +199,34 @@ __global__ void __launch_bounds__(256, 1) fprop_kernel(const __grid_constant__ F
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-        const int as = it & 1;
-        const uint32_t aphase = (it >> 1) & 1;
-        mbar_wait(&tempty_bar[as], aphase ^ 1u);
+    const uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[as], aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
+        if (elect_one()) {
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + kABytes;
+          const uint64_t da = make_smem_desc(sa, 0, 1024);
+          const uint64_t db = make_smem_desc(sa + kABytes, 0, 1024);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            const uint64_t da = make_smem_desc(sa + k * 32, 0, 1024);
-            const uint64_t db = make_smem_desc(sb + k * 32, 0, 1024);
-            umma_bf16(d_tmem, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          }
+          for (int k = 0; k < kBlockK / 16; ++k)   // +32 B per K step = +2 in the descriptor's address field
+            umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);
-          if (++stage == Cfg::kStages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          if (kb == kblocks - 1) umma_commit(&tfull_bar[as]);
         }
-        umma_commit(&tfull_bar[as]);
+        __syncwarp();
+        if (++stage == Cfg::kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
     }
   } else if (warp >= 4) {
@@ -332,76 +337,89 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   const int nk = kb1 > kb0 ? kb1 - kb0 : 0;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const Tap ta = p.tapA[tap];
-      const Tap tb = p.tapB[tap];
-      const int per_img = p.blocks_h * p.blocks_w;
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = kb0; kb < kb0 + nk; ++kb) {
-        int img = 0, rem = kb;
-        if (!p.fold_img) {
-          img = kb / per_img;
-          rem = kb - img * per_img;
-        }
-        const int hb = rem / p.blocks_w;
-        const int wb = rem - hb * p.blocks_w;
-        const int oh0 = hb * p.PH, ow0 = wb * p.PW;
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
+    const Tap ta = p.tapA[tap];
+    const Tap tb = p.tapB[tap];
+    const int per_img = p.blocks_h * p.blocks_w;
+    int stage = 0;
+    uint32_t phase = 0;
+    // (img, hb, wb) of the first K block, then incremented (no division in the loop)
+    int img = 0, rem = kb0;
+    if (!p.fold_img) {
+      img = kb0 / per_img;
+      rem = kb0 - img * per_img;
+    }
+    int hb = rem / p.blocks_w;
+    int wb = rem - hb * p.blocks_w;
+    int vca[2], na[2], vcb[BLOCK_N / 64], nb[BLOCK_N / 64];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      vca[i] = m_blk * kTileM + 64 * i;
+      na[i] = 0;
+      if (p.fold_img) {
+        na[i] = vca[i] / p.CA;
+        vca[i] -= na[i] * p.CA;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < BLOCK_N / 64; ++i) {
+      vcb[i] = n_blk * BLOCK_N + 64 * i;
+      nb[i] = 0;
+      if (p.fold_img) {
+        nb[i] = vcb[i] / p.CB;
+        vcb[i] -= nb[i] * p.CB;
+      }
+    }
+    for (int kb = 0; kb < nk; ++kb) {
+      const int oh0 = hb * p.PH, ow0 = wb * p.PW;
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      if (elect_one()) {
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kABytes;
         mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          int vc = m_blk * kTileM + 64 * i;
-          int n_a = img;
-          if (p.fold_img) {
-            n_a = vc / p.CA;
-            vc -= n_a * p.CA;
-          }
-          tma_load_4d(sa + i * 8192, &p.tmA[ta.map], &full_bar[stage], vc, ow0 + ta.dw,
-                      oh0 + ta.dh, n_a);
-        }
+        for (int i = 0; i < 2; ++i)
+          tma_load_4d(sa + i * 8192, &p.tmA[ta.map], &full_bar[stage], vca[i], ow0 + ta.dw, oh0 + ta.dh,
+                      p.fold_img ? na[i] : img);
 #pragma unroll
-        for (int i = 0; i < BLOCK_N / 64; ++i) {
-          int vc = n_blk * BLOCK_N + 64 * i;
-          int n_b = img;
-          if (p.fold_img) {
-            n_b = vc / p.CB;
-            vc -= n_b * p.CB;
-          }
-          tma_load_4d(sb + i * 8192, &p.tmB[tb.map], &full_bar[stage], vc, ow0 + tb.dw,
-                      oh0 + tb.dh, n_b);
+        for (int i = 0; i < BLOCK_N / 64; ++i)
+          tma_load_4d(sb + i * 8192, &p.tmB[tb.map], &full_bar[stage], vcb[i], ow0 + tb.dw, oh0 + tb.dh,
+                      p.fold_img ? nb[i] : img);
+      }
+      __syncwarp();
+      if (++wb == p.blocks_w) {
+        wb = 0;
+        if (++hb == p.blocks_h) {
+          hb = 0;
+          ++img;
         }
-        if (++stage == Cfg::kStages) {
-          stage = 0;
-          phase ^= 1u;
-        }
+      }
+      if (++stage == Cfg::kStages) {
+        stage = 0;
+        phase ^= 1u;
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && nk > 0) {
-      const uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 1, 1);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int kb = 0; kb < nk; ++kb) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
+    const uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < nk; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
         const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
-        const uint32_t sb = sa + Cfg::kABytes;
+        const uint64_t da = make_smem_desc(sa, 8192, 1024);
+        const uint64_t db = make_smem_desc(sa + Cfg::kABytes, 8192, 1024);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {  // 16 pixel rows (2 swizzle atoms of 8 rows) per MMA
-          const uint64_t da = make_smem_desc(sa + k * 2048, 8192, 1024);
-          const uint64_t db = make_smem_desc(sb + k * 2048, 8192, 1024);
-          umma_bf16(tmem_base, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-        }
+        for (int k = 0; k < 4; ++k)   // 16 pixel rows (2 swizzle atoms of 8 rows = 2048 B) per MMA
+          umma_bf16(tmem_base, da + 128 * k, db + 128 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
         umma_commit(&empty_bar[stage]);
-        if (++stage == Cfg::kStages) {
-          stage = 0;
-          phase ^= 1u;
-        }
+        if (kb == nk - 1) umma_commit(tfull_bar);
       }
-      umma_commit(tfull_bar);
+      __syncwarp();
+      if (++stage == Cfg::kStages) {
+        stage = 0;
+        phase ^= 1u;
+      }
     }
   } else if (warp >= 4) {
     const int q = warp & 3;

