@@ -8,6 +8,8 @@
 
 namespace msig {
 
+static int g_strip_mode = 1;   // 0: per-tap kernel, 1: strip kernel
+
 // ------------------------------------------------------------------------ phase tables
 // k=4, s=2, p=1: output row 2i+py of a transposed conv (or input row of a stride-2 conv's dgrad)
 // reads source row i+d through filter row r, for two (r, d) pairs per parity.
@@ -136,11 +138,37 @@ __global__ void wgrad_reduce_kernel(PackGeom g, const float* __restrict__ partia
   }
 }
 
+// Same reduction for the conv layouts ([O][RS][I] or, with swapped operand roles, [I][RS][O]), walking
+// the PARTIALS linearly: the (splits x) reads are coalesced, only the single write per element strides.
+__global__ void wgrad_reduce_fwd_kernel(PackGeom g, const float* __restrict__ partial, int splits,
+                                        int64_t split_stride, float* __restrict__ dw, int accumulate,
+                                        int64_t numel) {
+  const int inner = g.partT ? g.O : g.I;
+  for (int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; q < numel;
+       q += int64_t(gridDim.x) * blockDim.x) {
+    const int a = static_cast<int>(q % inner);
+    const int64_t r2 = q / inner;
+    const int t = static_cast<int>(r2 % g.RS);
+    const int b = static_cast<int>(r2 / g.RS);
+    const int o = g.partT ? a : b, i = g.partT ? b : a;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += partial[s * split_stride + q];
+    const int64_t idx = (int64_t(o) * g.I + i) * g.RS + t;
+    dw[idx] = accumulate ? dw[idx] + acc : acc;
+  }
+}
+
 static int launch_wgrad_reduce(const PackGeom& g, const float* partial, int splits,
                                int64_t split_stride, float* dw, int accumulate, cudaStream_t st) {
   const int64_t numel = int64_t(g.O) * g.I * g.RS;
   const int threads = 256;
   const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(numel, threads), 4096));
+  if (g.kind == MSIG_WPACK_FWD && g.OOFF == 0 && g.OC == g.O) {
+    wgrad_reduce_fwd_kernel<<<blocks, threads, 0, st>>>(g, partial, splits, split_stride, dw, accumulate, numel);
+    count_launch(1);
+    MSIG_CHECK_LAUNCH();
+    return MSIG_OK;
+  }
   wgrad_reduce_kernel<<<blocks, threads, 0, st>>>(g, partial, splits, split_stride, dw, accumulate,
                                                   numel);
   count_launch(1);
@@ -297,6 +325,20 @@ static int run_conv(const void* in, int n, int h, int w, int c, int k, int R, in
   if ((rc = make_w_map(&p.tmB, wpk, k_pad, int64_t(R) * S * c, block_n)) != MSIG_OK) return rc;
   const OutView ov = make_out_view(out, e ? e->out_layout : MSIG_OUT_BF16_NHWC, OH, OW, k);
   if ((rc = fill_epilogue(p, e, ov, k)) != MSIG_OK) return rc;
+  // Narrow-output "valid" stride-1 conv on 64 channels (the generator's final 7x7 conv on the
+  // pre-padded activation): resident filter + one strip per filter row instead of one tile per tap.
+  if (g_strip_mode != 0 && stride == 1 && pad_t == 0 && pad_l == 0 && c == 64 && block_n == 16 && R * S <= 49 &&
+      S <= 7 && R * S >= 9 && p.aux_mode == AUX_NONE) {
+    p.TW = 128; p.TH = 1;
+    p.tiles_h = OH;
+    p.tiles_w = static_cast<int>(ceil_div(OW, 128));
+    p.strip_r = R; p.strip_s = S;
+    ActView v{in, c, w, h, n, c, int64_t(w) * c, int64_t(h) * w * c};
+    if ((rc = make_act_map(&p.tmA[1], v, 128 + S - 1, 1)) != MSIG_OK) return rc;
+    cudaError_t ce = launch_fprop_strip16(p, sm_count(), st);
+    if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "fprop(strip) launch: %s", cudaGetErrorString(ce));
+    return MSIG_OK;
+  }
   cudaError_t ce = launch_fprop(p, block_n, sm_count(), st);
   if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "fprop launch: %s", cudaGetErrorString(ce));
   return MSIG_OK;
@@ -393,6 +435,12 @@ __global__ void sum_splits_kernel(const float* __restrict__ partial, int splits,
 using namespace msig;
 
 extern "C" {
+
+// Test hook: selects the kernel variant of the narrow-output 7x7 conv (see run_conv).
+int msig_debug_set_strip_mode(int mode) {
+  g_strip_mode = mode;
+  return MSIG_OK;
+}
 
 size_t msig_wpack_elems(const msig_wpack_desc* d) {
   if (!d) return 0;
@@ -755,17 +803,21 @@ int msig_gram_bwd(const void* f, const void* ssym, int32_t n, int32_t h, int32_t
   MSIG_REQUIRE(c % 64 == 0, "msig_gram_bwd: channels (%d) must be a multiple of 64", c);
   FpropParams p;
   init_fprop(p);
-  const int block_n = pick_block_n(c);
+  // GEMM view: rows = the h*w pixel positions, K = N = (image, channel) pairs. An output tile is 128
+  // pixel positions x BLOCK_N columns that may span several images (fold_c), so narrow feature maps
+  // (c = 64) still run 256-wide MMAs; the A tile of K block (image b', chunk) is shared by all of them.
+  const int block_n = pick_block_n(n * c);
   pick_tile(w, p.TW, p.TH);
   p.OH = h; p.OW = w;
   p.tiles_h = static_cast<int>(ceil_div(h, p.TH));
   p.tiles_w = static_cast<int>(ceil_div(w, p.TW));
-  p.n_img = n;
-  p.n_blocks = c / block_n;
+  p.n_img = 1;
+  p.n_blocks = (n * c) / block_n;
   p.taps = n;                 // one "tap" per source image
   p.cblocks = c / 64;
   p.tap_is_image = 1;
-  p.b_row_per_image = c;
+  p.b_row_per_image = 0;
+  p.fold_c = c;
   int rc;
   ActView v{f, c, w, h, n, c, int64_t(w) * c, int64_t(h) * w * c};
   if ((rc = make_act_map(&p.tmA[0], v, p.TW, p.TH)) != MSIG_OK) return rc;

@@ -36,6 +36,9 @@ struct FpropParams {
   int64_t o_ph[4], a_ph[4];
   int32_t tap_is_image;           // Gram backward: tap t reads image t (not the tile's image)
   int32_t b_row_per_image;        // B row offset added per output image (Gram backward)
+  int32_t fold_c;                 // >0: GEMM columns are (image, channel) pairs, fold_c channels per image;
+                                  //     column j is stored to image j / fold_c (Gram backward with N spanning images)
+  int32_t strip_r, strip_s;       // strip kernel: filter extent; tmA[1] has a (128 + strip_s - 1)-pixel box
   int32_t OH, OW, TH, TW;         // output plane and the 128-pixel tile (TH*TW == 128)
   int32_t tiles_h, tiles_w, n_img, n_blocks;
   // epilogue
@@ -75,6 +78,7 @@ struct WgradParams {
 
 cudaError_t launch_fprop(const FpropParams& p, int block_n, int num_sms, cudaStream_t stream);
 cudaError_t launch_wgrad(const WgradParams& p, int block_n, cudaStream_t stream);
+cudaError_t launch_fprop_strip16(const FpropParams& p, int num_sms, cudaStream_t stream);
 int igemm_kernel_launches();  // launches issued since process start (bench: gpu_launches)
 
 }  // namespace msig

@@ -157,6 +157,10 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// Measured on B200: the 128B swizzle is a function of the ABSOLUTE shared-memory address bits
+// (bits [4,7) ^= bits [7,10)), exactly as TMA writes it, so a K-major tile may start any number of
+// 128-byte rows into a swizzled buffer with the base-offset field left 0 (setting it to
+// (addr >> 7) & 7 gives wrong results). The strip kernel's row-shifted A descriptors rely on this.
 // Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, M x N, operand majorness.
 __host__ __device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N, int a_mn_major,
                                                              int b_mn_major) {

@@ -115,6 +115,25 @@ def case_convT(n, c, h, w, k, seed=0, which="fwd"):
     return rel_err(dw, wf.grad), 2e-3
 
 
+def case_final_conv(n, h, w, mode, seed=0):
+    """The generator's last layer (model.py:141) as executed: 7x7 'valid' conv 64->3 on the reflect-padded
+    activation + bias + tanh, fp32 NCHW out. mode selects the kernel variant (test hook)."""
+    ops.ensure_init()
+    L.load().msig_debug_set_strip_mode(mode)
+    try:
+        xp = _bf(_rand((n, 64, h + 6, w + 6), seed)).to(DEV)
+        wt = _bf(_rand((3, 64, 7, 7), seed + 1, 1.0 / (64 * 49) ** 0.5)).to(DEV)
+        b = _rand((3,), seed + 2).to(DEV)
+        ref = torch.tanh(F.conv2d(xp.float(), wt.float(), b))
+        wpk = ops.wpack(L.WPACK_FWD, wt.float().contiguous(), 3, 64, 7, 7)
+        g = ops.conv_geom(n, h + 6, w + 6, 64, 3, 7, 7, 1, 0, 0, h, w)
+        y = ops.conv2d_fwd(nhwc(xp), wpk, g, ops.epilogue(bias=b, act=L.ACT_TANH, out_layout=L.OUT_F32_NCHW))
+        torch.cuda.synchronize()
+        return rel_err(y, ref), 2e-3
+    finally:
+        L.load().msig_debug_set_strip_mode(1)
+
+
 def case_gemm(rows, k_in, n_out, seed=0, f32_out=False):
     """Linear layer as a 1x1 conv on a [1,1,rows,k_in] view."""
     ops.ensure_init()
@@ -164,6 +183,9 @@ CASES = {
     "fwd_3x3_64_256w": lambda: case_conv_fwd(1, 64, 16, 256, 64, 3, 1, 1),
     "fwd_4x4s2_64_128": lambda: case_conv_fwd(2, 64, 64, 64, 128, 4, 2, 1, act=L.ACT_LRELU),
     "fwd_4x4s2_256_512": lambda: case_conv_fwd(2, 256, 32, 32, 512, 4, 2, 1),
+    "final7x7_pertap": lambda: case_final_conv(2, 64, 256, 0),
+    "final7x7_strip": lambda: case_final_conv(2, 64, 256, 1),
+    "final7x7_strip_ragged": lambda: case_final_conv(1, 40, 200, 1),
     "fwd_1x1_gemm": lambda: case_gemm(200, 256, 512),
     "fwd_gemm_small_rows_f32": lambda: case_gemm(4, 512, 2560, f32_out=True),
     "dgrad_3x3_256": lambda: case_conv_dgrad(2, 256, 64, 64, 256, 3, 1, 1),
@@ -181,3 +203,4 @@ CASES = {
     "gram_256_b3": lambda: case_gram(3, 256, 16, 16),
     "gram_bwd_128": lambda: case_gram_bwd(2, 128, 32, 32),
 }
+
