@@ -152,6 +152,40 @@ def time_dominant_kernel(torch, ops, L, batch, iters=20):
     return ms, flops
 
 
+def time_inference(torch, T, O, dev, tr, batch=16, iters=10):
+    """BASELINE.json configs[1]: style injection, src+ref 256x256 batch 16, style encoder + generator
+    forward only (inference.py:119,290). Device-timed with resident inputs, and end to end through
+    inference.translate with pinned host images in and the translated images copied back out."""
+    from msig_b200 import inference as I
+    gb = O.synthetic_batch(batch, S, ND)
+    src_h, ref_h, dom_h = gb["source"].pin_memory(), gb["target"].pin_memory(), gb["target_domain"].pin_memory()
+    src, ref, dom = src_h.to(dev), ref_h.to(dev), dom_h.to(dev)
+    G, SE = tr.ema_G_A2B, tr.ema_SE_B
+    for _ in range(3):
+        out = I.translate(G, SE, src, ref, dom)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        out = I.translate(G, SE, src, ref, dom)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    host_out = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+    t0 = time.perf_counter()
+    for _ in range(iters):
+        out = I.translate(G, SE, src_h, ref_h, dom_h)
+        host_out.copy_(out, non_blocking=True)
+        torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1000.0 / iters
+    flops = batch * 100.28e9                     # SURVEY 8d: 96.96 (G) + 3.32 (SE) GF / image
+    return {"workload": "inference.py style injection: src+ref 256x256 batch %d, SE + G forward (BASELINE.json configs[1])" % batch,
+            "value": batch / (ms * 1e-3), "unit": "images/sec", "ms_per_batch": ms,
+            "e2e": {"value": batch / (e2e_ms * 1e-3), "unit": "images/sec",
+                    "h2d_bytes_per_step": 2 * src_h.numel() * 4 + dom_h.numel() * 8, "d2h_bytes_per_step": host_out.numel() * 4},
+            "tflops": flops / (ms * 1e-3) / 1e12}
+
+
 def run_ours(args):
     import torch
     import msig_b200  # noqa: F401
@@ -238,6 +272,9 @@ def run_ours(args):
         "step_tflops": {"achieved": step_tf, "peak_sustained": pk["bf16_sustained"], "frac": step_tf / pk["bf16_sustained"],
                         "flops_per_step": step_flops(B), "note": "necessary algorithmic FLOPs (SURVEY 8d) / step time"},
     }
+    if world == 1:
+        line["inference"] = time_inference(torch, T, O, dev, tr)
+        line["inference"]["frac_of_sustained_peak"] = line["inference"]["tflops"] / pk["bf16_sustained"]
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line), flush=True)
