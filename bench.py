@@ -227,8 +227,10 @@ def run_ours(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
+    th0 = time.perf_counter()
     for _ in range(args.steps):
         out = tr.train_step(devb, 0)
+    host_ms = (time.perf_counter() - th0) * 1000.0 / args.steps      # time to ENQUEUE one step
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -264,7 +266,7 @@ def run_ours(args):
                    "parallelism": f"dp{world}", "l2": "working set >> L2 (tens of GB of activations per step)",
                    "accumulate": "fp32", "loss_epoch": 0},
         "e2e": {"value": e2e, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": ach / pk["bf16_burst"],
                      "traffic": None, "kernel": "fprop_kernel<256> conv3x3 256->256 @64x64, batch %d" % B,

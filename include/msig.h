@@ -61,7 +61,18 @@ typedef struct msig_epilogue {
   const float* alpha_ptr; /* optional DEVICE scalar multiplied into alpha (upstream loss gradient) */
   float slope;            /* LeakyReLU slope */
   int32_t out_layout;     /* MSIG_OUT_* */
+  /* Optional fused per-(image, channel) reductions of the stored output v (bf16 NHWC outputs,
+   * k >= 64): stats_partial receives [rows][2][ld] fp32 partial sums, rows = 4 per 128-pixel output
+   * tile (msig_epilogue_stats_rows), ld = k rounded up to 64; q=0: sum v, q=1: sum v*v, or sum v*z
+   * when stats_z (bf16, shaped like the output) is given. They replace the separate statistics pass
+   * of InstanceNorm / AdaIN (model.py:16) and the two reductions of its backward; finish them with
+   * msig_in_stats_from_partials / msig_norm_bwd_from_partials. */
+  float* stats_partial;
+  const void* stats_z;
 } msig_epilogue;
+/* rows of stats_partial PER IMAGE for an output plane oh x ow produced in `phases` (1, or 4 for the
+ * k4 s2 transposed conv / stride-2 dgrad, where oh x ow is the per-phase plane = the INPUT plane). */
+int32_t msig_epilogue_stats_rows(int32_t oh, int32_t ow, int32_t phases);
 
 /* ---- weight packing --------------------------------------------------------------------
  * Master weights stay fp32 in the reference's state_dict layout (OIHW; ConvTranspose2d IOHW;
@@ -169,6 +180,19 @@ int msig_norm_act_bwd(const void* dy, const void* x, const float* mean, const fl
                       float* dgamma, float* dbeta, int64_t dgb_stride, int accumulate_dgb,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Finish epilogue-fused reductions (msig_epilogue.stats_partial): same results as msig_in_stats /
+ * msig_norm_act_bwd without re-reading the activation for the reduction. For the backward form the
+ * epilogue must already have applied act' to dy (aux mask), i.e. `g` is dy*act'(u), and stats_z = x. */
+int msig_in_stats_from_partials(const float* partial, int32_t n, int32_t rows_per_img, int32_t ld,
+                                int32_t hw, int32_t c, float eps, const float* gamma, const float* beta,
+                                int64_t gb_stride, float* mean, float* rstd, float* scale, float* shift,
+                                void* stream);
+int msig_norm_bwd_from_partials(const float* partial, int32_t n, int32_t rows_per_img, int32_t ld,
+                                const void* g, const void* x, const float* mean, const float* rstd,
+                                const float* scale, const float* shift, int32_t hw, int32_t c, void* dx,
+                                float* dgamma, float* dbeta, int64_t dgb_stride, int accumulate_dgb,
+                                float* coef_workspace /* [n][2][c] fp32 */, void* stream);
+
 /* ---- small bandwidth ops ------------------------------------------------------------------ */
 /* dz = dy * act'(y) (ReLU / LeakyReLU), bf16 */
 int msig_act_bwd(const void* dy, const void* y, int32_t act, float slope, int64_t numel, void* dz,
@@ -236,6 +260,12 @@ int msig_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
                    float* ema /* may be NULL */, int64_t numel, const float* grad_sumsq, float max_norm,
                    float grad_scale, float lr, float beta1, float beta2, float eps, int32_t step,
                    float ema_beta, void* stream);
+/* Same, with the step number kept in DEVICE memory: increments *step_counter, then uses it for the
+ * bias corrections, so the call has no per-step host argument and can be replayed from a CUDA graph. */
+int msig_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
+                       float* ema /* may be NULL */, int64_t numel, const float* grad_sumsq, float max_norm,
+                       float grad_scale, float lr, float beta1, float beta2, float eps,
+                       int32_t* step_counter, float ema_beta, void* stream);
 
 #ifdef __cplusplus
 }

@@ -271,6 +271,11 @@ static int fill_epilogue(FpropParams& p, const msig_epilogue* e, const OutView& 
     return set_error(MSIG_ERR_UNSUPPORTED, "bf16 NHWC output needs k %% 8 == 0 (k=%d)", n_valid);
   if ((p.bias != nullptr) && !ov.f32 && (reinterpret_cast<uintptr_t>(p.bias) & 15) != 0)
     return set_error(MSIG_ERR_ARG, "bias pointer must be 16-byte aligned");
+  p.stat_out = e ? e->stats_partial : nullptr;
+  p.stat_z = e ? reinterpret_cast<const __nv_bfloat16*>(e->stats_z) : nullptr;
+  p.stat_ld = static_cast<int>(round_up(n_valid, 64));
+  if (p.stat_out != nullptr && (ov.f32 || ov.sC != 1 || n_valid < 64 || p.fold_c != 0 || p.tap_is_image))
+    return set_error(MSIG_ERR_UNSUPPORTED, "epilogue statistics need a bf16 NHWC output with k >= 64");
   return MSIG_OK;
 }
 
@@ -435,6 +440,12 @@ __global__ void sum_splits_kernel(const float* __restrict__ partial, int splits,
 using namespace msig;
 
 extern "C" {
+
+int32_t msig_epilogue_stats_rows(int32_t oh, int32_t ow, int32_t phases) {
+  int TW, TH;
+  pick_tile(ow, TW, TH);
+  return static_cast<int32_t>(ceil_div(oh, TH) * ceil_div(ow, TW) * phases * 4);
+}
 
 // Test hook: selects the kernel variant of the narrow-output 7x7 conv (see run_conv).
 int msig_debug_set_strip_mode(int mode) {

@@ -46,18 +46,62 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
-// Epilogue for NC accumulator columns of one output pixel (thread-per-row).
+// Column sums over the 32 lanes of a warp for 32 per-lane values (a 32x32 transpose-reduce:
+// 31 shuffles instead of 160). On return lane l holds the total of column l in v[0].
+__device__ __forceinline__ float warp_col_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = up ? v[i] : v[i + off];
+      const float keep = up ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// Loads the epilogue's global operands for NC columns of one output pixel: `av` = aux (residual /
+// activation mask source), `zv` = stat_z. Issued one chunk ahead of their use so their latency hides
+// behind the previous chunk (and, for the first chunk, behind the tile's main loop).
 template <int NC>
+__device__ __forceinline__ void epilogue_load(const FpropParams& p, int col0, bool row_valid, int64_t out_off,
+                                              int64_t aux_off, uint4 (&av)[NC / 8], uint4 (&zv)[NC / 8]) {
+#pragma unroll
+  for (int g = 0; g < NC / 8; ++g) {
+    const int c = col0 + 8 * g;
+    const bool live = row_valid && (c + 8 <= p.n_valid);
+    if (live && p.aux_mode != AUX_NONE) av[g] = __ldg(reinterpret_cast<const uint4*>(p.aux + aux_off + c));
+    if (live && p.stat_z != nullptr) zv[g] = __ldg(reinterpret_cast<const uint4*>(p.stat_z + out_off + c));
+  }
+}
+
+// Epilogue for NC accumulator columns of one output pixel (thread-per-row). With STATS the warp
+// also reduces the stored values over its 32 pixels (see FpropParams::stat_out); `stat_row` is the
+// partial-sum row of this warp and `stat_col` the GEMM column of r[0].
+template <int NC, bool STATS>
 __device__ __forceinline__ void fprop_epilogue_chunk(const FpropParams& p, const uint32_t (&r)[NC],
-                                                     int col0, bool row_valid, int64_t out_off,
-                                                     int64_t aux_off, float alpha) {
-  if (!row_valid) return;
+                                                     const uint4 (&av)[NC / 8], const uint4 (&zv)[NC / 8],
+                                                     int col0, bool row_valid, int64_t out_off, float alpha,
+                                                     int64_t stat_row = 0, int stat_col = 0, int lane = 0) {
+  if (!STATS && !row_valid) return;
   if (!p.out_f32 && p.o_sc == 1) {
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+    float sv[STATS ? NC : 1], sq[STATS ? NC : 1];
 #pragma unroll
     for (int g = 0; g < NC / 8; ++g) {
       const int c = col0 + 8 * g;
-      if (c + 8 > p.n_valid) continue;
+      const bool live = row_valid && (c + 8 <= p.n_valid);
+      if (STATS) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sv[8 * g + j] = sq[8 * g + j] = 0.f;
+      }
+      if (!live) continue;
       float v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[8 * g + j]) * alpha;
@@ -68,8 +112,7 @@ __device__ __forceinline__ void fprop_epilogue_chunk(const FpropParams& p, const
         v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
       }
       if (p.aux_mode != AUX_NONE) {
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p.aux + aux_off + c));
-        const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+        const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&av[g]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = __bfloat1622float2(ah[j]);
@@ -95,8 +138,30 @@ __device__ __forceinline__ void fprop_epilogue_chunk(const FpropParams& p, const
       o.z = pack_bf16x2(v[4], v[5]);
       o.w = pack_bf16x2(v[6], v[7]);
       *reinterpret_cast<uint4*>(out + out_off + c) = o;
+      if (STATS) {
+        // statistics of the values as stored (bf16-rounded): what the consumer will normalise
+        const __nv_bfloat162* oh2 = reinterpret_cast<const __nv_bfloat162*>(&o);
+        const __nv_bfloat162* zh = (p.stat_z != nullptr) ? reinterpret_cast<const __nv_bfloat162*>(&zv[g]) : oh2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __bfloat1622float2(oh2[j]);
+          const float2 z = __bfloat1622float2(zh[j]);
+          sv[8 * g + 2 * j] = f.x;
+          sv[8 * g + 2 * j + 1] = f.y;
+          sq[8 * g + 2 * j] = f.x * z.x;
+          sq[8 * g + 2 * j + 1] = f.y * z.y;
+        }
+      }
+    }
+    if constexpr (STATS && NC == 32) {
+      const float s1 = warp_col_reduce32(sv, lane);
+      const float s2 = warp_col_reduce32(sq, lane);
+      float* so = p.stat_out + stat_row * 2 * p.stat_ld + stat_col + lane;
+      so[0] = s1;
+      so[p.stat_ld] = s2;
     }
   } else {
+    if (!row_valid) return;
     // generic strided path (fp32 outputs, narrow channel counts)
 #pragma unroll
     for (int j = 0; j < NC; ++j) {
@@ -250,29 +315,76 @@ __global__ void __launch_bounds__(256, 1) fprop_kernel(const __grid_constant__ F
       const bool row_valid = (oh < p.OH) && (ow < p.OW);
       const int64_t out_off = p.o_ph[ph] + img * p.o_sn + oh * p.o_sh + ow * p.o_sw;
       const int64_t aux_off = p.a_ph[ph] + img * p.a_sn + oh * p.a_sh + ow * p.a_sw;
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
       if constexpr (BLOCK_N == 16) {
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
         uint32_t r[16];
+        uint4 av[2], zv[2];
+        epilogue_load<16>(p, n_blk * BLOCK_N, row_valid, out_off, aux_off, av, zv);
         tmem_ld_32x16(taddr, r);
         tmem_ld_wait();
-        fprop_epilogue_chunk<16>(p, r, n_blk * BLOCK_N, row_valid, out_off, aux_off, alpha);
+        fprop_epilogue_chunk<16, false>(p, r, av, zv, n_blk * BLOCK_N, row_valid, out_off, alpha);
       } else {
-#pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c, r);
-          tmem_ld_wait();
-          int col = n_blk * BLOCK_N + c;
-          int64_t oo = out_off, ao = aux_off;
+        const int64_t stat_row = int64_t(tile / p.n_blocks) * 4 + q;
+        // (column, output offset, aux offset) of accumulator chunk c
+        auto locate = [&](int c, int& col, int64_t& oo, int64_t& ao) {
+          col = n_blk * BLOCK_N + c;
+          oo = out_off;
+          ao = aux_off;
           if (p.fold_c > 0) {                 // column -> (image, channel)
             const int img_o = col / p.fold_c;
             col -= img_o * p.fold_c;
             oo += img_o * p.o_sn;
             ao += img_o * p.a_sn;
           }
-          fprop_epilogue_chunk<32>(p, r, col, row_valid, oo, ao, alpha);
+        };
+        // While the main loop of this tile is still running: pull the tile's aux / stat_z rows into L2
+        // and the first chunk's operands into registers.
+        const bool has_aux = p.aux_mode != AUX_NONE, has_z = p.stat_z != nullptr;
+        uint4 pa[4], pz[4];
+        if (has_aux || has_z) {
+          if (row_valid) {
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N; c += 64) {
+              int col;
+              int64_t oo, ao;
+              locate(c, col, oo, ao);
+              if (has_aux) prefetch_l2(p.aux + ao + col);
+              if (has_z) prefetch_l2(p.stat_z + oo + col);
+            }
+          }
+          int col;
+          int64_t oo, ao;
+          locate(0, col, oo, ao);
+          epilogue_load<32>(p, col, row_valid, oo, ao, pa, pz);
+        }
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32(taddr + c, r);
+          uint4 ca[4], cz[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            ca[g] = pa[g];
+            cz[g] = pz[g];
+          }
+          if ((has_aux || has_z) && c + 32 < BLOCK_N) {
+            int ncol;
+            int64_t noo, nao;
+            locate(c + 32, ncol, noo, nao);
+            epilogue_load<32>(p, ncol, row_valid, noo, nao, pa, pz);
+          }
+          int col;
+          int64_t oo, ao;
+          locate(c, col, oo, ao);
+          tmem_ld_wait();
+          if (p.stat_out != nullptr)
+            fprop_epilogue_chunk<32, true>(p, r, ca, cz, col, row_valid, oo, alpha, stat_row, n_blk * BLOCK_N + c, lane);
+          else
+            fprop_epilogue_chunk<32, false>(p, r, ca, cz, col, row_valid, oo, alpha);
         }
       }
       tc_fence_before();
@@ -423,7 +535,8 @@ __global__ void __launch_bounds__(256, 1) fprop_strip16_kernel(const __grid_cons
       uint32_t r16[16];
       tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 16, r16);
       tmem_ld_wait();
-      fprop_epilogue_chunk<16>(p, r16, 0, row_valid, out_off, 0, alpha);
+      uint4 av16[2], zv16[2];
+      fprop_epilogue_chunk<16, false>(p, r16, av16, zv16, 0, row_valid, out_off, alpha);
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
     }

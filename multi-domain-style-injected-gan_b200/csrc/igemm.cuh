@@ -53,6 +53,13 @@ struct FpropParams {
   const __nv_bfloat16* aux;        // channel-contiguous tensor congruent with the output tile
   int64_t a_sn, a_sh, a_sw;
   int32_t aux_mode;
+  // per-(image, channel) partial sums of the stored values v, produced by the epilogue (bf16 NHWC
+  // outputs only): stat_out[(m_tile*4 + warp)*2 + q][stat_ld], q = 0: sum v, q = 1: sum v*v
+  // (stat_z == nullptr: InstanceNorm statistics) or sum v*z (stat_z congruent with the output:
+  // the two reductions of the InstanceNorm / AdaIN backward). An m-tile never spans two images.
+  float* stat_out;
+  const __nv_bfloat16* stat_z;
+  int32_t stat_ld;
 };
 
 // ---- "wgrad" kernel: D[m, n] = sum_{pixels} A[pixel + tapA, m] * B[pixel + tapB, n]

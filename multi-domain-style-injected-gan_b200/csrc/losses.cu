@@ -164,11 +164,21 @@ __global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __re
   block_atomic_add(s, 1.f, out);
 }
 
+__global__ void counter_inc_kernel(int32_t* c) { *c += 1; }
+
 // clip_grad_norm_(max_norm) + Adam (torch defaults: no weight decay, no amsgrad) + EMA, one pass.
+// step_dev != nullptr: the step number (bias corrections) comes from device memory, so the launch can
+// be replayed from a CUDA graph.
 __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                  float* __restrict__ v, float* __restrict__ ema, int64_t n,
                                  const float* __restrict__ grad_sumsq, float max_norm, float grad_scale, float lr,
-                                 float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float ema_beta) {
+                                 float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float ema_beta,
+                                 const int32_t* __restrict__ step_dev) {
+  if (step_dev != nullptr) {
+    const double st = double(__ldg(step_dev));
+    bc1 = float(1.0 - pow(double(beta1), st));
+    bc2_sqrt = float(sqrt(1.0 - pow(double(beta2), st)));
+  }
   float coef = grad_scale;
   if (grad_sumsq != nullptr && max_norm > 0.f) {
     const float total = sqrtf(__ldg(grad_sumsq)) * grad_scale;
@@ -282,8 +292,21 @@ int msig_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
   const double bc2 = 1.0 - pow(double(beta2), double(step));
   adam_step_kernel<<<lgrid(numel, 256), 256, 0, ST(stream)>>>(param, grad, exp_avg, exp_avg_sq, ema, numel,
                                                              grad_sumsq, max_norm, grad_scale, lr, beta1, beta2, eps,
-                                                             float(bc1), float(sqrt(bc2)), ema_beta);
+                                                             float(bc1), float(sqrt(bc2)), ema_beta, nullptr);
   count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+int msig_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* ema, int64_t numel,
+                       const float* grad_sumsq, float max_norm, float grad_scale, float lr, float beta1, float beta2,
+                       float eps, int32_t* step_counter, float ema_beta, void* stream) {
+  MSIG_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_counter && numel > 0, "msig_adam_step_dev: bad argument");
+  counter_inc_kernel<<<1, 1, 0, ST(stream)>>>(step_counter);
+  MSIG_CHECK_LAUNCH();
+  adam_step_kernel<<<lgrid(numel, 256), 256, 0, ST(stream)>>>(param, grad, exp_avg, exp_avg_sq, ema, numel,
+                                                             grad_sumsq, max_norm, grad_scale, lr, beta1, beta2, eps,
+                                                             1.f, 1.f, ema_beta, step_counter);
+  count_launch(2);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
 }

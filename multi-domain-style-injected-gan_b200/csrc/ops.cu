@@ -236,19 +236,59 @@ __global__ void reflect_pad_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int
 }
 
 // ---------------------------------------------------------------- per-(n,c) reductions
-// Block = 256 threads = (c/8) channel groups x (2048/c) pixel lanes; grid = (chunks, n).
-// MODE 0: sum x, sum x^2 (statistics)   MODE 1: sum g, sum g*xhat (norm backward), g = dy*act'(u)
+// Block = 256 threads = (c/8) channel groups x (2048/c) pixel lanes; grid = (chunks, n). Every thread
+// keeps kUnroll independent 16-byte loads in flight per operand (HBM latency x bandwidth needs
+// ~36 KB in flight per SM). The last block of an image to finish (ticket counter in the workspace,
+// reset by that block) folds the per-chunk partials into the per-(n,c) results, in chunk order, so
+// the result is deterministic and no separate finalize launch is needed.
+// MODE 0: sum x, sum x^2 -> mean/rstd/scale/shift (statistics)
+// MODE 1: sum g, sum g*xhat -> coef, dgamma, dbeta (norm backward), g = dy*act'(u)
+constexpr int kUnroll = 4;
+
+__device__ __forceinline__ uint4 ldg_stream(const __nv_bfloat16* p) {
+  return __ldg(reinterpret_cast<const uint4*>(p));
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 t = __bfloat1622float2(h[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+
+struct NcFinal {
+  // MODE 0
+  float eps;
+  const float* gamma;
+  const float* beta;
+  int64_t gb_stride;
+  float* mean_out;
+  float* rstd_out;
+  float* scale_out;
+  float* shift_out;
+  // MODE 1
+  float* coef;
+  float* dgamma;
+  float* dbeta;
+  int64_t dgb_stride;
+  int accumulate;
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(256) nc_reduce_kernel(
     const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
     const float* __restrict__ shift, int act, float slope, int hw, int c, int pix_per_block,
-    float* __restrict__ partial) {
+    float* __restrict__ partial, unsigned int* __restrict__ tickets, NcFinal fin) {
   __shared__ float red[16][256 + 1];
+  __shared__ bool is_last;
   const int cg = c / 8;
   const int lanes = 256 / cg;
   const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
   const int img = blockIdx.y, chunk = blockIdx.x;
+  const int chunks = gridDim.x;
   const int p0 = chunk * pix_per_block;
   const int p1 = min(p0 + pix_per_block, hw);
   float a[8], b[8];
@@ -263,24 +303,38 @@ __global__ void __launch_bounds__(256) nc_reduce_kernel(
     }
   }
   const int64_t base = int64_t(img) * hw * c + tx * 8;
-  for (int p = p0 + ty; p < p1; p += lanes) {
-    float xf[8];
-    load8(x + base + int64_t(p) * c, xf);
-    if (MODE == 0) {
+  for (int p = p0 + ty; p < p1; p += kUnroll * lanes) {
+    uint4 xv[kUnroll], dv[kUnroll];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        a[j] += xf[j];
-        b[j] += xf[j] * xf[j];
+    for (int u = 0; u < kUnroll; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p1) {
+        xv[u] = ldg_stream(x + base + int64_t(pp) * c);
+        if (MODE == 1) dv[u] = ldg_stream(dy + base + int64_t(pp) * c);
       }
-    } else {
-      float df[8];
-      load8(dy + base + int64_t(p) * c, df);
+    }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float u = xf[j] * sc[j] + sh[j];
-        const float gq = df[j] * act_grad(u, act, slope);
-        a[j] += gq;
-        b[j] += gq * (xf[j] - mu[j]) * rs[j];
+    for (int u = 0; u < kUnroll; ++u) {
+      if (p + u * lanes < p1) {
+        float xf[8];
+        unpack8(xv[u], xf);
+        if (MODE == 0) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            a[j] += xf[j];
+            b[j] += xf[j] * xf[j];
+          }
+        } else {
+          float df[8];
+          unpack8(dv[u], df);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float uu = xf[j] * sc[j] + sh[j];
+            const float gq = df[j] * act_grad(uu, act, slope);
+            a[j] += gq;
+            b[j] += gq * (xf[j] - mu[j]) * rs[j];
+          }
+        }
       }
     }
   }
@@ -296,53 +350,113 @@ __global__ void __launch_bounds__(256) nc_reduce_kernel(
     const int gx = ch / 8, j = ch % 8;
     float s = 0.f;
     for (int l = 0; l < lanes; ++l) s += red[q * 8 + j][l * cg + gx];
-    partial[((int64_t(img) * gridDim.x + chunk) * 2 + q) * c + ch] = s;
+    partial[((int64_t(img) * chunks + chunk) * 2 + q) * c + ch] = s;
+  }
+  // ---- last block of this image finalizes
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(&tickets[img], 1u);
+    is_last = (t == static_cast<unsigned int>(chunks) - 1u);
+    if (is_last) tickets[img] = 0u;       // self-cleaning for the next call on this workspace
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int ch = threadIdx.x; ch < c; ch += 256) {
+    double s1 = 0.0, s2 = 0.0;
+    const float* pp = partial + int64_t(img) * chunks * 2 * c + ch;
+    for (int k = 0; k < chunks; ++k) {
+      s1 += __ldcg(pp + (int64_t(k) * 2 + 0) * c);
+      s2 += __ldcg(pp + (int64_t(k) * 2 + 1) * c);
+    }
+    if (MODE == 0) {
+      const double m = s1 / hw;
+      double var = s2 / hw - m * m;
+      if (var < 0.0) var = 0.0;
+      const float r = static_cast<float>(1.0 / sqrt(var + double(fin.eps)));
+      const float gm = fin.gamma ? fin.gamma[img * fin.gb_stride + ch] : 1.f;
+      const float bt = fin.beta ? fin.beta[img * fin.gb_stride + ch] : 0.f;
+      const int o = img * c + ch;
+      fin.mean_out[o] = static_cast<float>(m);
+      fin.rstd_out[o] = r;
+      fin.scale_out[o] = gm * r;
+      fin.shift_out[o] = bt - static_cast<float>(m) * gm * r;
+    } else {
+      fin.coef[(int64_t(img) * 2 + 0) * c + ch] = static_cast<float>(s1 / hw);
+      fin.coef[(int64_t(img) * 2 + 1) * c + ch] = static_cast<float>(s2 / hw);
+      if (fin.dgamma != nullptr) {
+        const int64_t o = img * fin.dgb_stride + ch;
+        fin.dgamma[o] = (fin.accumulate ? fin.dgamma[o] : 0.f) + static_cast<float>(s2);
+        fin.dbeta[o] = (fin.accumulate ? fin.dbeta[o] : 0.f) + static_cast<float>(s1);
+      }
+    }
   }
 }
 
-__global__ void in_stats_finalize_kernel(const float* __restrict__ partial, int chunks, int hw, int c,
-                                         float eps, const float* __restrict__ gamma,
-                                         const float* __restrict__ beta, int64_t gb_stride,
-                                         float* __restrict__ mean, float* __restrict__ rstd,
-                                         float* __restrict__ scale, float* __restrict__ shift) {
+// Folds the partial sums written by the implicit-GEMM epilogue (FpropParams::stat_out:
+// [img*rows + r][2][ld]) into the per-(image, channel) results. Block = 8 row lanes x 32 channels.
+// MODE 0: sum v, sum v^2 -> mean/rstd/scale/shift.  MODE 1: sum g, sum g*z -> coef, dgamma, dbeta.
+template <int MODE>
+__global__ void __launch_bounds__(1024) epi_stats_finalize_kernel(const float* __restrict__ partial, int rows,
+                                                                  int ld, int hw, int c,
+                                                                  const float* __restrict__ mean,
+                                                                  const float* __restrict__ rstd, NcFinal fin) {
+  __shared__ double red[2][32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 channels x 32 row lanes
   const int img = blockIdx.y;
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
-  double s = 0.0, ss = 0.0;
-  for (int k = 0; k < chunks; ++k) {
-    s += partial[((int64_t(img) * chunks + k) * 2 + 0) * c + ch];
-    ss += partial[((int64_t(img) * chunks + k) * 2 + 1) * c + ch];
-  }
-  const double m = s / hw;
-  double var = ss / hw - m * m;
-  if (var < 0.0) var = 0.0;
-  const float r = static_cast<float>(1.0 / sqrt(var + double(eps)));
-  const float gm = gamma ? gamma[img * gb_stride + ch] : 1.f;
-  const float bt = beta ? beta[img * gb_stride + ch] : 0.f;
-  const int o = img * c + ch;
-  mean[o] = static_cast<float>(m);
-  rstd[o] = r;
-  scale[o] = gm * r;
-  shift[o] = bt - static_cast<float>(m) * gm * r;
-}
-
-__global__ void norm_bwd_finalize_kernel(const float* __restrict__ partial, int chunks, int hw, int c,
-                                         float* __restrict__ coef, float* __restrict__ dgamma,
-                                         float* __restrict__ dbeta, int64_t dgb_stride, int accumulate) {
-  const int img = blockIdx.y;
-  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
+  const int ch = blockIdx.x * 32 + tx;
   double s1 = 0.0, s2 = 0.0;
-  for (int k = 0; k < chunks; ++k) {
-    s1 += partial[((int64_t(img) * chunks + k) * 2 + 0) * c + ch];
-    s2 += partial[((int64_t(img) * chunks + k) * 2 + 1) * c + ch];
+  if (ch < c) {
+    const float* pp = partial + int64_t(img) * rows * 2 * ld + ch;
+    for (int r0 = ty; r0 < rows; r0 += 32 * 8) {
+      float a[8], b[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {            // 16 independent loads in flight per thread
+        const int r = r0 + 32 * u;
+        a[u] = b[u] = 0.f;
+        if (r < rows) {
+          a[u] = __ldg(pp + int64_t(r) * 2 * ld);
+          b[u] = __ldg(pp + int64_t(r) * 2 * ld + ld);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        s1 += a[u];
+        s2 += b[u];
+      }
+    }
   }
-  coef[(int64_t(img) * 2 + 0) * c + ch] = static_cast<float>(s1 / hw);
-  coef[(int64_t(img) * 2 + 1) * c + ch] = static_cast<float>(s2 / hw);
-  if (dgamma != nullptr) {
-    const int64_t o = img * dgb_stride + ch;
-    dgamma[o] = (accumulate ? dgamma[o] : 0.f) + static_cast<float>(s2);
-    dbeta[o] = (accumulate ? dbeta[o] : 0.f) + static_cast<float>(s1);
+  red[0][ty][tx] = s1;
+  red[1][ty][tx] = s2;
+  __syncthreads();
+  if (ty != 0 || ch >= c) return;
+  for (int l = 1; l < 32; ++l) {
+    s1 += red[0][l][tx];
+    s2 += red[1][l][tx];
+  }
+  if (MODE == 0) {
+    const double m = s1 / hw;
+    double var = s2 / hw - m * m;
+    if (var < 0.0) var = 0.0;
+    const float r = static_cast<float>(1.0 / sqrt(var + double(fin.eps)));
+    const float gm = fin.gamma ? fin.gamma[img * fin.gb_stride + ch] : 1.f;
+    const float bt = fin.beta ? fin.beta[img * fin.gb_stride + ch] : 0.f;
+    const int o = img * c + ch;
+    fin.mean_out[o] = static_cast<float>(m);
+    fin.rstd_out[o] = r;
+    fin.scale_out[o] = gm * r;
+    fin.shift_out[o] = bt - static_cast<float>(m) * gm * r;
+  } else {
+    const int o = img * c + ch;
+    const double sgx = double(rstd[o]) * (s2 - double(mean[o]) * s1);   // sum g*xhat
+    fin.coef[(int64_t(img) * 2 + 0) * c + ch] = static_cast<float>(s1 / hw);
+    fin.coef[(int64_t(img) * 2 + 1) * c + ch] = static_cast<float>(sgx / hw);
+    if (fin.dgamma != nullptr) {
+      const int64_t oo = img * fin.dgb_stride + ch;
+      fin.dgamma[oo] = (fin.accumulate ? fin.dgamma[oo] : 0.f) + static_cast<float>(sgx);
+      fin.dbeta[oo] = (fin.accumulate ? fin.dbeta[oo] : 0.f) + static_cast<float>(s1);
+    }
   }
 }
 
@@ -364,18 +478,33 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(
     sh[j] = shift[img * c + tx * 8 + j];
   }
   const int64_t base = int64_t(img) * hw * c + tx * 8;
-  for (int p = p0 + ty; p < p1; p += lanes) {
-    float f[8];
-    load8(x + base + int64_t(p) * c, f);
+  for (int p = p0 + ty; p < p1; p += kUnroll * lanes) {
+    uint4 xv[kUnroll], rv[kUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = act_fwd(f[j] * sc[j] + sh[j], act, slope);
-    if (res != nullptr) {
-      float rf[8];
-      load8(res + base + int64_t(p) * c, rf);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] += rf[j];
+    for (int u = 0; u < kUnroll; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p1) {
+        xv[u] = ldg_stream(x + base + int64_t(pp) * c);
+        if (res != nullptr) rv[u] = ldg_stream(res + base + int64_t(pp) * c);
+      }
     }
-    store8(y + base + int64_t(p) * c, f);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p1) {
+        float f[8];
+        unpack8(xv[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = act_fwd(f[j] * sc[j] + sh[j], act, slope);
+        if (res != nullptr) {
+          float rf[8];
+          unpack8(rv[u], rf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += rf[j];
+        }
+        store8(y + base + int64_t(pp) * c, f);
+      }
+    }
   }
 }
 
@@ -391,27 +520,45 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(
   const int img = blockIdx.y;
   const int p0 = blockIdx.x * pix_per_block;
   const int p1 = min(p0 + pix_per_block, hw);
-  float mu[8], rs[8], sc[8], sh[8], c1[8], c2[8];
+  // dx = k0*g + k1*x + k2 with k0 = scale, k1 = -scale*rstd*c2, k2 = -scale*(c1 - mean*rstd*c2)
+  float sc[8], sh[8], k1[8], k2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int ch = img * c + tx * 8 + j;
-    mu[j] = mean[ch]; rs[j] = rstd[ch]; sc[j] = scale[ch]; sh[j] = shift[ch];
-    c1[j] = coef[(int64_t(img) * 2 + 0) * c + tx * 8 + j];
-    c2[j] = coef[(int64_t(img) * 2 + 1) * c + tx * 8 + j];
+    const float mu = mean[ch], rs = rstd[ch];
+    sc[j] = scale[ch]; sh[j] = shift[ch];
+    const float c1 = coef[(int64_t(img) * 2 + 0) * c + tx * 8 + j];
+    const float c2 = coef[(int64_t(img) * 2 + 1) * c + tx * 8 + j];
+    k1[j] = -sc[j] * rs * c2;
+    k2[j] = -sc[j] * (c1 - mu * rs * c2);
   }
   const int64_t base = int64_t(img) * hw * c + tx * 8;
-  for (int p = p0 + ty; p < p1; p += lanes) {
-    float xf[8], df[8];
-    load8(x + base + int64_t(p) * c, xf);
-    load8(dy + base + int64_t(p) * c, df);
+  for (int p = p0 + ty; p < p1; p += kUnroll * lanes) {
+    uint4 xv[kUnroll], dv[kUnroll];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float u = xf[j] * sc[j] + sh[j];
-      const float gq = df[j] * act_grad(u, act, slope);
-      const float xh = (xf[j] - mu[j]) * rs[j];
-      df[j] = sc[j] * (gq - c1[j] - xh * c2[j]);
+    for (int u = 0; u < kUnroll; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p1) {
+        xv[u] = ldg_stream(x + base + int64_t(pp) * c);
+        dv[u] = ldg_stream(dy + base + int64_t(pp) * c);
+      }
     }
-    store8(dx + base + int64_t(p) * c, df);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p1) {
+        float xf[8], df[8];
+        unpack8(xv[u], xf);
+        unpack8(dv[u], df);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float uu = xf[j] * sc[j] + sh[j];
+          const float gq = df[j] * act_grad(uu, act, slope);
+          df[j] = sc[j] * gq + (k1[j] * xf[j] + k2[j]);
+        }
+        store8(dx + base + int64_t(pp) * c, df);
+      }
+    }
   }
 }
 
@@ -728,10 +875,11 @@ int msig_reflect_pad_bwd(const void* dy, int32_t n, int32_t h, int32_t w, int32_
 
 static bool norm_c_ok(int c) { return c == 64 || c == 128 || c == 256 || c == 512; }
 
+// workspace: partial [n][chunks][2][c] f32 | coef [n][2][c] f32 | tickets [n] u32
 size_t msig_in_stats_workspace(int32_t n, int32_t hw, int32_t c) {
   const int ppb = pick_pix_per_block(n, hw);
   const size_t chunks = static_cast<size_t>(ceil_div(hw, ppb));
-  return (size_t(n) * chunks * 2 * c + size_t(n) * 2 * c) * sizeof(float);
+  return (size_t(n) * chunks * 2 * c + size_t(n) * 2 * c + size_t(n)) * sizeof(float);
 }
 
 int msig_in_stats(const void* x, int32_t n, int32_t hw, int32_t c, float eps, const float* gamma,
@@ -743,12 +891,14 @@ int msig_in_stats(const void* x, int32_t n, int32_t hw, int32_t c, float eps, co
   const int ppb = pick_pix_per_block(n, hw);
   const int chunks = static_cast<int>(ceil_div(hw, ppb));
   float* partial = reinterpret_cast<float*>(workspace);
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(partial + size_t(n) * chunks * 2 * c + size_t(n) * 2 * c);
+  MSIG_CHECK_CUDA(cudaMemsetAsync(tickets, 0, size_t(n) * sizeof(unsigned int), ST(stream)));
+  NcFinal fin{};
+  fin.eps = eps; fin.gamma = gamma; fin.beta = beta; fin.gb_stride = gb_stride;
+  fin.mean_out = mean; fin.rstd_out = rstd; fin.scale_out = scale; fin.shift_out = shift;
   nc_reduce_kernel<0><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), nullptr, nullptr, nullptr, nullptr,
-                                                              nullptr, 0, 0.f, hw, c, ppb, partial);
-  MSIG_CHECK_LAUNCH();
-  in_stats_finalize_kernel<<<dim3(static_cast<unsigned>(ceil_div(c, 128)), n), 128, 0, ST(stream)>>>(
-      partial, chunks, hw, c, eps, gamma, beta, gb_stride, mean, rstd, scale, shift);
-  count_launch(2);
+                                                              nullptr, 0, 0.f, hw, c, ppb, partial, tickets, fin);
+  count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
 }
@@ -780,15 +930,53 @@ int msig_norm_act_bwd(const void* dy, const void* x, const float* mean, const fl
   const int chunks = static_cast<int>(ceil_div(hw, ppb));
   float* partial = reinterpret_cast<float*>(workspace);
   float* coef = partial + size_t(n) * chunks * 2 * c;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(coef + size_t(n) * 2 * c);
+  MSIG_CHECK_CUDA(cudaMemsetAsync(tickets, 0, size_t(n) * sizeof(unsigned int), ST(stream)));
+  NcFinal fin{};
+  fin.coef = coef; fin.dgamma = dgamma; fin.dbeta = dbeta; fin.dgb_stride = dgb_stride; fin.accumulate = accumulate_dgb;
   nc_reduce_kernel<1><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), CBF(dy), mean, rstd, scale, shift, act,
-                                                              slope, hw, c, ppb, partial);
-  MSIG_CHECK_LAUNCH();
-  norm_bwd_finalize_kernel<<<dim3(static_cast<unsigned>(ceil_div(c, 128)), n), 128, 0, ST(stream)>>>(
-      partial, chunks, hw, c, coef, dgamma, dbeta, dgb_stride, accumulate_dgb);
+                                                              slope, hw, c, ppb, partial, tickets, fin);
   MSIG_CHECK_LAUNCH();
   norm_act_bwd_kernel<<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(dy), CBF(x), mean, rstd, scale, shift, coef,
                                                               act, slope, hw, c, ppb, BF(dx));
-  count_launch(3);
+  count_launch(2);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
+int msig_in_stats_from_partials(const float* partial, int32_t n, int32_t rows_per_img, int32_t ld, int32_t hw,
+                                int32_t c, float eps, const float* gamma, const float* beta, int64_t gb_stride,
+                                float* mean, float* rstd, float* scale, float* shift, void* stream) {
+  MSIG_REQUIRE(partial && mean && rstd && scale && shift, "msig_in_stats_from_partials: null argument");
+  MSIG_REQUIRE(rows_per_img > 0 && ld >= c && c % 32 == 0, "msig_in_stats_from_partials: bad shape");
+  NcFinal fin{};
+  fin.eps = eps; fin.gamma = gamma; fin.beta = beta; fin.gb_stride = gb_stride;
+  fin.mean_out = mean; fin.rstd_out = rstd; fin.scale_out = scale; fin.shift_out = shift;
+  epi_stats_finalize_kernel<0><<<dim3(c / 32, n), 1024, 0, ST(stream)>>>(partial, rows_per_img, ld, hw, c, nullptr,
+                                                                        nullptr, fin);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
+int msig_norm_bwd_from_partials(const float* partial, int32_t n, int32_t rows_per_img, int32_t ld, const void* g,
+                                const void* x, const float* mean, const float* rstd, const float* scale,
+                                const float* shift, int32_t hw, int32_t c, void* dx, float* dgamma, float* dbeta,
+                                int64_t dgb_stride, int accumulate_dgb, float* coef, void* stream) {
+  MSIG_REQUIRE(partial && g && x && mean && rstd && scale && shift && dx && coef,
+               "msig_norm_bwd_from_partials: null argument");
+  MSIG_REQUIRE(norm_c_ok(c) && rows_per_img > 0 && ld >= c, "msig_norm_bwd_from_partials: bad shape");
+  MSIG_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "msig_norm_bwd_from_partials: dgamma/dbeta go together");
+  NcFinal fin{};
+  fin.coef = coef; fin.dgamma = dgamma; fin.dbeta = dbeta; fin.dgb_stride = dgb_stride; fin.accumulate = accumulate_dgb;
+  epi_stats_finalize_kernel<1><<<dim3(c / 32, n), 1024, 0, ST(stream)>>>(partial, rows_per_img, ld, hw, c, mean, rstd,
+                                                                        fin);
+  MSIG_CHECK_LAUNCH();
+  const int ppb = pick_pix_per_block(n, hw);
+  const int chunks = static_cast<int>(ceil_div(hw, ppb));
+  norm_act_bwd_kernel<<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(g), CBF(x), mean, rstd, scale, shift, coef,
+                                                              MSIG_ACT_NONE, 0.f, hw, c, ppb, BF(dx));
+  count_launch(2);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
 }

@@ -28,7 +28,7 @@ class ConvGeom(Structure):
 class Epilogue(Structure):
     _fields_ = [("bias", c_void_p), ("aux", c_void_p), ("aux_mode", c_int32), ("act", c_int32),
                 ("alpha", c_float), ("alpha_ptr", c_void_p), ("slope", c_float),
-                ("out_layout", c_int32)]
+                ("out_layout", c_int32), ("stats_partial", c_void_p), ("stats_z", c_void_p)]
 
 
 class WpackDesc(Structure):
@@ -76,6 +76,11 @@ _SIGS = {
                                   _P]),
     "msig_norm_act_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_float, c_int32,
                                   c_int32, c_int32, _P, _P, _P, c_int64, c_int, _P, c_size_t, _P]),
+    "msig_epilogue_stats_rows": (c_int32, [c_int32, c_int32, c_int32]),
+    "msig_in_stats_from_partials": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P,
+                                            c_int64, _P, _P, _P, _P, _P]),
+    "msig_norm_bwd_from_partials": (c_int, [_P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, c_int32,
+                                            c_int32, _P, _P, _P, c_int64, c_int, _P, _P]),
     "msig_act_bwd": (c_int, [_P, _P, c_int32, c_float, c_int64, _P, _P]),
     "msig_add_bf16": (c_int, [_P, _P, c_int64, _P, _P]),
     "msig_colsum": (c_int, [_P, c_int64, c_int32, _P, c_int, _P]),
@@ -105,6 +110,8 @@ _SIGS = {
     "msig_sumsq": (c_int, [_P, c_int64, _P, c_int, _P]),
     "msig_adam_step": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float,
                                c_float, c_float, c_int32, c_float, _P]),
+    "msig_adam_step_dev": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float,
+                                   c_float, c_float, _P, c_float, _P]),
 }
 
 _lib = None

@@ -36,6 +36,18 @@ def _require_cuda(t, what):
         raise RuntimeError(f"{what}: expected a CUDA tensor; msig_b200 has no CPU path")
 
 
+def _conv_stats(x, wpk, g, gamma=None, beta=None, gstride=0, transposed=False):
+    """conv (or k4 s2 transposed conv) whose epilogue also emits the InstanceNorm / AdaIN statistics of
+    its output: returns (z, NormStats). Replaces conv + a separate statistics pass (model.py:16,28-36)."""
+    if transposed:
+        es = ops.epi_stats(g.n, g.h, g.w, g.k, x.device, phases=4)
+        z = ops.convT2d_fwd(x, wpk, g, ops.epilogue(stats=es))
+    else:
+        es = ops.epi_stats(g.n, g.oh, g.ow, g.k, x.device)
+        z = ops.conv2d_fwd(x, wpk, g, ops.epilogue(stats=es))
+    return z, ops.in_stats_from(es, g.oh * g.ow, g.k, gamma, beta, gstride)
+
+
 class _PackedWeights:
     """bf16 packed copies of a module's fp32 master weights, rebuilt when the parameters change
     (detected through tensor versions plus an explicit dirty counter bumped by the fused optimizer,
@@ -249,17 +261,17 @@ class _GeneratorFn(torch.autograd.Function):
         pg0 = ops.patch_geom(B, 3, H, W, 7, 7, 1, 3, 3, H, W, True)
         a0 = ops.patch_gather_cached(img, pg0)
         m0 = B * H * W
-        z0 = ops.conv2d_fwd(a0.view(1, 1, m0, pg0.kpad), P["e0"], ops.gemm_geom(m0, pg0.kpad, 64)).view(B, H, W, 64)
+        es0 = ops.epi_stats_rows(B, H * W, 64, img.device)
+        z0 = ops.conv2d_fwd(a0.view(1, 1, m0, pg0.kpad), P["e0"], ops.gemm_geom(m0, pg0.kpad, 64),
+                            ops.epilogue(stats=es0)).view(B, H, W, 64)
         del a0
-        st0 = ops.in_stats(z0)
+        st0 = ops.in_stats_from(es0, H * W, 64) if es0 is not None else ops.in_stats(z0)
         y0 = ops.norm_act_fwd(z0, st0, ACT_RELU)
         g1 = ops.conv_geom(B, H, W, 64, 128, 4, 4, 2, 1, 1, H // 2, W // 2)
-        z1 = ops.conv2d_fwd(y0, P["e1"], g1)
-        st1 = ops.in_stats(z1)
+        z1, st1 = _conv_stats(y0, P["e1"], g1)
         y1 = ops.norm_act_fwd(z1, st1, ACT_RELU)
         g2 = ops.conv_geom(B, H // 2, W // 2, 128, 256, 4, 4, 2, 1, 1, H // 4, W // 4)
-        z2 = ops.conv2d_fwd(y1, P["e2"], g2)
-        st2 = ops.in_stats(z2)
+        z2, st2 = _conv_stats(y1, P["e2"], g2)
         x = ops.norm_act_fwd(z2, st2, ACT_RELU)
         # ---- all 2k style Linears in one GEMM (model.py:28)
         nl = 2 * k
@@ -273,22 +285,18 @@ class _GeneratorFn(torch.autograd.Function):
         res = []
         for i in range(k):
             l = 2 * i
-            za = ops.conv2d_fwd(x, P[f"r{i}0"], g3)
-            sta = ops.in_stats(za, gb[:, l * 512:], gb[:, l * 512 + 256:], gstride)
+            za, sta = _conv_stats(x, P[f"r{i}0"], g3, gb[:, l * 512:], gb[:, l * 512 + 256:], gstride)
             ha = ops.norm_act_fwd(za, sta, ACT_RELU)
-            zb = ops.conv2d_fwd(ha, P[f"r{i}1"], g3)
-            stb = ops.in_stats(zb, gb[:, (l + 1) * 512:], gb[:, (l + 1) * 512 + 256:], gstride)
+            zb, stb = _conv_stats(ha, P[f"r{i}1"], g3, gb[:, (l + 1) * 512:], gb[:, (l + 1) * 512 + 256:], gstride)
             xn = ops.norm_act_fwd(zb, stb, ACT_NONE, residual=x)
             res.append((x, za, sta, ha, zb, stb))
             x = xn
         # ---- decoder (model.py:139-141)
         gu1 = ops.conv_geom(B, h4, w4, 256, 128, 4, 4, 2, 1, 1, H // 2, W // 2)
-        zu1 = ops.convT2d_fwd(x, P["u1"], gu1)
-        stu1 = ops.in_stats(zu1)
+        zu1, stu1 = _conv_stats(x, P["u1"], gu1, transposed=True)
         yu1 = ops.norm_act_fwd(zu1, stu1, ACT_RELU)
         gu2 = ops.conv_geom(B, H // 2, W // 2, 128, 64, 4, 4, 2, 1, 1, H, W)
-        zu2 = ops.convT2d_fwd(yu1, P["u2"], gu2)
-        stu2 = ops.in_stats(zu2)
+        zu2, stu2 = _conv_stats(yu1, P["u2"], gu2, transposed=True)
         yu2 = ops.norm_act_fwd(zu2, stu2, ACT_RELU)
         xp = ops.reflect_pad_fwd(yu2, 3)
         gf = ops.conv_geom(B, H + 6, W + 6, 64, 3, 7, 7, 1, 0, 0, H, W)
@@ -330,13 +338,21 @@ class _GeneratorFn(torch.autograd.Function):
         dzu2 = ops.norm_act_bwd(dy, S["zu2"], S["stu2"], ACT_RELU)
         if wg:
             ops.convT2d_wgrad(S["yu1"], dzu2, S["gu2"], _grad_buf(dec[k + 3].weight))
-        dy = ops.convT2d_dgrad(dzu2, P["u2_d"], S["gu2"])
+        # Every dgrad below also applies the previous layer's ReLU mask and reduces (sum g, sum g*z)
+        # over pixels in its epilogue, so the norm backward that follows needs no reduction pass.
+        dev = dout.device
+        gu2, gu1 = S["gu2"], S["gu1"]
+        es = ops.epi_stats(B, gu2.h, gu2.w, gu2.c, dev)
+        dy = ops.convT2d_dgrad(dzu2, P["u2_d"], gu2,
+                               ops.epilogue(aux=S["yu1"], aux_mode=AUX_RELU_MASK, stats=es, stats_z=S["zu1"]))
         del dzu2
         # ---- up 1 (ConvTranspose 256->128 + IN + ReLU)
-        dzu1 = ops.norm_act_bwd(dy, S["zu1"], S["stu1"], ACT_RELU)
+        dzu1 = ops.norm_bwd_from(es, dy, S["zu1"], S["stu1"])
         if wg:
-            ops.convT2d_wgrad(S["x_res"], dzu1, S["gu1"], _grad_buf(dec[k].weight))
-        dy = ops.convT2d_dgrad(dzu1, P["u1_d"], S["gu1"])
+            ops.convT2d_wgrad(S["x_res"], dzu1, gu1, _grad_buf(dec[k].weight))
+        es = ops.epi_stats(B, gu1.h, gu1.w, gu1.c, dev) if k else None
+        dy = ops.convT2d_dgrad(dzu1, P["u1_d"], gu1,
+                               ops.epilogue(stats=es, stats_z=S["res"][k - 1][4]) if k else None)
         del dzu1
         # ---- residual blocks, reversed
         nl = 2 * k
@@ -346,16 +362,22 @@ class _GeneratorFn(torch.autograd.Function):
             x_in, za, sta, ha, zb, stb = S["res"][i]
             blk = dec[i]
             l = 2 * i
-            dzb = ops.norm_act_bwd(dy, zb, stb, ACT_NONE, dgamma=dgb[:, (l + 1) * 512:], dbeta=dgb[:, (l + 1) * 512 + 256:],
-                                   dgb_stride=nl * 512)
+            dzb = ops.norm_bwd_from(es, dy, zb, stb, dgamma=dgb[:, (l + 1) * 512:], dbeta=dgb[:, (l + 1) * 512 + 256:],
+                                    dgb_stride=nl * 512)
             if wg:
                 ops.conv2d_wgrad(ha, dzb, g3, _grad_buf(blk.conv2.weight))
-            dh = ops.conv2d_dgrad(dzb, P[f"r{i}1_d"], g3)
-            dza = ops.norm_act_bwd(dh, za, sta, ACT_RELU, dgamma=dgb[:, l * 512:], dbeta=dgb[:, l * 512 + 256:],
-                                   dgb_stride=nl * 512)
+            es = ops.epi_stats(B, h4, w4, 256, dev)
+            dh = ops.conv2d_dgrad(dzb, P[f"r{i}1_d"], g3,
+                                  ops.epilogue(aux=ha, aux_mode=AUX_RELU_MASK, stats=es, stats_z=za))
+            dza = ops.norm_bwd_from(es, dh, za, sta, dgamma=dgb[:, l * 512:], dbeta=dgb[:, l * 512 + 256:],
+                                    dgb_stride=nl * 512)
             if wg:
                 ops.conv2d_wgrad(x_in, dza, g3, _grad_buf(blk.conv1.weight))
-            dy = ops.conv2d_dgrad(dza, P[f"r{i}0_d"], g3, ops.epilogue(aux=dy, aux_mode=AUX_ADD))
+            # + the skip connection's gradient; for i > 0 also the reductions of block i-1's second AdaIN
+            es = ops.epi_stats(B, h4, w4, 256, dev) if i > 0 else None
+            dy = ops.conv2d_dgrad(dza, P[f"r{i}0_d"], g3,
+                                  ops.epilogue(aux=dy, aux_mode=AUX_ADD, stats=es,
+                                               stats_z=S["res"][i - 1][4] if i > 0 else None))
         # ---- style Linears (model.py:28): dstyle, dW, db for all 2k layers
         bs = S["bs"]
         if bs == 1 and B > 1:
@@ -380,14 +402,19 @@ class _GeneratorFn(torch.autograd.Function):
         dz2 = ops.norm_act_bwd(dy, S["z2"], S["st2"], ACT_RELU)
         if wg:
             ops.conv2d_wgrad(S["y1"], dz2, S["g2"], _grad_buf(enc[6].weight))
-        dy = ops.conv2d_dgrad(dz2, P["e2_d"], S["g2"])
+        g2, g1 = S["g2"], S["g1"]
+        es = ops.epi_stats(B, g2.oh, g2.ow, g2.c, dev, phases=4)
+        dy = ops.conv2d_dgrad(dz2, P["e2_d"], g2,
+                              ops.epilogue(aux=S["y1"], aux_mode=AUX_RELU_MASK, stats=es, stats_z=S["z1"]))
         del dz2
-        dz1 = ops.norm_act_bwd(dy, S["z1"], S["st1"], ACT_RELU)
+        dz1 = ops.norm_bwd_from(es, dy, S["z1"], S["st1"])
         if wg:
-            ops.conv2d_wgrad(S["y0"], dz1, S["g1"], _grad_buf(enc[3].weight))
-        dy = ops.conv2d_dgrad(dz1, P["e1_d"], S["g1"])
+            ops.conv2d_wgrad(S["y0"], dz1, g1, _grad_buf(enc[3].weight))
+        es = ops.epi_stats(B, g1.oh, g1.ow, g1.c, dev, phases=4)
+        dy = ops.conv2d_dgrad(dz1, P["e1_d"], g1,
+                              ops.epilogue(aux=S["y0"], aux_mode=AUX_RELU_MASK, stats=es, stats_z=S["z0"]))
         del dz1
-        dz0 = ops.norm_act_bwd(dy, S["z0"], S["st0"], ACT_RELU)
+        dz0 = ops.norm_bwd_from(es, dy, S["z0"], S["st0"])
         m0 = B * H * W
         pg0 = S["pg0"]
         if wg:
@@ -628,8 +655,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         for j in (1, 2, 3):
             ci, co = _TRUNK[j]
             g = ops.conv_geom(B, h, w, ci, co, 4, 4, 2, 1, 1, h // 2, w // 2)
-            z = ops.conv2d_fwd(y, P[f"c{j}"], g)          # bias feeds an InstanceNorm: a no-op on the output
-            st = ops.in_stats(z)
+            z, st = _conv_stats(y, P[f"c{j}"], g)         # bias feeds an InstanceNorm: a no-op on the output
             yn = ops.norm_act_fwd(z, st, ACT_LRELU)
             layers.append((y, g, z, st))
             y = yn
@@ -659,7 +685,13 @@ class _DiscriminatorFn(torch.autograd.Function):
         pgh = ops.patch_geom(B, nd, h, w, 4, 4, 1, 1, 1, h, w, False)
         ad = ops.patch_gather(dall, pgh)
         mh = B * h * w
-        dy = ops.conv2d_fwd(ad.view(1, 1, mh, pgh.kpad), P["h_d"], ops.gemm_geom(mh, pgh.kpad, 512)).view(B, h, w, 512)
+        # the dgrads apply LeakyReLU' of the layer below and reduce (sum g, sum g*z) for its norm backward
+        dev = dout.device
+        z3 = S["layers"][2][2]
+        es = ops.epi_stats_rows(B, h * w, 512, dev)
+        dy = ops.conv2d_fwd(ad.view(1, 1, mh, pgh.kpad), P["h_d"], ops.gemm_geom(mh, pgh.kpad, 512),
+                            ops.epilogue(aux=S["y3"], aux_mode=AUX_LRELU_MASK, stats=es, stats_z=z3)
+                            if es is not None else None).view(B, h, w, 512)
         if wg:
             ws, splits = ops.gemm_tn_partial(mh, ad, pgh.kpad, S["y3"], 512)
             for kx, br in enumerate(mod.domain_branches):
@@ -670,11 +702,14 @@ class _DiscriminatorFn(torch.autograd.Function):
         for j in (3, 2, 1):
             ci, co = _TRUNK[j]
             y_in, g, z, st = S["layers"][j - 1]
-            dz = ops.norm_act_bwd(dy, z, st, ACT_LRELU)
+            dz = ops.norm_bwd_from(es, dy, z, st) if es is not None else ops.norm_act_bwd(dy, z, st, ACT_LRELU)
             if wg:
                 ops.conv2d_wgrad(y_in, dz, g, _grad_buf(convs[j].weight))
             if j > 1:
-                dy = ops.conv2d_dgrad(dz, P[f"c{j}_d"], g)
+                es = ops.epi_stats(B, g.oh, g.ow, g.c, dev, phases=4)
+                dy = ops.conv2d_dgrad(dz, P[f"c{j}_d"], g,
+                                      ops.epilogue(aux=y_in, aux_mode=AUX_LRELU_MASK, stats=es,
+                                                   stats_z=S["layers"][j - 2][2]))
             else:   # dgrad fused with LeakyReLU' of the first layer's output
                 dy = ops.conv2d_dgrad(dz, P[f"c{j}_d"], g, ops.epilogue(aux=S["y0"], aux_mode=AUX_LRELU_MASK))
         dz0 = dy

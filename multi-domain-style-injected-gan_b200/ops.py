@@ -49,9 +49,33 @@ def conv_geom(n, h, w, c, k, r, s, stride, pad_t, pad_l, oh, ow):
 
 
 def epilogue(bias=None, aux=None, aux_mode=AUX_NONE, act=ACT_NONE, alpha=1.0, alpha_ptr=None,
-             slope=0.2, out_layout=OUT_BF16_NHWC):
+             slope=0.2, out_layout=OUT_BF16_NHWC, stats=None, stats_z=None):
+    """`stats`: an EpiStats buffer that receives the per-(image, channel) partial sums of the stored
+    output (sum v, sum v*v, or sum v*z when `stats_z` is given) from the GEMM epilogue."""
     return Epilogue(_p(bias), _p(aux), aux_mode if aux is not None else AUX_NONE, act, alpha,
-                    _p(alpha_ptr), slope, out_layout)
+                    _p(alpha_ptr), slope, out_layout, _p(None if stats is None else stats.buf), _p(stats_z))
+
+
+class EpiStats:
+    """Partial-sum buffer of the epilogue-fused reductions: [n * rows_per_img][2][ld] fp32."""
+    __slots__ = ("buf", "n", "rows", "ld")
+
+    def __init__(self, n, rows_per_img, k, device):
+        self.n, self.rows, self.ld = n, rows_per_img, (k + 63) // 64 * 64
+        self.buf = torch.empty((n * rows_per_img, 2, self.ld), dtype=F32, device=device)
+
+
+def epi_stats(n, oh, ow, k, device, phases=1):
+    """Buffer for an [n, oh, ow, k] conv output (phases=4: transposed conv / stride-2 dgrad, oh x ow
+    = the per-phase plane)."""
+    return EpiStats(n, int(L.load().msig_epilogue_stats_rows(oh, ow, phases)), k, device)
+
+
+def epi_stats_rows(n, hw, k, device):
+    """Buffer for a GEMM-view output [n*hw, k] (128-row tiles); None when a tile would span images."""
+    if hw % 128:
+        return None
+    return EpiStats(n, hw // 128 * 4, k, device)
 
 
 # ------------------------------------------------------------------ weights
@@ -226,6 +250,27 @@ def in_stats(x, gamma=None, beta=None, gb_stride=0, eps=1e-5):
     L.call("msig_in_stats", _p(x), n, h * w, c, eps, _p(gamma), _p(beta), gb_stride, _p(st.mean),
            _p(st.rstd), _p(st.scale), _p(st.shift), _p(ws), ws.numel(), _stream())
     return st
+
+
+def in_stats_from(es, hw, c, gamma=None, beta=None, gb_stride=0, eps=1e-5):
+    """InstanceNorm / AdaIN statistics from epilogue partial sums (no pass over the activation)."""
+    st = NormStats(es.n, c, es.buf.device)
+    L.call("msig_in_stats_from_partials", _p(es.buf), es.n, es.rows, es.ld, hw, c, eps, _p(gamma), _p(beta),
+           gb_stride, _p(st.mean), _p(st.rstd), _p(st.scale), _p(st.shift), _stream())
+    return st
+
+
+def norm_bwd_from(es, g, x, st, dgamma=None, dbeta=None, dgb_stride=0, accumulate_dgb=False, out=None):
+    """Norm backward whose two reductions (sum g, sum g*x) came from the producing dgrad's epilogue;
+    `g` already carries the activation mask."""
+    n, h, w, c = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    coef = torch.empty((n, 2, c), dtype=F32, device=x.device)
+    L.call("msig_norm_bwd_from_partials", _p(es.buf), n, es.rows, es.ld, _p(g), _p(x), _p(st.mean), _p(st.rstd),
+           _p(st.scale), _p(st.shift), h * w, c, _p(out), _p(dgamma), _p(dbeta), dgb_stride, int(accumulate_dgb),
+           _p(coef), _stream())
+    return out
 
 
 def norm_act_fwd(x, st, act=ACT_NONE, residual=None, slope=0.2, out=None):
@@ -447,5 +492,23 @@ def adam_step(param, grad, exp_avg, exp_avg_sq, ema, grad_sumsq, max_norm, grad_
            float(eps), int(step), float(ema_beta), _stream())
 
 
+def adam_step_dev(param, grad, exp_avg, exp_avg_sq, ema, grad_sumsq, max_norm, grad_scale, lr, beta1, beta2,
+                  eps, step_counter, ema_beta):
+    """adam_step whose step number lives in the int32 device tensor `step_counter` (incremented by
+    the call): replayable from a CUDA graph."""
+    L.call("msig_adam_step_dev", _p(param), _p(grad), _p(exp_avg), _p(exp_avg_sq), _p(ema), param.numel(),
+           _p(grad_sumsq), float(max_norm), float(grad_scale), float(lr), float(beta1), float(beta2),
+           float(eps), _p(step_counter), float(ema_beta), _stream())
+
+
+_replayed_launches = 0
+
+
+def add_replayed_launches(n):
+    """Kernels executed by CUDA-graph replays (the C-side counter only sees direct launches)."""
+    global _replayed_launches
+    _replayed_launches += int(n)
+
+
 def kernel_launches():
-    return int(L.load().msig_kernel_launches())
+    return int(L.load().msig_kernel_launches()) + _replayed_launches

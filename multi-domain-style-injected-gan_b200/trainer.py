@@ -10,7 +10,11 @@ Reference: /root/reference/trainer.py:19-239. Result-preserving differences (SUR
   * clip_grad_norm_ + Adam + EMA run as one fused pass over flat buffers;
   * with world_size > 1 each rank takes an equal shard of the batch and gradients are averaged with
     an NCCL all-reduce; the generator-side all-reduce overlaps the discriminator phase (which does
-    not depend on the generator update).
+    not depend on the generator update);
+  * the step has static shapes and no host synchronisation, so from the second call with the same
+    (batch shape, epoch, learning rates) it is replayed from ONE captured CUDA graph (~1900 kernel
+    launches per step otherwise cost as much host time as the GPU needs to run them). The first call
+    runs eagerly. `use_cuda_graph=False` (or MSIG_CUDA_GRAPH=0) keeps every step eager.
 """
 import copy
 import os
@@ -28,7 +32,7 @@ class MultiDomainStyleCycleGAN:
     """Multi-domain StyleCycleGAN trainer (reference trainer.py:19-72)."""
 
     def __init__(self, device, total_epochs, lr_g, lr_d, loss_weights, num_domains, process_group=None,
-                 vgg_state=None):
+                 vgg_state=None, use_cuda_graph=None):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("msig_b200 trainer needs a CUDA device (sm_100a); there is no CPU path")
@@ -79,77 +83,175 @@ class MultiDomainStyleCycleGAN:
         self.loss_history = {k: [] for k in (list(loss_weights.keys()) + ['D_loss', 'G_loss'])}
         self.current_epoch_losses = {k: [] for k in self.loss_history.keys()}
         self._comm = FlatAllReduce(process_group, self.device)
+        if use_cuda_graph is None:
+            use_cuda_graph = os.environ.get("MSIG_CUDA_GRAPH", "1") != "0"
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._graph_key = None     # configuration of the last call
+        self._graph = None         # captured step for that configuration (None until the second call)
+        self._graph_stream = None
 
     def train_step(self, batch, epoch):
         """One G+D optimisation step (reference trainer.py:74-155). Returns the same dict of loss
         tensors: D_loss, G_loss, gan, cycle, identity, style, content."""
+        if self.use_cuda_graph:
+            return self._train_step_graphed(batch, epoch)
+        return self._train_step_eager(batch, epoch)
+
+    def _train_step_eager(self, batch, epoch):
         ops.step_cache_begin()
         try:
-            return self._train_step(batch, epoch)
+            st = {}
+            for seg, comm in self._segments(batch, epoch, st, device_step=False):
+                seg()
+                comm()
+            return st["out"]
         finally:
             ops.step_cache_end()
 
-    def _train_step(self, batch, epoch):
+    # ------------------------------------------------------------------ the step, in four segments
+    def _segments(self, batch, epoch, st, device_step):
+        """The step as (compute segment, communication hook) pairs. A segment only launches kernels
+        of this library on the current stream (capturable into a CUDA graph); the hooks hold the
+        gradient all-reduces (NCCL, own stream), which stay outside the graphs. `st` carries tensors
+        from one segment to the next."""
         dev = self.device
-        real_A = batch['source'].to(dev, non_blocking=True)
-        real_B = batch['target'].to(dev, non_blocking=True)
-        y_org = batch['source_domain'].to(dev, non_blocking=True)
-        y_trg = batch['target_domain'].to(dev, non_blocking=True)
         valid, fake = 1.0, 0.0     # LSGAN targets (all-ones / all-zeros, trainer.py:85-86)
         dp = self.world_size > 1
-
-        # ================================== generators
-        self.g_optimizer.zero_grad()
-        self.D_A.skip_param_grads = self.D_B.skip_param_grads = True
-
-        style_A = self.SE_A(real_A, y_org)
-        style_B = self.SE_B(real_B, y_trg)
-        loss_identity = self.criterion_identity(self.G_A2B(real_B, style_B), real_B)
-
-        fake_B = self.G_A2B(real_A, style_B)
-        loss_gan_A2B = self.criterion_gan(self.D_B(fake_B, y_trg), valid)
-        content_loss_B, style_loss_B = self.criterion_style_content(fake_B, real_B, real_A)
-
-        fake_A = self.G_B2A(real_B, style_A)
-        loss_gan_B2A = self.criterion_gan(self.D_A(fake_A, y_org), valid)
-        content_loss_A, style_loss_A = self.criterion_style_content(fake_A, real_A, real_B)
-
-        loss_gan = (loss_gan_A2B + loss_gan_B2A) / 2
-        loss_style = (style_loss_A + style_loss_B) / 2
-        loss_content = (content_loss_A + content_loss_B) / 2
-        loss_cycle = (self.criterion_cycle(self.G_B2A(fake_B, style_A), real_A) +
-                      self.criterion_cycle(self.G_A2B(fake_A, style_B), real_B)) / 2
-
-        individual_losses = {'gan': loss_gan, 'cycle': loss_cycle, 'identity': loss_identity,
-                             'style': loss_style, 'content': loss_content}
-        weights = self.weight_scheduler.get_current_weights(epoch, individual_losses)
-        g_loss = sum(loss * weights[name] for name, loss in individual_losses.items())
-        g_loss.backward()
-        self.D_A.skip_param_grads = self.D_B.skip_param_grads = False
-
-        g_ev = self._comm.start(self._g_flat.grad) if dp else None
-
-        # ================================== discriminators (independent of the generator update)
-        self.d_optimizer.zero_grad()
-        fake_A_d, fake_B_d = fake_A.detach(), fake_B.detach()
-        loss_real_A = self.criterion_gan(self.D_A(real_A, y_org), valid)
-        loss_real_B = self.criterion_gan(self.D_B(real_B, y_trg), valid)
-        loss_fake_A = self.criterion_gan(self.D_A(fake_A_d, y_org), fake)
-        loss_fake_B = self.criterion_gan(self.D_B(fake_B_d, y_trg), fake)
-        d_loss = (loss_real_A + loss_fake_A + loss_real_B + loss_fake_B) / 2
-        d_loss.backward()
-
-        # generator update: clip_grad_norm_(1.0) + Adam + EMA (trainer.py:127-134), fused
         scale = self._comm.grad_scale
-        if dp:
-            self._comm.wait(g_ev, dev)
-        self.g_optimizer.step(max_norm=1.0, grad_scale=scale)
-        # discriminator update (trainer.py:152-153)
-        if dp:
-            self._comm.wait(self._comm.start(self._d_flat.grad), dev)
-        self.d_optimizer.step(max_norm=1.0, grad_scale=scale)
 
-        return {'D_loss': d_loss, 'G_loss': g_loss, **individual_losses}
+        def inputs():
+            return (batch['source'].to(dev, non_blocking=True), batch['target'].to(dev, non_blocking=True),
+                    batch['source_domain'].to(dev, non_blocking=True), batch['target_domain'].to(dev, non_blocking=True))
+
+        def seg_generators():        # trainer.py:88-125
+            real_A, real_B, y_org, y_trg = inputs()
+            self.g_optimizer.zero_grad()
+            self.D_A.skip_param_grads = self.D_B.skip_param_grads = True
+            style_A = self.SE_A(real_A, y_org)
+            style_B = self.SE_B(real_B, y_trg)
+            loss_identity = self.criterion_identity(self.G_A2B(real_B, style_B), real_B)
+
+            fake_B = self.G_A2B(real_A, style_B)
+            loss_gan_A2B = self.criterion_gan(self.D_B(fake_B, y_trg), valid)
+            content_loss_B, style_loss_B = self.criterion_style_content(fake_B, real_B, real_A)
+
+            fake_A = self.G_B2A(real_B, style_A)
+            loss_gan_B2A = self.criterion_gan(self.D_A(fake_A, y_org), valid)
+            content_loss_A, style_loss_A = self.criterion_style_content(fake_A, real_A, real_B)
+
+            loss_gan = (loss_gan_A2B + loss_gan_B2A) / 2
+            loss_style = (style_loss_A + style_loss_B) / 2
+            loss_content = (content_loss_A + content_loss_B) / 2
+            loss_cycle = (self.criterion_cycle(self.G_B2A(fake_B, style_A), real_A) +
+                          self.criterion_cycle(self.G_A2B(fake_A, style_B), real_B)) / 2
+
+            individual_losses = {'gan': loss_gan, 'cycle': loss_cycle, 'identity': loss_identity,
+                                 'style': loss_style, 'content': loss_content}
+            weights = self.weight_scheduler.get_current_weights(epoch, individual_losses, record=not device_step)
+            g_loss = sum(loss * weights[name] for name, loss in individual_losses.items())
+            g_loss.backward()
+            self.D_A.skip_param_grads = self.D_B.skip_param_grads = False
+            st["fakes"] = (fake_A.detach(), fake_B.detach())
+            st["out"] = {'G_loss': g_loss, **individual_losses}
+
+        def comm_g_start():          # overlaps the whole discriminator phase
+            st["g_ev"] = self._comm.start(self._g_flat.grad) if dp else None
+
+        def seg_discriminators():    # trainer.py:136-151; independent of the generator update
+            real_A, real_B, y_org, y_trg = inputs()
+            fake_A_d, fake_B_d = st.pop("fakes")
+            self.d_optimizer.zero_grad()
+            loss_real_A = self.criterion_gan(self.D_A(real_A, y_org), valid)
+            loss_real_B = self.criterion_gan(self.D_B(real_B, y_trg), valid)
+            loss_fake_A = self.criterion_gan(self.D_A(fake_A_d, y_org), fake)
+            loss_fake_B = self.criterion_gan(self.D_B(fake_B_d, y_trg), fake)
+            d_loss = (loss_real_A + loss_fake_A + loss_real_B + loss_fake_B) / 2
+            d_loss.backward()
+            st["out"] = {'D_loss': d_loss, **st["out"]}
+
+        def comm_g_wait():
+            if dp:
+                self._comm.wait(st.pop("g_ev"), dev)
+
+        def seg_g_update():          # clip_grad_norm_(1.0) + Adam + EMA (trainer.py:127-134), fused
+            self.g_optimizer.step(max_norm=1.0, grad_scale=scale, device_step=device_step)
+
+        def comm_d():
+            if dp:
+                self._comm.wait(self._comm.start(self._d_flat.grad), dev)
+
+        def seg_d_update():          # trainer.py:152-153
+            self.d_optimizer.step(max_norm=1.0, grad_scale=scale, device_step=device_step)
+
+        return [(seg_generators, comm_g_start), (seg_discriminators, comm_g_wait), (seg_g_update, comm_d),
+                (seg_d_update, lambda: None)]
+
+    # ------------------------------------------------------------------ CUDA-graph replay
+    _BATCH_KEYS = ('source', 'target', 'source_domain', 'target_domain')
+
+    def _train_step_graphed(self, batch, epoch):
+        key = (tuple(batch['source'].shape), tuple(batch['target'].shape), int(epoch),
+               float(self.g_optimizer.param_groups[0]['lr']), float(self.d_optimizer.param_groups[0]['lr']))
+        if self._graph_stream is None:
+            self._graph_stream = torch.cuda.Stream(device=self.device)
+        if key != self._graph_key:          # new configuration: one eager step, capture on the next call
+            self._graph_key, self._graph = key, None
+            # ... on the capture stream: autograd's gradient-accumulator nodes remember the stream they
+            # were created on, and a capture may only depend on work of its own stream
+            cur = torch.cuda.current_stream(self.device)
+            self._graph_stream.wait_stream(cur)
+            with torch.cuda.stream(self._graph_stream):
+                out = self._train_step_eager(batch, epoch)
+            cur.wait_stream(self._graph_stream)
+            return out
+        if self._graph is None:
+            self._graph = self._capture(batch, epoch)
+        gs = self._graph
+        for k in self._BATCH_KEYS:
+            gs["static"][k].copy_(batch[k], non_blocking=True)
+        for graph, comm in gs["segments"]:
+            graph.replay()
+            comm()
+        self.g_optimizer.after_replay()
+        self.d_optimizer.after_replay()
+        ops.add_replayed_launches(gs["launches"])
+        vals = gs["out"].clone()            # the graphs' output buffer is overwritten by the next replay
+        out = {name: vals[i] for i, name in enumerate(gs["names"])}
+        self.weight_scheduler.get_current_weights(epoch, {k: v for k, v in out.items() if k not in ('D_loss', 'G_loss')})
+        return out
+
+    def _capture(self, batch, epoch):
+        """Captures the four compute segments as four CUDA graphs sharing one memory pool (replayed
+        in capture order); the all-reduce hooks run between the replays."""
+        dev = self.device
+        static = {k: torch.empty(batch[k].shape, dtype=batch[k].dtype, device=dev) for k in self._BATCH_KEYS}
+        for k in self._BATCH_KEYS:
+            static[k].copy_(batch[k], non_blocking=True)
+        for flat in (self._g_flat, self._d_flat):
+            flat.mark_dirty()               # the captured step re-packs the bf16 weight copies it uses
+        self.g_optimizer.step_counter()
+        self.d_optimizer.step_counter()
+        torch.cuda.synchronize(dev)
+        l0 = ops.kernel_launches()
+        st, segments, pool = {}, [], None
+        ops.step_cache_begin()
+        try:
+            segs = self._segments(static, epoch, st, device_step=True)
+            for i, (seg, comm) in enumerate(segs):
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph, pool=pool, stream=self._graph_stream, capture_error_mode="thread_local"):
+                    seg()
+                    if i == len(segs) - 1:
+                        names = list(st["out"].keys())
+                        stacked = torch.stack([st["out"][k].detach().float().reshape(()) for k in names])
+                pool = graph.pool()
+                segments.append((graph, comm))
+        finally:
+            ops.step_cache_end()
+        launches = ops.kernel_launches() - l0
+        ops.add_replayed_launches(-launches)   # recorded, not executed, during capture
+        return {"segments": segments, "static": static, "out": stacked, "names": names, "launches": launches,
+                "keep": st}
 
     # ------------------------------------------------------------------ checkpoints (trainer.py:157-207)
     def save_models(self, save_dir):
@@ -193,6 +295,7 @@ class MultiDomainStyleCycleGAN:
             self.ema_SE_A.load_state_dict(ema_ckpt['ema_SE_A']); self.ema_SE_B.load_state_dict(ema_ckpt['ema_SE_B'])
         for flat in (self._g_flat, self._d_flat, self._ema_flat):
             flat.mark_dirty()
+        self._graph_key = self._graph = None    # optimizer step counts changed: re-capture
         print(f"Models successfully loaded from {checkpoint_dir}")
         return len(self.loss_history.get('G_loss', []))
 

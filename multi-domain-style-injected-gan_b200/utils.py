@@ -68,6 +68,7 @@ class FusedAdam(torch.optim.Optimizer):
         self.exp_avg_sq = torch.zeros_like(flat.data)
         self.grad_sumsq = torch.zeros((), dtype=F32, device=flat.data.device)
         self.step_count = 0
+        self._step_dev = None        # int32 device copy of step_count (CUDA-graph replay)
         m_views, v_views = flat.views_of(self.exp_avg), flat.views_of(self.exp_avg_sq)
         for p, m, v in zip(flat.params, m_views, v_views):
             self.state[p] = {"step": torch.tensor(0.0), "exp_avg": m, "exp_avg_sq": v}
@@ -76,17 +77,38 @@ class FusedAdam(torch.optim.Optimizer):
         self.flat.grad.zero_()
         self.flat.rebind_grads()
 
-    @torch.no_grad()
-    def step(self, closure=None, max_norm=None, grad_scale=1.0):
-        g = self.param_groups[0]
+    def step_counter(self):
+        """Device-resident step number, (re)synchronised with the host count."""
+        if self._step_dev is None:
+            self._step_dev = torch.zeros((), dtype=torch.int32, device=self.flat.data.device)
+        self._step_dev.fill_(self.step_count)
+        return self._step_dev
+
+    def after_replay(self):
+        """Host bookkeeping for one optimizer step executed inside a replayed CUDA graph."""
         self.step_count += 1
+        self.flat.mark_dirty()
+        if self.ema_flat is not None:
+            self.ema_flat.mark_dirty()
+
+    @torch.no_grad()
+    def step(self, closure=None, max_norm=None, grad_scale=1.0, device_step=False):
+        """device_step=True (CUDA-graph capture): the bias-correction step number is read from the
+        device counter, which the captured kernels increment themselves; the host count is advanced
+        by after_replay()."""
+        g = self.param_groups[0]
         use_clip = max_norm is not None and max_norm > 0
         if use_clip:
             ops.sumsq(self.flat.grad, self.grad_sumsq, accumulate=False)
-        ops.adam_step(self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq,
-                      None if self.ema_flat is None else self.ema_flat.data,
-                      self.grad_sumsq if use_clip else None, max_norm if use_clip else 0.0, grad_scale,
-                      g["lr"], g["betas"][0], g["betas"][1], g["eps"], self.step_count, self.ema_beta)
+        args = (self.flat.data, self.flat.grad, self.exp_avg, self.exp_avg_sq,
+                None if self.ema_flat is None else self.ema_flat.data,
+                self.grad_sumsq if use_clip else None, max_norm if use_clip else 0.0, grad_scale,
+                g["lr"], g["betas"][0], g["betas"][1], g["eps"])
+        if device_step:
+            ops.adam_step_dev(*args, self._step_dev, self.ema_beta)
+            return
+        self.step_count += 1
+        ops.adam_step(*args, self.step_count, self.ema_beta)
         self.flat.mark_dirty()
         if self.ema_flat is not None:
             self.ema_flat.mark_dirty()
@@ -154,7 +176,14 @@ class DynamicWeightScheduler:
         self.loss_history = {k: [] for k in init_weights.keys()}
         self.weight_history = {k: [] for k in init_weights.keys()}
 
-    def get_current_weights(self, epoch, current_losses):
+    def get_current_weights(self, epoch, current_losses, record=True):
+        """record=False (CUDA-graph capture): compute the weights only; the histories are appended
+        after each replay, from that replay's loss values."""
+        if not record:
+            saved = {k: list(v) for k, v in self.weight_history.items()}
+            w = self.get_current_weights(epoch, {})
+            self.weight_history = saved
+            return w
         for k, v in current_losses.items():
             if k in self.loss_history:
                 self.loss_history[k].append(v.detach() if hasattr(v, "detach") else v)

@@ -254,6 +254,50 @@ def case_train_step(b=2, s=64, nd=3, steps=2, seed=0):
     return res, ok
 
 
+def case_graph_vs_eager(b=2, s=64, nd=3, steps=4, seed=0):
+    """The CUDA-graph replay of train_step (steps 2..n) against the same steps run eagerly."""
+    from msig_b200 import trainer as T
+    vgg_sd = O.seeded_vgg_state()
+    batch = O.synthetic_batch(b, s, nd)
+    outs = []
+    for graph in (False, True):
+        torch.manual_seed(seed)
+        tr = T.MultiDomainStyleCycleGAN(torch.device(DEV), 200, 2e-4, 1e-4, dict(O.DEFAULT_LOSS_WEIGHTS), nd,
+                                        vgg_state=vgg_sd, use_cuda_graph=graph)
+        losses = []
+        for _ in range(steps):
+            out = tr.train_step(batch, 0)
+            losses.append({k: float(v) for k, v in out.items()})
+        torch.cuda.synchronize()
+        assert (tr._graph is not None) == graph
+        assert tr.g_optimizer.step_count == steps and len(tr.weight_scheduler.loss_history["gan"]) == steps
+        params = {f"{net}.{n}": p.detach().clone() for net in list(O.OracleTrainer.NETS) + ["ema_G_A2B", "ema_SE_B"]
+                  for n, p in getattr(tr, net).named_parameters()}
+        outs.append((losses, params, tr))
+    res, ok = {}, True
+    for it in range(steps):
+        for k, v in outs[0][0][it].items():
+            e = abs(outs[1][0][it][k] - v) / max(abs(v), 1e-6)
+            res[f"s{it}.{k}"] = e
+            # step 0 is the same eager code; step 1 replays the captured graph on identical weights up to
+            # fp32-atomic reordering in the bias-gradient sums (Adam's first steps move every weight by
+            # ~lr * sign(g), so that noise then grows like any two runs of a GAN)
+            ok = ok and e <= (0.0 if it == 0 else 2e-3 if it == 1 else 3e-2)
+    worst = max((outs[0][1][k] - outs[1][1][k]).abs().max().item() for k in outs[0][1])
+    res["param_max_abs_diff"] = worst          # fp32 atomics in the loss reductions reorder sums; Adam
+    ok = ok and worst <= 2.5 * steps * 2e-4    # turns a sign flip of a tiny gradient into ~lr
+    # the EMA generator's packed weights must follow the replayed optimizer (inference after training)
+    g = torch.Generator().manual_seed(5)
+    x = (torch.rand(1, 3, s, s, generator=g) * 2 - 1).to(DEV)
+    sty = torch.randn(1, 256, generator=g).to(DEV)
+    with torch.no_grad():
+        y0 = outs[0][2].ema_G_A2B(x, sty)
+        y1 = outs[1][2].ema_G_A2B(x, sty)
+    res["ema_out"] = rel(y1.cpu(), y0.cpu())
+    ok = ok and res["ema_out"] <= ACT_TOL
+    return res, ok
+
+
 CASES = {
     "adain_module": case_adain_module,
     "generator_b2_s64": lambda: case_generator(2, 64),
@@ -264,4 +308,5 @@ CASES = {
     "discriminator_none_leaf": lambda: case_discriminator(2, 64, 3, False, False),
     "vgg_loss": lambda: case_vgg(2, 64),
     "train_step_b2_s64": lambda: case_train_step(2, 64, 3, 2),
+    "train_step_graph_vs_eager": case_graph_vs_eager,
 }
