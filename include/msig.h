@@ -86,6 +86,9 @@ enum {
   MSIG_WPACK_IM2COL = 5,      /* OIHW (small I) -> [Opad][Kpad], k=(r*s)*I+i   gathered-patch GEMM    */
   MSIG_WPACK_IM2COL_DGRAD = 6,/* OIHW (small I) -> [Kpad][O]                   its dgrad              */
   MSIG_WPACK_IM2COL_FLIP = 7, /* OIHW (small O) -> [Ipad][Kpad], k=flip(r*s)*O+o  dgrad of a small-O conv via gathered dy */
+  MSIG_WPACK_ROWFOLD = 8,     /* OIHW (O <= 4, I = 64) -> [r][s*4+o][I]            msig_conv_narrow_fwd            */
+  MSIG_WPACK_ROWFOLD_DGRAD = 9,/* OIHW (I <= 4, O = 64) -> [R-1-r][(S-1-s)*4+i][O]  dgrad (w.r.t. the image) of a
+                                 small-I conv, run as msig_conv_narrow_fwd over dy with pad = R-1-pad          */
 };
 typedef struct msig_wpack_desc {
   int32_t kind;
@@ -99,6 +102,12 @@ int msig_wpack(const msig_wpack_desc* d, const float* w, void* packed, void* str
  * (model.py:18; r=s=1 on a [1,1,M,K] view) and the 1x1 heads (model.py:84). */
 int msig_conv2d_fwd(const msig_conv_geom* g, const void* x, const void* w_fwd,
                     const msig_epilogue* e, void* y, void* stream);
+/* Stride-1 convolution with k <= 4 output channels of a 64-channel input (model.py:141, the final 7x7
+ * 64->3 conv; and, with MSIG_WPACK_ROWFOLD_DGRAD weights, the image gradient of the first 7x7 3->64 conv,
+ * model.py:131): the horizontal taps are folded into the GEMM N dimension and consecutive output rows
+ * share their input strips in shared memory. y is fp32 (NCHW or NHWC); epilogue: alpha, bias, act. */
+int msig_conv_narrow_fwd(const msig_conv_geom* g, const void* x, const void* w_rowfold,
+                         const msig_epilogue* e, void* y, void* stream);
 /* dx = dgrad(dy): w_dgrad is MSIG_WPACK_DGRAD_S1 (stride 1) or MSIG_WPACK_DGRAD_S2 (stride 2). */
 int msig_conv2d_dgrad(const msig_conv_geom* g, const void* dy, const void* w_dgrad,
                       const msig_epilogue* e, void* dx, void* stream);
@@ -159,6 +168,10 @@ int msig_reflect_pad_fwd(const void* x, int32_t n, int32_t h, int32_t w, int32_t
                          void* y, void* stream);
 int msig_reflect_pad_bwd(const void* dy, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad,
                          void* dx, void* stream);
+/* Same adjoint for an fp32 NCHW gradient (image side of the reflect-padded first conv, model.py:131):
+ * dx[n,c,h,w] = sum of dy_padded[n,c,.,.] over the padded positions that mirror onto (h,w). */
+int msig_reflect_fold_nchw(const float* dy_padded, int32_t n, int32_t c, int32_t h, int32_t w, int32_t pad,
+                           float* dx, void* stream);
 
 /* ---- InstanceNorm / AdaIN (model.py:16,20-36,131-133,139-140,167) -----------------------
  * x: [n,hw,c] bf16. Statistics are biased, eps inside the sqrt, fp32.

@@ -52,6 +52,8 @@ static int64_t pack_elems(const PackGeom& g) {
     case MSIG_WPACK_IM2COL: return int64_t(g.Opad) * g.Kpad;
     case MSIG_WPACK_IM2COL_DGRAD: return int64_t(g.Kpad) * g.OC;
     case MSIG_WPACK_IM2COL_FLIP: return int64_t(g.Ipad) * g.Kpad;
+    case MSIG_WPACK_ROWFOLD: return (g.O <= 4 && g.S <= 8 && g.I == 64) ? int64_t(g.R) * 32 * g.I : -1;
+    case MSIG_WPACK_ROWFOLD_DGRAD: return (g.I <= 4 && g.S <= 8 && g.O == 64) ? int64_t(g.R) * 32 * g.O : -1;
     default: return -1;
   }
 }
@@ -91,6 +93,14 @@ __device__ __forceinline__ int64_t packed_offset(const PackGeom& g, int o, int i
     case MSIG_WPACK_IM2COL: return int64_t(oo) * g.Kpad + t * g.I + i;
     case MSIG_WPACK_IM2COL_DGRAD: return (int64_t(t) * g.I + i) * g.OC + oo;
     case MSIG_WPACK_IM2COL_FLIP: return int64_t(i) * g.Kpad + (g.RS - 1 - t) * g.OC + oo;
+    case MSIG_WPACK_ROWFOLD: {        // [r][s*4 + o][i]
+      const int r = t / g.S, s2 = t % g.S;
+      return (int64_t(r) * 32 + s2 * 4 + oo) * g.I + i;
+    }
+    case MSIG_WPACK_ROWFOLD_DGRAD: {  // [R-1-r][(S-1-s)*4 + i][o]
+      const int r = t / g.S, s2 = t % g.S;
+      return (int64_t(g.R - 1 - r) * 32 + (g.S - 1 - s2) * 4 + i) * g.O + oo;
+    }
   }
   return 0;
 }
@@ -495,6 +505,49 @@ int msig_conv2d_fwd(const msig_conv_geom* g, const void* x, const void* w_fwd, c
   MSIG_REQUIRE(g && x && w_fwd && y, "msig_conv2d_fwd: null argument");
   return run_conv(x, g->n, g->h, g->w, g->c, g->k, g->r, g->s, g->stride, g->pad_t, g->pad_l, g->oh,
                   g->ow, w_fwd, e, y, static_cast<cudaStream_t>(stream));
+}
+
+// Narrow-output stride-1 conv through the row-fold kernel (see RowfoldParams).
+int msig_conv_narrow_fwd(const msig_conv_geom* g, const void* x, const void* w_rowfold, const msig_epilogue* e,
+                         void* y, void* stream) {
+  MSIG_REQUIRE(g && x && w_rowfold && y, "msig_conv_narrow_fwd: null argument");
+  MSIG_REQUIRE(context_ready(), "msig_init() has not been called");
+  MSIG_REQUIRE(g->c == 64 && g->k >= 1 && g->k <= 4 && g->stride == 1 && g->r >= 1 && g->r <= 7 && g->s >= 1 &&
+                   g->s <= 8,
+               "msig_conv_narrow_fwd: needs c = 64, k <= 4, stride 1, r <= 7, s <= 8 (got c=%d k=%d stride=%d %dx%d)",
+               g->c, g->k, g->stride, g->r, g->s);
+  const int layout = e ? e->out_layout : MSIG_OUT_F32_NCHW;
+  MSIG_REQUIRE(layout == MSIG_OUT_F32_NCHW || layout == MSIG_OUT_F32_NHWC, "msig_conv_narrow_fwd: fp32 outputs only");
+  MSIG_REQUIRE(!e || e->aux == nullptr, "msig_conv_narrow_fwd: no aux operand");
+  RowfoldParams p;
+  memset(&p, 0, sizeof(p));
+  p.R = g->r; p.S = g->s;
+  p.org_h = -g->pad_t; p.org_w = -g->pad_l;
+  p.OH = g->oh; p.OW = g->ow; p.n_img = g->n;
+  const int tile_out = 128 - (g->s - 1);
+  p.tiles_w = static_cast<int>(ceil_div(g->ow, tile_out));
+  // chunk of output rows per work item: long enough to amortise the R-1 extra strips, short enough
+  // for several waves of items over the SMs
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  int rows = 64;
+  while (rows > 8 && int64_t(g->n) * p.tiles_w * ceil_div(g->oh, rows) < int64_t(6) * sms) rows /= 2;
+  p.rows_per_item = rows;
+  p.chunks_h = static_cast<int>(ceil_div(g->oh, rows));
+  int rc;
+  ActView v{x, g->c, g->w, g->h, g->n, g->c, int64_t(g->w) * g->c, int64_t(g->h) * g->w * g->c};
+  if ((rc = make_act_map(&p.tmA, v, 128, 1)) != MSIG_OK) return rc;
+  if ((rc = make_w_map(&p.tmB, w_rowfold, int64_t(g->r) * 32, 64, 32)) != MSIG_OK) return rc;
+  const OutView ov = make_out_view(y, layout, g->oh, g->ow, g->k);
+  p.out = reinterpret_cast<float*>(y);
+  p.o_sn = ov.sN; p.o_sh = ov.sH; p.o_sw = ov.sW; p.o_sc = ov.sC;
+  p.n_valid = g->k;
+  p.bias = e ? e->bias : nullptr;
+  p.alpha = e ? e->alpha : 1.f;
+  p.alpha_ptr = e ? e->alpha_ptr : nullptr;
+  p.act = e ? e->act : ACT_NONE;
+  cudaError_t ce = launch_rowfold(p, sms, static_cast<cudaStream_t>(stream));
+  if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "rowfold launch: %s", cudaGetErrorString(ce));
+  return MSIG_OK;
 }
 
 int msig_conv2d_dgrad(const msig_conv_geom* g, const void* dy, const void* w_dgrad,

@@ -179,8 +179,12 @@ __device__ __forceinline__ void fprop_epilogue_chunk(const FpropParams& p, const
   }
 }
 
+// 12 warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 idle, 4..11 = epilogue. The two
+// epilogue warps of a TMEM lane quadrant (warp % 4) split the accumulator columns in halves.
+constexpr int kFpropThreads = 384;
+
 template <int BLOCK_N>
-__global__ void __launch_bounds__(256, 1) fprop_kernel(const __grid_constant__ FpropParams p) {
+__global__ void __launch_bounds__(kFpropThreads, 1) fprop_kernel(const __grid_constant__ FpropParams p) {
   using Cfg = FpropCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__(256, 1) fprop_kernel(const __grid_constant__ F
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 128);
+      mbar_init(&tempty_bar[a], BLOCK_N >= 64 ? 256 : 128);
     }
     fence_barrier_init();
   }
@@ -294,8 +298,11 @@ __global__ void __launch_bounds__(256, 1) fprop_kernel(const __grid_constant__ F
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (warp >= 4 && (BLOCK_N >= 64 || warp < 8)) {
     const int q = warp & 3;
+    const int half = (warp - 4) >> 2;                       // which half of the columns
+    constexpr int kHalfCols = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;
+    const int c_begin = half * kHalfCols, c_end = c_begin + kHalfCols;
     const int row = q * 32 + lane;
     const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
     int it = 0;
@@ -346,7 +353,7 @@ __global__ void __launch_bounds__(256, 1) fprop_kernel(const __grid_constant__ F
         if (has_aux || has_z) {
           if (row_valid) {
 #pragma unroll 1
-            for (int c = 0; c < BLOCK_N; c += 64) {
+            for (int c = c_begin; c < c_end; c += 64) {
               int col;
               int64_t oo, ao;
               locate(c, col, oo, ao);
@@ -356,13 +363,13 @@ __global__ void __launch_bounds__(256, 1) fprop_kernel(const __grid_constant__ F
           }
           int col;
           int64_t oo, ao;
-          locate(0, col, oo, ao);
+          locate(c_begin, col, oo, ao);
           epilogue_load<32>(p, col, row_valid, oo, ao, pa, pz);
         }
         mbar_wait(&tfull_bar[as], aphase);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 32) {
+        for (int c = c_begin; c < c_end; c += 32) {
           uint32_t r[32];
           tmem_ld_32x32(taddr + c, r);
           uint4 ca[4], cz[4];
@@ -371,7 +378,7 @@ __global__ void __launch_bounds__(256, 1) fprop_kernel(const __grid_constant__ F
             ca[g] = pa[g];
             cz[g] = pz[g];
           }
-          if ((has_aux || has_z) && c + 32 < BLOCK_N) {
+          if ((has_aux || has_z) && c + 32 < c_end) {
             int ncol;
             int64_t noo, nao;
             locate(c + 32, ncol, noo, nao);
@@ -547,6 +554,183 @@ __global__ void __launch_bounds__(256, 1) fprop_strip16_kernel(const __grid_cons
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 32);
+  }
+}
+
+
+// ------------------------------------------------------------------------------------ row-fold
+constexpr int kRfRing = 8;                       // strips resident (>= R + 1)
+constexpr int kRfStripBytes = kTileM * 128;      // 128 pixels x 64 ch bf16
+constexpr int kRfMaxR = 7;
+constexpr int kRfWBytes = 32 * 128;              // one filter row: 32 (s, co) rows x 64 ch
+constexpr int kRfFoldLd = 33;
+constexpr int kRfSmemBytes = kRfMaxR * kRfWBytes + kRfRing * kRfStripBytes + 2 * kTileM * kRfFoldLd * 4 + 1024 + 256;
+
+__global__ void __launch_bounds__(256, 1) fprop_rowfold_kernel(const __grid_constant__ RowfoldParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* wsm = smem;                                              // R x [32][64] bf16
+  uint8_t* ring = smem + kRfMaxR * kRfWBytes;                        // 28 KiB -> 1024-aligned
+  float* fold = reinterpret_cast<float*>(ring + kRfRing * kRfStripBytes);   // 2 x [128][33] fp32
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(fold) + 2 * kTileM * kRfFoldLd * 4);
+  uint64_t* empty_bar = full_bar + kRfRing;
+  uint64_t* tfull_bar = empty_bar + kRfRing;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* wfull_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int R = p.R, S = p.S;
+  const int tile_out = kTileM - (S - 1);             // output pixels per tile
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmA);
+    prefetch_tmap(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kRfRing; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 128);
+    }
+    mbar_init(wfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int items = p.n_img * p.tiles_w * p.chunks_h;
+
+  // work item -> (image, column tile, first output row, number of output rows)
+  auto decode = [&](int item, int& img, int& tw, int& h0, int& nrows) {
+    const int ch = item % p.chunks_h;
+    const int rest = item / p.chunks_h;
+    tw = rest % p.tiles_w;
+    img = rest / p.tiles_w;
+    h0 = ch * p.rows_per_item;
+    nrows = min(p.rows_per_item, p.OH - h0);
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(wfull_bar, static_cast<uint32_t>(R) * kRfWBytes);
+      for (int r = 0; r < R; ++r) tma_load_2d(wsm + r * kRfWBytes, &p.tmB, wfull_bar, 0, r * 32);
+    }
+    __syncwarp();
+    uint32_t g = 0;                                  // strips issued so far (ring position)
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int img, tw, h0, nrows;
+      decode(item, img, tw, h0, nrows);
+      const int x0 = p.org_w + tw * tile_out;
+      const int y0 = p.org_h + h0;
+      const int nstrips = nrows + R - 1;
+      for (int j = 0; j < nstrips; ++j, ++g) {
+        const uint32_t slot = g % kRfRing;
+        mbar_wait(&empty_bar[slot], ((g / kRfRing) & 1u) ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[slot], kRfStripBytes);
+          tma_load_4d(ring + slot * kRfStripBytes, &p.tmA, &full_bar[slot], 0, x0, y0 + j, img);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_bf16(kTileM, 32, 0, 0);
+    mbar_wait(wfull_bar, 0);
+    const uint32_t w_addr = smem_u32(wsm);
+    const uint32_t ring_addr = smem_u32(ring);
+    uint32_t g0 = 0;                                 // ring position of the item's first strip
+    int it = 0;                                      // tiles issued (accumulator stage / phase)
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int img, tw, h0, nrows;
+      decode(item, img, tw, h0, nrows);
+      for (int i = 0; i < nrows; ++i, ++it) {
+        const int as = it & 1;
+        mbar_wait(&tempty_bar[as], (((it >> 1) & 1) ^ 1u));
+        // strips g0+i .. g0+i+R-1 must have landed (only the last one is new after the first row)
+        for (int r = (i == 0 ? 0 : R - 1); r < R; ++r) {
+          const uint32_t g = g0 + i + r;
+          mbar_wait(&full_bar[g % kRfRing], (g / kRfRing) & 1u);
+        }
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d_tmem = tmem_base + as * 32;
+          for (int r = 0; r < R; ++r) {
+            const uint32_t g = g0 + i + r;
+            const uint64_t da = make_smem_desc(ring_addr + (g % kRfRing) * kRfStripBytes, 0, 1024);
+            const uint64_t db = make_smem_desc(w_addr + r * kRfWBytes, 0, 1024);
+#pragma unroll
+            for (int k = 0; k < kBlockK / 16; ++k)
+              umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (r > 0 || k > 0) ? 1u : 0u);
+          }
+          // the first strip of this row is dead now; after the item's last row so are the other R-1
+          umma_commit(&empty_bar[(g0 + i) % kRfRing]);
+          if (i == nrows - 1)
+            for (int r = 1; r < R; ++r) umma_commit(&empty_bar[(g0 + i + r) % kRfRing]);
+          umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+      }
+      g0 += nrows + R - 1;
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int t = q * 32 + lane;                     // TMEM lane = strip pixel = local output pixel
+    const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
+    float bias[4] = {0.f, 0.f, 0.f, 0.f};
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int co = 0; co < 4; ++co)
+        if (co < p.n_valid) bias[co] = __ldg(p.bias + co);
+    }
+    int it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int img, tw, h0, nrows;
+      decode(item, img, tw, h0, nrows);
+      const int ow = tw * tile_out + t;
+      const bool valid = (t < tile_out) && (ow < p.OW);
+      for (int i = 0; i < nrows; ++i, ++it) {
+        const int as = it & 1;
+        mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+        tc_fence_after();
+        uint32_t r32[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 32, r32);
+        tmem_ld_wait();
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);                // accumulator is in registers: free the stage
+        float* fb = fold + (it & 1) * kTileM * kRfFoldLd;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) fb[t * kRfFoldLd + j] = __uint_as_float(r32[j]);
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+        if (valid) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          for (int s = 0; s < S; ++s) {
+            const float* row = fb + (t + s) * kRfFoldLd + s * 4;
+#pragma unroll
+            for (int co = 0; co < 4; ++co) acc[co] += row[co];
+          }
+          const int oh = h0 + i;
+          float* o = p.out + img * p.o_sn + oh * p.o_sh + ow * p.o_sw;
+#pragma unroll
+          for (int co = 0; co < 4; ++co)
+            if (co < p.n_valid) o[co * p.o_sc] = apply_act(acc[co] * alpha + bias[co], p.act, 0.f);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
   }
 }
 
@@ -755,7 +939,7 @@ static cudaError_t launch_fprop_t(const FpropParams& p, int num_sms, cudaStream_
   const int total = p.n_img * p.tiles_h * p.tiles_w * p.phases * p.n_blocks;
   const int grid = total < num_sms ? total : num_sms;
   if (grid <= 0) return cudaSuccess;
-  fprop_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(p);
+  fprop_kernel<BLOCK_N><<<grid, kFpropThreads, Cfg::kSmemBytes, stream>>>(p);
   count_launch(1);
   return cudaGetLastError();
 }
@@ -783,6 +967,24 @@ cudaError_t launch_fprop_strip16(const FpropParams& p, int num_sms, cudaStream_t
   const int grid = total < num_sms ? total : num_sms;
   if (grid <= 0) return cudaSuccess;
   fprop_strip16_kernel<<<grid, 256, kStripSmemBytes, stream>>>(p);
+  count_launch(1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rowfold(const RowfoldParams& p, int num_sms, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fprop_rowfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kRfSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (p.R < 1 || p.R > kRfMaxR || p.S < 1 || p.S * 4 > 32 || p.n_valid > 4 || p.R + 1 > kRfRing)
+    return cudaErrorInvalidValue;
+  const int items = p.n_img * p.tiles_w * p.chunks_h;
+  const int grid = items < num_sms ? items : num_sms;
+  if (grid <= 0) return cudaSuccess;
+  fprop_rowfold_kernel<<<grid, 256, kRfSmemBytes, stream>>>(p);
   count_launch(1);
   return cudaGetLastError();
 }

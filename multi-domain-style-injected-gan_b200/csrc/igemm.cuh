@@ -83,7 +83,32 @@ struct WgradParams {
   int32_t upper_only;              // Gram: skip tiles strictly below the diagonal
 };
 
+// ---- "row-fold" kernel: stride-1 convolution with <= 4 output channels (the generator's final 7x7
+// 64->3 conv, model.py:141, and the input gradient of its first 7x7 3->64 conv, model.py:131).
+// The S horizontal taps are folded into the GEMM N dimension: for one output row,
+//   Q[q, (s, co)] = sum_{r, c} x[oh + r, q, c] * w[r][(s, co)][c]          (N = 4*S <= 32, K = R*64)
+// is accumulated in TMEM over the R input rows (one 128-pixel TMA strip each, kept in a shared-memory
+// ring so that consecutive output rows re-use R-1 of them), and the epilogue finishes
+//   y[oh, ow, co] = act(bias[co] + sum_s Q[ow + s, (s, co)])
+// through a shared-memory transpose. One tile = 128 - (S-1) output pixels of one row.
+struct RowfoldParams {
+  CUtensorMap tmA;                 // input [64 ch, W, H, N], box {64, 128, 1, 1}
+  CUtensorMap tmB;                 // packed weights [R*32 rows][64], box {64, 32}
+  int32_t R, S;
+  int32_t org_h, org_w;            // input coordinate read by output (0,0) through tap (0,0) (= -pad)
+  int32_t OH, OW, n_img;
+  int32_t tiles_w, rows_per_item, chunks_h;   // work item = (image, column tile, chunk of output rows)
+  float* out;                      // fp32
+  int64_t o_sn, o_sh, o_sw, o_sc;
+  int32_t n_valid;                 // output channels (<= 4)
+  const float* bias;
+  float alpha;
+  const float* alpha_ptr;
+  int32_t act;
+};
+
 cudaError_t launch_fprop(const FpropParams& p, int block_n, int num_sms, cudaStream_t stream);
+cudaError_t launch_rowfold(const RowfoldParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_wgrad(const WgradParams& p, int block_n, cudaStream_t stream);
 cudaError_t launch_fprop_strip16(const FpropParams& p, int num_sms, cudaStream_t stream);
 int igemm_kernel_launches();  // launches issued since process start (bench: gpu_launches)

@@ -235,6 +235,30 @@ __global__ void reflect_pad_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int
   }
 }
 
+__global__ void reflect_fold_nchw_kernel(const float* __restrict__ dy, int h, int w, int pad,
+                                         float* __restrict__ dx, int64_t total) {
+  const int H2 = h + 2 * pad, W2 = w + 2 * pad;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int iw = static_cast<int>(idx % w);
+    int64_t rem = idx / w;
+    const int ih = static_cast<int>(rem % h);
+    const int64_t plane = rem / h;                 // (n, c)
+    int ph[3], pw[3], nph = 0, npw = 0;
+    ph[nph++] = ih + pad;
+    pw[npw++] = iw + pad;
+    if (ih >= 1 && ih <= pad) ph[nph++] = pad - ih;
+    if (ih <= h - 2 && ih >= h - 1 - pad) ph[nph++] = pad + 2 * (h - 1) - ih;
+    if (iw >= 1 && iw <= pad) pw[npw++] = pad - iw;
+    if (iw <= w - 2 && iw >= w - 1 - pad) pw[npw++] = pad + 2 * (w - 1) - iw;
+    const float* src = dy + plane * H2 * W2;
+    float acc = 0.f;
+    for (int a = 0; a < nph; ++a)
+      for (int b = 0; b < npw; ++b) acc += __ldg(src + int64_t(ph[a]) * W2 + pw[b]);
+    dx[idx] = acc;
+  }
+}
+
 // ---------------------------------------------------------------- per-(n,c) reductions
 // Block = 256 threads = (c/8) channel groups x (2048/c) pixel lanes; grid = (chunks, n). Every thread
 // keeps kUnroll independent 16-byte loads in flight per operand (HBM latency x bandwidth needs
@@ -868,6 +892,16 @@ int msig_reflect_pad_bwd(const void* dy, int32_t n, int32_t h, int32_t w, int32_
   const int64_t groups = int64_t(n) * h * w * (c / 8);
   reflect_pad_bwd_kernel<<<grid_for(groups, 256, 148 * 32), 256, 0, ST(stream)>>>(CBF(dy), n, h, w, c, pad,
                                                                                  BF(dx), groups);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
+int msig_reflect_fold_nchw(const float* dy_padded, int32_t n, int32_t c, int32_t h, int32_t w, int32_t pad, float* dx,
+                           void* stream) {
+  MSIG_REQUIRE(dy_padded && dx && pad < h && pad < w, "msig_reflect_fold_nchw: bad argument");
+  const int64_t total = int64_t(n) * c * h * w;
+  reflect_fold_nchw_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, ST(stream)>>>(dy_padded, h, w, pad, dx, total);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;

@@ -17,7 +17,8 @@ import torch.nn as nn
 from . import ops
 from .lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, AUX_ADD, AUX_RELU_MASK, AUX_LRELU_MASK,
                   OUT_F32_NCHW, OUT_F32_NHWC, WPACK_CONVT_DGRAD, WPACK_CONVT_FWD, WPACK_DGRAD_S1,
-                  WPACK_DGRAD_S2, WPACK_FWD, WPACK_IM2COL, WPACK_IM2COL_DGRAD, WPACK_IM2COL_FLIP)
+                  WPACK_DGRAD_S2, WPACK_FWD, WPACK_IM2COL, WPACK_IM2COL_DGRAD, WPACK_IM2COL_FLIP,
+                  WPACK_ROWFOLD, WPACK_ROWFOLD_DGRAD)
 
 N_RESIDUAL_BLOCKS = 8   # reference config.py:19
 F32 = torch.float32
@@ -39,6 +40,9 @@ def _require_cuda(t, what):
 def _conv_stats(x, wpk, g, gamma=None, beta=None, gstride=0, transposed=False):
     """conv (or k4 s2 transposed conv) whose epilogue also emits the InstanceNorm / AdaIN statistics of
     its output: returns (z, NormStats). Replaces conv + a separate statistics pass (model.py:16,28-36)."""
+    if not ops.epi_fusable(4 if transposed else g.r * g.s, g.c):   # short K: the epilogue would dominate
+        z = ops.convT2d_fwd(x, wpk, g) if transposed else ops.conv2d_fwd(x, wpk, g)
+        return z, ops.in_stats(z, gamma, beta, gstride)
     if transposed:
         es = ops.epi_stats(g.n, g.h, g.w, g.k, x.device, phases=4)
         z = ops.convT2d_fwd(x, wpk, g, ops.epilogue(stats=es))
@@ -209,7 +213,7 @@ class StyleCycleGANGenerator(_Net):
     def _pack(self, t):
         enc, dec, k, sd = self.content_encoder, self.decoder, self.n_res, self.style_dim
         t["e0"] = ops.wpack(WPACK_IM2COL, enc[0].weight, 64, 3, 7, 7, out=t.get("e0"))
-        t["e0_d"] = ops.wpack(WPACK_IM2COL_DGRAD, enc[0].weight, 64, 3, 7, 7, out=t.get("e0_d"))
+        t["e0_rf"] = ops.wpack(WPACK_ROWFOLD_DGRAD, enc[0].weight, 64, 3, 7, 7, out=t.get("e0_rf"))
         t["e1"] = ops.wpack(WPACK_FWD, enc[3].weight, 128, 64, 4, 4, out=t.get("e1"))
         t["e1_d"] = ops.wpack(WPACK_DGRAD_S2, enc[3].weight, 128, 64, 4, 4, out=t.get("e1_d"))
         t["e2"] = ops.wpack(WPACK_FWD, enc[6].weight, 256, 128, 4, 4, out=t.get("e2"))
@@ -233,7 +237,7 @@ class StyleCycleGANGenerator(_Net):
         t["u1_d"] = ops.wpack(WPACK_CONVT_DGRAD, dec[k].weight, 128, 256, 4, 4, out=t.get("u1_d"))
         t["u2"] = ops.wpack(WPACK_CONVT_FWD, dec[k + 3].weight, 64, 128, 4, 4, out=t.get("u2"))
         t["u2_d"] = ops.wpack(WPACK_CONVT_DGRAD, dec[k + 3].weight, 64, 128, 4, 4, out=t.get("u2_d"))
-        t["f"] = ops.wpack(WPACK_FWD, dec[k + 6].weight, 3, 64, 7, 7, out=t.get("f"))
+        t["f"] = ops.wpack(WPACK_ROWFOLD, dec[k + 6].weight, 3, 64, 7, 7, out=t.get("f"))
         t["f_d"] = ops.wpack(WPACK_IM2COL_FLIP, dec[k + 6].weight, 3, 64, 7, 7, out=t.get("f_d"))
 
     def forward(self, content_image, style_code):
@@ -261,11 +265,9 @@ class _GeneratorFn(torch.autograd.Function):
         pg0 = ops.patch_geom(B, 3, H, W, 7, 7, 1, 3, 3, H, W, True)
         a0 = ops.patch_gather_cached(img, pg0)
         m0 = B * H * W
-        es0 = ops.epi_stats_rows(B, H * W, 64, img.device)
-        z0 = ops.conv2d_fwd(a0.view(1, 1, m0, pg0.kpad), P["e0"], ops.gemm_geom(m0, pg0.kpad, 64),
-                            ops.epilogue(stats=es0)).view(B, H, W, 64)
+        z0 = ops.conv2d_fwd(a0.view(1, 1, m0, pg0.kpad), P["e0"], ops.gemm_geom(m0, pg0.kpad, 64)).view(B, H, W, 64)
         del a0
-        st0 = ops.in_stats_from(es0, H * W, 64) if es0 is not None else ops.in_stats(z0)
+        st0 = ops.in_stats(z0)
         y0 = ops.norm_act_fwd(z0, st0, ACT_RELU)
         g1 = ops.conv_geom(B, H, W, 64, 128, 4, 4, 2, 1, 1, H // 2, W // 2)
         z1, st1 = _conv_stats(y0, P["e1"], g1)
@@ -300,8 +302,8 @@ class _GeneratorFn(torch.autograd.Function):
         yu2 = ops.norm_act_fwd(zu2, stu2, ACT_RELU)
         xp = ops.reflect_pad_fwd(yu2, 3)
         gf = ops.conv_geom(B, H + 6, W + 6, 64, 3, 7, 7, 1, 0, 0, H, W)
-        out = ops.conv2d_fwd(xp, P["f"], gf, ops.epilogue(bias=mod.decoder[k + 6].bias.detach(), act=ACT_TANH,
-                                                          out_layout=OUT_F32_NCHW))
+        out = ops.conv_narrow_fwd(xp, P["f"], gf, ops.epilogue(bias=mod.decoder[k + 6].bias.detach(), act=ACT_TANH,
+                                                               out_layout=OUT_F32_NCHW))
         if need_grad:
             ctx.mod = mod
             ctx.saved = dict(img=img, pg0=pg0, z0=z0, st0=st0, y0=y0, g1=g1, z1=z1, st1=st1, y1=y1, g2=g2, z2=z2,
@@ -410,11 +412,9 @@ class _GeneratorFn(torch.autograd.Function):
         dz1 = ops.norm_bwd_from(es, dy, S["z1"], S["st1"])
         if wg:
             ops.conv2d_wgrad(S["y0"], dz1, g1, _grad_buf(enc[3].weight))
-        es = ops.epi_stats(B, g1.oh, g1.ow, g1.c, dev, phases=4)
-        dy = ops.conv2d_dgrad(dz1, P["e1_d"], g1,
-                              ops.epilogue(aux=S["y0"], aux_mode=AUX_RELU_MASK, stats=es, stats_z=S["z0"]))
+        dy = ops.conv2d_dgrad(dz1, P["e1_d"], g1)      # K = 4*128: too short to hide the fused reductions
         del dz1
-        dz0 = ops.norm_bwd_from(es, dy, S["z0"], S["st0"])
+        dz0 = ops.norm_act_bwd(dy, S["z0"], S["st0"], ACT_RELU)
         m0 = B * H * W
         pg0 = S["pg0"]
         if wg:
@@ -427,8 +427,9 @@ class _GeneratorFn(torch.autograd.Function):
                 _grad_buf(p)
         dimg = None
         if S["img_grad"]:
-            da0 = ops.conv2d_fwd(dz0.view(1, 1, m0, 64), P["e0_d"], ops.gemm_geom(m0, 64, pg0.kpad))
-            dimg = ops.patch_scatter(da0.view(m0, pg0.kpad), pg0)
+            # 7x7 conv of dz0 (64 -> 3, flipped filter) over the reflect-padded domain, then the fold
+            gd = ops.conv_geom(B, H, W, 64, 3, 7, 7, 1, 6, 6, H + 6, W + 6)
+            dimg = ops.reflect_fold_nchw(ops.conv_narrow_fwd(dz0, P["e0_rf"], gd), 3)
         ctx.saved = None
         return (None, dimg, dstyle) + (None,) * (len(ctx.needs_input_grad) - 3)
 
@@ -687,11 +688,8 @@ class _DiscriminatorFn(torch.autograd.Function):
         mh = B * h * w
         # the dgrads apply LeakyReLU' of the layer below and reduce (sum g, sum g*z) for its norm backward
         dev = dout.device
-        z3 = S["layers"][2][2]
-        es = ops.epi_stats_rows(B, h * w, 512, dev)
-        dy = ops.conv2d_fwd(ad.view(1, 1, mh, pgh.kpad), P["h_d"], ops.gemm_geom(mh, pgh.kpad, 512),
-                            ops.epilogue(aux=S["y3"], aux_mode=AUX_LRELU_MASK, stats=es, stats_z=z3)
-                            if es is not None else None).view(B, h, w, 512)
+        es = None                                      # (the head GEMM's K is too short to fuse them)
+        dy = ops.conv2d_fwd(ad.view(1, 1, mh, pgh.kpad), P["h_d"], ops.gemm_geom(mh, pgh.kpad, 512)).view(B, h, w, 512)
         if wg:
             ws, splits = ops.gemm_tn_partial(mh, ad, pgh.kpad, S["y3"], 512)
             for kx, br in enumerate(mod.domain_branches):

@@ -56,6 +56,16 @@ def epilogue(bias=None, aux=None, aux_mode=AUX_NONE, act=ACT_NONE, alpha=1.0, al
                     _p(alpha_ptr), slope, out_layout, _p(None if stats is None else stats.buf), _p(stats_z))
 
 
+# The epilogue-fused reductions cost ~900 cycles per 64 accumulator columns per tile; they are hidden
+# behind the tile's main loop (2*N cycles per 64-deep K block) only when K is long enough. Below this
+# many K blocks the separate statistics / reduction pass is cheaper.
+EPI_STATS_MIN_KBLOCKS = 11
+
+
+def epi_fusable(taps, c):
+    return taps * c // 64 >= EPI_STATS_MIN_KBLOCKS
+
+
 class EpiStats:
     """Partial-sum buffer of the epilogue-fused reductions: [n * rows_per_img][2][ld] fp32."""
     __slots__ = ("buf", "n", "rows", "ld")
@@ -105,6 +115,24 @@ def conv2d_fwd(x, wpk, g, e=None, out=None):
             out = torch.empty((g.n, g.oh, g.ow, g.k), dtype=BF16, device=x.device)
     L.call("msig_conv2d_fwd", ctypes.byref(g), _p(x), _p(wpk), ctypes.byref(e), _p(out), _stream())
     return out
+
+
+def conv_narrow_fwd(x, wpk, g, e=None, out=None):
+    """Stride-1 conv with <= 4 output channels of a 64-channel NHWC input (row-fold kernel); fp32 NCHW out."""
+    e = e or epilogue(out_layout=OUT_F32_NCHW)
+    if out is None:
+        shape = (g.n, g.k, g.oh, g.ow) if e.out_layout == OUT_F32_NCHW else (g.n, g.oh, g.ow, g.k)
+        out = torch.empty(shape, dtype=F32, device=x.device)
+    L.call("msig_conv_narrow_fwd", ctypes.byref(g), _p(x), _p(wpk), ctypes.byref(e), _p(out), _stream())
+    return out
+
+
+def reflect_fold_nchw(dy_padded, pad):
+    n, c, h2, w2 = dy_padded.shape
+    h, w = h2 - 2 * pad, w2 - 2 * pad
+    dx = torch.empty((n, c, h, w), dtype=F32, device=dy_padded.device)
+    L.call("msig_reflect_fold_nchw", _p(dy_padded), n, c, h, w, pad, _p(dx), _stream())
+    return dx
 
 
 def conv2d_dgrad(dy, wpk, g, e=None, out=None):

@@ -117,6 +117,22 @@ conv_case("G enc 4x4s2 128->256 @128", B, 128, 128, 128, 256, 4, 2, 1, "fwd dgra
 convT_case("G up convT 256->128 @64", B, 64, 64, 256, 128)
 convT_case("G up convT 128->64 @128", B, 128, 128, 128, 64)
 conv_case("G final 7x7 64->3 (valid) @262", B, 262, 262, 64, 3, 7, 1, 0, "fwd")
+if not args.only or "narrow" in args.only:
+    xp = bf(B, 262, 262, 64)
+    wt = torch.randn(3, 64, 7, 7, device=dev) * 0.02
+    wpk = ops.wpack(L.WPACK_ROWFOLD, wt, 3, 64, 7, 7)
+    g = ops.conv_geom(B, 262, 262, 64, 3, 7, 7, 1, 0, 0, 256, 256)
+    y = torch.empty(B, 3, 256, 256, device=dev)
+    report("narrow (row-fold) 7x7 64->3 @262 fwd", timeit(lambda: ops.conv_narrow_fwd(xp, wpk, g, out=y)),
+           2.0 * B * 65536 * 3 * 64 * 49, xp.numel() * 2.0 + y.numel() * 4.0)
+    dz = bf(B, 256, 256, 64)
+    wt = torch.randn(64, 3, 7, 7, device=dev) * 0.02
+    wpk = ops.wpack(L.WPACK_ROWFOLD_DGRAD, wt, 64, 3, 7, 7)
+    g = ops.conv_geom(B, 256, 256, 64, 3, 7, 7, 1, 6, 6, 262, 262)
+    y = torch.empty(B, 3, 262, 262, device=dev)
+    report("narrow (row-fold) first-conv dgrad @256", timeit(lambda: ops.conv_narrow_fwd(dz, wpk, g, out=y)),
+           2.0 * B * 262 * 262 * 3 * 64 * 49, dz.numel() * 2.0 + y.numel() * 4.0)
+    report("reflect_fold_nchw", timeit(lambda: ops.reflect_fold_nchw(y, 3)), None, y.numel() * 4.0 + B * 3 * 65536 * 4.0)
 gemm_case("G first GEMM M=B*65536 K=192 N=64", B * 65536, 192, 64)
 gemm_case("G final dgrad GEMM M=B*262^2 K=192 N=64", B * 262 * 262, 192, 64)
 gemm_case("G first dgrad GEMM M=B*65536 K=64 N=192", B * 65536, 64, 192)

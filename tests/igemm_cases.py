@@ -134,6 +134,37 @@ def case_final_conv(n, h, w, mode, seed=0):
         L.load().msig_debug_set_strip_mode(1)
 
 
+def case_narrow_fwd(n, h, w, seed=0):
+    """Final 7x7 64->3 conv + bias + tanh through the row-fold kernel (msig_conv_narrow_fwd)."""
+    ops.ensure_init()
+    xp = _bf(_rand((n, 64, h + 6, w + 6), seed)).to(DEV)
+    wt = _bf(_rand((3, 64, 7, 7), seed + 1, 1.0 / (64 * 49) ** 0.5)).to(DEV)
+    b = _rand((3,), seed + 2).to(DEV)
+    ref = torch.tanh(F.conv2d(xp.float(), wt.float(), b))
+    wpk = ops.wpack(L.WPACK_ROWFOLD, wt.float().contiguous(), 3, 64, 7, 7)
+    g = ops.conv_geom(n, h + 6, w + 6, 64, 3, 7, 7, 1, 0, 0, h, w)
+    y = ops.conv_narrow_fwd(nhwc(xp), wpk, g, ops.epilogue(bias=b, act=L.ACT_TANH, out_layout=L.OUT_F32_NCHW))
+    torch.cuda.synchronize()
+    return rel_err(y, ref), 2e-3
+
+
+def case_narrow_dgrad(n, h, w, seed=0):
+    """Image gradient of the first 7x7 reflect conv 3->64 (model.py:131): row-fold conv of dz over the
+    zero-extended domain (out-of-bounds strips), then the reflect fold."""
+    ops.ensure_init()
+    dz = _bf(_rand((n, 64, h, w), seed)).to(DEV)
+    wt = _bf(_rand((64, 3, 7, 7), seed + 1, 1.0 / (64 * 49) ** 0.5)).to(DEV)
+    img = torch.zeros((n, 3, h, w), device=DEV, requires_grad=True)
+    z = F.conv2d(F.pad(img, (3, 3, 3, 3), mode="reflect"), wt.float())
+    z.backward(dz.float())
+    wpk = ops.wpack(L.WPACK_ROWFOLD_DGRAD, wt.float().contiguous(), 64, 3, 7, 7)
+    g = ops.conv_geom(n, h, w, 64, 3, 7, 7, 1, 6, 6, h + 6, w + 6)
+    dpad = ops.conv_narrow_fwd(nhwc(dz), wpk, g)
+    dimg = ops.reflect_fold_nchw(dpad, 3)
+    torch.cuda.synchronize()
+    return rel_err(dimg, img.grad), 2e-3
+
+
 def case_gemm(rows, k_in, n_out, seed=0, f32_out=False):
     """Linear layer as a 1x1 conv on a [1,1,rows,k_in] view."""
     ops.ensure_init()
@@ -186,6 +217,11 @@ CASES = {
     "final7x7_pertap": lambda: case_final_conv(2, 64, 256, 0),
     "final7x7_strip": lambda: case_final_conv(2, 64, 256, 1),
     "final7x7_strip_ragged": lambda: case_final_conv(1, 40, 200, 1),
+    "narrow_fwd_7x7": lambda: case_narrow_fwd(2, 64, 256),
+    "narrow_fwd_7x7_ragged": lambda: case_narrow_fwd(3, 40, 200),
+    "narrow_fwd_7x7_small": lambda: case_narrow_fwd(2, 16, 16),
+    "narrow_dgrad_7x7": lambda: case_narrow_dgrad(2, 64, 256),
+    "narrow_dgrad_7x7_small": lambda: case_narrow_dgrad(2, 24, 40),
     "fwd_1x1_gemm": lambda: case_gemm(200, 256, 512),
     "fwd_gemm_small_rows_f32": lambda: case_gemm(4, 512, 2560, f32_out=True),
     "dgrad_3x3_256": lambda: case_conv_dgrad(2, 256, 64, 64, 256, 3, 1, 1),
