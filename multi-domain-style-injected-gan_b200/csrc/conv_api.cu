@@ -337,7 +337,8 @@ static int run_conv(const void* in, int n, int h, int w, int c, int k, int R, in
         p.tap[r * S + s] = Tap{int8_t((rr - ph) / 2), int8_t((ss - pw) / 2), int8_t(ph * 2 + pw), 0};
       }
   }
-  if ((rc = make_w_map(&p.tmB, wpk, k_pad, int64_t(R) * S * c, block_n)) != MSIG_OK) return rc;
+  if ((rc = make_w_map(&p.tmB, wpk, k_pad, int64_t(R) * S * c, fprop_uses_pairs(p, block_n) ? 128 : block_n)) != MSIG_OK)
+    return rc;
   const OutView ov = make_out_view(out, e ? e->out_layout : MSIG_OUT_BF16_NHWC, OH, OW, k);
   if ((rc = fill_epilogue(p, e, ov, k)) != MSIG_OK) return rc;
   // Narrow-output "valid" stride-1 conv on 64 channels (the generator's final 7x7 conv on the
@@ -455,6 +456,12 @@ int32_t msig_epilogue_stats_rows(int32_t oh, int32_t ow, int32_t phases) {
   int TW, TH;
   pick_tile(ow, TW, TH);
   return static_cast<int32_t>(ceil_div(oh, TH) * ceil_div(ow, TW) * phases * 4);
+}
+
+// Test hook: CTA-pair (cta_group::2) kernel for 256-wide tiles on (default) / off.
+int msig_debug_set_pair_mode(int on) {
+  set_pair_mode(on != 0);
+  return MSIG_OK;
 }
 
 // Test hook: selects the kernel variant of the narrow-output 7x7 conv (see run_conv).

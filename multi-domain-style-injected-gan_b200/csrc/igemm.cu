@@ -179,6 +179,100 @@ __device__ __forceinline__ void fprop_epilogue_chunk(const FpropParams& p, const
   }
 }
 
+// Epilogue of ONE output tile for one epilogue warp: waits for the accumulator stage, then
+// alpha / bias / aux / activation / store (+ fused statistics) for this warp's columns
+// [c_begin, c_end) of accumulator rows q*32 .. q*32+31. `mt_full` = m-tile index incl. phase.
+template <int BLOCK_N>
+__device__ __forceinline__ void fprop_epilogue_tile(const FpropParams& p, int mt_full, int n_blk, uint32_t tmem_base,
+                                                    int as, uint32_t aphase, uint64_t* tfull_bar, int q, int lane,
+                                                    int c_begin, int c_end, float alpha) {
+  const int row = q * 32 + lane;
+  int mt = mt_full;
+  const int ph = mt % p.phases;
+  mt /= p.phases;
+  const int tw = mt % p.tiles_w;
+  mt /= p.tiles_w;
+  const int th = mt % p.tiles_h;
+  const int img = mt / p.tiles_h;
+  const int oh = th * p.TH + row / p.TW;
+  const int ow = tw * p.TW + row % p.TW;
+  const bool row_valid = (oh < p.OH) && (ow < p.OW);
+  const int64_t out_off = p.o_ph[ph] + img * p.o_sn + oh * p.o_sh + ow * p.o_sw;
+  const int64_t aux_off = p.a_ph[ph] + img * p.a_sn + oh * p.a_sh + ow * p.a_sw;
+  const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
+  if constexpr (BLOCK_N == 16) {
+    mbar_wait(&tfull_bar[as], aphase);
+    tc_fence_after();
+    uint32_t r[16];
+    uint4 av[2], zv[2];
+    epilogue_load<16>(p, n_blk * BLOCK_N, row_valid, out_off, aux_off, av, zv);
+    tmem_ld_32x16(taddr, r);
+    tmem_ld_wait();
+    fprop_epilogue_chunk<16, false>(p, r, av, zv, n_blk * BLOCK_N, row_valid, out_off, alpha);
+  } else {
+    const int64_t stat_row = int64_t(mt_full) * 4 + q;
+    // (column, output offset, aux offset) of accumulator chunk c
+    auto locate = [&](int c, int& col, int64_t& oo, int64_t& ao) {
+      col = n_blk * BLOCK_N + c;
+      oo = out_off;
+      ao = aux_off;
+      if (p.fold_c > 0) {                 // column -> (image, channel)
+        const int img_o = col / p.fold_c;
+        col -= img_o * p.fold_c;
+        oo += img_o * p.o_sn;
+        ao += img_o * p.a_sn;
+      }
+    };
+    // While the main loop of this tile is still running: pull the tile's aux / stat_z rows into L2
+    // and the first chunk's operands into registers.
+    const bool has_aux = p.aux_mode != AUX_NONE, has_z = p.stat_z != nullptr;
+    uint4 pa[4], pz[4];
+    if (has_aux || has_z) {
+      if (row_valid) {
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; c += 64) {
+          int col;
+          int64_t oo, ao;
+          locate(c, col, oo, ao);
+          if (has_aux) prefetch_l2(p.aux + ao + col);
+          if (has_z) prefetch_l2(p.stat_z + oo + col);
+        }
+      }
+      int col;
+      int64_t oo, ao;
+      locate(c_begin, col, oo, ao);
+      epilogue_load<32>(p, col, row_valid, oo, ao, pa, pz);
+    }
+    mbar_wait(&tfull_bar[as], aphase);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 32) {
+      uint32_t r[32];
+      tmem_ld_32x32(taddr + c, r);
+      uint4 ca[4], cz[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        ca[g] = pa[g];
+        cz[g] = pz[g];
+      }
+      if ((has_aux || has_z) && c + 32 < c_end) {
+        int ncol;
+        int64_t noo, nao;
+        locate(c + 32, ncol, noo, nao);
+        epilogue_load<32>(p, ncol, row_valid, noo, nao, pa, pz);
+      }
+      int col;
+      int64_t oo, ao;
+      locate(c, col, oo, ao);
+      tmem_ld_wait();
+      if (p.stat_out != nullptr)
+        fprop_epilogue_chunk<32, true>(p, r, ca, cz, col, row_valid, oo, alpha, stat_row, n_blk * BLOCK_N + c, lane);
+      else
+        fprop_epilogue_chunk<32, false>(p, r, ca, cz, col, row_valid, oo, alpha);
+    }
+  }
+}
+
 // 12 warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 idle, 4..11 = epilogue. The two
 // epilogue warps of a TMEM lane quadrant (warp % 4) split the accumulator columns in halves.
 constexpr int kFpropThreads = 384;
@@ -303,97 +397,13 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_kernel(const __grid_co
     const int half = (warp - 4) >> 2;                       // which half of the columns
     constexpr int kHalfCols = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;
     const int c_begin = half * kHalfCols, c_end = c_begin + kHalfCols;
-    const int row = q * 32 + lane;
     const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       const int as = it & 1;
       const uint32_t aphase = (it >> 1) & 1;
-      const int n_blk = tile % p.n_blocks;
-      int mt = tile / p.n_blocks;
-      const int ph = mt % p.phases;
-      mt /= p.phases;
-      const int tw = mt % p.tiles_w;
-      mt /= p.tiles_w;
-      const int th = mt % p.tiles_h;
-      const int img = mt / p.tiles_h;
-      const int oh = th * p.TH + row / p.TW;
-      const int ow = tw * p.TW + row % p.TW;
-      const bool row_valid = (oh < p.OH) && (ow < p.OW);
-      const int64_t out_off = p.o_ph[ph] + img * p.o_sn + oh * p.o_sh + ow * p.o_sw;
-      const int64_t aux_off = p.a_ph[ph] + img * p.a_sn + oh * p.a_sh + ow * p.a_sw;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N;
-      if constexpr (BLOCK_N == 16) {
-        mbar_wait(&tfull_bar[as], aphase);
-        tc_fence_after();
-        uint32_t r[16];
-        uint4 av[2], zv[2];
-        epilogue_load<16>(p, n_blk * BLOCK_N, row_valid, out_off, aux_off, av, zv);
-        tmem_ld_32x16(taddr, r);
-        tmem_ld_wait();
-        fprop_epilogue_chunk<16, false>(p, r, av, zv, n_blk * BLOCK_N, row_valid, out_off, alpha);
-      } else {
-        const int64_t stat_row = int64_t(tile / p.n_blocks) * 4 + q;
-        // (column, output offset, aux offset) of accumulator chunk c
-        auto locate = [&](int c, int& col, int64_t& oo, int64_t& ao) {
-          col = n_blk * BLOCK_N + c;
-          oo = out_off;
-          ao = aux_off;
-          if (p.fold_c > 0) {                 // column -> (image, channel)
-            const int img_o = col / p.fold_c;
-            col -= img_o * p.fold_c;
-            oo += img_o * p.o_sn;
-            ao += img_o * p.a_sn;
-          }
-        };
-        // While the main loop of this tile is still running: pull the tile's aux / stat_z rows into L2
-        // and the first chunk's operands into registers.
-        const bool has_aux = p.aux_mode != AUX_NONE, has_z = p.stat_z != nullptr;
-        uint4 pa[4], pz[4];
-        if (has_aux || has_z) {
-          if (row_valid) {
-#pragma unroll 1
-            for (int c = c_begin; c < c_end; c += 64) {
-              int col;
-              int64_t oo, ao;
-              locate(c, col, oo, ao);
-              if (has_aux) prefetch_l2(p.aux + ao + col);
-              if (has_z) prefetch_l2(p.stat_z + oo + col);
-            }
-          }
-          int col;
-          int64_t oo, ao;
-          locate(c_begin, col, oo, ao);
-          epilogue_load<32>(p, col, row_valid, oo, ao, pa, pz);
-        }
-        mbar_wait(&tfull_bar[as], aphase);
-        tc_fence_after();
-#pragma unroll 1
-        for (int c = c_begin; c < c_end; c += 32) {
-          uint32_t r[32];
-          tmem_ld_32x32(taddr + c, r);
-          uint4 ca[4], cz[4];
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            ca[g] = pa[g];
-            cz[g] = pz[g];
-          }
-          if ((has_aux || has_z) && c + 32 < c_end) {
-            int ncol;
-            int64_t noo, nao;
-            locate(c + 32, ncol, noo, nao);
-            epilogue_load<32>(p, ncol, row_valid, noo, nao, pa, pz);
-          }
-          int col;
-          int64_t oo, ao;
-          locate(c, col, oo, ao);
-          tmem_ld_wait();
-          if (p.stat_out != nullptr)
-            fprop_epilogue_chunk<32, true>(p, r, ca, cz, col, row_valid, oo, alpha, stat_row, n_blk * BLOCK_N + c, lane);
-          else
-            fprop_epilogue_chunk<32, false>(p, r, ca, cz, col, row_valid, oo, alpha);
-        }
-      }
+      fprop_epilogue_tile<BLOCK_N>(p, tile / p.n_blocks, tile % p.n_blocks, tmem_base, as, aphase, tfull_bar, q, lane,
+                                   c_begin, c_end, alpha);
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
     }
@@ -404,6 +414,149 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_kernel(const __grid_co
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------ CTA-pair fprop
+// fprop2_kernel: the BLOCK_N = 256 implicit GEMM on a CTA PAIR (cluster of 2, tcgen05 cta_group::2).
+// One MMA covers 256 output pixels (two 128-pixel m-tiles, one per CTA) x 256 channels; each CTA
+// stages its own A tile and only HALF of the weight tile (128 of the 256 rows), so the L2 -> shared
+// memory traffic per MMA drops from 48 KiB to 32 KiB per SM (the 1-CTA kernel runs at the L2
+// bandwidth roof) and the stage ring gets 6 slots instead of 4. Rank 0 issues the MMAs and
+// owns the full / accumulator-empty barriers; commits are multicast to both CTAs.
+// Requirements (host): phases == 1, no per-image B offsets, an even number of m-tiles.
+constexpr int k2Stages = 6;
+constexpr int k2BHalfBytes = 128 * kBlockK * 2;           // 16 KiB
+constexpr int k2StageBytes = kABytes + k2BHalfBytes;      // 32 KiB
+constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpropThreads, 1)
+    fprop2_kernel(const __grid_constant__ FpropParams p) {
+  constexpr int BLOCK_N = 256;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + k2Stages * k2StageBytes);
+  uint64_t* empty_bar = full_bar + k2Stages;
+  uint64_t* tfull_bar = empty_bar + k2Stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) prefetch_tmap(&p.tmA[i]);
+    prefetch_tmap(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < k2Stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 512);          // the 8 epilogue warps of BOTH CTAs (rank 0's copy is used)
+    }
+    fence_barrier_init();
+  }
+  cluster_sync_all();                          // barriers of both CTAs are initialised
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, 512);
+  tc_fence_before();
+  cluster_sync_all();                          // both halves of the accumulator are allocated
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = p.n_img * p.tiles_h * p.tiles_w;          // phases == 1
+  const int pairs = (m_tiles / 2) * p.n_blocks;
+  const int cluster_id = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int kblocks = p.taps * p.cblocks;
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int pr = cluster_id; pr < pairs; pr += n_clusters) {
+      const int n_blk = pr % p.n_blocks;
+      int mt = (pr / p.n_blocks) * 2 + static_cast<int>(rank);
+      const int tw = mt % p.tiles_w;
+      mt /= p.tiles_w;
+      const int th = mt % p.tiles_h;
+      const int img = mt / p.tiles_h;
+      const int oh0 = th * p.TH, ow0 = tw * p.TW;
+      const int n_off = n_blk * BLOCK_N + static_cast<int>(rank) * 128;      // this CTA's half of the weight rows
+      int kb = 0;
+      for (int t = 0; t < p.taps; ++t) {
+        const Tap tp = p.tap[t];
+        for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * k2StageBytes;
+            if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * k2StageBytes);   // both CTAs' bytes
+            tma_load_4d_2sm(sa, &p.tmA[tp.map], &full_bar[stage], cb * kBlockK, ow0 + tp.dw, oh0 + tp.dh, img);
+            tma_load_2d_2sm(sa + kABytes, &p.tmB, &full_bar[stage], kb * kBlockK, n_off);
+          }
+          __syncwarp();
+          if (++stage == k2Stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    const uint32_t idesc = make_idesc_bf16(256, BLOCK_N, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int pr = cluster_id; pr < pairs; pr += n_clusters, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[as], aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * k2StageBytes);
+          const uint64_t da = make_smem_desc(sa, 0, 1024);
+          const uint64_t db = make_smem_desc(sa + kABytes, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16_2sm(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(&empty_bar[stage], 3);
+          if (kb == kblocks - 1) umma_commit_2sm(&tfull_bar[as], 3);
+        }
+        __syncwarp();
+        if (++stage == k2Stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int c_begin = half * (BLOCK_N / 2), c_end = c_begin + BLOCK_N / 2;
+    const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
+    int it = 0;
+    for (int pr = cluster_id; pr < pairs; pr += n_clusters, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      const int n_blk = pr % p.n_blocks;
+      const int mt = (pr / p.n_blocks) * 2 + static_cast<int>(rank);
+      fprop_epilogue_tile<BLOCK_N>(p, mt, n_blk, tmem_base, as, aphase, tfull_bar, q, lane, c_begin, c_end, alpha);
+      tc_fence_before();
+      mbar_arrive_rank0(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();                          // no CTA exits (or frees TMEM) while its pair still works
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, 512);
   }
 }
 
@@ -944,7 +1097,34 @@ static cudaError_t launch_fprop_t(const FpropParams& p, int num_sms, cudaStream_
   return cudaGetLastError();
 }
 
+static bool g_pair_mode = true;
+void set_pair_mode(bool on) { g_pair_mode = on; }
+
+static cudaError_t launch_fprop2(const FpropParams& p, int num_sms, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fprop2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int pairs = (p.n_img * p.tiles_h * p.tiles_w / 2) * p.n_blocks;
+  int clusters = num_sms / 2;
+  if (pairs < clusters) clusters = pairs;
+  if (clusters <= 0) return cudaSuccess;
+  fprop2_kernel<<<2 * clusters, kFpropThreads, k2SmemBytes, stream>>>(p);
+  count_launch(1);
+  return cudaGetLastError();
+}
+
+// CTA pairs for the wide tiles whenever both CTAs of a pair can share the weight tile. (The weight
+// tensor map of a paired launch must have a 128-row box: each CTA loads half of the 256 rows.)
+bool fprop_uses_pairs(const FpropParams& p, int block_n) {
+  return g_pair_mode && block_n == 256 && p.phases == 1 && !p.tap_is_image && p.b_row_per_image == 0 &&
+         p.fold_c == 0 && ((p.n_img * p.tiles_h * p.tiles_w) % 2) == 0 && p.taps * p.cblocks >= 4;
+}
+
 cudaError_t launch_fprop(const FpropParams& p, int block_n, int num_sms, cudaStream_t stream) {
+  if (fprop_uses_pairs(p, block_n)) return launch_fprop2(p, num_sms, stream);
   switch (block_n) {
     case 16: return launch_fprop_t<16>(p, num_sms, stream);
     case 64: return launch_fprop_t<64>(p, num_sms, stream);
