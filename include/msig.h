@@ -87,6 +87,9 @@ enum {
   MSIG_WPACK_IM2COL = 5,      /* OIHW (small I) -> [Opad][Kpad], k=(r*s)*I+i   gathered-patch GEMM    */
   MSIG_WPACK_IM2COL_DGRAD = 6,/* OIHW (small I) -> [Kpad][O]                   its dgrad              */
   MSIG_WPACK_IM2COL_FLIP = 7, /* OIHW (small O) -> [Ipad][Kpad], k=flip(r*s)*O+o  dgrad of a small-O conv via gathered dy */
+  MSIG_WPACK_ROWPATCH = 10,   /* OIHW (I <= 8) -> [Opad][r][s*8+i]                msig_conv_rowpatch_fwd          */
+  MSIG_WPACK_ROWPATCH_FLIP = 11,/* OIHW (O <= 8) -> [Ipad][R-1-r][(S-1-s)*8+o]     dgrad of a small-O conv as a
+                                 msig_conv_rowpatch_fwd over the pad8 output gradient (pad = R-1)              */
   MSIG_WPACK_ROWFOLD = 8,     /* OIHW (O <= 4, I = 64) -> [r][s*4+o][I]            msig_conv_narrow_fwd            */
   MSIG_WPACK_ROWFOLD_DGRAD = 9,/* OIHW (I <= 4, O = 64) -> [R-1-r][(S-1-s)*4+i][O]  dgrad (w.r.t. the image) of a
                                  small-I conv, run as msig_conv_narrow_fwd over dy with pad = R-1-pad          */
@@ -103,6 +106,22 @@ int msig_wpack(const msig_wpack_desc* d, const float* w, void* packed, void* str
  * (model.py:18; r=s=1 on a [1,1,M,K] view) and the 1x1 heads (model.py:84). */
 int msig_conv2d_fwd(const msig_conv_geom* g, const void* x, const void* w_fwd,
                     const msig_epilogue* e, void* y, void* stream);
+/* ---- row-patch convolutions of few-channel images (model.py:131 forward + weight gradient; model.py:141
+ * input gradient + weight gradient): no gathered patch matrix. msig_img_pad8 stores the fp32 NCHW image
+ * (c <= 8) reflect- or zero-padded as bf16 [n][h+2p][w+2p+2][8]; a TMA map with a one-pixel (16-byte) W
+ * stride then reads the (s, c) window of filter row r for every output pixel as one K-major 128-byte
+ * row. Geometry: n,h,w,c = the UNPADDED image, pad_t = pad_l = p, stride 1, s <= 8. */
+int msig_img_pad8(const float* src_nchw, int32_t n, int32_t c, int32_t h, int32_t w, int32_t pad,
+                  int32_t reflect, void* dst_pad8, void* stream);
+int msig_conv_rowpatch_fwd(const msig_conv_geom* g, const void* x_pad8, const void* w_rowpatch,
+                           const msig_epilogue* e, void* y, void* stream);
+size_t msig_conv_rowpatch_wgrad_workspace(const msig_conv_geom* g);
+/* flip=0: dw[k][c][r][s] (+)= wgrad(pad8 image, dy [n,oh,ow,64]); flip=1: pad8 holds the few-channel output
+ * gradient (pad = R-1) and `other` the 64-channel input [n,oh,ow,64] of a small-O conv (dw is [c][64][r][s]). */
+int msig_conv_rowpatch_wgrad(const msig_conv_geom* g, const void* x_pad8, const void* other, int flip,
+                             float* dw, int accumulate, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
 /* Stride-1 convolution with k <= 4 output channels of a 64-channel input (model.py:141, the final 7x7
  * 64->3 conv; and, with MSIG_WPACK_ROWFOLD_DGRAD weights, the image gradient of the first 7x7 3->64 conv,
  * model.py:131): the horizontal taps are folded into the GEMM N dimension and consecutive output rows

@@ -52,6 +52,8 @@ static int64_t pack_elems(const PackGeom& g) {
     case MSIG_WPACK_IM2COL: return int64_t(g.Opad) * g.Kpad;
     case MSIG_WPACK_IM2COL_DGRAD: return int64_t(g.Kpad) * g.OC;
     case MSIG_WPACK_IM2COL_FLIP: return int64_t(g.Ipad) * g.Kpad;
+    case MSIG_WPACK_ROWPATCH: return (g.I <= 8 && g.S <= 8) ? int64_t(g.Opad) * g.R * 64 : -1;
+    case MSIG_WPACK_ROWPATCH_FLIP: return (g.O <= 8 && g.S <= 8) ? int64_t(g.Ipad) * g.R * 64 : -1;
     case MSIG_WPACK_ROWFOLD: return (g.O <= 4 && g.S <= 8 && g.I == 64) ? int64_t(g.R) * 32 * g.I : -1;
     case MSIG_WPACK_ROWFOLD_DGRAD: return (g.I <= 4 && g.S <= 8 && g.O == 64) ? int64_t(g.R) * 32 * g.O : -1;
     default: return -1;
@@ -93,6 +95,14 @@ __device__ __forceinline__ int64_t packed_offset(const PackGeom& g, int o, int i
     case MSIG_WPACK_IM2COL: return int64_t(oo) * g.Kpad + t * g.I + i;
     case MSIG_WPACK_IM2COL_DGRAD: return (int64_t(t) * g.I + i) * g.OC + oo;
     case MSIG_WPACK_IM2COL_FLIP: return int64_t(i) * g.Kpad + (g.RS - 1 - t) * g.OC + oo;
+    case MSIG_WPACK_ROWPATCH: {       // [o][r][s*8 + i]
+      const int r = t / g.S, s2 = t % g.S;
+      return (int64_t(oo) * g.R + r) * 64 + s2 * 8 + i;
+    }
+    case MSIG_WPACK_ROWPATCH_FLIP: {  // [i][R-1-r][(S-1-s)*8 + o]
+      const int r = t / g.S, s2 = t % g.S;
+      return (int64_t(i) * g.R + (g.R - 1 - r)) * 64 + (g.S - 1 - s2) * 8 + oo;
+    }
     case MSIG_WPACK_ROWFOLD: {        // [r][s*4 + o][i]
       const int r = t / g.S, s2 = t % g.S;
       return (int64_t(r) * 32 + s2 * 4 + oo) * g.I + i;
@@ -130,6 +140,14 @@ __device__ __forceinline__ int64_t partial_offset(const PackGeom& g, int o, int 
     }
     case MSIG_WPACK_IM2COL: return int64_t(o) * g.Kpad + t * g.I + i;
     case MSIG_WPACK_IM2COL_FLIP: return (int64_t(g.RS - 1 - t) * g.OC + o + g.OOFF) * g.I + i;
+    case MSIG_WPACK_ROWPATCH: {       // [r / 4][o (64 rows)][(r % 4) * 64 + s*8 + i]
+      const int r = t / g.S, s2 = t % g.S;
+      return (int64_t(r / 4) * 64 + o) * 256 + (r % 4) * 64 + s2 * 8 + i;
+    }
+    case MSIG_WPACK_ROWPATCH_FLIP: {  // r' = R-1-r, s' = S-1-s:  [r' / 4][i (64 rows)][(r' % 4) * 64 + s'*8 + o]
+      const int r = g.R - 1 - t / g.S, s2 = g.S - 1 - t % g.S;
+      return (int64_t(r / 4) * 64 + i) * 256 + (r % 4) * 64 + s2 * 8 + o;
+    }
   }
   return 0;
 }
@@ -514,6 +532,121 @@ int msig_conv2d_fwd(const msig_conv_geom* g, const void* x, const void* w_fwd, c
                   g->ow, w_fwd, e, y, static_cast<cudaStream_t>(stream));
 }
 
+static size_t wgrad_ws_bytes(int M, int N, int taps, int64_t kb_total);
+
+// ---------------------------------------------------------------- row-patch convs (few-channel images)
+// A few-channel image (c <= 8) is stored zero/reflect-padded as bf16 [n][h+2p][w+2p+2][8] ("pad8").
+// The 8 consecutive pixels x 8 channels starting at pixel (y, x) are 64 contiguous bf16 = exactly one
+// 128-byte K row, so a TMA map whose W stride is ONE pixel (16 B, overlapping rows) delivers the
+// im2col row of filter row r for 128 output pixels as an ordinary K-major operand tile: the
+// implicit GEMM runs with taps = R, one 64-wide K block per tap, and no patch matrix ever exists.
+static void pick_tile_any(int OH, int OW, int& TW, int& TH) {
+  const int cand[4][2] = {{128, 1}, {64, 2}, {32, 4}, {16, 8}};
+  int64_t best = -1;
+  for (auto& cd : cand) {
+    const int64_t area = ceil_div(OW, cd[0]) * cd[0] * ceil_div(OH, cd[1]) * cd[1];
+    if (best < 0 || area < best) { best = area; TW = cd[0]; TH = cd[1]; }
+  }
+}
+
+static ActView pad8_view(const void* x_pad8, const msig_conv_geom* g) {
+  const int64_t Hp = g->h + 2 * g->pad_t, Wp = g->w + 2 * g->pad_l + 2;
+  // extents: 64 elements per window, one window per output column, every padded row
+  return ActView{x_pad8, 64, g->ow, Hp, g->n, 8, Wp * 8, Hp * Wp * 8};
+}
+
+static int rowpatch_check(const msig_conv_geom* g, const char* what) {
+  MSIG_REQUIRE(context_ready(), "msig_init() has not been called");
+  MSIG_REQUIRE(g->stride == 1 && g->s >= 1 && g->s <= 8 && g->r >= 1 && g->r <= kMaxTaps && g->pad_t >= 0 &&
+                   g->pad_l >= 0 && g->oh == g->h + 2 * g->pad_t - g->r + 1 && g->ow == g->w + 2 * g->pad_l - g->s + 1,
+               "%s: needs stride 1, s <= 8 and oh/ow = h/w + 2*pad - r/s + 1", what);
+  return MSIG_OK;
+}
+
+int msig_conv_rowpatch_fwd(const msig_conv_geom* g, const void* x_pad8, const void* w_rowpatch,
+                           const msig_epilogue* e, void* y, void* stream) {
+  MSIG_REQUIRE(g && x_pad8 && w_rowpatch && y, "msig_conv_rowpatch_fwd: null argument");
+  int rc;
+  if ((rc = rowpatch_check(g, "msig_conv_rowpatch_fwd")) != MSIG_OK) return rc;
+  FpropParams p;
+  init_fprop(p);
+  const int k_pad = pad_rows(g->k);
+  const int block_n = pick_block_n(k_pad);
+  pick_tile_any(g->oh, g->ow, p.TW, p.TH);
+  p.OH = g->oh; p.OW = g->ow;
+  p.tiles_h = static_cast<int>(ceil_div(g->oh, p.TH));
+  p.tiles_w = static_cast<int>(ceil_div(g->ow, p.TW));
+  p.n_img = g->n;
+  p.n_blocks = k_pad / block_n;
+  p.taps = g->r;
+  p.cblocks = 1;
+  if ((rc = make_act_map(&p.tmA[0], pad8_view(x_pad8, g), p.TW, p.TH)) != MSIG_OK) return rc;
+  for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
+  for (int r = 0; r < g->r; ++r) p.tap[r] = Tap{int8_t(r), 0, 0, 0};
+  if ((rc = make_w_map(&p.tmB, w_rowpatch, k_pad, int64_t(g->r) * 64, fprop_uses_pairs(p, block_n) ? 128 : block_n)) !=
+      MSIG_OK)
+    return rc;
+  const OutView ov = make_out_view(y, e ? e->out_layout : MSIG_OUT_BF16_NHWC, g->oh, g->ow, g->k);
+  if ((rc = fill_epilogue(p, e, ov, g->k)) != MSIG_OK) return rc;
+  cudaError_t ce = launch_fprop(p, block_n, sm_count(), static_cast<cudaStream_t>(stream));
+  if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "fprop(rowpatch) launch: %s", cudaGetErrorString(ce));
+  return MSIG_OK;
+}
+
+size_t msig_conv_rowpatch_wgrad_workspace(const msig_conv_geom* g) {
+  if (!g) return 0;
+  int PW, PH;
+  pick_kblock(g->ow, PW, PH);
+  const int64_t kb = int64_t(g->n) * ceil_div(g->oh, PH) * ceil_div(g->ow, PW);
+  return wgrad_ws_bytes(64, 256, static_cast<int>(ceil_div(g->r, 4)), kb);
+}
+
+// flip = 0: dw[k][c][r][s] (+)= sum_pix dy[pix, k] * patch_r[pix, (s, c)]         (k = 64 output channels of
+//           a conv over the pad8 image; `other` = dy, its bf16 NHWC output gradient [n, oh, ow, 64])
+// flip = 1: the image is a few-channel GRADIENT (pad8 of dz, pad = R-1) and `other` is the 64-channel
+//           input xp [n, oh, ow, 64] of a small-O conv: dw[o][c][r][s] (+)= sum_q xp[q, c] * dzpatch_r'[q, (s', o)],
+//           r' = R-1-r, s' = S-1-s   (the weight gradient of the generator's final conv, model.py:141)
+// GEMM: M = the 64 channels of `other` (one A box; the second half of the 128-row tile is never
+// stored), N = 256 = FOUR filter rows' (s, c) windows (one B box per filter row), K = pixels.
+int msig_conv_rowpatch_wgrad(const msig_conv_geom* g, const void* x_pad8, const void* other, int flip, float* dw,
+                             int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  MSIG_REQUIRE(g && x_pad8 && other && dw && workspace, "msig_conv_rowpatch_wgrad: null argument");
+  int rc;
+  if ((rc = rowpatch_check(g, "msig_conv_rowpatch_wgrad")) != MSIG_OK) return rc;
+  MSIG_REQUIRE(g->k == 64, "msig_conv_rowpatch_wgrad: the wide side must have 64 channels (k=%d)", g->k);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  pick_kblock(g->ow, p.PW, p.PH);
+  p.blocks_w = static_cast<int>(ceil_div(g->ow, p.PW));
+  p.blocks_h = static_cast<int>(ceil_div(g->oh, p.PH));
+  p.n_img = g->n;
+  p.taps = static_cast<int>(ceil_div(g->r, 4));         // groups of four filter rows
+  MSIG_REQUIRE(p.taps * 4 <= kMaxTaps, "rowpatch wgrad: too many filter rows");
+  const int64_t kb_total = int64_t(g->n) * p.blocks_h * p.blocks_w;
+  WgradPlan pl = plan_wgrad(64, 256, p.taps, kb_total);
+  const size_t need = size_t(pl.splits) * 64 * p.taps * 256 * sizeof(float);
+  MSIG_REQUIRE(workspace_bytes >= need, "rowpatch wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
+  p.m_blocks = pl.m_blocks; p.n_blocks = pl.n_blocks; p.splits = pl.splits;
+  p.kb_per_split = pl.kb_per_split; p.kb_total = pl.kb_total;
+  p.out = reinterpret_cast<float*>(workspace);
+  p.o_row = 256; p.o_tap = 64 * 256; p.o_split = int64_t(p.taps) * 64 * 256;
+  p.alpha = 1.f; p.m_valid = 64; p.n_valid = 256;
+  p.a_boxes = 1; p.b_box_tap = 1;
+  ActView vo{other, 64, g->ow, g->oh, g->n, 64, int64_t(g->ow) * 64, int64_t(g->oh) * g->ow * 64};
+  if ((rc = make_act_map(&p.tmA[0], vo, p.PW, p.PH)) != MSIG_OK) return rc;
+  if ((rc = make_act_map(&p.tmB[0], pad8_view(x_pad8, g), p.PW, p.PH)) != MSIG_OK) return rc;
+  for (int i = 1; i < 4; ++i) { p.tmA[i] = p.tmA[0]; p.tmB[i] = p.tmB[0]; }
+  for (int y = 0; y < p.taps; ++y) p.tapA[y] = Tap{0, 0, 0, 0};
+  // filter rows past R read whatever lies below (or TMA zero fill); their columns are never unpacked
+  for (int r = 0; r < p.taps * 4; ++r) p.tapB[r] = Tap{int8_t(r), 0, 0, 0};
+  cudaError_t ce = launch_wgrad(p, pl.block_n, st);
+  if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "rowpatch wgrad launch: %s", cudaGetErrorString(ce));
+  msig_wpack_desc d{flip ? MSIG_WPACK_ROWPATCH_FLIP : MSIG_WPACK_ROWPATCH, flip ? g->c : 64, flip ? 64 : g->c, g->r, g->s};
+  PackGeom pg = make_pack_geom(&d, 0, 0);
+  return launch_wgrad_reduce(pg, p.out, pl.splits, p.o_split, dw, accumulate, st);
+}
+
 // Narrow-output stride-1 conv through the row-fold kernel (see RowfoldParams).
 int msig_conv_narrow_fwd(const msig_conv_geom* g, const void* x, const void* w_rowfold, const msig_epilogue* e,
                          void* y, void* stream) {
@@ -778,7 +911,8 @@ int msig_wgrad_unpack(const msig_wpack_desc* d, int32_t oc, int32_t o_off, const
   MSIG_REQUIRE(d && partial && dw && splits >= 1, "msig_wgrad_unpack: bad argument");
   PackGeom pg = make_pack_geom(d, oc, o_off);
   MSIG_REQUIRE(pg.kind == MSIG_WPACK_FWD || pg.kind == MSIG_WPACK_IM2COL || pg.kind == MSIG_WPACK_IM2COL_FLIP ||
-                   pg.kind == MSIG_WPACK_CONVT_FWD,
+                   pg.kind == MSIG_WPACK_CONVT_FWD || pg.kind == MSIG_WPACK_ROWPATCH ||
+                   pg.kind == MSIG_WPACK_ROWPATCH_FLIP,
                "msig_wgrad_unpack: kind %d has no weight-gradient layout", pg.kind);
   return launch_wgrad_reduce(pg, partial, splits, split_stride, dw, accumulate, static_cast<cudaStream_t>(stream));
 }
@@ -894,7 +1028,7 @@ int msig_gram_bwd(const void* f, const void* ssym, int32_t n, int32_t h, int32_t
   if ((rc = make_act_map(&p.tmA[0], v, p.TW, p.TH)) != MSIG_OK) return rc;
   for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
   const int64_t dim = int64_t(n) * c;
-  if ((rc = make_w_map(&p.tmB, ssym, dim, dim, block_n)) != MSIG_OK) return rc;
+  if ((rc = make_w_map(&p.tmB, ssym, dim, dim, fprop_uses_pairs(p, block_n) ? 128 : block_n)) != MSIG_OK) return rc;
   msig_epilogue e;
   memset(&e, 0, sizeof(e));
   e.alpha = alpha; e.alpha_ptr = gscale; e.aux = aux; e.aux_mode = aux ? MSIG_AUX_ADD : MSIG_AUX_NONE;

@@ -487,13 +487,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpropThreads, 1)
       const int n_off = n_blk * BLOCK_N + static_cast<int>(rank) * 128;      // this CTA's half of the weight rows
       int kb = 0;
       for (int t = 0; t < p.taps; ++t) {
-        const Tap tp = p.tap[t];
+        int map = 0, cw = ow0, chh = oh0, cn = t;          // Gram backward: tap t reads image t
+        if (!p.tap_is_image) {
+          const Tap tp = p.tap[t];
+          map = tp.map;
+          cw = ow0 + tp.dw;
+          chh = oh0 + tp.dh;
+          cn = img;
+        }
         for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           if (elect_one()) {
             uint8_t* sa = smem + stage * k2StageBytes;
             if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * k2StageBytes);   // both CTAs' bytes
-            tma_load_4d_2sm(sa, &p.tmA[tp.map], &full_bar[stage], cb * kBlockK, ow0 + tp.dw, oh0 + tp.dh, img);
+            tma_load_4d_2sm(sa, &p.tmA[map], &full_bar[stage], cb * kBlockK, cw, chh, cn);
             tma_load_2d_2sm(sa + kABytes, &p.tmB, &full_bar[stage], kb * kBlockK, n_off);
           }
           __syncwarp();
@@ -976,21 +983,32 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
         vcb[i] -= nb[i] * p.CB;
       }
     }
+    const int a_boxes = p.a_boxes == 1 ? 1 : 2;
+    const uint32_t stage_tx = static_cast<uint32_t>(a_boxes * 8192 + Cfg::kBBytes);
     for (int kb = 0; kb < nk; ++kb) {
       const int oh0 = hb * p.PH, ow0 = wb * p.PW;
       mbar_wait(&empty_bar[stage], phase ^ 1u);
       if (elect_one()) {
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kABytes;
-        mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+        mbar_expect_tx(&full_bar[stage], stage_tx);
 #pragma unroll
         for (int i = 0; i < 2; ++i)
-          tma_load_4d(sa + i * 8192, &p.tmA[ta.map], &full_bar[stage], vca[i], ow0 + ta.dw, oh0 + ta.dh,
-                      p.fold_img ? na[i] : img);
+          if (i < a_boxes)
+            tma_load_4d(sa + i * 8192, &p.tmA[ta.map], &full_bar[stage], vca[i], ow0 + ta.dw, oh0 + ta.dh,
+                        p.fold_img ? na[i] : img);
+        if (p.b_box_tap) {
 #pragma unroll
-        for (int i = 0; i < BLOCK_N / 64; ++i)
-          tma_load_4d(sb + i * 8192, &p.tmB[tb.map], &full_bar[stage], vcb[i], ow0 + tb.dw, oh0 + tb.dh,
-                      p.fold_img ? nb[i] : img);
+          for (int i = 0; i < BLOCK_N / 64; ++i) {
+            const Tap tbi = p.tapB[tap * (BLOCK_N / 64) + i];
+            tma_load_4d(sb + i * 8192, &p.tmB[tbi.map], &full_bar[stage], 0, ow0 + tbi.dw, oh0 + tbi.dh, img);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < BLOCK_N / 64; ++i)
+            tma_load_4d(sb + i * 8192, &p.tmB[tb.map], &full_bar[stage], vcb[i], ow0 + tb.dw, oh0 + tb.dh,
+                        p.fold_img ? nb[i] : img);
+        }
       }
       __syncwarp();
       if (++wb == p.blocks_w) {
@@ -1119,8 +1137,8 @@ static cudaError_t launch_fprop2(const FpropParams& p, int num_sms, cudaStream_t
 // CTA pairs for the wide tiles whenever both CTAs of a pair can share the weight tile. (The weight
 // tensor map of a paired launch must have a 128-row box: each CTA loads half of the 256 rows.)
 bool fprop_uses_pairs(const FpropParams& p, int block_n) {
-  return g_pair_mode && block_n == 256 && p.phases == 1 && !p.tap_is_image && p.b_row_per_image == 0 &&
-         p.fold_c == 0 && ((p.n_img * p.tiles_h * p.tiles_w) % 2) == 0 && p.taps * p.cblocks >= 4;
+  return g_pair_mode && block_n == 256 && p.phases == 1 && p.b_row_per_image == 0 &&
+         ((p.n_img * p.tiles_h * p.tiles_w) % 2) == 0 && p.taps * p.cblocks >= 4;
 }
 
 cudaError_t launch_fprop(const FpropParams& p, int block_n, int num_sms, cudaStream_t stream) {

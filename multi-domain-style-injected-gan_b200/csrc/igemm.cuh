@@ -81,6 +81,11 @@ struct WgradParams {
   float alpha;
   int32_t m_valid, n_valid;
   int32_t upper_only;              // Gram: skip tiles strictly below the diagonal
+  int32_t a_boxes;                 // 0/2: both 64-channel A boxes are loaded; 1: only the first (M <= 64 valid rows;
+                                   //      rows 64..127 of the tile are never stored)
+  int32_t b_box_tap;               // 1: the BLOCK_N/64 boxes of the B tile are the SAME 64 "channels" read through
+                                   //    different taps: box i of CTA-tap y uses tapB[y*(BLOCK_N/64) + i]
+                                   //    (row-patch weight gradients: 4 filter rows per CTA)
 };
 
 // ---- "row-fold" kernel: stride-1 convolution with <= 4 output channels (the generator's final 7x7

@@ -235,6 +235,36 @@ __global__ void reflect_pad_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int
   }
 }
 
+// fp32 NCHW [n,c,h,w] (c <= 8) -> bf16 [n][h+2p][w+2p+2][8], reflect or zero padding; channels >= c and
+// the two slack columns are zero. One thread per padded pixel (one 16-byte store).
+__global__ void img_pad8_kernel(const float* __restrict__ src, int c, int h, int w, int pad, int reflect,
+                                __nv_bfloat16* __restrict__ dst, int64_t total) {
+  const int Hp = h + 2 * pad, Wp = w + 2 * pad + 2;
+  const int64_t plane = int64_t(h) * w;
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    const int px = static_cast<int>(idx % Wp);
+    int64_t rem = idx / Wp;
+    const int py = static_cast<int>(rem % Hp);
+    const int64_t img = rem / Hp;
+    int ih = py - pad, iw = px - pad;
+    bool ok = px < w + 2 * pad;
+    if (reflect) {
+      ih = reflect_idx(ih, h);
+      iw = reflect_idx(iw, w);
+    }
+    ok = ok && ih >= 0 && ih < h && iw >= 0 && iw < w;
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (ok) {
+      const float* sp = src + img * c * plane + int64_t(ih) * w + iw;
+#pragma unroll
+      for (int ch = 0; ch < 8; ++ch)
+        if (ch < c) f[ch] = __ldg(sp + ch * plane);
+    }
+    store8(dst + idx * 8, f);
+  }
+}
+
 __global__ void reflect_fold_nchw_kernel(const float* __restrict__ dy, int h, int w, int pad,
                                          float* __restrict__ dx, int64_t total) {
   const int H2 = h + 2 * pad, W2 = w + 2 * pad;
@@ -892,6 +922,17 @@ int msig_reflect_pad_bwd(const void* dy, int32_t n, int32_t h, int32_t w, int32_
   const int64_t groups = int64_t(n) * h * w * (c / 8);
   reflect_pad_bwd_kernel<<<grid_for(groups, 256, 148 * 32), 256, 0, ST(stream)>>>(CBF(dy), n, h, w, c, pad,
                                                                                  BF(dx), groups);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
+int msig_img_pad8(const float* src_nchw, int32_t n, int32_t c, int32_t h, int32_t w, int32_t pad, int32_t reflect,
+                  void* dst, void* stream) {
+  MSIG_REQUIRE(src_nchw && dst && c >= 1 && c <= 8 && pad >= 0 && (!reflect || (pad < h && pad < w)),
+               "msig_img_pad8: bad argument");
+  const int64_t total = int64_t(n) * (h + 2 * pad) * (w + 2 * pad + 2);
+  img_pad8_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, ST(stream)>>>(src_nchw, c, h, w, pad, reflect, BF(dst), total);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;

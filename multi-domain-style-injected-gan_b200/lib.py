@@ -17,7 +17,8 @@ ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
 AUX_NONE, AUX_ADD, AUX_RELU_MASK, AUX_LRELU_MASK = 0, 1, 2, 3
 OUT_BF16_NHWC, OUT_F32_NCHW, OUT_F32_NHWC = 0, 1, 2
 (WPACK_FWD, WPACK_DGRAD_S1, WPACK_DGRAD_S2, WPACK_CONVT_FWD, WPACK_CONVT_DGRAD, WPACK_IM2COL,
- WPACK_IM2COL_DGRAD, WPACK_IM2COL_FLIP, WPACK_ROWFOLD, WPACK_ROWFOLD_DGRAD) = range(10)
+ WPACK_IM2COL_DGRAD, WPACK_IM2COL_FLIP, WPACK_ROWFOLD, WPACK_ROWFOLD_DGRAD, WPACK_ROWPATCH,
+ WPACK_ROWPATCH_FLIP) = range(12)
 
 
 class ConvGeom(Structure):
@@ -55,6 +56,10 @@ _SIGS = {
     "msig_wpack_part_elems": (c_size_t, [POINTER(WpackDesc), c_int32]),
     "msig_wpack_part": (c_int, [POINTER(WpackDesc), c_int32, c_int32, _P, _P, _P]),
     "msig_conv2d_fwd": (c_int, [POINTER(ConvGeom), _P, _P, POINTER(Epilogue), _P, _P]),
+    "msig_img_pad8": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
+    "msig_conv_rowpatch_fwd": (c_int, [POINTER(ConvGeom), _P, _P, POINTER(Epilogue), _P, _P]),
+    "msig_conv_rowpatch_wgrad_workspace": (c_size_t, [POINTER(ConvGeom)]),
+    "msig_conv_rowpatch_wgrad": (c_int, [POINTER(ConvGeom), _P, _P, c_int, _P, c_int, _P, c_size_t, _P]),
     "msig_conv_narrow_fwd": (c_int, [POINTER(ConvGeom), _P, _P, POINTER(Epilogue), _P, _P]),
     "msig_reflect_fold_nchw": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "msig_conv2d_dgrad": (c_int, [POINTER(ConvGeom), _P, _P, POINTER(Epilogue), _P, _P]),

@@ -18,7 +18,7 @@ from . import ops
 from .lib import (ACT_LRELU, ACT_NONE, ACT_RELU, ACT_TANH, AUX_ADD, AUX_RELU_MASK, AUX_LRELU_MASK,
                   OUT_F32_NCHW, OUT_F32_NHWC, WPACK_CONVT_DGRAD, WPACK_CONVT_FWD, WPACK_DGRAD_S1,
                   WPACK_DGRAD_S2, WPACK_FWD, WPACK_IM2COL, WPACK_IM2COL_DGRAD, WPACK_IM2COL_FLIP,
-                  WPACK_ROWFOLD, WPACK_ROWFOLD_DGRAD)
+                  WPACK_ROWFOLD, WPACK_ROWFOLD_DGRAD, WPACK_ROWPATCH, WPACK_ROWPATCH_FLIP)
 
 N_RESIDUAL_BLOCKS = 8   # reference config.py:19
 F32 = torch.float32
@@ -212,7 +212,7 @@ class StyleCycleGANGenerator(_Net):
     # -- packed weights ------------------------------------------------------------------
     def _pack(self, t):
         enc, dec, k, sd = self.content_encoder, self.decoder, self.n_res, self.style_dim
-        t["e0"] = ops.wpack(WPACK_IM2COL, enc[0].weight, 64, 3, 7, 7, out=t.get("e0"))
+        t["e0"] = ops.wpack(WPACK_ROWPATCH, enc[0].weight, 64, 3, 7, 7, out=t.get("e0"))
         t["e0_rf"] = ops.wpack(WPACK_ROWFOLD_DGRAD, enc[0].weight, 64, 3, 7, 7, out=t.get("e0_rf"))
         t["e1"] = ops.wpack(WPACK_FWD, enc[3].weight, 128, 64, 4, 4, out=t.get("e1"))
         t["e1_d"] = ops.wpack(WPACK_DGRAD_S2, enc[3].weight, 128, 64, 4, 4, out=t.get("e1_d"))
@@ -238,7 +238,7 @@ class StyleCycleGANGenerator(_Net):
         t["u2"] = ops.wpack(WPACK_CONVT_FWD, dec[k + 3].weight, 64, 128, 4, 4, out=t.get("u2"))
         t["u2_d"] = ops.wpack(WPACK_CONVT_DGRAD, dec[k + 3].weight, 64, 128, 4, 4, out=t.get("u2_d"))
         t["f"] = ops.wpack(WPACK_ROWFOLD, dec[k + 6].weight, 3, 64, 7, 7, out=t.get("f"))
-        t["f_d"] = ops.wpack(WPACK_IM2COL_FLIP, dec[k + 6].weight, 3, 64, 7, 7, out=t.get("f_d"))
+        t["f_d"] = ops.wpack(WPACK_ROWPATCH_FLIP, dec[k + 6].weight, 3, 64, 7, 7, out=t.get("f_d"))
 
     def forward(self, content_image, style_code):
         return _GeneratorFn.apply(self, content_image, style_code, *self.parameters())
@@ -262,11 +262,9 @@ class _GeneratorFn(torch.autograd.Function):
         need_grad = any(ctx.needs_input_grad)   # (forward itself always runs with grad mode off)
         S = {}   # saved activations
         # ---- content encoder (model.py:130-134)
-        pg0 = ops.patch_geom(B, 3, H, W, 7, 7, 1, 3, 3, H, W, True)
-        a0 = ops.patch_gather_cached(img, pg0)
-        m0 = B * H * W
-        z0 = ops.conv2d_fwd(a0.view(1, 1, m0, pg0.kpad), P["e0"], ops.gemm_geom(m0, pg0.kpad, 64)).view(B, H, W, 64)
-        del a0
+        # 7x7 reflect conv on the 3-channel image: row-patch implicit GEMM over the padded bf16 copy
+        g0 = ops.conv_geom(B, H, W, 3, 64, 7, 7, 1, 3, 3, H, W)
+        z0 = ops.conv_rowpatch_fwd(ops.img_pad8_cached(img, 3, True), P["e0"], g0)
         st0 = ops.in_stats(z0)
         y0 = ops.norm_act_fwd(z0, st0, ACT_RELU)
         g1 = ops.conv_geom(B, H, W, 64, 128, 4, 4, 2, 1, 1, H // 2, W // 2)
@@ -306,7 +304,7 @@ class _GeneratorFn(torch.autograd.Function):
                                                                out_layout=OUT_F32_NCHW))
         if need_grad:
             ctx.mod = mod
-            ctx.saved = dict(img=img, pg0=pg0, z0=z0, st0=st0, y0=y0, g1=g1, z1=z1, st1=st1, y1=y1, g2=g2, z2=z2,
+            ctx.saved = dict(img=img, g0=g0, z0=z0, st0=st0, y0=y0, g1=g1, z1=z1, st1=st1, y1=y1, g2=g2, z2=z2,
                              st2=st2, x2=res[0][0] if k else x, sb=sb, bs=bs, res=res, g3=g3, x_res=x, gu1=gu1,
                              zu1=zu1, stu1=stu1, yu1=yu1, gu2=gu2, zu2=zu2, stu2=stu2, xp=xp, out=out,
                              style_shape=style.shape, img_grad=ctx.needs_input_grad[1], style_grad=ctx.needs_input_grad[2])
@@ -327,13 +325,12 @@ class _GeneratorFn(torch.autograd.Function):
         dz = ops.tanh_bwd(dout, out)
         if wg:
             ops.nchw_chansum(dz, _grad_buf(dec[k + 6].bias))
-        pgf = ops.patch_geom(B, 3, H, W, 7, 7, 1, 6, 6, H + 6, W + 6, False)
-        ad = ops.patch_gather(dz, pgf)
-        mq = B * (H + 6) * (W + 6)
-        dxp = ops.conv2d_fwd(ad.view(1, 1, mq, pgf.kpad), P["f_d"], ops.gemm_geom(mq, pgf.kpad, 64)).view(B, H + 6, W + 6, 64)
+        gfd = ops.conv_geom(B, H, W, 3, 64, 7, 7, 1, 6, 6, H + 6, W + 6)
+        dz8 = ops.img_pad8(dz, 6, False)            # zero-extended bf16 copy of the 3-channel gradient
+        dxp = ops.conv_rowpatch_fwd(dz8, P["f_d"], gfd)
         if wg:
-            ops.patch_wgrad(WPACK_IM2COL_FLIP, 3, 64, 7, 7, mq, ad, pgf.kpad, S["xp"], 64, _grad_buf(dec[k + 6].weight))
-        del ad
+            ops.conv_rowpatch_wgrad(dz8, S["xp"], gfd, _grad_buf(dec[k + 6].weight), flip=True)
+        del dz8
         dy = ops.reflect_pad_bwd(dxp, 3)
         del dxp
         # ---- up 2 (ConvTranspose 128->64 + IN + ReLU)
@@ -415,12 +412,9 @@ class _GeneratorFn(torch.autograd.Function):
         dy = ops.conv2d_dgrad(dz1, P["e1_d"], g1)      # K = 4*128: too short to hide the fused reductions
         del dz1
         dz0 = ops.norm_act_bwd(dy, S["z0"], S["st0"], ACT_RELU)
-        m0 = B * H * W
-        pg0 = S["pg0"]
         if wg:
-            a0 = ops.patch_gather_cached(S["img"], pg0)   # re-gathered (or step-cached), not saved: 25 MB / image
-            ops.patch_wgrad(WPACK_IM2COL, 64, 3, 7, 7, m0, dz0, 64, a0, pg0.kpad, _grad_buf(enc[0].weight))
-            del a0
+            # the padded bf16 image copy is re-made (or step-cached), not saved
+            ops.conv_rowpatch_wgrad(ops.img_pad8_cached(S["img"], 3, True), dz0, S["g0"], _grad_buf(enc[0].weight))
             # conv biases that feed an InstanceNorm have an exactly-zero true gradient (the mean
             # subtraction removes them); the reference produces float noise ~1e-9 there.
             for p in mod._dead_biases():

@@ -117,6 +117,41 @@ def conv2d_fwd(x, wpk, g, e=None, out=None):
     return out
 
 
+def img_pad8(src, pad, reflect):
+    """fp32 NCHW image (c <= 8) -> bf16 [n, h+2p, w+2p+2, 8], reflect or zero padded (row-patch convs)."""
+    n, c, h, w = src.shape
+    out = torch.empty((n, h + 2 * pad, w + 2 * pad + 2, 8), dtype=BF16, device=src.device)
+    L.call("msig_img_pad8", _p(src), n, c, h, w, pad, int(reflect), _p(out), _stream())
+    return out
+
+
+def img_pad8_cached(src, pad, reflect):
+    """img_pad8 of an IMAGE that stays unchanged for the rest of the step (see patch_gather_cached)."""
+    if _step_cache is None:
+        return img_pad8(src, pad, reflect)
+    key = ("pad8", src.data_ptr(), src._version, tuple(src.shape), pad, bool(reflect))
+    hit = _step_cache.get(key)
+    if hit is None:
+        hit = (src, img_pad8(src, pad, reflect))
+        _step_cache[key] = hit
+    return hit[1]
+
+
+def conv_rowpatch_fwd(x_pad8, wpk, g, e=None, out=None):
+    e = e or epilogue()
+    if out is None:
+        out = torch.empty((g.n, g.oh, g.ow, g.k), dtype=BF16, device=x_pad8.device)
+    L.call("msig_conv_rowpatch_fwd", ctypes.byref(g), _p(x_pad8), _p(wpk), ctypes.byref(e), _p(out), _stream())
+    return out
+
+
+def conv_rowpatch_wgrad(x_pad8, other, g, dw, flip=False, accumulate=True):
+    nbytes = L.load().msig_conv_rowpatch_wgrad_workspace(ctypes.byref(g))
+    ws = workspace(nbytes, x_pad8.device)
+    L.call("msig_conv_rowpatch_wgrad", ctypes.byref(g), _p(x_pad8), _p(other), int(flip), _p(dw), int(accumulate),
+           _p(ws), ws.numel(), _stream())
+
+
 def conv_narrow_fwd(x, wpk, g, e=None, out=None):
     """Stride-1 conv with <= 4 output channels of a 64-channel NHWC input (row-fold kernel); fp32 NCHW out."""
     e = e or epilogue(out_layout=OUT_F32_NCHW)

@@ -133,6 +133,26 @@ if not args.only or "narrow" in args.only:
     report("narrow (row-fold) first-conv dgrad @256", timeit(lambda: ops.conv_narrow_fwd(dz, wpk, g, out=y)),
            2.0 * B * 262 * 262 * 3 * 64 * 49, dz.numel() * 2.0 + y.numel() * 4.0)
     report("reflect_fold_nchw", timeit(lambda: ops.reflect_fold_nchw(y, 3)), None, y.numel() * 4.0 + B * 3 * 65536 * 4.0)
+if not args.only or "rowpatch" in args.only:
+    img = torch.randn(B, 3, 256, 256, device=dev)
+    wt = torch.randn(64, 3, 7, 7, device=dev) * 0.02
+    g = ops.conv_geom(B, 256, 256, 3, 64, 7, 7, 1, 3, 3, 256, 256)
+    report("rowpatch img_pad8 reflect", timeit(lambda: ops.img_pad8(img, 3, True)), None, img.numel() * 4.0 + B * 262 * 264 * 16.0)
+    x8 = ops.img_pad8(img, 3, True)
+    wpk = ops.wpack(L.WPACK_ROWPATCH, wt, 64, 3, 7, 7)
+    y = torch.empty(B, 256, 256, 64, device=dev, dtype=torch.bfloat16)
+    report("rowpatch first conv 7x7 3->64 fwd", timeit(lambda: ops.conv_rowpatch_fwd(x8, wpk, g, out=y)), 2.0 * B * 65536 * 64 * 147)
+    dw = torch.zeros(64, 3, 7, 7, device=dev)
+    report("rowpatch first conv wgrad", timeit(lambda: ops.conv_rowpatch_wgrad(x8, y, g, dw)), 2.0 * B * 65536 * 64 * 147)
+    dz = torch.randn(B, 3, 256, 256, device=dev)
+    gfd = ops.conv_geom(B, 256, 256, 3, 64, 7, 7, 1, 6, 6, 262, 262)
+    dz8 = ops.img_pad8(dz, 6, False)
+    wt3 = torch.randn(3, 64, 7, 7, device=dev) * 0.02
+    wpf = ops.wpack(L.WPACK_ROWPATCH_FLIP, wt3, 3, 64, 7, 7)
+    dxp = torch.empty(B, 262, 262, 64, device=dev, dtype=torch.bfloat16)
+    report("rowpatch final conv dgrad 3->64 @262", timeit(lambda: ops.conv_rowpatch_fwd(dz8, wpf, gfd, out=dxp)), 2.0 * B * 262 * 262 * 64 * 147)
+    dw3 = torch.zeros(3, 64, 7, 7, device=dev)
+    report("rowpatch final conv wgrad", timeit(lambda: ops.conv_rowpatch_wgrad(dz8, dxp, gfd, dw3, flip=True)), 2.0 * B * 262 * 262 * 64 * 147)
 gemm_case("G first GEMM M=B*65536 K=192 N=64", B * 65536, 192, 64)
 gemm_case("G final dgrad GEMM M=B*262^2 K=192 N=64", B * 262 * 262, 192, 64)
 gemm_case("G first dgrad GEMM M=B*65536 K=64 N=192", B * 65536, 64, 192)

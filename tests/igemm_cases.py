@@ -165,6 +165,50 @@ def case_narrow_dgrad(n, h, w, seed=0):
     return rel_err(dimg, img.grad), 2e-3
 
 
+def case_rowpatch_first(n, h, w, which, seed=0):
+    """First generator conv (model.py:131): 7x7 reflect-padded 3->64 through the row-patch path."""
+    ops.ensure_init()
+    img = _bf(_rand((n, 3, h, w), seed)).float().to(DEV)
+    wt = _bf(_rand((64, 3, 7, 7), seed + 1, 1.0 / 147 ** 0.5)).float().to(DEV)
+    g = ops.conv_geom(n, h, w, 3, 64, 7, 7, 1, 3, 3, h, w)
+    xp8 = ops.img_pad8(img, 3, True)
+    padded = F.pad(img, (3, 3, 3, 3), mode="reflect")
+    if which == "fwd":
+        ref = F.conv2d(padded, wt)
+        wpk = ops.wpack(L.WPACK_ROWPATCH, wt.contiguous(), 64, 3, 7, 7)
+        y = ops.conv_rowpatch_fwd(xp8, wpk, g)
+        torch.cuda.synchronize()
+        return rel_err(nchw(y), ref), 1e-2
+    dy = _bf(_rand((n, 64, h, w), seed + 2)).to(DEV)
+    ref = torch.nn.grad.conv2d_weight(padded, (64, 3, 7, 7), dy.float())
+    dw = torch.zeros((64, 3, 7, 7), dtype=torch.float32, device=DEV)
+    ops.conv_rowpatch_wgrad(xp8, nhwc(dy), g, dw, flip=False, accumulate=False)
+    torch.cuda.synchronize()
+    return rel_err(dw, ref), 2e-3
+
+
+def case_rowpatch_final_bwd(n, h, w, which, seed=0):
+    """Backward of the final 7x7 64->3 conv (model.py:141) w.r.t. its reflect-padded input xp and its
+    weight, from the 3-channel gradient dz, through the row-patch path (pad8 of dz with pad 6)."""
+    ops.ensure_init()
+    xp = _bf(_rand((n, 64, h + 6, w + 6), seed)).to(DEV)
+    dz = _bf(_rand((n, 3, h, w), seed + 1)).float().to(DEV)
+    wt = _bf(_rand((3, 64, 7, 7), seed + 2, 1.0 / (64 * 49) ** 0.5)).float().to(DEV)
+    g = ops.conv_geom(n, h, w, 3, 64, 7, 7, 1, 6, 6, h + 6, w + 6)
+    dz8 = ops.img_pad8(dz, 6, False)
+    if which == "dgrad":
+        ref = torch.nn.grad.conv2d_input((n, 64, h + 6, w + 6), wt, dz)
+        wpk = ops.wpack(L.WPACK_ROWPATCH_FLIP, wt.contiguous(), 3, 64, 7, 7)
+        dxp = ops.conv_rowpatch_fwd(dz8, wpk, g)
+        torch.cuda.synchronize()
+        return rel_err(nchw(dxp), ref), 1e-2
+    ref = torch.nn.grad.conv2d_weight(xp.float(), (3, 64, 7, 7), dz)
+    dw = torch.zeros((3, 64, 7, 7), dtype=torch.float32, device=DEV)
+    ops.conv_rowpatch_wgrad(dz8, nhwc(xp), g, dw, flip=True, accumulate=False)
+    torch.cuda.synchronize()
+    return rel_err(dw, ref), 2e-3
+
+
 def case_gemm(rows, k_in, n_out, seed=0, f32_out=False):
     """Linear layer as a 1x1 conv on a [1,1,rows,k_in] view."""
     ops.ensure_init()
@@ -222,6 +266,14 @@ CASES = {
     "narrow_fwd_7x7_small": lambda: case_narrow_fwd(2, 16, 16),
     "narrow_dgrad_7x7": lambda: case_narrow_dgrad(2, 64, 256),
     "narrow_dgrad_7x7_small": lambda: case_narrow_dgrad(2, 24, 40),
+    "rowpatch_first_fwd": lambda: case_rowpatch_first(2, 64, 256, "fwd"),
+    "rowpatch_first_fwd_small": lambda: case_rowpatch_first(3, 24, 40, "fwd"),
+    "rowpatch_first_wgrad": lambda: case_rowpatch_first(2, 64, 256, "wgrad"),
+    "rowpatch_first_wgrad_w32": lambda: case_rowpatch_first(2, 32, 32, "wgrad"),
+    "rowpatch_final_dgrad": lambda: case_rowpatch_final_bwd(2, 64, 256, "dgrad"),
+    "rowpatch_final_dgrad_small": lambda: case_rowpatch_final_bwd(2, 26, 58, "dgrad"),
+    "rowpatch_final_wgrad": lambda: case_rowpatch_final_bwd(2, 64, 256, "wgrad"),
+    "rowpatch_final_wgrad_small": lambda: case_rowpatch_final_bwd(1, 26, 58, "wgrad"),
     "fwd_1x1_gemm": lambda: case_gemm(200, 256, 512),
     "fwd_gemm_small_rows_f32": lambda: case_gemm(4, 512, 2560, f32_out=True),
     "dgrad_3x3_256": lambda: case_conv_dgrad(2, 256, 64, 64, 256, 3, 1, 1),
