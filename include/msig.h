@@ -101,6 +101,20 @@ typedef struct msig_wpack_desc {
 size_t msig_wpack_elems(const msig_wpack_desc* d);   /* bf16 elements of the packed buffer */
 int msig_wpack(const msig_wpack_desc* d, const float* w, void* packed, void* stream);
 
+/* All packs of one network in one launch (they are refreshed after every optimizer step): describe them
+ * once as jobs, build the table (host memory, msig_wpack_table_bytes), copy it to the device, then call
+ * msig_wpack_multi each step. d.kind < 0 marks a plain fp32 copy of copy_numel elements (bias tables). */
+typedef struct msig_wpack_job {
+  msig_wpack_desc d;
+  int32_t oc, o_off;      /* composite packs, as in msig_wpack_part */
+  const float* src;       /* fp32 master weight (device) */
+  void* dst;              /* packed bf16 buffer (device); fp32 for copies */
+  int64_t copy_numel;
+} msig_wpack_job;
+size_t msig_wpack_table_bytes(int32_t n_jobs);
+int msig_wpack_table_build(const msig_wpack_job* jobs, int32_t n_jobs, void* table_host, int64_t* total_out);
+int msig_wpack_multi(const void* table_dev, int32_t n_jobs, int64_t total, void* stream);
+
 /* ---- convolutions (tcgen05 implicit GEMM) ------------------------------------------------
  * Replace nn.Conv2d (model.py:45,48,72-75,132-133,165,183; losses.py:15), nn.Linear
  * (model.py:18; r=s=1 on a [1,1,M,K] view) and the 1x1 heads (model.py:84). */

@@ -125,6 +125,35 @@ __global__ void wpack_kernel(PackGeom g, const float* __restrict__ w, __nv_bfloa
   }
 }
 
+// All weight packs of one network in ONE launch: a device-resident table of jobs (built once per
+// network by msig_wpack_table_build) indexed by a prefix sum over their element counts.
+struct PackJob {
+  PackGeom g;            // g.kind < 0: plain fp32 copy of `numel` elements (bias tables)
+  const float* w;
+  void* out;
+  int64_t start, numel;
+};
+
+__global__ void wpack_multi_kernel(const PackJob* __restrict__ jobs, int n_jobs, int64_t total) {
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+       idx += int64_t(gridDim.x) * blockDim.x) {
+    int lo = 0, hi = n_jobs - 1;                      // last job with start <= idx
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].start <= idx) lo = mid; else hi = mid - 1;
+    }
+    const PackJob& j = jobs[lo];
+    const int64_t li = idx - j.start;
+    if (j.g.kind < 0) {
+      reinterpret_cast<float*>(j.out)[li] = j.w[li];
+    } else {
+      int o, i, t;
+      decode_src(j.g, li, o, i, t);
+      reinterpret_cast<__nv_bfloat16*>(j.out)[packed_offset(j.g, o, i, t)] = __float2bfloat16(j.w[li]);
+    }
+  }
+}
+
 // Layout of the fp32 split-K partials written by the wgrad kernel, per kind:
 //   FWD          [O][RS][I]            CONVT_FWD     [O][16 = phase*4+tap][I]
 //   IM2COL       [O][Kpad]             IM2COL_FLIP   [Kpad][I]
@@ -519,6 +548,43 @@ size_t msig_wpack_part_elems(const msig_wpack_desc* d, int32_t oc) {
   PackGeom g = make_pack_geom(d, oc, 0);
   const int64_t n = pack_elems(g);
   return n < 0 ? 0 : static_cast<size_t>(n);
+}
+
+size_t msig_wpack_table_bytes(int32_t n_jobs) { return size_t(n_jobs) * sizeof(PackJob); }
+
+int msig_wpack_table_build(const msig_wpack_job* jobs, int32_t n_jobs, void* table_host, int64_t* total_out) {
+  MSIG_REQUIRE(jobs && table_host && total_out && n_jobs > 0, "msig_wpack_table_build: bad argument");
+  PackJob* t = reinterpret_cast<PackJob*>(table_host);
+  int64_t start = 0;
+  for (int k = 0; k < n_jobs; ++k) {
+    const msig_wpack_job& j = jobs[k];
+    MSIG_REQUIRE(j.src && j.dst, "msig_wpack_table_build: job %d has a null pointer", k);
+    memset(&t[k], 0, sizeof(PackJob));
+    if (j.d.kind < 0) {
+      t[k].g.kind = -1;
+      t[k].numel = j.copy_numel;
+    } else {
+      t[k].g = make_pack_geom(&j.d, j.oc, j.o_off);
+      MSIG_REQUIRE(pack_elems(t[k].g) > 0, "msig_wpack_table_build: job %d: unknown kind %d", k, j.d.kind);
+      t[k].numel = int64_t(t[k].g.O) * t[k].g.I * t[k].g.RS;
+    }
+    t[k].w = j.src;
+    t[k].out = j.dst;
+    t[k].start = start;
+    start += t[k].numel;
+  }
+  *total_out = start;
+  return MSIG_OK;
+}
+
+int msig_wpack_multi(const void* table_dev, int32_t n_jobs, int64_t total, void* stream) {
+  MSIG_REQUIRE(table_dev && n_jobs > 0 && total > 0, "msig_wpack_multi: bad argument");
+  const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(total, 256), 148 * 16));
+  wpack_multi_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const PackJob*>(table_dev), n_jobs, total);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
 }
 
 int msig_wpack(const msig_wpack_desc* d, const float* w, void* packed, void* stream) {

@@ -11,6 +11,7 @@ import random
 
 import torch
 
+from . import ops
 from .model import MultiDomainStyleEncoder, StyleCycleGANGenerator
 
 
@@ -114,16 +115,69 @@ def apply_style_mode(style_vectors, mode, noise_level=0.1):
     return style
 
 
-@torch.no_grad()
-def translate(generator, style_encoder, src, ref=None, ref_domain=None, style=None):
-    """Style injection (inference.py:119,290), batched: src [B,3,S,S] in [-1,1]; either reference
-    images `ref` [B,3,S,S] with their domain indices `ref_domain` [B], or a ready style code
-    `style` [1|B, style_dim]. Returns the translated images [B,3,S,S]."""
-    dev = next(generator.parameters()).device
+_translate_graphs = {}   # (generator, style encoder, shapes) -> captured forward, or "warm" after the first eager call
+
+
+def _translate_eager(generator, style_encoder, src, ref, ref_domain, style, dev):
     src = src.to(dev, non_blocking=True)
     if style is None:
-        if ref is None:
-            raise ValueError("translate: give reference images or a style code")
         y = None if ref_domain is None else ref_domain.to(dev, non_blocking=True)
         style = style_encoder(ref.to(dev, non_blocking=True), y)
     return generator(src, style.to(dev))
+
+
+@torch.no_grad()
+def translate(generator, style_encoder, src, ref=None, ref_domain=None, style=None, use_cuda_graph=None):
+    """Style injection (inference.py:119,290), batched: src [B,3,S,S] in [-1,1]; either reference
+    images `ref` [B,3,S,S] with their domain indices `ref_domain` [B], or a ready style code
+    `style` [1|B, style_dim]. Returns the translated images [B,3,S,S].
+
+    The forward has static shapes and no host synchronisation: from the second call with the same
+    shapes it is replayed from a captured CUDA graph (the ~110 launches of one batch otherwise cost
+    more host time than GPU time). The packed bf16 weights are refreshed outside the graph, in place,
+    so a weight update does not invalidate it. The returned tensor is the graph's output buffer: it
+    is overwritten by the next call with the same shapes (clone it to keep it).
+    `use_cuda_graph=False` (or MSIG_CUDA_GRAPH=0) keeps every call eager."""
+    dev = next(generator.parameters()).device
+    if style is None and ref is None:
+        raise ValueError("translate: give reference images or a style code")
+    if use_cuda_graph is None:
+        use_cuda_graph = os.environ.get("MSIG_CUDA_GRAPH", "1") != "0"
+    if not use_cuda_graph or dev.type != "cuda":
+        return _translate_eager(generator, style_encoder, src, ref, ref_domain, style, dev)
+    other = style if style is not None else ref
+    key = (id(generator), id(style_encoder), tuple(src.shape), style is None, tuple(other.shape), ref_domain is None)
+    entry = _translate_graphs.get(key)
+    if entry is None:                       # first call: eager (also builds the packed weights)
+        _translate_graphs[key] = "warm"
+        return _translate_eager(generator, style_encoder, src, ref, ref_domain, style, dev)
+    generator._packed.get()                 # refresh packed weights (no-op unless the parameters changed)
+    style_encoder._packed.get()
+    if entry == "warm":
+        st = {"src": torch.empty(src.shape, dtype=torch.float32, device=dev),
+              "other": torch.empty(other.shape, dtype=torch.float32, device=dev),
+              "dom": None if ref_domain is None else torch.empty(ref_domain.shape, dtype=torch.int64, device=dev)}
+        st["src"].copy_(src, non_blocking=True)
+        st["other"].copy_(other, non_blocking=True)
+        if st["dom"] is not None:
+            st["dom"].copy_(ref_domain, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        l0 = ops.kernel_launches()
+        with torch.cuda.graph(graph):
+            if style is None:
+                out = _translate_eager(generator, style_encoder, st["src"], st["other"], st["dom"], None, dev)
+            else:
+                out = _translate_eager(generator, style_encoder, st["src"], None, None, st["other"], dev)
+        launches = ops.kernel_launches() - l0
+        ops.add_replayed_launches(-launches)      # recorded, not executed, during capture
+        entry = {"graph": graph, "st": st, "out": out, "gen": generator, "se": style_encoder, "launches": launches}
+        _translate_graphs[key] = entry
+    st = entry["st"]
+    st["src"].copy_(src, non_blocking=True)
+    st["other"].copy_(other, non_blocking=True)
+    if st["dom"] is not None:
+        st["dom"].copy_(ref_domain, non_blocking=True)
+    entry["graph"].replay()
+    ops.add_replayed_launches(entry["launches"])
+    return entry["out"]

@@ -36,6 +36,11 @@ class WpackDesc(Structure):
     _fields_ = [(k, c_int32) for k in ("kind", "o", "i", "r", "s")]
 
 
+class WpackJob(Structure):
+    _fields_ = [("d", WpackDesc), ("oc", c_int32), ("o_off", c_int32), ("src", c_void_p), ("dst", c_void_p),
+                ("copy_numel", c_int64)]
+
+
 class PatchGeom(Structure):
     _fields_ = [(k, c_int32) for k in
                 ("n", "c", "h", "w", "r", "s", "stride", "pad_t", "pad_l", "oh", "ow", "reflect",
@@ -53,6 +58,9 @@ _SIGS = {
     "msig_kernel_launches": (c_longlong, []),
     "msig_wpack_elems": (c_size_t, [POINTER(WpackDesc)]),
     "msig_wpack": (c_int, [POINTER(WpackDesc), _P, _P, _P]),
+    "msig_wpack_table_bytes": (c_size_t, [c_int32]),
+    "msig_wpack_table_build": (c_int, [POINTER(WpackJob), c_int32, _P, POINTER(c_int64)]),
+    "msig_wpack_multi": (c_int, [_P, c_int32, c_int64, _P]),
     "msig_wpack_part_elems": (c_size_t, [POINTER(WpackDesc), c_int32]),
     "msig_wpack_part": (c_int, [POINTER(WpackDesc), c_int32, c_int32, _P, _P, _P]),
     "msig_conv2d_fwd": (c_int, [POINTER(ConvGeom), _P, _P, POINTER(Epilogue), _P, _P]),

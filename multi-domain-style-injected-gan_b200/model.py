@@ -60,14 +60,24 @@ class _PackedWeights:
     def __init__(self, module):
         self._module = module
         self._key = None
+        self._table = None      # ops.PackTable: all packs of the network in one launch
+        self._ptrs = None
         self.t = {}
 
     def get(self):
         m = self._module
         key = (m._dirty,) + tuple((p._version, p.data_ptr()) for p in m.parameters())
         if key != self._key:
+            ptrs = tuple(p.data_ptr() for p in m.parameters())
             with torch.no_grad():
-                m._pack(self.t)
+                if self._table is None or ptrs != self._ptrs:
+                    # first use (or the parameters moved): run the packs one by one and record them
+                    with ops.record_packs() as jobs:
+                        m._pack(self.t)
+                    self._table = ops.PackTable(jobs, next(m.parameters()).device)
+                    self._ptrs = ptrs
+                else:
+                    self._table.run()
             self._key = key
         return self.t
 
@@ -232,7 +242,7 @@ class StyleCycleGANGenerator(_Net):
                 ops.wpack(WPACK_FWD, ada.style_modulation.weight, 512, sd, 1, 1, out=t["lin"], oc=nl * 512, o_off=l * 512)
                 ops.wpack(WPACK_DGRAD_S1, ada.style_modulation.weight, 512, sd, 1, 1, out=t["lin_d"], oc=nl * 512,
                           o_off=l * 512)
-                t["lin_b"][l * 512:(l + 1) * 512].copy_(ada.style_modulation.bias)
+                ops.copy_f32(t["lin_b"][l * 512:(l + 1) * 512], ada.style_modulation.bias)
         t["u1"] = ops.wpack(WPACK_CONVT_FWD, dec[k].weight, 128, 256, 4, 4, out=t.get("u1"))
         t["u1_d"] = ops.wpack(WPACK_CONVT_DGRAD, dec[k].weight, 128, 256, 4, 4, out=t.get("u1_d"))
         t["u2"] = ops.wpack(WPACK_CONVT_FWD, dec[k + 3].weight, 64, 128, 4, 4, out=t.get("u2"))
@@ -490,7 +500,7 @@ class MultiDomainStyleEncoder(_Net):
         for kx, br in enumerate(self.domain_branches):
             ops.wpack(WPACK_FWD, br[0].weight, sd, 512, 1, 1, out=t["h"], oc=nd * sd, o_off=kx * sd)
             ops.wpack(WPACK_DGRAD_S1, br[0].weight, sd, 512, 1, 1, out=t["h_d"], oc=nd * sd, o_off=kx * sd)
-            t["h_b"][kx * sd:(kx + 1) * sd].copy_(br[0].bias)
+            ops.copy_f32(t["h_b"][kx * sd:(kx + 1) * sd], br[0].bias)
 
     def forward(self, img, domain_idx=None):
         return _StyleEncoderFn.apply(self, img, domain_idx, *self.parameters())
@@ -615,7 +625,7 @@ class MultiDomainDiscriminator(_Net):
         for kx, br in enumerate(self.domain_branches):
             ops.wpack(WPACK_FWD, br[1].weight, 1, 512, 4, 4, out=t["h"], oc=nd, o_off=kx)
             ops.wpack(WPACK_IM2COL_FLIP, br[1].weight, 1, 512, 4, 4, out=t["h_d"], oc=nd, o_off=kx)
-            t["h_b"][kx:kx + 1].copy_(br[1].bias)
+            ops.copy_f32(t["h_b"][kx:kx + 1], br[1].bias)
 
     def _dead_biases(self):
         c = self._convs()

@@ -93,6 +93,9 @@ def pad_rows(k):
     return 16 if k <= 16 else (k + 63) // 64 * 64
 
 
+_pack_recorder = None     # list of jobs while a network's packs are being recorded (see record_packs)
+
+
 def wpack(kind, w, o, i, r, s, out=None, oc=0, o_off=0):
     """Pack an fp32 master weight (reference layout) into the bf16 matrix the kernels read."""
     d = WpackDesc(kind, o, i, r, s)
@@ -100,7 +103,54 @@ def wpack(kind, w, o, i, r, s, out=None, oc=0, o_off=0):
         n = L.load().msig_wpack_part_elems(ctypes.byref(d), oc)
         out = torch.zeros(n, dtype=BF16, device=w.device)
     L.call("msig_wpack_part", ctypes.byref(d), oc, o_off, _p(w), _p(out), _stream())
+    if _pack_recorder is not None:
+        _pack_recorder.append((d, oc, o_off, w, out, 0))
     return out
+
+
+def copy_f32(dst, src):
+    """dst.copy_(src) for fp32 device tensors that belong to a network's packed-weight set (bias tables)."""
+    dst.copy_(src)
+    if _pack_recorder is not None:
+        _pack_recorder.append((WpackDesc(-1, 0, 0, 0, 0), 0, 0, src, dst, src.numel()))
+
+
+class record_packs:
+    """Context manager: every wpack / copy_f32 inside is executed AND recorded as a job, so that the whole
+    set can afterwards be refreshed with one launch (PackTable.run)."""
+
+    def __enter__(self):
+        global _pack_recorder
+        self.jobs = []
+        _pack_recorder = self.jobs
+        return self.jobs
+
+    def __exit__(self, *exc):
+        global _pack_recorder
+        _pack_recorder = None
+        return False
+
+
+class PackTable:
+    """Device-resident job table of one network's packs (msig_wpack_table_build / msig_wpack_multi)."""
+
+    def __init__(self, jobs, device):
+        n = len(jobs)
+        arr = (L.WpackJob * n)()
+        self.keep = []
+        for k, (d, oc, o_off, w, out, numel) in enumerate(jobs):
+            if not w.is_contiguous():
+                raise RuntimeError("packed-weight sources must be contiguous master tensors")
+            arr[k] = L.WpackJob(d, oc, o_off, w.data_ptr(), out.data_ptr(), numel)
+            self.keep.append((w, out))
+        host = torch.empty(int(L.load().msig_wpack_table_bytes(n)), dtype=torch.uint8)
+        total = ctypes.c_int64(0)
+        L.call("msig_wpack_table_build", arr, n, ctypes.c_void_p(host.data_ptr()), ctypes.byref(total))
+        self.table = host.to(device)
+        self.n, self.total = n, int(total.value)
+
+    def run(self):
+        L.call("msig_wpack_multi", _p(self.table), self.n, self.total, _stream())
 
 
 # ------------------------------------------------------------------ convolutions

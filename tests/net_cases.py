@@ -306,6 +306,33 @@ def case_graph_vs_eager(b=2, s=64, nd=3, steps=3, seed=0):
     return res, ok
 
 
+def case_translate_graph(b=3, s=64, nd=4, seed=0):
+    """inference.translate: the CUDA-graph replay (calls 2..n) against eager calls, before and after a
+    weight update (the packed weights are refreshed in place, outside the graph)."""
+    from msig_b200 import inference as I
+    torch.manual_seed(seed)
+    G = M.StyleCycleGANGenerator().to(DEV).eval()
+    SE = M.MultiDomainStyleEncoder(num_domains=nd).to(DEV).eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    res, ok = {}, True
+    for rnd in range(2):
+        for it in range(3):
+            src = torch.rand(b, 3, s, s, generator=g) * 2 - 1
+            ref = torch.rand(b, 3, s, s, generator=g) * 2 - 1
+            dom = torch.randint(0, nd, (b,), generator=g)
+            y_ref = I.translate(G, SE, src.to(DEV), ref.to(DEV), dom.to(DEV), use_cuda_graph=False).clone()
+            y = I.translate(G, SE, src, ref, dom).clone()          # host tensors in: copied into the static inputs
+            torch.cuda.synchronize()
+            e = rel(y.cpu(), y_ref.cpu())
+            res[f"r{rnd}.c{it}"] = e
+            ok = ok and e <= 1e-6
+        with torch.no_grad():                                       # "optimizer step": the graph must see it
+            for p in list(G.parameters()) + list(SE.parameters()):
+                p.mul_(1.05)
+    ok = ok and any(isinstance(v, dict) for v in I._translate_graphs.values())
+    return res, ok
+
+
 CASES = {
     "adain_module": case_adain_module,
     "generator_b2_s64": lambda: case_generator(2, 64),
@@ -317,4 +344,5 @@ CASES = {
     "vgg_loss": lambda: case_vgg(2, 64),
     "train_step_b2_s64": lambda: case_train_step(2, 64, 3, 2),
     "train_step_graph_vs_eager": case_graph_vs_eager,
+    "translate_graph_vs_eager": case_translate_graph,
 }
