@@ -152,6 +152,40 @@ def time_dominant_kernel(torch, ops, L, batch, iters=20):
     return ms, flops
 
 
+def time_hbm_kernel(torch, ops, L, batch, iters=20):
+    """The dominant HBM-bound kernel: fused norm-apply + ReLU (norm_act_fwd_kernel) on the residual-block
+    activation [B,64,64,256] bf16: 1 read + 1 write per element, L2 flushed, CUDA events."""
+    dev = torch.device("cuda")
+    x = torch.randn(batch, 64, 64, 256, device=dev).to(torch.bfloat16)
+    y = torch.empty_like(x)
+    st = ops.in_stats(x)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    for _ in range(3):
+        ops.norm_act_fwd(x, st, L.ACT_RELU, out=y)
+    total = 0.0
+    for _ in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.norm_act_fwd(x, st, L.ACT_RELU, out=y)
+        e1.record()
+        e1.synchronize()
+        total += e0.elapsed_time(e1)
+    ms = total / iters
+    return ms, 2.0 * x.numel() * 2
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
+    (profiles/ncu_fprop_r1.txt, first line = plain forward launch)."""
+    try:
+        line = open(os.path.join(ROOT, "profiles", "ncu_fprop_r1.txt")).readline()
+        kv = dict(t.split("=") for t in line.split() if "=" in t)
+        return (float(kv["dram_read_MB"]) + float(kv["dram_write_MB"])) * 1e6
+    except Exception:
+        return None
+
+
 def time_inference(torch, T, O, dev, tr, batch=16, iters=10):
     """BASELINE.json configs[1]: style injection, src+ref 256x256 batch 16, style encoder + generator
     forward only (inference.py:119,290). Device-timed with resident inputs, and end to end through
@@ -257,6 +291,8 @@ def run_ours(args):
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     kms, kflops = time_dominant_kernel(torch, ops, L, B)
     ach = kflops / (kms * 1e-3) / 1e12
+    hms, hbytes = time_hbm_kernel(torch, ops, L, B)
+    hach = hbytes / (hms * 1e-3) / 1e9
     step_tf = step_flops(B) / (ms / args.steps * 1e-3) / 1e12
     line = {
         "metric": "train images/sec at 256^2", "value": value, "unit": "images/sec", "n_gpus": world,
@@ -264,13 +300,22 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "image": S, "num_domains": ND,
                    "parallelism": f"dp{world}", "l2": "working set >> L2 (tens of GB of activations per step)",
-                   "accumulate": "fp32", "loss_epoch": 0},
+                   "accumulate": "fp32", "loss_epoch": 0,
+                   "cuda_graph": "step replayed from 4 captured graph segments (warm-up steps include the capture)"},
         "e2e": {"value": e2e, "unit": "images/sec", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
         "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": ach / pk["bf16_burst"],
-                     "traffic": None, "kernel": "fprop_kernel<256> conv3x3 256->256 @64x64, batch %d" % B,
-                     "kernel_ms": kms, "peak_source": pk["source"] + " (burst, kernel timed alone, L2 flushed)"},
+                     "traffic": ncu_traffic(),
+                     "kernel": "fprop2_kernel (tcgen05 cta_group::2 implicit GEMM) conv3x3 256->256 @64x64, batch %d" % B,
+                     "kernel_ms": kms, "algorithmic_flops_per_launch": kflops,
+                     "algorithmic_bytes_per_launch": 2.0 * (2 * B * 4096 * 256 + 256 * 2304),
+                     "traffic_note": "dram__bytes_read+write of one launch (ncu --set full, profiles/ncu_fprop_r1.txt); "
+                                     "below the algorithmic bytes because most of the output is still in L2 when the kernel ends",
+                     "peak_source": pk["source"] + " (burst, kernel timed alone, L2 flushed)"},
+        "roofline_hbm": {"bound": "hbm", "achieved": hach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hach / pk["hbm_gbs"],
+                         "kernel": "norm_act_fwd_kernel (IN/AdaIN apply + ReLU) [%d,64,64,256] bf16, 1R+1W" % B,
+                         "kernel_ms": hms, "algorithmic_bytes_per_launch": hbytes, "peak_source": pk["source"]},
         "step_tflops": {"achieved": step_tf, "peak_sustained": pk["bf16_sustained"], "frac": step_tf / pk["bf16_sustained"],
                         "flops_per_step": step_flops(B), "note": "necessary algorithmic FLOPs (SURVEY 8d) / step time"},
     }
