@@ -38,6 +38,7 @@ int msig_version(void);
 const char* msig_last_error(void);       /* thread-local */
 int msig_sm_count(void);
 int msig_debug_set_strip_mode(int mode);  /* test hook: 0 = per-tap kernel, 1 = strip kernel (default) for the 7x7 64->3 conv */
+int msig_debug_set_ring_mode(int on);     /* test hook: strip-ring kernel for 64-channel stride-1 layers, default on */
 int msig_debug_set_pair_mode(int on);     /* test hook: CTA-pair (tcgen05 cta_group::2) kernel for 256-wide conv tiles, default on */
 long long msig_kernel_launches(void);    /* kernels launched by this library since load */
 

@@ -336,6 +336,23 @@ static int fill_epilogue(FpropParams& p, const msig_epilogue* e, const OutView& 
   return MSIG_OK;
 }
 
+static int g_ring_mode = 1;    // test hook: 0 = generic per-tap kernel for the 64-channel stride-1 layers
+
+// Configure `p` (epilogue already filled, n_img / OH / OW set) for the N = 64 ring kernel.
+static void set_ring(FpropParams& p, int R, int S, int org_h, int org_w) {
+  p.TW = 128; p.TH = 1;
+  p.tiles_h = p.OH;
+  p.tiles_w = static_cast<int>(ceil_div(p.OW, 128));
+  p.n_blocks = 1;
+  p.strip_r = R; p.strip_s = S;
+  p.org_h = org_h; p.org_w = org_w;
+  const int sms = sm_count() > 0 ? sm_count() : 148;
+  int rows = 64;
+  while (rows > 8 && int64_t(p.n_img) * p.tiles_w * ceil_div(p.OH, rows) < int64_t(6) * sms) rows /= 2;
+  p.ring_rows = rows;
+  p.ring_chunks = static_cast<int>(ceil_div(p.OH, rows));
+}
+
 static void init_fprop(FpropParams& p) {
   memset(&p, 0, sizeof(p));
   p.phases = 1;
@@ -388,6 +405,16 @@ static int run_conv(const void* in, int n, int h, int w, int c, int k, int R, in
     return rc;
   const OutView ov = make_out_view(out, e ? e->out_layout : MSIG_OUT_BF16_NHWC, OH, OW, k);
   if ((rc = fill_epilogue(p, e, ov, k)) != MSIG_OK) return rc;
+  // 64 -> <=64 channel stride-1 layers on wide planes (VGG conv 1_2 fwd / dgrad): resident filter + strip ring.
+  if (g_ring_mode != 0 && stride == 1 && c == 64 && block_n == 64 && k_pad == 64 && R * S >= 2 && R * S <= 9 && R <= 7 &&
+      S <= 8 && OW >= 128) {
+    set_ring(p, R, S, -pad_t, -pad_l);
+    ActView v{in, c, w, h, n, c, int64_t(w) * c, int64_t(h) * w * c};
+    if ((rc = make_act_map(&p.tmA[1], v, 128 + S - 1, 1)) != MSIG_OK) return rc;
+    cudaError_t ce = launch_fprop_ring64(p, sm_count(), st);
+    if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "fprop(ring) launch: %s", cudaGetErrorString(ce));
+    return MSIG_OK;
+  }
   // Narrow-output "valid" stride-1 conv on 64 channels (the generator's final 7x7 conv on the
   // pre-padded activation): resident filter + one strip per filter row instead of one tile per tap.
   if (g_strip_mode != 0 && stride == 1 && pad_t == 0 && pad_l == 0 && c == 64 && block_n == 16 && R * S <= 49 &&
@@ -503,6 +530,12 @@ int32_t msig_epilogue_stats_rows(int32_t oh, int32_t ow, int32_t phases) {
   int TW, TH;
   pick_tile(ow, TW, TH);
   return static_cast<int32_t>(ceil_div(oh, TH) * ceil_div(ow, TW) * phases * 4);
+}
+
+// Test hook: ring kernel for the 64-channel stride-1 layers on (default) / off.
+int msig_debug_set_ring_mode(int on) {
+  g_ring_mode = on;
+  return MSIG_OK;
 }
 
 // Test hook: CTA-pair (cta_group::2) kernel for 256-wide tiles on (default) / off.
@@ -654,6 +687,14 @@ int msig_conv_rowpatch_fwd(const msig_conv_geom* g, const void* x_pad8, const vo
     return rc;
   const OutView ov = make_out_view(y, e ? e->out_layout : MSIG_OUT_BF16_NHWC, g->oh, g->ow, g->k);
   if ((rc = fill_epilogue(p, e, ov, g->k)) != MSIG_OK) return rc;
+  if (g_ring_mode != 0 && k_pad == 64 && g->r <= 7 && g->ow >= 128) {
+    // resident filter + one overlapped-window strip per padded image row, shared by R output rows
+    set_ring(p, g->r, 1, 0, 0);
+    if ((rc = make_act_map(&p.tmA[1], pad8_view(x_pad8, g), 128, 1)) != MSIG_OK) return rc;
+    cudaError_t ce = launch_fprop_ring64(p, sm_count(), static_cast<cudaStream_t>(stream));
+    if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "fprop(rowpatch ring) launch: %s", cudaGetErrorString(ce));
+    return MSIG_OK;
+  }
   cudaError_t ce = launch_fprop(p, block_n, sm_count(), static_cast<cudaStream_t>(stream));
   if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "fprop(rowpatch) launch: %s", cudaGetErrorString(ce));
   return MSIG_OK;

@@ -894,6 +894,164 @@ __global__ void __launch_bounds__(256, 1) fprop_rowfold_kernel(const __grid_cons
   }
 }
 
+// ------------------------------------------------------------------------------------ ring (N = 64)
+// Stride-1 R x S convolution with 64 input and <= 64 output channels (VGG conv 1_2 fwd / dgrad,
+// losses.py:15) and the row-patch 7x7 convs (R = 7 overlapped-window rows, S = 1). The generic kernel
+// re-fetches the A tile once per filter tap and the weight tile once per K block, and at N = 64 that
+// traffic (24 KiB per 2 MF) pins it to the L2 -> shared-memory roof at ~25 % tensor-pipe activity. Here
+//   * the whole packed filter (R*S x [64][64] bf16) stays resident in shared memory,
+//   * one TMA strip of 128 + S - 1 pixels per INPUT row lives in an 8-slot ring: the S horizontal taps
+//     are MMAs whose A descriptors start s rows into the strip, and the R - 1 strips shared with the
+//     next output row are re-used instead of re-loaded (work item = a column of consecutive output rows).
+// L2 traffic per 128-pixel tile drops from R*S*24 KiB to ~17 KiB. Epilogue = the generic one (BLOCK_N = 64).
+constexpr int kRingSlots = 8;
+constexpr int kRingSlotBytes = 17408;              // (128 + 8) rows x 128 B
+constexpr int kRingMaxTaps = 9;
+constexpr int kRingWBytes = 64 * 128;              // one tap: 64 output channels x 64 K
+constexpr int kRingSmemBytes = kRingMaxTaps * kRingWBytes + kRingSlots * kRingSlotBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __grid_constant__ FpropParams p) {
+  constexpr int BLOCK_N = 64;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint8_t* wsm = smem;                                             // taps x 8 KiB
+  uint8_t* ring = smem + kRingMaxTaps * kRingWBytes;               // 72 KiB: 1024-aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + kRingSlots * kRingSlotBytes);
+  uint64_t* empty_bar = full_bar + kRingSlots;
+  uint64_t* tfull_bar = empty_bar + kRingSlots;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint64_t* wfull_bar = tempty_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int R = p.strip_r, S = p.strip_s;
+  const uint32_t strip_tx = static_cast<uint32_t>(kTileM + S - 1) * 128u;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&p.tmA[1]);
+    prefetch_tmap(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kRingSlots; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 256);
+    }
+    mbar_init(wfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 2 * BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int items = p.n_img * p.tiles_w * p.ring_chunks;
+
+  auto decode = [&](int item, int& img, int& tw, int& h0, int& nrows) {
+    const int ch = item % p.ring_chunks;
+    const int rest = item / p.ring_chunks;
+    tw = rest % p.tiles_w;
+    img = rest / p.tiles_w;
+    h0 = ch * p.ring_rows;
+    nrows = min(p.ring_rows, p.OH - h0);
+  };
+
+  if (warp == 0) {
+    if (elect_one()) {
+      mbar_expect_tx(wfull_bar, static_cast<uint32_t>(R * S) * kRingWBytes);
+      for (int t = 0; t < R * S; ++t) tma_load_2d(wsm + t * kRingWBytes, &p.tmB, wfull_bar, t * kBlockK, 0);
+    }
+    __syncwarp();
+    uint32_t g = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int img, tw, h0, nrows;
+      decode(item, img, tw, h0, nrows);
+      const int x0 = p.org_w + tw * kTileM;
+      const int y0 = p.org_h + h0;
+      const int nstrips = nrows + R - 1;
+      for (int j = 0; j < nstrips; ++j, ++g) {
+        const uint32_t slot = g % kRingSlots;
+        mbar_wait(&empty_bar[slot], ((g / kRingSlots) & 1u) ^ 1u);
+        if (elect_one()) {
+          mbar_expect_tx(&full_bar[slot], strip_tx);
+          tma_load_4d(ring + slot * kRingSlotBytes, &p.tmA[1], &full_bar[slot], 0, x0, y0 + j, img);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
+    mbar_wait(wfull_bar, 0);
+    const uint32_t w_addr = smem_u32(wsm);
+    const uint32_t ring_addr = smem_u32(ring);
+    uint32_t g0 = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int img, tw, h0, nrows;
+      decode(item, img, tw, h0, nrows);
+      for (int i = 0; i < nrows; ++i, ++it) {
+        const int as = it & 1;
+        mbar_wait(&tempty_bar[as], (((it >> 1) & 1) ^ 1u));
+        for (int r = (i == 0 ? 0 : R - 1); r < R; ++r) {
+          const uint32_t g = g0 + i + r;
+          mbar_wait(&full_bar[g % kRingSlots], (g / kRingSlots) & 1u);
+        }
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t d_tmem = tmem_base + as * BLOCK_N;
+          for (int r = 0; r < R; ++r) {
+            const uint32_t g = g0 + i + r;
+            const uint32_t sa = ring_addr + (g % kRingSlots) * kRingSlotBytes;
+            for (int s = 0; s < S; ++s) {
+              const uint64_t da = make_smem_desc(sa + s * 128, 0, 1024);      // s pixels into the strip
+              const uint64_t db = make_smem_desc(w_addr + (r * S + s) * kRingWBytes, 0, 1024);
+#pragma unroll
+              for (int k = 0; k < kBlockK / 16; ++k)
+                umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (r > 0 || s > 0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty_bar[(g0 + i) % kRingSlots]);
+          if (i == nrows - 1)
+            for (int r = 1; r < R; ++r) umma_commit(&empty_bar[(g0 + i + r) % kRingSlots]);
+          umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+      }
+      g0 += nrows + R - 1;
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int c_begin = half * (BLOCK_N / 2), c_end = c_begin + BLOCK_N / 2;
+    const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
+    int it = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      int img, tw, h0, nrows;
+      decode(item, img, tw, h0, nrows);
+      for (int i = 0; i < nrows; ++i, ++it) {
+        const int as = it & 1;
+        // m-tile index in the generic numbering (TH = 1, TW = 128): (img, oh, tw)
+        const int mt = (img * p.tiles_h + (h0 + i)) * p.tiles_w + tw;
+        fprop_epilogue_tile<BLOCK_N>(p, mt, 0, tmem_base, as, (it >> 1) & 1, tfull_bar, q, lane, c_begin, c_end, alpha);
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BLOCK_N);
+  }
+}
+
 // ------------------------------------------------------------------------------------ wgrad
 template <int BLOCK_N>
 struct WgradCfg {
@@ -1183,6 +1341,25 @@ cudaError_t launch_rowfold(const RowfoldParams& p, int num_sms, cudaStream_t str
   const int grid = items < num_sms ? items : num_sms;
   if (grid <= 0) return cudaSuccess;
   fprop_rowfold_kernel<<<grid, 256, kRfSmemBytes, stream>>>(p);
+  count_launch(1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fprop_ring64(const FpropParams& p, int num_sms, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(fprop_ring64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kRingSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  if (p.strip_r < 1 || p.strip_s < 1 || p.strip_r * p.strip_s > kRingMaxTaps || p.strip_r + 1 > kRingSlots ||
+      (kTileM + p.strip_s - 1) * 128 > kRingSlotBytes || p.TW != kTileM || p.TH != 1 || p.phases != 1 || p.n_blocks != 1)
+    return cudaErrorInvalidValue;
+  const int items = p.n_img * p.tiles_w * p.ring_chunks;
+  const int grid = items < num_sms ? items : num_sms;
+  if (grid <= 0) return cudaSuccess;
+  fprop_ring64_kernel<<<grid, kFpropThreads, kRingSmemBytes, stream>>>(p);
   count_launch(1);
   return cudaGetLastError();
 }

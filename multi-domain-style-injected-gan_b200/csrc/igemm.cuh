@@ -38,7 +38,9 @@ struct FpropParams {
   int32_t b_row_per_image;        // B row offset added per output image (Gram backward)
   int32_t fold_c;                 // >0: GEMM columns are (image, channel) pairs, fold_c channels per image;
                                   //     column j is stored to image j / fold_c (Gram backward with N spanning images)
-  int32_t strip_r, strip_s;       // strip kernel: filter extent; tmA[1] has a (128 + strip_s - 1)-pixel box
+  int32_t strip_r, strip_s;       // strip / ring kernels: filter extent; tmA[1] has a (128 + strip_s - 1)-pixel box
+  int32_t ring_rows, ring_chunks; // ring kernel: output rows per work item, items per image column
+  int32_t org_h, org_w;           // ring kernel: input coordinate read by output (0,0) through tap (0,0)
   int32_t OH, OW, TH, TW;         // output plane and the 128-pixel tile (TH*TW == 128)
   int32_t tiles_h, tiles_w, n_img, n_blocks;
   // epilogue
@@ -114,6 +116,7 @@ struct RowfoldParams {
 
 cudaError_t launch_fprop(const FpropParams& p, int block_n, int num_sms, cudaStream_t stream);
 cudaError_t launch_rowfold(const RowfoldParams& p, int num_sms, cudaStream_t stream);
+cudaError_t launch_fprop_ring64(const FpropParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_wgrad(const WgradParams& p, int block_n, cudaStream_t stream);
 cudaError_t launch_fprop_strip16(const FpropParams& p, int num_sms, cudaStream_t stream);
 bool fprop_uses_pairs(const FpropParams& p, int block_n);

@@ -55,6 +55,7 @@ _SIGS = {
     "msig_sm_count": (c_int, []),
     "msig_debug_set_strip_mode": (c_int, [c_int]),
     "msig_debug_set_pair_mode": (c_int, [c_int]),
+    "msig_debug_set_ring_mode": (c_int, [c_int]),
     "msig_kernel_launches": (c_longlong, []),
     "msig_wpack_elems": (c_size_t, [POINTER(WpackDesc)]),
     "msig_wpack": (c_int, [POINTER(WpackDesc), _P, _P, _P]),

@@ -256,6 +256,9 @@ CASES = {
     "fwd_3x3_64_32_relu": lambda: case_conv_fwd(1, 64, 32, 32, 64, 3, 1, 1, act=L.ACT_RELU),
     "fwd_3x3_128_128w": lambda: case_conv_fwd(1, 64, 128, 128, 128, 3, 1, 1),
     "fwd_3x3_64_256w": lambda: case_conv_fwd(1, 64, 16, 256, 64, 3, 1, 1),
+    "ring_fwd_3x3_64_ragged": lambda: case_conv_fwd(3, 64, 40, 200, 64, 3, 1, 1, act=L.ACT_RELU),
+    "ring_fwd_3x3_64_tall": lambda: case_conv_fwd(2, 64, 300, 128, 64, 3, 1, 1),
+    "ring_dgrad_3x3_64_256w": lambda: case_conv_dgrad(2, 64, 48, 256, 64, 3, 1, 1),
     "fwd_4x4s2_64_128": lambda: case_conv_fwd(2, 64, 64, 64, 128, 4, 2, 1, act=L.ACT_LRELU),
     "fwd_4x4s2_256_512": lambda: case_conv_fwd(2, 256, 32, 32, 512, 4, 2, 1),
     "final7x7_pertap": lambda: case_final_conv(2, 64, 256, 0),
