@@ -1,0 +1,130 @@
+"""Parity at BASELINE.json's full sizes (256x256 batch 32; 512x512) through size-independent properties
+— the CPU oracle would need minutes per case there — plus one 512x512 forward against the oracle at
+batch 1. Properties (each compares two CUDA computations that must agree, or an invariant of the op):
+
+  * batch independence: InstanceNorm / AdaIN statistics are per sample (model.py:16), so image i of a
+    batch-32 generator pass must equal the batch-1 pass of image i (different tile schedules, CTA pairs
+    and statistics partitions, same arithmetic per pixel);
+  * normalisation invariant: after the fused statistics + apply kernels every (n, c) plane has mean 0 and
+    variance 1 (biased, eps = 1e-5) at the residual-block size [32, 256, 64, 64];
+  * linearity of the implicit GEMM at the dominant shape: conv(x1 + x2) = conv(x1) + conv(x2) for
+    operands exactly representable in bf16 (fp32 accumulation: equal up to the output rounding);
+  * shard property of train_step (data parallel): the sum-reduced gradients of two half batches, scaled
+    by 1/2, equal the full-batch gradients for every loss term that is a per-sample mean — checked on the
+    discriminator phase (the VGG style term is deliberately batch-coupled).
+"""
+import torch
+
+import msig_b200  # noqa: F401
+from msig_b200 import lib as L
+from msig_b200 import model as M
+from msig_b200 import ops
+from oracle import oracle as O
+
+DEV = "cuda"
+
+
+def _rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def case_batch_independence(b=32, s=256, seed=0):
+    torch.manual_seed(seed)
+    G = M.StyleCycleGANGenerator().to(DEV).eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    x = (torch.rand(b, 3, s, s, generator=g) * 2 - 1).to(DEV)
+    sty = torch.randn(b, 256, generator=g).to(DEV)
+    with torch.no_grad():
+        y = G(x, sty).clone()
+        worst = 0.0
+        for i in (0, b // 2, b - 1):
+            yi = G(x[i:i + 1].contiguous(), sty[i:i + 1].contiguous())
+            worst = max(worst, _rel(yi[0], y[i]))
+    torch.cuda.synchronize()
+    # same per-pixel arithmetic; only the order of the fp32 partial sums of the statistics changes
+    return {"max_rel": worst, "finite": bool(torch.isfinite(y).all()), "range": float(y.abs().max())}, \
+        worst <= 1e-3 and bool(torch.isfinite(y).all()) and float(y.abs().max()) <= 1.0
+
+
+def case_norm_invariant(n=32, h=64, c=256, seed=0):
+    ops.ensure_init()
+    g = torch.Generator().manual_seed(seed)
+    x = (torch.randn(n, h, h, c, generator=g) * 3 + 0.7).to(DEV).to(torch.bfloat16)
+    st = ops.in_stats(x)
+    y = ops.norm_act_fwd(x, st, L.ACT_NONE).float()
+    mean = y.mean(dim=(1, 2))
+    var = y.var(dim=(1, 2), unbiased=False)
+    torch.cuda.synchronize()
+    em, ev = float(mean.abs().max()), float((var - 1).abs().max())
+    return {"max|mean|": em, "max|var-1|": ev}, em <= 5e-3 and ev <= 2e-2     # bf16 output rounding: 2^-9 relative
+
+
+def case_conv_linearity(n=32, h=64, c=256, k=256, seed=0):
+    ops.ensure_init()
+    g = torch.Generator().manual_seed(seed)
+    # small integers / 8: sums of two operands stay exactly representable in bf16
+    x1 = (torch.randint(-8, 9, (n, h, h, c), generator=g).float() / 8).to(DEV).to(torch.bfloat16)
+    x2 = (torch.randint(-8, 9, (n, h, h, c), generator=g).float() / 8).to(DEV).to(torch.bfloat16)
+    w = (torch.randint(-4, 5, (k, c, 3, 3), generator=g).float() / 64).to(DEV)
+    wpk = ops.wpack(L.WPACK_FWD, w, k, c, 3, 3)
+    geo = ops.conv_geom(n, h, h, c, k, 3, 3, 1, 1, 1, h, h)
+    e = ops.epilogue(out_layout=L.OUT_F32_NHWC)
+    y12 = ops.conv2d_fwd(x1 + x2, wpk, geo, e)
+    y1 = ops.conv2d_fwd(x1, wpk, geo, e)
+    y2 = ops.conv2d_fwd(x2, wpk, geo, e)
+    torch.cuda.synchronize()
+    err = _rel(y12, y1 + y2)
+    return {"err": err}, err <= 1e-5          # all products and partial sums are exact multiples of 2^-9 < 2^24
+
+
+def case_shard_property(b=8, s=256, nd=10, seed=0):
+    """Discriminator: grads of the mean LSGAN loss over a batch = mean of the two half-batch grads."""
+    torch.manual_seed(seed)
+    D = M.MultiDomainDiscriminator(num_domains=nd).to(DEV)
+    g = torch.Generator().manual_seed(seed + 1)
+    x = (torch.rand(b, 3, s, s, generator=g) * 2 - 1).to(DEV)
+    idx = (torch.arange(b) % nd).to(DEV)
+
+    def grads(xs, ids):
+        for p in D.parameters():
+            p.grad = None
+        ((D(xs, ids) - 1.0) ** 2).mean().backward()
+        return [p.grad.detach().clone() for p in D.parameters()]
+
+    full = grads(x, idx)
+    h0 = grads(x[:b // 2].contiguous(), idx[:b // 2].contiguous())
+    h1 = grads(x[b // 2:].contiguous(), idx[b // 2:].contiguous())
+    torch.cuda.synchronize()
+    dead = set(id(p) for p in D._dead_biases())
+    worst = 0.0
+    for p, f, a, c in zip(D.parameters(), full, h0, h1):
+        if id(p) in dead or float(f.abs().max()) == 0.0:
+            continue
+        worst = max(worst, _rel((a + c) / 2, f))
+    return {"max_rel": worst}, worst <= 1e-3
+
+
+def case_generator_512(seed=0):
+    """512x512 (BASELINE.json configs[4]) generator forward, batch 1, against the CPU oracle."""
+    torch.manual_seed(seed)
+    G = M.StyleCycleGANGenerator().to(DEV).eval()
+    sd = {k: v.detach().float().cpu().clone() for k, v in G.state_dict().items()}
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.rand(1, 3, 512, 512, generator=g) * 2 - 1
+    sty = torch.randn(1, 256, generator=g)
+    with torch.no_grad():
+        ref = O.generator_forward(sd, x, sty)
+        y = G(x.to(DEV), sty.to(DEV))
+    torch.cuda.synchronize()
+    e = _rel(y.cpu(), ref)
+    return {"out": e}, e <= 4e-2
+
+
+CASES = {
+    "full_batch_independence_b32_256": case_batch_independence,
+    "full_norm_invariant_b32": case_norm_invariant,
+    "full_conv_linearity_b32": case_conv_linearity,
+    "full_shard_property_d_256": case_shard_property,
+    "generator_512_vs_oracle": case_generator_512,
+}

@@ -42,9 +42,11 @@ def all_cases():
     import igemm_cases
     import ops_cases
     import net_cases
+    import fullsize_cases
     d = dict(igemm_cases.CASES)
     d.update(ops_cases.CASES)
     d.update(net_cases.CASES)
+    d.update(fullsize_cases.CASES)
     return d
 
 
