@@ -834,11 +834,17 @@ static size_t wgrad_ws_bytes(int M, int N, int taps, int64_t kb_total) {
   return size_t(pl.splits) * size_t(M) * taps * N * sizeof(float);
 }
 
+// 64-input-channel convs (model.py:132 and the second layer of the SE / D trunks): dy is the 128-wide M
+// operand and FOUR filter taps share one CTA as four 64-channel B boxes (N = 256), so the dy tile is
+// fetched once per four taps instead of once per tap (these layers sit on the L2 -> shared-memory roof).
+static bool wgrad_groups_taps(const msig_conv_geom* g) { return g->c == 64 && (g->r * g->s) % 4 == 0; }
+
 size_t msig_conv2d_wgrad_workspace(const msig_conv_geom* g) {
   if (!g) return 0;
   int PW, PH;
   pick_kblock(g->ow, PW, PH);
   const int64_t kb = int64_t(g->n) * ceil_div(g->oh, PH) * ceil_div(g->ow, PW);
+  if (wgrad_groups_taps(g)) return wgrad_ws_bytes(g->k, 256, g->r * g->s / 4, kb);
   const bool swap = g->c >= 128;
   return wgrad_ws_bytes(swap ? g->c : g->k, swap ? g->k : g->c, g->r * g->s, kb);
 }
@@ -856,22 +862,26 @@ int msig_conv2d_wgrad(const msig_conv_geom* g, const void* x, const void* dy, fl
   p.blocks_w = static_cast<int>(ceil_div(g->ow, p.PW));
   p.blocks_h = static_cast<int>(ceil_div(g->oh, p.PH));
   p.n_img = g->n;
-  p.taps = g->r * g->s;
+  const int taps = g->r * g->s;
+  const bool group = wgrad_groups_taps(g);
+  p.taps = group ? taps / 4 : taps;
   const int64_t kb_total = int64_t(g->n) * p.blocks_h * p.blocks_w;
   // Operand roles. All CTAs of one pixel range read the SAME dy tile (L2 serves it once) but a
   // different shifted x window per tap, so the per-CTA-unique operand should be the 128-wide M side:
   // with >= 128 input channels x is the M operand (partials come out [ci][tap-major][co]).
-  const bool swap = g->c >= 128;
-  const int M = swap ? g->c : g->k, N = swap ? g->k : g->c;
+  const bool swap = !group && g->c >= 128;
+  const int M = swap ? g->c : g->k, N = group ? 256 : (swap ? g->k : g->c);
   WgradPlan pl = plan_wgrad(M, N, p.taps, kb_total);
-  const size_t need = size_t(pl.splits) * size_t(g->k) * p.taps * g->c * sizeof(float);
+  const size_t need = size_t(pl.splits) * size_t(g->k) * taps * g->c * sizeof(float);
   MSIG_REQUIRE(workspace_bytes >= need, "wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
   p.m_blocks = pl.m_blocks; p.n_blocks = pl.n_blocks; p.splits = pl.splits;
   p.kb_per_split = pl.kb_per_split; p.kb_total = pl.kb_total;
   p.out = reinterpret_cast<float*>(workspace);
-  p.o_row = int64_t(p.taps) * N; p.o_tap = N;
-  p.o_split = int64_t(g->k) * p.taps * g->c;
+  // partial layout [m][tap][n]: with grouped taps a CTA's 256 columns are 4 consecutive taps x 64 channels
+  p.o_row = int64_t(taps) * (group ? 64 : N); p.o_tap = N;
+  p.o_split = int64_t(g->k) * taps * g->c;
   p.alpha = 1.f; p.m_valid = M; p.n_valid = N;
+  p.b_box_tap = group ? 1 : 0;
   int rc;
   CUtensorMap* tm_dy = swap ? p.tmB : p.tmA;
   CUtensorMap* tm_x = swap ? p.tmA : p.tmB;
@@ -880,15 +890,14 @@ int msig_conv2d_wgrad(const msig_conv_geom* g, const void* x, const void* dy, fl
   ActView va{dy, g->k, g->ow, g->oh, g->n, g->k, int64_t(g->ow) * g->k, int64_t(g->oh) * g->ow * g->k};
   if ((rc = make_act_map(&tm_dy[0], va, p.PW, p.PH)) != MSIG_OK) return rc;
   for (int i = 1; i < 4; ++i) tm_dy[i] = tm_dy[0];
+  for (int t = 0; t < taps; ++t) tap_dy[t] = Tap{0, 0, 0, 0};
   if (g->stride == 1) {
     ActView vb{x, g->c, g->w, g->h, g->n, g->c, int64_t(g->w) * g->c, int64_t(g->h) * g->w * g->c};
     if ((rc = make_act_map(&tm_x[0], vb, p.PW, p.PH)) != MSIG_OK) return rc;
     for (int i = 1; i < 4; ++i) tm_x[i] = tm_x[0];
     for (int r = 0; r < g->r; ++r)
-      for (int s = 0; s < g->s; ++s) {
-        tap_dy[r * g->s + s] = Tap{0, 0, 0, 0};
+      for (int s = 0; s < g->s; ++s)
         tap_x[r * g->s + s] = Tap{int8_t(r - g->pad_t), int8_t(s - g->pad_l), 0, 0};
-      }
   } else {
     MSIG_REQUIRE(g->stride == 2 && g->h % 2 == 0 && g->w % 2 == 0, "wgrad: stride-2 needs even dims");
     for (int ph = 0; ph < 2; ++ph)
@@ -903,7 +912,6 @@ int msig_conv2d_wgrad(const msig_conv_geom* g, const void* x, const void* dy, fl
       for (int s = 0; s < g->s; ++s) {
         const int rr = r - g->pad_t, ss = s - g->pad_l;
         const int ph = ((rr % 2) + 2) % 2, pw = ((ss % 2) + 2) % 2;
-        tap_dy[r * g->s + s] = Tap{0, 0, 0, 0};
         tap_x[r * g->s + s] = Tap{int8_t((rr - ph) / 2), int8_t((ss - pw) / 2), int8_t(ph * 2 + pw), 0};
       }
   }

@@ -243,7 +243,9 @@ def case_adam(seed=0):
         ops.sumsq(g, ss, accumulate=False)
         ops.adam_step(p, g, m, v, ema, ss, 1.0, 1.0, 2e-4, 0.5, 0.999, 1e-8, step, 0.995)
     torch.cuda.synchronize()
-    return max(rel_err(p, ref_p.data), rel_err(ema, ema_ref), ((p - ref_p.data).abs().max() / 2e-4).item() * 1e-2), 1e-5
+    # parameters ~N(0,1): one fp32 ulp at |p| ~ 4 is 4.8e-7, so the absolute bound is 1e-6 (0.5 % of one
+    # lr-sized update); the clip coefficient comes from an fp32-atomic sum whose last bits vary run to run
+    return max(rel_err(p, ref_p.data), rel_err(ema, ema_ref), ((p - ref_p.data).abs().max() / 2e-4).item() * 2e-3), 1e-5
 
 
 CASES = {
