@@ -69,15 +69,40 @@ __device__ __forceinline__ void prefetch_l2(const void* p) {
 // Loads the epilogue's global operands for NC columns of one output pixel: `av` = aux (residual /
 // activation mask source), `zv` = stat_z. Issued one chunk ahead of their use so their latency hides
 // behind the previous chunk (and, for the first chunk, behind the tile's main loop).
+// 32-byte read-only load: one full DRAM/L2 sector per thread per instruction. (With 16-byte loads a
+// warp touches 32 half-used sectors per instruction and relies on L1 to merge the two halves; with the
+// aux AND z streams in flight that merging breaks down and the L2 -> SM traffic of the epilogue doubles.)
+__device__ __forceinline__ void ldg256(const void* ptr, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w)
+               : "l"(ptr));
+}
+
+__device__ __forceinline__ void stg256(void* ptr, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(a.x), "r"(a.y), "r"(a.z),
+               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 template <int NC>
 __device__ __forceinline__ void epilogue_load(const FpropParams& p, int col0, bool row_valid, int64_t out_off,
                                               int64_t aux_off, uint4 (&av)[NC / 8], uint4 (&zv)[NC / 8]) {
 #pragma unroll
-  for (int g = 0; g < NC / 8; ++g) {
+  for (int g = 0; g < NC / 8; g += 2) {
     const int c = col0 + 8 * g;
-    const bool live = row_valid && (c + 8 <= p.n_valid);
-    if (live && p.aux_mode != AUX_NONE) av[g] = __ldg(reinterpret_cast<const uint4*>(p.aux + aux_off + c));
-    if (live && p.stat_z != nullptr) zv[g] = __ldg(reinterpret_cast<const uint4*>(p.stat_z + out_off + c));
+    if (row_valid && c + 16 <= p.n_valid) {          // column pairs are 32-byte aligned (channels % 16 == 0)
+      if (p.aux_mode != AUX_NONE) ldg256(p.aux + aux_off + c, av[g], av[g + 1]);
+      if (p.stat_z != nullptr) ldg256(p.stat_z + out_off + c, zv[g], zv[g + 1]);
+    } else {
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const bool live = row_valid && (c + 8 * h + 8 <= p.n_valid);
+        if (live && p.aux_mode != AUX_NONE)
+          av[g + h] = __ldg(reinterpret_cast<const uint4*>(p.aux + aux_off + c + 8 * h));
+        if (live && p.stat_z != nullptr)
+          zv[g + h] = __ldg(reinterpret_cast<const uint4*>(p.stat_z + out_off + c + 8 * h));
+      }
+    }
   }
 }
 
@@ -93,6 +118,7 @@ __device__ __forceinline__ void fprop_epilogue_chunk(const FpropParams& p, const
   if (!p.out_f32 && p.o_sc == 1) {
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
     float sv[STATS ? NC : 1], sq[STATS ? NC : 1];
+    uint4 o_even = make_uint4(0, 0, 0, 0);      // even group's packed output, stored with the odd one (32 bytes)
 #pragma unroll
     for (int g = 0; g < NC / 8; ++g) {
       const int c = col0 + 8 * g;
@@ -137,7 +163,13 @@ __device__ __forceinline__ void fprop_epilogue_chunk(const FpropParams& p, const
       o.y = pack_bf16x2(v[2], v[3]);
       o.z = pack_bf16x2(v[4], v[5]);
       o.w = pack_bf16x2(v[6], v[7]);
-      *reinterpret_cast<uint4*>(out + out_off + c) = o;
+      // one full 32-byte sector per store where the group pair is complete
+      if ((g & 1) == 0) {
+        if (c + 16 <= p.n_valid) o_even = o;
+        else *reinterpret_cast<uint4*>(out + out_off + c) = o;
+      } else {
+        stg256(out + out_off + c - 8, o_even, o);
+      }
       if (STATS) {
         // statistics of the values as stored (bf16-rounded): what the consumer will normalise
         const __nv_bfloat162* oh2 = reinterpret_cast<const __nv_bfloat162*>(&o);
@@ -1226,7 +1258,21 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
       }
       if (row_valid) {
         const int col0 = n_blk * BLOCK_N + c;
-        if (col0 + 32 <= p.n_valid && (p.o_row & 3) == 0) {
+        if (col0 + 32 <= p.n_valid && (p.o_row & 7) == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {        // one full 32-byte sector per store
+            uint4 a, b;
+            a.x = __float_as_uint(__uint_as_float(r[j]) * p.alpha);
+            a.y = __float_as_uint(__uint_as_float(r[j + 1]) * p.alpha);
+            a.z = __float_as_uint(__uint_as_float(r[j + 2]) * p.alpha);
+            a.w = __float_as_uint(__uint_as_float(r[j + 3]) * p.alpha);
+            b.x = __float_as_uint(__uint_as_float(r[j + 4]) * p.alpha);
+            b.y = __float_as_uint(__uint_as_float(r[j + 5]) * p.alpha);
+            b.z = __float_as_uint(__uint_as_float(r[j + 6]) * p.alpha);
+            b.w = __float_as_uint(__uint_as_float(r[j + 7]) * p.alpha);
+            stg256(orow + col0 + j, a, b);
+          }
+        } else if (col0 + 32 <= p.n_valid && (p.o_row & 3) == 0) {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 o;

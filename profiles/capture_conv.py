@@ -48,3 +48,25 @@ for _ in range(REPS):
     ops.conv2d_fwd(x, wpk, g, out=y)
 torch.cuda.synchronize()
 print("ok")
+
+if os.environ.get("TIME"):
+    # CUDA-event timing of the four residual-conv variants (L2 flushed between iterations)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    h, c, k = 64, 256, 256
+    x = torch.randn(B, h, h, c, device=dev).to(torch.bfloat16)
+    w = torch.randn(k, c, 3, 3, device=dev) * 0.02
+    wpk = ops.wpack(L.WPACK_FWD, w, k, c, 3, 3)
+    wpd = ops.wpack(L.WPACK_DGRAD_S1, w, k, c, 3, 3)
+    g = ops.conv_geom(B, h, h, c, k, 3, 3, 1, 1, 1, h, h)
+    y = torch.empty(B, h, h, k, device=dev, dtype=torch.bfloat16)
+    names = ["plain fwd", "fwd + stats", "dgrad + residual", "dgrad + mask + reductions"]
+    for name, v in zip(names, variants):
+        for _ in range(3):
+            v()
+        tot = 0.0
+        for _ in range(10):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); v(); e1.record(); e1.synchronize()
+            tot += e0.elapsed_time(e1)
+        print(f"{name:28s} {tot / 10 * 1000:7.1f} us")
