@@ -215,9 +215,44 @@ __global__ void wgrad_reduce_fwd_kernel(PackGeom g, const float* __restrict__ pa
   }
 }
 
+// Swapped-role partials [it = i*RS + t][o] -> dw[o][it]: a tiled transpose, so that both the (splits x)
+// reads (along o) and the single read-modify-write per element (along it) are 128-byte coalesced.
+// Tile = 32 (it) x 32 (o); block = 32 x 8 threads.
+__global__ void __launch_bounds__(256) wgrad_reduce_t_kernel(const float* __restrict__ partial, int splits,
+                                                             int64_t split_stride, float* __restrict__ dw,
+                                                             int accumulate, int IT, int O) {
+  __shared__ float tile[32][33];
+  const int it0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int it = it0 + r, o = o0 + threadIdx.x;
+    float acc = 0.f;
+    if (it < IT && o < O) {
+      const float* pp = partial + int64_t(it) * O + o;
+      for (int s = 0; s < splits; ++s) acc += pp[s * split_stride];
+    }
+    tile[r][threadIdx.x] = acc;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += 8) {
+    const int o = o0 + r, it = it0 + threadIdx.x;
+    if (it < IT && o < O) {
+      float* d = dw + int64_t(o) * IT + it;
+      *d = accumulate ? *d + tile[threadIdx.x][r] : tile[threadIdx.x][r];
+    }
+  }
+}
+
 static int launch_wgrad_reduce(const PackGeom& g, const float* partial, int splits,
                                int64_t split_stride, float* dw, int accumulate, cudaStream_t st) {
   const int64_t numel = int64_t(g.O) * g.I * g.RS;
+  if (g.kind == MSIG_WPACK_FWD && g.OOFF == 0 && g.OC == g.O && g.partT) {
+    const int IT = g.I * g.RS;
+    wgrad_reduce_t_kernel<<<dim3(static_cast<unsigned>(ceil_div(IT, 32)), static_cast<unsigned>(ceil_div(g.O, 32))),
+                            dim3(32, 8), 0, st>>>(partial, splits, split_stride, dw, accumulate, IT, g.O);
+    count_launch(1);
+    MSIG_CHECK_LAUNCH();
+    return MSIG_OK;
+  }
   const int threads = 256;
   const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(numel, threads), 4096));
   if (g.kind == MSIG_WPACK_FWD && g.OOFF == 0 && g.OC == g.O) {
