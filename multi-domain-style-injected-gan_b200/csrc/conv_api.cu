@@ -381,6 +381,8 @@ static void set_ring(FpropParams& p, int R, int S, int org_h, int org_w) {
   p.n_blocks = 1;
   p.strip_r = R; p.strip_s = S;
   p.org_h = org_h; p.org_w = org_w;
+  p.ring_cb = 1;
+  for (int t = 0; t < R * S && t < 16; ++t) p.ring_tap[t] = static_cast<int8_t>(t);
   const int sms = sm_count() > 0 ? sm_count() : 148;
   int rows = 64;
   while (rows > 8 && int64_t(p.n_img) * p.tiles_w * ceil_div(p.OH, rows) < int64_t(6) * sms) rows /= 2;
@@ -511,6 +513,30 @@ static int run_phased(const void* in, int n, int h, int w, int c, int k, const v
   ov.base = out; ov.f32 = 0; ov.sC = 1;
   ov.sN = int64_t(4) * h * w * k; ov.sH = 2 * OW2 * k; ov.sW = 2 * int64_t(k);
   if ((rc = fill_epilogue(p, e, ov, k)) != MSIG_OK) return rc;
+  // 128 -> 64 channel layers on wide planes (model.py:140 forward, the dgrad of model.py:132): every phase is
+  // a 2x2 stride-1 conv; run each through the strip-ring kernel (resident 64 KiB filter slab, input rows
+  // shared by consecutive output rows) instead of re-fetching 24 KiB per K block.
+  if (g_ring_mode != 0 && c == 128 && block_n == 64 && k_pad == 64 && w >= 128 && p.stat_out == nullptr) {
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const int ph = py * 2 + px;
+        FpropParams q = p;
+        q.phases = 1;
+        q.out = reinterpret_cast<__nv_bfloat16*>(out) + p.o_ph[ph];
+        if (q.aux != nullptr) q.aux = q.aux + p.a_ph[ph];
+        // input rows / columns of a phase in ascending order: ring position r <-> tap 1 - r
+        set_ring(q, 2, 2, py == 0 ? -1 : 0, px == 0 ? -1 : 0);
+        q.ring_cb = 2;
+        for (int r = 0; r < 2; ++r)
+          for (int s2 = 0; s2 < 2; ++s2) q.ring_tap[r * 2 + s2] = static_cast<int8_t>((1 - r) * 2 + (1 - s2));
+        if ((rc = make_act_map(&q.tmA[1], v, 128 + 1, 1)) != MSIG_OK) return rc;
+        const __nv_bfloat16* wph = reinterpret_cast<const __nv_bfloat16*>(wpk) + int64_t(ph) * k_pad * 4 * c;
+        if ((rc = make_w_map(&q.tmB, wph, k_pad, int64_t(4) * c, 64)) != MSIG_OK) return rc;
+        cudaError_t ce = launch_fprop_ring64(q, sm_count(), st);
+        if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "fprop(phased ring) launch: %s", cudaGetErrorString(ce));
+      }
+    return MSIG_OK;
+  }
   cudaError_t ce = launch_fprop(p, block_n, sm_count(), st);
   if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "fprop(phased) launch: %s", cudaGetErrorString(ce));
   return MSIG_OK;

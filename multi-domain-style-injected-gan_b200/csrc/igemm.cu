@@ -959,6 +959,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int R = p.strip_r, S = p.strip_s;
+  const int CB = p.ring_cb > 1 ? p.ring_cb : 1;                    // 64-channel blocks per input pixel
   const uint32_t strip_tx = static_cast<uint32_t>(kTileM + S - 1) * 128u;
 
   if (warp == 0 && lane == 0) {
@@ -995,8 +996,11 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
 
   if (warp == 0) {
     if (elect_one()) {
-      mbar_expect_tx(wfull_bar, static_cast<uint32_t>(R * S) * kRingWBytes);
-      for (int t = 0; t < R * S; ++t) tma_load_2d(wsm + t * kRingWBytes, &p.tmB, wfull_bar, t * kBlockK, 0);
+      // resident filter, in ring order: slot (r*S + s)*CB + cb <- K block (tap(r,s)*CB + cb) of the packed matrix
+      mbar_expect_tx(wfull_bar, static_cast<uint32_t>(R * S * CB) * kRingWBytes);
+      for (int t = 0; t < R * S; ++t)
+        for (int cb = 0; cb < CB; ++cb)
+          tma_load_2d(wsm + (t * CB + cb) * kRingWBytes, &p.tmB, wfull_bar, (p.ring_tap[t] * CB + cb) * kBlockK, 0);
     }
     __syncwarp();
     uint32_t g = 0;
@@ -1005,13 +1009,13 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
       decode(item, img, tw, h0, nrows);
       const int x0 = p.org_w + tw * kTileM;
       const int y0 = p.org_h + h0;
-      const int nstrips = nrows + R - 1;
+      const int nstrips = (nrows + R - 1) * CB;                    // ring entry = (input row, channel block)
       for (int j = 0; j < nstrips; ++j, ++g) {
         const uint32_t slot = g % kRingSlots;
         mbar_wait(&empty_bar[slot], ((g / kRingSlots) & 1u) ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(&full_bar[slot], strip_tx);
-          tma_load_4d(ring + slot * kRingSlotBytes, &p.tmA[1], &full_bar[slot], 0, x0, y0 + j, img);
+          tma_load_4d(ring + slot * kRingSlotBytes, &p.tmA[1], &full_bar[slot], (j % CB) * kBlockK, x0, y0 + j / CB, img);
         }
         __syncwarp();
       }
@@ -1029,32 +1033,34 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
       for (int i = 0; i < nrows; ++i, ++it) {
         const int as = it & 1;
         mbar_wait(&tempty_bar[as], (((it >> 1) & 1) ^ 1u));
-        for (int r = (i == 0 ? 0 : R - 1); r < R; ++r) {
-          const uint32_t g = g0 + i + r;
+        for (int e = (i == 0 ? 0 : (R - 1) * CB); e < R * CB; ++e) {
+          const uint32_t g = g0 + i * CB + e;
           mbar_wait(&full_bar[g % kRingSlots], (g / kRingSlots) & 1u);
         }
         tc_fence_after();
         if (elect_one()) {
           const uint32_t d_tmem = tmem_base + as * BLOCK_N;
-          for (int r = 0; r < R; ++r) {
-            const uint32_t g = g0 + i + r;
-            const uint32_t sa = ring_addr + (g % kRingSlots) * kRingSlotBytes;
-            for (int s = 0; s < S; ++s) {
-              const uint64_t da = make_smem_desc(sa + s * 128, 0, 1024);      // s pixels into the strip
-              const uint64_t db = make_smem_desc(w_addr + (r * S + s) * kRingWBytes, 0, 1024);
+          for (int r = 0; r < R; ++r)
+            for (int cb = 0; cb < CB; ++cb) {
+              const uint32_t g = g0 + (i + r) * CB + cb;
+              const uint32_t sa = ring_addr + (g % kRingSlots) * kRingSlotBytes;
+              for (int s = 0; s < S; ++s) {
+                const uint64_t da = make_smem_desc(sa + s * 128, 0, 1024);      // s pixels into the strip
+                const uint64_t db = make_smem_desc(w_addr + ((r * S + s) * CB + cb) * kRingWBytes, 0, 1024);
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k)
-                umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (r > 0 || s > 0 || k > 0) ? 1u : 0u);
+                for (int k = 0; k < kBlockK / 16; ++k)
+                  umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (r > 0 || cb > 0 || s > 0 || k > 0) ? 1u : 0u);
+              }
             }
-          }
-          umma_commit(&empty_bar[(g0 + i) % kRingSlots]);
+          // the first input row of this output row is dead now; after the item's last row so are the others
+          for (int cb = 0; cb < CB; ++cb) umma_commit(&empty_bar[(g0 + i * CB + cb) % kRingSlots]);
           if (i == nrows - 1)
-            for (int r = 1; r < R; ++r) umma_commit(&empty_bar[(g0 + i + r) % kRingSlots]);
+            for (int e = CB; e < R * CB; ++e) umma_commit(&empty_bar[(g0 + i * CB + e) % kRingSlots]);
           umma_commit(&tfull_bar[as]);
         }
         __syncwarp();
       }
-      g0 += nrows + R - 1;
+      g0 += (nrows + R - 1) * CB;
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
@@ -1399,8 +1405,10 @@ cudaError_t launch_fprop_ring64(const FpropParams& p, int num_sms, cudaStream_t 
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  if (p.strip_r < 1 || p.strip_s < 1 || p.strip_r * p.strip_s > kRingMaxTaps || p.strip_r + 1 > kRingSlots ||
-      (kTileM + p.strip_s - 1) * 128 > kRingSlotBytes || p.TW != kTileM || p.TH != 1 || p.phases != 1 || p.n_blocks != 1)
+  const int cbs = p.ring_cb > 1 ? p.ring_cb : 1;
+  if (p.strip_r < 1 || p.strip_s < 1 || p.strip_r * p.strip_s * cbs > kRingMaxTaps || p.strip_r * p.strip_s > 16 ||
+      (p.strip_r + 1) * cbs > kRingSlots || (kTileM + p.strip_s - 1) * 128 > kRingSlotBytes || p.TW != kTileM ||
+      p.TH != 1 || p.phases != 1 || p.n_blocks != 1)
     return cudaErrorInvalidValue;
   const int items = p.n_img * p.tiles_w * p.ring_chunks;
   const int grid = items < num_sms ? items : num_sms;

@@ -41,6 +41,8 @@ struct FpropParams {
   int32_t strip_r, strip_s;       // strip / ring kernels: filter extent; tmA[1] has a (128 + strip_s - 1)-pixel box
   int32_t ring_rows, ring_chunks; // ring kernel: output rows per work item, items per image column
   int32_t org_h, org_w;           // ring kernel: input coordinate read by output (0,0) through tap (0,0)
+  int32_t ring_cb;                // ring kernel: 64-channel blocks of the input (1 or 2; 0 means 1)
+  int8_t ring_tap[16];            // ring kernel: filter position (r*S + s) -> tap index in the packed weights
   int32_t OH, OW, TH, TW;         // output plane and the 128-pixel tile (TH*TW == 128)
   int32_t tiles_h, tiles_w, n_img, n_blocks;
   // epilogue

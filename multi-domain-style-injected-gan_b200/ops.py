@@ -59,7 +59,7 @@ def epilogue(bias=None, aux=None, aux_mode=AUX_NONE, act=ACT_NONE, alpha=1.0, al
 # The epilogue-fused reductions cost ~900 cycles per 64 accumulator columns per tile; they are hidden
 # behind the tile's main loop (2*N cycles per 64-deep K block) only when K is long enough. Below this
 # many K blocks the separate statistics / reduction pass is cheaper.
-EPI_STATS_MIN_KBLOCKS = 11
+EPI_STATS_MIN_KBLOCKS = int(__import__('os').environ.get('MSIG_EPI_MIN_KB', '11'))
 
 
 def epi_fusable(taps, c):

@@ -284,6 +284,9 @@ CASES = {
     "dgrad_4x4s2_64_128_w128": lambda: case_conv_dgrad(1, 64, 256, 256, 128, 4, 2, 1),
     "convT_fwd_256_128": lambda: case_convT(2, 256, 32, 32, 128, which="fwd"),
     "convT_fwd_128_64": lambda: case_convT(1, 128, 64, 64, 64, which="fwd"),
+    "convT_fwd_128_64_w128_ring": lambda: case_convT(2, 128, 24, 128, 64, which="fwd"),
+    "convT_fwd_128_64_w256_ring": lambda: case_convT(1, 128, 10, 256, 64, which="fwd"),
+    "dgrad_4x4s2_64_128_ring_b2": lambda: case_conv_dgrad(2, 64, 40, 256, 128, 4, 2, 1),
     "convT_dgrad_256_128": lambda: case_convT(2, 256, 32, 32, 128, which="dgrad"),
     "wgrad_3x3_256": lambda: case_conv_wgrad(2, 256, 64, 64, 256, 3, 1, 1),
     "wgrad_3x3_64_128_w32": lambda: case_conv_wgrad(3, 64, 32, 32, 128, 3, 1, 1),
