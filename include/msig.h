@@ -228,6 +228,18 @@ int msig_norm_act_bwd(const void* dy, const void* x, const float* mean, const fl
                       float* dgamma, float* dbeta, int64_t dgb_stride, int accumulate_dgb,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same two kernels with the reflect padding of the generator's last conv (model.py:141) fused in: the
+ * forward writes act(x*scale+shift) straight into the reflect-padded buffer [n][h+2p][w+2p][c] (interior
+ * plus mirrored border copies); the backward reads dy through the fold of the padded gradient
+ * [n][h+2p][w+2p][c]. They replace msig_reflect_pad_fwd / msig_reflect_pad_bwd and one full pass each. */
+int msig_norm_act_fwd_pad(const void* x, const float* scale, const float* shift, int32_t act, float slope,
+                          int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad, void* y_padded,
+                          void* stream);
+int msig_norm_act_bwd_pad(const void* dy_padded, const void* x, const float* mean, const float* rstd,
+                          const float* scale, const float* shift, int32_t act, float slope, int32_t n,
+                          int32_t h, int32_t w, int32_t c, int32_t pad, void* dx, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
 /* Finish epilogue-fused reductions (msig_epilogue.stats_partial): same results as msig_in_stats /
  * msig_norm_act_bwd without re-reading the activation for the reduction. For the backward form the
  * epilogue must already have applied act' to dy (aux mask), i.e. `g` is dy*act'(u), and stats_z = x. */

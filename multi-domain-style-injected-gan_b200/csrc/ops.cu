@@ -330,12 +330,44 @@ struct NcFinal {
   int accumulate;
 };
 
-template <int MODE>
+// Reflect padding fused into the norm kernels of the layer in front of the generator's final 7x7 conv
+// (model.py:140-141): the forward apply writes its output straight into the reflect-padded buffer
+// (interior + mirrored border copies), and the backward reads its dy THROUGH the fold (the sum of the
+// padded gradient over the positions that mirror onto a pixel). W == 0: plain, unpadded tensors.
+struct PadGeom {
+  int W, H, pad;
+};
+__device__ __forceinline__ void mirror_positions(int i, int n, int pad, int (&pos)[3], int& cnt) {
+  cnt = 0;
+  pos[cnt++] = i + pad;
+  if (i >= 1 && i <= pad) pos[cnt++] = pad - i;
+  if (i <= n - 2 && i >= n - 1 - pad) pos[cnt++] = pad + 2 * (n - 1) - i;
+}
+// dy of pixel p (8 channels at tx*8) = sum of the padded gradient over its mirror positions
+__device__ __forceinline__ void load_fold8(const __nv_bfloat16* __restrict__ dyp, int img, int p, const PadGeom& pg,
+                                           int c, int tx, float (&f)[8]) {
+  const int h = p / pg.W, w = p - h * pg.W;
+  const int W2 = pg.W + 2 * pg.pad, H2 = pg.H + 2 * pg.pad;
+  int ph[3], pw[3], nph, npw;
+  mirror_positions(h, pg.H, pg.pad, ph, nph);
+  mirror_positions(w, pg.W, pg.pad, pw, npw);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) f[j] = 0.f;
+  for (int a = 0; a < nph; ++a)
+    for (int b = 0; b < npw; ++b) {
+      float t[8];
+      load8(dyp + ((int64_t(img) * H2 + ph[a]) * W2 + pw[b]) * c + tx * 8, t);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] += t[j];
+    }
+}
+
+template <int MODE, bool FOLD = false>
 __global__ void __launch_bounds__(256) nc_reduce_kernel(
     const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
     const float* __restrict__ shift, int act, float slope, int hw, int c, int pix_per_block,
-    float* __restrict__ partial, unsigned int* __restrict__ tickets, NcFinal fin) {
+    float* __restrict__ partial, unsigned int* __restrict__ tickets, NcFinal fin, PadGeom pg = PadGeom{0, 0, 0}) {
   __shared__ float red[16][256 + 1];
   __shared__ bool is_last;
   const int cg = c / 8;
@@ -364,7 +396,7 @@ __global__ void __launch_bounds__(256) nc_reduce_kernel(
       const int pp = p + u * lanes;
       if (pp < p1) {
         xv[u] = ldg_stream(x + base + int64_t(pp) * c);
-        if (MODE == 1) dv[u] = ldg_stream(dy + base + int64_t(pp) * c);
+        if (MODE == 1 && !FOLD) dv[u] = ldg_stream(dy + base + int64_t(pp) * c);
       }
     }
 #pragma unroll
@@ -380,7 +412,8 @@ __global__ void __launch_bounds__(256) nc_reduce_kernel(
           }
         } else {
           float df[8];
-          unpack8(dv[u], df);
+          if constexpr (FOLD) load_fold8(dy, img, p + u * lanes, pg, c, tx, df);
+          else unpack8(dv[u], df);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float uu = xf[j] * sc[j] + sh[j];
@@ -514,11 +547,12 @@ __global__ void __launch_bounds__(1024) epi_stats_finalize_kernel(const float* _
   }
 }
 
-// y = act(x*scale + shift) (+ residual)
+// y = act(x*scale + shift) (+ residual); PADOUT: y is the reflect-padded buffer [n][H+2p][W+2p][c]
+template <bool PADOUT = false>
 __global__ void __launch_bounds__(256) norm_act_fwd_kernel(
     const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
     const __nv_bfloat16* __restrict__ res, int act, float slope, int hw, int c, int pix_per_block,
-    __nv_bfloat16* __restrict__ y) {
+    __nv_bfloat16* __restrict__ y, PadGeom pg = PadGeom{0, 0, 0}) {
   const int cg = c / 8;
   const int lanes = 256 / cg;
   const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
@@ -556,18 +590,30 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] += rf[j];
         }
-        store8(y + base + int64_t(pp) * c, f);
+        if constexpr (PADOUT) {
+          const int h = pp / pg.W, w = pp - h * pg.W;
+          const int W2 = pg.W + 2 * pg.pad, H2 = pg.H + 2 * pg.pad;
+          int ph[3], pw[3], nph, npw;
+          mirror_positions(h, pg.H, pg.pad, ph, nph);
+          mirror_positions(w, pg.W, pg.pad, pw, npw);
+          for (int a = 0; a < nph; ++a)
+            for (int b = 0; b < npw; ++b)
+              store8(y + ((int64_t(img) * H2 + ph[a]) * W2 + pw[b]) * c + tx * 8, f);
+        } else {
+          store8(y + base + int64_t(pp) * c, f);
+        }
       }
     }
   }
 }
 
-// dx = scale * (g - c1 - xhat*c2),  g = dy*act'(x*scale+shift)
+// dx = scale * (g - c1 - xhat*c2),  g = dy*act'(x*scale+shift); FOLD: dy is read through the reflect fold
+template <bool FOLD = false>
 __global__ void __launch_bounds__(256) norm_act_bwd_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
     const float* __restrict__ shift, const float* __restrict__ coef, int act, float slope, int hw, int c,
-    int pix_per_block, __nv_bfloat16* __restrict__ dx) {
+    int pix_per_block, __nv_bfloat16* __restrict__ dx, PadGeom pg = PadGeom{0, 0, 0}) {
   const int cg = c / 8;
   const int lanes = 256 / cg;
   const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
@@ -594,7 +640,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(
       const int pp = p + u * lanes;
       if (pp < p1) {
         xv[u] = ldg_stream(x + base + int64_t(pp) * c);
-        dv[u] = ldg_stream(dy + base + int64_t(pp) * c);
+        if (!FOLD) dv[u] = ldg_stream(dy + base + int64_t(pp) * c);
       }
     }
 #pragma unroll
@@ -603,7 +649,8 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(
       if (pp < p1) {
         float xf[8], df[8];
         unpack8(xv[u], xf);
-        unpack8(dv[u], df);
+        if constexpr (FOLD) load_fold8(dy, img, pp, pg, c, tx, df);
+        else unpack8(dv[u], df);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float uu = xf[j] * sc[j] + sh[j];
@@ -984,7 +1031,7 @@ int msig_norm_act_fwd(const void* x, const float* scale, const float* shift, con
   MSIG_REQUIRE(norm_c_ok(c), "msig_norm_act_fwd: channels %d unsupported", c);
   const int ppb = pick_pix_per_block(n, hw);
   const int chunks = static_cast<int>(ceil_div(hw, ppb));
-  norm_act_fwd_kernel<<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), scale, shift, CBF(residual), act, slope,
+  norm_act_fwd_kernel<false><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), scale, shift, CBF(residual), act, slope,
                                                               hw, c, ppb, BF(y));
   count_launch(1);
   MSIG_CHECK_LAUNCH();
@@ -1012,8 +1059,50 @@ int msig_norm_act_bwd(const void* dy, const void* x, const float* mean, const fl
   nc_reduce_kernel<1><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), CBF(dy), mean, rstd, scale, shift, act,
                                                               slope, hw, c, ppb, partial, tickets, fin);
   MSIG_CHECK_LAUNCH();
-  norm_act_bwd_kernel<<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(dy), CBF(x), mean, rstd, scale, shift, coef,
+  norm_act_bwd_kernel<false><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(dy), CBF(x), mean, rstd, scale, shift, coef,
                                                               act, slope, hw, c, ppb, BF(dx));
+  count_launch(2);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
+int msig_norm_act_fwd_pad(const void* x, const float* scale, const float* shift, int32_t act, float slope, int32_t n,
+                          int32_t h, int32_t w, int32_t c, int32_t pad, void* y_padded, void* stream) {
+  MSIG_REQUIRE(x && scale && shift && y_padded, "msig_norm_act_fwd_pad: null argument");
+  MSIG_REQUIRE(norm_c_ok(c) && pad >= 1 && pad < h && pad < w, "msig_norm_act_fwd_pad: bad shape");
+  const int hw = h * w;
+  const int ppb = pick_pix_per_block(n, hw);
+  const int chunks = static_cast<int>(ceil_div(hw, ppb));
+  norm_act_fwd_kernel<true><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), scale, shift, nullptr, act, slope, hw, c,
+                                                                    ppb, BF(y_padded), PadGeom{w, h, pad});
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
+int msig_norm_act_bwd_pad(const void* dy_padded, const void* x, const float* mean, const float* rstd,
+                          const float* scale, const float* shift, int32_t act, float slope, int32_t n, int32_t h,
+                          int32_t w, int32_t c, int32_t pad, void* dx, void* workspace, size_t workspace_bytes,
+                          void* stream) {
+  MSIG_REQUIRE(dy_padded && x && mean && rstd && scale && shift && dx && workspace,
+               "msig_norm_act_bwd_pad: null argument");
+  MSIG_REQUIRE(norm_c_ok(c) && pad >= 1 && pad < h && pad < w, "msig_norm_act_bwd_pad: bad shape");
+  const int hw = h * w;
+  MSIG_REQUIRE(workspace_bytes >= msig_in_stats_workspace(n, hw, c), "msig_norm_act_bwd_pad: workspace too small");
+  const int ppb = pick_pix_per_block(n, hw);
+  const int chunks = static_cast<int>(ceil_div(hw, ppb));
+  float* partial = reinterpret_cast<float*>(workspace);
+  float* coef = partial + size_t(n) * chunks * 2 * c;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(coef + size_t(n) * 2 * c);
+  MSIG_CHECK_CUDA(cudaMemsetAsync(tickets, 0, size_t(n) * sizeof(unsigned int), ST(stream)));
+  NcFinal fin{};
+  fin.coef = coef;
+  const PadGeom pg{w, h, pad};
+  nc_reduce_kernel<1, true><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), CBF(dy_padded), mean, rstd, scale, shift,
+                                                                    act, slope, hw, c, ppb, partial, tickets, fin, pg);
+  MSIG_CHECK_LAUNCH();
+  norm_act_bwd_kernel<true><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(dy_padded), CBF(x), mean, rstd, scale, shift,
+                                                                    coef, act, slope, hw, c, ppb, BF(dx), pg);
   count_launch(2);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -1049,7 +1138,7 @@ int msig_norm_bwd_from_partials(const float* partial, int32_t n, int32_t rows_pe
   MSIG_CHECK_LAUNCH();
   const int ppb = pick_pix_per_block(n, hw);
   const int chunks = static_cast<int>(ceil_div(hw, ppb));
-  norm_act_bwd_kernel<<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(g), CBF(x), mean, rstd, scale, shift, coef,
+  norm_act_bwd_kernel<false><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(g), CBF(x), mean, rstd, scale, shift, coef,
                                                               MSIG_ACT_NONE, 0.f, hw, c, ppb, BF(dx));
   count_launch(2);
   MSIG_CHECK_LAUNCH();

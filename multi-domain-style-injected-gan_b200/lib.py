@@ -93,6 +93,10 @@ _SIGS = {
                                   _P]),
     "msig_norm_act_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int32, c_float, c_int32,
                                   c_int32, c_int32, _P, _P, _P, c_int64, c_int, _P, c_size_t, _P]),
+    "msig_norm_act_fwd_pad": (c_int, [_P, _P, _P, c_int32, c_float, c_int32, c_int32, c_int32, c_int32, c_int32, _P,
+                                      _P]),
+    "msig_norm_act_bwd_pad": (c_int, [_P, _P, _P, _P, _P, _P, c_int32, c_float, c_int32, c_int32, c_int32, c_int32,
+                                      c_int32, _P, _P, c_size_t, _P]),
     "msig_epilogue_stats_rows": (c_int32, [c_int32, c_int32, c_int32]),
     "msig_in_stats_from_partials": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P,
                                             c_int64, _P, _P, _P, _P, _P]),

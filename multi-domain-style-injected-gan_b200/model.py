@@ -307,8 +307,7 @@ class _GeneratorFn(torch.autograd.Function):
         yu1 = ops.norm_act_fwd(zu1, stu1, ACT_RELU)
         gu2 = ops.conv_geom(B, H // 2, W // 2, 128, 64, 4, 4, 2, 1, 1, H, W)
         zu2, stu2 = _conv_stats(yu1, P["u2"], gu2, transposed=True)
-        yu2 = ops.norm_act_fwd(zu2, stu2, ACT_RELU)
-        xp = ops.reflect_pad_fwd(yu2, 3)
+        xp = ops.norm_act_fwd_pad(zu2, stu2, ACT_RELU, 3)   # IN + ReLU written straight into the reflect-padded buffer
         gf = ops.conv_geom(B, H + 6, W + 6, 64, 3, 7, 7, 1, 0, 0, H, W)
         out = ops.conv_narrow_fwd(xp, P["f"], gf, ops.epilogue(bias=mod.decoder[k + 6].bias.detach(), act=ACT_TANH,
                                                                out_layout=OUT_F32_NCHW))
@@ -341,10 +340,9 @@ class _GeneratorFn(torch.autograd.Function):
         if wg:
             ops.conv_rowpatch_wgrad(dz8, S["xp"], gfd, _grad_buf(dec[k + 6].weight), flip=True)
         del dz8
-        dy = ops.reflect_pad_bwd(dxp, 3)
+        # ---- up 2 (ConvTranspose 128->64 + IN + ReLU); the reflect fold of dxp happens inside the norm backward
+        dzu2 = ops.norm_act_bwd_pad(dxp, S["zu2"], S["stu2"], ACT_RELU, 3)
         del dxp
-        # ---- up 2 (ConvTranspose 128->64 + IN + ReLU)
-        dzu2 = ops.norm_act_bwd(dy, S["zu2"], S["stu2"], ACT_RELU)
         if wg:
             ops.convT2d_wgrad(S["yu1"], dzu2, S["gu2"], _grad_buf(dec[k + 3].weight))
         # Every dgrad below also applies the previous layer's ReLU mask and reduces (sum g, sum g*z)

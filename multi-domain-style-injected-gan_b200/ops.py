@@ -395,6 +395,25 @@ def norm_act_fwd(x, st, act=ACT_NONE, residual=None, slope=0.2, out=None):
     return out
 
 
+def norm_act_fwd_pad(x, st, act, pad, slope=0.2):
+    """norm-apply + activation written straight into the reflect-padded buffer [n, h+2p, w+2p, c]."""
+    n, h, w, c = x.shape
+    out = torch.empty((n, h + 2 * pad, w + 2 * pad, c), dtype=BF16, device=x.device)
+    L.call("msig_norm_act_fwd_pad", _p(x), _p(st.scale), _p(st.shift), act, slope, n, h, w, c, pad, _p(out), _stream())
+    return out
+
+
+def norm_act_bwd_pad(dy_padded, x, st, act, pad, slope=0.2):
+    """norm backward whose dy is the fold of the reflect-padded gradient [n, h+2p, w+2p, c]."""
+    n, h, w, c = x.shape
+    out = torch.empty_like(x)
+    nbytes = L.load().msig_in_stats_workspace(n, h * w, c)
+    ws = workspace(nbytes, x.device)
+    L.call("msig_norm_act_bwd_pad", _p(dy_padded), _p(x), _p(st.mean), _p(st.rstd), _p(st.scale), _p(st.shift),
+           act, slope, n, h, w, c, pad, _p(out), _p(ws), ws.numel(), _stream())
+    return out
+
+
 def norm_act_bwd(dy, x, st, act=ACT_NONE, slope=0.2, dgamma=None, dbeta=None, dgb_stride=0,
                  accumulate_dgb=False, out=None):
     n, h, w, c = x.shape

@@ -221,6 +221,26 @@ def case_gram_l1(seed=0):
     return max(abs(loss.item() - ref.item()) / ref.item(), (ssym.float() - sref).abs().max().item()), 1e-5
 
 
+def case_norm_pad(n=2, h=24, w=40, c=64, pad=3, seed=0):
+    """Reflect padding fused into the norm kernels (model.py:140-141) vs the separate pad / fold passes and
+    vs PyTorch (F.pad reflect + its autograd)."""
+    ops.ensure_init()
+    x = _rand((n, h, w, c), seed).to(DEV).to(torch.bfloat16)
+    st = ops.in_stats(x)
+    y_ref = ops.reflect_pad_fwd(ops.norm_act_fwd(x, st, L.ACT_RELU), pad)
+    y = ops.norm_act_fwd_pad(x, st, L.ACT_RELU, pad)
+    e_fwd = (y.float() - y_ref.float()).abs().max().item()            # same arithmetic: bit-exact
+    dyp = _rand((n, h + 2 * pad, w + 2 * pad, c), seed + 1).to(DEV).to(torch.bfloat16)
+    dx = ops.norm_act_bwd_pad(dyp, x, st, L.ACT_RELU, pad)
+    # PyTorch fp32: y = relu(instance_norm(x)); loss = <reflect_pad(y), dyp>
+    xt = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    yt = F.pad(F.relu(F.instance_norm(xt, eps=1e-5)), (pad, pad, pad, pad), mode="reflect")
+    (yt * dyp.float().permute(0, 3, 1, 2)).sum().backward()
+    torch.cuda.synchronize()
+    e_bwd = rel_err(dx.float().permute(0, 3, 1, 2), xt.grad)
+    return max(e_fwd * 1e2, e_bwd), 1e-2
+
+
 def case_adam(seed=0):
     """clip_grad_norm_(1.0) + Adam(betas 0.5/0.999) + EMA(0.995) over a flat buffer, 3 steps."""
     ops.ensure_init()
@@ -269,5 +289,7 @@ CASES = {
     "heads": case_heads,
     "losses": case_losses,
     "gram_l1": case_gram_l1,
+    "norm_pad_fused": case_norm_pad,
+    "norm_pad_fused_256": lambda: case_norm_pad(1, 256, 256, 64, 3, 3),
     "adam": case_adam,
 }
