@@ -235,6 +235,7 @@ int msig_norm_act_bwd(const void* dy, const void* x, const float* mean, const fl
 int msig_norm_act_fwd_pad(const void* x, const float* scale, const float* shift, int32_t act, float slope,
                           int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad, void* y_padded,
                           void* stream);
+size_t msig_norm_act_bwd_pad_workspace(int32_t n, int32_t h, int32_t w, int32_t c);
 int msig_norm_act_bwd_pad(const void* dy_padded, const void* x, const float* mean, const float* rstd,
                           const float* scale, const float* shift, int32_t act, float slope, int32_t n,
                           int32_t h, int32_t w, int32_t c, int32_t pad, void* dx, void* workspace,

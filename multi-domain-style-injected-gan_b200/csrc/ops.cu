@@ -336,25 +336,39 @@ struct NcFinal {
 // padded gradient over the positions that mirror onto a pixel). W == 0: plain, unpadded tensors.
 struct PadGeom {
   int W, H, pad;
+  float inv_w;      // 1 / W: row of pixel p = int((p + 0.5) * inv_w), exact for p < 2^22
 };
+__device__ __forceinline__ void pixel_hw(const PadGeom& pg, int p, int& h, int& w) {
+  h = __float2int_rz((static_cast<float>(p) + 0.5f) * pg.inv_w);
+  w = p - h * pg.W;
+}
+__device__ __forceinline__ bool pad_interior(const PadGeom& pg, int h, int w) {   // no mirrored copy
+  return (h > pg.pad) & (h < pg.H - 1 - pg.pad) & (w > pg.pad) & (w < pg.W - 1 - pg.pad);
+}
 __device__ __forceinline__ void mirror_positions(int i, int n, int pad, int (&pos)[3], int& cnt) {
   cnt = 0;
   pos[cnt++] = i + pad;
   if (i >= 1 && i <= pad) pos[cnt++] = pad - i;
   if (i <= n - 2 && i >= n - 1 - pad) pos[cnt++] = pad + 2 * (n - 1) - i;
 }
-// dy of pixel p (8 channels at tx*8) = sum of the padded gradient over its mirror positions
-__device__ __forceinline__ void load_fold8(const __nv_bfloat16* __restrict__ dyp, int img, int p, const PadGeom& pg,
-                                           int c, int tx, float (&f)[8]) {
-  const int h = p / pg.W, w = p - h * pg.W;
+// dy of pixel p = sum of the padded gradient over its mirror positions. The position (h+pad, w+pad) is
+// always one of them: its load is issued with the batched loads (fold_direct_offset); the mirrored
+// border copies (a few % of the pixels) are added afterwards (fold_add_mirrors).
+// (The launchers make the block's pixel range a divisor of W, so a block stays inside one image row h.)
+__device__ __forceinline__ int64_t fold_direct_offset(const PadGeom& pg, int img, int h, int w, int c, int tx) {
+  const int W2 = pg.W + 2 * pg.pad, H2 = pg.H + 2 * pg.pad;
+  return ((int64_t(img) * H2 + h + pg.pad) * W2 + w + pg.pad) * c + tx * 8;
+}
+__device__ __forceinline__ void fold_add_mirrors(const __nv_bfloat16* __restrict__ dyp, int img, int h, int w,
+                                                 const PadGeom& pg, int c, int tx, float (&f)[8]) {
+  if (pad_interior(pg, h, w)) return;
   const int W2 = pg.W + 2 * pg.pad, H2 = pg.H + 2 * pg.pad;
   int ph[3], pw[3], nph, npw;
   mirror_positions(h, pg.H, pg.pad, ph, nph);
   mirror_positions(w, pg.W, pg.pad, pw, npw);
-#pragma unroll
-  for (int j = 0; j < 8; ++j) f[j] = 0.f;
   for (int a = 0; a < nph; ++a)
     for (int b = 0; b < npw; ++b) {
+      if (a == 0 && b == 0) continue;               // the direct position is already in f
       float t[8];
       load8(dyp + ((int64_t(img) * H2 + ph[a]) * W2 + pw[b]) * c + tx * 8, t);
 #pragma unroll
@@ -363,11 +377,11 @@ __device__ __forceinline__ void load_fold8(const __nv_bfloat16* __restrict__ dyp
 }
 
 template <int MODE, bool FOLD = false>
-__global__ void __launch_bounds__(256) nc_reduce_kernel(
+__global__ void __launch_bounds__(256, FOLD ? 2 : 1) nc_reduce_kernel(
     const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ dy,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
     const float* __restrict__ shift, int act, float slope, int hw, int c, int pix_per_block,
-    float* __restrict__ partial, unsigned int* __restrict__ tickets, NcFinal fin, PadGeom pg = PadGeom{0, 0, 0}) {
+    float* __restrict__ partial, unsigned int* __restrict__ tickets, NcFinal fin, PadGeom pg = PadGeom{0, 0, 0, 0.f}) {
   __shared__ float red[16][256 + 1];
   __shared__ bool is_last;
   const int cg = c / 8;
@@ -389,6 +403,8 @@ __global__ void __launch_bounds__(256) nc_reduce_kernel(
     }
   }
   const int64_t base = int64_t(img) * hw * c + tx * 8;
+  const int h_blk = FOLD ? p0 / pg.W : 0;                 // FOLD: the whole block lies in image row h_blk
+  const int64_t fold_base = FOLD ? fold_direct_offset(pg, img, h_blk, -h_blk * pg.W, c, tx) : 0;   // + p*c
   for (int p = p0 + ty; p < p1; p += kUnroll * lanes) {
     uint4 xv[kUnroll], dv[kUnroll];
 #pragma unroll
@@ -396,7 +412,7 @@ __global__ void __launch_bounds__(256) nc_reduce_kernel(
       const int pp = p + u * lanes;
       if (pp < p1) {
         xv[u] = ldg_stream(x + base + int64_t(pp) * c);
-        if (MODE == 1 && !FOLD) dv[u] = ldg_stream(dy + base + int64_t(pp) * c);
+        if (MODE == 1) dv[u] = ldg_stream(FOLD ? dy + fold_base + int64_t(pp) * c : dy + base + int64_t(pp) * c);
       }
     }
 #pragma unroll
@@ -412,8 +428,8 @@ __global__ void __launch_bounds__(256) nc_reduce_kernel(
           }
         } else {
           float df[8];
-          if constexpr (FOLD) load_fold8(dy, img, p + u * lanes, pg, c, tx, df);
-          else unpack8(dv[u], df);
+          unpack8(dv[u], df);
+          if constexpr (FOLD) fold_add_mirrors(dy, img, h_blk, p + u * lanes - h_blk * pg.W, pg, c, tx, df);
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float uu = xf[j] * sc[j] + sh[j];
@@ -552,7 +568,7 @@ template <bool PADOUT = false>
 __global__ void __launch_bounds__(256) norm_act_fwd_kernel(
     const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
     const __nv_bfloat16* __restrict__ res, int act, float slope, int hw, int c, int pix_per_block,
-    __nv_bfloat16* __restrict__ y, PadGeom pg = PadGeom{0, 0, 0}) {
+    __nv_bfloat16* __restrict__ y, PadGeom pg = PadGeom{0, 0, 0, 0.f}) {
   const int cg = c / 8;
   const int lanes = 256 / cg;
   const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
@@ -591,14 +607,19 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(
           for (int j = 0; j < 8; ++j) f[j] += rf[j];
         }
         if constexpr (PADOUT) {
-          const int h = pp / pg.W, w = pp - h * pg.W;
+          int h, w;
+          pixel_hw(pg, pp, h, w);
           const int W2 = pg.W + 2 * pg.pad, H2 = pg.H + 2 * pg.pad;
-          int ph[3], pw[3], nph, npw;
-          mirror_positions(h, pg.H, pg.pad, ph, nph);
-          mirror_positions(w, pg.W, pg.pad, pw, npw);
-          for (int a = 0; a < nph; ++a)
-            for (int b = 0; b < npw; ++b)
-              store8(y + ((int64_t(img) * H2 + ph[a]) * W2 + pw[b]) * c + tx * 8, f);
+          if (pad_interior(pg, h, w)) {
+            store8(y + ((int64_t(img) * H2 + h + pg.pad) * W2 + w + pg.pad) * c + tx * 8, f);
+          } else {
+            int ph[3], pw[3], nph, npw;
+            mirror_positions(h, pg.H, pg.pad, ph, nph);
+            mirror_positions(w, pg.W, pg.pad, pw, npw);
+            for (int a = 0; a < nph; ++a)
+              for (int b = 0; b < npw; ++b)
+                store8(y + ((int64_t(img) * H2 + ph[a]) * W2 + pw[b]) * c + tx * 8, f);
+          }
         } else {
           store8(y + base + int64_t(pp) * c, f);
         }
@@ -609,11 +630,11 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(
 
 // dx = scale * (g - c1 - xhat*c2),  g = dy*act'(x*scale+shift); FOLD: dy is read through the reflect fold
 template <bool FOLD = false>
-__global__ void __launch_bounds__(256) norm_act_bwd_kernel(
+__global__ void __launch_bounds__(256, FOLD ? 2 : 1) norm_act_bwd_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
     const float* __restrict__ shift, const float* __restrict__ coef, int act, float slope, int hw, int c,
-    int pix_per_block, __nv_bfloat16* __restrict__ dx, PadGeom pg = PadGeom{0, 0, 0}) {
+    int pix_per_block, __nv_bfloat16* __restrict__ dx, PadGeom pg = PadGeom{0, 0, 0, 0.f}) {
   const int cg = c / 8;
   const int lanes = 256 / cg;
   const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
@@ -633,6 +654,8 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(
     k2[j] = -sc[j] * (c1 - mu * rs * c2);
   }
   const int64_t base = int64_t(img) * hw * c + tx * 8;
+  const int h_blk = FOLD ? p0 / pg.W : 0;
+  const int64_t fold_base = FOLD ? fold_direct_offset(pg, img, h_blk, -h_blk * pg.W, c, tx) : 0;
   for (int p = p0 + ty; p < p1; p += kUnroll * lanes) {
     uint4 xv[kUnroll], dv[kUnroll];
 #pragma unroll
@@ -640,7 +663,7 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(
       const int pp = p + u * lanes;
       if (pp < p1) {
         xv[u] = ldg_stream(x + base + int64_t(pp) * c);
-        if (!FOLD) dv[u] = ldg_stream(dy + base + int64_t(pp) * c);
+        dv[u] = ldg_stream(FOLD ? dy + fold_base + int64_t(pp) * c : dy + base + int64_t(pp) * c);
       }
     }
 #pragma unroll
@@ -649,8 +672,8 @@ __global__ void __launch_bounds__(256) norm_act_bwd_kernel(
       if (pp < p1) {
         float xf[8], df[8];
         unpack8(xv[u], xf);
-        if constexpr (FOLD) load_fold8(dy, img, pp, pg, c, tx, df);
-        else unpack8(dv[u], df);
+        unpack8(dv[u], df);
+        if constexpr (FOLD) fold_add_mirrors(dy, img, h_blk, pp - h_blk * pg.W, pg, c, tx, df);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float uu = xf[j] * sc[j] + sh[j];
@@ -1069,15 +1092,24 @@ int msig_norm_act_bwd(const void* dy, const void* x, const float* mean, const fl
 int msig_norm_act_fwd_pad(const void* x, const float* scale, const float* shift, int32_t act, float slope, int32_t n,
                           int32_t h, int32_t w, int32_t c, int32_t pad, void* y_padded, void* stream) {
   MSIG_REQUIRE(x && scale && shift && y_padded, "msig_norm_act_fwd_pad: null argument");
-  MSIG_REQUIRE(norm_c_ok(c) && pad >= 1 && pad < h && pad < w, "msig_norm_act_fwd_pad: bad shape");
+  MSIG_REQUIRE(norm_c_ok(c) && pad >= 1 && pad < h && pad < w && int64_t(h) * w < (1 << 22),
+               "msig_norm_act_fwd_pad: bad shape");
   const int hw = h * w;
   const int ppb = pick_pix_per_block(n, hw);
   const int chunks = static_cast<int>(ceil_div(hw, ppb));
   norm_act_fwd_kernel<true><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), scale, shift, nullptr, act, slope, hw, c,
-                                                                    ppb, BF(y_padded), PadGeom{w, h, pad});
+                                                                    ppb, BF(y_padded), PadGeom{w, h, pad, 1.f / w});
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
+}
+
+size_t msig_norm_act_bwd_pad_workspace(int32_t n, int32_t h, int32_t w, int32_t c) {
+  const int hw = h * w;
+  int ppb = std::min(pick_pix_per_block(n, hw), w);
+  while (w % ppb) --ppb;
+  const size_t chunks = size_t(hw / ppb);
+  return (size_t(n) * chunks * 2 * c + size_t(n) * 2 * c + size_t(n)) * sizeof(float);
 }
 
 int msig_norm_act_bwd_pad(const void* dy_padded, const void* x, const float* mean, const float* rstd,
@@ -1086,18 +1118,21 @@ int msig_norm_act_bwd_pad(const void* dy_padded, const void* x, const float* mea
                           void* stream) {
   MSIG_REQUIRE(dy_padded && x && mean && rstd && scale && shift && dx && workspace,
                "msig_norm_act_bwd_pad: null argument");
-  MSIG_REQUIRE(norm_c_ok(c) && pad >= 1 && pad < h && pad < w, "msig_norm_act_bwd_pad: bad shape");
+  MSIG_REQUIRE(norm_c_ok(c) && pad >= 1 && pad < h && pad < w && int64_t(h) * w < (1 << 22),
+               "msig_norm_act_bwd_pad: bad shape");
   const int hw = h * w;
-  MSIG_REQUIRE(workspace_bytes >= msig_in_stats_workspace(n, hw, c), "msig_norm_act_bwd_pad: workspace too small");
-  const int ppb = pick_pix_per_block(n, hw);
-  const int chunks = static_cast<int>(ceil_div(hw, ppb));
+  int ppb = std::min(pick_pix_per_block(n, hw), w);
+  while (w % ppb) --ppb;                                   // a block never straddles two image rows
+  const int chunks = hw / ppb;
+  MSIG_REQUIRE(workspace_bytes >= (size_t(n) * chunks * 2 * c + size_t(n) * 2 * c + size_t(n)) * sizeof(float),
+               "msig_norm_act_bwd_pad: workspace too small");
   float* partial = reinterpret_cast<float*>(workspace);
   float* coef = partial + size_t(n) * chunks * 2 * c;
   unsigned int* tickets = reinterpret_cast<unsigned int*>(coef + size_t(n) * 2 * c);
   MSIG_CHECK_CUDA(cudaMemsetAsync(tickets, 0, size_t(n) * sizeof(unsigned int), ST(stream)));
   NcFinal fin{};
   fin.coef = coef;
-  const PadGeom pg{w, h, pad};
+  const PadGeom pg{w, h, pad, 1.f / w};
   nc_reduce_kernel<1, true><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), CBF(dy_padded), mean, rstd, scale, shift,
                                                                     act, slope, hw, c, ppb, partial, tickets, fin, pg);
   MSIG_CHECK_LAUNCH();

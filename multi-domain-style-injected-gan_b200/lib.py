@@ -95,6 +95,7 @@ _SIGS = {
                                   c_int32, c_int32, _P, _P, _P, c_int64, c_int, _P, c_size_t, _P]),
     "msig_norm_act_fwd_pad": (c_int, [_P, _P, _P, c_int32, c_float, c_int32, c_int32, c_int32, c_int32, c_int32, _P,
                                       _P]),
+    "msig_norm_act_bwd_pad_workspace": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "msig_norm_act_bwd_pad": (c_int, [_P, _P, _P, _P, _P, _P, c_int32, c_float, c_int32, c_int32, c_int32, c_int32,
                                       c_int32, _P, _P, c_size_t, _P]),
     "msig_epilogue_stats_rows": (c_int32, [c_int32, c_int32, c_int32]),

@@ -407,7 +407,7 @@ def norm_act_bwd_pad(dy_padded, x, st, act, pad, slope=0.2):
     """norm backward whose dy is the fold of the reflect-padded gradient [n, h+2p, w+2p, c]."""
     n, h, w, c = x.shape
     out = torch.empty_like(x)
-    nbytes = L.load().msig_in_stats_workspace(n, h * w, c)
+    nbytes = L.load().msig_norm_act_bwd_pad_workspace(n, h, w, c)
     ws = workspace(nbytes, x.device)
     L.call("msig_norm_act_bwd_pad", _p(dy_padded), _p(x), _p(st.mean), _p(st.rstd), _p(st.scale), _p(st.shift),
            act, slope, n, h, w, c, pad, _p(out), _p(ws), ws.numel(), _stream())
