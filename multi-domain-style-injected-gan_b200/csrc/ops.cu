@@ -1061,7 +1061,7 @@ int msig_norm_act_fwd(const void* x, const float* scale, const float* shift, con
                       float slope, int32_t n, int32_t hw, int32_t c, void* y, void* stream) {
   MSIG_REQUIRE(x && scale && shift && y, "msig_norm_act_fwd: null argument");
   MSIG_REQUIRE(norm_c_ok(c), "msig_norm_act_fwd: channels %d unsupported", c);
-  const int ppb = pick_pix_per_block(n, hw, residual ? 2 : 3);
+  const int ppb = pick_pix_per_block(n, hw, 3);
   const int chunks = static_cast<int>(ceil_div(hw, ppb));
   norm_act_fwd_kernel<false><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), scale, shift, CBF(residual), act, slope,
                                                               hw, c, ppb, BF(y));
