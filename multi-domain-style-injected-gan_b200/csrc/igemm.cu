@@ -1305,6 +1305,169 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
   }
 }
 
+
+// ------------------------------------------------------------------------------------ CTA-pair wgrad
+// wgrad2_kernel: the 256 x 256 weight-gradient tile (M = 256 channels of the A side, N = 256 of the B
+// side) of one (tap, K split) on a CTA PAIR: one tcgen05.mma.cta_group::2 per 16 pixels covers both CTAs'
+// 128 M rows; each CTA stages its own 128-channel A tile and HALF of the B tile (32 KiB instead of
+// 48 KiB per 64-pixel K block per SM), 6-stage ring. Rank 0 issues the MMAs. Used for the residual
+// blocks' 3x3 256->256 layers (m_blocks == 2, n_blocks == 1).
+constexpr int kW2Stages = 6;
+constexpr int kW2StageBytes = 4 * 8192;                 // A: 2 x 64 ch x 64 px, B half: 2 x 64 ch x 64 px
+constexpr int kW2SmemBytes = kW2Stages * kW2StageBytes + 1024 + 256;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) wgrad2_kernel(const __grid_constant__ WgradParams p) {
+  constexpr int BLOCK_N = 256;
+  const uint32_t rank = cluster_ctarank();               // == m_blk
+  const int m_blk = static_cast<int>(rank);
+  const int tap = blockIdx.y;
+  const int split = blockIdx.z;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kW2Stages * kW2StageBytes);
+  uint64_t* empty_bar = full_bar + kW2Stages;
+  uint64_t* tfull_bar = empty_bar + kW2Stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) {
+      prefetch_tmap(&p.tmA[i]);
+      prefetch_tmap(&p.tmB[i]);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kW2Stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  cluster_sync_all();
+  if (warp == 2) tmem_alloc_2sm(tmem_slot, BLOCK_N);
+  tc_fence_before();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int kb0 = split * p.kb_per_split;
+  int kb1 = kb0 + p.kb_per_split;
+  if (kb1 > p.kb_total) kb1 = p.kb_total;
+  const int nk = kb1 > kb0 ? kb1 - kb0 : 0;
+
+  if (warp == 0) {
+    const Tap ta = p.tapA[tap];
+    const Tap tb = p.tapB[tap];
+    const int per_img = p.blocks_h * p.blocks_w;
+    int stage = 0;
+    uint32_t phase = 0;
+    int img = kb0 / per_img;
+    const int rem = kb0 - img * per_img;
+    int hb = rem / p.blocks_w;
+    int wb = rem - hb * p.blocks_w;
+    for (int kb = 0; kb < nk; ++kb) {
+      const int oh0 = hb * p.PH, ow0 = wb * p.PW;
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      if (elect_one()) {
+        uint8_t* sa = smem + stage * kW2StageBytes;
+        uint8_t* sb = sa + 2 * 8192;
+        if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * kW2StageBytes);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          tma_load_4d_2sm(sa + i * 8192, &p.tmA[ta.map], &full_bar[stage], m_blk * kTileM + 64 * i, ow0 + ta.dw,
+                          oh0 + ta.dh, img);
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+          tma_load_4d_2sm(sb + i * 8192, &p.tmB[tb.map], &full_bar[stage], static_cast<int>(rank) * 128 + 64 * i,
+                          ow0 + tb.dw, oh0 + tb.dh, img);
+      }
+      __syncwarp();
+      if (++wb == p.blocks_w) {
+        wb = 0;
+        if (++hb == p.blocks_h) {
+          hb = 0;
+          ++img;
+        }
+      }
+      if (++stage == kW2Stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp == 1 && rank == 0) {
+    const uint32_t idesc = make_idesc_bf16(256, BLOCK_N, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < nk; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t sa = smem_u32(smem + stage * kW2StageBytes);
+        const uint64_t da = make_smem_desc(sa, 8192, 1024);
+        const uint64_t db = make_smem_desc(sa + 2 * 8192, 8192, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16_2sm(tmem_base, da + 128 * k, db + 128 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        umma_commit_2sm(&empty_bar[stage], 3);
+        if (kb == nk - 1) umma_commit_2sm(tfull_bar, 3);
+      }
+      __syncwarp();
+      if (++stage == kW2Stages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int m = m_blk * kTileM + q * 32 + lane;
+    const bool row_valid = m < p.m_valid;
+    float* orow = p.out + split * p.o_split + tap * p.o_tap + static_cast<int64_t>(m) * p.o_row;
+    if (nk > 0) {
+      mbar_wait(tfull_bar, 0);
+      tc_fence_after();
+    }
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      uint32_t r[32];
+      if (nk > 0) {
+        tmem_ld_32x32(taddr + c, r);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (row_valid) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 a, b;
+          a.x = __float_as_uint(__uint_as_float(r[j]) * p.alpha);
+          a.y = __float_as_uint(__uint_as_float(r[j + 1]) * p.alpha);
+          a.z = __float_as_uint(__uint_as_float(r[j + 2]) * p.alpha);
+          a.w = __float_as_uint(__uint_as_float(r[j + 3]) * p.alpha);
+          b.x = __float_as_uint(__uint_as_float(r[j + 4]) * p.alpha);
+          b.y = __float_as_uint(__uint_as_float(r[j + 5]) * p.alpha);
+          b.z = __float_as_uint(__uint_as_float(r[j + 6]) * p.alpha);
+          b.w = __float_as_uint(__uint_as_float(r[j + 7]) * p.alpha);
+          stg256(orow + c + j, a, b);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, BLOCK_N);
+  }
+}
+
 // ------------------------------------------------------------------------------------ launch
 template <int BLOCK_N>
 static cudaError_t launch_fprop_t(const FpropParams& p, int num_sms, cudaStream_t stream) {
@@ -1435,7 +1598,24 @@ static cudaError_t launch_wgrad_t(const WgradParams& p, cudaStream_t stream) {
   return cudaGetLastError();
 }
 
+static cudaError_t launch_wgrad2(const WgradParams& p, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kW2SmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid(2, p.taps, p.splits);
+  wgrad2_kernel<<<grid, 256, kW2SmemBytes, stream>>>(p);
+  count_launch(1);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_wgrad(const WgradParams& p, int block_n, cudaStream_t stream) {
+  // CTA pairs for the full 256 x 256 tiles (both m-blocks of one (tap, split) share the B tile)
+  if (g_pair_mode && block_n == 256 && p.m_blocks == 2 && p.n_blocks == 1 && !p.fold_img && !p.upper_only &&
+      !p.b_box_tap && p.a_boxes != 1 && p.m_valid == 256 && p.n_valid == 256 && (p.o_row & 7) == 0)
+    return launch_wgrad2(p, stream);
   switch (block_n) {
     case 64: return launch_wgrad_t<64>(p, stream);
     case 128: return launch_wgrad_t<128>(p, stream);
