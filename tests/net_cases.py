@@ -333,6 +333,47 @@ def case_translate_graph(b=3, s=64, nd=4, seed=0):
     return res, ok
 
 
+def case_epoch_change_and_checkpoint(b=2, s=64, nd=3, seed=0):
+    """Trainer life cycle around the captured graphs: a new epoch (new loss weights) and an LR-scheduler
+    step re-capture; save_models / load_models into a fresh trainer reproduces the next step (weights,
+    Adam moments and step counts, EMA) of the original."""
+    import tempfile
+    from msig_b200 import trainer as T
+    vgg_sd = O.seeded_vgg_state()
+    batch = O.synthetic_batch(b, s, nd)
+    torch.manual_seed(seed)
+    tr = T.MultiDomainStyleCycleGAN(torch.device(DEV), 200, 2e-4, 1e-4, dict(O.DEFAULT_LOSS_WEIGHTS), nd, vgg_state=vgg_sd)
+    res, ok = {}, True
+    for epoch in (0, 0, 0, 1, 1, 1):            # eager, capture, replay; new epoch: eager, capture, replay
+        out = tr.train_step(batch, epoch)
+        ok = ok and all(bool(torch.isfinite(v)) for v in out.values())
+    w0 = tr.weight_scheduler.get_current_weights(0, {}, record=False)["cycle"]
+    w1 = tr.weight_scheduler.get_current_weights(1, {}, record=False)["cycle"]
+    res["weights_epoch0_1"] = [w0, w1]
+    ok = ok and abs(w1 / w0 - 2.0) < 1e-6       # warm-up factor (epoch+1)/10 (utils.py:117-121)
+    tr.g_scheduler.step(); tr.d_scheduler.step()          # lr changes -> new graph key
+    out = tr.train_step(batch, 1)
+    ok = ok and tr._graph is None and tr.g_optimizer.step_count == 7
+    with tempfile.TemporaryDirectory() as d:
+        tr.save_models(d)
+        torch.manual_seed(seed + 99)            # different init: everything must come from the checkpoint
+        tr2 = T.MultiDomainStyleCycleGAN(torch.device(DEV), 200, 2e-4, 1e-4, dict(O.DEFAULT_LOSS_WEIGHTS), nd, vgg_state=vgg_sd)
+        tr2.load_models(d)
+    ok = ok and tr2.g_optimizer.step_count == 7 and tr2.d_optimizer.step_count == 7
+    a = tr.train_step(batch, 1)
+    bb = tr2.train_step(batch, 1)
+    torch.cuda.synchronize()
+    for k in a:
+        e = abs(float(a[k]) - float(bb[k])) / max(abs(float(a[k])), 1e-6)
+        res[f"resume.{k}"] = e
+        ok = ok and e <= 2e-3
+    worst = max((p.detach() - q.detach()).abs().max().item()
+                for p, q in zip(tr.G_A2B.parameters(), tr2.G_A2B.parameters()))
+    res["resume.param_max_abs_diff"] = worst
+    ok = ok and worst <= 2.5 * 1.99e-4          # one Adam step apart at most (sign flips of tiny gradients)
+    return res, ok
+
+
 CASES = {
     "adain_module": case_adain_module,
     "generator_b2_s64": lambda: case_generator(2, 64),
@@ -345,4 +386,5 @@ CASES = {
     "train_step_b2_s64": lambda: case_train_step(2, 64, 3, 2),
     "train_step_graph_vs_eager": case_graph_vs_eager,
     "translate_graph_vs_eager": case_translate_graph,
+    "epoch_change_and_checkpoint": case_epoch_change_and_checkpoint,
 }
