@@ -1,11 +1,20 @@
-// tcgen05 implicit-GEMM kernels for sm_100a.
+// tcgen05 implicit-GEMM kernels for sm_100a (TMA-staged operands, TMEM accumulators, mbarrier pipelines).
 //
-//   fprop_kernel<BLOCK_N>: persistent, warp-specialised. Warp 0 = TMA producer, warp 1 = MMA
-//     issuer (one elected lane), warp 2 = TMEM allocator, warps 4..7 = epilogue. The fp32
-//     accumulator (128 pixels x BLOCK_N channels) lives in TMEM and is double buffered so the
-//     epilogue of tile i overlaps the main loop of tile i+1.
-//   wgrad_kernel<BLOCK_N>: one 128 x BLOCK_N output tile per CTA, K = pixels, both operands are
-//     pixel-major NHWC tiles consumed as MN-major UMMA operands; split-K over pixel blocks.
+//   fprop_kernel<BLOCK_N>   persistent, warp-specialised (warp 0 TMA producer, warp 1 MMA issuer, warp 2
+//                           TMEM allocator, warps 4..11 epilogue); the 128 x BLOCK_N fp32 accumulator is
+//                           double buffered in TMEM so the epilogue of tile i overlaps the main loop of
+//                           tile i+1. Epilogue: alpha / bias / residual / activation mask / activation,
+//                           fused per-(image, channel) reductions, 256-bit loads and stores.
+//   fprop2_kernel           the same GEMM for 256-wide tiles on a CTA pair (cluster of 2, cta_group::2):
+//                           each CTA stages half of the weight tile (the 1-CTA kernel sits on the L2 roof).
+//   fprop_ring64_kernel     64-channel stride-1 layers: resident filter, strip ring shared by output rows,
+//                           horizontal taps as row-shifted descriptors (also the row-patch 7x7 convs and
+//                           the phases of the 128 -> 64 transposed conv / stride-2 dgrad).
+//   fprop_rowfold_kernel    <= 4 output channels: horizontal taps folded into N, shift-add epilogue.
+//   fprop_strip16_kernel    earlier narrow-output variant (kept behind msig_conv2d_fwd for k <= 16).
+//   wgrad_kernel<BLOCK_N>   one 128 x BLOCK_N tile per CTA, K = pixels, both operands pixel-major NHWC tiles
+//                           consumed as MN-major UMMA operands; split-K into fp32 partials.
+//   wgrad2_kernel           the 256 x 256 tile on a CTA pair (cta_group::2).
 //
 // Reference ops these replace: every nn.Conv2d / nn.ConvTranspose2d / nn.Linear in
 // /root/reference/model.py:18,45,48,72-75,84,131-141,165,183 and the VGG convs + torch.mm Gram of
