@@ -26,7 +26,7 @@ extern "C" {
 
 #define MSIG_VERSION 100
 
-enum { MSIG_OK = 0, MSIG_ERR_ARG = -1, MSIG_ERR_CUDA = -2, MSIG_ERR_UNSUPPORTED = -3, MSIG_ERR_NCCL = -4 };
+enum { MSIG_OK = 0, MSIG_ERR_ARG = -1, MSIG_ERR_CUDA = -2, MSIG_ERR_UNSUPPORTED = -3 };
 
 enum { MSIG_ACT_NONE = 0, MSIG_ACT_RELU = 1, MSIG_ACT_LRELU = 2, MSIG_ACT_TANH = 3 };
 enum { MSIG_AUX_NONE = 0, MSIG_AUX_ADD = 1, MSIG_AUX_RELU_MASK = 2, MSIG_AUX_LRELU_MASK = 3 };
@@ -37,7 +37,6 @@ int msig_init(int device);               /* binds the device, resolves cuTensorM
 int msig_version(void);
 const char* msig_last_error(void);       /* thread-local */
 int msig_sm_count(void);
-int msig_debug_set_strip_mode(int mode);  /* test hook: 0 = per-tap kernel, 1 = strip kernel (default) for the 7x7 64->3 conv */
 int msig_debug_set_ring_mode(int on);     /* test hook: strip-ring kernel for 64-channel stride-1 layers, default on */
 int msig_debug_set_pair_mode(int on);     /* test hook: CTA-pair (tcgen05 cta_group::2) kernel for 256-wide conv tiles, default on */
 long long msig_kernel_launches(void);    /* kernels launched by this library since load */
@@ -199,11 +198,7 @@ int msig_patch_wgrad(const msig_wpack_desc* d, int64_t rows, const void* a_rows_
                      float* dw, int accumulate, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- reflect padding of NHWC bf16 (7x7 reflect conv on 64 channels, model.py:141) -------- */
-int msig_reflect_pad_fwd(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad,
-                         void* y, void* stream);
-int msig_reflect_pad_bwd(const void* dy, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad,
-                         void* dx, void* stream);
-/* Same adjoint for an fp32 NCHW gradient (image side of the reflect-padded first conv, model.py:131):
+/* Adjoint of a reflect padding for an fp32 NCHW gradient (image side of the reflect-padded first conv, model.py:131):
  * dx[n,c,h,w] = sum of dy_padded[n,c,.,.] over the padded positions that mirror onto (h,w). */
 int msig_reflect_fold_nchw(const float* dy_padded, int32_t n, int32_t c, int32_t h, int32_t w, int32_t pad,
                            float* dx, void* stream);
@@ -231,7 +226,7 @@ int msig_norm_act_bwd(const void* dy, const void* x, const float* mean, const fl
 /* The same two kernels with the reflect padding of the generator's last conv (model.py:141) fused in: the
  * forward writes act(x*scale+shift) straight into the reflect-padded buffer [n][h+2p][w+2p][c] (interior
  * plus mirrored border copies); the backward reads dy through the fold of the padded gradient
- * [n][h+2p][w+2p][c]. They replace msig_reflect_pad_fwd / msig_reflect_pad_bwd and one full pass each. */
+ * [n][h+2p][w+2p][c]: no separate pad / fold pass exists. */
 int msig_norm_act_fwd_pad(const void* x, const float* scale, const float* shift, int32_t act, float slope,
                           int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad, void* y_padded,
                           void* stream);
@@ -258,10 +253,11 @@ int msig_norm_bwd_from_partials(const float* partial, int32_t n, int32_t rows_pe
 /* dz = dy * act'(y) (ReLU / LeakyReLU), bf16 */
 int msig_act_bwd(const void* dy, const void* y, int32_t act, float slope, int64_t numel, void* dz,
                  void* stream);
-/* out = a + b (bf16) */
-int msig_add_bf16(const void* a, const void* b, int64_t numel, void* out, void* stream);
-/* bias gradient: db[c] (+)= sum over rows of dy[rows][c] (bf16 rows, fp32 out) */
-int msig_colsum(const void* dy, int64_t rows, int32_t c, float* db, int accumulate, void* stream);
+/* bias gradient: db[c] (+)= sum over rows of dy[rows][c] (bf16 rows, fp32 out). Deterministic two-stage
+ * sum (per-block partials in the workspace, folded in block order by the last block; no fp32 atomics). */
+size_t msig_colsum_workspace(int64_t rows, int32_t c);
+int msig_colsum(const void* dy, int64_t rows, int32_t c, float* db, int accumulate, void* workspace,
+                size_t workspace_bytes, void* stream);
 /* MaxPool2d(2) on NHWC bf16 (losses.py pool_2 / pool_4) */
 int msig_maxpool2_fwd(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* y, void* stream);
 int msig_maxpool2_bwd(const void* dy, const void* x, const void* y, int32_t n, int32_t h, int32_t w,
@@ -271,39 +267,57 @@ int msig_avgpool_fwd(const void* x, int32_t n, int32_t hw, int32_t c, void* y, v
 int msig_avgpool_bwd(const void* dy, int32_t n, int32_t hw, int32_t c, void* dx, void* stream);
 /* per-sample head selection (model.py:112-116, 208-212): out[b, :] = all[b, idx[b], :] over a
  * [n, heads*per_head] fp32 row (SE) or [n, pix, heads_pad] (D); the backward writes zeros to the
- * unselected heads. idx is int64 like the reference's domain_idx. */
+ * unselected heads. idx is int64 like the reference's domain_idx; `heads` = the number of real heads
+ * (<= heads_ld, the padded stride): negative indices wrap like torch's, an index outside [-heads, heads)
+ * never reads out of bounds -- the selected output is NaN and the backward routes nothing. */
 int msig_head_gather(const float* all, const int64_t* idx, int32_t n, int32_t pix, int32_t heads_ld,
-                     int32_t per_head, int32_t head_major, float* out, void* stream);
+                     int32_t heads, int32_t per_head, int32_t head_major, float* out, void* stream);
 int msig_head_scatter(const float* dout, const int64_t* idx, int32_t n, int32_t pix, int32_t heads_ld,
-                      int32_t per_head, int32_t head_major, float* dall, void* stream);
+                      int32_t heads, int32_t per_head, int32_t head_major, float* dall, void* stream);
 /* dtype / layout converters at the module surface */
 int msig_f32_to_bf16(const float* x, int64_t numel, void* y, void* stream);
 int msig_bf16_to_f32(const void* x, int64_t numel, float* y, void* stream);
 int msig_tanh_bwd(const float* dy, const float* y, int64_t numel, float* dz, void* stream);
 /* sum over (n, h, w) of an fp32 NCHW tensor per channel (bias grad of the final conv) */
+size_t msig_nchw_chansum_workspace(int32_t n, int32_t c, int64_t hw);
 int msig_nchw_chansum(const float* x, int32_t n, int32_t c, int64_t hw, int64_t img_stride, float* out,
-                      int accumulate, void* stream);   /* img_stride: elements between images (c*hw if dense) */
+                      int accumulate, void* workspace, size_t workspace_bytes,
+                      void* stream);   /* img_stride: elements between images (c*hw if dense); deterministic */
 
 /* ---- losses (trainer.py:50-52, losses.py:70-98) ---------------------------------------------
  * Forward kernels write the mean-reduced loss (fp32 device scalar). Backward kernels write
  * d(loss)/da * (*gscale), where gscale is the upstream gradient as a DEVICE scalar, so no host
- * synchronisation is needed anywhere in a training step. */
-int msig_l1_loss_f32_fwd(const float* a, const float* b, int64_t numel, float* loss, void* stream);
+ * synchronisation is needed anywhere in a training step. The reductions are deterministic (per-block
+ * partial sums in `workspace`, folded in a fixed order by the last block; no floating-point atomics):
+ * msig_reduce_workspace() bytes cover every 1-D loss kernel and msig_sumsq. */
+size_t msig_reduce_workspace(void);
+int msig_l1_loss_f32_fwd(const float* a, const float* b, int64_t numel, float* loss, void* workspace,
+                         size_t workspace_bytes, void* stream);
 int msig_l1_loss_f32_bwd(const float* a, const float* b, int64_t numel, const float* gscale,
                          float* grad_a, void* stream);                   /* nn.L1Loss on images */
-int msig_l1_loss_bf16_fwd(const void* a, const void* b, int64_t numel, float* loss, void* stream);
+int msig_l1_loss_bf16_fwd(const void* a, const void* b, int64_t numel, float* loss, void* workspace,
+                          size_t workspace_bytes, void* stream);
 int msig_l1_loss_bf16_bwd(const void* a, const void* b, int64_t numel, const float* gscale,
                           const void* aux, void* grad_a, void* stream);  /* F.l1_loss on VGG features; (+ aux) */
-int msig_mse_const_fwd(const float* a, float target, int64_t numel, float* loss, void* stream);
+int msig_mse_const_fwd(const float* a, float target, int64_t numel, float* loss, void* workspace,
+                       size_t workspace_bytes, void* stream);
 int msig_mse_const_bwd(const float* a, float target, int64_t numel, const float* gscale,
                        float* grad_a, void* stream);                     /* nn.MSELoss vs ones / zeros */
+/* nn.MSELoss against a target TENSOR (trainer.py:84-86 builds `valid` / `fake` tensors): no host read of
+ * the target is needed when a caller keeps the reference's calling convention. */
+int msig_mse_loss_fwd(const float* a, const float* target, int64_t numel, float* loss, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int msig_mse_loss_bwd(const float* a, const float* target, int64_t numel, const float* gscale,
+                      float* grad_a, void* stream);
 /* Gram matrix (losses.py:70-78): f [n,h,w,c] bf16 -> G [n*c][n*c] fp32 = F F^T / (n*c*h*w), batch
  * folded into rows exactly like the reference's view(a*b, c*d). */
 size_t msig_gram_workspace(int32_t n, int32_t h, int32_t w, int32_t c);
 int msig_gram_fwd(const void* f, int32_t n, int32_t h, int32_t w, int32_t c, float* gram,
                   void* workspace, size_t workspace_bytes, void* stream);
 /* loss = mean |G_a - G_b|; ssym (bf16 [dim][dim]) = sign(D) + sign(D)^T, D = G_a - G_b. */
+size_t msig_gram_l1_workspace(int32_t dim);
 int msig_gram_l1(const float* ga, const float* gb, int32_t dim, float* loss, int accumulate, void* ssym,
+                 void* workspace, size_t workspace_bytes,
                  void* stream);   /* accumulate=1: loss += (sum over the five taps, losses.py:84-89) */
 /* df = alpha * (*gscale) * ssym * F (+ aux): gradient of the style term w.r.t. the generated
  * features; alpha = 1 / (dim^2 * n*c*h*w) supplied by the caller. */
@@ -316,7 +330,7 @@ int msig_colsum_f32(const float* x, int64_t rows, int32_t c, int64_t ld, float* 
 /* ---- optimizer-side multi-tensor ops on flat fp32 buffers (trainer.py:127-134,152-153;
  *      utils.py:80-91): global grad-norm clip + Adam + EMA + in one pass ------------------- */
 int msig_sumsq(const float* x, int64_t numel, float* out /* fp32 scalar, (+)= */, int accumulate,
-               void* stream);
+               void* workspace /* msig_reduce_workspace() bytes */, size_t workspace_bytes, void* stream);
 int msig_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq,
                    float* ema /* may be NULL */, int64_t numel, const float* grad_sumsq, float max_norm,
                    float grad_scale, float lr, float beta1, float beta2, float eps, int32_t step,

@@ -8,8 +8,8 @@
 namespace msig {
 
 static thread_local char g_err[512] = "";
-static int g_sm_count = 0;
-static int g_device = -1;
+constexpr int kMaxDevices = 64;
+static int g_sm_counts[kMaxDevices] = {0};   // per device, filled by msig_init(device)
 static EncodeTiledFn g_encode = nullptr;
 static std::mutex g_init_mu;
 
@@ -20,7 +20,11 @@ int set_error(int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
-int sm_count() { return g_sm_count; }
+int sm_count() {                              // SM count of the CURRENT device (0 before its msig_init)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  return g_sm_counts[dev];
+}
 bool context_ready() { return g_encode != nullptr; }
 EncodeTiledFn encode_tiled() { return g_encode; }
 
@@ -32,7 +36,7 @@ extern "C" {
 
 int msig_version(void) { return MSIG_VERSION; }
 const char* msig_last_error(void) { return g_err; }
-int msig_sm_count(void) { return g_sm_count; }
+int msig_sm_count(void) { return sm_count(); }
 long long msig_kernel_launches(void) { return igemm_kernel_launches(); }
 
 int msig_init(int device) {
@@ -42,16 +46,16 @@ int msig_init(int device) {
   if (e != cudaSuccess || count == 0)
     return set_error(MSIG_ERR_CUDA, "msig_init: no CUDA device (%s); this library has no CPU path",
                      cudaGetErrorString(e));
-  if (device < 0 || device >= count) return set_error(MSIG_ERR_ARG, "msig_init: bad device %d", device);
-  MSIG_CHECK_CUDA(cudaSetDevice(device));
+  if (device < 0 || device >= count || device >= kMaxDevices)
+    return set_error(MSIG_ERR_ARG, "msig_init: bad device %d", device);
+  // The caller's current device is left untouched: launches go to the stream argument's device.
   cudaDeviceProp prop;
   MSIG_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
   if (prop.major != 10)
     return set_error(MSIG_ERR_UNSUPPORTED,
                      "msig_init: device %d is sm_%d%d; this library is built for sm_100a only", device,
                      prop.major, prop.minor);
-  g_sm_count = prop.multiProcessorCount;
-  g_device = device;
+  g_sm_counts[device] = prop.multiProcessorCount;
   if (g_encode == nullptr) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;

@@ -8,7 +8,6 @@
 
 namespace msig {
 
-static int g_strip_mode = 1;   // 0: per-tap kernel, 1: strip kernel
 
 // ------------------------------------------------------------------------ phase tables
 // k=4, s=2, p=1: output row 2i+py of a transposed conv (or input row of a stride-2 conv's dgrad)
@@ -452,20 +451,6 @@ static int run_conv(const void* in, int n, int h, int w, int c, int k, int R, in
     if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "fprop(ring) launch: %s", cudaGetErrorString(ce));
     return MSIG_OK;
   }
-  // Narrow-output "valid" stride-1 conv on 64 channels (the generator's final 7x7 conv on the
-  // pre-padded activation): resident filter + one strip per filter row instead of one tile per tap.
-  if (g_strip_mode != 0 && stride == 1 && pad_t == 0 && pad_l == 0 && c == 64 && block_n == 16 && R * S <= 49 &&
-      S <= 7 && R * S >= 9 && p.aux_mode == AUX_NONE) {
-    p.TW = 128; p.TH = 1;
-    p.tiles_h = OH;
-    p.tiles_w = static_cast<int>(ceil_div(OW, 128));
-    p.strip_r = R; p.strip_s = S;
-    ActView v{in, c, w, h, n, c, int64_t(w) * c, int64_t(h) * w * c};
-    if ((rc = make_act_map(&p.tmA[1], v, 128 + S - 1, 1)) != MSIG_OK) return rc;
-    cudaError_t ce = launch_fprop_strip16(p, sm_count(), st);
-    if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "fprop(strip) launch: %s", cudaGetErrorString(ce));
-    return MSIG_OK;
-  }
   cudaError_t ce = launch_fprop(p, block_n, sm_count(), st);
   if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "fprop launch: %s", cudaGetErrorString(ce));
   return MSIG_OK;
@@ -606,11 +591,6 @@ int msig_debug_set_pair_mode(int on) {
 }
 
 // Test hook: selects the kernel variant of the narrow-output 7x7 conv (see run_conv).
-int msig_debug_set_strip_mode(int mode) {
-  g_strip_mode = mode;
-  return MSIG_OK;
-}
-
 size_t msig_wpack_elems(const msig_wpack_desc* d) {
   if (!d) return 0;
   PackGeom g = make_pack_geom(d, 0, 0);

@@ -11,7 +11,6 @@
 //                           horizontal taps as row-shifted descriptors (also the row-patch 7x7 convs and
 //                           the phases of the 128 -> 64 transposed conv / stride-2 dgrad).
 //   fprop_rowfold_kernel    <= 4 output channels: horizontal taps folded into N, shift-add epilogue.
-//   fprop_strip16_kernel    earlier narrow-output variant (kept behind msig_conv2d_fwd for k <= 16).
 //   wgrad_kernel<BLOCK_N>   one 128 x BLOCK_N tile per CTA, K = pixels, both operands pixel-major NHWC tiles
 //                           consumed as MN-major UMMA operands; split-K into fp32 partials.
 //   wgrad2_kernel           the 256 x 256 tile on a CTA pair (cta_group::2).
@@ -607,157 +606,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpropThreads, 1)
     tmem_dealloc_2sm(tmem_base, 512);
   }
 }
-
-// ------------------------------------------------------------------------------------ strip
-// Narrow-output stride-1 "valid" convolution (the generator's final 7x7 64->3 conv on the reflect-
-// padded activation, model.py:141), N = 16 (3 valid). The per-tap kernel above re-reads every
-// activation row once per filter tap (49x here) and is bound by L2->SM traffic. Here the whole packed
-// filter (R*S taps x 16 x 64 bf16) stays resident in shared memory and one TMA box per filter ROW
-// brings a strip of 128 + S - 1 pixels; the S horizontal taps are S MMAs whose A descriptors start
-// s rows (s*128 B) into the same strip. Activation traffic drops S-fold, weight traffic to zero.
-constexpr int kStripStages = 7;
-constexpr int kStripBytes = 17408;        // (128 + 7 - 1) rows x 128 B = 17152, padded to 17 KiB
-constexpr int kStripMaxTaps = 49;
-constexpr int kStripSmemBytes = kStripMaxTaps * 2048 + kStripStages * kStripBytes + 1024 + 256;
-
-__global__ void __launch_bounds__(256, 1) fprop_strip16_kernel(const __grid_constant__ FpropParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  const uint32_t raw_addr = smem_u32(smem_raw);
-  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* wsm = smem;                                   // taps x [16][64] bf16, 2 KiB each
-  uint8_t* strips = smem + kStripMaxTaps * 2048;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(strips + kStripStages * kStripBytes);
-  uint64_t* empty_bar = full_bar + kStripStages;
-  uint64_t* tfull_bar = empty_bar + kStripStages;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* wfull_bar = tempty_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const int R = p.strip_r, S = p.strip_s;
-  const int taps = R * S;
-  const uint32_t strip_tx = static_cast<uint32_t>(kTileM + S - 1) * 128u;
-
-  if (warp == 0 && lane == 0) {
-    prefetch_tmap(&p.tmA[1]);
-    prefetch_tmap(&p.tmB);
-  }
-  if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStripStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 128);
-    }
-    mbar_init(wfull_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 2) tmem_alloc(tmem_slot, 32);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const int total = p.n_img * p.tiles_h * p.tiles_w;
-
-  if (warp == 0) {
-    if (elect_one()) {
-      mbar_expect_tx(wfull_bar, static_cast<uint32_t>(taps) * 2048u);
-      for (int t = 0; t < taps; ++t) tma_load_2d(wsm + t * 2048, &p.tmB, wfull_bar, t * kBlockK, 0);
-    }
-    __syncwarp();
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      const int tw = tile % p.tiles_w;
-      const int mt = tile / p.tiles_w;
-      const int oh = mt % p.tiles_h;
-      const int img = mt / p.tiles_h;
-      for (int r = 0; r < R; ++r) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        if (elect_one()) {
-          mbar_expect_tx(&full_bar[stage], strip_tx);
-          tma_load_4d(strips + stage * kStripBytes, &p.tmA[1], &full_bar[stage], 0, tw * kTileM, oh + r, img);
-        }
-        __syncwarp();
-        if (++stage == kStripStages) {
-          stage = 0;
-          phase ^= 1u;
-        }
-      }
-    }
-  } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(kTileM, 16, 0, 0);
-    mbar_wait(wfull_bar, 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    const uint32_t w_addr = smem_u32(wsm);
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      mbar_wait(&tempty_bar[as], aphase ^ 1u);
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * 16;
-      for (int r = 0; r < R; ++r) {
-        mbar_wait(&full_bar[stage], phase);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t sa = smem_u32(strips + stage * kStripBytes);
-          for (int s = 0; s < S; ++s) {
-            const uint64_t da = make_smem_desc(sa + s * 128, 0, 1024);   // s rows into the strip
-            const uint64_t db = make_smem_desc(w_addr + (r * S + s) * 2048, 0, 1024);
-#pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (r > 0 || s > 0 || k > 0) ? 1u : 0u);
-          }
-          umma_commit(&empty_bar[stage]);
-          if (r == R - 1) umma_commit(&tfull_bar[as]);
-        }
-        __syncwarp();
-        if (++stage == kStripStages) {
-          stage = 0;
-          phase ^= 1u;
-        }
-      }
-    }
-  } else if (warp >= 4) {
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
-      const int tw = tile % p.tiles_w;
-      const int mt = tile / p.tiles_w;
-      const int oh = mt % p.tiles_h;
-      const int img = mt / p.tiles_h;
-      const int ow = tw * kTileM + row;
-      const bool row_valid = (oh < p.OH) && (ow < p.OW);
-      const int64_t out_off = img * p.o_sn + oh * p.o_sh + ow * p.o_sw;
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
-      uint32_t r16[16];
-      tmem_ld_32x16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 16, r16);
-      tmem_ld_wait();
-      uint4 av16[2], zv16[2];
-      fprop_epilogue_chunk<16, false>(p, r16, av16, zv16, 0, row_valid, out_off, alpha);
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 32);
-  }
-}
-
 
 // ------------------------------------------------------------------------------------ row-fold
 constexpr int kRfRing = 8;                       // strips resident (>= R + 1)
@@ -1478,16 +1326,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) wgrad2_kerne
 }
 
 // ------------------------------------------------------------------------------------ launch
+// cudaFuncSetAttribute is per device: one bit per device ordinal records where it has been applied.
+static int current_dev_bit() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d & 63;
+}
+static bool attr_needed(uint64_t mask) { return ((mask >> current_dev_bit()) & 1ull) == 0; }
+static void attr_done(uint64_t& mask) { mask |= 1ull << current_dev_bit(); }
+
 template <int BLOCK_N>
 static cudaError_t launch_fprop_t(const FpropParams& p, int num_sms, cudaStream_t stream) {
   using Cfg = FpropCfg<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static uint64_t attr_devs = 0;
+  if (attr_needed(attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(fprop_kernel<BLOCK_N>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_done(attr_devs);
   }
   const int total = p.n_img * p.tiles_h * p.tiles_w * p.phases * p.n_blocks;
   const int grid = total < num_sms ? total : num_sms;
@@ -1501,11 +1358,11 @@ static bool g_pair_mode = true;
 void set_pair_mode(bool on) { g_pair_mode = on; }
 
 static cudaError_t launch_fprop2(const FpropParams& p, int num_sms, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static uint64_t attr_devs = 0;
+  if (attr_needed(attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(fprop2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, k2SmemBytes);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_done(attr_devs);
   }
   const int pairs = (p.n_img * p.tiles_h * p.tiles_w / 2) * p.n_blocks;
   int clusters = num_sms / 2;
@@ -1534,30 +1391,13 @@ cudaError_t launch_fprop(const FpropParams& p, int block_n, int num_sms, cudaStr
   }
 }
 
-cudaError_t launch_fprop_strip16(const FpropParams& p, int num_sms, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(fprop_strip16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kStripSmemBytes);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  if (p.strip_r * p.strip_s > kStripMaxTaps || (kTileM + p.strip_s - 1) * 128 > kStripBytes) return cudaErrorInvalidValue;
-  const int total = p.n_img * p.tiles_h * p.tiles_w;
-  const int grid = total < num_sms ? total : num_sms;
-  if (grid <= 0) return cudaSuccess;
-  fprop_strip16_kernel<<<grid, 256, kStripSmemBytes, stream>>>(p);
-  count_launch(1);
-  return cudaGetLastError();
-}
-
 cudaError_t launch_rowfold(const RowfoldParams& p, int num_sms, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static uint64_t attr_devs = 0;
+  if (attr_needed(attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(fprop_rowfold_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kRfSmemBytes);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_done(attr_devs);
   }
   if (p.R < 1 || p.R > kRfMaxR || p.S < 1 || p.S * 4 > 32 || p.n_valid > 4 || p.R + 1 > kRfRing)
     return cudaErrorInvalidValue;
@@ -1570,12 +1410,12 @@ cudaError_t launch_rowfold(const RowfoldParams& p, int num_sms, cudaStream_t str
 }
 
 cudaError_t launch_fprop_ring64(const FpropParams& p, int num_sms, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static uint64_t attr_devs = 0;
+  if (attr_needed(attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(fprop_ring64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          kRingSmemBytes);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_done(attr_devs);
   }
   const int cbs = p.ring_cb > 1 ? p.ring_cb : 1;
   if (p.strip_r < 1 || p.strip_s < 1 || p.strip_r * p.strip_s * cbs > kRingMaxTaps || p.strip_r * p.strip_s > 16 ||
@@ -1593,13 +1433,13 @@ cudaError_t launch_fprop_ring64(const FpropParams& p, int num_sms, cudaStream_t 
 template <int BLOCK_N>
 static cudaError_t launch_wgrad_t(const WgradParams& p, cudaStream_t stream) {
   using Cfg = WgradCfg<BLOCK_N>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static uint64_t attr_devs = 0;
+  if (attr_needed(attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(wgrad_kernel<BLOCK_N>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Cfg::kSmemBytes);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_done(attr_devs);
   }
   dim3 grid(p.m_blocks * p.n_blocks, p.taps, p.splits);
   wgrad_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(p);
@@ -1608,11 +1448,11 @@ static cudaError_t launch_wgrad_t(const WgradParams& p, cudaStream_t stream) {
 }
 
 static cudaError_t launch_wgrad2(const WgradParams& p, cudaStream_t stream) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static uint64_t attr_devs = 0;
+  if (attr_needed(attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kW2SmemBytes);
     if (e != cudaSuccess) return e;
-    attr_set = true;
+    attr_done(attr_devs);
   }
   dim3 grid(2, p.taps, p.splits);
   wgrad2_kernel<<<grid, 256, kW2SmemBytes, stream>>>(p);

@@ -120,7 +120,6 @@ cudaError_t launch_fprop(const FpropParams& p, int block_n, int num_sms, cudaStr
 cudaError_t launch_rowfold(const RowfoldParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_fprop_ring64(const FpropParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_wgrad(const WgradParams& p, int block_n, cudaStream_t stream);
-cudaError_t launch_fprop_strip16(const FpropParams& p, int num_sms, cudaStream_t stream);
 bool fprop_uses_pairs(const FpropParams& p, int block_n);
 void set_pair_mode(bool on);   // test hook: CTA-pair (cta_group::2) kernel for 256-wide tiles on/off
 int igemm_kernel_launches();  // launches issued since process start (bench: gpu_launches)

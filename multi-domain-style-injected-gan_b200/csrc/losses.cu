@@ -13,17 +13,41 @@ __device__ __forceinline__ float warp_sum_l(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-// block-wide sum -> one atomicAdd (scaled) per block
-__device__ __forceinline__ void block_atomic_add(float v, float scale, float* out) {
-  __shared__ float ws[32];
+// Deterministic grid-wide sum (no floating-point atomics): every block writes its partial sum to
+// `partial[block]`; the last block to arrive (integer ticket, reset for the next launch) adds all partials
+// in a fixed order and writes out = (accumulate ? out : 0) + scale * total. The summation order depends
+// on the grid size only, so an eager step and its CUDA-graph replay produce identical bits.
+// Call from ALL threads of a 1-D block of 256 threads (tid = linear thread id, nblocks = grid size).
+__device__ __forceinline__ float block_sum_256(float v, int tid) {
+  __shared__ float ws[8];
+  __syncthreads();                       // (ws may still be read by a previous call)
   v = warp_sum_l(v);
-  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+  if ((tid & 31) == 0) ws[tid >> 5] = v;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    float t = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.f;
-    t = warp_sum_l(t);
-    if (threadIdx.x == 0) atomicAdd(out, t * scale);
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += ws[i];
+  return t;                              // every thread holds the block total
+}
+__device__ __forceinline__ void grid_sum_ordered(float v, float scale, float* out, int accumulate,
+                                                 float* partial, unsigned int* ticket, int tid, int block,
+                                                 int nblocks) {
+  __shared__ bool last;
+  const float t = block_sum_256(v, tid);
+  if (tid == 0) {
+    partial[block] = t;
+    __threadfence();
+    const unsigned int k = atomicAdd(ticket, 1u);
+    last = (k == static_cast<unsigned int>(nblocks) - 1u);
+    if (last) *ticket = 0u;
   }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float s = 0.f;
+  for (int i = tid; i < nblocks; i += 256) s += __ldcg(partial + i);
+  s = block_sum_256(s, tid);
+  if (tid == 0) *out = (accumulate ? *out : 0.f) + s * scale;
 }
 __device__ __forceinline__ float sgn(float d) { return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f); }
 
@@ -31,8 +55,9 @@ static inline int lgrid(int64_t work, int threads) {
   return static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(ceil_div(work, threads), 148 * 8)));
 }
 
-__global__ void l1_f32_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
-                                  float inv_n, float* __restrict__ loss) {
+__global__ void __launch_bounds__(256) l1_f32_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                         int64_t n, float inv_n, float* __restrict__ loss,
+                                                         float* __restrict__ partial, unsigned int* ticket) {
   float s = 0.f;
   const int64_t n4 = n / 4;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
@@ -42,7 +67,7 @@ __global__ void l1_f32_fwd_kernel(const float* __restrict__ a, const float* __re
   }
   if (blockIdx.x == 0)
     for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) s += fabsf(a[i] - b[i]);
-  block_atomic_add(s, inv_n, loss);
+  grid_sum_ordered(s, inv_n, loss, 0, partial, ticket, threadIdx.x, blockIdx.x, gridDim.x);
 }
 __global__ void l1_f32_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
                                   float inv_n, const float* __restrict__ gscale, float* __restrict__ g) {
@@ -50,8 +75,10 @@ __global__ void l1_f32_bwd_kernel(const float* __restrict__ a, const float* __re
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
     g[i] = sgn(a[i] - b[i]) * k;
 }
-__global__ void l1_bf16_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
-                                   int64_t groups, float inv_n, float* __restrict__ loss) {
+__global__ void __launch_bounds__(256) l1_bf16_fwd_kernel(const __nv_bfloat16* __restrict__ a,
+                                                          const __nv_bfloat16* __restrict__ b, int64_t groups,
+                                                          float inv_n, float* __restrict__ loss,
+                                                          float* __restrict__ partial, unsigned int* ticket) {
   float s = 0.f;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < groups; i += int64_t(gridDim.x) * blockDim.x) {
     const uint4 ua = reinterpret_cast<const uint4*>(a)[i];
@@ -64,7 +91,7 @@ __global__ void l1_bf16_fwd_kernel(const __nv_bfloat16* __restrict__ a, const __
       s += fabsf(x.x - y.x) + fabsf(x.y - y.y);
     }
   }
-  block_atomic_add(s, inv_n, loss);
+  grid_sum_ordered(s, inv_n, loss, 0, partial, ticket, threadIdx.x, blockIdx.x, gridDim.x);
 }
 __global__ void l1_bf16_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                                    int64_t groups, float inv_n, const float* __restrict__ gscale,
@@ -88,27 +115,31 @@ __global__ void l1_bf16_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __
     reinterpret_cast<uint4*>(g)[i] = uo;
   }
 }
-__global__ void mse_const_fwd_kernel(const float* __restrict__ a, float t, int64_t n, float inv_n,
-                                     float* __restrict__ loss) {
+// mean (a - target)^2; the target is the constant `t` (LSGAN all-ones / all-zeros) or the tensor `b`
+__global__ void __launch_bounds__(256) mse_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                      float t, int64_t n, float inv_n, float* __restrict__ loss,
+                                                      float* __restrict__ partial, unsigned int* ticket) {
   float s = 0.f;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
-    const float d = a[i] - t;
+    const float d = a[i] - (b ? b[i] : t);
     s += d * d;
   }
-  block_atomic_add(s, inv_n, loss);
+  grid_sum_ordered(s, inv_n, loss, 0, partial, ticket, threadIdx.x, blockIdx.x, gridDim.x);
 }
-__global__ void mse_const_bwd_kernel(const float* __restrict__ a, float t, int64_t n, float inv_n,
-                                     const float* __restrict__ gscale, float* __restrict__ g) {
+__global__ void mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float t, int64_t n,
+                               float inv_n, const float* __restrict__ gscale, float* __restrict__ g) {
   const float k = 2.f * inv_n * (gscale ? __ldg(gscale) : 1.f);
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
-    g[i] = (a[i] - t) * k;
+    g[i] = (a[i] - (b ? b[i] : t)) * k;
 }
 
 // loss = mean |Ga - Gb| over the full symmetric matrix; ssym = 2*sign(D) (= sign(D) + sign(D)^T).
 // Only 32x32 tiles on/above the diagonal are read (the Gram kernel skips tiles below it); a block
 // below the diagonal reads its mirror tile and transposes it through shared memory (coalesced).
-__global__ void gram_l1_kernel(const float* __restrict__ ga, const float* __restrict__ gb, int dim,
-                               float inv_n, float* __restrict__ loss, __nv_bfloat16* __restrict__ ssym) {
+__global__ void __launch_bounds__(256) gram_l1_kernel(const float* __restrict__ ga, const float* __restrict__ gb,
+                                                      int dim, float inv_n, float* __restrict__ loss, int accumulate,
+                                                      __nv_bfloat16* __restrict__ ssym, float* __restrict__ partial,
+                                                      unsigned int* ticket) {
   __shared__ float tile[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;   // this block: rows by.., cols bx..
@@ -131,16 +162,8 @@ __global__ void gram_l1_kernel(const float* __restrict__ ga, const float* __rest
       ssym[int64_t(i) * dim + j] = __float2bfloat16(2.f * sgn(d));
     }
   }
-  __shared__ float ws[8];
-  s = warp_sum_l(s);
-  const int tid = ty * 32 + tx;
-  if ((tid & 31) == 0) ws[tid >> 5] = s;
-  __syncthreads();
-  if (tid == 0) {
-    float t = 0.f;
-    for (int k = 0; k < 8; ++k) t += ws[k];
-    atomicAdd(loss, t * inv_n);
-  }
+  grid_sum_ordered(s, inv_n, loss, accumulate, partial, ticket, ty * 32 + tx, blockIdx.y * gridDim.x + blockIdx.x,
+                   gridDim.x * gridDim.y);
 }
 
 __global__ void colsum_f32_kernel(const float* __restrict__ x, int64_t rows, int c, int64_t ld,
@@ -152,7 +175,9 @@ __global__ void colsum_f32_kernel(const float* __restrict__ x, int64_t rows, int
   out[ch] = accumulate ? out[ch] + s : s;
 }
 
-__global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out) {
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out,
+                                                    int accumulate, float* __restrict__ partial,
+                                                    unsigned int* ticket) {
   float s = 0.f;
   const int64_t n4 = n / 4;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
@@ -161,7 +186,7 @@ __global__ void sumsq_kernel(const float* __restrict__ x, int64_t n, float* __re
   }
   if (blockIdx.x == 0)
     for (int64_t i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) s += x[i] * x[i];
-  block_atomic_add(s, 1.f, out);
+  grid_sum_ordered(s, 1.f, out, accumulate, partial, ticket, threadIdx.x, blockIdx.x, gridDim.x);
 }
 
 __global__ void counter_inc_kernel(int32_t* c) { *c += 1; }
@@ -208,10 +233,27 @@ using namespace msig;
 
 extern "C" {
 
-int msig_l1_loss_f32_fwd(const float* a, const float* b, int64_t numel, float* loss, void* stream) {
+// Reduction scratch of the loss kernels: [blocks] fp32 partial sums followed by one u32 ticket.
+static inline float* ws_partial(void* ws) { return reinterpret_cast<float*>(ws); }
+static inline unsigned int* ws_ticket(void* ws, int64_t blocks) {
+  return reinterpret_cast<unsigned int*>(reinterpret_cast<float*>(ws) + blocks);
+}
+#define REDUCE_WS_OK(blocks) (workspace != nullptr && workspace_bytes >= (size_t(blocks) + 1) * sizeof(float))
+
+size_t msig_reduce_workspace(void) { return (size_t(148) * 8 + 1) * sizeof(float); }
+size_t msig_gram_l1_workspace(int32_t dim) {
+  const size_t t = static_cast<size_t>(ceil_div(dim, 32));
+  return (t * t + 1) * sizeof(float);
+}
+
+int msig_l1_loss_f32_fwd(const float* a, const float* b, int64_t numel, float* loss, void* workspace,
+                         size_t workspace_bytes, void* stream) {
   MSIG_REQUIRE(a && b && loss && numel > 0, "msig_l1_loss_f32_fwd: bad argument");
-  MSIG_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), ST(stream)));
-  l1_f32_fwd_kernel<<<lgrid(numel / 4 + 1, 256), 256, 0, ST(stream)>>>(a, b, numel, 1.f / numel, loss);
+  const int blocks = lgrid(numel / 4 + 1, 256);
+  MSIG_REQUIRE(REDUCE_WS_OK(blocks), "msig_l1_loss_f32_fwd: workspace too small");
+  MSIG_CHECK_CUDA(cudaMemsetAsync(ws_ticket(workspace, blocks), 0, sizeof(unsigned int), ST(stream)));
+  l1_f32_fwd_kernel<<<blocks, 256, 0, ST(stream)>>>(a, b, numel, 1.f / numel, loss, ws_partial(workspace),
+                                                   ws_ticket(workspace, blocks));
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -224,10 +266,14 @@ int msig_l1_loss_f32_bwd(const float* a, const float* b, int64_t numel, const fl
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
 }
-int msig_l1_loss_bf16_fwd(const void* a, const void* b, int64_t numel, float* loss, void* stream) {
+int msig_l1_loss_bf16_fwd(const void* a, const void* b, int64_t numel, float* loss, void* workspace,
+                          size_t workspace_bytes, void* stream) {
   MSIG_REQUIRE(a && b && loss && numel > 0 && numel % 8 == 0, "msig_l1_loss_bf16_fwd: bad argument");
-  MSIG_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), ST(stream)));
-  l1_bf16_fwd_kernel<<<lgrid(numel / 8, 256), 256, 0, ST(stream)>>>(CBF(a), CBF(b), numel / 8, 1.f / numel, loss);
+  const int blocks = lgrid(numel / 8, 256);
+  MSIG_REQUIRE(REDUCE_WS_OK(blocks), "msig_l1_loss_bf16_fwd: workspace too small");
+  MSIG_CHECK_CUDA(cudaMemsetAsync(ws_ticket(workspace, blocks), 0, sizeof(unsigned int), ST(stream)));
+  l1_bf16_fwd_kernel<<<blocks, 256, 0, ST(stream)>>>(CBF(a), CBF(b), numel / 8, 1.f / numel, loss,
+                                                    ws_partial(workspace), ws_ticket(workspace, blocks));
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -241,29 +287,53 @@ int msig_l1_loss_bf16_bwd(const void* a, const void* b, int64_t numel, const flo
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
 }
-int msig_mse_const_fwd(const float* a, float target, int64_t numel, float* loss, void* stream) {
-  MSIG_REQUIRE(a && loss && numel > 0, "msig_mse_const_fwd: bad argument");
-  MSIG_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), ST(stream)));
-  mse_const_fwd_kernel<<<lgrid(numel, 256), 256, 0, ST(stream)>>>(a, target, numel, 1.f / numel, loss);
+static int mse_fwd(const float* a, const float* b, float target, int64_t numel, float* loss, void* workspace,
+                   size_t workspace_bytes, void* stream, const char* what) {
+  MSIG_REQUIRE(a && loss && numel > 0, "%s: bad argument", what);
+  const int blocks = lgrid(numel, 256);
+  MSIG_REQUIRE(REDUCE_WS_OK(blocks), "%s: workspace too small", what);
+  MSIG_CHECK_CUDA(cudaMemsetAsync(ws_ticket(workspace, blocks), 0, sizeof(unsigned int), ST(stream)));
+  mse_fwd_kernel<<<blocks, 256, 0, ST(stream)>>>(a, b, target, numel, 1.f / numel, loss, ws_partial(workspace),
+                                                ws_ticket(workspace, blocks));
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
 }
+int msig_mse_const_fwd(const float* a, float target, int64_t numel, float* loss, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  return mse_fwd(a, nullptr, target, numel, loss, workspace, workspace_bytes, stream, "msig_mse_const_fwd");
+}
 int msig_mse_const_bwd(const float* a, float target, int64_t numel, const float* gscale, float* grad_a,
                        void* stream) {
   MSIG_REQUIRE(a && grad_a && numel > 0, "msig_mse_const_bwd: bad argument");
-  mse_const_bwd_kernel<<<lgrid(numel, 256), 256, 0, ST(stream)>>>(a, target, numel, 1.f / numel, gscale, grad_a);
+  mse_bwd_kernel<<<lgrid(numel, 256), 256, 0, ST(stream)>>>(a, nullptr, target, numel, 1.f / numel, gscale, grad_a);
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+int msig_mse_loss_fwd(const float* a, const float* target, int64_t numel, float* loss, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  MSIG_REQUIRE(target != nullptr, "msig_mse_loss_fwd: null target");
+  return mse_fwd(a, target, 0.f, numel, loss, workspace, workspace_bytes, stream, "msig_mse_loss_fwd");
+}
+int msig_mse_loss_bwd(const float* a, const float* target, int64_t numel, const float* gscale, float* grad_a,
+                      void* stream) {
+  MSIG_REQUIRE(a && target && grad_a && numel > 0, "msig_mse_loss_bwd: bad argument");
+  mse_bwd_kernel<<<lgrid(numel, 256), 256, 0, ST(stream)>>>(a, target, 0.f, numel, 1.f / numel, gscale, grad_a);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
 }
 int msig_gram_l1(const float* ga, const float* gb, int32_t dim, float* loss, int accumulate, void* ssym,
-                 void* stream) {
+                 void* workspace, size_t workspace_bytes, void* stream) {
   MSIG_REQUIRE(ga && gb && loss && ssym && dim > 0, "msig_gram_l1: bad argument");
-  if (!accumulate) MSIG_CHECK_CUDA(cudaMemsetAsync(loss, 0, sizeof(float), ST(stream)));
   const unsigned t = static_cast<unsigned>(ceil_div(dim, 32));
+  const int64_t blocks = int64_t(t) * t;
+  MSIG_REQUIRE(REDUCE_WS_OK(blocks), "msig_gram_l1: workspace too small");
+  MSIG_CHECK_CUDA(cudaMemsetAsync(ws_ticket(workspace, blocks), 0, sizeof(unsigned int), ST(stream)));
   gram_l1_kernel<<<dim3(t, t), dim3(32, 8), 0, ST(stream)>>>(ga, gb, dim, 1.f / (float(dim) * float(dim)), loss,
-                                                             BF(ssym));
+                                                             accumulate, BF(ssym), ws_partial(workspace),
+                                                             ws_ticket(workspace, blocks));
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -276,10 +346,14 @@ int msig_colsum_f32(const float* x, int64_t rows, int32_t c, int64_t ld, float* 
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
 }
-int msig_sumsq(const float* x, int64_t numel, float* out, int accumulate, void* stream) {
+int msig_sumsq(const float* x, int64_t numel, float* out, int accumulate, void* workspace, size_t workspace_bytes,
+               void* stream) {
   MSIG_REQUIRE(x && out && numel > 0, "msig_sumsq: bad argument");
-  if (!accumulate) MSIG_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(float), ST(stream)));
-  sumsq_kernel<<<lgrid(numel / 4 + 1, 256), 256, 0, ST(stream)>>>(x, numel, out);
+  const int blocks = lgrid(numel / 4 + 1, 256);
+  MSIG_REQUIRE(REDUCE_WS_OK(blocks), "msig_sumsq: workspace too small");
+  MSIG_CHECK_CUDA(cudaMemsetAsync(ws_ticket(workspace, blocks), 0, sizeof(unsigned int), ST(stream)));
+  sumsq_kernel<<<blocks, 256, 0, ST(stream)>>>(x, numel, out, accumulate, ws_partial(workspace),
+                                              ws_ticket(workspace, blocks));
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;

@@ -185,56 +185,7 @@ __global__ void patch_scatter_kernel(msig_patch_geom g, const __nv_bfloat16* __r
   }
 }
 
-// ---------------------------------------------------------------- reflect pad (NHWC bf16)
-__global__ void reflect_pad_fwd_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int c,
-                                       int pad, __nv_bfloat16* __restrict__ y, int64_t groups) {
-  const int cg = c / 8;
-  const int H2 = h + 2 * pad, W2 = w + 2 * pad;
-  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < groups;
-       idx += int64_t(gridDim.x) * blockDim.x) {
-    const int g8 = static_cast<int>(idx % cg);
-    int64_t rem = idx / cg;
-    const int pw = static_cast<int>(rem % W2);
-    rem /= W2;
-    const int ph = static_cast<int>(rem % H2);
-    const int img = static_cast<int>(rem / H2);
-    const int ih = reflect_idx(ph - pad, h), iw = reflect_idx(pw - pad, w);
-    const uint4 v = *reinterpret_cast<const uint4*>(x + ((int64_t(img) * h + ih) * w + iw) * c + g8 * 8);
-    *reinterpret_cast<uint4*>(y + idx * 8) = v;
-  }
-}
-
-__global__ void reflect_pad_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int n, int h, int w, int c,
-                                       int pad, __nv_bfloat16* __restrict__ dx, int64_t groups) {
-  const int cg = c / 8;
-  const int H2 = h + 2 * pad, W2 = w + 2 * pad;
-  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < groups;
-       idx += int64_t(gridDim.x) * blockDim.x) {
-    const int g8 = static_cast<int>(idx % cg);
-    int64_t rem = idx / cg;
-    const int iw = static_cast<int>(rem % w);
-    rem /= w;
-    const int ih = static_cast<int>(rem % h);
-    const int img = static_cast<int>(rem / h);
-    int ph[3], pw[3], nph = 0, npw = 0;
-    ph[nph++] = ih + pad;
-    pw[npw++] = iw + pad;
-    if (ih >= 1 && ih <= pad) ph[nph++] = pad - ih;
-    if (ih <= h - 2 && ih >= h - 1 - pad) ph[nph++] = pad + 2 * (h - 1) - ih;
-    if (iw >= 1 && iw <= pad) pw[npw++] = pad - iw;
-    if (iw <= w - 2 && iw >= w - 1 - pad) pw[npw++] = pad + 2 * (w - 1) - iw;
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int a = 0; a < nph; ++a)
-      for (int b = 0; b < npw; ++b) {
-        float f[8];
-        load8(dy + ((int64_t(img) * H2 + ph[a]) * W2 + pw[b]) * c + g8 * 8, f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += f[j];
-      }
-    store8(dx + idx * 8, acc);
-  }
-}
-
+// ---------------------------------------------------------------- padded image copies
 // fp32 NCHW [n,c,h,w] (c <= 8) -> bf16 [n][h+2p][w+2p+2][8], reflect or zero padding; channels >= c and
 // the two slack columns are zero. One thread per padded pixel (one 16-byte store).
 __global__ void img_pad8_kernel(const float* __restrict__ src, int c, int h, int w, int pad, int reflect,
@@ -715,18 +666,6 @@ __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_
     store8(dz + i * 8, a);
   }
 }
-__global__ void add_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
-                                int64_t groups, __nv_bfloat16* __restrict__ o) {
-  for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < groups;
-       i += int64_t(gridDim.x) * blockDim.x) {
-    float x[8], y[8];
-    load8(a + i * 8, x);
-    load8(b + i * 8, y);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] += y[j];
-    store8(o + i * 8, x);
-  }
-}
 __global__ void f32_to_bf16_kernel(const float* __restrict__ x, int64_t n, __nv_bfloat16* __restrict__ y) {
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
     y[i] = __float2bfloat16(x[i]);
@@ -741,10 +680,15 @@ __global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __res
     dz[i] = dy[i] * (1.f - y[i] * y[i]);
 }
 
-// db[c] (+)= sum_rows dy[rows][c]; block = 256 threads = (c/8 groups) x lanes, atomics on fp32.
+// db[c] (+)= sum_rows dy[rows][c]; block = 256 threads = (c/8 groups) x lanes. Deterministic: every block
+// writes its per-channel partial sums, the last block to arrive (integer ticket) adds them in block order
+// (no floating-point atomics: an eager step and its CUDA-graph replay give identical bias gradients).
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ dy, int64_t rows,
-                                                     int c, int rows_per_block, float* __restrict__ db) {
+                                                     int c, int rows_per_block, float* __restrict__ db,
+                                                     int accumulate, float* __restrict__ partial,
+                                                     unsigned int* ticket) {
   __shared__ float red[8][256 + 1];
+  __shared__ bool is_last;
   const int cg = c / 8;
   const int lanes = 256 / cg;
   const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
@@ -766,13 +710,30 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
     const int gx = ch / 8, j = ch % 8;
     float s = 0.f;
     for (int l = 0; l < lanes; ++l) s += red[j][l * cg + gx];
-    atomicAdd(db + ch, s);
+    partial[int64_t(blockIdx.x) * c + ch] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int t = atomicAdd(ticket, 1u);
+    is_last = (t == gridDim.x - 1u);
+    if (is_last) *ticket = 0u;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  for (int ch = threadIdx.x; ch < c; ch += 256) {
+    float s = 0.f;
+    for (unsigned int k = 0; k < gridDim.x; ++k) s += __ldcg(partial + int64_t(k) * c + ch);
+    db[ch] = (accumulate ? db[ch] : 0.f) + s;
   }
 }
 
-__global__ void nchw_chansum_kernel(const float* __restrict__ x, int n, int c, int64_t hw,
-                                    int64_t img_stride, float* __restrict__ out) {
-  // grid (blocks, c): each block reduces a slice of (n, hw) for channel blockIdx.y
+// out[c] (+)= sum over (n, hw) of an fp32 NCHW tensor; grid (blocks, c), same two-stage scheme per channel.
+__global__ void __launch_bounds__(256) nchw_chansum_kernel(const float* __restrict__ x, int n, int c, int64_t hw,
+                                                           int64_t img_stride, float* __restrict__ out,
+                                                           int accumulate, float* __restrict__ partial,
+                                                           unsigned int* tickets) {
   const int ch = blockIdx.y;
   const int64_t total = int64_t(n) * hw;
   float s = 0.f;
@@ -783,13 +744,24 @@ __global__ void nchw_chansum_kernel(const float* __restrict__ x, int n, int c, i
   }
   s = warp_sum(s);
   __shared__ float ws[8];
+  __shared__ bool is_last;
   if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x == 0) {
     float t = 0.f;
-    for (int i = 0; i < (blockDim.x >> 5); ++i) t += ws[i];
-    atomicAdd(out + ch, t);
+    for (int i = 0; i < 8; ++i) t += ws[i];
+    partial[int64_t(ch) * gridDim.x + blockIdx.x] = t;
+    __threadfence();
+    const unsigned int k = atomicAdd(&tickets[ch], 1u);
+    is_last = (k == gridDim.x - 1u);
+    if (is_last) tickets[ch] = 0u;
   }
+  __syncthreads();
+  if (!is_last || threadIdx.x != 0) return;
+  __threadfence();
+  float t = 0.f;
+  for (unsigned int k = 0; k < gridDim.x; ++k) t += __ldcg(partial + int64_t(ch) * gridDim.x + k);
+  out[ch] = (accumulate ? out[ch] : 0.f) + t;
 }
 
 // ---------------------------------------------------------------- pooling
@@ -904,8 +876,16 @@ __global__ void avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int hw,
 // ---------------------------------------------------------------- head selection
 // head_major = 1: all is [n][heads_ld*per_head], head k occupies [k*per_head, (k+1)*per_head) (SE).
 // head_major = 0: all is [n][pix][heads_ld], head k is channel k of every pixel (D, per_head = 1).
+// Index semantics of torch advanced indexing (model.py:112-116): a negative index counts from the end;
+// an index outside [-heads, heads) is an error there -- here the selected output is poisoned with NaN
+// (loud in every downstream loss) instead of reading out of bounds. Host-side callers that hold the
+// indices on the CPU raise IndexError before the launch (model.py of this package).
+__device__ __forceinline__ int wrap_head(long long k, int heads) {
+  if (k < 0) k += heads;
+  return (k >= 0 && k < heads) ? static_cast<int>(k) : -1;
+}
 __global__ void head_gather_kernel(const float* __restrict__ all, const int64_t* __restrict__ idx, int n,
-                                   int pix, int heads_ld, int per_head, int head_major,
+                                   int pix, int heads_ld, int heads, int per_head, int head_major,
                                    float* __restrict__ out) {
   const int64_t total = int64_t(n) * pix * per_head;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total;
@@ -914,14 +894,18 @@ __global__ void head_gather_kernel(const float* __restrict__ all, const int64_t*
     const int64_t rem = i / per_head;
     const int p = static_cast<int>(rem % pix);
     const int b = static_cast<int>(rem / pix);
-    const int k = idx ? static_cast<int>(idx[b]) : 0;
+    const int k = idx ? wrap_head(idx[b], heads) : 0;
+    if (k < 0) {
+      out[i] = __int_as_float(0x7fc00000);
+      continue;
+    }
     const int64_t src = head_major ? (int64_t(b) * pix + p) * heads_ld * per_head + int64_t(k) * per_head + e
                                    : (int64_t(b) * pix + p) * heads_ld + k;
     out[i] = all[src];
   }
 }
 __global__ void head_scatter_kernel(const float* __restrict__ dout, const int64_t* __restrict__ idx, int n,
-                                    int pix, int heads_ld, int per_head, int head_major,
+                                    int pix, int heads_ld, int heads, int per_head, int head_major,
                                     float* __restrict__ dall) {
   const int64_t total = int64_t(n) * pix * heads_ld * per_head;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total;
@@ -941,7 +925,7 @@ __global__ void head_scatter_kernel(const float* __restrict__ dout, const int64_
       p = static_cast<int>(rem % pix);
       b = static_cast<int>(rem / pix);
     }
-    const int sel = idx ? static_cast<int>(idx[b]) : 0;
+    const int sel = idx ? wrap_head(idx[b], heads) : 0;
     dall[i] = (k == sel) ? dout[(int64_t(b) * pix + p) * per_head + e] : 0.f;
   }
 }
@@ -980,27 +964,6 @@ int msig_patch_scatter(const msig_patch_geom* g, const void* dpatches, const flo
   const int64_t total = int64_t(g->n) * g->c * g->h * g->w;
   patch_scatter_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, ST(stream)>>>(*g, CBF(dpatches), scale, dsrc,
                                                                               accumulate, total);
-  count_launch(1);
-  MSIG_CHECK_LAUNCH();
-  return MSIG_OK;
-}
-
-int msig_reflect_pad_fwd(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad, void* y,
-                         void* stream) {
-  MSIG_REQUIRE(x && y && c % 8 == 0 && pad < h && pad < w, "msig_reflect_pad_fwd: bad argument");
-  const int64_t groups = int64_t(n) * (h + 2 * pad) * (w + 2 * pad) * (c / 8);
-  reflect_pad_fwd_kernel<<<grid_for(groups, 256, 148 * 32), 256, 0, ST(stream)>>>(CBF(x), n, h, w, c, pad,
-                                                                                 BF(y), groups);
-  count_launch(1);
-  MSIG_CHECK_LAUNCH();
-  return MSIG_OK;
-}
-int msig_reflect_pad_bwd(const void* dy, int32_t n, int32_t h, int32_t w, int32_t c, int32_t pad, void* dx,
-                         void* stream) {
-  MSIG_REQUIRE(dy && dx && c % 8 == 0 && pad < h && pad < w, "msig_reflect_pad_bwd: bad argument");
-  const int64_t groups = int64_t(n) * h * w * (c / 8);
-  reflect_pad_bwd_kernel<<<grid_for(groups, 256, 148 * 32), 256, 0, ST(stream)>>>(CBF(dy), n, h, w, c, pad,
-                                                                                 BF(dx), groups);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -1196,31 +1159,41 @@ int msig_act_bwd(const void* dy, const void* y, int32_t act, float slope, int64_
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
 }
-int msig_add_bf16(const void* a, const void* b, int64_t numel, void* out, void* stream) {
-  MSIG_REQUIRE(a && b && out && numel % 8 == 0, "msig_add_bf16: bad argument");
-  add_bf16_kernel<<<grid_for(numel / 8, 256), 256, 0, ST(stream)>>>(CBF(a), CBF(b), numel / 8, BF(out));
+static int colsum_rows_per_block(int64_t rows) {
+  return static_cast<int>(std::max<int64_t>(512, ceil_div(rows, 148 * 2)));
+}
+size_t msig_colsum_workspace(int64_t rows, int32_t c) {
+  const int64_t blocks = std::max<int64_t>(1, ceil_div(rows, colsum_rows_per_block(rows)));
+  return (size_t(blocks) * c + 1) * sizeof(float);
+}
+int msig_colsum(const void* dy, int64_t rows, int32_t c, float* db, int accumulate, void* workspace,
+                size_t workspace_bytes, void* stream) {
+  MSIG_REQUIRE(dy && db && workspace && c % 8 == 0 && c / 8 <= 256 && 256 % (c / 8) == 0, "msig_colsum: bad argument");
+  MSIG_REQUIRE(workspace_bytes >= msig_colsum_workspace(rows, c), "msig_colsum: workspace too small");
+  const int rpb = colsum_rows_per_block(rows);
+  const int blocks = static_cast<int>(std::max<int64_t>(1, ceil_div(rows, rpb)));
+  float* partial = reinterpret_cast<float*>(workspace);
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(partial + size_t(blocks) * c);
+  MSIG_CHECK_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), ST(stream)));
+  colsum_kernel<<<blocks, 256, 0, ST(stream)>>>(CBF(dy), rows, c, rpb, db, accumulate, partial, ticket);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
 }
-int msig_colsum(const void* dy, int64_t rows, int32_t c, float* db, int accumulate, void* stream) {
-  MSIG_REQUIRE(dy && db && c % 8 == 0 && c <= 2048 && (256 % (c / 8) == 0 || c / 8 > 256 || true),
-               "msig_colsum: bad argument");
-  MSIG_REQUIRE(c / 8 <= 256, "msig_colsum: c too large");
-  if (!accumulate) MSIG_CHECK_CUDA(cudaMemsetAsync(db, 0, size_t(c) * sizeof(float), ST(stream)));
-  const int rpb = 512;
-  const int blocks = static_cast<int>(ceil_div(rows, rpb));
-  colsum_kernel<<<std::max(blocks, 1), 256, 0, ST(stream)>>>(CBF(dy), rows, c, rpb, db);
-  count_launch(1);
-  MSIG_CHECK_LAUNCH();
-  return MSIG_OK;
+static int chansum_blocks(int32_t n, int64_t hw) { return grid_for(int64_t(n) * hw, 256, 256); }
+size_t msig_nchw_chansum_workspace(int32_t n, int32_t c, int64_t hw) {
+  return (size_t(c) * chansum_blocks(n, hw) + size_t(c)) * sizeof(float);
 }
 int msig_nchw_chansum(const float* x, int32_t n, int32_t c, int64_t hw, int64_t img_stride, float* out,
-                      int accumulate, void* stream) {
-  MSIG_REQUIRE(x && out, "msig_nchw_chansum: null argument");
-  if (!accumulate) MSIG_CHECK_CUDA(cudaMemsetAsync(out, 0, size_t(c) * sizeof(float), ST(stream)));
-  const int blocks = grid_for(int64_t(n) * hw, 256, 256);
-  nchw_chansum_kernel<<<dim3(blocks, c), 256, 0, ST(stream)>>>(x, n, c, hw, img_stride, out);
+                      int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
+  MSIG_REQUIRE(x && out && workspace && c >= 1, "msig_nchw_chansum: null argument");
+  MSIG_REQUIRE(workspace_bytes >= msig_nchw_chansum_workspace(n, c, hw), "msig_nchw_chansum: workspace too small");
+  const int blocks = chansum_blocks(n, hw);
+  float* partial = reinterpret_cast<float*>(workspace);
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(partial + size_t(c) * blocks);
+  MSIG_CHECK_CUDA(cudaMemsetAsync(tickets, 0, size_t(c) * sizeof(unsigned int), ST(stream)));
+  nchw_chansum_kernel<<<dim3(blocks, c), 256, 0, ST(stream)>>>(x, n, c, hw, img_stride, out, accumulate, partial,
+                                                              tickets);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -1262,19 +1235,21 @@ int msig_avgpool_bwd(const void* dy, int32_t n, int32_t hw, int32_t c, void* dx,
 }
 
 int msig_head_gather(const float* all, const int64_t* idx, int32_t n, int32_t pix, int32_t heads_ld,
-                     int32_t per_head, int32_t head_major, float* out, void* stream) {
-  MSIG_REQUIRE(all && out, "msig_head_gather: null argument");
+                     int32_t heads, int32_t per_head, int32_t head_major, float* out, void* stream) {
+  MSIG_REQUIRE(all && out && heads >= 1 && heads <= heads_ld, "msig_head_gather: bad argument");
   const int64_t total = int64_t(n) * pix * per_head;
-  head_gather_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(all, idx, n, pix, heads_ld, per_head, head_major, out);
+  head_gather_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(all, idx, n, pix, heads_ld, heads, per_head,
+                                                                  head_major, out);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
 }
 int msig_head_scatter(const float* dout, const int64_t* idx, int32_t n, int32_t pix, int32_t heads_ld,
-                      int32_t per_head, int32_t head_major, float* dall, void* stream) {
-  MSIG_REQUIRE(dout && dall, "msig_head_scatter: null argument");
+                      int32_t heads, int32_t per_head, int32_t head_major, float* dall, void* stream) {
+  MSIG_REQUIRE(dout && dall && heads >= 1 && heads <= heads_ld, "msig_head_scatter: bad argument");
   const int64_t total = int64_t(n) * pix * heads_ld * per_head;
-  head_scatter_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(dout, idx, n, pix, heads_ld, per_head, head_major, dall);
+  head_scatter_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(dout, idx, n, pix, heads_ld, heads, per_head,
+                                                                   head_major, dall);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;

@@ -53,7 +53,6 @@ _SIGS = {
     "msig_version": (c_int, []),
     "msig_last_error": (c_char_p, []),
     "msig_sm_count": (c_int, []),
-    "msig_debug_set_strip_mode": (c_int, [c_int]),
     "msig_debug_set_pair_mode": (c_int, [c_int]),
     "msig_debug_set_ring_mode": (c_int, [c_int]),
     "msig_kernel_launches": (c_longlong, []),
@@ -84,8 +83,6 @@ _SIGS = {
     "msig_patch_wgrad": (c_int, [POINTER(WpackDesc), c_int64, _P, _P, _P, c_int, _P, c_size_t, _P]),
     "msig_patch_wgrad_part": (c_int, [POINTER(WpackDesc), c_int32, c_int32, c_int64, _P, c_int32,
                                       _P, c_int32, _P, c_int, _P, c_size_t, _P]),
-    "msig_reflect_pad_fwd": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
-    "msig_reflect_pad_bwd": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "msig_in_stats_workspace": (c_size_t, [c_int32, c_int32, c_int32]),
     "msig_in_stats": (c_int, [_P, c_int32, c_int32, c_int32, c_float, _P, _P, c_int64, _P, _P, _P,
                               _P, _P, c_size_t, _P]),
@@ -104,32 +101,37 @@ _SIGS = {
     "msig_norm_bwd_from_partials": (c_int, [_P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, c_int32,
                                             c_int32, _P, _P, _P, c_int64, c_int, _P, _P]),
     "msig_act_bwd": (c_int, [_P, _P, c_int32, c_float, c_int64, _P, _P]),
-    "msig_add_bf16": (c_int, [_P, _P, c_int64, _P, _P]),
-    "msig_colsum": (c_int, [_P, c_int64, c_int32, _P, c_int, _P]),
+    "msig_colsum_workspace": (c_size_t, [c_int64, c_int32]),
+    "msig_colsum": (c_int, [_P, c_int64, c_int32, _P, c_int, _P, c_size_t, _P]),
     "msig_colsum_f32": (c_int, [_P, c_int64, c_int32, c_int64, _P, c_int, _P]),
-    "msig_nchw_chansum": (c_int, [_P, c_int32, c_int32, c_int64, c_int64, _P, c_int, _P]),
+    "msig_nchw_chansum_workspace": (c_size_t, [c_int32, c_int32, c_int64]),
+    "msig_nchw_chansum": (c_int, [_P, c_int32, c_int32, c_int64, c_int64, _P, c_int, _P, c_size_t, _P]),
     "msig_gemm_tn_partial": (c_int, [c_int64, _P, c_int32, _P, c_int32, _P, c_size_t, POINTER(c_int32), _P]),
     "msig_wgrad_unpack": (c_int, [POINTER(WpackDesc), c_int32, c_int32, _P, c_int32, c_int64, _P, c_int, _P]),
     "msig_maxpool2_fwd": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "msig_maxpool2_bwd": (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "msig_avgpool_fwd": (c_int, [_P, c_int32, c_int32, c_int32, _P, _P]),
     "msig_avgpool_bwd": (c_int, [_P, c_int32, c_int32, c_int32, _P, _P]),
-    "msig_head_gather": (c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
-    "msig_head_scatter": (c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
+    "msig_head_gather": (c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
+    "msig_head_scatter": (c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "msig_f32_to_bf16": (c_int, [_P, c_int64, _P, _P]),
     "msig_bf16_to_f32": (c_int, [_P, c_int64, _P, _P]),
     "msig_tanh_bwd": (c_int, [_P, _P, c_int64, _P, _P]),
-    "msig_l1_loss_f32_fwd": (c_int, [_P, _P, c_int64, _P, _P]),
+    "msig_reduce_workspace": (c_size_t, []),
+    "msig_l1_loss_f32_fwd": (c_int, [_P, _P, c_int64, _P, _P, c_size_t, _P]),
     "msig_l1_loss_f32_bwd": (c_int, [_P, _P, c_int64, _P, _P, _P]),
-    "msig_l1_loss_bf16_fwd": (c_int, [_P, _P, c_int64, _P, _P]),
+    "msig_l1_loss_bf16_fwd": (c_int, [_P, _P, c_int64, _P, _P, c_size_t, _P]),
     "msig_l1_loss_bf16_bwd": (c_int, [_P, _P, c_int64, _P, _P, _P, _P]),
-    "msig_mse_const_fwd": (c_int, [_P, c_float, c_int64, _P, _P]),
+    "msig_mse_const_fwd": (c_int, [_P, c_float, c_int64, _P, _P, c_size_t, _P]),
+    "msig_mse_loss_fwd": (c_int, [_P, _P, c_int64, _P, _P, c_size_t, _P]),
+    "msig_mse_loss_bwd": (c_int, [_P, _P, c_int64, _P, _P, _P]),
     "msig_mse_const_bwd": (c_int, [_P, c_float, c_int64, _P, _P, _P]),
     "msig_gram_workspace": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "msig_gram_fwd": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, _P, _P, c_size_t, _P]),
-    "msig_gram_l1": (c_int, [_P, _P, c_int32, _P, c_int, _P, _P]),
+    "msig_gram_l1_workspace": (c_size_t, [c_int32]),
+    "msig_gram_l1": (c_int, [_P, _P, c_int32, _P, c_int, _P, _P, c_size_t, _P]),
     "msig_gram_bwd": (c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P, _P, _P]),
-    "msig_sumsq": (c_int, [_P, c_int64, _P, c_int, _P]),
+    "msig_sumsq": (c_int, [_P, c_int64, _P, c_int, _P, c_size_t, _P]),
     "msig_adam_step": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float,
                                c_float, c_float, c_int32, c_float, _P]),
     "msig_adam_step_dev": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float,

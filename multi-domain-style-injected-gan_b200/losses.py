@@ -131,6 +131,7 @@ class VGGStyleContentLoss(nn.Module):
 
 class _VGGLossFn(torch.autograd.Function):
     @staticmethod
+    @ops.dev_guard
     def forward(ctx, mod, gen, real_style, real_content):
         if not gen.is_cuda:
             raise RuntimeError("VGGStyleContentLoss: expected CUDA tensors; msig_b200 has no CPU path")
@@ -154,6 +155,7 @@ class _VGGLossFn(torch.autograd.Function):
         return content, style
 
     @staticmethod
+    @ops.dev_guard
     def backward(ctx, g_content, g_style):
         mod = ctx.mod
         fg, fc4, ssyms, g, pg = ctx.saved
@@ -195,6 +197,7 @@ class _VGGLossFn(torch.autograd.Function):
 # ---------------------------------------------------------------------------- simple criteria
 class _L1Fn(torch.autograd.Function):
     @staticmethod
+    @ops.dev_guard
     def forward(ctx, a, b):
         a = a.contiguous().float()
         b = b.contiguous().float()
@@ -203,6 +206,7 @@ class _L1Fn(torch.autograd.Function):
         return ops.l1_loss_f32_fwd(a, b)
 
     @staticmethod
+    @ops.dev_guard
     def backward(ctx, g):
         a, b = ctx.saved_tensors
         return ops.l1_loss_f32_bwd(a, b, g.contiguous().float()), None
@@ -210,6 +214,7 @@ class _L1Fn(torch.autograd.Function):
 
 class _MSEConstFn(torch.autograd.Function):
     @staticmethod
+    @ops.dev_guard
     def forward(ctx, a, target):
         a = a.contiguous().float()
         ops.ensure_init(a.device)
@@ -218,9 +223,27 @@ class _MSEConstFn(torch.autograd.Function):
         return ops.mse_const_fwd(a, target)
 
     @staticmethod
+    @ops.dev_guard
     def backward(ctx, g):
         (a,) = ctx.saved_tensors
         return ops.mse_const_bwd(a, ctx.target, g.contiguous().float()), None
+
+
+class _MSEFn(torch.autograd.Function):
+    @staticmethod
+    @ops.dev_guard
+    def forward(ctx, a, target):
+        a = a.contiguous().float()
+        ops.ensure_init(a.device)
+        target = target.to(device=a.device, dtype=F32).expand_as(a).contiguous()
+        ctx.save_for_backward(a, target)
+        return ops.mse_loss_fwd(a, target)
+
+    @staticmethod
+    @ops.dev_guard
+    def backward(ctx, g):
+        a, target = ctx.saved_tensors
+        return ops.mse_loss_bwd(a, target, g.contiguous().float()), None
 
 
 class L1Loss(nn.Module):
@@ -232,11 +255,11 @@ class L1Loss(nn.Module):
 
 
 class MSELoss(nn.Module):
-    """nn.MSELoss() (mean) against an all-ones / all-zeros target (LSGAN, trainer.py:85-86).
-    `target` may be the float 1.0 / 0.0 or a constant tensor (its first element is read once on
-    the host when it is not a float, so pass floats on the hot path)."""
+    """nn.MSELoss() (mean). `target` is either a float (the LSGAN constants 1.0 / 0.0: no target tensor is
+    read at all) or a tensor like the reference's `valid` / `fake` (trainer.py:85-86,103): both forms run
+    on the device without a host synchronisation."""
 
     def forward(self, input, target):
         if torch.is_tensor(target):
-            target = float(target.flatten()[0].item())
+            return _MSEFn.apply(input, target)
         return _MSEConstFn.apply(input, float(target))

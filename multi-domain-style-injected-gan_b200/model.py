@@ -91,6 +91,15 @@ class _Net(nn.Module):
 
     def mark_weights_dirty(self):
         self._dirty += 1
+        for m in self._child_nets():       # nested stand-alone-capable blocks keep their own packed copies
+            m._dirty += 1
+
+    def _child_nets(self):
+        c = self.__dict__.get("_child_nets_cache")
+        if c is None:
+            c = [m for m in self.modules() if m is not self and isinstance(m, _Net)]
+            self.__dict__["_child_nets_cache"] = c
+        return c
 
     def _apply(self, fn, *a, **k):   # .to()/.cuda() move parameters: invalidate packed copies
         r = super()._apply(fn, *a, **k)
@@ -103,7 +112,7 @@ class _Net(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k == "_packed":
+            if k in ("_packed", "_child_nets_cache"):
                 continue
             setattr(new, k, copy.deepcopy(v, memo))
         new._packed = _PackedWeights(new)
@@ -127,20 +136,139 @@ class AdaIN(nn.Module):
                               self.style_modulation.bias)
 
 
-class ResidualBlockWithAdaIN(nn.Module):
-    """Residual block with two AdaIN layers (reference model.py:38-55)."""
+class ResidualBlockWithAdaIN(_Net):
+    """Residual block with two AdaIN layers (reference model.py:38-55). Inside the generator the block
+    is part of the fused network pass (_GeneratorFn); called on its own it runs the same kernels through
+    _ResBlockFn: conv + epilogue statistics, fused AdaIN apply (+ReLU / +residual), dgrads with fused
+    mask + norm-backward reductions."""
 
     def __init__(self, channels, style_dim):
         super().__init__()
+        self.channels, self.style_dim = channels, style_dim
         self.conv1 = nn.Conv2d(channels, channels, kernel_size=3, padding=1)
         self.adain1 = AdaIN(channels, style_dim)
         self.relu1 = nn.ReLU(inplace=True)
         self.conv2 = nn.Conv2d(channels, channels, kernel_size=3, padding=1)
         self.adain2 = AdaIN(channels, style_dim)
 
+    def _pack(self, t):
+        c, sd = self.channels, self.style_dim
+        dev = self.conv1.weight.device
+        if "lin" not in t:
+            t["lin"] = torch.zeros(2 * 2 * c * sd, dtype=BF16, device=dev)
+            t["lin_d"] = torch.zeros(ops.pad_rows(sd) * 2 * 2 * c, dtype=BF16, device=dev)
+            t["lin_b"] = torch.zeros(2 * 2 * c, dtype=F32, device=dev)
+        for j, (conv, ada) in enumerate(((self.conv1, self.adain1), (self.conv2, self.adain2))):
+            t[f"w{j}"] = ops.wpack(WPACK_FWD, conv.weight, c, c, 3, 3, out=t.get(f"w{j}"))
+            t[f"w{j}_d"] = ops.wpack(WPACK_DGRAD_S1, conv.weight, c, c, 3, 3, out=t.get(f"w{j}_d"))
+            ops.wpack(WPACK_FWD, ada.style_modulation.weight, 2 * c, sd, 1, 1, out=t["lin"], oc=4 * c, o_off=j * 2 * c)
+            ops.wpack(WPACK_DGRAD_S1, ada.style_modulation.weight, 2 * c, sd, 1, 1, out=t["lin_d"], oc=4 * c,
+                      o_off=j * 2 * c)
+            ops.copy_f32(t["lin_b"][j * 2 * c:(j + 1) * 2 * c], ada.style_modulation.bias)
+
+    def _dead_biases(self):
+        return [self.conv1.bias, self.conv2.bias]
+
     def forward(self, x, style_code):
-        raise RuntimeError("ResidualBlockWithAdaIN is executed inside StyleCycleGANGenerator's fused pass; "
-                           "call the generator (stand-alone block execution is not on the accelerated path)")
+        return _ResBlockFn.apply(self, x, style_code, *self.parameters())
+
+
+def _style_linears_backward(dgb, B, bs, nl, c2, sd, sb, lin_d, adains, wg, want_dstyle, style_shape):
+    """Backward of the batched style Linears (model.py:28): dgb [B, nl*c2] fp32 holds (dgamma | dbeta) of
+    every AdaIN site. Returns dstyle (or None) and accumulates dW / db into the Linear parameters."""
+    if bs == 1 and B > 1:                      # one style code broadcast over the batch
+        red = torch.empty((1, nl * c2), dtype=F32, device=dgb.device)
+        ops.colsum_f32(dgb, B, nl * c2, red, accumulate=False)
+        dgb = red
+    rows = dgb.shape[0]
+    dgbb = ops.to_bf16(dgb)
+    dstyle = None
+    if want_dstyle:
+        dstyle = ops.conv2d_fwd(dgbb.view(1, 1, rows, nl * c2), lin_d, ops.gemm_geom(rows, nl * c2, sd),
+                                ops.epilogue(out_layout=OUT_F32_NHWC)).view(rows, sd).view(style_shape)
+    if wg:
+        ws, splits = ops.gemm_tn_partial(rows, dgbb, nl * c2, sb, sd)
+        for l, ada in enumerate(adains):
+            ops.wgrad_unpack(WPACK_FWD, c2, sd, 1, 1, ws, splits, nl * c2 * sd,
+                             _grad_buf(ada.style_modulation.weight), partial_offset=l * c2 * sd)
+            ops.colsum_f32(dgb, rows, c2, _grad_buf(ada.style_modulation.bias), ld=nl * c2, offset=l * c2)
+    return dstyle
+
+
+class _ResBlockFn(torch.autograd.Function):
+    """x + AdaIN2(conv2(ReLU(AdaIN1(conv1(x))))) on fp32 NCHW features (model.py:51-55)."""
+
+    @staticmethod
+    @ops.dev_guard
+    def forward(ctx, mod, x, style, *params):
+        _require_cuda(x, "ResidualBlockWithAdaIN")
+        ops.ensure_init(x.device)
+        P = mod._packed.get()
+        c, sd = mod.channels, mod.style_dim
+        B, C, H, W = x.shape
+        if C != c or c % 64:
+            raise RuntimeError(f"ResidualBlockWithAdaIN: expected {c} channels (a multiple of 64), got {C}")
+        s2 = _style_2d(style).contiguous().float()
+        bs = s2.shape[0]
+        if bs not in (1, B):
+            raise RuntimeError(f"style code batch {bs} does not match feature batch {B}")
+        xh = ops.to_bf16(x.float().permute(0, 2, 3, 1).contiguous())
+        sb = ops.to_bf16(s2)
+        c2 = 2 * c
+        gb = ops.conv2d_fwd(sb.view(1, 1, bs, sd), P["lin"], ops.gemm_geom(bs, sd, 2 * c2),
+                            ops.epilogue(bias=P["lin_b"], out_layout=OUT_F32_NHWC)).view(bs, 2 * c2)
+        gstride = 0 if bs == 1 else 2 * c2
+        g3 = ops.conv_geom(B, H, W, c, c, 3, 3, 1, 1, 1, H, W)
+        za, sta = _conv_stats(xh, P["w0"], g3, gb[:, 0:], gb[:, c:], gstride)
+        ha = ops.norm_act_fwd(za, sta, ACT_RELU)
+        zb, stb = _conv_stats(ha, P["w1"], g3, gb[:, c2:], gb[:, c2 + c:], gstride)
+        out = ops.norm_act_fwd(zb, stb, ACT_NONE, residual=xh)
+        if any(ctx.needs_input_grad):
+            ctx.mod = mod
+            ctx.saved = dict(xh=xh, za=za, sta=sta, ha=ha, zb=zb, stb=stb, sb=sb, bs=bs, g3=g3,
+                             style_shape=style.shape, x_grad=ctx.needs_input_grad[1],
+                             style_grad=ctx.needs_input_grad[2])
+        return ops.to_f32(out).permute(0, 3, 1, 2)
+
+    @staticmethod
+    @ops.dev_guard
+    def backward(ctx, dout):
+        mod, S = ctx.mod, ctx.saved
+        P = mod._packed.get()
+        c, sd = mod.channels, mod.style_dim
+        wg = not mod.skip_param_grads
+        g3 = S["g3"]
+        B = g3.n
+        c2 = 2 * c
+        dy = ops.to_bf16(dout.float().permute(0, 2, 3, 1).contiguous())
+        dgb = torch.zeros((B, 2 * c2), dtype=F32, device=dout.device)
+        # second AdaIN (no activation): the upstream gradient comes from outside, so its two reductions
+        # are a separate pass; the dgrads below emit the reductions of the first AdaIN in their epilogue
+        dzb = ops.norm_act_bwd(dy, S["zb"], S["stb"], ACT_NONE, dgamma=dgb[:, c2:], dbeta=dgb[:, c2 + c:],
+                               dgb_stride=2 * c2)
+        if wg:
+            ops.conv2d_wgrad(S["ha"], dzb, g3, _grad_buf(mod.conv2.weight))
+        if ops.epi_fusable(9, c):
+            es = ops.epi_stats(B, g3.h, g3.w, c, dout.device)
+            dh = ops.conv2d_dgrad(dzb, P["w1_d"], g3,
+                                  ops.epilogue(aux=S["ha"], aux_mode=AUX_RELU_MASK, stats=es, stats_z=S["za"]))
+            dza = ops.norm_bwd_from(es, dh, S["za"], S["sta"], dgamma=dgb[:, 0:], dbeta=dgb[:, c:], dgb_stride=2 * c2)
+        else:
+            dh = ops.conv2d_dgrad(dzb, P["w1_d"], g3)
+            dza = ops.norm_act_bwd(dh, S["za"], S["sta"], ACT_RELU, dgamma=dgb[:, 0:], dbeta=dgb[:, c:],
+                                   dgb_stride=2 * c2)
+        if wg:
+            ops.conv2d_wgrad(S["xh"], dza, g3, _grad_buf(mod.conv1.weight))
+            for p in mod._dead_biases():
+                _grad_buf(p)
+        dx = None
+        if S["x_grad"]:
+            dxh = ops.conv2d_dgrad(dza, P["w0_d"], g3, ops.epilogue(aux=dy, aux_mode=AUX_ADD))
+            dx = ops.to_f32(dxh).permute(0, 3, 1, 2)
+        dstyle = _style_linears_backward(dgb, B, S["bs"], 2, c2, sd, S["sb"], P["lin_d"], (mod.adain1, mod.adain2),
+                                         wg, S["style_grad"], S["style_shape"])
+        ctx.saved = None
+        return (None, dx, dstyle) + (None,) * (len(ctx.needs_input_grad) - 3)
 
 
 def _style_2d(style_code):
@@ -154,6 +282,7 @@ class _AdaINFn(torch.autograd.Function):
     statistics + modulation. Used by the unit tests of the building block."""
 
     @staticmethod
+    @ops.dev_guard
     def forward(ctx, x, style, w, b):
         _require_cuda(x, "AdaIN")
         ops.ensure_init(x.device)
@@ -171,6 +300,7 @@ class _AdaINFn(torch.autograd.Function):
         return ops.to_f32(y).permute(0, 3, 1, 2)
 
     @staticmethod
+    @ops.dev_guard
     def backward(ctx, dy):
         xh, st, sb, w, style_shape, bs = ctx.saved
         n, h, wd, c = xh.shape
@@ -256,6 +386,7 @@ class StyleCycleGANGenerator(_Net):
 
 class _GeneratorFn(torch.autograd.Function):
     @staticmethod
+    @ops.dev_guard
     def forward(ctx, mod, img, style, *params):
         _require_cuda(img, "StyleCycleGANGenerator")
         ops.ensure_init(img.device)
@@ -320,6 +451,7 @@ class _GeneratorFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @ops.dev_guard
     def backward(ctx, dout):
         mod, S = ctx.mod, ctx.saved
         P = mod._packed.get()
@@ -386,25 +518,9 @@ class _GeneratorFn(torch.autograd.Function):
                                   ops.epilogue(aux=dy, aux_mode=AUX_ADD, stats=es,
                                                stats_z=S["res"][i - 1][4] if i > 0 else None))
         # ---- style Linears (model.py:28): dstyle, dW, db for all 2k layers
-        bs = S["bs"]
-        if bs == 1 and B > 1:
-            red = torch.empty((1, nl * 512), dtype=F32, device=dout.device)
-            ops.colsum_f32(dgb, B, nl * 512, red, accumulate=False)
-            dgb = red
-        rows = dgb.shape[0]
-        dgbb = ops.to_bf16(dgb)
-        dstyle = None
-        if S["style_grad"]:
-            dstyle = ops.conv2d_fwd(dgbb.view(1, 1, rows, nl * 512), P["lin_d"], ops.gemm_geom(rows, nl * 512, sd),
-                                    ops.epilogue(out_layout=OUT_F32_NHWC)).view(rows, sd).view(S["style_shape"])
-        if wg:
-            ws, splits = ops.gemm_tn_partial(rows, dgbb, nl * 512, S["sb"], sd)
-            for i in range(k):
-                for j, ada in enumerate((dec[i].adain1, dec[i].adain2)):
-                    l = 2 * i + j
-                    ops.wgrad_unpack(WPACK_FWD, 512, sd, 1, 1, ws, splits, nl * 512 * sd,
-                                     _grad_buf(ada.style_modulation.weight), partial_offset=l * 512 * sd)
-                    ops.colsum_f32(dgb, rows, 512, _grad_buf(ada.style_modulation.bias), ld=nl * 512, offset=l * 512)
+        adains = [a for i in range(k) for a in (dec[i].adain1, dec[i].adain2)]
+        dstyle = _style_linears_backward(dgb, B, S["bs"], nl, 512, sd, S["sb"], P["lin_d"], adains, wg,
+                                         S["style_grad"], S["style_shape"])
         # ---- encoder, reversed
         dz2 = ops.norm_act_bwd(dy, S["z2"], S["st2"], ACT_RELU)
         if wg:
@@ -506,6 +622,7 @@ class MultiDomainStyleEncoder(_Net):
 
 class _StyleEncoderFn(torch.autograd.Function):
     @staticmethod
+    @ops.dev_guard
     def forward(ctx, mod, img, domain_idx, *params):
         _require_cuda(img, "MultiDomainStyleEncoder")
         ops.ensure_init(img.device)
@@ -516,7 +633,7 @@ class _StyleEncoderFn(torch.autograd.Function):
         B, _, H, W = img.shape
         if H % 16 or W % 16:
             raise RuntimeError("style encoder input height/width must be multiples of 16")
-        idx = None if domain_idx is None else domain_idx.to(device=img.device, dtype=torch.int64).contiguous()
+        idx = ops.domain_index(domain_idx, nd, B, img.device)
         pg = ops.patch_geom(B, 3, H, W, 4, 4, 2, 1, 1, H // 2, W // 2, False)
         a = ops.patch_gather_cached(img, pg)
         m0 = B * (H // 2) * (W // 2)
@@ -538,10 +655,12 @@ class _StyleEncoderFn(torch.autograd.Function):
         out = ops.head_gather(allh, idx, B, 1, nd, sd, True).view(B, sd)
         if any(ctx.needs_input_grad):
             ctx.mod = mod
-            ctx.saved = dict(img=img, pg=pg, ys=ys, gs=gs, pooled=pooled, idx=idx, hw=(h, w))
+            ctx.saved = dict(img=img, pg=pg, ys=ys, gs=gs, pooled=pooled, idx=idx, hw=(h, w),
+                             img_grad=ctx.needs_input_grad[1])
         return out
 
     @staticmethod
+    @ops.dev_guard
     def backward(ctx, dout):
         mod, S = ctx.mod, ctx.saved
         P = mod._packed.get()
@@ -573,9 +692,13 @@ class _StyleEncoderFn(torch.autograd.Function):
         ops.colsum(dz, 64, _grad_buf(convs[0].bias))
         a = ops.patch_gather_cached(S["img"], pg)
         ops.patch_wgrad(WPACK_IM2COL, 64, 3, 4, 4, m0, dz, 64, a, pg.kpad, _grad_buf(convs[0].weight))
+        del a
+        dimg = None
+        if S["img_grad"]:      # (train_step only feeds leaf images, trainer.py:94-95; model.py:89-118 is differentiable)
+            da = ops.conv2d_fwd(dz.view(1, 1, m0, 64), P["c0_d"], ops.gemm_geom(m0, 64, pg.kpad))
+            dimg = ops.patch_scatter(da.view(m0, pg.kpad), pg)
         ctx.saved = None
-        # the style encoder only ever sees leaf images (trainer.py:94-95): no image gradient
-        return (None, None, None) + (None,) * (len(ctx.needs_input_grad) - 3)
+        return (None, dimg, None) + (None,) * (len(ctx.needs_input_grad) - 3)
 
 
 # ######################################################################
@@ -635,6 +758,7 @@ class MultiDomainDiscriminator(_Net):
 
 class _DiscriminatorFn(torch.autograd.Function):
     @staticmethod
+    @ops.dev_guard
     def forward(ctx, mod, img, domain_idx, *params):
         _require_cuda(img, "MultiDomainDiscriminator")
         ops.ensure_init(img.device)
@@ -645,7 +769,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         B, _, H, W = img.shape
         if H % 16 or W % 16:
             raise RuntimeError("discriminator input height/width must be multiples of 16")
-        idx = None if domain_idx is None else domain_idx.to(device=img.device, dtype=torch.int64).contiguous()
+        idx = ops.domain_index(domain_idx, nd, B, img.device)
         pg = ops.patch_geom(B, 3, H, W, 4, 4, 2, 1, 1, H // 2, W // 2, False)
         a = ops.patch_gather_cached(img, pg)
         m0 = B * (H // 2) * (W // 2)
@@ -674,6 +798,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @ops.dev_guard
     def backward(ctx, dout):
         mod, S = ctx.mod, ctx.saved
         P = mod._packed.get()

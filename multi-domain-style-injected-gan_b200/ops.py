@@ -18,6 +18,28 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def dev_guard(fn):
+    """Decorator for autograd.Function forward / backward: run with the CUDA device of the first CUDA
+    tensor argument current, so that `torch.cuda.current_stream()` (the stream every launch of this module
+    goes to), the scratch workspace and the library's per-device context all belong to the tensors'
+    device -- a trainer built with device='cuda:1' works without torch.cuda.set_device(1), like the
+    reference's."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(ctx, *args):
+        dev = None
+        for a in args:
+            if torch.is_tensor(a) and a.is_cuda:
+                dev = a.device
+                break
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(ctx, *args)
+        with torch.cuda.device(dev):
+            return fn(ctx, *args)
+    return wrapped
+
+
 def _p(t):
     return ctypes.c_void_p(0 if t is None else t.data_ptr())
 
@@ -330,21 +352,6 @@ def patch_wgrad(kind, o, i, r, s, rows, a, m, b, ncols, dw, accumulate=True, oc=
            int(accumulate), _p(ws), ws.numel(), _stream())
 
 
-def reflect_pad_fwd(x, pad):
-    n, h, w, c = x.shape
-    y = torch.empty((n, h + 2 * pad, w + 2 * pad, c), dtype=BF16, device=x.device)
-    L.call("msig_reflect_pad_fwd", _p(x), n, h, w, c, pad, _p(y), _stream())
-    return y
-
-
-def reflect_pad_bwd(dy, pad):
-    n, h2, w2, c = dy.shape
-    h, w = h2 - 2 * pad, w2 - 2 * pad
-    dx = torch.empty((n, h, w, c), dtype=BF16, device=dy.device)
-    L.call("msig_reflect_pad_bwd", _p(dy), n, h, w, c, pad, _p(dx), _stream())
-    return dx
-
-
 # ------------------------------------------------------------------ InstanceNorm / AdaIN
 class NormStats:
     """mean / rstd / scale / shift, each fp32 [n, c] (one allocation)."""
@@ -435,16 +442,10 @@ def act_bwd(dy, y, act, slope=0.2, out=None):
     return out
 
 
-def add_bf16(a, b, out=None):
-    if out is None:
-        out = torch.empty_like(a)
-    L.call("msig_add_bf16", _p(a), _p(b), a.numel(), _p(out), _stream())
-    return out
-
-
 def colsum(dy2d_rows, c, db, accumulate=True, rows=None):
     rows = dy2d_rows.numel() // c if rows is None else rows
-    L.call("msig_colsum", _p(dy2d_rows), rows, c, _p(db), int(accumulate), _stream())
+    ws = workspace(L.load().msig_colsum_workspace(rows, c), dy2d_rows.device)
+    L.call("msig_colsum", _p(dy2d_rows), rows, c, _p(db), int(accumulate), _p(ws), ws.numel(), _stream())
 
 
 def colsum_f32(x, rows, c, out, accumulate=True, ld=None, offset=0):
@@ -458,8 +459,9 @@ def nchw_chansum(x, out, accumulate=True, n=None, c=None, hw=None, img_stride=No
         n, c, h, w = x.shape
         hw = h * w
     ptr = ctypes.c_void_p(x.data_ptr() + 4 * offset)
+    ws = workspace(L.load().msig_nchw_chansum_workspace(n, c, hw), x.device)
     L.call("msig_nchw_chansum", ptr, n, c, hw, c * hw if img_stride is None else img_stride, _p(out),
-           int(accumulate), _stream())
+           int(accumulate), _p(ws), ws.numel(), _stream())
 
 
 def gemm_tn_partial(rows, a, m, b, ncols):
@@ -508,18 +510,36 @@ def avgpool_bwd(dy, h, w):
     return dx
 
 
-def head_gather(all_, idx, n, pix, heads_ld, per_head, head_major):
+def head_gather(all_, idx, n, pix, heads_ld, per_head, head_major, heads=None):
+    """`heads_ld`: heads stored per row (the padded stride); `heads`: real heads (index range)."""
     out = torch.empty((n, pix * per_head), dtype=F32, device=all_.device)
-    L.call("msig_head_gather", _p(all_), _p(idx), n, pix, heads_ld, per_head, int(head_major), _p(out),
-           _stream())
+    L.call("msig_head_gather", _p(all_), _p(idx), n, pix, heads_ld, heads_ld if heads is None else heads, per_head,
+           int(head_major), _p(out), _stream())
     return out
 
 
-def head_scatter(dout, idx, n, pix, heads_ld, per_head, head_major):
+def head_scatter(dout, idx, n, pix, heads_ld, per_head, head_major, heads=None):
     dall = torch.empty((n, pix * heads_ld * per_head), dtype=F32, device=dout.device)
-    L.call("msig_head_scatter", _p(dout), _p(idx), n, pix, heads_ld, per_head, int(head_major), _p(dall),
-           _stream())
+    L.call("msig_head_scatter", _p(dout), _p(idx), n, pix, heads_ld, heads_ld if heads is None else heads, per_head,
+           int(head_major), _p(dall), _stream())
     return dall
+
+
+def domain_index(domain_idx, num_domains, batch, device):
+    """domain_idx as a contiguous int64 device tensor. Indices that live on the HOST are range-checked
+    here (free: no device sync) and raise IndexError like the reference's advanced indexing
+    (model.py:112-116, 208-212); device-resident indices are checked by the kernels (NaN poison)."""
+    if domain_idx is None:
+        return None
+    if not torch.is_tensor(domain_idx):
+        domain_idx = torch.as_tensor(domain_idx)
+    if domain_idx.numel() != batch:
+        raise IndexError(f"domain_idx has {domain_idx.numel()} entries for a batch of {batch}")
+    if not domain_idx.is_cuda and domain_idx.numel():
+        lo, hi = int(domain_idx.min()), int(domain_idx.max())
+        if lo < -num_domains or hi >= num_domains:
+            raise IndexError(f"domain index out of range for {num_domains} domains: [{lo}, {hi}]")
+    return domain_idx.to(device=device, dtype=torch.int64).contiguous()
 
 
 def to_bf16(x, out=None):
@@ -547,9 +567,15 @@ def _scalar(device):
     return torch.empty((), dtype=F32, device=device)
 
 
+def _reduce_ws(device):
+    """Scratch of the deterministic two-stage reductions (per-block partials + ticket)."""
+    return workspace(L.load().msig_reduce_workspace(), device)
+
+
 def l1_loss_f32_fwd(a, b):
     loss = _scalar(a.device)
-    L.call("msig_l1_loss_f32_fwd", _p(a), _p(b), a.numel(), _p(loss), _stream())
+    ws = _reduce_ws(a.device)
+    L.call("msig_l1_loss_f32_fwd", _p(a), _p(b), a.numel(), _p(loss), _p(ws), ws.numel(), _stream())
     return loss
 
 
@@ -561,7 +587,8 @@ def l1_loss_f32_bwd(a, b, gscale):
 
 def l1_loss_bf16_fwd(a, b):
     loss = _scalar(a.device)
-    L.call("msig_l1_loss_bf16_fwd", _p(a), _p(b), a.numel(), _p(loss), _stream())
+    ws = _reduce_ws(a.device)
+    L.call("msig_l1_loss_bf16_fwd", _p(a), _p(b), a.numel(), _p(loss), _p(ws), ws.numel(), _stream())
     return loss
 
 
@@ -573,8 +600,22 @@ def l1_loss_bf16_bwd(a, b, gscale, aux=None):
 
 def mse_const_fwd(a, target):
     loss = _scalar(a.device)
-    L.call("msig_mse_const_fwd", _p(a), float(target), a.numel(), _p(loss), _stream())
+    ws = _reduce_ws(a.device)
+    L.call("msig_mse_const_fwd", _p(a), float(target), a.numel(), _p(loss), _p(ws), ws.numel(), _stream())
     return loss
+
+
+def mse_loss_fwd(a, target):
+    loss = _scalar(a.device)
+    ws = _reduce_ws(a.device)
+    L.call("msig_mse_loss_fwd", _p(a), _p(target), a.numel(), _p(loss), _p(ws), ws.numel(), _stream())
+    return loss
+
+
+def mse_loss_bwd(a, target, gscale):
+    g = torch.empty_like(a)
+    L.call("msig_mse_loss_bwd", _p(a), _p(target), a.numel(), _p(gscale), _p(g), _stream())
+    return g
 
 
 def mse_const_bwd(a, target, gscale):
@@ -600,7 +641,8 @@ def gram_l1(ga, gb, loss=None):
     if loss is None:
         loss = _scalar(ga.device)
     ssym = torch.empty((dim, dim), dtype=BF16, device=ga.device)
-    L.call("msig_gram_l1", _p(ga), _p(gb), dim, _p(loss), int(acc), _p(ssym), _stream())
+    ws = workspace(L.load().msig_gram_l1_workspace(dim), ga.device)
+    L.call("msig_gram_l1", _p(ga), _p(gb), dim, _p(loss), int(acc), _p(ssym), _p(ws), ws.numel(), _stream())
     return loss, ssym
 
 
@@ -614,7 +656,8 @@ def gram_bwd(f, ssym, alpha, gscale=None, aux=None):
 
 # ------------------------------------------------------------------ optimizer
 def sumsq(x, out, accumulate=False):
-    L.call("msig_sumsq", _p(x), x.numel(), _p(out), int(accumulate), _stream())
+    ws = _reduce_ws(x.device)
+    L.call("msig_sumsq", _p(x), x.numel(), _p(out), int(accumulate), _p(ws), ws.numel(), _stream())
 
 
 def adam_step(param, grad, exp_avg, exp_avg_sq, ema, grad_sumsq, max_norm, grad_scale, lr, beta1, beta2,

@@ -163,9 +163,14 @@ class EMA:
 
 
 class DynamicWeightScheduler:
-    """Warm-up x cosine-decay loss weights (reference utils.py:94-134). The weights depend on the
-    epoch only; the reference's per-step `.item()` host syncs (utils.py:114) are replaced by keeping
-    the detached device scalars, materialised on demand through `loss_history_values()`."""
+    """Warm-up x cosine-decay loss weights (reference utils.py:94-134). The weights depend on the epoch
+    only; the reference's per-step `.item()` host syncs (utils.py:114) are replaced by a preallocated
+    device ring: each step's loss scalars are copied into one ring row (stream-ordered, no sync) and the
+    ring is flushed to host floats with ONE device->host copy when it fills or when `loss_history` is
+    read. `loss_history` therefore holds Python floats like the reference's, and no device memory is
+    retained per step."""
+
+    RING_ROWS = 1024
 
     def __init__(self, init_weights, warmup_epochs=10, decay_epochs=100, total_epochs=200):
         self.init_weights = init_weights
@@ -173,8 +178,57 @@ class DynamicWeightScheduler:
         self.warmup_epochs = warmup_epochs
         self.decay_end_epoch = warmup_epochs + decay_epochs
         self.total_epochs = total_epochs
-        self.loss_history = {k: [] for k in init_weights.keys()}
-        self.weight_history = {k: [] for k in init_weights.keys()}
+        self._keys = list(init_weights.keys())
+        self._loss_history = {k: [] for k in self._keys}
+        self.weight_history = {k: [] for k in self._keys}
+        self._ring = None          # [RING_ROWS, len(keys)] fp32 on the losses' device
+        self._pending = 0
+
+    # -- loss history: floats, flushed lazily -------------------------------------------------
+    @property
+    def loss_history(self):
+        self._flush()
+        return self._loss_history
+
+    @loss_history.setter
+    def loss_history(self, value):
+        self._pending = 0
+        self._loss_history = value
+
+    def _flush(self):
+        if self._pending:
+            rows = self._ring[:self._pending].cpu().tolist()       # one D2H copy (synchronises once)
+            self._pending = 0
+            for row in rows:
+                for k, v in zip(self._keys, row):
+                    self._loss_history[k].append(v)
+
+    def record_device(self, row):
+        """Append one step's losses given as a device vector ordered like the weight keys."""
+        if self._ring is None or self._ring.device != row.device:
+            self._flush()
+            self._ring = torch.empty((self.RING_ROWS, len(self._keys)), dtype=F32, device=row.device)
+        if self._pending == self.RING_ROWS:
+            self._flush()
+        self._ring[self._pending].copy_(row, non_blocking=True)
+        self._pending += 1
+
+    def _record(self, current_losses):
+        vals = [current_losses.get(k) for k in self._keys]
+        if any(v is None for v in vals):            # partial dict (e.g. {}): reference semantics, per key
+            for k, v in current_losses.items():
+                if k in self._loss_history:
+                    self._flush()
+                    self._loss_history[k].append(float(v))
+            return
+        if any(torch.is_tensor(v) and v.is_cuda for v in vals):
+            dev = next(v.device for v in vals if torch.is_tensor(v) and v.is_cuda)
+            self.record_device(torch.stack([v.detach().float().reshape(()) if torch.is_tensor(v)
+                                            else torch.tensor(float(v), device=dev) for v in vals]))
+        else:
+            self._flush()
+            for k, v in zip(self._keys, vals):
+                self._loss_history[k].append(float(v))
 
     def get_current_weights(self, epoch, current_losses, record=True):
         """record=False (CUDA-graph capture): compute the weights only; the histories are appended
@@ -184,9 +238,8 @@ class DynamicWeightScheduler:
             w = self.get_current_weights(epoch, {})
             self.weight_history = saved
             return w
-        for k, v in current_losses.items():
-            if k in self.loss_history:
-                self.loss_history[k].append(v.detach() if hasattr(v, "detach") else v)
+        if current_losses:
+            self._record(current_losses)
         warmup_factor = min(1.0, (epoch + 1) / self.warmup_epochs)
         decay_factor = 1.0
         if epoch >= self.warmup_epochs:
@@ -198,4 +251,4 @@ class DynamicWeightScheduler:
         return self.current_weights
 
     def loss_history_values(self):
-        return {k: [float(x) for x in v] for k, v in self.loss_history.items()}
+        return {k: list(v) for k, v in self.loss_history.items()}

@@ -24,24 +24,164 @@ LRELU = 0.2
 IN_EPS = 1e-5
 
 
+# ----------------------------------------------------------------------------- bf16-storage emulation
+# The CUDA path keeps operands and activations in bf16 and accumulates / normalises / reduces in fp32
+# (DESIGN.md "Precision contract"). `with emulate_bf16():` makes this restatement round to bf16 at exactly
+# the points where that path STORES a tensor -- conv operands (images, packed weights), conv outputs z,
+# post-norm activations y, the bf16 gradient tensors of the backward pass (dy / dz / the gathered-patch
+# gradients), pooled features -- while everything in between stays fp32, like the kernels' registers.
+# With it, CUDA-vs-oracle gradient parity can be held to bounds that are ~50x tighter than against the
+# plain fp32 oracle, because the two sides then differ only where an fp32 summation-order difference
+# flips a bf16 rounding. Outside the context manager every helper below is the identity and the
+# restatement is the plain fp32 reference arithmetic (pinned by tests/golden/ref_small.pt).
+_EMU = False
+
+
+class emulate_bf16:
+    def __enter__(self):
+        global _EMU
+        self._prev, _EMU = _EMU, True
+        return self
+
+    def __exit__(self, *exc):
+        global _EMU
+        _EMU = self._prev
+        return False
+
+
+def _r(x):
+    return x.to(torch.bfloat16).to(x.dtype)
+
+
+class _Store(torch.autograd.Function):
+    """A tensor stored in bf16 whose gradient is stored in bf16 too (activations z / y, pooled features)."""
+    @staticmethod
+    def forward(ctx, x):
+        return _r(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _r(g)
+
+
+class _RoundFwd(torch.autograd.Function):
+    """Rounded operand with an fp32 gradient (packed weights; images and style codes at a network input)."""
+    @staticmethod
+    def forward(ctx, x):
+        return _r(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _RoundBwd(torch.autograd.Function):
+    """fp32 tensor whose GRADIENT is consumed in bf16 (GEMM outputs in front of an fp32 bias / tanh, the
+    gathered patch matrices, the reflect-padded activation)."""
+    @staticmethod
+    def forward(ctx, x):
+        return x.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return _r(g)
+
+
+class _ActStore(torch.autograd.Function):
+    """y = bf16(act(u)); backward g = bf16(dy * act'(u)) (mask fused into the producing dgrad epilogue,
+    mask_first) or bf16(dy) * act'(u) (dy stored first, mask applied by the norm backward)."""
+    @staticmethod
+    def forward(ctx, u, slope, mask_first):
+        ctx.save_for_backward(u)
+        ctx.slope, ctx.mask_first = slope, mask_first
+        return _r(torch.where(u > 0, u, u * slope))
+
+    @staticmethod
+    def backward(ctx, g):
+        (u,) = ctx.saved_tensors
+        d = torch.where(u > 0, torch.ones_like(u), torch.full_like(u, ctx.slope))
+        return (_r(g * d) if ctx.mask_first else _r(g) * d), None, None
+
+
+class _Tap(torch.autograd.Function):
+    """A stored feature map with a main consumer and 1-2 side consumers whose gradients are added one
+    after the other into the bf16 gradient tensor (losses.py VGG taps: conv/pool path first, then the
+    content L1, then the Gram term; each addition re-rounds, like the aux operand of the kernels)."""
+    @staticmethod
+    def forward(ctx, f, n_side):
+        ctx.n_side = n_side
+        return tuple(f.clone() for _ in range(1 + n_side))
+
+    @staticmethod
+    def backward(ctx, *gs):
+        acc = None
+        for g in gs:
+            if g is None:
+                continue
+            acc = _r(g) if acc is None else _r(acc + g)
+        return acc, None
+
+
+def st(x):
+    return _Store.apply(x) if _EMU else x
+
+
+def wq(x):
+    return _RoundFwd.apply(x) if (_EMU and x is not None) else x
+
+
+def gq(x):
+    return _RoundBwd.apply(x) if _EMU else x
+
+
+def act_store(u, slope=0.0, mask_first=True, round_grad=True):
+    """act = ReLU (slope 0) / LeakyReLU(slope) followed by the bf16 store of the emulated path."""
+    if not _EMU:
+        return F.relu(u) if slope == 0.0 else F.leaky_relu(u, slope)
+    if not round_grad:
+        return _RoundFwd.apply(F.relu(u) if slope == 0.0 else F.leaky_relu(u, slope))
+    return _ActStore.apply(u, slope, mask_first)
+
+
+def _dead(b):
+    """A conv bias in front of an InstanceNorm: removed by the mean subtraction, so the CUDA path neither
+    adds it nor gives it a gradient; the emulation drops it to round the same values."""
+    return None if _EMU else b
+
+
 # ----------------------------------------------------------------------------- building blocks
-def instance_norm(x):
+def instance_norm(x, gamma=None, beta=None):
     """nn.InstanceNorm2d(affine=False): per-(n,c) biased variance, eps inside the sqrt
-    (model.py:16,131-133,139-140,167)."""
+    (model.py:16,131-133,139-140,167); with gamma / beta the AdaIN modulation of model.py:28-36.
+    Emulation: the kernels apply it as x*scale + shift with scale = gamma*rstd, shift = beta - mean*scale."""
     mu = x.mean(dim=(2, 3), keepdim=True)
     var = x.var(dim=(2, 3), unbiased=False, keepdim=True)
-    return (x - mu) / torch.sqrt(var + IN_EPS)
+    if _EMU:
+        rstd = 1.0 / torch.sqrt(var + IN_EPS)
+        scale = rstd if gamma is None else gamma * rstd
+        shift = -mu * scale if beta is None else beta - mu * scale
+        return x * scale + shift
+    xh = (x - mu) / torch.sqrt(var + IN_EPS)
+    return xh if gamma is None else gamma * xh + beta
+
+
+def style_affine(style, w, b):
+    """[gamma | beta] = Linear(style) (model.py:18,28). Emulation: bf16 style code and weight, fp32 output
+    and bias; the output's gradient is rounded before the two backward GEMMs (the bias sums the fp32 one)."""
+    if style.dim() == 4:
+        style = style.squeeze(-1).squeeze(-1)
+    if _EMU:
+        return gq(F.linear(wq(style), wq(w))) + b
+    return F.linear(style, w, b)
 
 
 def adain(x, style, w, b):
     """AdaIN.forward (model.py:20-36): gamma = first C outputs of the Linear, beta = last C."""
-    if style.dim() == 4:
-        style = style.squeeze(-1).squeeze(-1)
-    gb = F.linear(style, w, b)
+    gb = style_affine(style, w, b)
     c = x.shape[1]
     gamma = gb[:, :c].reshape(-1, c, 1, 1)
     beta = gb[:, c:].reshape(-1, c, 1, 1)
-    return gamma * instance_norm(x) + beta
+    return instance_norm(x, gamma, beta)
 
 
 def reflect_conv7(x, w, b):
@@ -49,23 +189,54 @@ def reflect_conv7(x, w, b):
     return F.conv2d(F.pad(x, (3, 3, 3, 3), mode="reflect"), w, b)
 
 
+def residual_block_forward(sd, p, x, style):
+    """ResidualBlockWithAdaIN.forward (model.py:51-55); `p` = key prefix of the block in `sd` ("" for a
+    stand-alone block's own state_dict). Storage points of the emulation: both conv outputs, the
+    activation between them, and the block output (after the residual add)."""
+    r = x
+    h = st(F.conv2d(x, wq(sd[p + "conv1.weight"]), _dead(sd[p + "conv1.bias"]), padding=1))
+    h = act_store(adain(h, style, sd[p + "adain1.style_modulation.weight"], sd[p + "adain1.style_modulation.bias"]))
+    h = st(F.conv2d(h, wq(sd[p + "conv2.weight"]), _dead(sd[p + "conv2.bias"]), padding=1))
+    h = adain(h, style, sd[p + "adain2.style_modulation.weight"], sd[p + "adain2.style_modulation.bias"])
+    return st(h + r)
+
+
 def generator_forward(sd, img, style, n_res=8):
     """StyleCycleGANGenerator.forward (model.py:145-151; layers :130-143)."""
-    x = F.relu(instance_norm(reflect_conv7(img, sd["content_encoder.0.weight"], sd["content_encoder.0.bias"])))
-    x = F.relu(instance_norm(F.conv2d(x, sd["content_encoder.3.weight"], sd["content_encoder.3.bias"], stride=2, padding=1)))
-    x = F.relu(instance_norm(F.conv2d(x, sd["content_encoder.6.weight"], sd["content_encoder.6.bias"], stride=2, padding=1)))
-    for i in range(n_res):  # ResidualBlockWithAdaIN.forward, model.py:51-55
-        p = f"decoder.{i}."
-        r = x
-        h = F.conv2d(x, sd[p + "conv1.weight"], sd[p + "conv1.bias"], padding=1)
-        h = F.relu(adain(h, style, sd[p + "adain1.style_modulation.weight"], sd[p + "adain1.style_modulation.bias"]))
-        h = F.conv2d(h, sd[p + "conv2.weight"], sd[p + "conv2.bias"], padding=1)
-        h = adain(h, style, sd[p + "adain2.style_modulation.weight"], sd[p + "adain2.style_modulation.bias"])
-        x = h + r
+    x = wq(img)
+    x = act_store(instance_norm(st(reflect_conv7(x, wq(sd["content_encoder.0.weight"]), _dead(sd["content_encoder.0.bias"])))))
+    x = act_store(instance_norm(st(F.conv2d(x, wq(sd["content_encoder.3.weight"]), _dead(sd["content_encoder.3.bias"]), stride=2, padding=1))))
+    x = act_store(instance_norm(st(F.conv2d(x, wq(sd["content_encoder.6.weight"]), _dead(sd["content_encoder.6.bias"]), stride=2, padding=1))))
+    for i in range(n_res):
+        x = residual_block_forward(sd, f"decoder.{i}.", x, style)
     k = n_res
-    x = F.relu(instance_norm(F.conv_transpose2d(x, sd[f"decoder.{k}.weight"], sd[f"decoder.{k}.bias"], stride=2, padding=1)))
-    x = F.relu(instance_norm(F.conv_transpose2d(x, sd[f"decoder.{k + 3}.weight"], sd[f"decoder.{k + 3}.bias"], stride=2, padding=1)))
-    return torch.tanh(reflect_conv7(x, sd[f"decoder.{k + 6}.weight"], sd[f"decoder.{k + 6}.bias"]))
+    x = act_store(instance_norm(st(F.conv_transpose2d(x, wq(sd[f"decoder.{k}.weight"]), _dead(sd[f"decoder.{k}.bias"]), stride=2, padding=1))))
+    # the IN + ReLU in front of the final conv writes the reflect-padded buffer; its gradient arrives as a
+    # bf16 padded tensor and is folded + masked in fp32 (no second rounding)
+    x = act_store(instance_norm(st(F.conv_transpose2d(x, wq(sd[f"decoder.{k + 3}.weight"]), _dead(sd[f"decoder.{k + 3}.bias"]), stride=2, padding=1))),
+                  round_grad=False)
+    if not _EMU:
+        return torch.tanh(reflect_conv7(x, sd[f"decoder.{k + 6}.weight"], sd[f"decoder.{k + 6}.bias"]))
+    xp = gq(F.pad(x, (3, 3, 3, 3), mode="reflect"))
+    # fp32 output; tanh' is applied in fp32 and the product is rounded for the dgrad / wgrad (the bias sums fp32)
+    return torch.tanh(gq(F.conv2d(xp, wq(sd[f"decoder.{k + 6}.weight"]))) + sd[f"decoder.{k + 6}.bias"].view(1, -1, 1, 1))
+
+
+def _first_conv(img, w, b, k, stride, pad, slope, pre_scale=None, pre_shift=None):
+    """The 3-channel first conv of SE / D / VGG + bias + (Leaky)ReLU. Emulation: the CUDA path runs it as a
+    GEMM over a gathered bf16 patch matrix, and its image gradient is the scatter-add (fp32) of the bf16
+    patch-matrix gradient -- restated with unfold so that the per-tap products are rounded the same way.
+    pre_scale / pre_shift: the VGG input renormalisation x*scale + shift, applied before the rounding."""
+    if not _EMU:
+        x = img if pre_scale is None else img * pre_scale + pre_shift
+        y = F.conv2d(x, w, b, stride=stride, padding=pad)
+        return F.relu(y) if slope == 0.0 else F.leaky_relu(y, slope)
+    x = wq(img if pre_scale is None else img * pre_scale + pre_shift)
+    n, c, h, wd = x.shape
+    oh, ow = (h + 2 * pad - k) // stride + 1, (wd + 2 * pad - k) // stride + 1
+    a = gq(F.unfold(x, k, padding=pad, stride=stride))                       # [n, c*k*k, oh*ow]
+    y = (wq(w).reshape(w.shape[0], -1) @ a).view(n, w.shape[0], oh, ow) + b.view(1, -1, 1, 1)
+    return act_store(y, slope)
 
 
 def _select_heads(all_out, domain_idx):
@@ -77,30 +248,37 @@ def _select_heads(all_out, domain_idx):
 def style_encoder_forward(sd, img, domain_idx, num_domains):
     """MultiDomainStyleEncoder.forward (model.py:89-118): 4x (conv4x4 s2 + ReLU), global average
     pool, one 1x1-conv head per domain, per-sample head selection."""
-    x = img
-    for i in (0, 2, 4, 6):
-        x = F.relu(F.conv2d(x, sd[f"shared_layers.{i}.weight"], sd[f"shared_layers.{i}.bias"], stride=2, padding=1))
-    x = x.mean(dim=(2, 3), keepdim=True)
+    x = _first_conv(img, sd["shared_layers.0.weight"], sd["shared_layers.0.bias"], 4, 2, 1, 0.0)
+    for i in (2, 4, 6):
+        x = act_store(F.conv2d(x, wq(sd[f"shared_layers.{i}.weight"]), sd[f"shared_layers.{i}.bias"], stride=2, padding=1))
+    x = st(x.mean(dim=(2, 3), keepdim=True))
+
+    def head(k):   # fp32 output and bias; the output's gradient is rounded for the two backward GEMMs
+        return (gq(F.conv2d(x, wq(sd[f"domain_branches.{k}.0.weight"]))) +
+                sd[f"domain_branches.{k}.0.bias"].view(1, -1, 1, 1)).flatten(1) if _EMU else \
+            F.conv2d(x, sd[f"domain_branches.{k}.0.weight"], sd[f"domain_branches.{k}.0.bias"]).flatten(1)
     if domain_idx is None:
-        return F.conv2d(x, sd["domain_branches.0.0.weight"], sd["domain_branches.0.0.bias"]).flatten(1)
-    outs = [F.conv2d(x, sd[f"domain_branches.{k}.0.weight"], sd[f"domain_branches.{k}.0.bias"]).flatten(1)
-            for k in range(num_domains)]
-    return _select_heads(torch.stack(outs, dim=1), domain_idx)
+        return head(0)
+    return _select_heads(torch.stack([head(k) for k in range(num_domains)], dim=1), domain_idx)
 
 
 def discriminator_forward(sd, img, domain_idx, num_domains):
     """MultiDomainDiscriminator.forward (model.py:186-214): conv+LeakyReLU, 3x (conv + IN +
     LeakyReLU), per-domain ZeroPad2d((1,0,1,0)) + conv4x4 p1 head, per-sample selection."""
-    x = F.leaky_relu(F.conv2d(img, sd["shared_layers.0.weight"], sd["shared_layers.0.bias"], stride=2, padding=1), LRELU)
+    x = _first_conv(img, sd["shared_layers.0.weight"], sd["shared_layers.0.bias"], 4, 2, 1, LRELU)
     for i in (2, 5, 8):
-        x = F.conv2d(x, sd[f"shared_layers.{i}.weight"], sd[f"shared_layers.{i}.bias"], stride=2, padding=1)
-        x = F.leaky_relu(instance_norm(x), LRELU)
+        x = st(F.conv2d(x, wq(sd[f"shared_layers.{i}.weight"]), _dead(sd[f"shared_layers.{i}.bias"]), stride=2, padding=1))
+        # the gradient of the last trunk activation is stored by the head GEMM before LeakyReLU' is applied
+        x = act_store(instance_norm(x), LRELU, mask_first=(i != 8))
     xp = F.pad(x, (1, 0, 1, 0))
+
+    def head(k):
+        return gq(F.conv2d(xp, wq(sd[f"domain_branches.{k}.1.weight"]), padding=1)) + \
+            sd[f"domain_branches.{k}.1.bias"].view(1, -1, 1, 1) if _EMU else \
+            F.conv2d(xp, sd[f"domain_branches.{k}.1.weight"], sd[f"domain_branches.{k}.1.bias"], padding=1)
     if domain_idx is None:
-        return F.conv2d(xp, sd["domain_branches.0.1.weight"], sd["domain_branches.0.1.bias"], padding=1)
-    outs = [F.conv2d(xp, sd[f"domain_branches.{k}.1.weight"], sd[f"domain_branches.{k}.1.bias"], padding=1)
-            for k in range(num_domains)]
-    return _select_heads(torch.stack(outs, dim=1), domain_idx)
+        return head(0)
+    return _select_heads(torch.stack([head(k) for k in range(num_domains)], dim=1), domain_idx)
 
 
 # ----------------------------------------------------------------------------- VGG loss
@@ -116,6 +294,8 @@ def vgg_features(vgg_sd, img):
     Input renormalisation: losses.py:49-56."""
     mean = torch.tensor(VGG_MEAN, device=img.device).view(1, 3, 1, 1)
     std = torch.tensor(VGG_STD, device=img.device).view(1, 3, 1, 1)
+    if _EMU:
+        return _vgg_features_emulated(vgg_sd, img, 0.5 / std, (0.5 - mean) / std)
     x = ((img + 1) / 2 - mean) / std
     feats = []
     for j, idx in enumerate(VGG_CONV_IDX):
@@ -123,6 +303,34 @@ def vgg_features(vgg_sd, img):
         feats.append(x)
         if j in (1, 3):
             x = F.max_pool2d(x, 2)
+    return feats
+
+
+def _vgg_features_emulated(vgg_sd, img, scale, shift):
+    """Storage points of the CUDA VGG pass: renormalised bf16 patch matrix, every tap (bf16), the pooled
+    maps' gradients. Each tap is returned as (feature for the Gram term, feature for the content term):
+    the gradient tensor of a tap receives the conv / pool path first, then the content L1 (tap 4 only),
+    then the Gram term, re-rounded after each addition (aux operands of l1_loss_bf16_bwd / gram_bwd)."""
+    feats = []
+    x = None
+    for j, idx in enumerate(VGG_CONV_IDX):
+        w, b = vgg_sd[f"{idx}.weight"], vgg_sd[f"{idx}.bias"]
+        if j == 0:
+            f = _first_conv(img, w, b, 3, 1, 1, 0.0, scale, shift)
+        else:
+            f = act_store(F.conv2d(x, wq(w), b, padding=1))
+        if j == 4:
+            main, gram_side, content_side = None, f, None
+        elif j == 3:
+            main, content_side, gram_side = _Tap.apply(f, 2)
+        else:
+            main, gram_side = _Tap.apply(f, 1)
+            content_side = None
+        feats.append((gram_side, content_side))
+        if j in (1, 3):
+            x = gq(F.max_pool2d(main, 2))
+        else:
+            x = main
     return feats
 
 
@@ -138,6 +346,9 @@ def vgg_loss(vgg_sd, generated, real_style, real_content):
     fg = vgg_features(vgg_sd, generated)
     fs = vgg_features(vgg_sd, real_style)
     fc = vgg_features(vgg_sd, real_content)
+    if _EMU:   # (Gram-term view, content-term view) per tap, see _vgg_features_emulated
+        style = sum(F.l1_loss(gram(a[0]), gram(b[0])) for a, b in zip(fg, fs))
+        return F.l1_loss(fg[3][1], fc[3][1]), style
     style = sum(F.l1_loss(gram(a), gram(b)) for a, b in zip(fg, fs))
     content = F.l1_loss(fg[3], fc[3])   # 'relu_4_1' = ReLU after the 4th conv
     return content, style

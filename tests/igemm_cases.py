@@ -115,23 +115,19 @@ def case_convT(n, c, h, w, k, seed=0, which="fwd"):
     return rel_err(dw, wf.grad), 2e-3
 
 
-def case_final_conv(n, h, w, mode, seed=0):
-    """The generator's last layer (model.py:141) as executed: 7x7 'valid' conv 64->3 on the reflect-padded
-    activation + bias + tanh, fp32 NCHW out. mode selects the kernel variant (test hook)."""
+def case_final_conv(n, h, w, seed=0):
+    """A 7x7 'valid' conv 64->3 + bias + tanh (fp32 NCHW out) through the generic per-tap kernel with a
+    16-wide tile (the path msig_conv2d_fwd takes for <= 16 output channels, e.g. the discriminator heads)."""
     ops.ensure_init()
-    L.load().msig_debug_set_strip_mode(mode)
-    try:
-        xp = _bf(_rand((n, 64, h + 6, w + 6), seed)).to(DEV)
-        wt = _bf(_rand((3, 64, 7, 7), seed + 1, 1.0 / (64 * 49) ** 0.5)).to(DEV)
-        b = _rand((3,), seed + 2).to(DEV)
-        ref = torch.tanh(F.conv2d(xp.float(), wt.float(), b))
-        wpk = ops.wpack(L.WPACK_FWD, wt.float().contiguous(), 3, 64, 7, 7)
-        g = ops.conv_geom(n, h + 6, w + 6, 64, 3, 7, 7, 1, 0, 0, h, w)
-        y = ops.conv2d_fwd(nhwc(xp), wpk, g, ops.epilogue(bias=b, act=L.ACT_TANH, out_layout=L.OUT_F32_NCHW))
-        torch.cuda.synchronize()
-        return rel_err(y, ref), 2e-3
-    finally:
-        L.load().msig_debug_set_strip_mode(1)
+    xp = _bf(_rand((n, 64, h + 6, w + 6), seed)).to(DEV)
+    wt = _bf(_rand((3, 64, 7, 7), seed + 1, 1.0 / (64 * 49) ** 0.5)).to(DEV)
+    b = _rand((3,), seed + 2).to(DEV)
+    ref = torch.tanh(F.conv2d(xp.float(), wt.float(), b))
+    wpk = ops.wpack(L.WPACK_FWD, wt.float().contiguous(), 3, 64, 7, 7)
+    g = ops.conv_geom(n, h + 6, w + 6, 64, 3, 7, 7, 1, 0, 0, h, w)
+    y = ops.conv2d_fwd(nhwc(xp), wpk, g, ops.epilogue(bias=b, act=L.ACT_TANH, out_layout=L.OUT_F32_NCHW))
+    torch.cuda.synchronize()
+    return rel_err(y, ref), 2e-3
 
 
 def case_narrow_fwd(n, h, w, seed=0):
@@ -261,9 +257,8 @@ CASES = {
     "ring_dgrad_3x3_64_256w": lambda: case_conv_dgrad(2, 64, 48, 256, 64, 3, 1, 1),
     "fwd_4x4s2_64_128": lambda: case_conv_fwd(2, 64, 64, 64, 128, 4, 2, 1, act=L.ACT_LRELU),
     "fwd_4x4s2_256_512": lambda: case_conv_fwd(2, 256, 32, 32, 512, 4, 2, 1),
-    "final7x7_pertap": lambda: case_final_conv(2, 64, 256, 0),
-    "final7x7_strip": lambda: case_final_conv(2, 64, 256, 1),
-    "final7x7_strip_ragged": lambda: case_final_conv(1, 40, 200, 1),
+    "final7x7_pertap": lambda: case_final_conv(2, 64, 256),
+    "final7x7_pertap_ragged": lambda: case_final_conv(1, 40, 200),
     "narrow_fwd_7x7": lambda: case_narrow_fwd(2, 64, 256),
     "narrow_fwd_7x7_ragged": lambda: case_narrow_fwd(3, 40, 200),
     "narrow_fwd_7x7_small": lambda: case_narrow_fwd(2, 16, 16),

@@ -51,19 +51,6 @@ def case_patch_scatter(n, c, h, w, r, stride, pad, reflect, affine=False, seed=0
     return rel_err(got, x.grad), 1e-5
 
 
-def case_reflect_pad(n, c, h, w, pad, seed=0):
-    ops.ensure_init()
-    x = _bf(_rand((n, c, h, w), seed)).to(DEV)
-    ref = F.pad(x.float(), (pad,) * 4, mode="reflect")
-    y = ops.reflect_pad_fwd(nhwc(x), pad)
-    dy = _bf(_rand(tuple(ref.shape), seed + 1)).to(DEV)
-    xr = x.float().clone().requires_grad_(True)
-    (F.pad(xr, (pad,) * 4, mode="reflect") * dy.float()).sum().backward()
-    dx = ops.reflect_pad_bwd(nhwc(dy), pad)
-    torch.cuda.synchronize()
-    return max(rel_err(nchw(y), ref), rel_err(nchw(dx), xr.grad)), 1e-2
-
-
 def case_norm(n, c, h, w, act, adain, residual, seed=0):
     """InstanceNorm / AdaIN (+act, +residual) forward and backward (dx, dgamma, dbeta)."""
     ops.ensure_init()
@@ -108,9 +95,8 @@ def case_act_bwd(seed=0):
     dy = _bf(_rand((4, 32, 32, 64), seed + 1)).to(DEV)
     ref = dy.float() * torch.where(y.float() > 0, 1.0, 0.2)
     got = ops.act_bwd(dy, y, L.ACT_LRELU)
-    s = ops.add_bf16(dy, y)
     torch.cuda.synchronize()
-    return max(rel_err(got, ref), rel_err(s, dy.float() + y.float())), 1e-2
+    return rel_err(got, ref), 1e-2
 
 
 def case_colsum(seed=0):
@@ -151,7 +137,7 @@ def case_heads(seed=0):
     ops.ensure_init()
     n, nd, sd = 5, 10, 256
     allv = _rand((n, nd * sd), seed).to(DEV)
-    idx = torch.tensor([0, 3, 9, 1, 3], device=DEV)
+    idx = torch.tensor([0, 3, 9, -9, -1], device=DEV)       # negative indices wrap like torch's
     got = ops.head_gather(allv, idx, n, 1, nd, sd, True)
     ref = allv.view(n, nd, sd)[torch.arange(n), idx]
     dout = _rand((n, sd), seed + 1).to(DEV)
@@ -161,14 +147,26 @@ def case_heads(seed=0):
     # discriminator layout [n][pix][16] (heads padded to 16)
     pix = 256
     alld = _rand((n, pix, 16), seed + 2).to(DEV)
-    gd = ops.head_gather(alld, idx, n, pix, 16, 1, False)
-    refd = alld[torch.arange(n), :, idx]
-    dd = ops.head_scatter(gd, idx, n, pix, 16, 1, False).view(n, pix, 16)
+    gd = ops.head_gather(alld, idx, n, pix, 16, 1, False, heads=nd)
+    refd = alld[:, :, :nd][torch.arange(n), :, idx]
+    dd = ops.head_scatter(gd, idx, n, pix, 16, 1, False, heads=nd).view(n, pix, 16)
     drefd = torch.zeros(n, pix, 16, device=DEV)
-    drefd[torch.arange(n), :, idx] = refd
+    drefd[torch.arange(n), :, idx % nd] = refd
+    # out-of-range index: never read out of bounds -- NaN output, nothing routed backward (the reference
+    # raises IndexError; host-resident indices do too, see ops.domain_index)
+    bad = torch.tensor([0, 10, 2, -11, 4], device=DEV)
+    gb = ops.head_gather(allv, bad, n, 1, nd, sd, True)
+    db = ops.head_scatter(dout, bad, n, 1, nd, sd, True).view(n, nd, sd)
     torch.cuda.synchronize()
+    poisoned = bool(torch.isnan(gb[1]).all() and torch.isnan(gb[3]).all() and not torch.isnan(gb[[0, 2, 4]]).any()
+                    and float(db[1].abs().max()) == 0.0 and float(db[3].abs().max()) == 0.0)
+    raised = False
+    try:
+        ops.domain_index(torch.tensor([0, 10]), nd, 2, DEV)
+    except IndexError:
+        raised = True
     e = [(got - ref).abs().max().item(), (dall.view(n, nd, sd) - dref).abs().max().item(),
-         (gd - refd).abs().max().item(), (dd - drefd).abs().max().item()]
+         (gd - refd).abs().max().item(), (dd - drefd).abs().max().item(), 0.0 if (poisoned and raised) else 1.0]
     return max(e), 0.0
 
 
@@ -195,11 +193,51 @@ def case_losses(seed=0):
     (lref3 * gs).backward()
     l3 = ops.mse_const_fwd(d, 1.0)
     g3 = ops.mse_const_bwd(d, 1.0, gs)
+    # tensor target (the reference's calling convention, trainer.py:85-86,103)
+    tgt = _rand((4, 1, 16, 16), seed + 5).to(DEV)
+    dr2 = d.clone().requires_grad_(True)
+    lref4 = F.mse_loss(dr2, tgt)
+    (lref4 * gs).backward()
+    l4 = ops.mse_loss_fwd(d, tgt)
+    g4 = ops.mse_loss_bwd(d, tgt, gs)
     torch.cuda.synchronize()
     e = [abs(l1.item() - lref.item()) / lref.item(), rel_err(g1, ar.grad),
          abs(l2.item() - lref2.item()) / lref2.item(), rel_err(g2, far.grad) / 100,  # grads ~1e-5 in bf16
-         abs(l3.item() - lref3.item()) / lref3.item(), rel_err(g3, dr.grad)]
+         abs(l3.item() - lref3.item()) / lref3.item(), rel_err(g3, dr.grad),
+         abs(l4.item() - lref4.item()) / lref4.item(), rel_err(g4, dr2.grad)]
     return max(e), 1e-4
+
+
+def case_determinism(seed=0):
+    """Every reduction of the step is deterministic (two-stage sums in a fixed order, no fp32 atomics):
+    two launches on the same data give identical bits, at sizes that span many blocks."""
+    ops.ensure_init()
+    dy = _bf(_rand((300000, 64), seed)).to(DEV)
+    img = _rand((8, 3, 256, 256), seed + 1).to(DEV)
+    a = _rand((8, 3, 256, 256), seed + 2).to(DEV)
+    fa, fb = _bf(_rand((4, 64, 64, 128), seed + 3)).to(DEV), _bf(_rand((4, 64, 64, 128), seed + 4)).to(DEV)
+    ga, gb = _rand((1500, 1500), seed + 5).to(DEV), _rand((1500, 1500), seed + 6).to(DEV)
+    flat = _rand((5_000_003,), seed + 7).to(DEV)
+
+    def run():
+        db = torch.zeros(64, device=DEV)
+        ops.colsum(dy, 64, db, accumulate=False)
+        cs = torch.zeros(3, device=DEV)
+        ops.nchw_chansum(img, cs, accumulate=False)
+        ss = torch.zeros((), device=DEV)
+        ops.sumsq(flat, ss)
+        gl, _ = ops.gram_l1(ga, gb)
+        return [db.clone(), cs.clone(), ops.l1_loss_f32_fwd(img, a).clone(), ops.l1_loss_bf16_fwd(fa, fb).clone(),
+                ops.mse_const_fwd(a, 1.0).clone(), ss.clone(), gl.clone()]
+    r1 = run()
+    torch.empty(64 << 20, dtype=torch.uint8, device=DEV).zero_()      # perturb scheduling / cache state
+    r2 = run()
+    torch.cuda.synchronize()
+    diff = max(float((x - y).abs().max()) for x, y in zip(r1, r2))
+    ref = [dy.float().sum(0), img.sum((0, 2, 3)), (img - a).abs().mean(), (fa.float() - fb.float()).abs().mean(),
+           ((a - 1) ** 2).mean(), (flat.double() ** 2).sum().float(), (ga - gb).abs().mean()]
+    acc = max(rel_err(x, y) for x, y in zip(r1, ref))
+    return (1.0 if diff != 0.0 else 0.0) + acc, 1e-4
 
 
 def case_gram_l1(seed=0):
@@ -227,7 +265,8 @@ def case_norm_pad(n=2, h=24, w=40, c=64, pad=3, seed=0):
     ops.ensure_init()
     x = _rand((n, h, w, c), seed).to(DEV).to(torch.bfloat16)
     st = ops.in_stats(x)
-    y_ref = ops.reflect_pad_fwd(ops.norm_act_fwd(x, st, L.ACT_RELU), pad)
+    y_ref = F.pad(ops.norm_act_fwd(x, st, L.ACT_RELU).float().permute(0, 3, 1, 2), (pad,) * 4,
+                  mode="reflect").permute(0, 2, 3, 1)           # a reflect pad only copies: bit-exact
     y = ops.norm_act_fwd_pad(x, st, L.ACT_RELU, pad)
     e_fwd = (y.float() - y_ref.float()).abs().max().item()            # same arithmetic: bit-exact
     dyp = _rand((n, h + 2 * pad, w + 2 * pad, c), seed + 1).to(DEV).to(torch.bfloat16)
@@ -277,17 +316,17 @@ CASES = {
     "scatter_7x7_reflect": lambda: case_patch_scatter(2, 3, 32, 40, 7, 1, 3, True),
     "scatter_4x4s2_zero": lambda: case_patch_scatter(2, 3, 32, 32, 4, 2, 1, False),
     "scatter_3x3_affine": lambda: case_patch_scatter(1, 3, 16, 24, 3, 1, 1, False, affine=True),
-    "reflect_pad": lambda: case_reflect_pad(2, 64, 24, 32, 3),
     "in_relu_64": lambda: case_norm(2, 64, 32, 32, L.ACT_RELU, False, False),
     "in_lrelu_512": lambda: case_norm(3, 512, 16, 16, L.ACT_LRELU, False, False),
     "adain_relu_256": lambda: case_norm(2, 256, 32, 32, L.ACT_RELU, True, False),
     "adain_res_256": lambda: case_norm(2, 256, 64, 64, L.ACT_NONE, True, True),
     "in_relu_128_big": lambda: case_norm(1, 128, 128, 128, L.ACT_RELU, False, False),
-    "act_bwd_add": case_act_bwd,
+    "act_bwd": case_act_bwd,
     "colsum": case_colsum,
     "pool": case_pool,
     "heads": case_heads,
     "losses": case_losses,
+    "determinism": case_determinism,
     "gram_l1": case_gram_l1,
     "norm_pad_fused": case_norm_pad,
     "norm_pad_fused_256": lambda: case_norm_pad(1, 256, 256, 64, 3, 3),
