@@ -1,7 +1,11 @@
 #!/usr/bin/env python
 """Benchmark of the hot path: one full G+D training step (trainer.train_step) at 256x256.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config c3|c4|c5] [--batch B] [--impl ours|reference]
+
+--config (BASELINE.json `configs`): c3 (default; the driver's line) = 256x256, batch 32 per GPU (weak scaling
+when N > 1; at N = 8 this IS configs[3]); c4 = configs[3] as written: 256x256, GLOBAL batch 256, i.e.
+256/N per GPU (strong scaling: N = 2 / 4 / 8 -> 128 / 64 / 32); c5 = configs[4]: 512x512, batch 8 per GPU.
 
 Prints ONE JSON line (rank 0). Contract fields: metric/value/unit (BASELINE.json's metric: train
 images/sec at 256^2), e2e (same metric through the public trainer API with pinned HOST batches and a
@@ -25,7 +29,15 @@ sys.path.insert(0, ROOT)
 
 S = 256
 ND = 10
-WORKLOAD = "full G+D training step 256x256 batch 32 per GPU (BASELINE.json configs[2]; configs[3] at 8 GPUs)"
+CONFIGS = {
+    "c3": dict(size=256, batch=lambda world: 32, scaling="weak",
+               workload="full G+D training step 256x256 batch 32 per GPU (BASELINE.json configs[2]; configs[3] at 8 GPUs)"),
+    "c4": dict(size=256, batch=lambda world: 256 // world, scaling="strong",
+               workload="data-parallel training 256x256 global batch 256 (BASELINE.json configs[3]): 256/N per GPU"),
+    "c5": dict(size=512, batch=lambda world: 8, scaling="weak",
+               workload="512x512 multi-domain training batch 8 per GPU (BASELINE.json configs[4])"),
+}
+WORKLOAD = CONFIGS["c3"]["workload"]
 
 
 def peaks():
@@ -76,15 +88,16 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_baseline(sample_steps=2, threads=None):
-    """The reference's CPU path (oracle port, fp32, all host threads) on a bounded sample: B=1, 256^2."""
+def cpu_baseline(sample_steps=5, threads=None, size=S):
+    """The reference's CPU path (oracle port, fp32, all host threads) on a bounded sample: B=1 (SURVEY 8d:
+    1 warm-up + 5 timed steps, median and min -- host timing is noisy)."""
     import torch
     from oracle import oracle as O
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     state = O.init_state(0, ND)
     tr = O.OracleTrainer(state, O.seeded_vgg_state(), ND)
-    batch = O.synthetic_batch(1, S, ND)
+    batch = O.synthetic_batch(1, size, ND)
     tr.train_step(batch, 0)                      # warm-up
     ts = []
     for _ in range(sample_steps):
@@ -94,8 +107,59 @@ def cpu_baseline(sample_steps=2, threads=None):
     ts.sort()
     med = ts[len(ts) // 2]
     return {"value": 1.0 / med, "unit": "images/sec", "cores": threads, "kind": "port",
-            "sample": f"oracle port of trainer.train_step, B=1 256x256 nd={ND}, fp32, 1 warm-up + {sample_steps} timed steps "
-                      f"(median {med:.2f} s/step, min {ts[0]:.2f})"}
+            "median_s_per_step": med, "min_s_per_step": ts[0],
+            "sample": f"oracle port of trainer.train_step, B=1 {size}x{size} nd={ND}, fp32, 1 warm-up + {sample_steps} timed "
+                      f"steps (median {med:.2f} s/step, min {ts[0]:.2f})"}
+
+
+def eager_cuda_baseline(dev, batch, size, steps=3):
+    """The honest same-box bar: the reference's arithmetic as PyTorch-eager CUDA ops
+    (cuDNN / cuBLAS / ATen, i.e. what the reference itself runs on a B200) on the SAME train step and batch
+    -- the oracle restatement moved to the device -- (a) fp32 with the cuDNN TF32 default, (b) under bf16
+    autocast with channels_last tensors. Reported beside our number; it is NOT the --impl reference arm."""
+    import torch
+    from oracle import oracle as O
+    out = {}
+    for name in ("fp32_tf32conv", "bf16_autocast_channels_last"):
+        try:
+            cl = name.startswith("bf16")
+            state = {k: {n: (t.to(dev).contiguous(memory_format=torch.channels_last) if (cl and t.dim() == 4) else t.to(dev))
+                         for n, t in sd.items()} for k, sd in O.init_state(0, ND).items()}
+            vgg = {n: (t.to(dev).contiguous(memory_format=torch.channels_last) if (cl and t.dim() == 4) else t.to(dev))
+                   for n, t in O.seeded_vgg_state().items()}
+            tr = O.OracleTrainer(state, vgg, ND)
+            b = {k: v.to(dev) for k, v in O.synthetic_batch(batch, size, ND).items()}
+            if cl:
+                b = {k: (v.contiguous(memory_format=torch.channels_last) if v.dim() == 4 else v) for k, v in b.items()}
+
+            def step():
+                if cl:
+                    with torch.autocast("cuda", dtype=torch.bfloat16):
+                        return tr.train_step(b, 0)
+                return tr.train_step(b, 0)
+            torch.cuda.reset_peak_memory_stats(dev)
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                step()
+            e1.record()
+            torch.cuda.synchronize(dev)
+            ms = e0.elapsed_time(e1) / steps
+            out[name] = {"value": batch / (ms * 1e-3), "unit": "images/sec", "ms_per_step": ms,
+                         "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+            del tr, state, vgg, b
+        except Exception as e:          # e.g. out of memory at a large batch: reported, not fatal
+            out[name] = {"unavailable": f"{type(e).__name__}: {str(e)[:160]}"}
+        import gc
+        gc.collect()
+        torch.cuda.empty_cache()
+    out["note"] = (f"oracle restatement of trainer.train_step as PyTorch-eager CUDA ops, B={batch} {size}x{size} nd={ND}, "
+                   f"2 warm-up + {steps} timed steps, CUDA events; torch {torch.__version__}, cudnn.allow_tf32="
+                   f"{torch.backends.cudnn.allow_tf32}")
+    return out
 
 
 def run_reference(args):
@@ -106,9 +170,11 @@ def run_reference(args):
     from oracle import oracle as O
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
+    cfg = CONFIGS[args.config]
+    size = cfg["size"]
     state = O.init_state(0, ND)
     tr = O.OracleTrainer(state, O.seeded_vgg_state(), ND)
-    batch = O.synthetic_batch(1, S, ND)
+    batch = O.synthetic_batch(1, size, ND)
     for _ in range(max(args.warmup, 0)):
         tr.train_step(batch, 0)
     t0 = time.time()
@@ -116,13 +182,13 @@ def run_reference(args):
         tr.train_step(batch, 0)
     dt = time.time() - t0
     v = args.steps * 1.0 / dt
-    line = {"impl": "reference", "metric": "train images/sec at 256^2", "value": v, "unit": "images/sec",
+    line = {"impl": "reference", "metric": f"train images/sec at {size}^2", "value": v, "unit": "images/sec",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": "each step = B=1 256x256 train_step on the host CPU",
+            "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["workload"], "sample": f"each step = B=1 {size}x{size} train_step on the host CPU",
                        "num_domains": ND},
             "cpu_baseline": {"value": v, "unit": "images/sec", "cores": threads, "kind": "port",
-                             "sample": f"B=1 256x256 train_step x {args.steps} (oracle port of the reference CPU path)"},
+                             "sample": f"B=1 {size}x{size} train_step x {args.steps} (oracle port of the reference CPU path)"},
             "e2e": {"value": v, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -179,7 +245,10 @@ def ncu_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
     (profiles/ncu_fprop_r1.txt, first line = plain forward launch)."""
     try:
-        line = open(os.path.join(ROOT, "profiles", "ncu_fprop_r1.txt")).readline()
+        path = os.path.join(ROOT, "profiles", "ncu_fprop_r2.txt")
+        if not os.path.exists(path):
+            path = os.path.join(ROOT, "profiles", "ncu_fprop_r1.txt")
+        line = open(path).readline()
         kv = dict(t.split("=") for t in line.split() if "=" in t)
         return (float(kv["dram_read_MB"]) + float(kv["dram_write_MB"])) * 1e6
     except Exception:
@@ -205,18 +274,24 @@ def time_inference(torch, T, O, dev, tr, batch=16, iters=10):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    host_out = torch.empty(out.shape, dtype=out.dtype).pin_memory()
+    # end to end through the batched inference driver: pinned host images in, translated images out (pinned
+    # host), H2D(i+1) / replay(i) / D2H(i-1) overlapped on three streams (inference.translate_batches)
+    n_e2e = 4 * iters
+    list(I.translate_batches(G, SE, ((src_h, ref_h, dom_h) for _ in range(4))))      # warm-up: captures both slots
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(iters):
-        out = I.translate(G, SE, src_h, ref_h, dom_h)
-        host_out.copy_(out, non_blocking=True)
-        torch.cuda.synchronize()
-    e2e_ms = (time.perf_counter() - t0) * 1000.0 / iters
+    checksum = 0.0
+    for _, host in I.translate_batches(G, SE, ((src_h, ref_h, dom_h) for _ in range(n_e2e))):
+        checksum += float(host[0, 0, 0, 0])         # the consumer touches every result on the host
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1000.0 / n_e2e
+    host_out = host
     flops = batch * 100.28e9                     # 96.96 (G) + 3.32 (SE) GF / image
     return {"workload": "inference.py style injection: src+ref 256x256 batch %d, SE + G forward (BASELINE.json configs[1])" % batch,
             "value": batch / (ms * 1e-3), "unit": "images/sec", "ms_per_batch": ms,
             "e2e": {"value": batch / (e2e_ms * 1e-3), "unit": "images/sec",
                     "h2d_bytes_per_step": 2 * src_h.numel() * 4 + dom_h.numel() * 8, "d2h_bytes_per_step": host_out.numel() * 4},
+            "e2e_path": "inference.translate_batches (double-buffered pinned staging, 3 streams, 2 captured graphs)",
             "tflops": flops / (ms * 1e-3) / 1e12}
 
 
@@ -235,8 +310,16 @@ def run_ours(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         torch.distributed.init_process_group("nccl", device_id=dev)
-    B = args.batch
+    cfg = CONFIGS[args.config]
+    S = args.size or cfg["size"]
+    B = args.batch or cfg["batch"](world)
+    if B < 1 or (args.config == "c4" and not args.batch and 256 % world):
+        raise SystemExit(f"config {args.config}: world size {world} does not divide the global batch")
     pk = peaks()
+
+    eager = None
+    if world == 1 and rank == 0 and not args.no_eager_baseline:
+        eager = eager_cuda_baseline(dev, B, S)      # first: it needs ~2.2 GB per sample of its own
 
     torch.manual_seed(0)
     tr = T.MultiDomainStyleCycleGAN(dev, 200, 2e-4, 1e-4, dict(O.DEFAULT_LOSS_WEIGHTS), ND, vgg_state=O.seeded_vgg_state())
@@ -250,6 +333,7 @@ def run_ours(args):
             torch.distributed.barrier()
             torch.cuda.synchronize()
 
+    torch.cuda.reset_peak_memory_stats(dev)
     for _ in range(max(args.warmup, 3)):
         out = tr.train_step(devb, 0)
     barrier()
@@ -289,16 +373,19 @@ def run_ours(args):
     value = B * world * args.steps / (ms / 1000.0)
     e2e = B * world * args.steps / (e2e_ms / 1000.0)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
-    kms, kflops = time_dominant_kernel(torch, ops, L, B)
+    peak_mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+    kb = min(B, 32)                              # roofline kernels are timed at (up to) batch 32
+    kms, kflops = time_dominant_kernel(torch, ops, L, kb)
     ach = kflops / (kms * 1e-3) / 1e12
-    hms, hbytes = time_hbm_kernel(torch, ops, L, B)
+    hms, hbytes = time_hbm_kernel(torch, ops, L, kb)
     hach = hbytes / (hms * 1e-3) / 1e9
-    step_tf = step_flops(B) / (ms / args.steps * 1e-3) / 1e12
+    step_tf = step_flops(B, S) / (ms / args.steps * 1e-3) / 1e12
     line = {
-        "metric": "train images/sec at 256^2", "value": value, "unit": "images/sec", "n_gpus": world,
+        "metric": f"train images/sec at {S}^2", "value": value, "unit": "images/sec", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world, "image": S, "num_domains": ND,
+        "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": cfg["workload"], "name": args.config, "per_gpu_batch": B, "global_batch": B * world,
+                   "image": S, "num_domains": ND, "peak_mem_gb": peak_mem,
                    "parallelism": f"dp{world}", "l2": "working set >> L2 (tens of GB of activations per step)",
                    "accumulate": "fp32", "loss_epoch": 0,
                    "cuda_graph": "step replayed from 4 captured graph segments (warm-up steps include the capture)"},
@@ -307,23 +394,28 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": ach, "peak": pk["bf16_burst"], "unit": "TFLOP/s", "frac": ach / pk["bf16_burst"],
                      "traffic": ncu_traffic(),
-                     "kernel": "fprop2_kernel (tcgen05 cta_group::2 implicit GEMM) conv3x3 256->256 @64x64, batch %d" % B,
+                     "kernel": "fprop2_kernel (tcgen05 cta_group::2 implicit GEMM) conv3x3 256->256 @64x64, batch %d" % kb,
                      "kernel_ms": kms, "algorithmic_flops_per_launch": kflops,
-                     "algorithmic_bytes_per_launch": 2.0 * (2 * B * 4096 * 256 + 256 * 2304),
+                     "algorithmic_bytes_per_launch": 2.0 * (2 * kb * 4096 * 256 + 256 * 2304),
                      "traffic_note": "dram__bytes_read+write of one launch (ncu --set full, profiles/ncu_fprop_r1.txt); "
                                      "below the algorithmic bytes because most of the output is still in L2 when the kernel ends",
                      "peak_source": pk["source"] + " (burst, kernel timed alone, L2 flushed)"},
         "roofline_hbm": {"bound": "hbm", "achieved": hach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hach / pk["hbm_gbs"],
-                         "kernel": "norm_act_fwd_kernel (IN/AdaIN apply + ReLU) [%d,64,64,256] bf16, 1R+1W" % B,
+                         "kernel": "norm_act_fwd_kernel (IN/AdaIN apply + ReLU) [%d,64,64,256] bf16, 1R+1W" % kb,
                          "kernel_ms": hms, "algorithmic_bytes_per_launch": hbytes, "peak_source": pk["source"]},
         "step_tflops": {"achieved": step_tf, "peak_sustained": pk["bf16_sustained"], "frac": step_tf / pk["bf16_sustained"],
-                        "flops_per_step": step_flops(B), "note": "necessary algorithmic FLOPs (SURVEY 8d) / step time"},
+                        "flops_per_step": step_flops(B, S), "note": "necessary algorithmic FLOPs (SURVEY 8d) / step time"},
     }
-    if world == 1:
+    if eager is not None:
+        line["eager_cuda_baseline"] = eager
+        for k, v in eager.items():
+            if isinstance(v, dict) and "value" in v:
+                v["ours_over_this"] = value / v["value"]
+    if world == 1 and args.config == "c3" and not args.no_inference:
         line["inference"] = time_inference(torch, T, O, dev, tr)
         line["inference"]["frac_of_sustained_peak"] = line["inference"]["tflops"] / pk["bf16_sustained"]
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline()
+        line["cpu_baseline"] = cpu_baseline(size=S)
     print(json.dumps(line), flush=True)
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -334,9 +426,13 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS), help="BASELINE.json configs[2] / [3] / [4]")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch (default: the config's)")
+    ap.add_argument("--size", type=int, default=0, help="image side (default: the config's)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
+    ap.add_argument("--no-inference", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

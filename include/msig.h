@@ -342,6 +342,18 @@ int msig_adam_step_dev(float* param, const float* grad, float* exp_avg, float* e
                        float grad_scale, float lr, float beta1, float beta2, float eps,
                        int32_t* step_counter, float ema_beta, void* stream);
 
+/* ---- GPU-side training augmentation (dataset.py:16-22: RandomResizedCrop + 0/90/180/270 rotation +
+ *      ToTensor + Normalize(0.5)) for GIVEN draws ---------------------------------------------------
+ * src: uint8 [n][h][w][3] decoded images; boxes: int32 [n][4] = (top, left, height, width) of each crop;
+ * quarter_turns: int32 [n], counter-clockwise multiples of 90 degrees (NULL = none); out: fp32
+ * [n][3][size][size] in [-1, 1]. Bit-exact with Pillow's 8-bit bilinear resample (22-bit fixed-point
+ * coefficients, horizontal then vertical pass, each rounded to uint8) + torchvision to_tensor / normalize.
+ * workspace: msig_augment_workspace bytes (the horizontally resampled rows). Shrink factors up to 8. */
+size_t msig_augment_workspace(int32_t n, int32_t h, int32_t w, int32_t size);
+int msig_augment_u8(const void* src, int32_t n, int32_t h, int32_t w, const int32_t* boxes,
+                    const int32_t* quarter_turns, int32_t size, float* out, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -8,6 +8,7 @@ of the reference's main() are out of scope; `translate()` is the batched forward
 """
 import os
 import random
+import weakref
 
 import torch
 
@@ -115,15 +116,64 @@ def apply_style_mode(style_vectors, mode, noise_level=0.1):
     return style
 
 
-_translate_graphs = {}   # (generator, style encoder, shapes) -> captured forward, or "warm" after the first eager call
-
-
 def _translate_eager(generator, style_encoder, src, ref, ref_domain, style, dev):
     src = src.to(dev, non_blocking=True)
     if style is None:
         y = None if ref_domain is None else ref_domain.to(dev, non_blocking=True)
         style = style_encoder(ref.to(dev, non_blocking=True), y)
     return generator(src, style.to(dev))
+
+
+class _CapturedTranslate:
+    """One captured SE -> G forward: static device inputs, the CUDA graph, its output buffer."""
+
+    def __init__(self, generator, style_encoder, src, other, ref_domain, with_ref, dev, pool=None):
+        self.dev = dev
+        self.se = None if style_encoder is None else weakref.ref(style_encoder)
+        self.src = torch.empty(src.shape, dtype=torch.float32, device=dev)
+        self.other = torch.empty(other.shape, dtype=torch.float32, device=dev)
+        self.dom = None if ref_domain is None else torch.empty(ref_domain.shape, dtype=torch.int64, device=dev)
+        self.load(src, other, ref_domain)
+        torch.cuda.synchronize(dev)
+        self.graph = torch.cuda.CUDAGraph()
+        l0 = ops.kernel_launches()
+        with torch.cuda.graph(self.graph, pool=pool):
+            if with_ref:
+                self.out = _translate_eager(generator, style_encoder, self.src, self.other, self.dom, None, dev)
+            else:
+                self.out = _translate_eager(generator, style_encoder, self.src, None, None, self.other, dev)
+        self.launches = ops.kernel_launches() - l0
+        ops.add_replayed_launches(-self.launches)      # recorded, not executed, during capture
+
+    def load(self, src, other, ref_domain):
+        self.src.copy_(src, non_blocking=True)
+        self.other.copy_(other, non_blocking=True)
+        if self.dom is not None:
+            self.dom.copy_(ref_domain, non_blocking=True)
+
+    def replay(self):
+        self.graph.replay()
+        ops.add_replayed_launches(self.launches)
+        return self.out
+
+
+def _graph_cache(generator):
+    """Captured forwards live ON the generator instance (dropped with it; never keyed by a recyclable
+    id()): {key: "warm" | _CapturedTranslate}. The style encoder is held weakly and re-validated."""
+    c = generator.__dict__.get("_msig_translate_cache")
+    if c is None:
+        c = {}
+        generator.__dict__["_msig_translate_cache"] = c
+    return c
+
+
+def _cache_lookup(generator, style_encoder, key):
+    cache = _graph_cache(generator)
+    entry = cache.get(key)
+    if isinstance(entry, _CapturedTranslate) and entry.se is not None and entry.se() is not style_encoder:
+        del cache[key]                               # the encoder this graph was captured with is gone
+        entry = None
+    return cache, entry
 
 
 @torch.no_grad()
@@ -143,41 +193,106 @@ def translate(generator, style_encoder, src, ref=None, ref_domain=None, style=No
         raise ValueError("translate: give reference images or a style code")
     if use_cuda_graph is None:
         use_cuda_graph = os.environ.get("MSIG_CUDA_GRAPH", "1") != "0"
-    if not use_cuda_graph or dev.type != "cuda":
+    if dev.type != "cuda":
         return _translate_eager(generator, style_encoder, src, ref, ref_domain, style, dev)
-    other = style if style is not None else ref
-    key = (id(generator), id(style_encoder), tuple(src.shape), style is None, tuple(other.shape), ref_domain is None)
-    entry = _translate_graphs.get(key)
-    if entry is None:                       # first call: eager (also builds the packed weights)
-        _translate_graphs[key] = "warm"
-        return _translate_eager(generator, style_encoder, src, ref, ref_domain, style, dev)
-    generator._packed.get()                 # refresh packed weights (no-op unless the parameters changed)
-    style_encoder._packed.get()
-    if entry == "warm":
-        st = {"src": torch.empty(src.shape, dtype=torch.float32, device=dev),
-              "other": torch.empty(other.shape, dtype=torch.float32, device=dev),
-              "dom": None if ref_domain is None else torch.empty(ref_domain.shape, dtype=torch.int64, device=dev)}
-        st["src"].copy_(src, non_blocking=True)
-        st["other"].copy_(other, non_blocking=True)
-        if st["dom"] is not None:
-            st["dom"].copy_(ref_domain, non_blocking=True)
-        torch.cuda.synchronize(dev)
-        graph = torch.cuda.CUDAGraph()
-        l0 = ops.kernel_launches()
-        with torch.cuda.graph(graph):
-            if style is None:
-                out = _translate_eager(generator, style_encoder, st["src"], st["other"], st["dom"], None, dev)
-            else:
-                out = _translate_eager(generator, style_encoder, st["src"], None, None, st["other"], dev)
-        launches = ops.kernel_launches() - l0
-        ops.add_replayed_launches(-launches)      # recorded, not executed, during capture
-        entry = {"graph": graph, "st": st, "out": out, "gen": generator, "se": style_encoder, "launches": launches}
-        _translate_graphs[key] = entry
-    st = entry["st"]
-    st["src"].copy_(src, non_blocking=True)
-    st["other"].copy_(other, non_blocking=True)
-    if st["dom"] is not None:
-        st["dom"].copy_(ref_domain, non_blocking=True)
-    entry["graph"].replay()
-    ops.add_replayed_launches(entry["launches"])
-    return entry["out"]
+    with torch.cuda.device(dev):
+        if not use_cuda_graph:
+            return _translate_eager(generator, style_encoder, src, ref, ref_domain, style, dev)
+        other = style if style is not None else ref
+        key = (id(style_encoder) if style is None else None, tuple(src.shape), style is None, tuple(other.shape),
+               ref_domain is None)
+        cache, entry = _cache_lookup(generator, style_encoder if style is None else None, key)
+        if entry is None:                       # first call: eager (also builds the packed weights)
+            cache[key] = "warm"
+            return _translate_eager(generator, style_encoder, src, ref, ref_domain, style, dev)
+        generator._packed.get()                 # refresh packed weights (no-op unless the parameters changed)
+        if style is None:
+            style_encoder._packed.get()
+        if entry == "warm":
+            entry = _CapturedTranslate(generator, style_encoder if style is None else None, src, other, ref_domain,
+                                       style is None, dev)
+            cache[key] = entry
+        else:
+            entry.load(src, other, ref_domain)
+        return entry.replay()
+
+
+def translate_batches(generator, style_encoder, batches, consume=None):
+    """See _translate_pipeline. With `consume` the pipeline is run to completion here and
+    `consume(index, images)` is called per batch; without it a generator of `(index, images)` is returned."""
+    gen = _translate_pipeline(generator, style_encoder, batches)
+    if consume is None:
+        return gen
+    for i, host in gen:
+        consume(i, host)
+    return None
+
+
+@torch.no_grad()
+def _translate_pipeline(generator, style_encoder, batches):
+    """The batched inference DRIVER (the loop of inference.py:273-305, where the reference generates one
+    image at a time and writes its PNG before starting the next): a software pipeline over an iterable of
+    host batches `(src, ref, ref_domain)` (pinned CPU tensors for full overlap) that keeps three things in
+    flight at once on three streams -- the host->device copy of batch i+1, the graph replay of batch i and
+    the device->host copy of batch i-1 -- through two captured forwards with double-buffered staging.
+
+    Yields `(index, images)` with `images` a pinned host tensor [B,3,S,S] (valid until two more batches
+    have been yielded): whatever the caller does with a result (save_image, encoding) overlaps the GPU
+    work of the next batches. All batches must share one shape (a ragged tail batch is run eagerly)."""
+    dev = next(generator.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("translate_batches: expected CUDA models; msig_b200 has no CPU path")
+
+    def emit(i, host):
+        return ((i, host),)
+
+    with torch.cuda.device(dev):
+        s_in, s_run, s_out = (torch.cuda.Stream(device=dev) for _ in range(3))
+        slots, shape, pending, pool = [], None, None, None
+        for i, (src, ref, dom) in enumerate(batches):
+            if shape is None:
+                shape = (tuple(src.shape), tuple(ref.shape))
+                _translate_eager(generator, style_encoder, src, ref, dom, None, dev)      # warm-up: packs weights
+                torch.cuda.synchronize(dev)
+            if (tuple(src.shape), tuple(ref.shape)) != shape:          # ragged tail: plain call
+                if pending is not None:
+                    pending[2].synchronize()
+                    yield from emit(pending[0], pending[1])
+                    pending = None
+                yield from emit(i, translate(generator, style_encoder, src, ref, dom, use_cuda_graph=False).cpu())
+                continue
+            generator._packed.get()
+            style_encoder._packed.get()
+            k = i % 2
+            if len(slots) <= k:
+                cur = torch.cuda.current_stream(dev)
+                s_run.wait_stream(cur)
+                with torch.cuda.stream(s_run):
+                    cap = _CapturedTranslate(generator, style_encoder, src, ref, dom, True, dev, pool=pool)
+                pool = cap.graph.pool()
+                slots.append({"cap": cap, "host": torch.empty(cap.out.shape, dtype=cap.out.dtype).pin_memory(),
+                              "in": torch.cuda.Event(), "run": torch.cuda.Event(), "out": torch.cuda.Event()})
+                slots[k]["run"].record(s_run)
+                slots[k]["out"].record(s_out)
+            sl = slots[k]
+            with torch.cuda.stream(s_in):              # H2D(i): the slot's inputs are free once replay(i-2) is done
+                s_in.wait_event(sl["run"])
+                sl["cap"].load(src, ref, dom)
+                sl["in"].record(s_in)
+            with torch.cuda.stream(s_run):             # replay(i): needs its inputs, and D2H(i-2) off its output
+                s_run.wait_event(sl["in"])
+                s_run.wait_event(sl["out"])
+                sl["cap"].replay()
+                sl["run"].record(s_run)
+            with torch.cuda.stream(s_out):             # D2H(i)
+                s_out.wait_event(sl["run"])
+                sl["host"].copy_(sl["cap"].out, non_blocking=True)
+                sl["out"].record(s_out)
+            if pending is not None:                    # hand batch i-1 to the caller while i runs
+                pending[2].synchronize()
+                yield from emit(pending[0], pending[1])
+            pending = (i, sl["host"], sl["out"])
+        if pending is not None:
+            pending[2].synchronize()
+            yield from emit(pending[0], pending[1])
+        torch.cuda.current_stream(dev).wait_stream(s_run)

@@ -131,6 +131,8 @@ _SIGS = {
     "msig_gram_l1_workspace": (c_size_t, [c_int32]),
     "msig_gram_l1": (c_int, [_P, _P, c_int32, _P, c_int, _P, _P, c_size_t, _P]),
     "msig_gram_bwd": (c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P, _P, _P]),
+    "msig_augment_workspace": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
+    "msig_augment_u8": (c_int, [_P, c_int32, c_int32, c_int32, _P, _P, c_int32, _P, _P, c_size_t, _P]),
     "msig_sumsq": (c_int, [_P, c_int64, _P, c_int, _P, c_size_t, _P]),
     "msig_adam_step": (c_int, [_P, _P, _P, _P, _P, c_int64, _P, c_float, c_float, c_float, c_float,
                                c_float, c_float, c_int32, c_float, _P]),

@@ -112,7 +112,7 @@ class _Net(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_packed", "_child_nets_cache"):
+            if k in ("_packed", "_child_nets_cache") or k.startswith("_msig_"):   # caches are per instance
                 continue
             setattr(new, k, copy.deepcopy(v, memo))
         new._packed = _PackedWeights(new)

@@ -5,6 +5,15 @@ the only exchange step is the gradient all-reduce. Rank r takes rows [r*B, (r+1)
 batch; gradients are SUMMED over ranks into the flat gradient buffer and the 1/world factor is folded
 into the fused clip+Adam kernel (msig_adam_step's grad_scale), so the clip sees the averaged gradient
 exactly like DistributedDataParallel around the reference would.
+
+Semantics: an R-rank run equals "the reference wrapped in DistributedDataParallel on per-rank shards",
+NOT the single-process reference at the global batch. Every loss term that is a per-sample mean (LSGAN,
+cycle, identity, content) is identical in both; the VGG STYLE term is not: compute_gram_matrix
+(losses.py:70-78) folds the batch into the Gram rows, so it couples the samples of one forward pass --
+the (B*C) x (B*C) Gram and its 1/(B*C*H*W) divisor are built from the LOCAL batch on each rank. Cross-rank
+Gram terms are therefore absent and the term's scale follows the local batch size, exactly as DDP around
+the reference would behave (SURVEY.md section 8e "Caveat"). tests/test_dp_gloo.py pins this: the sharded
+run matches the per-shard oracle average, and differs from the global-batch oracle in the style term only.
 """
 import torch
 import torch.distributed as dist

@@ -9,8 +9,9 @@ Reference: /root/reference/trainer.py:19-239. Result-preserving differences (SUR
   * the loss-weight scheduler keeps device scalars instead of calling .item() (utils.py:114);
   * clip_grad_norm_ + Adam + EMA run as one fused pass over flat buffers;
   * with world_size > 1 each rank takes an equal shard of the batch and gradients are averaged with
-    an NCCL all-reduce; the generator-side all-reduce overlaps the discriminator phase (which does
-    not depend on the generator update);
+    NCCL all-reduces on a communication stream: the generator-side one (135.6 MB) overlaps the whole
+    discriminator phase (which does not depend on the generator update), the discriminator-side one
+    (22.7 MB) overlaps the generator's clip + Adam + EMA pass;
   * the step has static shapes and no host synchronisation, so from the second call with the same
     (batch shape, epoch, learning rates) it is replayed from ONE captured CUDA graph (~1900 kernel
     launches per step otherwise cost as much host time as the GPU needs to run them). The first call
@@ -26,6 +27,19 @@ from .losses import L1Loss, MSELoss, VGGStyleContentLoss
 from .model import MultiDomainDiscriminator, MultiDomainStyleEncoder, StyleCycleGANGenerator
 from .parallel import FlatAllReduce
 from .utils import EMA, DynamicWeightScheduler, FlatParams, FusedAdam
+
+
+def checkpoint_payload(nets, g_optimizer, d_optimizer, g_scheduler, d_scheduler, loss_history, num_domains):
+    """The two dicts the reference writes to checkpoint.pth / ema_checkpoint.pth (trainer.py:157-174), from
+    `nets` = {name: module} holding the six networks and the four EMA copies. Plain tensors / floats /
+    ints only, so a reference build (torch.load with weights_only=True) reads them; the optimizer entries
+    use torch.optim.Adam's state_dict layout (FusedAdam.state_dict)."""
+    main = {k: nets[k].state_dict() for k in ('G_A2B', 'G_B2A', 'SE_A', 'SE_B', 'D_A', 'D_B')}
+    main.update({'g_optimizer': g_optimizer.state_dict(), 'd_optimizer': d_optimizer.state_dict(),
+                 'g_scheduler': g_scheduler.state_dict(), 'd_scheduler': d_scheduler.state_dict(),
+                 'loss_history': loss_history, 'num_domains': num_domains})
+    ema = {k: nets[k].state_dict() for k in ('ema_G_A2B', 'ema_G_B2A', 'ema_SE_A', 'ema_SE_B')}
+    return main, ema
 
 
 class MultiDomainStyleCycleGAN:
@@ -93,16 +107,19 @@ class MultiDomainStyleCycleGAN:
     def train_step(self, batch, epoch):
         """One G+D optimisation step (reference trainer.py:74-155). Returns the same dict of loss
         tensors: D_loss, G_loss, gan, cycle, identity, style, content."""
-        if self.use_cuda_graph:
-            return self._train_step_graphed(batch, epoch)
-        return self._train_step_eager(batch, epoch)
+        with torch.cuda.device(self.device):      # streams / workspaces of the trainer's device, whatever is current
+            if self.use_cuda_graph:
+                return self._train_step_graphed(batch, epoch)
+            return self._train_step_eager(batch, epoch)
 
     def _train_step_eager(self, batch, epoch):
         ops.step_cache_begin()
         try:
             st = {}
             for seg, comm in self._segments(batch, epoch, st, device_step=False):
+                torch.cuda.nvtx.range_push("msig." + seg.__name__)
                 seg()
+                torch.cuda.nvtx.range_pop()
                 comm()
             return st["out"]
         finally:
@@ -169,21 +186,23 @@ class MultiDomainStyleCycleGAN:
             d_loss.backward()
             st["out"] = {'D_loss': d_loss, **st["out"]}
 
-        def comm_g_wait():
+        def comm_g_wait_d_start():   # G grads are needed now; the D-side all-reduce hides behind the G update
             if dp:
+                d_ev = self._comm.start(self._d_flat.grad)
                 self._comm.wait(st.pop("g_ev"), dev)
+                st["d_ev"] = d_ev
 
         def seg_g_update():          # clip_grad_norm_(1.0) + Adam + EMA (trainer.py:127-134), fused
             self.g_optimizer.step(max_norm=1.0, grad_scale=scale, device_step=device_step)
 
-        def comm_d():
+        def comm_d_wait():
             if dp:
-                self._comm.wait(self._comm.start(self._d_flat.grad), dev)
+                self._comm.wait(st.pop("d_ev"), dev)
 
         def seg_d_update():          # trainer.py:152-153
             self.d_optimizer.step(max_norm=1.0, grad_scale=scale, device_step=device_step)
 
-        return [(seg_generators, comm_g_start), (seg_discriminators, comm_g_wait), (seg_g_update, comm_d),
+        return [(seg_generators, comm_g_start), (seg_discriminators, comm_g_wait_d_start), (seg_g_update, comm_d_wait),
                 (seg_d_update, lambda: None)]
 
     # ------------------------------------------------------------------ CUDA-graph replay
@@ -209,15 +228,19 @@ class MultiDomainStyleCycleGAN:
         gs = self._graph
         for k in self._BATCH_KEYS:
             gs["static"][k].copy_(batch[k], non_blocking=True)
-        for graph, comm in gs["segments"]:
+        for (graph, comm), name in zip(gs["segments"], gs["seg_names"]):
+            torch.cuda.nvtx.range_push(name)
             graph.replay()
+            torch.cuda.nvtx.range_pop()
             comm()
         self.g_optimizer.after_replay()
         self.d_optimizer.after_replay()
         ops.add_replayed_launches(gs["launches"])
         vals = gs["out"].clone()            # the graphs' output buffer is overwritten by the next replay
         out = {name: vals[i] for i, name in enumerate(gs["names"])}
-        self.weight_scheduler.get_current_weights(epoch, {k: v for k, v in out.items() if k not in ('D_loss', 'G_loss')})
+        # loss history: one gathered row into the scheduler's device ring (flushed to floats lazily)
+        self.weight_scheduler.record_device(vals.index_select(0, gs["hist_idx"]))
+        self.weight_scheduler.get_current_weights(epoch, {})
         return out
 
     def _capture(self, batch, epoch):
@@ -232,6 +255,9 @@ class MultiDomainStyleCycleGAN:
         self.g_optimizer.step_counter()
         self.d_optimizer.step_counter()
         torch.cuda.synchronize(dev)
+        # The graphs get a private memory pool holding the whole step's working set; hand the eager step's
+        # cached blocks back first, or a large batch needs that working set twice (B=128: ~2 x 100 GB).
+        torch.cuda.empty_cache()
         l0 = ops.kernel_launches()
         st, segments, pool = {}, [], None
         ops.step_cache_begin()
@@ -250,25 +276,19 @@ class MultiDomainStyleCycleGAN:
             ops.step_cache_end()
         launches = ops.kernel_launches() - l0
         ops.add_replayed_launches(-launches)   # recorded, not executed, during capture
+        hist_idx = torch.tensor([names.index(k) for k in self.weight_scheduler._keys], dtype=torch.int64, device=dev)
         return {"segments": segments, "static": static, "out": stacked, "names": names, "launches": launches,
-                "keep": st}
+                "keep": st, "hist_idx": hist_idx, "seg_names": ["msig." + seg.__name__ for seg, _ in segs]}
 
     # ------------------------------------------------------------------ checkpoints (trainer.py:157-207)
     def save_models(self, save_dir):
         os.makedirs(save_dir, exist_ok=True)
-        torch.save({
-            'G_A2B': self.G_A2B.state_dict(), 'G_B2A': self.G_B2A.state_dict(),
-            'SE_A': self.SE_A.state_dict(), 'SE_B': self.SE_B.state_dict(),
-            'D_A': self.D_A.state_dict(), 'D_B': self.D_B.state_dict(),
-            'g_optimizer': self.g_optimizer.state_dict(), 'd_optimizer': self.d_optimizer.state_dict(),
-            'g_scheduler': self.g_scheduler.state_dict(), 'd_scheduler': self.d_scheduler.state_dict(),
-            'loss_history': self.loss_history,
-            'num_domains': self.num_domains
-        }, os.path.join(save_dir, 'checkpoint.pth'))
-        torch.save({
-            'ema_G_A2B': self.ema_G_A2B.state_dict(), 'ema_G_B2A': self.ema_G_B2A.state_dict(),
-            'ema_SE_A': self.ema_SE_A.state_dict(), 'ema_SE_B': self.ema_SE_B.state_dict()
-        }, os.path.join(save_dir, 'ema_checkpoint.pth'))
+        nets = {k: getattr(self, k) for k in ('G_A2B', 'G_B2A', 'SE_A', 'SE_B', 'D_A', 'D_B',
+                                              'ema_G_A2B', 'ema_G_B2A', 'ema_SE_A', 'ema_SE_B')}
+        main, ema = checkpoint_payload(nets, self.g_optimizer, self.d_optimizer, self.g_scheduler, self.d_scheduler,
+                                       self.loss_history, self.num_domains)
+        torch.save(main, os.path.join(save_dir, 'checkpoint.pth'))
+        torch.save(ema, os.path.join(save_dir, 'ema_checkpoint.pth'))
         print(f"Models successfully saved to {save_dir}")
 
     def load_models(self, checkpoint_dir):

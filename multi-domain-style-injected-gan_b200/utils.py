@@ -60,7 +60,11 @@ class FusedAdam(torch.optim.Optimizer):
     (CosineAnnealingLR, trainer.py:64-65) work unchanged; state_dict() uses Adam's layout."""
 
     def __init__(self, flat, lr, betas=(0.5, 0.999), eps=1e-8, ema_flat=None, ema_beta=0.995):
-        super().__init__(flat.params, dict(lr=lr, betas=betas, eps=eps))
+        # every hyper-parameter key torch.optim.Adam keeps in a param_group (at its defaults): a
+        # state_dict() written here then loads into the reference's torch.optim.Adam and can step
+        super().__init__(flat.params, dict(lr=lr, betas=betas, eps=eps, weight_decay=0, amsgrad=False, maximize=False,
+                                           foreach=None, capturable=False, differentiable=False, fused=None,
+                                           decoupled_weight_decay=False))
         self.flat = flat
         self.ema_flat = ema_flat
         self.ema_beta = ema_beta
@@ -126,9 +130,12 @@ class FusedAdam(torch.optim.Optimizer):
         # copy into the flat-backed state instead of replacing the tensors
         groups = state_dict["param_groups"]
         for g, sg in zip(self.param_groups, groups):
+            if sg.get("weight_decay", 0) or sg.get("amsgrad", False) or sg.get("maximize", False):
+                raise RuntimeError("FusedAdam: weight_decay / amsgrad / maximize are not supported (the reference "
+                                   "uses none of them, trainer.py:58-61)")
             for k in ("lr", "betas", "eps", "initial_lr"):
                 if k in sg:
-                    g[k] = sg[k]
+                    g[k] = tuple(sg[k]) if k == "betas" else sg[k]
         ids = [i for sg in groups for i in sg["params"]]
         steps = []
         for i, p in zip(ids, self.flat.params):

@@ -552,7 +552,38 @@ def case_translate_graph(b=3, s=64, nd=4, seed=0):
         with torch.no_grad():                                       # "optimizer step": the graph must see it
             for p in list(G.parameters()) + list(SE.parameters()):
                 p.mul_(1.05)
-    ok = ok and any(isinstance(v, dict) for v in I._translate_graphs.values())
+    cache = G.__dict__.get("_msig_translate_cache", {})
+    ok = ok and any(isinstance(v, I._CapturedTranslate) for v in cache.values())
+    # the cache lives on the generator (no id()-keyed global): a deep copy starts without captured graphs
+    import copy
+    ok = ok and "_msig_translate_cache" not in copy.deepcopy(G).__dict__
+    return res, ok
+
+
+def case_translate_batches(b=4, s=64, nd=4, n_batches=5, seed=0):
+    """The pipelined inference driver (double-buffered H2D / replay / D2H on three streams) returns, batch
+    for batch, what eager `translate` returns; a ragged tail batch is handled; results arrive in order."""
+    from msig_b200 import inference as I
+    torch.manual_seed(seed)
+    G = M.StyleCycleGANGenerator().to(DEV).eval()
+    SE = M.MultiDomainStyleEncoder(num_domains=nd).to(DEV).eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    batches = []
+    for i in range(n_batches):
+        bb = b if i < n_batches - 1 else b - 1                      # ragged tail
+        batches.append(((torch.rand(bb, 3, s, s, generator=g) * 2 - 1).pin_memory(),
+                        (torch.rand(bb, 3, s, s, generator=g) * 2 - 1).pin_memory(),
+                        torch.randint(0, nd, (bb,), generator=g).pin_memory()))
+    want = [I.translate(G, SE, *bt, use_cuda_graph=False).cpu() for bt in batches]
+    res, ok, seen = {}, True, []
+    for i, host in I.translate_batches(G, SE, iter(batches)):
+        seen.append(i)
+        res[f"b{i}"] = rel(host.clone(), want[i])
+        ok = ok and res[f"b{i}"] <= 1e-6 and tuple(host.shape) == tuple(want[i].shape)
+    got = []
+    I.translate_batches(G, SE, iter(batches[:3]), consume=lambda i, h: got.append((i, h.clone())))
+    ok = ok and seen == list(range(n_batches)) and [i for i, _ in got] == [0, 1, 2]
+    ok = ok and all(rel(h, want[i]) <= 1e-6 for i, h in got)
     return res, ok
 
 
@@ -615,5 +646,6 @@ CASES = {
     "translate_vs_oracle": case_translate_vs_oracle,
     "train_step_graph_vs_eager": case_graph_vs_eager,
     "translate_graph_vs_eager": case_translate_graph,
+    "translate_batches_pipeline": case_translate_batches,
     "epoch_change_and_checkpoint": case_epoch_change_and_checkpoint,
 }

@@ -307,6 +307,35 @@ def case_adam(seed=0):
     return max(rel_err(p, ref_p.data), rel_err(ema, ema_ref), ((p - ref_p.data).abs().max() / 2e-4).item() * 2e-3), 1e-5
 
 
+def case_augment(n=6, h=200, w=320, size=64, seed=0, sampled=False):
+    """msig_augment_u8 (crop + PIL-exact bilinear resize + rotation + ToTensor + Normalize, dataset.py:16-22)
+    vs the numpy oracle, which tests/test_augment_oracle.py pins against Pillow / torchvision: BIT-exact."""
+    import numpy as np
+    from msig_b200 import augment as G
+    from oracle import augment_oracle as A
+    ops.ensure_init()
+    rng = np.random.RandomState(seed)
+    imgs = rng.randint(0, 256, (n, h, w, 3), dtype=np.uint8)
+    imgs[n // 2:] = (imgs[n // 2:].astype(np.int32) // 8 * 8 + 3).astype(np.uint8)          # banded content too
+    if sampled:
+        boxes, rots = G.sample_params(n, h, w, generator=torch.Generator().manual_seed(seed))
+    else:   # full image, upscale, anisotropic shrink, tiny crop, identity axis (width == size), bottom-right corner
+        fixed = [(0, 0, h, w), (10, 20, 100, 140), (3, 0, 180, 75), (60, 70, 20, 24), (0, 0, h, min(size, w)),
+                 (h - 37, w - 41, 37, 41)]
+        boxes = torch.tensor([fixed[i % len(fixed)] for i in range(n)], dtype=torch.int32)
+        rots = torch.tensor([i % 4 for i in range(n)], dtype=torch.int32)
+    out = G.augment(torch.from_numpy(imgs).to(DEV), boxes, rots, size)
+    torch.cuda.synchronize()
+    got = out.cpu().numpy()
+    worst = 0.0
+    check = range(n) if n <= 8 else (0, n // 3, n // 2, n - 1)
+    for i in check:
+        t, l, hh, ww = [int(v) for v in boxes[i]]
+        want = A.augment(imgs[i], t, l, hh, ww, int(rots[i]), size)
+        worst = max(worst, float(np.abs(got[i] - want).max()))
+    return worst, 0.0
+
+
 CASES = {
     "gather_7x7_reflect": lambda: case_patch_gather(2, 3, 32, 40, 7, 1, 3, True),
     "gather_4x4s2_zero": lambda: case_patch_gather(2, 3, 32, 32, 4, 2, 1, False),
@@ -331,4 +360,8 @@ CASES = {
     "norm_pad_fused": case_norm_pad,
     "norm_pad_fused_256": lambda: case_norm_pad(1, 256, 256, 64, 3, 3),
     "adam": case_adam,
+    "augment_fixed_boxes_64": lambda: case_augment(6, 200, 320, 64),
+    "augment_fixed_boxes_256": lambda: case_augment(6, 256, 256, 256, seed=1),
+    "augment_shrink_512_to_96": lambda: case_augment(3, 512, 512, 96, seed=2),
+    "augment_sampled_b32_256": lambda: case_augment(32, 256, 256, 256, seed=3, sampled=True),
 }

@@ -78,3 +78,29 @@ def test_two_rank_allreduce_equals_averaged_shards():
     torch.nn.utils.clip_grad_norm_(params, 1.0)
     ref = torch.cat([p.grad.flatten() for p in params])
     assert torch.allclose(got, ref, rtol=1e-3, atol=1e-6), float((got - ref).abs().max())
+
+
+def test_sharded_semantics_style_term_is_per_rank_local():
+    """The intended data-parallel semantics (parallel.py docstring): per-sample-mean loss terms of the
+    equal shards average to the global-batch value; the VGG style term (Gram rows span the batch,
+    losses.py:70-78) does NOT -- an R-rank run equals the reference under DDP, not the reference at the
+    global batch. Pinned on the oracle so that nobody 'fixes' one side only."""
+    sys.path.insert(0, ROOT)
+    from oracle import oracle as O
+    import msig_b200  # noqa: F401
+    from msig_b200 import parallel as P
+    vgg = O.seeded_vgg_state()
+    g = torch.Generator().manual_seed(3)
+    gen = torch.rand(4, 3, 32, 32, generator=g) * 2 - 1
+    sty = torch.rand(4, 3, 32, 32, generator=g) * 2 - 1
+    con = torch.rand(4, 3, 32, 32, generator=g) * 2 - 1
+    with torch.no_grad():
+        c_all, s_all = O.vgg_loss(vgg, gen, sty, con)
+        parts = []
+        for r in range(2):
+            b = P.shard_batch({"g": gen, "s": sty, "c": con}, r, 2)
+            parts.append(O.vgg_loss(vgg, b["g"], b["s"], b["c"]))
+    c_avg = sum(float(p[0]) for p in parts) / 2
+    s_avg = sum(float(p[1]) for p in parts) / 2
+    assert abs(c_avg - float(c_all)) <= 1e-6 * abs(float(c_all))          # per-sample mean: shards average exactly
+    assert abs(s_avg - float(s_all)) > 1e-2 * abs(float(s_all))           # batch-coupled: they do not

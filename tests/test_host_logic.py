@@ -55,6 +55,13 @@ def test_weight_scheduler_matches_oracle():
         for k in ref:
             assert abs(got[k] - ref[k]) <= 1e-12
     assert len(ws.loss_history["gan"]) == 7 and ws.loss_history_values()["gan"][0] == 1.0
+    # the history holds Python floats like the reference's (utils.py:114), never live tensors
+    assert all(isinstance(v, float) for v in ws.loss_history["gan"])
+    full = {k: torch.tensor(float(i)) for i, k in enumerate(O.DEFAULT_LOSS_WEIGHTS)}
+    for _ in range(3):
+        ws.get_current_weights(0, full)
+    assert ws.loss_history["cycle"][-3:] == [1.0, 1.0, 1.0] and len(ws.loss_history["gan"]) == 10
+    assert all(isinstance(v, float) for k in ws.loss_history for v in ws.loss_history[k])
 
 
 def test_flat_params_keep_state_dict_and_views():
