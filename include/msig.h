@@ -70,6 +70,8 @@ typedef struct msig_epilogue {
    * msig_in_stats_from_partials / msig_norm_bwd_from_partials. */
   float* stats_partial;
   const void* stats_z;
+  const float* ch_scale;  /* optional [k] fp32 per-output-channel multiplier, applied with alpha before the bias
+                           * (msig_conv_narrow_fwd only: the VGG input renormalisation's 0.5/std on d(image)) */
 } msig_epilogue;
 /* rows of stats_partial PER IMAGE for an output plane oh x ow produced in `phases` (1, or 4 for the
  * k4 s2 transposed conv / stride-2 dgrad, where oh x ow is the per-phase plane = the INPUT plane). */
@@ -126,7 +128,8 @@ int msig_conv2d_fwd(const msig_conv_geom* g, const void* x, const void* w_fwd,
  * stride then reads the (s, c) window of filter row r for every output pixel as one K-major 128-byte
  * row. Geometry: n,h,w,c = the UNPADDED image, pad_t = pad_l = p, stride 1, s <= 8. */
 int msig_img_pad8(const float* src_nchw, int32_t n, int32_t c, int32_t h, int32_t w, int32_t pad,
-                  int32_t reflect, void* dst_pad8, void* stream);
+                  int32_t reflect, const float* scale /* [c] or NULL */, const float* shift /* [c] or NULL */,
+                  void* dst_pad8, void* stream);   /* stores x*scale + shift (VGG renorm, losses.py:49-56); padding = 0 */
 int msig_conv_rowpatch_fwd(const msig_conv_geom* g, const void* x_pad8, const void* w_rowpatch,
                            const msig_epilogue* e, void* y, void* stream);
 size_t msig_conv_rowpatch_wgrad_workspace(const msig_conv_geom* g);

@@ -365,6 +365,8 @@ static int fill_epilogue(FpropParams& p, const msig_epilogue* e, const OutView& 
   p.stat_out = e ? e->stats_partial : nullptr;
   p.stat_z = e ? reinterpret_cast<const __nv_bfloat16*>(e->stats_z) : nullptr;
   p.stat_ld = static_cast<int>(round_up(n_valid, 64));
+  if (e && e->ch_scale != nullptr)
+    return set_error(MSIG_ERR_UNSUPPORTED, "epilogue ch_scale is only implemented by msig_conv_narrow_fwd");
   if (p.stat_out != nullptr && (ov.f32 || ov.sC != 1 || n_valid < 64 || p.fold_c != 0 || p.tap_is_image))
     return set_error(MSIG_ERR_UNSUPPORTED, "epilogue statistics need a bf16 NHWC output with k >= 64");
   return MSIG_OK;
@@ -833,6 +835,7 @@ int msig_conv_narrow_fwd(const msig_conv_geom* g, const void* x, const void* w_r
   p.alpha = e ? e->alpha : 1.f;
   p.alpha_ptr = e ? e->alpha_ptr : nullptr;
   p.act = e ? e->act : ACT_NONE;
+  p.ch_scale = e ? e->ch_scale : nullptr;
   cudaError_t ce = launch_rowfold(p, sms, static_cast<cudaStream_t>(stream));
   if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "rowfold launch: %s", cudaGetErrorString(ce));
   return MSIG_OK;

@@ -734,10 +734,11 @@ __global__ void __launch_bounds__(256, 1) fprop_rowfold_kernel(const __grid_cons
     const int t = q * 32 + lane;                     // TMEM lane = strip pixel = local output pixel
     const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
     float bias[4] = {0.f, 0.f, 0.f, 0.f};
-    if (p.bias != nullptr) {
+    float chs[4] = {alpha, alpha, alpha, alpha};
 #pragma unroll
-      for (int co = 0; co < 4; ++co)
-        if (co < p.n_valid) bias[co] = __ldg(p.bias + co);
+    for (int co = 0; co < 4; ++co) {
+      if (co < p.n_valid && p.bias != nullptr) bias[co] = __ldg(p.bias + co);
+      if (co < p.n_valid && p.ch_scale != nullptr) chs[co] = alpha * __ldg(p.ch_scale + co);
     }
     int it = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
@@ -769,7 +770,7 @@ __global__ void __launch_bounds__(256, 1) fprop_rowfold_kernel(const __grid_cons
           float* o = p.out + img * p.o_sn + oh * p.o_sh + ow * p.o_sw;
 #pragma unroll
           for (int co = 0; co < 4; ++co)
-            if (co < p.n_valid) o[co * p.o_sc] = apply_act(acc[co] * alpha + bias[co], p.act, 0.f);
+            if (co < p.n_valid) o[co * p.o_sc] = apply_act(acc[co] * chs[co] + bias[co], p.act, 0.f);
         }
       }
     }

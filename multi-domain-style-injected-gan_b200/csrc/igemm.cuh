@@ -114,6 +114,7 @@ struct RowfoldParams {
   float alpha;
   const float* alpha_ptr;
   int32_t act;
+  const float* ch_scale;           // optional per-output-channel multiplier applied with alpha (before the bias)
 };
 
 cudaError_t launch_fprop(const FpropParams& p, int block_n, int num_sms, cudaStream_t stream);

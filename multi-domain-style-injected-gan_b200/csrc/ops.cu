@@ -189,6 +189,7 @@ __global__ void patch_scatter_kernel(msig_patch_geom g, const __nv_bfloat16* __r
 // fp32 NCHW [n,c,h,w] (c <= 8) -> bf16 [n][h+2p][w+2p+2][8], reflect or zero padding; channels >= c and
 // the two slack columns are zero. One thread per padded pixel (one 16-byte store).
 __global__ void img_pad8_kernel(const float* __restrict__ src, int c, int h, int w, int pad, int reflect,
+                                const float* __restrict__ scale, const float* __restrict__ shift,
                                 __nv_bfloat16* __restrict__ dst, int64_t total) {
   const int Hp = h + 2 * pad, Wp = w + 2 * pad + 2;
   const int64_t plane = int64_t(h) * w;
@@ -210,7 +211,10 @@ __global__ void img_pad8_kernel(const float* __restrict__ src, int c, int h, int
       const float* sp = src + img * c * plane + int64_t(ih) * w + iw;
 #pragma unroll
       for (int ch = 0; ch < 8; ++ch)
-        if (ch < c) f[ch] = __ldg(sp + ch * plane);
+        if (ch < c) {
+          f[ch] = __ldg(sp + ch * plane);
+          if (scale != nullptr) f[ch] = f[ch] * __ldg(scale + ch) + __ldg(shift + ch);
+        }
     }
     store8(dst + idx * 8, f);
   }
@@ -970,11 +974,13 @@ int msig_patch_scatter(const msig_patch_geom* g, const void* dpatches, const flo
 }
 
 int msig_img_pad8(const float* src_nchw, int32_t n, int32_t c, int32_t h, int32_t w, int32_t pad, int32_t reflect,
-                  void* dst, void* stream) {
+                  const float* scale, const float* shift, void* dst, void* stream) {
   MSIG_REQUIRE(src_nchw && dst && c >= 1 && c <= 8 && pad >= 0 && (!reflect || (pad < h && pad < w)),
                "msig_img_pad8: bad argument");
+  MSIG_REQUIRE((scale == nullptr) == (shift == nullptr), "msig_img_pad8: scale and shift go together");
   const int64_t total = int64_t(n) * (h + 2 * pad) * (w + 2 * pad + 2);
-  img_pad8_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, ST(stream)>>>(src_nchw, c, h, w, pad, reflect, BF(dst), total);
+  img_pad8_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, ST(stream)>>>(src_nchw, c, h, w, pad, reflect, scale, shift,
+                                                                          BF(dst), total);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;

@@ -29,7 +29,8 @@ class ConvGeom(Structure):
 class Epilogue(Structure):
     _fields_ = [("bias", c_void_p), ("aux", c_void_p), ("aux_mode", c_int32), ("act", c_int32),
                 ("alpha", c_float), ("alpha_ptr", c_void_p), ("slope", c_float),
-                ("out_layout", c_int32), ("stats_partial", c_void_p), ("stats_z", c_void_p)]
+                ("out_layout", c_int32), ("stats_partial", c_void_p), ("stats_z", c_void_p),
+                ("ch_scale", c_void_p)]
 
 
 class WpackDesc(Structure):
@@ -64,7 +65,7 @@ _SIGS = {
     "msig_wpack_part_elems": (c_size_t, [POINTER(WpackDesc), c_int32]),
     "msig_wpack_part": (c_int, [POINTER(WpackDesc), c_int32, c_int32, _P, _P, _P]),
     "msig_conv2d_fwd": (c_int, [POINTER(ConvGeom), _P, _P, POINTER(Epilogue), _P, _P]),
-    "msig_img_pad8": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P]),
+    "msig_img_pad8": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, c_int32, _P, _P, _P, _P]),
     "msig_conv_rowpatch_fwd": (c_int, [POINTER(ConvGeom), _P, _P, POINTER(Epilogue), _P, _P]),
     "msig_conv_rowpatch_wgrad_workspace": (c_size_t, [POINTER(ConvGeom)]),
     "msig_conv_rowpatch_wgrad": (c_int, [POINTER(ConvGeom), _P, _P, c_int, _P, c_int, _P, c_size_t, _P]),

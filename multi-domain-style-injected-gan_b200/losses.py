@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .lib import (ACT_RELU, OUT_F32_NHWC, WPACK_DGRAD_S1, WPACK_FWD, WPACK_IM2COL, WPACK_IM2COL_DGRAD)
+from .lib import ACT_RELU, OUT_F32_NCHW, WPACK_DGRAD_S1, WPACK_FWD, WPACK_ROWFOLD_DGRAD, WPACK_ROWPATCH
 
 F32 = torch.float32
 VGG_CONV_IDX = (0, 2, 5, 7, 10)          # torchvision vgg19().features indices of convs 1..5
@@ -68,8 +68,9 @@ class VGGStyleContentLoss(nn.Module):
             t = {}
             convs = [self.vgg_layers[f"conv_{i}_1"] for i in range(1, 6)]
             with torch.no_grad():
-                t["w0"] = ops.wpack(WPACK_IM2COL, convs[0].weight, 64, 3, 3, 3)
-                t["w0_d"] = ops.wpack(WPACK_IM2COL_DGRAD, convs[0].weight, 64, 3, 3, 3)
+                # conv 1_1 on the 3-channel image: row-patch forward, row-fold image gradient (no patch matrix)
+                t["w0"] = ops.wpack(WPACK_ROWPATCH, convs[0].weight, 64, 3, 3, 3)
+                t["w0_rf"] = ops.wpack(WPACK_ROWFOLD_DGRAD, convs[0].weight, 64, 3, 3, 3)
                 for j in range(1, 5):
                     ci, co = VGG_CH[j]
                     t[f"w{j}"] = ops.wpack(WPACK_FWD, convs[j].weight, co, ci, 3, 3)
@@ -88,13 +89,12 @@ class VGGStyleContentLoss(nn.Module):
         P = self._packed()
         img = img.contiguous().float()
         B, _, H, W = img.shape
-        pg = ops.patch_geom(B, 3, H, W, 3, 3, 1, 1, 1, H, W, False)
-        a = ops.patch_gather_cached(img, pg, P["scale"], P["shift"])
-        m0 = B * H * W
-        f1 = ops.conv2d_fwd(a.view(1, 1, m0, pg.kpad), P["w0"], ops.gemm_geom(m0, pg.kpad, 64),
-                            ops.epilogue(bias=P["b"][0], act=ACT_RELU)).view(B, H, W, 64)
-        del a
+        # input renormalisation (losses.py:49-56) fused into the padded bf16 copy; zero padding = padding=1
+        g0 = ops.conv_geom(B, H, W, 3, 64, 3, 3, 1, 1, 1, H, W)
+        f1 = ops.conv_rowpatch_fwd(ops.img_pad8_cached(img, 1, False, P["scale"], P["shift"]), P["w0"], g0,
+                                   ops.epilogue(bias=P["b"][0], act=ACT_RELU))
         g = [None] * 5
+        g[0] = g0
         g[1] = ops.conv_geom(B, H, W, 64, 64, 3, 3, 1, 1, 1, H, W)
         f2 = ops.conv2d_fwd(f1, P["w1"], g[1], ops.epilogue(bias=P["b"][1], act=ACT_RELU))
         feats = [f1, f2]
@@ -110,7 +110,7 @@ class VGGStyleContentLoss(nn.Module):
                 g[4] = ops.conv_geom(B, H // 4, W // 4, 128, 256, 3, 3, 1, 1, 1, H // 4, W // 4)
                 f5 = ops.conv2d_fwd(p4, P["w4"], g[4], ops.epilogue(bias=P["b"][4], act=ACT_RELU))
                 feats.append(f5)
-        return feats, g, pg
+        return feats, g
 
     def features_of_real(self, img, upto):
         """Features of a data image; inside a train_step they are computed once (all five levels)
@@ -138,7 +138,7 @@ class _VGGLossFn(torch.autograd.Function):
         ops.ensure_init(gen.device)
         if gen.shape[2] % 4 or gen.shape[3] % 4:
             raise RuntimeError("VGG loss input height/width must be multiples of 4")
-        fg, geoms, pg = mod.features(gen, 5)
+        fg, geoms = mod.features(gen, 5)
         fs = mod.features_of_real(real_style, 5)
         fc = mod.features_of_real(real_content, 4)         # only relu_4_1 is used (losses.py:110)
         style = torch.zeros((), dtype=F32, device=gen.device)
@@ -151,14 +151,14 @@ class _VGGLossFn(torch.autograd.Function):
         content = ops.l1_loss_bf16_fwd(fg[3], fc[3])        # losses.py:91-98
         if ctx.needs_input_grad[1]:
             ctx.mod = mod
-            ctx.saved = (fg, fc[3], ssyms, geoms, pg)
+            ctx.saved = (fg, fc[3], ssyms, geoms)
         return content, style
 
     @staticmethod
     @ops.dev_guard
     def backward(ctx, g_content, g_style):
         mod = ctx.mod
-        fg, fc4, ssyms, g, pg = ctx.saved
+        fg, fc4, ssyms, g = ctx.saved
         P = mod._packed()
         g_content = g_content.contiguous().float()
         g_style = g_style.contiguous().float()
@@ -186,10 +186,11 @@ class _VGGLossFn(torch.autograd.Function):
         d1 = ops.conv2d_dgrad(dz2, P["w1_d"], g[1])
         d1 = ops.gram_bwd(f1, ssyms[0], alpha(f1), g_style, aux=d1)
         dz1 = ops.act_bwd(d1, f1, ACT_RELU)
+        # image gradient of conv 1_1: 3x3 conv of dz1 with the flipped filter (row-fold kernel, fp32 NCHW out),
+        # times the renormalisation's per-channel scale (epilogue ch_scale)
         B, H, W, _ = f1.shape
-        m0 = B * H * W
-        da = ops.conv2d_fwd(dz1.view(1, 1, m0, 64), P["w0_d"], ops.gemm_geom(m0, 64, pg.kpad))
-        dgen = ops.patch_scatter(da.view(m0, pg.kpad), pg, P["scale"])
+        gd = ops.conv_geom(B, H, W, 64, 3, 3, 3, 1, 1, 1, H, W)          # pad' = R - 1 - pad = 1
+        dgen = ops.conv_narrow_fwd(dz1, P["w0_rf"], gd, ops.epilogue(out_layout=OUT_F32_NCHW, ch_scale=P["scale"]))
         ctx.saved = None
         return None, dgen, None, None
 

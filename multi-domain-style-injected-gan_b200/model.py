@@ -32,6 +32,15 @@ def _grad_buf(p):
     return p.grad
 
 
+def _trace(mod, name, t):
+    """Test hook (tests/layerwise_cases.py): when a module carries a `_msig_trace` dict, the network-level
+    Functions record their saved activations and the intermediate gradient tensors of their backward in it,
+    so that every layer can be checked on its own against the oracle. A no-op otherwise."""
+    tr = mod.__dict__.get("_msig_trace")
+    if tr is not None:
+        tr[name] = t
+
+
 def _require_cuda(t, what):
     if not t.is_cuda:
         raise RuntimeError(f"{what}: expected a CUDA tensor; msig_b200 has no CPU path")
@@ -448,6 +457,8 @@ class _GeneratorFn(torch.autograd.Function):
                              st2=st2, x2=res[0][0] if k else x, sb=sb, bs=bs, res=res, g3=g3, x_res=x, gu1=gu1,
                              zu1=zu1, stu1=stu1, yu1=yu1, gu2=gu2, zu2=zu2, stu2=stu2, xp=xp, out=out,
                              style_shape=style.shape, img_grad=ctx.needs_input_grad[1], style_grad=ctx.needs_input_grad[2])
+            _trace(mod, "fwd", ctx.saved)
+            _trace(mod, "gb", gb)
         return out
 
     @staticmethod
@@ -464,16 +475,19 @@ class _GeneratorFn(torch.autograd.Function):
         dout = dout.contiguous().float()
         # ---- final 7x7 reflect conv + tanh (model.py:141): gather dy patches ("full" correlation)
         dz = ops.tanh_bwd(dout, out)
+        _trace(mod, "dz_f", dz)
         if wg:
             ops.nchw_chansum(dz, _grad_buf(dec[k + 6].bias))
         gfd = ops.conv_geom(B, H, W, 3, 64, 7, 7, 1, 6, 6, H + 6, W + 6)
         dz8 = ops.img_pad8(dz, 6, False)            # zero-extended bf16 copy of the 3-channel gradient
         dxp = ops.conv_rowpatch_fwd(dz8, P["f_d"], gfd)
+        _trace(mod, "dxp", dxp)
         if wg:
             ops.conv_rowpatch_wgrad(dz8, S["xp"], gfd, _grad_buf(dec[k + 6].weight), flip=True)
         del dz8
         # ---- up 2 (ConvTranspose 128->64 + IN + ReLU); the reflect fold of dxp happens inside the norm backward
         dzu2 = ops.norm_act_bwd_pad(dxp, S["zu2"], S["stu2"], ACT_RELU, 3)
+        _trace(mod, "dzu2", dzu2)
         del dxp
         if wg:
             ops.convT2d_wgrad(S["yu1"], dzu2, S["gu2"], _grad_buf(dec[k + 3].weight))
@@ -486,7 +500,9 @@ class _GeneratorFn(torch.autograd.Function):
                                ops.epilogue(aux=S["yu1"], aux_mode=AUX_RELU_MASK, stats=es, stats_z=S["zu1"]))
         del dzu2
         # ---- up 1 (ConvTranspose 256->128 + IN + ReLU)
+        _trace(mod, "dyu1", dy)
         dzu1 = ops.norm_bwd_from(es, dy, S["zu1"], S["stu1"])
+        _trace(mod, "dzu1", dzu1)
         if wg:
             ops.convT2d_wgrad(S["x_res"], dzu1, gu1, _grad_buf(dec[k].weight))
         es = ops.epi_stats(B, gu1.h, gu1.w, gu1.c, dev) if k else None
@@ -496,6 +512,8 @@ class _GeneratorFn(torch.autograd.Function):
         # ---- residual blocks, reversed
         nl = 2 * k
         dgb = torch.zeros((B, nl * 512), dtype=F32, device=dout.device)
+        _trace(mod, "dgb", dgb)
+        _trace(mod, "dx_res", dy)
         g3 = S["g3"]
         for i in reversed(range(k)):
             x_in, za, sta, ha, zb, stb = S["res"][i]
@@ -510,6 +528,7 @@ class _GeneratorFn(torch.autograd.Function):
                                   ops.epilogue(aux=ha, aux_mode=AUX_RELU_MASK, stats=es, stats_z=za))
             dza = ops.norm_bwd_from(es, dh, za, sta, dgamma=dgb[:, l * 512:], dbeta=dgb[:, l * 512 + 256:],
                                     dgb_stride=nl * 512)
+            _trace(mod, f"res{i}", (dy, dzb, dh, dza))       # (dy into the block, dz conv2, dh, dz conv1)
             if wg:
                 ops.conv2d_wgrad(x_in, dza, g3, _grad_buf(blk.conv1.weight))
             # + the skip connection's gradient; for i > 0 also the reductions of block i-1's second AdaIN
@@ -522,7 +541,9 @@ class _GeneratorFn(torch.autograd.Function):
         dstyle = _style_linears_backward(dgb, B, S["bs"], nl, 512, sd, S["sb"], P["lin_d"], adains, wg,
                                          S["style_grad"], S["style_shape"])
         # ---- encoder, reversed
+        _trace(mod, "dx2", dy)
         dz2 = ops.norm_act_bwd(dy, S["z2"], S["st2"], ACT_RELU)
+        _trace(mod, "dz2", dz2)
         if wg:
             ops.conv2d_wgrad(S["y1"], dz2, S["g2"], _grad_buf(enc[6].weight))
         g2, g1 = S["g2"], S["g1"]
@@ -530,12 +551,16 @@ class _GeneratorFn(torch.autograd.Function):
         dy = ops.conv2d_dgrad(dz2, P["e2_d"], g2,
                               ops.epilogue(aux=S["y1"], aux_mode=AUX_RELU_MASK, stats=es, stats_z=S["z1"]))
         del dz2
+        _trace(mod, "dy1", dy)
         dz1 = ops.norm_bwd_from(es, dy, S["z1"], S["st1"])
+        _trace(mod, "dz1", dz1)
         if wg:
             ops.conv2d_wgrad(S["y0"], dz1, g1, _grad_buf(enc[3].weight))
         dy = ops.conv2d_dgrad(dz1, P["e1_d"], g1)      # K = 4*128: too short to hide the fused reductions
         del dz1
+        _trace(mod, "dy0", dy)
         dz0 = ops.norm_act_bwd(dy, S["z0"], S["st0"], ACT_RELU)
+        _trace(mod, "dz0", dz0)
         if wg:
             # the padded bf16 image copy is re-made (or step-cached), not saved
             ops.conv_rowpatch_wgrad(ops.img_pad8_cached(S["img"], 3, True), dz0, S["g0"], _grad_buf(enc[0].weight))

@@ -71,11 +71,12 @@ def conv_geom(n, h, w, c, k, r, s, stride, pad_t, pad_l, oh, ow):
 
 
 def epilogue(bias=None, aux=None, aux_mode=AUX_NONE, act=ACT_NONE, alpha=1.0, alpha_ptr=None,
-             slope=0.2, out_layout=OUT_BF16_NHWC, stats=None, stats_z=None):
+             slope=0.2, out_layout=OUT_BF16_NHWC, stats=None, stats_z=None, ch_scale=None):
     """`stats`: an EpiStats buffer that receives the per-(image, channel) partial sums of the stored
     output (sum v, sum v*v, or sum v*z when `stats_z` is given) from the GEMM epilogue."""
     return Epilogue(_p(bias), _p(aux), aux_mode if aux is not None else AUX_NONE, act, alpha,
-                    _p(alpha_ptr), slope, out_layout, _p(None if stats is None else stats.buf), _p(stats_z))
+                    _p(alpha_ptr), slope, out_layout, _p(None if stats is None else stats.buf), _p(stats_z),
+                    _p(ch_scale))
 
 
 # The epilogue-fused reductions cost ~900 cycles per 64 accumulator columns per tile; they are hidden
@@ -189,22 +190,24 @@ def conv2d_fwd(x, wpk, g, e=None, out=None):
     return out
 
 
-def img_pad8(src, pad, reflect):
-    """fp32 NCHW image (c <= 8) -> bf16 [n, h+2p, w+2p+2, 8], reflect or zero padded (row-patch convs)."""
+def img_pad8(src, pad, reflect, scale=None, shift=None):
+    """fp32 NCHW image (c <= 8) -> bf16 [n, h+2p, w+2p+2, 8], reflect or zero padded (row-patch convs);
+    with scale / shift ([c] fp32) the stored value is x*scale + shift (padding stays 0)."""
     n, c, h, w = src.shape
     out = torch.empty((n, h + 2 * pad, w + 2 * pad + 2, 8), dtype=BF16, device=src.device)
-    L.call("msig_img_pad8", _p(src), n, c, h, w, pad, int(reflect), _p(out), _stream())
+    L.call("msig_img_pad8", _p(src), n, c, h, w, pad, int(reflect), _p(scale), _p(shift), _p(out), _stream())
     return out
 
 
-def img_pad8_cached(src, pad, reflect):
+def img_pad8_cached(src, pad, reflect, scale=None, shift=None):
     """img_pad8 of an IMAGE that stays unchanged for the rest of the step (see patch_gather_cached)."""
     if _step_cache is None:
-        return img_pad8(src, pad, reflect)
-    key = ("pad8", src.data_ptr(), src._version, tuple(src.shape), pad, bool(reflect))
+        return img_pad8(src, pad, reflect, scale, shift)
+    key = ("pad8", src.data_ptr(), src._version, tuple(src.shape), pad, bool(reflect),
+           0 if scale is None else scale.data_ptr())
     hit = _step_cache.get(key)
     if hit is None:
-        hit = (src, img_pad8(src, pad, reflect))
+        hit = (src, img_pad8(src, pad, reflect, scale, shift))
         _step_cache[key] = hit
     return hit[1]
 

@@ -223,15 +223,18 @@ def generator_forward(sd, img, style, n_res=8):
 
 
 def _first_conv(img, w, b, k, stride, pad, slope, pre_scale=None, pre_shift=None):
-    """The 3-channel first conv of SE / D / VGG + bias + (Leaky)ReLU. Emulation: the CUDA path runs it as a
-    GEMM over a gathered bf16 patch matrix, and its image gradient is the scatter-add (fp32) of the bf16
-    patch-matrix gradient -- restated with unfold so that the per-tap products are rounded the same way.
-    pre_scale / pre_shift: the VGG input renormalisation x*scale + shift, applied before the rounding."""
+    """The 3-channel first conv of SE / D / VGG + bias + (Leaky)ReLU. Emulation: SE / D run it as a GEMM over
+    a gathered bf16 patch matrix, and the image gradient is the scatter-add (fp32) of the bf16 patch-matrix
+    gradient -- restated with unfold so that the per-tap products are rounded the same way. The VGG conv
+    (pre_scale / pre_shift = the input renormalisation x*scale + shift, applied before the rounding) runs
+    on the row-patch / row-fold kernels: its image gradient is accumulated in fp32 and scaled in fp32."""
     if not _EMU:
         x = img if pre_scale is None else img * pre_scale + pre_shift
         y = F.conv2d(x, w, b, stride=stride, padding=pad)
         return F.relu(y) if slope == 0.0 else F.leaky_relu(y, slope)
     x = wq(img if pre_scale is None else img * pre_scale + pre_shift)
+    if pre_scale is not None:
+        return act_store(F.conv2d(x, wq(w), b, stride=stride, padding=pad), slope)
     n, c, h, wd = x.shape
     oh, ow = (h + 2 * pad - k) // stride + 1, (wd + 2 * pad - k) // stride + 1
     a = gq(F.unfold(x, k, padding=pad, stride=stride))                       # [n, c*k*k, oh*ow]

@@ -43,10 +43,12 @@ def all_cases():
     import ops_cases
     import net_cases
     import fullsize_cases
+    import layerwise_cases
     d = dict(igemm_cases.CASES)
     d.update(ops_cases.CASES)
     d.update(net_cases.CASES)
     d.update(fullsize_cases.CASES)
+    d.update(layerwise_cases.CASES)
     return d
 
 

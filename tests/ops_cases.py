@@ -236,8 +236,8 @@ def case_determinism(seed=0):
     diff = max(float((x - y).abs().max()) for x, y in zip(r1, r2))
     ref = [dy.float().sum(0), img.sum((0, 2, 3)), (img - a).abs().mean(), (fa.float() - fb.float()).abs().mean(),
            ((a - 1) ** 2).mean(), (flat.double() ** 2).sum().float(), (ga - gb).abs().mean()]
-    acc = max(rel_err(x, y) for x, y in zip(r1, ref))
-    return (1.0 if diff != 0.0 else 0.0) + acc, 1e-4
+    acc = max(rel_err(x, y) for x, y in zip(r1, ref))      # fp32 sums of ~1e6 random-sign terms: ~1e-3 of max
+    return (1.0 if diff != 0.0 else 0.0) + acc, 3e-3
 
 
 def case_gram_l1(seed=0):
