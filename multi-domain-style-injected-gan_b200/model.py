@@ -820,6 +820,7 @@ class _DiscriminatorFn(torch.autograd.Function):
             ctx.mod = mod
             ctx.saved = dict(img=img, pg=pg, y0=y0, layers=layers, y3=y, idx=idx, hw=(h, w),
                              img_grad=ctx.needs_input_grad[1])
+            _trace(mod, "fwd", ctx.saved)
         return out
 
     @staticmethod
@@ -842,6 +843,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         dev = dout.device
         es = None                                      # (the head GEMM's K is too short to fuse them)
         dy = ops.conv2d_fwd(ad.view(1, 1, mh, pgh.kpad), P["h_d"], ops.gemm_geom(mh, pgh.kpad, 512)).view(B, h, w, 512)
+        _trace(mod, "dy3", dy)
         if wg:
             ws, splits = ops.gemm_tn_partial(mh, ad, pgh.kpad, S["y3"], 512)
             for kx, br in enumerate(mod.domain_branches):
@@ -853,6 +855,7 @@ class _DiscriminatorFn(torch.autograd.Function):
             ci, co = _TRUNK[j]
             y_in, g, z, st = S["layers"][j - 1]
             dz = ops.norm_bwd_from(es, dy, z, st) if es is not None else ops.norm_act_bwd(dy, z, st, ACT_LRELU)
+            _trace(mod, f"dz{j}", dz)
             if wg:
                 ops.conv2d_wgrad(y_in, dz, g, _grad_buf(convs[j].weight))
             if j > 1:
@@ -862,6 +865,7 @@ class _DiscriminatorFn(torch.autograd.Function):
                                                    stats_z=S["layers"][j - 2][2]))
             else:   # dgrad fused with LeakyReLU' of the first layer's output
                 dy = ops.conv2d_dgrad(dz, P[f"c{j}_d"], g, ops.epilogue(aux=S["y0"], aux_mode=AUX_LRELU_MASK))
+            _trace(mod, f"dy{j - 1}", dy)
         dz0 = dy
         pg = S["pg"]
         m0 = dz0.shape[0] * dz0.shape[1] * dz0.shape[2]

@@ -11,11 +11,11 @@ gradient tensor (model._trace), and EACH LAYER is then recomputed by the oracle 
 INPUTS to that layer (forward: its input activation; backward: its upstream gradient), so nothing is more
 than one layer deep and the bounds are tight:
 
-  * bf16 tensors (activations z / y, gradients dz / dy): cosine >= 0.99999, at most 3 % of the elements
+  * bf16 tensors (activations z / y, gradients dz / dy): cosine >= 0.999999, at most 1 % of the elements
     differ at all (single flipped roundings where the two fp32 summation orders straddle a rounding
-    boundary), at most 0.1 % by more than one bf16 ulp;
+    boundary), at most 0.05 % by more than one bf16 ulp;
   * fp32 tensors (weight / bias / gamma / beta / style / image gradients, statistics, the tanh output):
-    cosine >= 0.999999 and max|a-b| / max|b| <= 2e-3.
+    cosine >= 0.999999 and max|a-b| / max|b| <= 2e-4.
 
 Covers every layer of /root/reference/model.py:121-151 (generator) in both directions: first 7x7 reflect conv
 (row-patch kernel), both stride-2 convs, all 16 residual-block convs + AdaIN sites (fused statistics, fused
@@ -30,8 +30,9 @@ from msig_b200 import model as M
 from oracle import oracle as O
 
 DEV = "cuda"
-BF16_COS, BF16_FLIP_FRAC, BF16_GT1ULP_FRAC = 0.99999, 0.03, 1e-3
-F32_COS, F32_MAXREL = 0.999999, 2e-3
+# measured on B200 (profiles/parity_r2.json): 1-cos <= 1.2e-8, flipped <= 0.17 %, > 1 ulp <= 0.018 %; fp32 max-rel <= 2.2e-5
+BF16_COS, BF16_FLIP_FRAC, BF16_GT1ULP_FRAC = 0.999999, 0.01, 5e-4
+F32_COS, F32_MAXREL = 0.999999, 2e-4
 
 
 def nchw(t):
@@ -246,7 +247,103 @@ def case_generator_layerwise(b=2, s=64, style_batch=None, seed=0):
     return rep.summary(), rep.ok
 
 
+def case_discriminator_layerwise(b=3, s=64, nd=4, seed=0):
+    """Every layer of MultiDomainDiscriminator (model.py:154-214), forward and backward, teacher-forced: the
+    gathered-patch first conv (GEMM forward, bf16 patch-gradient + scatter-add image gradient, weight /
+    bias gradients), the three conv + InstanceNorm + LeakyReLU layers (fused statistics; LeakyReLU' fused
+    into the dgrad epilogues with the norm-backward reductions), and the per-domain heads run as one GEMM
+    (ZeroPad2d((1,0,1,0)) + padding 1, head selection, zero gradients for the unselected heads)."""
+    torch.manual_seed(seed)
+    D = M.MultiDomainDiscriminator(num_domains=nd).to(DEV)
+    tr = {}
+    D.__dict__["_msig_trace"] = tr
+    sd = {k: v.detach().float().cpu().clone() for k, v in D.state_dict().items()}
+    g = torch.Generator().manual_seed(seed + 1)
+    img = torch.rand(b, 3, s, s, generator=g) * 2 - 1
+    idx = torch.tensor([(i * 3 + 1) % nd for i in range(b)])
+    dout = torch.randn(b, 1, s // 16, s // 16, generator=g)
+    img_c = img.to(DEV).requires_grad_(True)
+    out = D(img_c, idx.to(DEV))
+    (out * dout.to(DEV)).sum().backward()
+    torch.cuda.synchronize()
+    S = tr["fwd"]
+    grads = {n: cpu(p.grad) for n, p in D.named_parameters()}
+    rep = Report()
+    keys = ("shared_layers.0", "shared_layers.2", "shared_layers.5", "shared_layers.8")
+    sl = O.LRELU
+
+    def lrelu_grad(y):
+        return torch.where(y > 0, torch.ones_like(y), torch.full_like(y, sl))
+
+    def first_conv(x, w, bias):
+        a = O.gq(F.unfold(O.wq(x), 4, padding=1, stride=2))
+        return (O.wq(w).reshape(64, -1) @ a).view(x.shape[0], 64, s // 2, s // 2) + bias.view(1, -1, 1, 1)
+
+    with O.emulate_bf16():
+        # ---- forward
+        y = [nchw(S["y0"])] + [None] * 3
+        z = [None] * 4
+        rep.bf16("fwd.c0.y", y[0], O.act_store(first_conv(img, sd[keys[0] + ".weight"], sd[keys[0] + ".bias"]), sl).detach())
+        for j in (1, 2, 3):
+            y_in, _, zj, st = S["layers"][j - 1]
+            z[j] = nchw(zj)
+            rep.bf16(f"fwd.c{j}.z", z[j], O.st(F.conv2d(y[j - 1], O.wq(sd[keys[j] + ".weight"]), None, stride=2, padding=1)).detach())
+            _stats_check(rep, f"fwd.c{j}", st, z[j])
+            y[j] = nchw(S["layers"][j][0]) if j < 3 else nchw(S["y3"])
+            rep.bf16(f"fwd.c{j}.y", y[j], O.act_store(O.instance_norm(z[j]), sl).detach())
+
+        def heads(y3, ws, bs_):
+            xp = F.pad(y3, (1, 0, 1, 0))
+            outs = [O.gq(F.conv2d(xp, O.wq(ws[k]), padding=1)) + bs_[k].view(1, -1, 1, 1) for k in range(nd)]
+            return torch.stack(outs, dim=1)[torch.arange(b), idx]
+        hw_ = [sd[f"domain_branches.{k}.1.weight"] for k in range(nd)]
+        hb_ = [sd[f"domain_branches.{k}.1.bias"] for k in range(nd)]
+        rep.f32("fwd.out", cpu(out), heads(y[3], hw_, hb_).detach(), 1e-4)
+        # ---- backward: heads
+        y3l = _leaf(y[3])
+        wl, bl = [_leaf(t) for t in hw_], [_leaf(t) for t in hb_]
+        heads(y3l, wl, bl).backward(dout)
+        dy3 = nchw(tr["dy3"])
+        rep.bf16("bwd.heads.dy", dy3, _r(y3l.grad))
+        for k in range(nd):
+            gw, gb_ = grads[f"domain_branches.{k}.1.weight"], grads[f"domain_branches.{k}.1.bias"]
+            if wl[k].grad is None or float(wl[k].grad.abs().max()) == 0.0:          # unselected head: exact zeros
+                rep.ok = rep.ok and float(gw.abs().max()) == 0.0 and float(gb_.abs().max()) == 0.0
+                rep.rows.append((f"bwd.head{k}.zero", "f32", 0.0, float(gw.abs().max()), 0.0,
+                                 float(gw.abs().max()) == 0.0))
+            else:
+                rep.f32(f"bwd.head{k}.dW", gw, wl[k].grad)
+                rep.f32(f"bwd.head{k}.db", gb_, bl[k].grad)
+        # ---- trunk, reversed
+        g_up = dy3
+        for j in (3, 2, 1):
+            zl = _leaf(z[j])
+            u = O.instance_norm(O.st(zl))
+            # layer 3: dy was stored by the head GEMM first, LeakyReLU' is applied by the norm backward;
+            # layers 2, 1: the dgrad epilogue already applied it (g_up is masked)
+            (F.leaky_relu(u, sl) if j == 3 else u).backward(g_up)
+            dz = nchw(tr[f"dz{j}"])
+            rep.bf16(f"bwd.c{j}.dz", dz, zl.grad)
+            xl, wj = _leaf(y[j - 1]), _leaf(sd[keys[j] + ".weight"])
+            O.st(F.conv2d(xl, O.wq(wj), None, stride=2, padding=1)).backward(dz)
+            rep.f32(f"bwd.c{j}.dW", grads[keys[j] + ".weight"], wj.grad)
+            g_up = nchw(tr[f"dy{j - 1}"])
+            rep.bf16(f"bwd.c{j}.dy", g_up, _r(xl.grad * lrelu_grad(y[j - 1])))
+        # ---- gathered first conv: weight / bias / image gradients from dz0 (= dy0, already masked)
+        il, w0, b0 = _leaf(img), _leaf(sd[keys[0] + ".weight"]), _leaf(sd[keys[0] + ".bias"])
+        first_conv(il, w0, b0).backward(g_up)
+        rep.f32("bwd.c0.dW", grads[keys[0] + ".weight"], w0.grad)
+        rep.f32("bwd.c0.db", grads[keys[0] + ".bias"], b0.grad)
+        # fp32 scatter-add of <= 16 bf16 patch-gradient entries per pixel: a flipped rounding of one entry
+        # moves the pixel by one bf16 ulp of that entry (measured max-rel 3e-4 .. 9e-4)
+        rep.f32("bwd.c0.dimg", cpu(img_c.grad), il.grad, 3e-3)
+    D.__dict__.pop("_msig_trace", None)
+    return rep.summary(), rep.ok
+
+
 CASES = {
+    "discriminator_layerwise": case_discriminator_layerwise,
+    "discriminator_layerwise_nd10": lambda: case_discriminator_layerwise(2, 128, 10, seed=4),
     "generator_layerwise_b2_s64": lambda: case_generator_layerwise(2, 64),
     "generator_layerwise_style_broadcast": lambda: case_generator_layerwise(3, 64, style_batch=1, seed=2),
     "generator_layerwise_s128": lambda: case_generator_layerwise(1, 128, seed=3),

@@ -73,9 +73,11 @@ def emu_ok(m, scale=1.0):
 NOISE_K = 2.0
 
 
-def noise_ok(m, e, k=NOISE_K):
-    """m = metrics(cuda, fp32), e = metrics(emulated, fp32): CUDA is within k x the bf16-storage noise floor."""
-    return (1.0 - m[0]) <= k * (1.0 - e[0]) + 1e-4 and m[1] <= max(k * e[1], 2e-2) and m[2] <= k * e[2] + 2e-2
+def noise_ok(m, e, k=NOISE_K, norm_floor=GRAD_NORM):
+    """m = metrics(cuda, fp32), e = metrics(emulated, fp32): CUDA is within k x the bf16-storage noise floor.
+    (The norm ratio is a signed random quantity: one emulated sample does not bound another, so its bound
+    is the larger of k x the sample and the fixed allowance, 5 % per network / 10 % for chained networks.)"""
+    return (1.0 - m[0]) <= k * (1.0 - e[0]) + 1e-4 and m[1] <= max(k * e[1], norm_floor) and m[2] <= k * e[2] + 2e-2
 
 
 def _worst(ms):
@@ -117,7 +119,7 @@ def _param_grad_errs(mod, sd_leaf, dead=(), ok_fn=None):
     return {"cos_min": w[0], "norm_err": w[1], "maxrel": w[2], "ok": all_ok}, worst_name, dead_worst
 
 
-def _param_grad_noise(mod, sd_ref, sd_emu, dead=()):
+def _param_grad_noise(mod, sd_ref, sd_emu, dead=(), norm_floor=GRAD_NORM):
     """noise_ok for every parameter gradient: CUDA-vs-fp32 against emulated-vs-fp32."""
     named = dict(mod.named_parameters())
     worst, worst_name, all_ok = 0.0, "", True
@@ -126,7 +128,7 @@ def _param_grad_noise(mod, sd_ref, sd_emu, dead=()):
             continue
         m = grad_metrics(named[k].grad, ref.grad)
         e = grad_metrics(sd_emu[k].grad, ref.grad)
-        all_ok = all_ok and noise_ok(m, e)
+        all_ok = all_ok and noise_ok(m, e, norm_floor=norm_floor)
         ratio = (1.0 - m[0]) / max(1.0 - e[0], 1e-6)
         if ratio > worst:
             worst, worst_name = ratio, k
@@ -448,7 +450,7 @@ def case_train_step(b=2, s=64, nd=3, steps=2, seed=0):
                     if n in dead or key not in floor:
                         continue
                     m = grad_metrics(p.grad, ref["grads"][key])
-                    t_ok = noise_ok(m, floor[key])
+                    t_ok = noise_ok(m, floor[key], norm_floor=(3 if n.endswith("bias") else 2) * GRAD_NORM)
                     worst_ratio = max(worst_ratio, (1.0 - m[0]) / max(1.0 - floor[key][0], 1e-6))
                     if not t_ok:
                         bad.append((key, [round(x, 5) for x in m], [round(x, 5) for x in floor[key]]))
@@ -509,8 +511,8 @@ def case_gd_512(seed=0):
     nf = res["noise_floor"]
     nf["fake"], nf["d"] = rel(emu["fake"], ref["fake"]), rel(emu["d"], ref["d"])
     nf["dimg"], nf["dstyle"] = grad_metrics(emu["dimg"], ref["dimg"]), grad_metrics(emu["dstyle"], ref["dstyle"])
-    res["G.wgrad_noise"] = _param_grad_noise(G, ref["G"], emu["G"], dead_g)
-    res["D.wgrad_noise"] = _param_grad_noise(D, ref["D"], emu["D"], dead_d)
+    res["G.wgrad_noise"] = _param_grad_noise(G, ref["G"], emu["G"], dead_g, 2 * GRAD_NORM)
+    res["D.wgrad_noise"] = _param_grad_noise(D, ref["D"], emu["D"], dead_d, 2 * GRAD_NORM)
     ok = (res["fake"] <= ACT_TOL and res["fake"] <= NOISE_K * nf["fake"] + 1e-3 and res["d"] <= NOISE_K * nf["d"] + 1e-2
           and res["loss"] <= LOSS_TOL and res["emu"]["loss"] <= 2.5 * EMU_LOSS
           and noise_ok(res["dimg"], nf["dimg"]) and noise_ok(res["dstyle"], nf["dstyle"])
