@@ -114,8 +114,11 @@ typedef struct msig_wpack_job {
   int64_t copy_numel;
 } msig_wpack_job;
 size_t msig_wpack_table_bytes(int32_t n_jobs);
-int msig_wpack_table_build(const msig_wpack_job* jobs, int32_t n_jobs, void* table_host, int64_t* total_out);
-int msig_wpack_multi(const void* table_dev, int32_t n_jobs, int64_t total, void* stream);
+/* total_out: elements handled by the generic (scatter) kernel; total_tiles_out: shared-memory tiles of the
+ * big FWD / DGRAD_S1 packs (coalesced reads AND writes). Pass both to msig_wpack_multi. */
+int msig_wpack_table_build(const msig_wpack_job* jobs, int32_t n_jobs, void* table_host, int64_t* total_out,
+                           int64_t* total_tiles_out);
+int msig_wpack_multi(const void* table_dev, int32_t n_jobs, int64_t total, int64_t total_tiles, void* stream);
 
 /* ---- convolutions (tcgen05 implicit GEMM) ------------------------------------------------
  * Replace nn.Conv2d (model.py:45,48,72-75,132-133,165,183; losses.py:15), nn.Linear

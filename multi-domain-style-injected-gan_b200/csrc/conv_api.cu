@@ -130,8 +130,75 @@ struct PackJob {
   PackGeom g;            // g.kind < 0: plain fp32 copy of `numel` elements (bias tables)
   const float* w;
   void* out;
-  int64_t start, numel;
+  int64_t start, numel;  // element range in the generic kernel's index space (numel = 0: a tiled job)
+  int64_t tile_start;    // tile range in the tiled kernel's index space
+  int32_t tiles, tile_mode;   // tile_mode: 0 none, 1 = FWD (one tile per o), 2 = DGRAD_S1 (64 o x 64 (i,t) tiles)
 };
+
+// The big packs (conv / Linear weights in the FWD and DGRAD_S1 layouts: 95 % of a generator's bytes) go
+// through shared memory so that BOTH sides are coalesced: the generic kernel below reads fp32 linearly but
+// scatters 2-byte stores (one 32-byte sector per element).
+//   mode 1, FWD     [O][I][RS] -> [o + off][RS][I]: the I*RS elements of one o stay one contiguous range,
+//                   permuted (i, t) -> (t, i): one block per o, transposed in shared memory.
+//   mode 2, DGRAD_S1 [O][I][RS] -> [i][RS-1-t][o + off]: o becomes the fastest index: 64 (o) x 64 (i, t)
+//                   tiles, read along (i, t), written along o (128 bytes per warp store).
+constexpr int kPackTile = 64;
+constexpr int kPackFwdMax = 8192;     // I * RS elements of one output channel held in shared memory
+
+__global__ void __launch_bounds__(256) wpack_multi_tiled_kernel(const PackJob* __restrict__ jobs, int n_jobs,
+                                                                int64_t total_tiles) {
+  __shared__ __align__(16) unsigned char smem_raw[kPackTile * (kPackTile + 1) * 4 > (kPackFwdMax + 64) * 2
+                                                      ? kPackTile * (kPackTile + 1) * 4
+                                                      : (kPackFwdMax + 64) * 2];
+  for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int lo = 0, hi = n_jobs - 1;                      // last job with tile_start <= tile (and tiles > 0)
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].tile_start <= tile) lo = mid; else hi = mid - 1;
+    }
+    const PackJob& j = jobs[lo];
+    const PackGeom& g = j.g;
+    const int lt = static_cast<int>(tile - j.tile_start);
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(j.out);
+    __syncthreads();                                  // the previous tile's readers are done with smem
+    if (j.tile_mode == 1) {
+      const int o = lt, n = g.I * g.RS, ld = g.I + 2;  // padded rows: conflict-free transposed writes
+      __nv_bfloat16* sm = reinterpret_cast<__nv_bfloat16*>(smem_raw);
+      const float* src = j.w + int64_t(o) * n;
+      for (int e = threadIdx.x; e < n; e += 256) {
+        const int i = e / g.RS, t = e - i * g.RS;
+        sm[t * ld + i] = __float2bfloat16(__ldg(src + e));
+      }
+      __syncthreads();
+      __nv_bfloat16* dst = out + int64_t(o + g.OOFF) * n;
+      const int half = g.I / 2;                       // I is even (eligibility): bf16x2 stores
+      for (int e = threadIdx.x; e < g.RS * half; e += 256) {
+        const int t = e / half, i2 = e - t * half;
+        *reinterpret_cast<uint32_t*>(dst + t * g.I + 2 * i2) = *reinterpret_cast<const uint32_t*>(sm + t * ld + 2 * i2);
+      }
+    } else {
+      float* sm = reinterpret_cast<float*>(smem_raw);  // [64 o][65]
+      const int n = g.I * g.RS;
+      const int e_tiles = (n + kPackTile - 1) / kPackTile;
+      const int o0 = (lt / e_tiles) * kPackTile, e0 = (lt % e_tiles) * kPackTile;
+      for (int q = threadIdx.x; q < kPackTile * kPackTile; q += 256) {
+        const int ol = q / kPackTile, x = q % kPackTile;
+        sm[ol * (kPackTile + 1) + x] = (e0 + x < n) ? __ldg(j.w + int64_t(o0 + ol) * n + e0 + x) : 0.f;
+      }
+      __syncthreads();
+      for (int q = threadIdx.x; q < kPackTile * (kPackTile / 2); q += 256) {
+        const int x = q / (kPackTile / 2), o2 = q % (kPackTile / 2);
+        const int e = e0 + x;
+        if (e >= n) continue;
+        const int i = e / g.RS, t = e - i * g.RS;
+        const int64_t row = int64_t(i) * g.RS + (g.RS - 1 - t);
+        const __nv_bfloat162 v = __floats2bfloat162_rn(sm[(2 * o2) * (kPackTile + 1) + x],
+                                                       sm[(2 * o2 + 1) * (kPackTile + 1) + x]);
+        *reinterpret_cast<__nv_bfloat162*>(out + row * g.OC + o0 + g.OOFF + 2 * o2) = v;
+      }
+    }
+  }
+}
 
 __global__ void wpack_multi_kernel(const PackJob* __restrict__ jobs, int n_jobs, int64_t total) {
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
@@ -628,10 +695,11 @@ size_t msig_wpack_part_elems(const msig_wpack_desc* d, int32_t oc) {
 
 size_t msig_wpack_table_bytes(int32_t n_jobs) { return size_t(n_jobs) * sizeof(PackJob); }
 
-int msig_wpack_table_build(const msig_wpack_job* jobs, int32_t n_jobs, void* table_host, int64_t* total_out) {
-  MSIG_REQUIRE(jobs && table_host && total_out && n_jobs > 0, "msig_wpack_table_build: bad argument");
+int msig_wpack_table_build(const msig_wpack_job* jobs, int32_t n_jobs, void* table_host, int64_t* total_out,
+                           int64_t* total_tiles_out) {
+  MSIG_REQUIRE(jobs && table_host && total_out && total_tiles_out && n_jobs > 0, "msig_wpack_table_build: bad argument");
   PackJob* t = reinterpret_cast<PackJob*>(table_host);
-  int64_t start = 0;
+  int64_t start = 0, tile_start = 0;
   for (int k = 0; k < n_jobs; ++k) {
     const msig_wpack_job& j = jobs[k];
     MSIG_REQUIRE(j.src && j.dst, "msig_wpack_table_build: job %d has a null pointer", k);
@@ -643,23 +711,50 @@ int msig_wpack_table_build(const msig_wpack_job* jobs, int32_t n_jobs, void* tab
       t[k].g = make_pack_geom(&j.d, j.oc, j.o_off);
       MSIG_REQUIRE(pack_elems(t[k].g) > 0, "msig_wpack_table_build: job %d: unknown kind %d", k, j.d.kind);
       t[k].numel = int64_t(t[k].g.O) * t[k].g.I * t[k].g.RS;
+      // big FWD / DGRAD_S1 packs go through the shared-memory tiled kernel (coalesced on both sides)
+      const PackGeom& g = t[k].g;
+      const int n = g.I * g.RS;
+      const bool aligned = (reinterpret_cast<uintptr_t>(j.dst) & 3) == 0;
+      if (aligned && g.kind == MSIG_WPACK_FWD && g.I % 2 == 0 && n >= 256 && n + 2 * g.RS <= kPackFwdMax + 64 &&
+          ((int64_t(g.OOFF) * n) % 2) == 0) {
+        t[k].tile_mode = 1;
+        t[k].tiles = g.O;
+      } else if (aligned && g.kind == MSIG_WPACK_DGRAD_S1 && g.O % kPackTile == 0 && g.OC % 2 == 0 && g.OOFF % 2 == 0 &&
+                 n >= 64) {
+        t[k].tile_mode = 2;
+        t[k].tiles = (g.O / kPackTile) * static_cast<int>(ceil_div(n, kPackTile));
+      }
+      if (t[k].tile_mode != 0) t[k].numel = 0;
     }
     t[k].w = j.src;
     t[k].out = j.dst;
     t[k].start = start;
     start += t[k].numel;
+    t[k].tile_start = tile_start;
+    tile_start += t[k].tiles;
   }
   *total_out = start;
+  *total_tiles_out = tile_start;
   return MSIG_OK;
 }
 
-int msig_wpack_multi(const void* table_dev, int32_t n_jobs, int64_t total, void* stream) {
-  MSIG_REQUIRE(table_dev && n_jobs > 0 && total > 0, "msig_wpack_multi: bad argument");
-  const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(total, 256), 148 * 16));
-  wpack_multi_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const PackJob*>(table_dev), n_jobs, total);
-  count_launch(1);
-  MSIG_CHECK_LAUNCH();
+int msig_wpack_multi(const void* table_dev, int32_t n_jobs, int64_t total, int64_t total_tiles, void* stream) {
+  MSIG_REQUIRE(table_dev && n_jobs > 0 && total >= 0 && total_tiles >= 0 && total + total_tiles > 0,
+               "msig_wpack_multi: bad argument");
+  if (total > 0) {
+    const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(total, 256), 148 * 16));
+    wpack_multi_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const PackJob*>(table_dev), n_jobs, total);
+    count_launch(1);
+    MSIG_CHECK_LAUNCH();
+  }
+  if (total_tiles > 0) {
+    const int blocks = static_cast<int>(std::min<int64_t>(total_tiles, 148 * 8));
+    wpack_multi_tiled_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const PackJob*>(table_dev), n_jobs, total_tiles);
+    count_launch(1);
+    MSIG_CHECK_LAUNCH();
+  }
   return MSIG_OK;
 }
 

@@ -60,8 +60,8 @@ _SIGS = {
     "msig_wpack_elems": (c_size_t, [POINTER(WpackDesc)]),
     "msig_wpack": (c_int, [POINTER(WpackDesc), _P, _P, _P]),
     "msig_wpack_table_bytes": (c_size_t, [c_int32]),
-    "msig_wpack_table_build": (c_int, [POINTER(WpackJob), c_int32, _P, POINTER(c_int64)]),
-    "msig_wpack_multi": (c_int, [_P, c_int32, c_int64, _P]),
+    "msig_wpack_table_build": (c_int, [POINTER(WpackJob), c_int32, _P, POINTER(c_int64), POINTER(c_int64)]),
+    "msig_wpack_multi": (c_int, [_P, c_int32, c_int64, c_int64, _P]),
     "msig_wpack_part_elems": (c_size_t, [POINTER(WpackDesc), c_int32]),
     "msig_wpack_part": (c_int, [POINTER(WpackDesc), c_int32, c_int32, _P, _P, _P]),
     "msig_conv2d_fwd": (c_int, [POINTER(ConvGeom), _P, _P, POINTER(Epilogue), _P, _P]),

@@ -167,13 +167,14 @@ class PackTable:
             arr[k] = L.WpackJob(d, oc, o_off, w.data_ptr(), out.data_ptr(), numel)
             self.keep.append((w, out))
         host = torch.empty(int(L.load().msig_wpack_table_bytes(n)), dtype=torch.uint8)
-        total = ctypes.c_int64(0)
-        L.call("msig_wpack_table_build", arr, n, ctypes.c_void_p(host.data_ptr()), ctypes.byref(total))
+        total, tiles = ctypes.c_int64(0), ctypes.c_int64(0)
+        L.call("msig_wpack_table_build", arr, n, ctypes.c_void_p(host.data_ptr()), ctypes.byref(total),
+               ctypes.byref(tiles))
         self.table = host.to(device)
-        self.n, self.total = n, int(total.value)
+        self.n, self.total, self.tiles = n, int(total.value), int(tiles.value)
 
     def run(self):
-        L.call("msig_wpack_multi", _p(self.table), self.n, self.total, _stream())
+        L.call("msig_wpack_multi", _p(self.table), self.n, self.total, self.tiles, _stream())
 
 
 # ------------------------------------------------------------------ convolutions

@@ -307,6 +307,45 @@ def case_adam(seed=0):
     return max(rel_err(p, ref_p.data), rel_err(ema, ema_ref), ((p - ref_p.data).abs().max() / 2e-4).item() * 2e-3), 1e-5
 
 
+def case_pack_table(seed=0):
+    """msig_wpack_multi (device-resident job table; big FWD / DGRAD_S1 packs through the shared-memory tiled
+    kernel, the rest through the generic kernel) against the same packs made one by one with msig_wpack_part:
+    bit-identical buffers, including composite packs (several sources into row ranges of one buffer)."""
+    ops.ensure_init()
+    g = torch.Generator().manual_seed(seed)
+    specs = [  # (kind, o, i, r, s, oc, n_parts)
+        (L.WPACK_FWD, 256, 256, 3, 3, 0, 1), (L.WPACK_DGRAD_S1, 256, 256, 3, 3, 0, 1),
+        (L.WPACK_FWD, 512, 256, 1, 1, 2048, 4), (L.WPACK_DGRAD_S1, 512, 256, 1, 1, 2048, 4),   # batched style Linears
+        (L.WPACK_FWD, 128, 64, 4, 4, 0, 1), (L.WPACK_DGRAD_S2, 128, 64, 4, 4, 0, 1),
+        (L.WPACK_CONVT_FWD, 128, 256, 4, 4, 0, 1), (L.WPACK_FWD, 64, 64, 3, 3, 0, 1), (L.WPACK_DGRAD_S1, 64, 64, 3, 3, 0, 1),
+        (L.WPACK_FWD, 1, 512, 4, 4, 10, 10), (L.WPACK_ROWPATCH, 64, 3, 7, 7, 0, 1), (L.WPACK_FWD, 256, 512, 1, 1, 0, 1),
+    ]
+    weights, singles = [], []
+    for kind, o, i, r, s, oc, parts in specs:
+        shape = (i, o, r, s) if kind in (L.WPACK_CONVT_FWD, L.WPACK_CONVT_DGRAD) else (o, i, r, s)
+        ws = [(torch.randn(shape, generator=g) * 0.1).to(DEV) for _ in range(parts)]
+        weights.append(ws)
+    with ops.record_packs() as jobs:
+        for (kind, o, i, r, s, oc, parts), ws in zip(specs, weights):
+            out = None
+            for p_, w in enumerate(ws):
+                out = ops.wpack(kind, w, o, i, r, s, out=out, oc=oc, o_off=p_ * o if oc else 0)
+            singles.append(out.clone())
+            out.zero_()
+    table = ops.PackTable(jobs, torch.device(DEV))
+    table.run()
+    torch.cuda.synchronize()
+    outs, seen = [], set()
+    for j in jobs:
+        if j[4].data_ptr() not in seen:
+            seen.add(j[4].data_ptr())
+            outs.append(j[4])
+    assert len(outs) == len(singles) and table.tiles > 0 and table.total > 0
+    worst = max(float((a.float() - b.float()).abs().max()) for a, b in zip(outs, singles))
+    nonzero = min(float(b.float().abs().max()) for b in singles)
+    return worst + (0.0 if nonzero > 0 else 1.0), 0.0
+
+
 def case_augment(n=6, h=200, w=320, size=64, seed=0, sampled=False):
     """msig_augment_u8 (crop + PIL-exact bilinear resize + rotation + ToTensor + Normalize, dataset.py:16-22)
     vs the numpy oracle, which tests/test_augment_oracle.py pins against Pillow / torchvision: BIT-exact."""
@@ -360,6 +399,7 @@ CASES = {
     "norm_pad_fused": case_norm_pad,
     "norm_pad_fused_256": lambda: case_norm_pad(1, 256, 256, 64, 3, 3),
     "adam": case_adam,
+    "pack_table_tiled_vs_single": case_pack_table,
     "augment_fixed_boxes_64": lambda: case_augment(6, 200, 320, 64),
     "augment_fixed_boxes_256": lambda: case_augment(6, 256, 256, 256, seed=1),
     "augment_shrink_512_to_96": lambda: case_augment(3, 512, 512, 96, seed=2),

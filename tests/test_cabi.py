@@ -77,11 +77,16 @@ def test_host_only_entry_points_run_without_gpu():
     jobs[0] = lib.WpackJob(lib.WpackDesc(lib.WPACK_FWD, 64, 64, 3, 3), 0, 0, 0x1000, 0x2000, 0)
     jobs[1] = lib.WpackJob(lib.WpackDesc(-1, 0, 0, 0, 0), 0, 0, 0x3000, 0x4000, 512)
     buf = ctypes.create_string_buffer(l.msig_wpack_table_bytes(2))
-    total = ctypes.c_int64(0)
-    assert l.msig_wpack_table_build(jobs, 2, buf, ctypes.byref(total)) == 0
-    assert total.value == 64 * 64 * 9 + 512
+    total, tiles = ctypes.c_int64(0), ctypes.c_int64(0)
+    assert l.msig_wpack_table_build(jobs, 2, buf, ctypes.byref(total), ctypes.byref(tiles)) == 0
+    # the 64x64x3x3 FWD pack (576 elements per output channel) goes through the tiled kernel, one tile per
+    # output channel; the fp32 copy stays with the generic kernel
+    assert total.value == 512 and tiles.value == 64
+    jobs[0] = lib.WpackJob(lib.WpackDesc(lib.WPACK_CONVT_FWD, 128, 256, 4, 4), 0, 0, 0x1000, 0x2000, 0)
+    assert l.msig_wpack_table_build(jobs, 2, buf, ctypes.byref(total), ctypes.byref(tiles)) == 0
+    assert total.value == 128 * 256 * 16 + 512 and tiles.value == 0
     jobs[1].src = 0                                       # null source: refused with a message
-    assert l.msig_wpack_table_build(jobs, 2, buf, ctypes.byref(total)) != 0
+    assert l.msig_wpack_table_build(jobs, 2, buf, ctypes.byref(total), ctypes.byref(tiles)) != 0
     assert b"null pointer" in l.msig_last_error()
 
 
