@@ -1158,6 +1158,20 @@ int msig_norm_bwd_from_partials(const float* partial, int32_t n, int32_t rows_pe
   return MSIG_OK;
 }
 
+int msig_norm_bwd_apply(const void* g, const void* x, const float* mean, const float* rstd, const float* scale,
+                        const float* shift, const float* coef, int32_t n, int32_t hw, int32_t c, void* dx,
+                        void* stream) {
+  MSIG_REQUIRE(g && x && mean && rstd && scale && shift && coef && dx, "msig_norm_bwd_apply: null argument");
+  MSIG_REQUIRE(norm_c_ok(c), "msig_norm_bwd_apply: channels %d unsupported", c);
+  const int ppb = pick_pix_per_block(n, hw, 2);
+  const int chunks = static_cast<int>(ceil_div(hw, ppb));
+  norm_act_bwd_kernel<false><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(g), CBF(x), mean, rstd, scale, shift, coef,
+                                                              MSIG_ACT_NONE, 0.f, hw, c, ppb, BF(dx));
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
 int msig_act_bwd(const void* dy, const void* y, int32_t act, float slope, int64_t numel, void* dz, void* stream) {
   MSIG_REQUIRE(dy && y && dz && numel % 8 == 0, "msig_act_bwd: bad argument");
   act_bwd_kernel<<<grid_for(numel / 8, 256), 256, 0, ST(stream)>>>(CBF(dy), CBF(y), act, slope, numel / 8, BF(dz));
