@@ -52,30 +52,6 @@ typedef struct msig_conv_geom {
   int32_t oh, ow;
 } msig_conv_geom;
 
-/* Fused finalize of the epilogue reductions (msig_epilogue.stats_partial): the CTA that completes the last
- * tile of an image folds that image's partial sums into the per-(image, channel) results inside the GEMM
- * kernel, so no finalize launch follows. mode 1 = InstanceNorm / AdaIN statistics (the result of
- * msig_in_stats_from_partials); mode 2 = the norm-backward coefficients (the first half of
- * msig_norm_bwd_from_partials; finish with msig_norm_bwd_apply). */
-typedef struct msig_epi_finalize {
-  int32_t mode;           /* 1 or 2 */
-  int32_t hw;             /* pixels per (image, channel) plane */
-  float eps;              /* mode 1 */
-  const float* gamma;     /* mode 1: AdaIN gamma / beta rows (NULL: plain InstanceNorm), element stride gb_stride */
-  const float* beta;
-  int64_t gb_stride;
-  float* mean;            /* [n][c]: mode 1 output, mode 2 input */
-  float* rstd;
-  float* scale;           /* mode 1 outputs: gamma*rstd, beta - mean*gamma*rstd */
-  float* shift;
-  float* coef;            /* mode 2 output [n][2][c]: mean(g), mean(g*xhat) */
-  float* dgamma;          /* mode 2, optional: (+)= sum g*xhat, sum g per (image, channel), row stride dgb_stride */
-  float* dbeta;
-  int64_t dgb_stride;
-  int32_t accumulate_dgb;
-  uint32_t* tickets;      /* [n] scratch, zero on entry; left zero */
-} msig_epi_finalize;
-
 /* Fused epilogue of every GEMM-shaped op:  y = act( aux_op( alpha*acc + bias ) ). */
 typedef struct msig_epilogue {
   const float* bias;      /* [k] fp32 or NULL */
@@ -96,7 +72,6 @@ typedef struct msig_epilogue {
   const void* stats_z;
   const float* ch_scale;  /* optional [k] fp32 per-output-channel multiplier, applied with alpha before the bias
                            * (msig_conv_narrow_fwd only: the VGG input renormalisation's 0.5/std on d(image)) */
-  const msig_epi_finalize* finalize;   /* optional, with stats_partial: finish the reductions inside the kernel */
 } msig_epilogue;
 /* rows of stats_partial PER IMAGE for an output plane oh x ow produced in `phases` (1, or 4 for the
  * k4 s2 transposed conv / stride-2 dgrad, where oh x ow is the per-phase plane = the INPUT plane). */
@@ -279,12 +254,6 @@ int msig_norm_bwd_from_partials(const float* partial, int32_t n, int32_t rows_pe
                                 const float* scale, const float* shift, int32_t hw, int32_t c, void* dx,
                                 float* dgamma, float* dbeta, int64_t dgb_stride, int accumulate_dgb,
                                 float* coef_workspace /* [n][2][c] fp32 */, void* stream);
-
-/* dx = scale*(g - coef0 - xhat*coef1) for a g that already carries act' and coefficients finalized inside the
- * producing dgrad (msig_epi_finalize mode 2): the apply half of msig_norm_bwd_from_partials. */
-int msig_norm_bwd_apply(const void* g, const void* x, const float* mean, const float* rstd, const float* scale,
-                        const float* shift, const float* coef, int32_t n, int32_t hw, int32_t c, void* dx,
-                        void* stream);
 
 /* ---- small bandwidth ops ------------------------------------------------------------------ */
 /* dz = dy * act'(y) (ReLU / LeakyReLU), bf16 */

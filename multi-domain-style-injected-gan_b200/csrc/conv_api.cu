@@ -436,30 +436,6 @@ static int fill_epilogue(FpropParams& p, const msig_epilogue* e, const OutView& 
     return set_error(MSIG_ERR_UNSUPPORTED, "epilogue ch_scale is only implemented by msig_conv_narrow_fwd");
   if (p.stat_out != nullptr && (ov.f32 || ov.sC != 1 || n_valid < 64 || p.fold_c != 0 || p.tap_is_image))
     return set_error(MSIG_ERR_UNSUPPORTED, "epilogue statistics need a bf16 NHWC output with k >= 64");
-  p.fin_mode = 0;
-  if (e && e->finalize != nullptr) {
-    const msig_epi_finalize& f = *e->finalize;
-    if (p.stat_out == nullptr) return set_error(MSIG_ERR_ARG, "epilogue finalize needs stats_partial");
-    if ((f.mode != 1 && f.mode != 2) || f.hw <= 0 || f.tickets == nullptr || f.mean == nullptr || f.rstd == nullptr)
-      return set_error(MSIG_ERR_ARG, "epilogue finalize: bad descriptor");
-    if (f.mode == 1 && (f.scale == nullptr || f.shift == nullptr || (f.gamma == nullptr) != (f.beta == nullptr)))
-      return set_error(MSIG_ERR_ARG, "epilogue finalize (statistics): scale / shift outputs, gamma and beta together");
-    if (f.mode == 2 && (f.coef == nullptr || (f.dgamma == nullptr) != (f.dbeta == nullptr) || p.stat_z == nullptr))
-      return set_error(MSIG_ERR_ARG, "epilogue finalize (backward): coef output, dgamma / dbeta together, stats_z");
-    if (n_valid != 64 && n_valid != 128 && n_valid != 256 && n_valid != 512)
-      return set_error(MSIG_ERR_UNSUPPORTED, "epilogue finalize: %d channels (64/128/256/512)", n_valid);
-    p.fin_mode = f.mode;
-    p.fin_hw = f.hw;
-    p.fin_eps = f.eps;
-    p.fin_gamma = f.gamma; p.fin_beta = f.beta; p.fin_gb_stride = f.gb_stride;
-    p.fin_mean = f.mean; p.fin_rstd = f.rstd; p.fin_scale = f.scale; p.fin_shift = f.shift;
-    p.fin_coef = f.coef; p.fin_dgamma = f.dgamma; p.fin_dbeta = f.dbeta; p.fin_dgb_stride = f.dgb_stride;
-    p.fin_accumulate = f.accumulate_dgb;
-    p.fin_tickets = f.tickets;
-    // (tiles_h / tiles_w / phases / n_blocks are set by the callers before the epilogue is filled)
-    p.fin_rows = p.tiles_h * p.tiles_w * p.phases * 4;
-    p.fin_tiles = p.tiles_h * p.tiles_w * p.phases * p.n_blocks;
-  }
   return MSIG_OK;
 }
 

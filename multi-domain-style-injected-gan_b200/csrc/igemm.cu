@@ -33,15 +33,13 @@ constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                     // bf16 elements per K block = one 128 B swizzle row
 constexpr int kABytes = kTileM * kBlockK * 2;   // 16 KiB
 
-constexpr int kFinSmemBytes = 2 * 256 * 8;     // fused finalize: cross-group reduction scratch (doubles)
-
 template <int BLOCK_N>
 struct FpropCfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
   static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : 2 * BLOCK_N;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kFinSmemBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -315,96 +313,6 @@ __device__ __forceinline__ void fprop_epilogue_tile(const FpropParams& p, int mt
   }
 }
 
-// ---- fused finalize of the epilogue reductions (FpropParams::fin_mode) -----------------------------------
-// Barrier 2 = the 8 epilogue warps (256 threads) of one CTA.
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
-
-// Folds the partial rows of image `img` (written by the epilogues of all its tiles, possibly by other CTAs)
-// into the per-(image, channel) results. Called by all 256 epilogue threads of the CTA that took the last
-// ticket of the image. Same arithmetic (double sums in row order) as epi_stats_finalize_kernel.
-__device__ __forceinline__ void epi_finalize_image(const FpropParams& p, int img, int tid, double* sm) {
-  const int c = p.n_valid, ld = p.stat_ld, rows = p.fin_rows;
-  const float* base = p.stat_out + int64_t(img) * rows * 2 * ld;
-  for (int c0 = 0; c0 < c; c0 += 256) {
-    const int cw = min(256, c - c0);                 // 64, 128 or 256 channels in this pass
-    const int groups = 256 / cw;                     // row groups working on the same channels
-    const int ch = c0 + tid % cw, grp = tid / cw;
-    double s1 = 0.0, s2 = 0.0;
-    for (int r0 = grp; r0 < rows; r0 += groups * 16) {
-      float a[16], b[16];
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {                 // 32 independent L2 loads in flight per thread
-        const int r = r0 + u * groups;
-        a[u] = b[u] = 0.f;
-        if (r < rows) {
-          a[u] = __ldcg(base + int64_t(r) * 2 * ld + ch);
-          b[u] = __ldcg(base + int64_t(r) * 2 * ld + ld + ch);
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        s1 += a[u];
-        s2 += b[u];
-      }
-    }
-    if (groups > 1) {
-      sm[tid] = s1;
-      sm[256 + tid] = s2;
-      epi_bar_sync();
-      if (grp == 0)
-        for (int g = 1; g < groups; ++g) {
-          s1 += sm[g * cw + tid];
-          s2 += sm[256 + g * cw + tid];
-        }
-    }
-    if (grp == 0) {
-      const int hw = p.fin_hw;
-      const int o = img * c + ch;
-      if (p.fin_mode == 1) {
-        const double m = s1 / hw;
-        double var = s2 / hw - m * m;
-        if (var < 0.0) var = 0.0;
-        const float r = static_cast<float>(1.0 / sqrt(var + double(p.fin_eps)));
-        const float gm = p.fin_gamma ? p.fin_gamma[img * p.fin_gb_stride + ch] : 1.f;
-        const float bt = p.fin_beta ? p.fin_beta[img * p.fin_gb_stride + ch] : 0.f;
-        p.fin_mean[o] = static_cast<float>(m);
-        p.fin_rstd[o] = r;
-        p.fin_scale[o] = gm * r;
-        p.fin_shift[o] = bt - static_cast<float>(m) * gm * r;
-      } else {
-        const double sgx = double(p.fin_rstd[o]) * (s2 - double(p.fin_mean[o]) * s1);   // sum g*xhat
-        p.fin_coef[(int64_t(img) * 2 + 0) * c + ch] = static_cast<float>(s1 / hw);
-        p.fin_coef[(int64_t(img) * 2 + 1) * c + ch] = static_cast<float>(sgx / hw);
-        if (p.fin_dgamma != nullptr) {
-          const int64_t oo = img * p.fin_dgb_stride + ch;
-          p.fin_dgamma[oo] = (p.fin_accumulate ? p.fin_dgamma[oo] : 0.f) + static_cast<float>(sgx);
-          p.fin_dbeta[oo] = (p.fin_accumulate ? p.fin_dbeta[oo] : 0.f) + static_cast<float>(s1);
-        }
-      }
-    }
-    if (groups > 1 || c0 + 256 < c) epi_bar_sync();   // scratch is re-used by the next pass
-  }
-}
-
-// Per-tile ticket of the fused finalize: called by all 256 epilogue threads after the tile's partial rows
-// are written (and its accumulator stage released). `flag` is one int of shared memory.
-__device__ __forceinline__ void epi_finalize_ticket(const FpropParams& p, int mt_full, int epi_tid, int* flag,
-                                                    double* sm) {
-  const int img = mt_full / (p.phases * p.tiles_w * p.tiles_h);
-  __threadfence();                                   // this thread's partial sums are visible device-wide
-  epi_bar_sync();
-  if (epi_tid == 0) {
-    const unsigned int t = atomicAdd(&p.fin_tickets[img], 1u);
-    *flag = (t == static_cast<unsigned int>(p.fin_tiles) - 1u) ? 1 : 0;
-  }
-  epi_bar_sync();
-  if (*flag != 0) {
-    __threadfence();
-    epi_finalize_image(p, img, epi_tid, sm);
-    if (epi_tid == 0) p.fin_tickets[img] = 0u;       // self-cleaning for the next launch
-  }
-}
-
 // 12 warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 idle, 4..11 = epilogue. The two
 // epilogue warps of a TMEM lane quadrant (warp % 4) split the accumulator columns in halves.
 constexpr int kFpropThreads = 384;
@@ -420,8 +328,6 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_kernel(const __grid_co
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  int* fin_flag = reinterpret_cast<int*>(tmem_slot + 1);
-  double* fin_sm = reinterpret_cast<double*>(smem + Cfg::kStages * Cfg::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -540,9 +446,6 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_kernel(const __grid_co
                                    c_begin, c_end, alpha);
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
-      if constexpr (BLOCK_N >= 64) {
-        if (p.fin_mode != 0) epi_finalize_ticket(p, tile / p.n_blocks, threadIdx.x - 128, fin_flag, fin_sm);
-      }
     }
   }
 
@@ -565,7 +468,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_kernel(const __grid_co
 constexpr int k2Stages = 6;
 constexpr int k2BHalfBytes = 128 * kBlockK * 2;           // 16 KiB
 constexpr int k2StageBytes = kABytes + k2BHalfBytes;      // 32 KiB
-constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256 + kFinSmemBytes;
+constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpropThreads, 1)
     fprop2_kernel(const __grid_constant__ FpropParams p) {
@@ -578,8 +481,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpropThreads, 1)
   uint64_t* tfull_bar = empty_bar + k2Stages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  int* fin_flag = reinterpret_cast<int*>(tmem_slot + 1);
-  double* fin_sm = reinterpret_cast<double*>(smem + k2Stages * k2StageBytes + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -695,7 +596,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpropThreads, 1)
       fprop_epilogue_tile<BLOCK_N>(p, mt, n_blk, tmem_base, as, aphase, tfull_bar, q, lane, c_begin, c_end, alpha);
       tc_fence_before();
       mbar_arrive_rank0(&tempty_bar[as]);
-      if (p.fin_mode != 0) epi_finalize_ticket(p, mt, threadIdx.x - 128, fin_flag, fin_sm);
     }
   }
 
@@ -1521,7 +1421,7 @@ cudaError_t launch_fprop_ring64(const FpropParams& p, int num_sms, cudaStream_t 
   const int cbs = p.ring_cb > 1 ? p.ring_cb : 1;
   if (p.strip_r < 1 || p.strip_s < 1 || p.strip_r * p.strip_s * cbs > kRingMaxTaps || p.strip_r * p.strip_s > 16 ||
       (p.strip_r + 1) * cbs > kRingSlots || (kTileM + p.strip_s - 1) * 128 > kRingSlotBytes || p.TW != kTileM ||
-      p.TH != 1 || p.phases != 1 || p.n_blocks != 1 || p.fin_mode != 0)
+      p.TH != 1 || p.phases != 1 || p.n_blocks != 1)
     return cudaErrorInvalidValue;
   const int items = p.n_img * p.tiles_w * p.ring_chunks;
   const int grid = items < num_sms ? items : num_sms;

@@ -64,26 +64,6 @@ struct FpropParams {
   float* stat_out;
   const __nv_bfloat16* stat_z;
   int32_t stat_ld;
-  // Fused finalize of those reductions (fin_mode != 0): the CTA that completes the LAST tile of an image
-  // (integer ticket per image) folds the image's partial rows into the per-(image, channel) results, so no
-  // separate finalize launch follows the GEMM. mode 1: sum v, sum v^2 -> mean / rstd / scale / shift;
-  // mode 2: sum g, sum g*z (+ mean, rstd) -> coef [n][2][c], dgamma, dbeta.
-  int32_t fin_mode;
-  int32_t fin_rows, fin_tiles, fin_hw;   // partial rows per image, tickets per image, pixels per plane
-  float fin_eps;
-  const float* fin_gamma;
-  const float* fin_beta;
-  int64_t fin_gb_stride;
-  float* fin_mean;
-  float* fin_rstd;
-  float* fin_scale;
-  float* fin_shift;
-  float* fin_coef;
-  float* fin_dgamma;
-  float* fin_dbeta;
-  int64_t fin_dgb_stride;
-  int32_t fin_accumulate;
-  unsigned int* fin_tickets;             // [n_img], zero on entry and again on exit
 };
 
 // ---- "wgrad" kernel: D[m, n] = sum_{pixels} A[pixel + tapA, m] * B[pixel + tapB, n]

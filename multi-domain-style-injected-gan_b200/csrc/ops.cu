@@ -470,18 +470,16 @@ __global__ void __launch_bounds__(1024) epi_stats_finalize_kernel(const float* _
     for (int r0 = ty; r0 < rows; r0 += 32 * 8) {
       float a[8], b[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {            // 16 independent loads in flight per thread
-        const int r = r0 + 32 * u;
-        a[u] = b[u] = 0.f;
-        if (r < rows) {
-          a[u] = __ldg(pp + int64_t(r) * 2 * ld);
-          b[u] = __ldg(pp + int64_t(r) * 2 * ld + ld);
-        }
+      for (int u = 0; u < 8; ++u) {            // 16 independent loads in flight per thread: unconditional
+        const int r = min(r0 + 32 * u, rows - 1);   // (clamped) -- guarded loads compile to one branch each
+        a[u] = __ldg(pp + int64_t(r) * 2 * ld);     // with the use right behind it, i.e. serialised
+        b[u] = __ldg(pp + int64_t(r) * 2 * ld + ld);
       }
 #pragma unroll
       for (int u = 0; u < 8; ++u) {
-        s1 += a[u];
-        s2 += b[u];
+        const bool live = r0 + 32 * u < rows;
+        s1 += live ? double(a[u]) : 0.0;
+        s2 += live ? double(b[u]) : 0.0;
       }
     }
   }
@@ -1154,20 +1152,6 @@ int msig_norm_bwd_from_partials(const float* partial, int32_t n, int32_t rows_pe
   norm_act_bwd_kernel<false><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(g), CBF(x), mean, rstd, scale, shift, coef,
                                                               MSIG_ACT_NONE, 0.f, hw, c, ppb, BF(dx));
   count_launch(2);
-  MSIG_CHECK_LAUNCH();
-  return MSIG_OK;
-}
-
-int msig_norm_bwd_apply(const void* g, const void* x, const float* mean, const float* rstd, const float* scale,
-                        const float* shift, const float* coef, int32_t n, int32_t hw, int32_t c, void* dx,
-                        void* stream) {
-  MSIG_REQUIRE(g && x && mean && rstd && scale && shift && coef && dx, "msig_norm_bwd_apply: null argument");
-  MSIG_REQUIRE(norm_c_ok(c), "msig_norm_bwd_apply: channels %d unsupported", c);
-  const int ppb = pick_pix_per_block(n, hw, 2);
-  const int chunks = static_cast<int>(ceil_div(hw, ppb));
-  norm_act_bwd_kernel<false><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(g), CBF(x), mean, rstd, scale, shift, coef,
-                                                              MSIG_ACT_NONE, 0.f, hw, c, ppb, BF(dx));
-  count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
 }

@@ -26,18 +26,11 @@ class ConvGeom(Structure):
                 ("n", "h", "w", "c", "k", "r", "s", "stride", "pad_t", "pad_l", "oh", "ow")]
 
 
-class EpiFinalize(Structure):
-    _fields_ = [("mode", c_int32), ("hw", c_int32), ("eps", c_float), ("gamma", c_void_p), ("beta", c_void_p),
-                ("gb_stride", c_int64), ("mean", c_void_p), ("rstd", c_void_p), ("scale", c_void_p),
-                ("shift", c_void_p), ("coef", c_void_p), ("dgamma", c_void_p), ("dbeta", c_void_p),
-                ("dgb_stride", c_int64), ("accumulate_dgb", c_int32), ("tickets", c_void_p)]
-
-
 class Epilogue(Structure):
     _fields_ = [("bias", c_void_p), ("aux", c_void_p), ("aux_mode", c_int32), ("act", c_int32),
                 ("alpha", c_float), ("alpha_ptr", c_void_p), ("slope", c_float),
                 ("out_layout", c_int32), ("stats_partial", c_void_p), ("stats_z", c_void_p),
-                ("ch_scale", c_void_p), ("finalize", POINTER(EpiFinalize))]
+                ("ch_scale", c_void_p)]
 
 
 class WpackDesc(Structure):
@@ -108,7 +101,6 @@ _SIGS = {
                                             c_int64, _P, _P, _P, _P, _P]),
     "msig_norm_bwd_from_partials": (c_int, [_P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, c_int32,
                                             c_int32, _P, _P, _P, c_int64, c_int, _P, _P]),
-    "msig_norm_bwd_apply": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int32, c_int32, c_int32, _P, _P]),
     "msig_act_bwd": (c_int, [_P, _P, c_int32, c_float, c_int64, _P, _P]),
     "msig_colsum_workspace": (c_size_t, [c_int64, c_int32]),
     "msig_colsum": (c_int, [_P, c_int64, c_int32, _P, c_int, _P, c_size_t, _P]),

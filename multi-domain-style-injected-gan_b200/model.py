@@ -52,12 +52,11 @@ def _conv_stats(x, wpk, g, gamma=None, beta=None, gstride=0, transposed=False):
     if not ops.epi_fusable(4 if transposed else g.r * g.s, g.c):   # short K: the epilogue would dominate
         z = ops.convT2d_fwd(x, wpk, g) if transposed else ops.conv2d_fwd(x, wpk, g)
         return z, ops.in_stats(z, gamma, beta, gstride)
-    fwd = dict(gamma=gamma, beta=beta, gb_stride=gstride)     # statistics finalized inside the conv kernel
     if transposed:
-        es = ops.epi_stats(g.n, g.h, g.w, g.k, x.device, phases=4, fwd=fwd)
+        es = ops.epi_stats(g.n, g.h, g.w, g.k, x.device, phases=4)
         z = ops.convT2d_fwd(x, wpk, g, ops.epilogue(stats=es))
     else:
-        es = ops.epi_stats(g.n, g.oh, g.ow, g.k, x.device, fwd=fwd)
+        es = ops.epi_stats(g.n, g.oh, g.ow, g.k, x.device)
         z = ops.conv2d_fwd(x, wpk, g, ops.epilogue(stats=es))
     return z, ops.in_stats_from(es, g.oh * g.ow, g.k, gamma, beta, gstride)
 
@@ -259,8 +258,7 @@ class _ResBlockFn(torch.autograd.Function):
         if wg:
             ops.conv2d_wgrad(S["ha"], dzb, g3, _grad_buf(mod.conv2.weight))
         if ops.epi_fusable(9, c):
-            es = ops.epi_stats(B, g3.h, g3.w, c, dout.device,
-                               bwd=dict(st=S["sta"], dgamma=dgb[:, 0:], dbeta=dgb[:, c:], dgb_stride=2 * c2))
+            es = ops.epi_stats(B, g3.h, g3.w, c, dout.device)
             dh = ops.conv2d_dgrad(dzb, P["w1_d"], g3,
                                   ops.epilogue(aux=S["ha"], aux_mode=AUX_RELU_MASK, stats=es, stats_z=S["za"]))
             dza = ops.norm_bwd_from(es, dh, S["za"], S["sta"], dgamma=dgb[:, 0:], dbeta=dgb[:, c:], dgb_stride=2 * c2)
@@ -497,7 +495,7 @@ class _GeneratorFn(torch.autograd.Function):
         # over pixels in its epilogue, so the norm backward that follows needs no reduction pass.
         dev = dout.device
         gu2, gu1 = S["gu2"], S["gu1"]
-        es = ops.epi_stats(B, gu2.h, gu2.w, gu2.c, dev, bwd=dict(st=S["stu1"]))
+        es = ops.epi_stats(B, gu2.h, gu2.w, gu2.c, dev)
         dy = ops.convT2d_dgrad(dzu2, P["u2_d"], gu2,
                                ops.epilogue(aux=S["yu1"], aux_mode=AUX_RELU_MASK, stats=es, stats_z=S["zu1"]))
         del dzu2
@@ -507,18 +505,13 @@ class _GeneratorFn(torch.autograd.Function):
         _trace(mod, "dzu1", dzu1)
         if wg:
             ops.convT2d_wgrad(S["x_res"], dzu1, gu1, _grad_buf(dec[k].weight))
-        nl = 2 * k
-        dgb = torch.zeros((B, nl * 512), dtype=F32, device=dout.device)     # (dgamma | dbeta) of every AdaIN site
-
-        def bwd_of(block, j):       # fused-finalize target: AdaIN j (0 / 1) of residual block `block`
-            l = 2 * block + j
-            return dict(st=S["res"][block][2 if j == 0 else 5], dgamma=dgb[:, l * 512:], dbeta=dgb[:, l * 512 + 256:],
-                        dgb_stride=nl * 512)
-        es = ops.epi_stats(B, gu1.h, gu1.w, gu1.c, dev, bwd=bwd_of(k - 1, 1)) if k else None
+        es = ops.epi_stats(B, gu1.h, gu1.w, gu1.c, dev) if k else None
         dy = ops.convT2d_dgrad(dzu1, P["u1_d"], gu1,
                                ops.epilogue(stats=es, stats_z=S["res"][k - 1][4]) if k else None)
         del dzu1
         # ---- residual blocks, reversed
+        nl = 2 * k
+        dgb = torch.zeros((B, nl * 512), dtype=F32, device=dout.device)
         _trace(mod, "dgb", dgb)
         _trace(mod, "dx_res", dy)
         g3 = S["g3"]
@@ -530,7 +523,7 @@ class _GeneratorFn(torch.autograd.Function):
                                     dgb_stride=nl * 512)
             if wg:
                 ops.conv2d_wgrad(ha, dzb, g3, _grad_buf(blk.conv2.weight))
-            es = ops.epi_stats(B, h4, w4, 256, dev, bwd=bwd_of(i, 0))
+            es = ops.epi_stats(B, h4, w4, 256, dev)
             dh = ops.conv2d_dgrad(dzb, P[f"r{i}1_d"], g3,
                                   ops.epilogue(aux=ha, aux_mode=AUX_RELU_MASK, stats=es, stats_z=za))
             dza = ops.norm_bwd_from(es, dh, za, sta, dgamma=dgb[:, l * 512:], dbeta=dgb[:, l * 512 + 256:],
@@ -539,7 +532,7 @@ class _GeneratorFn(torch.autograd.Function):
             if wg:
                 ops.conv2d_wgrad(x_in, dza, g3, _grad_buf(blk.conv1.weight))
             # + the skip connection's gradient; for i > 0 also the reductions of block i-1's second AdaIN
-            es = ops.epi_stats(B, h4, w4, 256, dev, bwd=bwd_of(i - 1, 1)) if i > 0 else None
+            es = ops.epi_stats(B, h4, w4, 256, dev) if i > 0 else None
             dy = ops.conv2d_dgrad(dza, P[f"r{i}0_d"], g3,
                                   ops.epilogue(aux=dy, aux_mode=AUX_ADD, stats=es,
                                                stats_z=S["res"][i - 1][4] if i > 0 else None))
@@ -554,7 +547,7 @@ class _GeneratorFn(torch.autograd.Function):
         if wg:
             ops.conv2d_wgrad(S["y1"], dz2, S["g2"], _grad_buf(enc[6].weight))
         g2, g1 = S["g2"], S["g1"]
-        es = ops.epi_stats(B, g2.oh, g2.ow, g2.c, dev, phases=4, bwd=dict(st=S["st1"]))
+        es = ops.epi_stats(B, g2.oh, g2.ow, g2.c, dev, phases=4)
         dy = ops.conv2d_dgrad(dz2, P["e2_d"], g2,
                               ops.epilogue(aux=S["y1"], aux_mode=AUX_RELU_MASK, stats=es, stats_z=S["z1"]))
         del dz2
@@ -866,7 +859,7 @@ class _DiscriminatorFn(torch.autograd.Function):
             if wg:
                 ops.conv2d_wgrad(y_in, dz, g, _grad_buf(convs[j].weight))
             if j > 1:
-                es = ops.epi_stats(B, g.oh, g.ow, g.c, dev, phases=4, bwd=dict(st=S["layers"][j - 2][3]))
+                es = ops.epi_stats(B, g.oh, g.ow, g.c, dev, phases=4)
                 dy = ops.conv2d_dgrad(dz, P[f"c{j}_d"], g,
                                       ops.epilogue(aux=y_in, aux_mode=AUX_LRELU_MASK, stats=es,
                                                    stats_z=S["layers"][j - 2][2]))

@@ -74,12 +74,9 @@ def epilogue(bias=None, aux=None, aux_mode=AUX_NONE, act=ACT_NONE, alpha=1.0, al
              slope=0.2, out_layout=OUT_BF16_NHWC, stats=None, stats_z=None, ch_scale=None):
     """`stats`: an EpiStats buffer that receives the per-(image, channel) partial sums of the stored
     output (sum v, sum v*v, or sum v*z when `stats_z` is given) from the GEMM epilogue."""
-    e = Epilogue(_p(bias), _p(aux), aux_mode if aux is not None else AUX_NONE, act, alpha,
-                 _p(alpha_ptr), slope, out_layout, _p(None if stats is None else stats.buf), _p(stats_z),
-                 _p(ch_scale), None)
-    if stats is not None and stats.fin is not None:
-        e.finalize = ctypes.pointer(stats.fin)       # (the EpiStats object keeps the descriptor alive)
-    return e
+    return Epilogue(_p(bias), _p(aux), aux_mode if aux is not None else AUX_NONE, act, alpha,
+                    _p(alpha_ptr), slope, out_layout, _p(None if stats is None else stats.buf), _p(stats_z),
+                    _p(ch_scale))
 
 
 # The epilogue-fused reductions cost ~900 cycles per 64 accumulator columns per tile; they are hidden
@@ -92,62 +89,19 @@ def epi_fusable(taps, c):
     return taps * c // 64 >= EPI_STATS_MIN_KBLOCKS
 
 
-# The reductions' finalize step runs inside the GEMM kernel (msig_epi_finalize: the CTA that completes an
-# image's last tile folds its partial rows), so no finalize launch follows. MSIG_EPI_FINALIZE=0 keeps the
-# separate finalize kernels (msig_in_stats_from_partials / msig_norm_bwd_from_partials).
-EPI_FINALIZE_FUSED = __import__('os').environ.get('MSIG_EPI_FINALIZE', '1') != '0'
-_tickets = {}
-
-
-def _ticket_buf(device, n):
-    """Zero-initialised per-image ticket counters of the fused finalize (the kernels leave them zero)."""
-    key = (device, torch.cuda.current_stream().cuda_stream)
-    t = _tickets.get(key)
-    if t is None or t.numel() < n:
-        t = torch.zeros(max(int(n), 1024), dtype=torch.int32, device=device)
-        _tickets[key] = t
-    return t
-
-
 class EpiStats:
-    """Partial-sum buffer of the epilogue-fused reductions: [n * rows_per_img][2][ld] fp32, plus (when the
-    finalize is fused into the producing kernel) its descriptor and results: `st` (forward statistics) or
-    `coef` (norm-backward coefficients)."""
-    __slots__ = ("buf", "n", "rows", "ld", "fin", "st", "coef", "_keep")
+    """Partial-sum buffer of the epilogue-fused reductions: [n * rows_per_img][2][ld] fp32."""
+    __slots__ = ("buf", "n", "rows", "ld")
 
     def __init__(self, n, rows_per_img, k, device):
         self.n, self.rows, self.ld = n, rows_per_img, (k + 63) // 64 * 64
         self.buf = torch.empty((n * rows_per_img, 2, self.ld), dtype=F32, device=device)
-        self.fin = self.st = self.coef = self._keep = None
 
 
-def epi_stats(n, oh, ow, k, device, phases=1, fwd=None, bwd=None):
+def epi_stats(n, oh, ow, k, device, phases=1):
     """Buffer for an [n, oh, ow, k] conv output (phases=4: transposed conv / stride-2 dgrad, oh x ow
-    = the per-phase plane).
-    fwd = dict(gamma, beta, gb_stride[, eps]): the producing conv also finalizes the InstanceNorm / AdaIN
-          statistics into `es.st` (NormStats).
-    bwd = dict(st, dgamma, dbeta, dgb_stride[, accumulate]): the producing dgrad also finalizes the norm-backward
-          coefficients of the layer whose statistics are `st` into `es.coef` (and dgamma / dbeta)."""
-    es = EpiStats(n, int(L.load().msig_epilogue_stats_rows(oh, ow, phases)), k, device)
-    if not EPI_FINALIZE_FUSED or k not in (64, 128, 256, 512):
-        return es
-    hw = oh * ow * phases
-    if fwd is not None:
-        st = NormStats(n, k, device)
-        gamma, beta = fwd.get("gamma"), fwd.get("beta")
-        es.fin = L.EpiFinalize(1, hw, float(fwd.get("eps", 1e-5)), _p(gamma).value, _p(beta).value,
-                               int(fwd.get("gb_stride", 0)), _p(st.mean).value, _p(st.rstd).value, _p(st.scale).value,
-                               _p(st.shift).value, None, None, None, 0, 0, _p(_ticket_buf(device, n)).value)
-        es.st, es._keep = st, (gamma, beta)
-    elif bwd is not None:
-        st = bwd["st"]
-        dgamma, dbeta = bwd.get("dgamma"), bwd.get("dbeta")
-        es.coef = torch.empty((n, 2, k), dtype=F32, device=device)
-        es.fin = L.EpiFinalize(2, hw, 0.0, None, None, 0, _p(st.mean).value, _p(st.rstd).value, None, None,
-                               _p(es.coef).value, _p(dgamma).value, _p(dbeta).value, int(bwd.get("dgb_stride", 0)),
-                               int(bool(bwd.get("accumulate", False))), _p(_ticket_buf(device, n)).value)
-        es.st, es._keep = st, (dgamma, dbeta)
-    return es
+    = the per-phase plane)."""
+    return EpiStats(n, int(L.load().msig_epilogue_stats_rows(oh, ow, phases)), k, device)
 
 
 def epi_stats_rows(n, hw, k, device):
@@ -423,10 +377,7 @@ def in_stats(x, gamma=None, beta=None, gb_stride=0, eps=1e-5):
 
 
 def in_stats_from(es, hw, c, gamma=None, beta=None, gb_stride=0, eps=1e-5):
-    """InstanceNorm / AdaIN statistics from epilogue partial sums (no pass over the activation). A no-op when
-    the producing conv already finalized them (epi_stats(fwd=...))."""
-    if es.fin is not None and es.fin.mode == 1:
-        return es.st
+    """InstanceNorm / AdaIN statistics from epilogue partial sums (no pass over the activation)."""
     st = NormStats(es.n, c, es.buf.device)
     L.call("msig_in_stats_from_partials", _p(es.buf), es.n, es.rows, es.ld, hw, c, eps, _p(gamma), _p(beta),
            gb_stride, _p(st.mean), _p(st.rstd), _p(st.scale), _p(st.shift), _stream())
@@ -439,12 +390,6 @@ def norm_bwd_from(es, g, x, st, dgamma=None, dbeta=None, dgb_stride=0, accumulat
     n, h, w, c = x.shape
     if out is None:
         out = torch.empty_like(x)
-    if es.fin is not None and es.fin.mode == 2:      # coefficients (and dgamma / dbeta) came out of the dgrad kernel
-        if es.st is not st:
-            raise RuntimeError("norm_bwd_from: the fused finalize was set up for another layer's statistics")
-        L.call("msig_norm_bwd_apply", _p(g), _p(x), _p(st.mean), _p(st.rstd), _p(st.scale), _p(st.shift),
-               _p(es.coef), n, h * w, c, _p(out), _stream())
-        return out
     coef = torch.empty((n, 2, c), dtype=F32, device=x.device)
     L.call("msig_norm_bwd_from_partials", _p(es.buf), n, es.rows, es.ld, _p(g), _p(x), _p(st.mean), _p(st.rstd),
            _p(st.scale), _p(st.shift), h * w, c, _p(out), _p(dgamma), _p(dbeta), dgb_stride, int(accumulate_dgb),
