@@ -192,6 +192,13 @@ size_t msig_patch_wgrad_workspace(int64_t rows, int32_t m, int32_t ncols);
  * workspace, then one msig_wgrad_unpack per master tensor. */
 int msig_gemm_tn_partial(int64_t rows, const void* a_rows_m, int32_t m, const void* b_rows_n, int32_t ncols,
                          void* workspace, size_t workspace_bytes, int32_t* splits_out, void* stream);
+/* ... or ONE launch for `layers` equally shaped Linear layers [out_features][in_features] (+ bias) whose
+ * outputs are consecutive column blocks of the batched GEMM: dW_l += sum of the split partials, db_l += column
+ * sums of the fp32 output gradient dy [rows][ld]; wgrad_ptrs / bgrad_ptrs are DEVICE arrays of `layers`
+ * fp32 pointers (the layers' own gradient tensors). */
+int msig_multi_linear_grads(const float* partial, int32_t splits, int64_t split_stride, const float* dy,
+                            int64_t rows, int64_t ld, int32_t layers, int32_t out_features, int32_t in_features,
+                            const void* wgrad_ptrs, const void* bgrad_ptrs, void* stream);
 int msig_wgrad_unpack(const msig_wpack_desc* d, int32_t oc, int32_t o_off, const float* partial,
                       int32_t splits, int64_t split_stride, float* dw, int accumulate, void* stream);
 size_t msig_wpack_part_elems(const msig_wpack_desc* d, int32_t oc);
@@ -326,9 +333,10 @@ int msig_gram_l1(const float* ga, const float* gb, int32_t dim, float* loss, int
                  void* workspace, size_t workspace_bytes,
                  void* stream);   /* accumulate=1: loss += (sum over the five taps, losses.py:84-89) */
 /* df = alpha * (*gscale) * ssym * F (+ aux): gradient of the style term w.r.t. the generated
- * features; alpha = 1 / (dim^2 * n*c*h*w) supplied by the caller. */
+ * features; alpha = 1 / (dim^2 * n*c*h*w) supplied by the caller. relu_mask = 1: df is additionally
+ * multiplied by (F > 0) -- F is the output of a ReLU (losses.py:23-35), whose backward is thereby fused. */
 int msig_gram_bwd(const void* f, const void* ssym, int32_t n, int32_t h, int32_t w, int32_t c,
-                  float alpha, const float* gscale, const void* aux, void* df, void* stream);
+                  float alpha, const float* gscale, const void* aux, int relu_mask, void* df, void* stream);
 /* column sums of an fp32 [rows][c] matrix (bias gradients of the fp32 heads / style Linear) */
 int msig_colsum_f32(const float* x, int64_t rows, int32_t c, int64_t ld, float* out, int accumulate,
                     void* stream);   /* ld: elements between rows */

@@ -1171,6 +1171,53 @@ int msig_wgrad_unpack(const msig_wpack_desc* d, int32_t oc, int32_t o_off, const
   return launch_wgrad_reduce(pg, partial, splits, split_stride, dw, accumulate, static_cast<cudaStream_t>(stream));
 }
 
+// Weight AND bias gradients of `layers` Linear layers that were evaluated as one batched GEMM (the 16 AdaIN
+// style Linears of a generator, model.py:18,28; the per-domain 1x1 heads of the style encoder, model.py:84),
+// in ONE launch: dW_l[o][i] += sum_splits partial[split][(l*O + o)][i] and db_l[o] += sum_rows dy[row][l*O + o],
+// scattered to the layers' own gradient tensors through device-resident pointer tables. Replaces one
+// msig_wgrad_unpack + one msig_colsum_f32 per layer (2 x 16 launches per generator backward).
+__global__ void __launch_bounds__(256) multi_linear_grads_kernel(const float* __restrict__ partial, int splits,
+                                                                 int64_t split_stride, const float* __restrict__ dy,
+                                                                 int64_t rows, int64_t ld, int layers, int O, int I,
+                                                                 float* const* __restrict__ wgrads,
+                                                                 float* const* __restrict__ bgrads) {
+  const int64_t per_layer = int64_t(O) * I;
+  const int64_t n_w = per_layer * layers, n_b = int64_t(O) * layers;
+  for (int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; q < n_w + n_b;
+       q += int64_t(gridDim.x) * blockDim.x) {
+    if (q < n_w) {
+      const int l = static_cast<int>(q / per_layer);
+      float acc = 0.f;
+      for (int s = 0; s < splits; ++s) acc += partial[s * split_stride + q];
+      float* d = wgrads[l] + (q - l * per_layer);
+      *d += acc;
+    } else {
+      const int64_t c = q - n_w;                       // column l*O + o of dy
+      const int l = static_cast<int>(c / O);
+      float acc = 0.f;
+      for (int64_t r = 0; r < rows; ++r) acc += dy[r * ld + c];
+      float* d = bgrads[l] + (c - int64_t(l) * O);
+      *d += acc;
+    }
+  }
+}
+
+int msig_multi_linear_grads(const float* partial, int32_t splits, int64_t split_stride, const float* dy,
+                            int64_t rows, int64_t ld, int32_t layers, int32_t out_features, int32_t in_features,
+                            const void* wgrad_ptrs, const void* bgrad_ptrs, void* stream) {
+  MSIG_REQUIRE(partial && dy && wgrad_ptrs && bgrad_ptrs && splits >= 1 && layers >= 1 && out_features >= 1 &&
+                   in_features >= 1 && rows >= 1,
+               "msig_multi_linear_grads: bad argument");
+  const int64_t total = int64_t(layers) * out_features * (int64_t(in_features) + 1);
+  const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(total, 256), 148 * 16));
+  multi_linear_grads_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      partial, splits, split_stride, dy, rows, ld, layers, out_features, in_features,
+      reinterpret_cast<float* const*>(wgrad_ptrs), reinterpret_cast<float* const*>(bgrad_ptrs));
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
 int msig_patch_wgrad_part(const msig_wpack_desc* d, int32_t oc, int32_t o_off, int64_t rows,
                           const void* a_rows_m, int32_t m, const void* b_rows_n, int32_t ncols, float* dw,
                           int accumulate, void* workspace, size_t workspace_bytes, void* stream) {
@@ -1256,7 +1303,7 @@ int msig_gram_fwd(const void* f, int32_t n, int32_t h, int32_t w, int32_t c, flo
 
 // df[b, p, c] = alpha * sum_{b', c'} ssym[(b,c)][(b',c')] * f[b', p, c']   (+ aux)
 int msig_gram_bwd(const void* f, const void* ssym, int32_t n, int32_t h, int32_t w, int32_t c, float alpha,
-                  const float* gscale, const void* aux, void* df, void* stream) {
+                  const float* gscale, const void* aux, int relu_mask, void* df, void* stream) {
   MSIG_REQUIRE(f && ssym && df, "msig_gram_bwd: null argument");
   MSIG_REQUIRE(context_ready(), "msig_init() has not been called");
   MSIG_REQUIRE(c % 64 == 0, "msig_gram_bwd: channels (%d) must be a multiple of 64", c);
@@ -1289,6 +1336,10 @@ int msig_gram_bwd(const void* f, const void* ssym, int32_t n, int32_t h, int32_t
   e.out_layout = MSIG_OUT_BF16_NHWC;
   const OutView ov = make_out_view(df, MSIG_OUT_BF16_NHWC, h, w, c);
   if ((rc = fill_epilogue(p, &e, ov, c)) != MSIG_OK) return rc;
+  if (relu_mask) {            // df *= (f > 0): the ReLU backward of the tapped feature map, fused
+    p.stat_z = reinterpret_cast<const __nv_bfloat16*>(f);
+    p.z_mask = 1;
+  }
   cudaError_t ce = launch_fprop(p, block_n, sm_count(), static_cast<cudaStream_t>(stream));
   if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "gram bwd launch: %s", cudaGetErrorString(ce));
   return MSIG_OK;

@@ -162,6 +162,15 @@ __device__ __forceinline__ void fprop_epilogue_chunk(const FpropParams& p, const
           }
         }
       }
+      if (p.z_mask != 0) {
+        const __nv_bfloat162* mh = reinterpret_cast<const __nv_bfloat162*>(&zv[g]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 m = __bfloat1622float2(mh[j]);
+          v[2 * j] = m.x > 0.f ? v[2 * j] : 0.f;
+          v[2 * j + 1] = m.y > 0.f ? v[2 * j + 1] : 0.f;
+        }
+      }
       if (p.act != ACT_NONE) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = apply_act(v[j], p.act, p.slope);

@@ -64,6 +64,10 @@ struct FpropParams {
   float* stat_out;
   const __nv_bfloat16* stat_z;
   int32_t stat_ld;
+  // z_mask = 1 (stat_out == nullptr): the result (after alpha / bias / aux) is multiplied by (stat_z > 0): a
+  // ReLU mask taken from a SECOND operand next to an additive aux (Gram backward + the ReLU backward of the
+  // tapped feature map, losses.py:70-89 with the ReLUs of the VGG stack).
+  int32_t z_mask;
 };
 
 // ---- "wgrad" kernel: D[m, n] = sum_{pixels} A[pixel + tapA, m] * B[pixel + tapB, n]

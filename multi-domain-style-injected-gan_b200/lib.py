@@ -108,6 +108,8 @@ _SIGS = {
     "msig_nchw_chansum_workspace": (c_size_t, [c_int32, c_int32, c_int64]),
     "msig_nchw_chansum": (c_int, [_P, c_int32, c_int32, c_int64, c_int64, _P, c_int, _P, c_size_t, _P]),
     "msig_gemm_tn_partial": (c_int, [c_int64, _P, c_int32, _P, c_int32, _P, c_size_t, POINTER(c_int32), _P]),
+    "msig_multi_linear_grads": (c_int, [_P, c_int32, c_int64, _P, c_int64, c_int64, c_int32, c_int32, c_int32, _P, _P,
+                                        _P]),
     "msig_wgrad_unpack": (c_int, [POINTER(WpackDesc), c_int32, c_int32, _P, c_int32, c_int64, _P, c_int, _P]),
     "msig_maxpool2_fwd": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
     "msig_maxpool2_bwd": (c_int, [_P, _P, _P, c_int32, c_int32, c_int32, c_int32, _P, _P]),
@@ -131,7 +133,7 @@ _SIGS = {
     "msig_gram_fwd": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, _P, _P, c_size_t, _P]),
     "msig_gram_l1_workspace": (c_size_t, [c_int32]),
     "msig_gram_l1": (c_int, [_P, _P, c_int32, _P, c_int, _P, _P, c_size_t, _P]),
-    "msig_gram_bwd": (c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P, _P, _P]),
+    "msig_gram_bwd": (c_int, [_P, _P, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P, c_int, _P, _P]),
     "msig_augment_workspace": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "msig_augment_u8": (c_int, [_P, c_int32, c_int32, c_int32, _P, _P, c_int32, _P, _P, c_size_t, _P]),
     "msig_sumsq": (c_int, [_P, c_int64, _P, c_int, _P, c_size_t, _P]),

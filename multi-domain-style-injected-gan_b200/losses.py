@@ -169,23 +169,20 @@ class _VGGLossFn(torch.autograd.Function):
             return 1.0 / (float(dim) * dim * n * c * h * w)
 
         f1, f2, f3, f4, f5 = fg
-        d5 = ops.gram_bwd(f5, ssyms[4], alpha(f5), g_style)
-        dz5 = ops.act_bwd(d5, f5, ACT_RELU)
+        # each Gram backward adds the gradient that arrived through the conv / pool path (aux) and applies the
+        # ReLU backward of its tap in the same epilogue (relu_mask): no separate act_bwd pass
+        dz5 = ops.gram_bwd(f5, ssyms[4], alpha(f5), g_style, relu_mask=True)
         dp4 = ops.conv2d_dgrad(dz5, P["w4_d"], g[4])
         d4 = ops.maxpool2_bwd(dp4, f4)
         d4 = ops.l1_loss_bf16_bwd(f4, fc4, g_content, aux=d4)
-        d4 = ops.gram_bwd(f4, ssyms[3], alpha(f4), g_style, aux=d4)
-        dz4 = ops.act_bwd(d4, f4, ACT_RELU)
+        dz4 = ops.gram_bwd(f4, ssyms[3], alpha(f4), g_style, aux=d4, relu_mask=True)
         d3 = ops.conv2d_dgrad(dz4, P["w3_d"], g[3])
-        d3 = ops.gram_bwd(f3, ssyms[2], alpha(f3), g_style, aux=d3)
-        dz3 = ops.act_bwd(d3, f3, ACT_RELU)
+        dz3 = ops.gram_bwd(f3, ssyms[2], alpha(f3), g_style, aux=d3, relu_mask=True)
         dp2 = ops.conv2d_dgrad(dz3, P["w2_d"], g[2])
         d2 = ops.maxpool2_bwd(dp2, f2)
-        d2 = ops.gram_bwd(f2, ssyms[1], alpha(f2), g_style, aux=d2)
-        dz2 = ops.act_bwd(d2, f2, ACT_RELU)
+        dz2 = ops.gram_bwd(f2, ssyms[1], alpha(f2), g_style, aux=d2, relu_mask=True)
         d1 = ops.conv2d_dgrad(dz2, P["w1_d"], g[1])
-        d1 = ops.gram_bwd(f1, ssyms[0], alpha(f1), g_style, aux=d1)
-        dz1 = ops.act_bwd(d1, f1, ACT_RELU)
+        dz1 = ops.gram_bwd(f1, ssyms[0], alpha(f1), g_style, aux=d1, relu_mask=True)
         # image gradient of conv 1_1: 3x3 conv of dz1 with the flipped filter (row-fold kernel, fp32 NCHW out),
         # times the renormalisation's per-channel scale (epilogue ch_scale)
         B, H, W, _ = f1.shape

@@ -197,10 +197,9 @@ def _style_linears_backward(dgb, B, bs, nl, c2, sd, sb, lin_d, adains, wg, want_
                                 ops.epilogue(out_layout=OUT_F32_NHWC)).view(rows, sd).view(style_shape)
     if wg:
         ws, splits = ops.gemm_tn_partial(rows, dgbb, nl * c2, sb, sd)
-        for l, ada in enumerate(adains):
-            ops.wgrad_unpack(WPACK_FWD, c2, sd, 1, 1, ws, splits, nl * c2 * sd,
-                             _grad_buf(ada.style_modulation.weight), partial_offset=l * c2 * sd)
-            ops.colsum_f32(dgb, rows, c2, _grad_buf(ada.style_modulation.bias), ld=nl * c2, offset=l * c2)
+        ops.multi_linear_grads(ws, splits, nl * c2 * sd, dgb, rows, nl * c2, nl, c2, sd,
+                               [_grad_buf(a.style_modulation.weight) for a in adains],
+                               [_grad_buf(a.style_modulation.bias) for a in adains])
     return dstyle
 
 
@@ -697,10 +696,9 @@ class _StyleEncoderFn(torch.autograd.Function):
         dallb = ops.to_bf16(dall)
         # heads: dW_k = dall[:, k]^T pooled, db_k = colsum(dall[:, k])
         ws, splits = ops.gemm_tn_partial(B, dallb, nd * sd, S["pooled"], 512)
-        for kx, br in enumerate(mod.domain_branches):
-            ops.wgrad_unpack(WPACK_FWD, sd, 512, 1, 1, ws, splits, nd * sd * 512, _grad_buf(br[0].weight),
-                             partial_offset=kx * sd * 512)
-            ops.colsum_f32(dall, B, sd, _grad_buf(br[0].bias), ld=nd * sd, offset=kx * sd)
+        ops.multi_linear_grads(ws, splits, nd * sd * 512, dall, B, nd * sd, nd, sd, 512,
+                               [_grad_buf(br[0].weight) for br in mod.domain_branches],
+                               [_grad_buf(br[0].bias) for br in mod.domain_branches])
         dpool = ops.conv2d_fwd(dallb.view(1, 1, B, nd * sd), P["h_d"], ops.gemm_geom(B, nd * sd, 512)).view(B, 512)
         h, w = S["hw"]
         dy = ops.avgpool_bwd(dpool, h, w)

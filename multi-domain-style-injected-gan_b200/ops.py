@@ -478,6 +478,32 @@ def gemm_tn_partial(rows, a, m, b, ncols):
     return ws, splits.value
 
 
+_ptr_tables = {}
+
+
+def grad_ptr_table(tensors):
+    """Device-resident array of the tensors' data pointers (cached by the pointer values: gradient views of
+    a flat buffer keep their addresses across steps; entries are never evicted because captured CUDA graphs
+    hold the table's address). Built with a host->device copy, so the first use must be outside a CUDA-graph
+    capture -- the trainer's first step is always eager."""
+    ptrs = tuple(t.data_ptr() for t in tensors)
+    key = (tensors[0].device, ptrs)
+    tab = _ptr_tables.get(key)
+    if tab is None:
+        if torch.cuda.is_current_stream_capturing():
+            raise RuntimeError("gradient pointer table requested for the first time during a CUDA-graph capture")
+        tab = torch.tensor(ptrs, dtype=torch.int64).to(tensors[0].device)
+        _ptr_tables[key] = tab
+    return tab
+
+
+def multi_linear_grads(ws, splits, split_stride, dy, rows, ld, layers, out_features, in_features, wgrads, bgrads):
+    """dW / db of `layers` Linear layers evaluated as one batched GEMM, accumulated into their own gradient
+    tensors in one launch (see msig_multi_linear_grads)."""
+    L.call("msig_multi_linear_grads", _p(ws), splits, split_stride, _p(dy), rows, ld, layers, out_features,
+           in_features, _p(grad_ptr_table(wgrads)), _p(grad_ptr_table(bgrads)), _stream())
+
+
 def wgrad_unpack(kind, o, i, r, s, ws, splits, split_stride, dw, accumulate=True, oc=0, o_off=0,
                  partial_offset=0):
     d = WpackDesc(kind, o, i, r, s)
@@ -650,11 +676,12 @@ def gram_l1(ga, gb, loss=None):
     return loss, ssym
 
 
-def gram_bwd(f, ssym, alpha, gscale=None, aux=None):
+def gram_bwd(f, ssym, alpha, gscale=None, aux=None, relu_mask=False):
+    """relu_mask: also apply the backward of the ReLU that produced `f` (result *= f > 0)."""
     n, h, w, c = f.shape
     df = torch.empty_like(f)
-    L.call("msig_gram_bwd", _p(f), _p(ssym), n, h, w, c, float(alpha), _p(gscale), _p(aux), _p(df),
-           _stream())
+    L.call("msig_gram_bwd", _p(f), _p(ssym), n, h, w, c, float(alpha), _p(gscale), _p(aux), int(relu_mask),
+           _p(df), _stream())
     return df
 
 

@@ -242,8 +242,14 @@ def case_gram_bwd(n, c, h, w, seed=0):
     alpha = 1.0 / dim
     ref = (alpha * (s @ feat)).reshape(n, c, h, w)
     df = ops.gram_bwd(f, s.to(torch.bfloat16).contiguous(), alpha)
+    # + an additive upstream gradient (aux) and the fused ReLU backward of the tapped feature map
+    aux = _bf(_rand((n, h, w, c), seed + 7)).to(DEV)
+    gs = torch.tensor(0.37, device=DEV)
+    dfm = ops.gram_bwd(f, s.to(torch.bfloat16).contiguous(), alpha, gscale=gs, aux=aux, relu_mask=True)
+    refm = (0.37 * ref + nchw(aux).float()) * (nchw(f).float() > 0)
     torch.cuda.synchronize()
-    return rel_err(nchw(df), ref), 1e-2
+    masked_exact = float((nchw(dfm).float()[nchw(f).float() <= 0]).abs().max()) == 0.0
+    return max(rel_err(nchw(df), ref), rel_err(nchw(dfm), refm), 0.0 if masked_exact else 1.0), 1e-2
 
 
 CASES = {
@@ -291,5 +297,6 @@ CASES = {
     "gram_64": lambda: case_gram(2, 64, 64, 64),
     "gram_256_b3": lambda: case_gram(3, 256, 16, 16),
     "gram_bwd_128": lambda: case_gram_bwd(2, 128, 32, 32),
+    "gram_bwd_64_fold": lambda: case_gram_bwd(4, 64, 32, 64, seed=3),
 }
 
