@@ -252,7 +252,82 @@ def case_gram_bwd(n, c, h, w, seed=0):
     return max(rel_err(nchw(df), ref), rel_err(nchw(dfm), refm), 0.0 if masked_exact else 1.0), 1e-2
 
 
+def case_repeatability(reps=12, seed=0):
+    """Race / missing-fence detector (compute-sanitizer is closed on this pool): every tcgen05 kernel family is
+    launched `reps` times on the same operands, with an L2-flushing write in between, and every output must be
+    BIT-identical to the first launch. The kernels are deterministic by construction (fixed tile -> CTA
+    assignment, fixed split-K order), so any difference is a shared-memory / TMEM / mbarrier hazard."""
+    ops.ensure_init()
+    flush = torch.empty(160 << 20, dtype=torch.uint8, device=DEV)
+    x256 = _bf(_rand((4, 256, 64, 64), seed)).to(DEV)
+    z256 = _bf(_rand((4, 256, 64, 64), seed + 1)).to(DEV)
+    w256 = _rand((256, 256, 3, 3), seed + 2, 0.02).to(DEV)
+    wf, wd = ops.wpack(L.WPACK_FWD, w256, 256, 256, 3, 3), ops.wpack(L.WPACK_DGRAD_S1, w256, 256, 256, 3, 3)
+    g256 = ops.conv_geom(4, 64, 64, 256, 256, 3, 3, 1, 1, 1, 64, 64)
+    x64 = _bf(_rand((2, 64, 96, 256), seed + 3)).to(DEV)
+    w64 = _rand((64, 64, 3, 3), seed + 4, 0.05).to(DEV)
+    w64f = ops.wpack(L.WPACK_FWD, w64, 64, 64, 3, 3)
+    g64 = ops.conv_geom(2, 96, 256, 64, 64, 3, 3, 1, 1, 1, 96, 256)
+    x128 = _bf(_rand((2, 128, 64, 128), seed + 5)).to(DEV)
+    wt = _rand((128, 64, 4, 4), seed + 6, 0.03).to(DEV)
+    wtf = ops.wpack(L.WPACK_CONVT_FWD, wt, 64, 128, 4, 4)
+    gt = ops.conv_geom(2, 64, 128, 128, 64, 4, 4, 2, 1, 1, 128, 256)
+    w128 = _rand((128, 64, 4, 4), seed + 7, 0.03).to(DEV)
+    w128f = ops.wpack(L.WPACK_FWD, w128, 128, 64, 4, 4)
+    x64b = _bf(_rand((2, 64, 64, 64), seed + 8)).to(DEV)
+    g128 = ops.conv_geom(2, 64, 64, 64, 128, 4, 4, 2, 1, 1, 32, 32)
+    dy128 = _bf(_rand((2, 128, 32, 32), seed + 9)).to(DEV)
+    xp = _bf(_rand((2, 64, 38, 134), seed + 10)).to(DEV)
+    wn = _rand((3, 64, 7, 7), seed + 11, 0.02).to(DEV)
+    wnf = ops.wpack(L.WPACK_ROWFOLD, wn, 3, 64, 7, 7)
+    gn = ops.conv_geom(2, 38, 134, 64, 3, 7, 7, 1, 0, 0, 32, 128)
+    nh = lambda t: t.permute(0, 2, 3, 1).contiguous()       # noqa: E731
+    x256h, z256h, x64h, x128h, x64bh, dy128h, xph = (nh(t) for t in (x256, z256, x64, x128, x64b, dy128, xp))
+
+    def fwd_stats():
+        es = ops.epi_stats(4, 64, 64, 256, torch.device(DEV))
+        y = ops.conv2d_fwd(x256h, wf, g256, ops.epilogue(stats=es))
+        st = ops.in_stats_from(es, 4096, 256)
+        return [y, st.buf]
+
+    def dgrad_mask_red():
+        es = ops.epi_stats(4, 64, 64, 256, torch.device(DEV))
+        dy = ops.conv2d_dgrad(x256h, wd, g256, ops.epilogue(aux=z256h, aux_mode=L.AUX_RELU_MASK, stats=es, stats_z=z256h))
+        return [dy, es.buf]
+
+    def wgrad_pair():
+        dw = torch.zeros((256, 256, 3, 3), device=DEV)
+        ops.conv2d_wgrad(x256h, z256h, g256, dw, accumulate=False)
+        return [dw]
+
+    def wgrad_taps():
+        dw = torch.zeros((128, 64, 4, 4), device=DEV)
+        ops.conv2d_wgrad(x64bh, dy128h, g128, dw, accumulate=False)
+        return [dw]
+    fams = {
+        "fprop2+stats": fwd_stats, "fprop2 dgrad+mask+reductions": dgrad_mask_red,
+        "ring64": lambda: [ops.conv2d_fwd(x64h, w64f, g64)],
+        "phased convT (ring)": lambda: [ops.convT2d_fwd(x128h, wtf, gt)],
+        "fprop<128> s2": lambda: [ops.conv2d_fwd(x64bh, w128f, g128)],
+        "rowfold": lambda: [ops.conv_narrow_fwd(xph, wnf, gn)],
+        "wgrad2 (pair)": wgrad_pair, "wgrad<256> grouped taps": wgrad_taps,
+        "gram": lambda: [ops.gram_fwd(x64bh)],
+    }
+    bad = []
+    for name, fn in fams.items():
+        first = [t.clone() for t in fn()]
+        for _ in range(reps - 1):
+            flush.fill_(1)
+            again = fn()
+            torch.cuda.synchronize()
+            if not all(torch.equal(a, b) for a, b in zip(first, again)):
+                bad.append(name)
+                break
+    return float(len(bad)), 0.0
+
+
 CASES = {
+    "repeatability_all_kernel_families": case_repeatability,
     # forward convs: the shapes of the reference networks (SURVEY appendix A), reduced batch
     "fwd_3x3_256_64": lambda: case_conv_fwd(2, 256, 64, 64, 256, 3, 1, 1),
     "fwd_3x3_64_32_relu": lambda: case_conv_fwd(1, 64, 32, 32, 64, 3, 1, 1, act=L.ACT_RELU),
