@@ -517,7 +517,7 @@ __global__ void __launch_bounds__(1024) epi_stats_finalize_kernel(const float* _
 }
 
 // y = act(x*scale + shift) (+ residual); PADOUT: y is the reflect-padded buffer [n][H+2p][W+2p][c]
-template <bool PADOUT = false>
+template <bool PADOUT = false, int U = kUnroll>
 __global__ void __launch_bounds__(256) norm_act_fwd_kernel(
     const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
     const __nv_bfloat16* __restrict__ res, int act, float slope, int hw, int c, int pix_per_block,
@@ -535,10 +535,10 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(
     sh[j] = shift[img * c + tx * 8 + j];
   }
   const int64_t base = int64_t(img) * hw * c + tx * 8;
-  for (int p = p0 + ty; p < p1; p += kUnroll * lanes) {
-    uint4 xv[kUnroll], rv[kUnroll];
+  for (int p = p0 + ty; p < p1; p += U * lanes) {
+    uint4 xv[U], rv[U];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int pp = p + u * lanes;
       if (pp < p1) {
         xv[u] = ldg_stream(x + base + int64_t(pp) * c);
@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(
       }
     }
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int pp = p + u * lanes;
       if (pp < p1) {
         float f[8];
@@ -582,8 +582,8 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(
 }
 
 // dx = scale * (g - c1 - xhat*c2),  g = dy*act'(x*scale+shift); FOLD: dy is read through the reflect fold
-template <bool FOLD = false>
-__global__ void __launch_bounds__(256, FOLD ? 2 : 1) norm_act_bwd_kernel(
+template <bool FOLD = false, int U = kUnroll>
+__global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
     const float* __restrict__ shift, const float* __restrict__ coef, int act, float slope, int hw, int c,
@@ -609,10 +609,10 @@ __global__ void __launch_bounds__(256, FOLD ? 2 : 1) norm_act_bwd_kernel(
   const int64_t base = int64_t(img) * hw * c + tx * 8;
   const int h_blk = FOLD ? p0 / pg.W : 0;
   const int64_t fold_base = FOLD ? fold_direct_offset(pg, img, h_blk, -h_blk * pg.W, c, tx) : 0;
-  for (int p = p0 + ty; p < p1; p += kUnroll * lanes) {
-    uint4 xv[kUnroll], dv[kUnroll];
+  for (int p = p0 + ty; p < p1; p += U * lanes) {
+    uint4 xv[U], dv[U];
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int pp = p + u * lanes;
       if (pp < p1) {
         xv[u] = ldg_stream(x + base + int64_t(pp) * c);
@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(256, FOLD ? 2 : 1) norm_act_bwd_kernel(
       }
     }
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u) {
+    for (int u = 0; u < U; ++u) {
       const int pp = p + u * lanes;
       if (pp < p1) {
         float xf[8], df[8];
@@ -939,7 +939,31 @@ using namespace msig;
 #define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
 #define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 
+// Independent 16-byte loads in flight per operand per thread in the plain norm apply kernels (test hook:
+// msig_debug_set_norm_unroll; 4 = the original setting).
+static int g_norm_unroll = 6;
+
+template <typename... Args>
+static void launch_norm_fwd(dim3 grid, cudaStream_t st, Args... args) {
+  if (g_norm_unroll == 8) norm_act_fwd_kernel<false, 8><<<grid, 256, 0, st>>>(args...);
+  else if (g_norm_unroll == 6) norm_act_fwd_kernel<false, 6><<<grid, 256, 0, st>>>(args...);
+  else norm_act_fwd_kernel<false, 4><<<grid, 256, 0, st>>>(args...);
+}
+template <typename... Args>
+static void launch_norm_bwd(dim3 grid, cudaStream_t st, Args... args) {
+  if (g_norm_unroll == 8) norm_act_bwd_kernel<false, 8><<<grid, 256, 0, st>>>(args...);
+  else if (g_norm_unroll == 6) norm_act_bwd_kernel<false, 6><<<grid, 256, 0, st>>>(args...);
+  else norm_act_bwd_kernel<false, 4><<<grid, 256, 0, st>>>(args...);
+}
+
+
 extern "C" {
+
+int msig_debug_set_norm_unroll(int u) {
+  if (u != 4 && u != 6 && u != 8) return msig::set_error(MSIG_ERR_ARG, "msig_debug_set_norm_unroll: 4, 6 or 8");
+  g_norm_unroll = u;
+  return MSIG_OK;
+}
 
 int msig_patch_gather(const msig_patch_geom* g, const float* src, const float* scale, const float* shift,
                       void* patches, void* stream) {
@@ -1028,10 +1052,10 @@ int msig_norm_act_fwd(const void* x, const float* scale, const float* shift, con
                       float slope, int32_t n, int32_t hw, int32_t c, void* y, void* stream) {
   MSIG_REQUIRE(x && scale && shift && y, "msig_norm_act_fwd: null argument");
   MSIG_REQUIRE(norm_c_ok(c), "msig_norm_act_fwd: channels %d unsupported", c);
-  const int ppb = pick_pix_per_block(n, hw, 3);
+  const int ppb = pick_pix_per_block(n, hw, g_norm_unroll == 4 ? 3 : 2);   // resident blocks per SM (registers)
   const int chunks = static_cast<int>(ceil_div(hw, ppb));
-  norm_act_fwd_kernel<false><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), scale, shift, CBF(residual), act, slope,
-                                                              hw, c, ppb, BF(y));
+  launch_norm_fwd(dim3(chunks, n), ST(stream), CBF(x), scale, shift, CBF(residual), act, slope, hw, c, ppb, BF(y),
+                  PadGeom{0, 0, 0, 0.f});
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -1058,8 +1082,8 @@ int msig_norm_act_bwd(const void* dy, const void* x, const float* mean, const fl
   nc_reduce_kernel<1><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), CBF(dy), mean, rstd, scale, shift, act,
                                                               slope, hw, c, ppb, partial, tickets, fin);
   MSIG_CHECK_LAUNCH();
-  norm_act_bwd_kernel<false><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(dy), CBF(x), mean, rstd, scale, shift, coef,
-                                                              act, slope, hw, c, ppb, BF(dx));
+  launch_norm_bwd(dim3(chunks, n), ST(stream), CBF(dy), CBF(x), mean, rstd, scale, shift,
+                  static_cast<const float*>(coef), act, slope, hw, c, ppb, BF(dx), PadGeom{0, 0, 0, 0.f});
   count_launch(2);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -1149,8 +1173,9 @@ int msig_norm_bwd_from_partials(const float* partial, int32_t n, int32_t rows_pe
   MSIG_CHECK_LAUNCH();
   const int ppb = pick_pix_per_block(n, hw, 2);
   const int chunks = static_cast<int>(ceil_div(hw, ppb));
-  norm_act_bwd_kernel<false><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(g), CBF(x), mean, rstd, scale, shift, coef,
-                                                              MSIG_ACT_NONE, 0.f, hw, c, ppb, BF(dx));
+  launch_norm_bwd(dim3(chunks, n), ST(stream), CBF(g), CBF(x), mean, rstd, scale, shift,
+                  static_cast<const float*>(coef), static_cast<int>(MSIG_ACT_NONE), 0.f, hw, c, ppb, BF(dx),
+                  PadGeom{0, 0, 0, 0.f});
   count_launch(2);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
