@@ -484,10 +484,12 @@ static int run_conv(const void* in, int n, int h, int w, int c, int k, int R, in
   p.n_blocks = k_pad / block_n;
   p.taps = R * S;
   p.cblocks = c / 64;
+  p.m2 = fprop_uses_m2(p, block_n) ? 1 : 0;            // two m-tiles per CTA: the A box is twice as tall
+  const int boxH = p.m2 ? 2 * p.TH : p.TH;
   int rc;
   if (stride == 1) {
     ActView v{in, c, w, h, n, c, int64_t(w) * c, int64_t(h) * w * c};
-    if ((rc = make_act_map(&p.tmA[0], v, p.TW, p.TH)) != MSIG_OK) return rc;
+    if ((rc = make_act_map(&p.tmA[0], v, p.TW, boxH)) != MSIG_OK) return rc;
     for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
     for (int r = 0; r < R; ++r)
       for (int s = 0; s < S; ++s) p.tap[r * S + s] = Tap{int8_t(r - pad_t), int8_t(s - pad_l), 0, 0};
@@ -497,7 +499,7 @@ static int run_conv(const void* in, int n, int h, int w, int c, int k, int R, in
       for (int pw = 0; pw < 2; ++pw) {
         const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(in) + (int64_t(ph) * w + pw) * c;
         ActView v{base, c, w / 2, h / 2, n, int64_t(2) * c, int64_t(2) * w * c, int64_t(h) * w * c};
-        if ((rc = make_act_map(&p.tmA[ph * 2 + pw], v, p.TW, p.TH)) != MSIG_OK) return rc;
+        if ((rc = make_act_map(&p.tmA[ph * 2 + pw], v, p.TW, boxH)) != MSIG_OK) return rc;
       }
     for (int r = 0; r < R; ++r)
       for (int s = 0; s < S; ++s) {
@@ -548,9 +550,10 @@ static int run_phased(const void* in, int n, int h, int w, int c, int k, const v
   p.cblocks = c / 64;
   p.phases = 4;
   p.b_row_per_phase = k_pad;
+  p.m2 = fprop_uses_m2(p, block_n) ? 1 : 0;
   int rc;
   ActView v{in, c, w, h, n, c, int64_t(w) * c, int64_t(h) * w * c};
-  if ((rc = make_act_map(&p.tmA[0], v, p.TW, p.TH)) != MSIG_OK) return rc;
+  if ((rc = make_act_map(&p.tmA[0], v, p.TW, p.m2 ? 2 * p.TH : p.TH)) != MSIG_OK) return rc;
   for (int i = 1; i < 4; ++i) p.tmA[i] = p.tmA[0];
   const int64_t OW2 = 2 * int64_t(w);
   for (int py = 0; py < 2; ++py)
@@ -654,6 +657,11 @@ int msig_debug_set_ring_mode(int on) {
 }
 
 // Test hook: CTA-pair (cta_group::2) kernel for 256-wide tiles on (default) / off.
+int msig_debug_set_m2_mode(int on) {
+  set_m2_mode(on != 0);
+  return MSIG_OK;
+}
+
 int msig_debug_set_pair_mode(int on) {
   set_pair_mode(on != 0);
   return MSIG_OK;

@@ -7,6 +7,7 @@
 //                           fused per-(image, channel) reductions, 256-bit loads and stores.
 //   fprop2_kernel           the same GEMM for 256-wide tiles on a CTA pair (cluster of 2, cta_group::2):
 //                           each CTA stages half of the weight tile (the 1-CTA kernel sits on the L2 roof).
+//   fprop_m2_kernel         the 128-wide tiles with TWO m-tiles per CTA sharing one weight tile (same roof).
 //   fprop_ring64_kernel     64-channel stride-1 layers: resident filter, strip ring shared by output rows,
 //                           horizontal taps as row-shifted descriptors (also the row-patch 7x7 convs and
 //                           the phases of the 128 -> 64 transposed conv / stride-2 dgrad).
@@ -463,6 +464,164 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_kernel(const __grid_co
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::kTmemCols);
+  }
+}
+
+// ------------------------------------------------------------------------------------ M = 256 per CTA, N = 128
+// fprop_m2_kernel: the BLOCK_N = 128 implicit GEMM with TWO 128-pixel m-tiles per CTA (vertically adjacent
+// logical tiles 2*th and 2*th+1 of one image / phase), both multiplied by the SAME weight tile: per 64-deep
+// K block the CTA stages 32 KiB of activations (one TMA box {64, TW, 2*TH}) + 16 KiB of weights for 4.2 MF
+// instead of 16 + 16 KiB for 2.1 MF. The 1-CTA N = 128 kernel sits on the L2 -> shared-memory roof (the
+// phased 256 -> 128 transposed conv and the stride-2 dgrad of 128 -> 256 measured 610 TF/s); this halves the
+// weight traffic per FLOP, the ratio the 256-wide tiles have. Two accumulators (128 columns each) per TMEM
+// stage, double buffered: 512 columns. Logical m-tile indices (and so the statistics rows) are unchanged.
+constexpr int kM2Stages = 4;
+constexpr int kM2ABytes = 2 * kABytes;                       // 32 KiB
+constexpr int kM2BBytes = 128 * kBlockK * 2;                 // 16 KiB
+constexpr int kM2StageBytes = kM2ABytes + kM2BBytes;         // 48 KiB
+constexpr int kM2SmemBytes = kM2Stages * kM2StageBytes + 1024 + 256;
+
+__global__ void __launch_bounds__(kFpropThreads, 1) fprop_m2_kernel(const __grid_constant__ FpropParams p) {
+  constexpr int BLOCK_N = 128;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kM2Stages * kM2StageBytes);
+  uint64_t* empty_bar = full_bar + kM2Stages;
+  uint64_t* tfull_bar = empty_bar + kM2Stages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < 4; ++i) prefetch_tmap(&p.tmA[i]);
+    prefetch_tmap(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < kM2Stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // work item = (image, pair of tile rows, tile column, phase, n block); phase and n block vary fastest
+  const int th_pairs = p.tiles_h / 2;
+  const int total = p.n_img * th_pairs * p.tiles_w * p.phases * p.n_blocks;
+  const int kblocks = p.taps * p.cblocks;
+  auto decode = [&](int item, int& n_blk, int& ph, int& tw, int& th2, int& img) {
+    n_blk = item % p.n_blocks;
+    int r = item / p.n_blocks;
+    ph = r % p.phases;
+    r /= p.phases;
+    tw = r % p.tiles_w;
+    r /= p.tiles_w;
+    th2 = r % th_pairs;
+    img = r / th_pairs;
+  };
+
+  if (warp == 0) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+      int n_blk, ph, tw, th2, img;
+      decode(item, n_blk, ph, tw, th2, img);
+      const int oh0 = 2 * th2 * p.TH, ow0 = tw * p.TW;
+      const int n_off = n_blk * BLOCK_N + ph * p.b_row_per_phase;
+      int kb = 0;
+      for (int t = 0; t < p.taps; ++t) {
+        const Tap tp = p.tap[ph * p.taps + t];
+        for (int cb = 0; cb < p.cblocks; ++cb, ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (elect_one()) {
+            uint8_t* sa = smem + stage * kM2StageBytes;
+            mbar_expect_tx(&full_bar[stage], kM2StageBytes);
+            tma_load_4d(sa, &p.tmA[tp.map], &full_bar[stage], cb * kBlockK, ow0 + tp.dw, oh0 + tp.dh, img);
+            tma_load_2d(sa + kM2ABytes, &p.tmB, &full_bar[stage], kb * kBlockK, n_off);
+          }
+          __syncwarp();
+          if (++stage == kM2Stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      mbar_wait(&tempty_bar[as], aphase ^ 1u);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * 2 * BLOCK_N;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t sa = smem_u32(smem + stage * kM2StageBytes);
+          const uint64_t da0 = make_smem_desc(sa, 0, 1024);
+          const uint64_t da1 = make_smem_desc(sa + kABytes, 0, 1024);
+          const uint64_t db = make_smem_desc(sa + kM2ABytes, 0, 1024);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+            umma_bf16(d_tmem, da0 + 2 * k, db + 2 * k, idesc, acc);
+            umma_bf16(d_tmem + BLOCK_N, da1 + 2 * k, db + 2 * k, idesc, acc);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == kblocks - 1) umma_commit(&tfull_bar[as]);
+        }
+        __syncwarp();
+        if (++stage == kM2Stages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int c_begin = half * (BLOCK_N / 2), c_end = c_begin + BLOCK_N / 2;
+    const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
+    int it = 0;
+    for (int item = blockIdx.x; item < total; item += gridDim.x, ++it) {
+      const int as = it & 1;
+      const uint32_t aphase = (it >> 1) & 1;
+      int n_blk, ph, tw, th2, img;
+      decode(item, n_blk, ph, tw, th2, img);
+#pragma unroll 1
+      for (int sub = 0; sub < 2; ++sub) {
+        // logical m-tile index in the 1-CTA kernel's order (phase fastest, then tile column, tile row, image)
+        const int mt_full = ((img * p.tiles_h + 2 * th2 + sub) * p.tiles_w + tw) * p.phases + ph;
+        // fprop_epilogue_tile addresses TMEM at base + as * BLOCK_N: fold this kernel's stage / sub-tile layout in
+        const uint32_t base = tmem_base + as * BLOCK_N + sub * BLOCK_N;
+        fprop_epilogue_tile<BLOCK_N>(p, mt_full, n_blk, base, as, aphase, tfull_bar, q, lane, c_begin, c_end, alpha);
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -1385,6 +1544,33 @@ static cudaError_t launch_fprop2(const FpropParams& p, int num_sms, cudaStream_t
 
 // CTA pairs for the wide tiles whenever both CTAs of a pair can share the weight tile. (The weight
 // tensor map of a paired launch must have a 128-row box: each CTA loads half of the 256 rows.)
+static bool g_m2_mode = true;
+void set_m2_mode(bool on) { g_m2_mode = on; }
+
+// Two m-tiles per CTA for the N = 128 layers whenever tile rows pair up inside an image and there is at
+// least one full wave of (pair, n block) work items.
+bool fprop_uses_m2(const FpropParams& p, int block_n) {
+  if (!g_m2_mode || block_n != 128 || p.tap_is_image || p.fold_c != 0 || p.b_row_per_image != 0) return false;
+  if ((p.tiles_h % 2) != 0 || 2 * p.TH > 256 || p.taps * p.cblocks < 4) return false;
+  const int64_t items = int64_t(p.n_img) * (p.tiles_h / 2) * p.tiles_w * p.phases * p.n_blocks;
+  return items >= 148;
+}
+
+static cudaError_t launch_fprop_m2(const FpropParams& p, int num_sms, cudaStream_t stream) {
+  static uint64_t attr_devs = 0;
+  if (attr_needed(attr_devs)) {
+    cudaError_t e = cudaFuncSetAttribute(fprop_m2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kM2SmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_done(attr_devs);
+  }
+  const int total = p.n_img * (p.tiles_h / 2) * p.tiles_w * p.phases * p.n_blocks;
+  const int grid = total < num_sms ? total : num_sms;
+  if (grid <= 0) return cudaSuccess;
+  fprop_m2_kernel<<<grid, kFpropThreads, kM2SmemBytes, stream>>>(p);
+  count_launch(1);
+  return cudaGetLastError();
+}
+
 bool fprop_uses_pairs(const FpropParams& p, int block_n) {
   return g_pair_mode && block_n == 256 && p.phases == 1 && p.b_row_per_image == 0 &&
          ((p.n_img * p.tiles_h * p.tiles_w) % 2) == 0 && p.taps * p.cblocks >= 4;
@@ -1392,6 +1578,7 @@ bool fprop_uses_pairs(const FpropParams& p, int block_n) {
 
 cudaError_t launch_fprop(const FpropParams& p, int block_n, int num_sms, cudaStream_t stream) {
   if (fprop_uses_pairs(p, block_n)) return launch_fprop2(p, num_sms, stream);
+  if (p.m2 != 0) return block_n == 128 ? launch_fprop_m2(p, num_sms, stream) : cudaErrorInvalidValue;
   switch (block_n) {
     case 16: return launch_fprop_t<16>(p, num_sms, stream);
     case 64: return launch_fprop_t<64>(p, num_sms, stream);

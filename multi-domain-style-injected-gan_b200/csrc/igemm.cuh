@@ -68,6 +68,9 @@ struct FpropParams {
   // ReLU mask taken from a SECOND operand next to an additive aux (Gram backward + the ReLU backward of the
   // tapped feature map, losses.py:70-89 with the ReLUs of the VGG stack).
   int32_t z_mask;
+  // m2 = 1: run on fprop_m2_kernel -- one CTA computes TWO vertically adjacent 128-pixel m-tiles (2*th, 2*th+1)
+  // against the same weight tile; tmA maps then carry a {64, TW, 2*TH} box (see fprop_uses_m2).
+  int32_t m2;
 };
 
 // ---- "wgrad" kernel: D[m, n] = sum_{pixels} A[pixel + tapA, m] * B[pixel + tapB, n]
@@ -126,6 +129,8 @@ cudaError_t launch_rowfold(const RowfoldParams& p, int num_sms, cudaStream_t str
 cudaError_t launch_fprop_ring64(const FpropParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_wgrad(const WgradParams& p, int block_n, cudaStream_t stream);
 bool fprop_uses_pairs(const FpropParams& p, int block_n);
+bool fprop_uses_m2(const FpropParams& p, int block_n);   // call with tiles / phases / taps / n_blocks already set
+void set_m2_mode(bool on);
 void set_pair_mode(bool on);   // test hook: CTA-pair (cta_group::2) kernel for 256-wide tiles on/off
 int igemm_kernel_launches();  // launches issued since process start (bench: gpu_launches)
 
