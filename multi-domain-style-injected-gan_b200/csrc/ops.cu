@@ -939,31 +939,19 @@ using namespace msig;
 #define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
 #define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 
-// Independent 16-byte loads in flight per operand per thread in the plain norm apply kernels (test hook:
-// msig_debug_set_norm_unroll; 4 = the original setting).
-static int g_norm_unroll = 6;
-
+// 16-byte loads in flight per operand per thread in the plain norm apply kernels: measured in situ at
+// [32,64,64,256] (profiles/probe/norm_unroll_r2.txt): forward 4 (27.7 us; 6: 30.7), backward 6 (46.1 us; 4: 50.0).
 template <typename... Args>
 static void launch_norm_fwd(dim3 grid, cudaStream_t st, Args... args) {
-  if (g_norm_unroll == 8) norm_act_fwd_kernel<false, 8><<<grid, 256, 0, st>>>(args...);
-  else if (g_norm_unroll == 6) norm_act_fwd_kernel<false, 6><<<grid, 256, 0, st>>>(args...);
-  else norm_act_fwd_kernel<false, 4><<<grid, 256, 0, st>>>(args...);
+  norm_act_fwd_kernel<false, 4><<<grid, 256, 0, st>>>(args...);
 }
 template <typename... Args>
 static void launch_norm_bwd(dim3 grid, cudaStream_t st, Args... args) {
-  if (g_norm_unroll == 8) norm_act_bwd_kernel<false, 8><<<grid, 256, 0, st>>>(args...);
-  else if (g_norm_unroll == 6) norm_act_bwd_kernel<false, 6><<<grid, 256, 0, st>>>(args...);
-  else norm_act_bwd_kernel<false, 4><<<grid, 256, 0, st>>>(args...);
+  norm_act_bwd_kernel<false, 6><<<grid, 256, 0, st>>>(args...);
 }
 
 
 extern "C" {
-
-int msig_debug_set_norm_unroll(int u) {
-  if (u != 4 && u != 6 && u != 8) return msig::set_error(MSIG_ERR_ARG, "msig_debug_set_norm_unroll: 4, 6 or 8");
-  g_norm_unroll = u;
-  return MSIG_OK;
-}
 
 int msig_patch_gather(const msig_patch_geom* g, const float* src, const float* scale, const float* shift,
                       void* patches, void* stream) {
@@ -1052,7 +1040,7 @@ int msig_norm_act_fwd(const void* x, const float* scale, const float* shift, con
                       float slope, int32_t n, int32_t hw, int32_t c, void* y, void* stream) {
   MSIG_REQUIRE(x && scale && shift && y, "msig_norm_act_fwd: null argument");
   MSIG_REQUIRE(norm_c_ok(c), "msig_norm_act_fwd: channels %d unsupported", c);
-  const int ppb = pick_pix_per_block(n, hw, g_norm_unroll == 4 ? 3 : 2);   // resident blocks per SM (registers)
+  const int ppb = pick_pix_per_block(n, hw, 3);
   const int chunks = static_cast<int>(ceil_div(hw, ppb));
   launch_norm_fwd(dim3(chunks, n), ST(stream), CBF(x), scale, shift, CBF(residual), act, slope, hw, c, ppb, BF(y),
                   PadGeom{0, 0, 0, 0.f});

@@ -49,7 +49,17 @@ def ensure_init(device=None):
         device = torch.cuda.current_device()
     elif isinstance(device, torch.device):
         device = device.index if device.index is not None else torch.cuda.current_device()
-    return L.init(int(device))
+    lib = L.init(int(device))
+    global _debug_env_applied
+    if not _debug_env_applied:          # A/B switches for measurements (defaults: everything on)
+        _debug_env_applied = True
+        import os
+        if os.environ.get("MSIG_M2", "1") == "0":
+            L.call("msig_debug_set_m2_mode", 0)
+    return lib
+
+
+_debug_env_applied = False
 
 
 _ws_cache = {}
