@@ -699,6 +699,37 @@ def case_epoch_change_and_checkpoint(b=2, s=64, nd=3, seed=0):
     return res, ok
 
 
+def case_second_device(b=2, s=64, nd=3, seed=0):
+    """A trainer built with device='cuda:1' while cuda:0 is the current device (the reference only ever does
+    `.to(device)`, main.py:30-35): every launch, stream, workspace and CUDA graph must follow the tensors'
+    device. Same losses as the same trainer on cuda:0; the current device is left untouched."""
+    from msig_b200 import trainer as T
+    if torch.cuda.device_count() < 2:
+        return {"skipped": "one GPU"}, True
+    vgg_sd = O.seeded_vgg_state()
+    batch = O.synthetic_batch(b, s, nd)
+    torch.cuda.set_device(0)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        torch.manual_seed(seed)
+        tr = T.MultiDomainStyleCycleGAN(torch.device(dev), 200, 2e-4, 1e-4, dict(O.DEFAULT_LOSS_WEIGHTS), nd, vgg_state=vgg_sd)
+        losses = []
+        for _ in range(3):                                   # eager, capture, replay
+            out = tr.train_step(batch, 0)
+            losses.append({k: float(v) for k, v in out.items()})
+            assert all(v.device == torch.device(dev) for v in out.values())
+        torch.cuda.synchronize(torch.device(dev))
+        outs.append(losses)
+        assert torch.cuda.current_device() == 0
+    res, ok = {}, True
+    for it in range(3):
+        for k, v in outs[0][it].items():
+            e = abs(outs[1][it][k] - v) / max(abs(v), 1e-6)
+            res[f"s{it}.{k}"] = e
+            ok = ok and e <= 1e-6                            # deterministic kernels: identical on both devices
+    return res, ok
+
+
 CASES = {
     "adain_module": case_adain_module,
     "resblock_256": lambda: case_resblock(2, 256, 32),
@@ -713,10 +744,12 @@ CASES = {
     "vgg_loss": lambda: case_vgg(2, 64),
     "train_step_b2_s64": lambda: case_train_step(2, 64, 3, 2),
     "train_step_b1_s256_nd10": lambda: case_train_step(1, 256, 10, 1),
+    "train_step_b1_s512_nd10": lambda: case_train_step(1, 512, 10, 1),
     "gd_512_b1": case_gd_512,
     "translate_vs_oracle": case_translate_vs_oracle,
     "train_step_graph_vs_eager": case_graph_vs_eager,
     "translate_graph_vs_eager": case_translate_graph,
     "translate_batches_pipeline": case_translate_batches,
     "epoch_change_and_checkpoint": case_epoch_change_and_checkpoint,
+    "trainer_on_second_device": case_second_device,
 }
