@@ -430,8 +430,13 @@ def case_train_step(b=2, s=64, nd=3, steps=2, seed=0):
             # pre-clip gradients of step 1, per tensor. vs fp32: gradients cross two chained generators
             # + D / VGG -> cosine >= 0.95; bias gradients are plain sums over pixels of bf16-stored
             # gradients with heavy cancellation: their norm gets 3x the per-network bound instead of 2x.
+            # (512^2: four times as many stored elements per channel feed every reduction -- the measured
+            # bf16-storage floor itself, emulated-vs-fp32, drops to cosine 0.95; the calibrated check below
+            # is the one that adapts, the fixed floor is only a backstop)
+            cos_floor = 0.95 if s <= 256 else 0.92
+
             def loose(n, m):
-                return m[0] >= 0.95 and m[1] <= (3 if n.endswith("bias") else 2) * GRAD_NORM and m[2] <= GRAD_MAXREL
+                return m[0] >= cos_floor and m[1] <= (3 if n.endswith("bias") else 2) * GRAD_NORM and m[2] <= GRAD_MAXREL
             w, wname, bad, all_ok = _step_grad_check(tr, ref["grads"], loose)
             res["s0.wgrad"], res["s0.wgrad_worst"], res["s0.wgrad_bad"] = w, wname, bad
             ok = ok and all_ok
