@@ -21,5 +21,14 @@ st = ops.in_stats(x)                                  # nc_reduce_kernel<0>
 ops.norm_act_fwd(x, st, L.ACT_RELU, out=y)            # norm_act_fwd_kernel
 ops.norm_act_fwd(x, st, L.ACT_NONE, residual=res, out=y)
 ops.norm_act_bwd(dy, x, st, L.ACT_RELU, out=y)        # nc_reduce_kernel<1> + norm_act_bwd_kernel
+es = ops.epi_stats(B, h, h, c, dev)
+es.buf.zero_()
+ops.norm_bwd_from(es, dy, x, st, out=y)               # epi_stats_finalize_kernel<1> + norm_act_bwd_kernel (fused-reduction form)
+# the pad-fused pair around the generator's final conv: [B,256,256,64]
+x64 = torch.randn(B, 256, 256, 64, device=dev).to(torch.bfloat16)
+st64 = ops.in_stats(x64)
+yp = ops.norm_act_fwd_pad(x64, st64, L.ACT_RELU, 3)   # norm_act_fwd_kernel<PADOUT>
+dyp = torch.randn(B, 262, 262, 64, device=dev).to(torch.bfloat16)
+ops.norm_act_bwd_pad(dyp, x64, st64, L.ACT_RELU, 3)   # nc_reduce_kernel<1, FOLD> + norm_act_bwd_kernel<FOLD>
 torch.cuda.synchronize()
 print("ok")
