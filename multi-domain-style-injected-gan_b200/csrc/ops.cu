@@ -309,7 +309,6 @@ __device__ __forceinline__ void mirror_positions(int i, int n, int pad, int (&po
 // dy of pixel p = sum of the padded gradient over its mirror positions. The position (h+pad, w+pad) is
 // always one of them: its load is issued with the batched loads (fold_direct_offset); the mirrored
 // border copies (a few % of the pixels) are added afterwards (fold_add_mirrors).
-// (The launchers make the block's pixel range a divisor of W, so a block stays inside one image row h.)
 __device__ __forceinline__ int64_t fold_direct_offset(const PadGeom& pg, int img, int h, int w, int c, int tx) {
   const int W2 = pg.W + 2 * pg.pad, H2 = pg.H + 2 * pg.pad;
   return ((int64_t(img) * H2 + h + pg.pad) * W2 + w + pg.pad) * c + tx * 8;
@@ -358,8 +357,6 @@ __global__ void __launch_bounds__(256, FOLD ? 2 : 1) nc_reduce_kernel(
     }
   }
   const int64_t base = int64_t(img) * hw * c + tx * 8;
-  const int h_blk = FOLD ? p0 / pg.W : 0;                 // FOLD: the whole block lies in image row h_blk
-  const int64_t fold_base = FOLD ? fold_direct_offset(pg, img, h_blk, -h_blk * pg.W, c, tx) : 0;   // + p*c
   for (int p = p0 + ty; p < p1; p += kUnroll * lanes) {
     uint4 xv[kUnroll], dv[kUnroll];
 #pragma unroll
@@ -367,7 +364,15 @@ __global__ void __launch_bounds__(256, FOLD ? 2 : 1) nc_reduce_kernel(
       const int pp = p + u * lanes;
       if (pp < p1) {
         xv[u] = ldg_stream(x + base + int64_t(pp) * c);
-        if (MODE == 1) dv[u] = ldg_stream(FOLD ? dy + fold_base + int64_t(pp) * c : dy + base + int64_t(pp) * c);
+        if (MODE == 1) {
+          if constexpr (FOLD) {                          // dy lives in the reflect-padded buffer: (h, w) per pixel
+            int h, w;
+            pixel_hw(pg, pp, h, w);
+            dv[u] = ldg_stream(dy + fold_direct_offset(pg, img, h, w, c, tx));
+          } else {
+            dv[u] = ldg_stream(dy + base + int64_t(pp) * c);
+          }
+        }
       }
     }
 #pragma unroll
@@ -384,7 +389,11 @@ __global__ void __launch_bounds__(256, FOLD ? 2 : 1) nc_reduce_kernel(
         } else {
           float df[8];
           unpack8(dv[u], df);
-          if constexpr (FOLD) fold_add_mirrors(dy, img, h_blk, p + u * lanes - h_blk * pg.W, pg, c, tx, df);
+          if constexpr (FOLD) {
+            int h, w;
+            pixel_hw(pg, p + u * lanes, h, w);
+            fold_add_mirrors(dy, img, h, w, pg, c, tx, df);
+          }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float uu = xf[j] * sc[j] + sh[j];
@@ -607,8 +616,6 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(
     k2[j] = -sc[j] * (c1 - mu * rs * c2);
   }
   const int64_t base = int64_t(img) * hw * c + tx * 8;
-  const int h_blk = FOLD ? p0 / pg.W : 0;
-  const int64_t fold_base = FOLD ? fold_direct_offset(pg, img, h_blk, -h_blk * pg.W, c, tx) : 0;
   for (int p = p0 + ty; p < p1; p += U * lanes) {
     uint4 xv[U], dv[U];
 #pragma unroll
@@ -616,7 +623,13 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(
       const int pp = p + u * lanes;
       if (pp < p1) {
         xv[u] = ldg_stream(x + base + int64_t(pp) * c);
-        dv[u] = ldg_stream(FOLD ? dy + fold_base + int64_t(pp) * c : dy + base + int64_t(pp) * c);
+        if constexpr (FOLD) {
+          int h, w;
+          pixel_hw(pg, pp, h, w);
+          dv[u] = ldg_stream(dy + fold_direct_offset(pg, img, h, w, c, tx));
+        } else {
+          dv[u] = ldg_stream(dy + base + int64_t(pp) * c);
+        }
       }
     }
 #pragma unroll
@@ -626,7 +639,11 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(
         float xf[8], df[8];
         unpack8(xv[u], xf);
         unpack8(dv[u], df);
-        if constexpr (FOLD) fold_add_mirrors(dy, img, h_blk, pp - h_blk * pg.W, pg, c, tx, df);
+        if constexpr (FOLD) {
+          int h, w;
+          pixel_hw(pg, pp, h, w);
+          fold_add_mirrors(dy, img, h, w, pg, c, tx, df);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float uu = xf[j] * sc[j] + sh[j];
@@ -1077,13 +1094,28 @@ int msig_norm_act_bwd(const void* dy, const void* x, const float* mean, const fl
   return MSIG_OK;
 }
 
+// Pad-fused norm kernels: one full wave of resident blocks (2 per SM) like the plain kernels; the first version
+// gave every image row its own 256-thread block (8192 blocks of 2 loop iterations each at [32,256,256,64]) and
+// sat at 39 % (reduction) / 70 % (apply) of the HBM peak in ncu. Test hook: 0 = the one-row blocks.
+static int g_padnorm_wave = 1;
+int msig_debug_set_padnorm_mode(int wave) {
+  g_padnorm_wave = wave != 0;
+  return MSIG_OK;
+}
+static int padnorm_ppb(int n, int hw, int w) {
+  if (g_padnorm_wave) return pick_pix_per_block(n, hw, 2);
+  int ppb = std::min(pick_pix_per_block(n, hw), w);
+  while (w % ppb) --ppb;
+  return ppb;
+}
+
 int msig_norm_act_fwd_pad(const void* x, const float* scale, const float* shift, int32_t act, float slope, int32_t n,
                           int32_t h, int32_t w, int32_t c, int32_t pad, void* y_padded, void* stream) {
   MSIG_REQUIRE(x && scale && shift && y_padded, "msig_norm_act_fwd_pad: null argument");
   MSIG_REQUIRE(norm_c_ok(c) && pad >= 1 && pad < h && pad < w && int64_t(h) * w < (1 << 22),
                "msig_norm_act_fwd_pad: bad shape");
   const int hw = h * w;
-  const int ppb = pick_pix_per_block(n, hw);
+  const int ppb = padnorm_ppb(n, hw, w);
   const int chunks = static_cast<int>(ceil_div(hw, ppb));
   norm_act_fwd_kernel<true><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), scale, shift, nullptr, act, slope, hw, c,
                                                                     ppb, BF(y_padded), PadGeom{w, h, pad, 1.f / w});
@@ -1094,9 +1126,10 @@ int msig_norm_act_fwd_pad(const void* x, const float* scale, const float* shift,
 
 size_t msig_norm_act_bwd_pad_workspace(int32_t n, int32_t h, int32_t w, int32_t c) {
   const int hw = h * w;
+  // covers both block sizings (one image row per block is the finer one)
   int ppb = std::min(pick_pix_per_block(n, hw), w);
   while (w % ppb) --ppb;
-  const size_t chunks = size_t(hw / ppb);
+  const size_t chunks = std::max(size_t(hw / ppb), size_t(ceil_div(hw, pick_pix_per_block(n, hw, 2))));
   return (size_t(n) * chunks * 2 * c + size_t(n) * 2 * c + size_t(n)) * sizeof(float);
 }
 
@@ -1109,9 +1142,8 @@ int msig_norm_act_bwd_pad(const void* dy_padded, const void* x, const float* mea
   MSIG_REQUIRE(norm_c_ok(c) && pad >= 1 && pad < h && pad < w && int64_t(h) * w < (1 << 22),
                "msig_norm_act_bwd_pad: bad shape");
   const int hw = h * w;
-  int ppb = std::min(pick_pix_per_block(n, hw), w);
-  while (w % ppb) --ppb;                                   // a block never straddles two image rows
-  const int chunks = hw / ppb;
+  const int ppb = padnorm_ppb(n, hw, w);
+  const int chunks = static_cast<int>(ceil_div(hw, ppb));
   MSIG_REQUIRE(workspace_bytes >= (size_t(n) * chunks * 2 * c + size_t(n) * 2 * c + size_t(n)) * sizeof(float),
                "msig_norm_act_bwd_pad: workspace too small");
   float* partial = reinterpret_cast<float*>(workspace);
