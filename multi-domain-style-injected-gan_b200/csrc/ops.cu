@@ -1094,20 +1094,10 @@ int msig_norm_act_bwd(const void* dy, const void* x, const float* mean, const fl
   return MSIG_OK;
 }
 
-// Pad-fused norm kernels: one full wave of resident blocks (2 per SM) like the plain kernels; the first version
-// gave every image row its own 256-thread block (8192 blocks of 2 loop iterations each at [32,256,256,64]) and
-// sat at 39 % (reduction) / 70 % (apply) of the HBM peak in ncu. Test hook: 0 = the one-row blocks.
-static int g_padnorm_wave = 1;
-int msig_debug_set_padnorm_mode(int wave) {
-  g_padnorm_wave = wave != 0;
-  return MSIG_OK;
-}
-static int padnorm_ppb(int n, int hw, int w) {
-  if (g_padnorm_wave) return pick_pix_per_block(n, hw, 2);
-  int ppb = std::min(pick_pix_per_block(n, hw), w);
-  while (w % ppb) --ppb;
-  return ppb;
-}
+// Pad-fused norm kernels: one full wave of resident blocks (2 per SM) like the plain kernels. The first version
+// gave every image row its own 256-thread block (8192 blocks of 2 loop iterations each at [32,256,256,64]):
+// forward 142.9 -> 132.4 us, backward (reduce + apply) 403.2 -> 340.9 us (profiles/probe/padnorm_r2.txt).
+static int padnorm_ppb(int n, int hw) { return pick_pix_per_block(n, hw, 2); }
 
 int msig_norm_act_fwd_pad(const void* x, const float* scale, const float* shift, int32_t act, float slope, int32_t n,
                           int32_t h, int32_t w, int32_t c, int32_t pad, void* y_padded, void* stream) {
@@ -1115,7 +1105,7 @@ int msig_norm_act_fwd_pad(const void* x, const float* scale, const float* shift,
   MSIG_REQUIRE(norm_c_ok(c) && pad >= 1 && pad < h && pad < w && int64_t(h) * w < (1 << 22),
                "msig_norm_act_fwd_pad: bad shape");
   const int hw = h * w;
-  const int ppb = padnorm_ppb(n, hw, w);
+  const int ppb = padnorm_ppb(n, hw);
   const int chunks = static_cast<int>(ceil_div(hw, ppb));
   norm_act_fwd_kernel<true><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), scale, shift, nullptr, act, slope, hw, c,
                                                                     ppb, BF(y_padded), PadGeom{w, h, pad, 1.f / w});
@@ -1126,10 +1116,8 @@ int msig_norm_act_fwd_pad(const void* x, const float* scale, const float* shift,
 
 size_t msig_norm_act_bwd_pad_workspace(int32_t n, int32_t h, int32_t w, int32_t c) {
   const int hw = h * w;
-  // covers both block sizings (one image row per block is the finer one)
-  int ppb = std::min(pick_pix_per_block(n, hw), w);
-  while (w % ppb) --ppb;
-  const size_t chunks = std::max(size_t(hw / ppb), size_t(ceil_div(hw, pick_pix_per_block(n, hw, 2))));
+  (void)w;
+  const size_t chunks = size_t(ceil_div(hw, padnorm_ppb(n, hw)));
   return (size_t(n) * chunks * 2 * c + size_t(n) * 2 * c + size_t(n)) * sizeof(float);
 }
 
@@ -1142,7 +1130,7 @@ int msig_norm_act_bwd_pad(const void* dy_padded, const void* x, const float* mea
   MSIG_REQUIRE(norm_c_ok(c) && pad >= 1 && pad < h && pad < w && int64_t(h) * w < (1 << 22),
                "msig_norm_act_bwd_pad: bad shape");
   const int hw = h * w;
-  const int ppb = padnorm_ppb(n, hw, w);
+  const int ppb = padnorm_ppb(n, hw);
   const int chunks = static_cast<int>(ceil_div(hw, ppb));
   MSIG_REQUIRE(workspace_bytes >= (size_t(n) * chunks * 2 * c + size_t(n) * 2 * c + size_t(n)) * sizeof(float),
                "msig_norm_act_bwd_pad: workspace too small");

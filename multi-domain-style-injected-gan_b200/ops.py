@@ -56,8 +56,6 @@ def ensure_init(device=None):
         import os
         if os.environ.get("MSIG_M2", "1") == "0":
             L.call("msig_debug_set_m2_mode", 0)
-        if os.environ.get("MSIG_PADNORM_WAVE", "1") == "0":
-            L.call("msig_debug_set_padnorm_mode", 0)
     return lib
 
 
