@@ -38,6 +38,7 @@ int msig_version(void);
 const char* msig_last_error(void);       /* thread-local */
 int msig_sm_count(void);
 int msig_debug_set_ring_mode(int on);     /* test hook: strip-ring kernel for 64-channel stride-1 layers, default on */
+int msig_debug_set_wgrad_mode(int mask);  /* test hook: bit 0 = M-stacked row-patch weight gradients, bit 1 = tap-grouped convT ones; default 3 */
 int msig_debug_set_m2_mode(int on);       /* test hook: two m-tiles per CTA for the 128-wide conv tiles, default on */
 int msig_debug_set_pair_mode(int on);     /* test hook: CTA-pair (tcgen05 cta_group::2) kernel for 256-wide conv tiles, default on */
 long long msig_kernel_launches(void);    /* kernels launched by this library since load */

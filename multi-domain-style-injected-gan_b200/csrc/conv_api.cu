@@ -440,6 +440,9 @@ static int fill_epilogue(FpropParams& p, const msig_epilogue* e, const OutView& 
 }
 
 static int g_ring_mode = 1;    // test hook: 0 = generic per-tap kernel for the 64-channel stride-1 layers
+static int g_wgrad_mode = 3;   // test hook: bit 0 = M-stacked row-patch weight gradients, bit 1 = tap-grouped convT ones
+#define g_rowpatch_stack (g_wgrad_mode & 1)
+#define g_convt_group (g_wgrad_mode & 2)
 
 // Configure `p` (epilogue already filled, n_img / OH / OW set) for the N = 64 ring kernel.
 static void set_ring(FpropParams& p, int R, int S, int org_h, int org_w) {
@@ -620,7 +623,6 @@ static WgradPlan plan_wgrad(int M, int N, int taps, int64_t kb_total, bool upper
   // one CTA per SM is resident (192 KiB of smem): fill ONE wave as completely as possible
   int64_t splits = std::max<int64_t>(1, int64_t(sms) / base);
   splits = std::max<int64_t>(1, std::min<int64_t>(splits, ceil_div(kb_total, 4)));
-  splits = std::min<int64_t>(splits, 128);
   pl.kb_per_split = static_cast<int>(ceil_div(kb_total, splits));
   pl.splits = static_cast<int>(ceil_div(kb_total, pl.kb_per_split));
   pl.kb_total = static_cast<int>(kb_total);
@@ -653,6 +655,12 @@ int32_t msig_epilogue_stats_rows(int32_t oh, int32_t ow, int32_t phases) {
 // Test hook: ring kernel for the 64-channel stride-1 layers on (default) / off.
 int msig_debug_set_ring_mode(int on) {
   g_ring_mode = on;
+  return MSIG_OK;
+}
+
+// Test hook: weight-gradient operand plans (bit 0: M-stacked row-patch, bit 1: tap-grouped convT); default 3.
+int msig_debug_set_wgrad_mode(int mask) {
+  g_wgrad_mode = mask;
   return MSIG_OK;
 }
 
@@ -846,12 +854,33 @@ int msig_conv_rowpatch_fwd(const msig_conv_geom* g, const void* x_pad8, const vo
   return MSIG_OK;
 }
 
+// Row-patch weight gradients: groups of four filter rows are the four B boxes of one CTA. With exactly two
+// groups (R = 5..8, the 7x7 convs of the generator) the groups are STACKED in M: the second 64-row A box is the
+// `other` tile shifted up by four rows, so rows 64..127 of the same MMA accumulate filter rows 4..7 against the
+// same B boxes (sum_y o[y-4] * img[y + r] == sum_y' o[y'] * img[y' + 4 + r]); the K range grows by four rows.
+struct RowpatchWgradPlan {
+  int groups, stacked, taps, M, PW, PH, blocks_w, blocks_h;
+  int64_t kb_total;
+  WgradPlan pl;
+};
+static RowpatchWgradPlan plan_rowpatch_wgrad(const msig_conv_geom* g) {
+  RowpatchWgradPlan r;
+  pick_kblock(g->ow, r.PW, r.PH);
+  r.groups = static_cast<int>(ceil_div(g->r, 4));
+  r.stacked = (r.groups == 2 && g_rowpatch_stack) ? 1 : 0;
+  r.taps = r.stacked ? 1 : r.groups;
+  r.M = r.stacked ? 128 : 64;
+  r.blocks_w = static_cast<int>(ceil_div(g->ow, r.PW));
+  r.blocks_h = static_cast<int>(ceil_div(g->oh + (r.stacked ? 4 : 0), r.PH));
+  r.kb_total = int64_t(g->n) * r.blocks_h * r.blocks_w;
+  r.pl = plan_wgrad(r.M, 256, r.taps, r.kb_total);
+  return r;
+}
+
 size_t msig_conv_rowpatch_wgrad_workspace(const msig_conv_geom* g) {
   if (!g) return 0;
-  int PW, PH;
-  pick_kblock(g->ow, PW, PH);
-  const int64_t kb = int64_t(g->n) * ceil_div(g->oh, PH) * ceil_div(g->ow, PW);
-  return wgrad_ws_bytes(64, 256, static_cast<int>(ceil_div(g->r, 4)), kb);
+  const RowpatchWgradPlan r = plan_rowpatch_wgrad(g);
+  return size_t(r.pl.splits) * 64 * r.groups * 256 * sizeof(float);
 }
 
 // flip = 0: dw[k][c][r][s] (+)= sum_pix dy[pix, k] * patch_r[pix, (s, c)]         (k = 64 output channels of
@@ -870,27 +899,32 @@ int msig_conv_rowpatch_wgrad(const msig_conv_geom* g, const void* x_pad8, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   WgradParams p;
   memset(&p, 0, sizeof(p));
-  pick_kblock(g->ow, p.PW, p.PH);
-  p.blocks_w = static_cast<int>(ceil_div(g->ow, p.PW));
-  p.blocks_h = static_cast<int>(ceil_div(g->oh, p.PH));
+  const RowpatchWgradPlan rp = plan_rowpatch_wgrad(g);
+  const WgradPlan& pl = rp.pl;
+  p.PW = rp.PW; p.PH = rp.PH;
+  p.blocks_w = rp.blocks_w; p.blocks_h = rp.blocks_h;
   p.n_img = g->n;
-  p.taps = static_cast<int>(ceil_div(g->r, 4));         // groups of four filter rows
-  MSIG_REQUIRE(p.taps * 4 <= kMaxTaps, "rowpatch wgrad: too many filter rows");
-  const int64_t kb_total = int64_t(g->n) * p.blocks_h * p.blocks_w;
-  WgradPlan pl = plan_wgrad(64, 256, p.taps, kb_total);
-  const size_t need = size_t(pl.splits) * 64 * p.taps * 256 * sizeof(float);
+  p.taps = rp.taps;                                     // CTA taps: groups of four filter rows (stacked: both groups)
+  MSIG_REQUIRE(rp.groups * 4 <= kMaxTaps, "rowpatch wgrad: too many filter rows");
+  const size_t need = size_t(pl.splits) * 64 * rp.groups * 256 * sizeof(float);
   MSIG_REQUIRE(workspace_bytes >= need, "rowpatch wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
   p.m_blocks = pl.m_blocks; p.n_blocks = pl.n_blocks; p.splits = pl.splits;
   p.kb_per_split = pl.kb_per_split; p.kb_total = pl.kb_total;
   p.out = reinterpret_cast<float*>(workspace);
-  p.o_row = 256; p.o_tap = 64 * 256; p.o_split = int64_t(p.taps) * 64 * 256;
-  p.alpha = 1.f; p.m_valid = 64; p.n_valid = 256;
-  p.a_boxes = 1; p.b_box_tap = 1;
+  // partial layout [group][64 rows][256]: stacked rows 64..127 of the single CTA tap ARE group 1
+  p.o_row = 256; p.o_tap = int64_t(rp.M) * 256; p.o_split = int64_t(rp.groups) * 64 * 256;
+  p.alpha = 1.f; p.m_valid = rp.M; p.n_valid = 256;
+  p.a_boxes = 1; p.b_box_tap = 1; p.a_box_tap = rp.stacked;
   ActView vo{other, 64, g->ow, g->oh, g->n, 64, int64_t(g->ow) * 64, int64_t(g->oh) * g->ow * 64};
   if ((rc = make_act_map(&p.tmA[0], vo, p.PW, p.PH)) != MSIG_OK) return rc;
   if ((rc = make_act_map(&p.tmB[0], pad8_view(x_pad8, g), p.PW, p.PH)) != MSIG_OK) return rc;
   for (int i = 1; i < 4; ++i) { p.tmA[i] = p.tmA[0]; p.tmB[i] = p.tmB[0]; }
-  for (int y = 0; y < p.taps; ++y) p.tapA[y] = Tap{0, 0, 0, 0};
+  if (rp.stacked) {
+    p.tapA[0] = Tap{0, 0, 0, 0};
+    p.tapA[1] = Tap{-4, 0, 0, 0};                       // rows above / below the plane are zero-filled by TMA
+  } else {
+    for (int y = 0; y < p.taps; ++y) p.tapA[y] = Tap{0, 0, 0, 0};
+  }
   // filter rows past R read whatever lies below (or TMA zero fill); their columns are never unpacked
   for (int r = 0; r < p.taps * 4; ++r) p.tapB[r] = Tap{int8_t(r), 0, 0, 0};
   cudaError_t ce = launch_wgrad(p, pl.block_n, st);
@@ -1070,12 +1104,42 @@ int msig_conv2d_wgrad(const msig_conv_geom* g, const void* x, const void* dy, fl
   return launch_wgrad_reduce(pg, p.out, pl.splits, p.o_split, dw, accumulate, st);
 }
 
+// 64 output channels and >= 128 input channels (model.py:138, the generator's second up-sampling layer): x is
+// the 128-wide M operand and the FOUR taps of one output phase share a CTA as four 64-channel dy boxes (N = 256),
+// sum_p x[p + d] dy_ph[p] = sum_q x[q] dy_ph[q - d]: the shift moves to the dy side (TMA zero fill either way).
+static bool convT_wgrad_groups(const msig_conv_geom* g) { return g_convt_group && g->k == 64 && g->c % 128 == 0; }
+
 size_t msig_convT2d_wgrad_workspace(const msig_conv_geom* g) {
   if (!g) return 0;
   int PW, PH;
   pick_kblock(g->w, PW, PH);
   const int64_t kb = int64_t(g->n) * ceil_div(g->h, PH) * ceil_div(g->w, PW);
+  if (convT_wgrad_groups(g)) return size_t(plan_wgrad(g->c, 256, 4, kb).splits) * g->k * 16 * g->c * sizeof(float);
   return wgrad_ws_bytes(g->k, g->c, 16, kb);
+}
+
+// Grouped-tap convT partials [ci][T = phase*4 + tap][co] -> dw[ci][co][r][s] (+)=: one block per input channel,
+// (splits x) reads coalesced along co, one coalesced write of the 16*O contiguous master elements.
+__global__ void __launch_bounds__(256) wgrad_reduce_convT_t_kernel(const float* __restrict__ partial, int splits,
+                                                                  int64_t split_stride, float* __restrict__ dw,
+                                                                  int accumulate, int O) {
+  extern __shared__ float sm_t[];                       // [O][17]
+  const int i = blockIdx.x;
+  const float* pp = partial + int64_t(i) * 16 * O;
+  for (int q = threadIdx.x; q < 16 * O; q += 256) {
+    const int T = q / O, o = q - T * O;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += pp[s * split_stride + q];
+    const int ph = T >> 2, tp = T & 3;
+    const int t = ph_r(ph >> 1, tp >> 1) * 4 + ph_r(ph & 1, tp & 1);
+    sm_t[o * 17 + t] = acc;
+  }
+  __syncthreads();
+  float* d = dw + int64_t(i) * 16 * O;
+  for (int e = threadIdx.x; e < 16 * O; e += 256) {
+    const float v = sm_t[(e >> 4) * 17 + (e & 15)];
+    d[e] = accumulate ? d[e] + v : v;
+  }
 }
 
 // dW[ci][co][r][s] = sum x[n, i+dh, j+dw, ci] * dy[n, 2i+py, 2j+px, co] over the 4 phases x 4 taps.
@@ -1091,36 +1155,62 @@ int msig_convT2d_wgrad(const msig_conv_geom* g, const void* x, const void* dy, f
   p.blocks_w = static_cast<int>(ceil_div(g->w, p.PW));
   p.blocks_h = static_cast<int>(ceil_div(g->h, p.PH));
   p.n_img = g->n;
-  p.taps = 16;
+  const bool group = convT_wgrad_groups(g);
+  p.taps = group ? 4 : 16;
   const int64_t kb_total = int64_t(g->n) * p.blocks_h * p.blocks_w;
-  WgradPlan pl = plan_wgrad(g->k, g->c, 16, kb_total);
+  WgradPlan pl = group ? plan_wgrad(g->c, 256, 4, kb_total) : plan_wgrad(g->k, g->c, 16, kb_total);
   const size_t need = size_t(pl.splits) * size_t(g->k) * 16 * g->c * sizeof(float);
   MSIG_REQUIRE(workspace_bytes >= need, "convT wgrad: workspace too small (%zu < %zu)", workspace_bytes, need);
   p.m_blocks = pl.m_blocks; p.n_blocks = pl.n_blocks; p.splits = pl.splits;
   p.kb_per_split = pl.kb_per_split; p.kb_total = pl.kb_total;
   p.out = reinterpret_cast<float*>(workspace);
-  p.o_row = int64_t(16) * g->c; p.o_tap = g->c;
   p.o_split = int64_t(g->k) * 16 * g->c;
-  p.alpha = 1.f; p.m_valid = g->k; p.n_valid = g->c;
+  p.alpha = 1.f;
+  if (group) {   // partials [ci][T][co]: the CTA of phase ph owns columns [ph*256, ph*256 + 256) of each row
+    p.o_row = int64_t(16) * g->k; p.o_tap = 256;
+    p.m_valid = g->c; p.n_valid = 256;
+    p.b_box_tap = 1;
+  } else {       // partials [co][T][ci]
+    p.o_row = int64_t(16) * g->c; p.o_tap = g->c;
+    p.m_valid = g->k; p.n_valid = g->c;
+  }
   int rc;
+  CUtensorMap* tm_dy = group ? p.tmB : p.tmA;
+  CUtensorMap* tm_x = group ? p.tmA : p.tmB;
+  Tap* tap_dy = group ? p.tapB : p.tapA;
+  Tap* tap_x = group ? p.tapA : p.tapB;
   const int64_t OH = 2 * int64_t(g->h), OW = 2 * int64_t(g->w);
   for (int py = 0; py < 2; ++py)
     for (int px = 0; px < 2; ++px) {
       const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(dy) + (py * OW + px) * g->k;
       ActView va{base, g->k, g->w, g->h, g->n, int64_t(2) * g->k, 2 * OW * g->k, OH * OW * g->k};
-      if ((rc = make_act_map(&p.tmA[py * 2 + px], va, p.PW, p.PH)) != MSIG_OK) return rc;
+      if ((rc = make_act_map(&tm_dy[py * 2 + px], va, p.PW, p.PH)) != MSIG_OK) return rc;
       for (int ty = 0; ty < 2; ++ty)
         for (int tx = 0; tx < 2; ++tx) {
           const int T = (py * 2 + px) * 4 + ty * 2 + tx;
-          p.tapA[T] = Tap{0, 0, int8_t(py * 2 + px), 0};
-          p.tapB[T] = Tap{int8_t(ph_d(py, ty)), int8_t(ph_d(px, tx)), 0, 0};
+          const int dh = ph_d(py, ty), dw_ = ph_d(px, tx);
+          if (group) {
+            tap_dy[T] = Tap{int8_t(-dh), int8_t(-dw_), int8_t(py * 2 + px), 0};
+          } else {
+            tap_dy[T] = Tap{0, 0, int8_t(py * 2 + px), 0};
+            tap_x[T] = Tap{int8_t(dh), int8_t(dw_), 0, 0};
+          }
         }
     }
+  if (group)
+    for (int ph = 0; ph < 4; ++ph) tap_x[ph] = Tap{0, 0, 0, 0};
   ActView vb{x, g->c, g->w, g->h, g->n, g->c, int64_t(g->w) * g->c, int64_t(g->h) * g->w * g->c};
-  if ((rc = make_act_map(&p.tmB[0], vb, p.PW, p.PH)) != MSIG_OK) return rc;
-  for (int i = 1; i < 4; ++i) p.tmB[i] = p.tmB[0];
+  if ((rc = make_act_map(&tm_x[0], vb, p.PW, p.PH)) != MSIG_OK) return rc;
+  for (int i = 1; i < 4; ++i) tm_x[i] = tm_x[0];
   cudaError_t ce = launch_wgrad(p, pl.block_n, st);
   if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "convT wgrad launch: %s", cudaGetErrorString(ce));
+  if (group) {
+    wgrad_reduce_convT_t_kernel<<<g->c, 256, size_t(g->k) * 17 * sizeof(float), st>>>(p.out, pl.splits, p.o_split, dw,
+                                                                                      accumulate, g->k);
+    count_launch(1);
+    MSIG_CHECK_LAUNCH();
+    return MSIG_OK;
+  }
   msig_wpack_desc d{MSIG_WPACK_CONVT_FWD, g->k, g->c, 4, 4};   // master weight [I=c][O=k][4][4]
   PackGeom pg = make_pack_geom(&d, 0, 0);
   return launch_wgrad_reduce(pg, p.out, pl.splits, p.o_split, dw, accumulate, st);

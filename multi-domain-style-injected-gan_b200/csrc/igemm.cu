@@ -1205,7 +1205,7 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
         vcb[i] -= nb[i] * p.CB;
       }
     }
-    const int a_boxes = p.a_boxes == 1 ? 1 : 2;
+    const int a_boxes = (p.a_boxes == 1 && !p.a_box_tap) ? 1 : 2;
     const uint32_t stage_tx = static_cast<uint32_t>(a_boxes * 8192 + Cfg::kBBytes);
     for (int kb = 0; kb < nk; ++kb) {
       const int oh0 = hb * p.PH, ow0 = wb * p.PW;
@@ -1214,11 +1214,19 @@ __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ W
         uint8_t* sa = smem + stage * Cfg::kStageBytes;
         uint8_t* sb = sa + Cfg::kABytes;
         mbar_expect_tx(&full_bar[stage], stage_tx);
+        if (p.a_box_tap) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i)
-          if (i < a_boxes)
-            tma_load_4d(sa + i * 8192, &p.tmA[ta.map], &full_bar[stage], vca[i], ow0 + ta.dw, oh0 + ta.dh,
-                        p.fold_img ? na[i] : img);
+          for (int i = 0; i < 2; ++i) {
+            const Tap tai = p.tapA[tap * 2 + i];
+            tma_load_4d(sa + i * 8192, &p.tmA[tai.map], &full_bar[stage], 0, ow0 + tai.dw, oh0 + tai.dh, img);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 2; ++i)
+            if (i < a_boxes)
+              tma_load_4d(sa + i * 8192, &p.tmA[ta.map], &full_bar[stage], vca[i], ow0 + ta.dw, oh0 + ta.dh,
+                          p.fold_img ? na[i] : img);
+        }
         if (p.b_box_tap) {
 #pragma unroll
           for (int i = 0; i < BLOCK_N / 64; ++i) {
@@ -1660,7 +1668,7 @@ static cudaError_t launch_wgrad2(const WgradParams& p, cudaStream_t stream) {
 cudaError_t launch_wgrad(const WgradParams& p, int block_n, cudaStream_t stream) {
   // CTA pairs for the full 256 x 256 tiles (both m-blocks of one (tap, split) share the B tile)
   if (g_pair_mode && block_n == 256 && p.m_blocks == 2 && p.n_blocks == 1 && !p.fold_img && !p.upper_only &&
-      !p.b_box_tap && p.a_boxes != 1 && p.m_valid == 256 && p.n_valid == 256 && (p.o_row & 7) == 0)
+      !p.b_box_tap && !p.a_box_tap && p.a_boxes != 1 && p.m_valid == 256 && p.n_valid == 256 && (p.o_row & 7) == 0)
     return launch_wgrad2(p, stream);
   switch (block_n) {
     case 64: return launch_wgrad_t<64>(p, stream);

@@ -94,6 +94,10 @@ struct WgradParams {
   int32_t upper_only;              // Gram: skip tiles strictly below the diagonal
   int32_t a_boxes;                 // 0/2: both 64-channel A boxes are loaded; 1: only the first (M <= 64 valid rows;
                                    //      rows 64..127 of the tile are never stored)
+  int32_t a_box_tap;               // 1: the two 64-row A boxes are the SAME 64 channels read through different taps:
+                                   //    box i of CTA-tap y uses tapA[2*y + i] (row-patch weight gradients: the
+                                   //    second box is the first shifted up by four rows, so rows 64..127 of the
+                                   //    tile accumulate the NEXT four filter rows against the same B boxes)
   int32_t b_box_tap;               // 1: the BLOCK_N/64 boxes of the B tile are the SAME 64 "channels" read through
                                    //    different taps: box i of CTA-tap y uses tapB[y*(BLOCK_N/64) + i]
                                    //    (row-patch weight gradients: 4 filter rows per CTA)

@@ -55,6 +55,7 @@ _SIGS = {
     "msig_last_error": (c_char_p, []),
     "msig_sm_count": (c_int, []),
     "msig_debug_set_m2_mode": (c_int, [c_int]),
+    "msig_debug_set_wgrad_mode": (c_int, [c_int]),
     "msig_debug_set_pair_mode": (c_int, [c_int]),
     "msig_debug_set_ring_mode": (c_int, [c_int]),
     "msig_kernel_launches": (c_longlong, []),

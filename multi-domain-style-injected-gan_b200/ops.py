@@ -56,6 +56,8 @@ def ensure_init(device=None):
         import os
         if os.environ.get("MSIG_M2", "1") == "0":
             L.call("msig_debug_set_m2_mode", 0)
+        if "MSIG_WGRAD_MODE" in os.environ:
+            L.call("msig_debug_set_wgrad_mode", int(os.environ["MSIG_WGRAD_MODE"]))
     return lib
 
 

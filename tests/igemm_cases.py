@@ -87,7 +87,12 @@ def case_conv_wgrad(n, c, h, w, k, r, stride, pad, seed=0):
     return rel_err(dw, ref), 2e-3
 
 
-def case_convT(n, c, h, w, k, seed=0, which="fwd"):
+def _wgrad_mode(mask):
+    """Test hook: weight-gradient operand plans (bit 0 M-stacked row-patch, bit 1 tap-grouped convT); 3 = default."""
+    L.call("msig_debug_set_wgrad_mode", mask)
+
+
+def case_convT(n, c, h, w, k, seed=0, which="fwd", wgrad_mode=3):
     ops.ensure_init()
     x = _bf(_rand((n, c, h, w), seed)).to(DEV)
     wt = _bf(_rand((c, k, 4, 4), seed + 1, 1.0 / (c * 4) ** 0.5)).to(DEV)   # ConvTranspose2d layout [in, out, 4, 4]
@@ -109,10 +114,16 @@ def case_convT(n, c, h, w, k, seed=0, which="fwd"):
     xf = x.float()
     wf = wt.float().clone().requires_grad_(True)
     (F.conv_transpose2d(xf, wf, None, stride=2, padding=1) * dy.float()).sum().backward()
-    dw = torch.zeros((c, k, 4, 4), dtype=torch.float32, device=DEV)
-    ops.convT2d_wgrad(nhwc(x), nhwc(dy), g, dw, accumulate=False)
+    dw = torch.full((c, k, 4, 4), 7.0, dtype=torch.float32, device=DEV)
+    _wgrad_mode(wgrad_mode)
+    try:
+        ops.convT2d_wgrad(nhwc(x), nhwc(dy), g, dw, accumulate=False)
+        dw2 = dw.clone()
+        ops.convT2d_wgrad(nhwc(x), nhwc(dy), g, dw2, accumulate=True)       # (+)= doubles it
+    finally:
+        _wgrad_mode(3)
     torch.cuda.synchronize()
-    return rel_err(dw, wf.grad), 2e-3
+    return max(rel_err(dw, wf.grad), rel_err(dw2, 2 * wf.grad)), 2e-3
 
 
 def case_final_conv(n, h, w, seed=0):
@@ -161,7 +172,7 @@ def case_narrow_dgrad(n, h, w, seed=0):
     return rel_err(dimg, img.grad), 2e-3
 
 
-def case_rowpatch_first(n, h, w, which, seed=0):
+def case_rowpatch_first(n, h, w, which, seed=0, wgrad_mode=3):
     """First generator conv (model.py:131): 7x7 reflect-padded 3->64 through the row-patch path."""
     ops.ensure_init()
     img = _bf(_rand((n, 3, h, w), seed)).float().to(DEV)
@@ -177,10 +188,16 @@ def case_rowpatch_first(n, h, w, which, seed=0):
         return rel_err(nchw(y), ref), 1e-2
     dy = _bf(_rand((n, 64, h, w), seed + 2)).to(DEV)
     ref = torch.nn.grad.conv2d_weight(padded, (64, 3, 7, 7), dy.float())
-    dw = torch.zeros((64, 3, 7, 7), dtype=torch.float32, device=DEV)
-    ops.conv_rowpatch_wgrad(xp8, nhwc(dy), g, dw, flip=False, accumulate=False)
+    dw = torch.full((64, 3, 7, 7), 7.0, dtype=torch.float32, device=DEV)
+    _wgrad_mode(wgrad_mode)
+    try:
+        ops.conv_rowpatch_wgrad(xp8, nhwc(dy), g, dw, flip=False, accumulate=False)
+        dw2 = dw.clone()
+        ops.conv_rowpatch_wgrad(xp8, nhwc(dy), g, dw2, flip=False, accumulate=True)
+    finally:
+        _wgrad_mode(3)
     torch.cuda.synchronize()
-    return rel_err(dw, ref), 2e-3
+    return max(rel_err(dw, ref), rel_err(dw2, 2 * ref)), 2e-3
 
 
 def case_rowpatch_final_bwd(n, h, w, which, seed=0):
@@ -369,6 +386,12 @@ CASES = {
     "wgrad_4x4s2_64_128": lambda: case_conv_wgrad(2, 64, 64, 64, 128, 4, 2, 1),
     "wgrad_4x4s2_256_512_w16": lambda: case_conv_wgrad(2, 256, 32, 32, 512, 4, 2, 1),
     "convT_wgrad_256_128": lambda: case_convT(2, 256, 32, 32, 128, which="wgrad"),
+    "convT_wgrad_128_64_grouped": lambda: case_convT(2, 128, 64, 64, 64, which="wgrad"),
+    "convT_wgrad_128_64_grouped_w32": lambda: case_convT(3, 128, 32, 32, 64, which="wgrad", seed=5),
+    "convT_wgrad_256_64_grouped_ragged": lambda: case_convT(1, 256, 20, 72, 64, which="wgrad", seed=7),
+    "convT_wgrad_128_64_per_tap_plan": lambda: case_convT(2, 128, 64, 64, 64, which="wgrad", wgrad_mode=1),
+    "rowpatch_first_wgrad_unstacked_plan": lambda: case_rowpatch_first(2, 64, 256, "wgrad", wgrad_mode=2),
+    "rowpatch_first_wgrad_tall": lambda: case_rowpatch_first(1, 133, 64, "wgrad", seed=9),
     "gram_64": lambda: case_gram(2, 64, 64, 64),
     "gram_256_b3": lambda: case_gram(3, 256, 16, 16),
     "gram_bwd_128": lambda: case_gram_bwd(2, 128, 32, 32),
