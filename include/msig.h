@@ -37,7 +37,7 @@ int msig_init(int device);               /* binds the device, resolves cuTensorM
 int msig_version(void);
 const char* msig_last_error(void);       /* thread-local */
 int msig_sm_count(void);
-int msig_debug_set_ring_mode(int on);     /* test hook: strip-ring kernel for 64-channel stride-1 layers, default on */
+int msig_debug_set_ring_mode(int mode);   /* test hook: strip-ring kernel for 64-channel layers: bit 0 on, bit 1 four convT phases in one launch, bits 8..15 ring-depth cap; default 3 */
 int msig_debug_set_wgrad_mode(int mask);  /* test hook: bit 0 = M-stacked row-patch weight gradients, bit 1 = tap-grouped convT ones; default 3 */
 int msig_debug_set_m2_mode(int on);       /* test hook: two m-tiles per CTA for the 128-wide conv tiles, default on */
 int msig_debug_set_pair_mode(int on);     /* test hook: CTA-pair (tcgen05 cta_group::2) kernel for 256-wide conv tiles, default on */
@@ -74,6 +74,12 @@ typedef struct msig_epilogue {
   const void* stats_z;
   const float* ch_scale;  /* optional [k] fp32 per-output-channel multiplier, applied with alpha before the bias
                            * (msig_conv_narrow_fwd only: the VGG input renormalisation's 0.5/std on d(image)) */
+  /* Optional (both or neither; fp32 [n][k], 16-byte aligned; needs stats_z, k % 16 == 0 and aux_mode RELU_MASK /
+   * LRELU_MASK): the activation mask is act'(stats_z * mask_scale + mask_shift), i.e. recomputed from the norm
+   * INPUT z and the scale / shift its InstanceNorm / AdaIN applied (model.py:16, 28-36), instead of being read
+   * from the saved activation: `aux` is ignored and one 2-byte-per-element stream leaves the epilogue. */
+  const float* mask_scale;
+  const float* mask_shift;
 } msig_epilogue;
 /* rows of stats_partial PER IMAGE for an output plane oh x ow produced in `phases` (1, or 4 for the
  * k4 s2 transposed conv / stride-2 dgrad, where oh x ow is the per-phase plane = the INPUT plane). */

@@ -422,6 +422,17 @@ static int fill_epilogue(FpropParams& p, const msig_epilogue* e, const OutView& 
   p.slope = e ? e->slope : 0.f;
   p.aux = e ? reinterpret_cast<const __nv_bfloat16*>(e->aux) : nullptr;
   p.aux_mode = (e && e->aux) ? e->aux_mode : AUX_NONE;
+  if (e && (e->mask_scale != nullptr || e->mask_shift != nullptr)) {
+    // activation mask recomputed from the norm input (stats_z) and its per-(image, channel) scale / shift
+    if (e->mask_scale == nullptr || e->mask_shift == nullptr || e->stats_z == nullptr ||
+        (e->aux_mode != AUX_RELU_MASK && e->aux_mode != AUX_LRELU_MASK) || p.fold_c != 0 || p.tap_is_image ||
+        (n_valid % 16) != 0 || ((reinterpret_cast<uintptr_t>(e->mask_scale) | reinterpret_cast<uintptr_t>(e->mask_shift)) & 15) != 0)
+      return set_error(MSIG_ERR_ARG, "epilogue mask_scale/mask_shift need both pointers (16-byte aligned), stats_z, "
+                                     "a ReLU / LeakyReLU mask mode and k %% 16 == 0");
+    p.aux = nullptr;
+    p.aux_mode = e->aux_mode;
+    p.mask_scale = e->mask_scale; p.mask_shift = e->mask_shift; p.mask_ld = n_valid;
+  }
   p.a_sn = ov.sN; p.a_sh = ov.sH; p.a_sw = ov.sW;   // aux is congruent with a bf16 NHWC output
   if (p.aux_mode != AUX_NONE && (ov.f32 || ov.sC != 1))
     return set_error(MSIG_ERR_UNSUPPORTED, "epilogue aux needs a bf16 NHWC output");
@@ -439,13 +450,14 @@ static int fill_epilogue(FpropParams& p, const msig_epilogue* e, const OutView& 
   return MSIG_OK;
 }
 
-static int g_ring_mode = 1;    // test hook: 0 = generic per-tap kernel for the 64-channel stride-1 layers
+static int g_ring_mode = 3;    // test hook: 0 = generic per-tap kernel for the 64-channel stride-1 layers; bit 1 =
+                               // the four phases of a transposed conv in one ring launch (else one launch each)
 static int g_wgrad_mode = 3;   // test hook: bit 0 = M-stacked row-patch weight gradients, bit 1 = tap-grouped convT ones
 #define g_rowpatch_stack (g_wgrad_mode & 1)
 #define g_convt_group (g_wgrad_mode & 2)
 
 // Configure `p` (epilogue already filled, n_img / OH / OW set) for the N = 64 ring kernel.
-static void set_ring(FpropParams& p, int R, int S, int org_h, int org_w) {
+static void set_ring(FpropParams& p, int R, int S, int org_h, int org_w, int nph = 1) {
   p.TW = 128; p.TH = 1;
   p.tiles_h = p.OH;
   p.tiles_w = static_cast<int>(ceil_div(p.OW, 128));
@@ -454,7 +466,7 @@ static void set_ring(FpropParams& p, int R, int S, int org_h, int org_w) {
   p.org_h = org_h; p.org_w = org_w;
   p.ring_cb = 1;
   for (int t = 0; t < R * S && t < 16; ++t) p.ring_tap[t] = static_cast<int8_t>(t);
-  const int sms = sm_count() > 0 ? sm_count() : 148;
+  const int sms = (sm_count() > 0 ? sm_count() : 148) / nph;      // CTAs that share one phase's items
   int rows = 64;
   while (rows > 8 && int64_t(p.n_img) * p.tiles_w * ceil_div(p.OH, rows) < int64_t(6) * sms) rows /= 2;
   p.ring_rows = rows;
@@ -577,6 +589,27 @@ static int run_phased(const void* in, int n, int h, int w, int c, int k, const v
   // a 2x2 stride-1 conv; run each through the strip-ring kernel (resident 64 KiB filter slab, input rows
   // shared by consecutive output rows) instead of re-fetching 24 KiB per K block.
   if (g_ring_mode != 0 && c == 128 && block_n == 64 && k_pad == 64 && w >= 128 && p.stat_out == nullptr) {
+    // input rows / columns of a phase in ascending order: ring position r <-> tap 1 - r
+    auto ring_taps = [](FpropParams& q) {
+      q.ring_cb = 2;
+      for (int r = 0; r < 2; ++r)
+        for (int s2 = 0; s2 < 2; ++s2) q.ring_tap[r * 2 + s2] = static_cast<int8_t>((1 - r) * 2 + (1 - s2));
+    };
+    if (g_ring_mode & 2) {
+      // all four phases in ONE launch (CTA b -> phase b % 4): the input is read from HBM once
+      set_ring(p, 2, 2, 0, 0, 4);
+      ring_taps(p);
+      p.ring_phases = 4;
+      for (int ph = 0; ph < 4; ++ph) {
+        p.ring_org_h[ph] = (ph >> 1) == 0 ? -1 : 0;
+        p.ring_org_w[ph] = (ph & 1) == 0 ? -1 : 0;
+      }
+      if ((rc = make_act_map(&p.tmA[1], v, 128 + 1, 1)) != MSIG_OK) return rc;
+      if ((rc = make_w_map(&p.tmB, wpk, int64_t(4) * k_pad, int64_t(4) * c, 64)) != MSIG_OK) return rc;
+      cudaError_t ce = launch_fprop_ring64(p, sm_count(), st);
+      if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "fprop(4-phase ring) launch: %s", cudaGetErrorString(ce));
+      return MSIG_OK;
+    }
     for (int py = 0; py < 2; ++py)
       for (int px = 0; px < 2; ++px) {
         const int ph = py * 2 + px;
@@ -584,11 +617,8 @@ static int run_phased(const void* in, int n, int h, int w, int c, int k, const v
         q.phases = 1;
         q.out = reinterpret_cast<__nv_bfloat16*>(out) + p.o_ph[ph];
         if (q.aux != nullptr) q.aux = q.aux + p.a_ph[ph];
-        // input rows / columns of a phase in ascending order: ring position r <-> tap 1 - r
         set_ring(q, 2, 2, py == 0 ? -1 : 0, px == 0 ? -1 : 0);
-        q.ring_cb = 2;
-        for (int r = 0; r < 2; ++r)
-          for (int s2 = 0; s2 < 2; ++s2) q.ring_tap[r * 2 + s2] = static_cast<int8_t>((1 - r) * 2 + (1 - s2));
+        ring_taps(q);
         if ((rc = make_act_map(&q.tmA[1], v, 128 + 1, 1)) != MSIG_OK) return rc;
         const __nv_bfloat16* wph = reinterpret_cast<const __nv_bfloat16*>(wpk) + int64_t(ph) * k_pad * 4 * c;
         if ((rc = make_w_map(&q.tmB, wph, k_pad, int64_t(4) * c, 64)) != MSIG_OK) return rc;
@@ -652,9 +682,11 @@ int32_t msig_epilogue_stats_rows(int32_t oh, int32_t ow, int32_t phases) {
   return static_cast<int32_t>(ceil_div(oh, TH) * ceil_div(ow, TW) * phases * 4);
 }
 
-// Test hook: ring kernel for the 64-channel stride-1 layers on (default) / off.
-int msig_debug_set_ring_mode(int on) {
-  g_ring_mode = on;
+// Test hook: ring kernel for the 64-channel stride-1 layers. Bit 0: on; bit 1: the four phases of a transposed
+// conv share one launch; bits 8..15: cap on the ring depth (0 = whatever fits). Default 3.
+int msig_debug_set_ring_mode(int mode) {
+  g_ring_mode = mode & 3;
+  set_ring_slots_cap((mode >> 8) & 0xff);
   return MSIG_OK;
 }
 

@@ -39,8 +39,13 @@ struct FpropCfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
-  static constexpr int kTmemCols = (2 * BLOCK_N) < 32 ? 32 : 2 * BLOCK_N;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // Accumulator stages in TMEM: double buffered. (Eight stages + alternate-tile epilogue warpgroups for the 64-wide
+  // tiles were tried and were SLOWER: those layers are bound by the epilogue's instruction stream, not by the
+  // accumulator hand-off latency -- profiles/README_r2.md section 4.)
+  static constexpr int kAccStages = 2;
+  static constexpr bool kAltTiles = false;
+  static constexpr int kTmemCols = (kAccStages * BLOCK_N) < 32 ? 32 : kAccStages * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 512 /*barriers*/;
 };
 
 __device__ __forceinline__ float apply_act(float v, int act, float slope) {
@@ -99,14 +104,15 @@ __device__ __forceinline__ void epilogue_load(const FpropParams& p, int col0, bo
 #pragma unroll
   for (int g = 0; g < NC / 8; g += 2) {
     const int c = col0 + 8 * g;
+    const bool ld_aux = p.aux_mode != AUX_NONE && p.mask_scale == nullptr;
     if (row_valid && c + 16 <= p.n_valid) {          // column pairs are 32-byte aligned (channels % 16 == 0)
-      if (p.aux_mode != AUX_NONE) ldg256(p.aux + aux_off + c, av[g], av[g + 1]);
+      if (ld_aux) ldg256(p.aux + aux_off + c, av[g], av[g + 1]);
       if (p.stat_z != nullptr) ldg256(p.stat_z + out_off + c, zv[g], zv[g + 1]);
     } else {
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const bool live = row_valid && (c + 8 * h + 8 <= p.n_valid);
-        if (live && p.aux_mode != AUX_NONE)
+        if (live && ld_aux)
           av[g + h] = __ldg(reinterpret_cast<const uint4*>(p.aux + aux_off + c + 8 * h));
         if (live && p.stat_z != nullptr)
           zv[g + h] = __ldg(reinterpret_cast<const uint4*>(p.stat_z + out_off + c + 8 * h));
@@ -118,11 +124,15 @@ __device__ __forceinline__ void epilogue_load(const FpropParams& p, int col0, bo
 // Epilogue for NC accumulator columns of one output pixel (thread-per-row). With STATS the warp
 // also reduces the stored values over its 32 pixels (see FpropParams::stat_out); `stat_row` is the
 // partial-sum row of this warp and `stat_col` the GEMM column of r[0].
+// Epilogue for NC accumulator columns of one output pixel (thread-per-row). With STATS the warp
+// also reduces the stored values over its 32 pixels (see FpropParams::stat_out); `stat_row` is the
+// partial-sum row of this warp and `stat_col` the GEMM column of r[0].
 template <int NC, bool STATS>
 __device__ __forceinline__ void fprop_epilogue_chunk(const FpropParams& p, const uint32_t (&r)[NC],
                                                      const uint4 (&av)[NC / 8], const uint4 (&zv)[NC / 8],
                                                      int col0, bool row_valid, int64_t out_off, float alpha,
-                                                     int64_t stat_row = 0, int stat_col = 0, int lane = 0) {
+                                                     int64_t stat_row = 0, int stat_col = 0, int lane = 0,
+                                                     const float* msc = nullptr, const float* msh = nullptr) {
   if (!STATS && !row_valid) return;
   if (!p.out_f32 && p.o_sc == 1) {
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
@@ -146,7 +156,21 @@ __device__ __forceinline__ void fprop_epilogue_chunk(const FpropParams& p, const
         v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
         v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
       }
-      if (p.aux_mode != AUX_NONE) {
+      if (p.aux_mode != AUX_NONE && msc != nullptr) {
+        // act' of the normalised value, recomputed exactly as the forward pass formed it (ops.cu, norm_act_fwd)
+        const __nv_bfloat162* zh2 = reinterpret_cast<const __nv_bfloat162*>(&zv[g]);
+        const float4 s0 = __ldg(reinterpret_cast<const float4*>(msc + c)), s1 = __ldg(reinterpret_cast<const float4*>(msc + c + 4));
+        const float4 h0 = __ldg(reinterpret_cast<const float4*>(msh + c)), h1 = __ldg(reinterpret_cast<const float4*>(msh + c + 4));
+        const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+        const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+        const float off = p.aux_mode == AUX_RELU_MASK ? 0.f : p.slope;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 z = __bfloat1622float2(zh2[j]);
+          v[2 * j] = fmaf(z.x, sc[2 * j], sh[2 * j]) > 0.f ? v[2 * j] : v[2 * j] * off;
+          v[2 * j + 1] = fmaf(z.y, sc[2 * j + 1], sh[2 * j + 1]) > 0.f ? v[2 * j + 1] : v[2 * j + 1] * off;
+        }
+      } else if (p.aux_mode != AUX_NONE) {
         const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&av[g]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -232,6 +256,13 @@ __device__ __forceinline__ void fprop_epilogue_chunk(const FpropParams& p, const
 // Epilogue of ONE output tile for one epilogue warp: waits for the accumulator stage, then
 // alpha / bias / aux / activation / store (+ fused statistics) for this warp's columns
 // [c_begin, c_end) of accumulator rows q*32 .. q*32+31. `mt_full` = m-tile index incl. phase.
+// fprop_epilogue_at: the tile's (phase, image) and this thread's output pixel (oh, ow) are already known.
+template <int BLOCK_N>
+__device__ __forceinline__ void fprop_epilogue_at(const FpropParams& p, int mt_full, int ph, int img, int oh, int ow,
+                                                  int n_blk, uint32_t tmem_base, int as, uint32_t aphase,
+                                                  uint64_t* tfull_bar, int q, int lane, int c_begin, int c_end,
+                                                  float alpha);
+
 template <int BLOCK_N>
 __device__ __forceinline__ void fprop_epilogue_tile(const FpropParams& p, int mt_full, int n_blk, uint32_t tmem_base,
                                                     int as, uint32_t aphase, uint64_t* tfull_bar, int q, int lane,
@@ -246,6 +277,15 @@ __device__ __forceinline__ void fprop_epilogue_tile(const FpropParams& p, int mt
   const int img = mt / p.tiles_h;
   const int oh = th * p.TH + row / p.TW;
   const int ow = tw * p.TW + row % p.TW;
+  fprop_epilogue_at<BLOCK_N>(p, mt_full, ph, img, oh, ow, n_blk, tmem_base, as, aphase, tfull_bar, q, lane, c_begin,
+                             c_end, alpha);
+}
+
+template <int BLOCK_N>
+__device__ __forceinline__ void fprop_epilogue_at(const FpropParams& p, int mt_full, int ph, int img, int oh, int ow,
+                                                  int n_blk, uint32_t tmem_base, int as, uint32_t aphase,
+                                                  uint64_t* tfull_bar, int q, int lane, int c_begin, int c_end,
+                                                  float alpha) {
   const bool row_valid = (oh < p.OH) && (ow < p.OW);
   const int64_t out_off = p.o_ph[ph] + img * p.o_sn + oh * p.o_sh + ow * p.o_sw;
   const int64_t aux_off = p.a_ph[ph] + img * p.a_sn + oh * p.a_sh + ow * p.a_sw;
@@ -275,7 +315,9 @@ __device__ __forceinline__ void fprop_epilogue_tile(const FpropParams& p, int mt
     };
     // While the main loop of this tile is still running: pull the tile's aux / stat_z rows into L2
     // and the first chunk's operands into registers.
-    const bool has_aux = p.aux_mode != AUX_NONE, has_z = p.stat_z != nullptr;
+    const bool has_aux = p.aux_mode != AUX_NONE && p.mask_scale == nullptr, has_z = p.stat_z != nullptr;
+    const float* msc = p.mask_scale ? p.mask_scale + int64_t(img) * p.mask_ld : nullptr;
+    const float* msh = p.mask_shift ? p.mask_shift + int64_t(img) * p.mask_ld : nullptr;
     uint4 pa[4], pz[4];
     if (has_aux || has_z) {
       if (row_valid) {
@@ -316,9 +358,10 @@ __device__ __forceinline__ void fprop_epilogue_tile(const FpropParams& p, int mt
       locate(c, col, oo, ao);
       tmem_ld_wait();
       if (p.stat_out != nullptr)
-        fprop_epilogue_chunk<32, true>(p, r, ca, cz, col, row_valid, oo, alpha, stat_row, n_blk * BLOCK_N + c, lane);
+        fprop_epilogue_chunk<32, true>(p, r, ca, cz, col, row_valid, oo, alpha, stat_row, n_blk * BLOCK_N + c, lane,
+                                       msc, msh);
       else
-        fprop_epilogue_chunk<32, false>(p, r, ca, cz, col, row_valid, oo, alpha);
+        fprop_epilogue_chunk<32, false>(p, r, ca, cz, col, row_valid, oo, alpha, 0, 0, 0, msc, msh);
     }
   }
 }
@@ -336,8 +379,9 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_kernel(const __grid_co
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
   uint64_t* empty_bar = full_bar + Cfg::kStages;
   uint64_t* tfull_bar = empty_bar + Cfg::kStages;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  constexpr int NACC = Cfg::kAccStages;
+  uint64_t* tempty_bar = tfull_bar + NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + NACC);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -351,9 +395,9 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_kernel(const __grid_co
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < NACC; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], BLOCK_N >= 64 ? 256 : 128);
+      mbar_init(&tempty_bar[a], (BLOCK_N >= 64 && !Cfg::kAltTiles) ? 256 : 128);
     }
     fence_barrier_init();
   }
@@ -417,8 +461,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_kernel(const __grid_co
     uint32_t phase = 0;
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      const int as = it % NACC;
+      const uint32_t aphase = (it / NACC) & 1;
       mbar_wait(&tempty_bar[as], aphase ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BLOCK_N;
@@ -444,14 +488,15 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_kernel(const __grid_co
     }
   } else if (warp >= 4 && (BLOCK_N >= 64 || warp < 8)) {
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;                       // which half of the columns
-    constexpr int kHalfCols = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;
-    const int c_begin = half * kHalfCols, c_end = c_begin + kHalfCols;
+    const int half = (warp - 4) >> 2;                       // which half of the columns (kAltTiles: which tiles)
+    constexpr int kHalfCols = (BLOCK_N >= 64 && !Cfg::kAltTiles) ? BLOCK_N / 2 : BLOCK_N;
+    const int c_begin = Cfg::kAltTiles ? 0 : half * kHalfCols, c_end = c_begin + kHalfCols;
     const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t aphase = (it >> 1) & 1;
+      if (Cfg::kAltTiles && (it & 1) != half) continue;
+      const int as = it % NACC;
+      const uint32_t aphase = (it / NACC) & 1;
       fprop_epilogue_tile<BLOCK_N>(p, tile / p.n_blocks, tile % p.n_blocks, tmem_base, as, aphase, tfull_bar, q, lane,
                                    c_begin, c_end, alpha);
       tc_fence_before();
@@ -776,25 +821,32 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpropThreads, 1)
 }
 
 // ------------------------------------------------------------------------------------ row-fold
-constexpr int kRfRing = 8;                       // strips resident (>= R + 1)
+// Every input strip is used ONCE: its MMAs add the strip's contribution to all R output rows it belongs to
+// (filter row j of input row y feeds output row y - j). Output row o accumulates in TMEM column block o % 16
+// (32 columns each, all 512 columns allocated), so the R blocks one strip touches are CONSECUTIVE (mod 16) and
+// the B operand is the fixed matrix [W_{R-1}; ...; W_0]: per 16-channel K step one N = 32*(R-1) accumulate MMA
+// (two when the block window wraps) plus the N = 32 MMA that initialises the newest row's block -- a quarter of
+// the MMA time of accumulating each output row from its R strips (R * 4 N = 32 MMAs, shared-memory bound).
+constexpr int kRfRing = 8;                       // strips in flight
 constexpr int kRfStripBytes = kTileM * 128;      // 128 pixels x 64 ch bf16
 constexpr int kRfMaxR = 7;
 constexpr int kRfWBytes = 32 * 128;              // one filter row: 32 (s, co) rows x 64 ch
 constexpr int kRfFoldLd = 33;
-constexpr int kRfSmemBytes = kRfMaxR * kRfWBytes + kRfRing * kRfStripBytes + 2 * kTileM * kRfFoldLd * 4 + 1024 + 256;
+constexpr int kRfThreads = 384;                  // warps 0..3 as in the fprop kernels, 4..7 / 8..11 = two epilogue groups
+constexpr int kRfSmemBytes = kRfMaxR * kRfWBytes + kRfRing * kRfStripBytes + 4 * kTileM * kRfFoldLd * 4 + 1024 + 512;
 
-__global__ void __launch_bounds__(256, 1) fprop_rowfold_kernel(const __grid_constant__ RowfoldParams p) {
+__global__ void __launch_bounds__(kRfThreads, 1) fprop_rowfold_kernel(const __grid_constant__ RowfoldParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   uint8_t* wsm = smem;                                              // R x [32][64] bf16
   uint8_t* ring = smem + kRfMaxR * kRfWBytes;                        // 28 KiB -> 1024-aligned
-  float* fold = reinterpret_cast<float*>(ring + kRfRing * kRfStripBytes);   // 2 x [128][33] fp32
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(fold) + 2 * kTileM * kRfFoldLd * 4);
+  float* fold = reinterpret_cast<float*>(ring + kRfRing * kRfStripBytes);   // 2 groups x 2 x [128][33] fp32
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(fold) + 4 * kTileM * kRfFoldLd * 4);
   uint64_t* empty_bar = full_bar + kRfRing;
   uint64_t* tfull_bar = empty_bar + kRfRing;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* wfull_bar = tempty_bar + 2;
+  uint64_t* tempty_bar = tfull_bar + 16;
+  uint64_t* wfull_bar = tempty_bar + 16;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -811,14 +863,14 @@ __global__ void __launch_bounds__(256, 1) fprop_rowfold_kernel(const __grid_cons
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < 16; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 128);
     }
     mbar_init(wfull_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 64);
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -838,7 +890,8 @@ __global__ void __launch_bounds__(256, 1) fprop_rowfold_kernel(const __grid_cons
   if (warp == 0) {
     if (elect_one()) {
       mbar_expect_tx(wfull_bar, static_cast<uint32_t>(R) * kRfWBytes);
-      for (int r = 0; r < R; ++r) tma_load_2d(wsm + r * kRfWBytes, &p.tmB, wfull_bar, 0, r * 32);
+      // resident filter in DESCENDING filter-row order: block j' holds W_{R-1-j'}
+      for (int r = 0; r < R; ++r) tma_load_2d(wsm + (R - 1 - r) * kRfWBytes, &p.tmB, wfull_bar, 0, r * 32);
     }
     __syncwarp();
     uint32_t g = 0;                                  // strips issued so far (ring position)
@@ -859,43 +912,50 @@ __global__ void __launch_bounds__(256, 1) fprop_rowfold_kernel(const __grid_cons
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(kTileM, 32, 0, 0);
     mbar_wait(wfull_bar, 0);
     const uint32_t w_addr = smem_u32(wsm);
     const uint32_t ring_addr = smem_u32(ring);
-    uint32_t g0 = 0;                                 // ring position of the item's first strip
-    int it = 0;                                      // tiles issued (accumulator stage / phase)
+    const int nacc = R - 1;                          // blocks that accumulate (filter rows R-1 .. 1)
+    const uint32_t idesc_new = make_idesc_bf16(kTileM, 32, 0, 0);
+    const uint32_t idesc_all = make_idesc_bf16(kTileM, 32 * R, 0, 0);
+    const uint64_t db_new = make_smem_desc(w_addr + nacc * kRfWBytes, 0, 1024);     // W_0
+    uint32_t g = 0;                                  // strips consumed so far == counter of the newest output row
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       int img, tw, h0, nrows;
       decode(item, img, tw, h0, nrows);
-      for (int i = 0; i < nrows; ++i, ++it) {
-        const int as = it & 1;
-        mbar_wait(&tempty_bar[as], (((it >> 1) & 1) ^ 1u));
-        // strips g0+i .. g0+i+R-1 must have landed (only the last one is new after the first row)
-        for (int r = (i == 0 ? 0 : R - 1); r < R; ++r) {
-          const uint32_t g = g0 + i + r;
-          mbar_wait(&full_bar[g % kRfRing], (g / kRfRing) & 1u);
-        }
+      const int nstrips = nrows + R - 1;
+      for (int t = 0; t < nstrips; ++t, ++g) {
+        const uint32_t blk = g & 15u;
+        mbar_wait(&tempty_bar[blk], ((g >> 4) & 1u) ^ 1u);          // the row that used this block 16 rows ago is read
+        mbar_wait(&full_bar[g % kRfRing], (g / kRfRing) & 1u);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t d_tmem = tmem_base + as * 32;
-          for (int r = 0; r < R; ++r) {
-            const uint32_t g = g0 + i + r;
-            const uint64_t da = make_smem_desc(ring_addr + (g % kRfRing) * kRfStripBytes, 0, 1024);
-            const uint64_t db = make_smem_desc(w_addr + r * kRfWBytes, 0, 1024);
+          const uint64_t da = make_smem_desc(ring_addr + (g % kRfRing) * kRfStripBytes, 0, 1024);
+          const uint32_t b0 = (g - static_cast<uint32_t>(nacc)) & 15u;   // block of filter row R-1
+          const int n1 = min(nacc, static_cast<int>(16u - b0));           // accumulate blocks before the wrap
+          const int n2 = nacc - n1;
+          const uint64_t db0 = make_smem_desc(w_addr, 0, 1024);
+          const uint64_t db1 = make_smem_desc(w_addr + n1 * kRfWBytes, 0, 1024);
+          const uint32_t idesc1 = make_idesc_bf16(kTileM, n1 > 0 ? 32 * n1 : 32, 0, 0);
+          const uint32_t idesc2 = make_idesc_bf16(kTileM, n2 > 0 ? 32 * n2 : 32, 0, 0);
+          const bool contiguous = (n2 == 0) && (nacc == 0 || blk == b0 + static_cast<uint32_t>(nacc));
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k)
-              umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (r > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            if (k > 0 && contiguous) {               // one MMA over all R blocks
+              umma_bf16(tmem_base + b0 * 32, da + 2 * k, db0 + 2 * k, idesc_all, 1u);
+              continue;
+            }
+            if (n1 > 0) umma_bf16(tmem_base + b0 * 32, da + 2 * k, db0 + 2 * k, idesc1, 1u);
+            if (n2 > 0) umma_bf16(tmem_base, da + 2 * k, db1 + 2 * k, idesc2, 1u);
+            umma_bf16(tmem_base + blk * 32, da + 2 * k, db_new + 2 * k, idesc_new, k > 0 ? 1u : 0u);
           }
-          // the first strip of this row is dead now; after the item's last row so are the other R-1
-          umma_commit(&empty_bar[(g0 + i) % kRfRing]);
-          if (i == nrows - 1)
-            for (int r = 1; r < R; ++r) umma_commit(&empty_bar[(g0 + i + r) % kRfRing]);
-          umma_commit(&tfull_bar[as]);
+          umma_commit(&empty_bar[g % kRfRing]);      // the strip is dead
+          // output row counter g - (R-1) is complete (for t < R-1 that is one of the previous item's phantom
+          // counters: committed all the same, the epilogue walks every counter in order)
+          if (g >= static_cast<uint32_t>(nacc)) umma_commit(&tfull_bar[(g - static_cast<uint32_t>(nacc)) & 15u]);
         }
         __syncwarp();
       }
-      g0 += nrows + R - 1;
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
@@ -908,25 +968,43 @@ __global__ void __launch_bounds__(256, 1) fprop_rowfold_kernel(const __grid_cons
       if (co < p.n_valid && p.bias != nullptr) bias[co] = __ldg(p.bias + co);
       if (co < p.n_valid && p.ch_scale != nullptr) chs[co] = alpha * __ldg(p.ch_scale + co);
     }
-    int it = 0;
+    // The two epilogue groups take ALTERNATE output rows (one row's chain -- tfull, tcgen05.ld, transpose through
+    // shared memory, fold, store -- is longer than a strip's MMAs); both walk every counter to stay in step.
+    const int grp = (warp - 4) >> 2;
+    float* gfold = fold + grp * 2 * kTileM * kRfFoldLd;
+    int it = 0;                                      // real rows seen
+    int mine = 0;                                    // real rows handled by this group (fold buffer parity)
+    uint32_t c = 0;                                  // output-row counter, phantom ones (R-1 per item) included
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       int img, tw, h0, nrows;
       decode(item, img, tw, h0, nrows);
       const int ow = tw * tile_out + t;
       const bool valid = (t < tile_out) && (ow < p.OW);
-      for (int i = 0; i < nrows; ++i, ++it) {
-        const int as = it & 1;
-        mbar_wait(&tfull_bar[as], (it >> 1) & 1);
+      const bool last_item = item + static_cast<int>(gridDim.x) >= items;
+      const int ncount = last_item ? nrows : nrows + R - 1;         // the last phantom counters never complete
+      for (int i = 0; i < ncount; ++i, ++c) {
+        const uint32_t blk = c & 15u;
+        if (i >= nrows) {                            // phantom: nothing to read, group 0 hands the block back
+          if (grp == 0) {
+            mbar_wait(&tfull_bar[blk], (c >> 4) & 1u);
+            mbar_arrive(&tempty_bar[blk]);
+          }
+          continue;
+        }
+        if (((it++) & 1) != grp) continue;
+        mbar_wait(&tfull_bar[blk], (c >> 4) & 1u);
         tc_fence_after();
         uint32_t r32[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * 32, r32);
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + blk * 32, r32);
         tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&tempty_bar[as]);                // accumulator is in registers: free the stage
-        float* fb = fold + (it & 1) * kTileM * kRfFoldLd;
+        mbar_arrive(&tempty_bar[blk]);               // accumulator is in registers: free the block
+        float* fb = gfold + (mine & 1) * kTileM * kRfFoldLd;
+        ++mine;
 #pragma unroll
         for (int j = 0; j < 32; ++j) fb[t * kRfFoldLd + j] = __uint_as_float(r32[j]);
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // the four epilogue warps only
+        if (grp == 0) asm volatile("bar.sync 1, 128;" ::: "memory");   // the four warps of this group only
+        else asm volatile("bar.sync 2, 128;" ::: "memory");
         if (valid) {
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
           for (int s = 0; s < S; ++s) {
@@ -948,7 +1026,7 @@ __global__ void __launch_bounds__(256, 1) fprop_rowfold_kernel(const __grid_cons
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 64);
+    tmem_dealloc(tmem_base, 512);
   }
 }
 
@@ -962,49 +1040,65 @@ __global__ void __launch_bounds__(256, 1) fprop_rowfold_kernel(const __grid_cons
 //     are MMAs whose A descriptors start s rows into the strip, and the R - 1 strips shared with the
 //     next output row are re-used instead of re-loaded (work item = a column of consecutive output rows).
 // L2 traffic per 128-pixel tile drops from R*S*24 KiB to ~17 KiB. Epilogue = the generic one (BLOCK_N = 64).
-constexpr int kRingSlots = 8;
-constexpr int kRingSlotBytes = 17408;              // (128 + 8) rows x 128 B
-constexpr int kRingMaxTaps = 9;
+//   * with ring_phases = 4 (the four output phases of a stride-2 transposed conv / dgrad, each a 2x2 stride-1 conv
+//     of the SAME input) CTA b works on phase b % 4: the four phases walk the images side by side in ONE launch,
+//     so the input comes from HBM once and the other three phases hit L2.
+// The ring takes whatever shared memory the resident filter leaves (ring_slots, up to 16): with R = 7 input rows
+// in use per output row (row-patch convs) the look-ahead is what hides the strip latency.
+// L2 traffic per 128-pixel tile drops from R*S*24 KiB to ~17 KiB. Epilogue = the generic one (BLOCK_N = 64).
+constexpr int kRingMaxSlots = 16;
+constexpr int kRingMaxTaps = 9;                    // resident [64][64] filter tiles (R * S * channel blocks)
 constexpr int kRingWBytes = 64 * 128;              // one tap: 64 output channels x 64 K
-constexpr int kRingSmemBytes = kRingMaxTaps * kRingWBytes + kRingSlots * kRingSlotBytes + 1024 + 256;
+constexpr int kRingBarBytes = 512;              // 2 x 16 ring + 2 x 8 accumulator barriers + filter barrier + TMEM slot
+constexpr int kRingSmemMax = 232448;               // 227 KiB
+static inline int ring_slot_bytes(int S) { return ((kTileM + S - 1) * 128 + 1023) & ~1023; }
 
 __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __grid_constant__ FpropParams p) {
   constexpr int BLOCK_N = 64;
+  constexpr int NACC = 4;                  // accumulator stages in TMEM (64 columns each)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
-  uint8_t* wsm = smem;                                             // taps x 8 KiB
-  uint8_t* ring = smem + kRingMaxTaps * kRingWBytes;               // 72 KiB: 1024-aligned
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + kRingSlots * kRingSlotBytes);
-  uint64_t* empty_bar = full_bar + kRingSlots;
-  uint64_t* tfull_bar = empty_bar + kRingSlots;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint64_t* wfull_bar = tempty_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
-
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int R = p.strip_r, S = p.strip_s;
   const int CB = p.ring_cb > 1 ? p.ring_cb : 1;                    // 64-channel blocks per input pixel
+  const int SLOTS = p.ring_slots;
+  const uint32_t slot_bytes = static_cast<uint32_t>(((kTileM + S - 1) * 128 + 1023) & ~1023);
+  uint8_t* wsm = smem;                                             // R*S*CB x 8 KiB
+  uint8_t* ring = smem + R * S * CB * kRingWBytes;                 // 1024-aligned
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + SLOTS * slot_bytes);
+  uint64_t* empty_bar = full_bar + kRingMaxSlots;
+  uint64_t* tfull_bar = empty_bar + kRingMaxSlots;
+  uint64_t* tempty_bar = tfull_bar + NACC;
+  uint64_t* wfull_bar = tempty_bar + NACC;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
   const uint32_t strip_tx = static_cast<uint32_t>(kTileM + S - 1) * 128u;
+  // phase interleave: CTA b -> phase b % NPH, item sequence b / NPH, b / NPH + gridDim / NPH, ...
+  const int NPH = p.ring_phases > 1 ? p.ring_phases : 1;
+  const int ph = NPH > 1 ? static_cast<int>(blockIdx.x) % NPH : 0;
+  const int cta0 = static_cast<int>(blockIdx.x) / NPH;
+  const int cta_stride = static_cast<int>(gridDim.x) / NPH;
+  const int org_h = NPH > 1 ? p.ring_org_h[ph] : p.org_h;
+  const int org_w = NPH > 1 ? p.ring_org_w[ph] : p.org_w;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&p.tmA[1]);
     prefetch_tmap(&p.tmB);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kRingSlots; ++s) {
+    for (int s = 0; s < SLOTS; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < NACC; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 256);
     }
     mbar_init(wfull_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, 2 * BLOCK_N);
+  if (warp == 2) tmem_alloc(tmem_slot, NACC * BLOCK_N);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1026,24 +1120,25 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
       mbar_expect_tx(wfull_bar, static_cast<uint32_t>(R * S * CB) * kRingWBytes);
       for (int t = 0; t < R * S; ++t)
         for (int cb = 0; cb < CB; ++cb)
-          tma_load_2d(wsm + (t * CB + cb) * kRingWBytes, &p.tmB, wfull_bar, (p.ring_tap[t] * CB + cb) * kBlockK, 0);
+          tma_load_2d(wsm + (t * CB + cb) * kRingWBytes, &p.tmB, wfull_bar, (p.ring_tap[t] * CB + cb) * kBlockK,
+                      ph * p.b_row_per_phase);
     }
     __syncwarp();
-    uint32_t g = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    uint32_t slot = 0, sphase = 0;
+    for (int item = cta0; item < items; item += cta_stride) {
       int img, tw, h0, nrows;
       decode(item, img, tw, h0, nrows);
-      const int x0 = p.org_w + tw * kTileM;
-      const int y0 = p.org_h + h0;
+      const int x0 = org_w + tw * kTileM;
+      const int y0 = org_h + h0;
       const int nstrips = (nrows + R - 1) * CB;                    // ring entry = (input row, channel block)
-      for (int j = 0; j < nstrips; ++j, ++g) {
-        const uint32_t slot = g % kRingSlots;
-        mbar_wait(&empty_bar[slot], ((g / kRingSlots) & 1u) ^ 1u);
+      for (int j = 0; j < nstrips; ++j) {
+        mbar_wait(&empty_bar[slot], sphase ^ 1u);
         if (elect_one()) {
           mbar_expect_tx(&full_bar[slot], strip_tx);
-          tma_load_4d(ring + slot * kRingSlotBytes, &p.tmA[1], &full_bar[slot], (j % CB) * kBlockK, x0, y0 + j / CB, img);
+          tma_load_4d(ring + slot * slot_bytes, &p.tmA[1], &full_bar[slot], (j % CB) * kBlockK, x0, y0 + j / CB, img);
         }
         __syncwarp();
+        if (++slot == static_cast<uint32_t>(SLOTS)) { slot = 0; sphase ^= 1u; }
       }
     }
   } else if (warp == 1) {
@@ -1051,25 +1146,35 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
     mbar_wait(wfull_bar, 0);
     const uint32_t w_addr = smem_u32(wsm);
     const uint32_t ring_addr = smem_u32(ring);
-    uint32_t g0 = 0;
+    // ring entries are numbered g = 0, 1, ... in load order; entry g sits in slot g % SLOTS, pass g / SLOTS.
+    // g0 = first entry of the current item, kept as (slot, pass parity) to stay clear of divisions by SLOTS.
+    uint32_t g0s = 0, g0p = 0;
     int it = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    auto entry = [&](int off, uint32_t& sl, uint32_t& par) {      // entry g0 + off (off < 2 * SLOTS)
+      uint32_t x = g0s + static_cast<uint32_t>(off);
+      par = g0p;
+      while (x >= static_cast<uint32_t>(SLOTS)) { x -= SLOTS; par ^= 1u; }
+      sl = x;
+    };
+    for (int item = cta0; item < items; item += cta_stride) {
       int img, tw, h0, nrows;
       decode(item, img, tw, h0, nrows);
       for (int i = 0; i < nrows; ++i, ++it) {
-        const int as = it & 1;
-        mbar_wait(&tempty_bar[as], (((it >> 1) & 1) ^ 1u));
+        const int as = it % NACC;
+        mbar_wait(&tempty_bar[as], (((it / NACC) & 1) ^ 1u));
         for (int e = (i == 0 ? 0 : (R - 1) * CB); e < R * CB; ++e) {
-          const uint32_t g = g0 + i * CB + e;
-          mbar_wait(&full_bar[g % kRingSlots], (g / kRingSlots) & 1u);
+          uint32_t sl, par;
+          entry(e, sl, par);
+          mbar_wait(&full_bar[sl], par);
         }
         tc_fence_after();
         if (elect_one()) {
           const uint32_t d_tmem = tmem_base + as * BLOCK_N;
           for (int r = 0; r < R; ++r)
             for (int cb = 0; cb < CB; ++cb) {
-              const uint32_t g = g0 + (i + r) * CB + cb;
-              const uint32_t sa = ring_addr + (g % kRingSlots) * kRingSlotBytes;
+              uint32_t sl, par;
+              entry(r * CB + cb, sl, par);
+              const uint32_t sa = ring_addr + sl * slot_bytes;
               for (int s = 0; s < S; ++s) {
                 const uint64_t da = make_smem_desc(sa + s * 128, 0, 1024);      // s pixels into the strip
                 const uint64_t db = make_smem_desc(w_addr + ((r * S + s) * CB + cb) * kRingWBytes, 0, 1024);
@@ -1079,31 +1184,88 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
               }
             }
           // the first input row of this output row is dead now; after the item's last row so are the others
-          for (int cb = 0; cb < CB; ++cb) umma_commit(&empty_bar[(g0 + i * CB + cb) % kRingSlots]);
-          if (i == nrows - 1)
-            for (int e = CB; e < R * CB; ++e) umma_commit(&empty_bar[(g0 + i * CB + e) % kRingSlots]);
+          for (int e = 0; e < (i == nrows - 1 ? R * CB : CB); ++e) {
+            uint32_t sl, par;
+            entry(e, sl, par);
+            umma_commit(&empty_bar[sl]);
+          }
           umma_commit(&tfull_bar[as]);
         }
         __syncwarp();
+        // the next output row starts one input row (CB entries) further
+        g0s += CB;
+        if (g0s >= static_cast<uint32_t>(SLOTS)) { g0s -= SLOTS; g0p ^= 1u; }
       }
-      g0 += (nrows + R - 1) * CB;
+      // ... and the next item after the R - 1 rows the last output row still used
+      g0s += (R - 1) * CB;
+      while (g0s >= static_cast<uint32_t>(SLOTS)) { g0s -= SLOTS; g0p ^= 1u; }
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int half = (warp - 4) >> 2;                 // which half of the 64 columns
     const int c_begin = half * (BLOCK_N / 2), c_end = c_begin + BLOCK_N / 2;
     const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
+    // These layers are bound by the epilogue's instruction stream (ncu: the accumulator is already complete when
+    // an epilogue warp gets to it 93 % of the time, and one 32-column chunk of the generic epilogue costs ~1.9 us
+    // of dependent loads, mode dispatch and index arithmetic). The common case -- full 64-channel bf16 NHWC
+    // output, bias + ReLU / LeakyReLU / none, no second operand, no fused statistics -- gets a lean path: bias in
+    // registers for the whole kernel, pixel coordinates straight from the work item, the accumulator stage handed
+    // back as soon as it is in registers.
+    const bool lean = p.aux_mode == AUX_NONE && p.stat_out == nullptr && p.stat_z == nullptr && p.z_mask == 0 &&
+                      !p.out_f32 && p.o_sc == 1 && p.fold_c == 0 && p.n_valid == BLOCK_N && p.act != ACT_TANH;
+    float bias_r[BLOCK_N / 2];
+#pragma unroll
+    for (int j = 0; j < BLOCK_N / 2; ++j) bias_r[j] = (lean && p.bias != nullptr) ? __ldg(p.bias + c_begin + j) : 0.f;
+    __nv_bfloat16* const out_ph = reinterpret_cast<__nv_bfloat16*>(p.out) + p.o_ph[ph] + c_begin;
     int it = 0;
-    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    for (int item = cta0; item < items; item += cta_stride) {
       int img, tw, h0, nrows;
       decode(item, img, tw, h0, nrows);
+      const int ow = tw * kTileM + q * 32 + lane;
       for (int i = 0; i < nrows; ++i, ++it) {
-        const int as = it & 1;
-        // m-tile index in the generic numbering (TH = 1, TW = 128): (img, oh, tw)
-        const int mt = (img * p.tiles_h + (h0 + i)) * p.tiles_w + tw;
-        fprop_epilogue_tile<BLOCK_N>(p, mt, 0, tmem_base, as, (it >> 1) & 1, tfull_bar, q, lane, c_begin, c_end, alpha);
+        const int as = it % NACC;
+        const uint32_t aphase = (it / NACC) & 1;
+        // m-tile index in the generic numbering (TH = 1, TW = 128): (img, oh, tw), phase innermost
+        const int mt = ((img * p.tiles_h + (h0 + i)) * p.tiles_w + tw) * NPH + ph;
+        if (!lean) {
+          fprop_epilogue_at<BLOCK_N>(p, mt, ph, img, h0 + i, ow, 0, tmem_base, as, aphase, tfull_bar, q, lane, c_begin,
+                                     c_end, alpha);
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[as]);
+          continue;
+        }
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+        uint32_t r[BLOCK_N / 2];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c_begin, r);
+        tmem_ld_wait();
         tc_fence_before();
-        mbar_arrive(&tempty_bar[as]);
+        mbar_arrive(&tempty_bar[as]);                 // the accumulator is in registers
+        if (ow >= p.OW) continue;
+        float v[BLOCK_N / 2];
+#pragma unroll
+        for (int j = 0; j < BLOCK_N / 2; ++j) v[j] = fmaf(__uint_as_float(r[j]), alpha, bias_r[j]);
+        if (p.act == ACT_RELU) {
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 2; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
+        } else if (p.act == ACT_LRELU) {
+#pragma unroll
+          for (int j = 0; j < BLOCK_N / 2; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+        }
+        __nv_bfloat16* o = out_ph + img * p.o_sn + int64_t(h0 + i) * p.o_sh + int64_t(ow) * p.o_sw;
+#pragma unroll
+        for (int g = 0; g < BLOCK_N / 16; g += 2) {
+          uint4 a, b;
+          a.x = pack_bf16x2(v[8 * g], v[8 * g + 1]);
+          a.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+          a.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+          a.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+          b.x = pack_bf16x2(v[8 * g + 8], v[8 * g + 9]);
+          b.y = pack_bf16x2(v[8 * g + 10], v[8 * g + 11]);
+          b.z = pack_bf16x2(v[8 * g + 12], v[8 * g + 13]);
+          b.w = pack_bf16x2(v[8 * g + 14], v[8 * g + 15]);
+          stg256(o + 8 * g, a, b);
+        }
       }
     }
   }
@@ -1112,7 +1274,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BLOCK_N);
+    tmem_dealloc(tmem_base, NACC * BLOCK_N);
   }
 }
 
@@ -1532,6 +1694,8 @@ static cudaError_t launch_fprop_t(const FpropParams& p, int num_sms, cudaStream_
 }
 
 static bool g_pair_mode = true;
+static int g_ring_slots_cap = 0;      // test hook: > 0 caps the ring depth (8 = the fixed depth of earlier builds)
+void set_ring_slots_cap(int n) { g_ring_slots_cap = n; }
 void set_pair_mode(bool on) { g_pair_mode = on; }
 
 static cudaError_t launch_fprop2(const FpropParams& p, int num_sms, cudaStream_t stream) {
@@ -1609,28 +1773,42 @@ cudaError_t launch_rowfold(const RowfoldParams& p, int num_sms, cudaStream_t str
   const int items = p.n_img * p.tiles_w * p.chunks_h;
   const int grid = items < num_sms ? items : num_sms;
   if (grid <= 0) return cudaSuccess;
-  fprop_rowfold_kernel<<<grid, 256, kRfSmemBytes, stream>>>(p);
+  fprop_rowfold_kernel<<<grid, kRfThreads, kRfSmemBytes, stream>>>(p);
   count_launch(1);
   return cudaGetLastError();
 }
 
-cudaError_t launch_fprop_ring64(const FpropParams& p, int num_sms, cudaStream_t stream) {
+// Ring slots that fit next to the resident filter (0: the shape does not fit the ring kernel at all).
+int ring_slots_for(int R, int S, int cbs) {
+  if (R < 1 || S < 1 || R * S * cbs > kRingMaxTaps || R * S > 16) return 0;
+  const int room = kRingSmemMax - 1024 - kRingBarBytes - R * S * cbs * kRingWBytes;
+  int slots = room / ring_slot_bytes(S);
+  if (slots > kRingMaxSlots) slots = kRingMaxSlots;
+  return slots >= (R + 1) * cbs ? slots : 0;
+}
+
+cudaError_t launch_fprop_ring64(const FpropParams& p0, int num_sms, cudaStream_t stream) {
   static uint64_t attr_devs = 0;
   if (attr_needed(attr_devs)) {
     cudaError_t e = cudaFuncSetAttribute(fprop_ring64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         kRingSmemBytes);
+                                         kRingSmemMax);
     if (e != cudaSuccess) return e;
     attr_done(attr_devs);
   }
+  FpropParams p = p0;
   const int cbs = p.ring_cb > 1 ? p.ring_cb : 1;
-  if (p.strip_r < 1 || p.strip_s < 1 || p.strip_r * p.strip_s * cbs > kRingMaxTaps || p.strip_r * p.strip_s > 16 ||
-      (p.strip_r + 1) * cbs > kRingSlots || (kTileM + p.strip_s - 1) * 128 > kRingSlotBytes || p.TW != kTileM ||
-      p.TH != 1 || p.phases != 1 || p.n_blocks != 1)
+  const int nph = p.ring_phases > 1 ? p.ring_phases : 1;
+  const int slots = ring_slots_for(p.strip_r, p.strip_s, cbs);
+  if (slots == 0 || p.TW != kTileM || p.TH != 1 || p.phases != nph || (nph != 1 && nph != 4) || p.n_blocks != 1)
     return cudaErrorInvalidValue;
+  p.ring_slots = g_ring_slots_cap > 0 && g_ring_slots_cap < slots ? g_ring_slots_cap : slots;
+  if (p.ring_slots < (p.strip_r + 1) * cbs) p.ring_slots = (p.strip_r + 1) * cbs;
   const int items = p.n_img * p.tiles_w * p.ring_chunks;
-  const int grid = items < num_sms ? items : num_sms;
+  int grid = items * nph < num_sms ? items * nph : num_sms / nph * nph;
   if (grid <= 0) return cudaSuccess;
-  fprop_ring64_kernel<<<grid, kFpropThreads, kRingSmemBytes, stream>>>(p);
+  const int smem_bytes = p.strip_r * p.strip_s * cbs * kRingWBytes + p.ring_slots * ring_slot_bytes(p.strip_s) + 1024 +
+                         kRingBarBytes;
+  fprop_ring64_kernel<<<grid, kFpropThreads, smem_bytes, stream>>>(p);
   count_launch(1);
   return cudaGetLastError();
 }

@@ -43,6 +43,9 @@ struct FpropParams {
   int32_t org_h, org_w;           // ring kernel: input coordinate read by output (0,0) through tap (0,0)
   int32_t ring_cb;                // ring kernel: 64-channel blocks of the input (1 or 2; 0 means 1)
   int8_t ring_tap[16];            // ring kernel: filter position (r*S + s) -> tap index in the packed weights
+  int32_t ring_slots;             // ring kernel: strips resident in shared memory (set by the launcher)
+  int32_t ring_phases;            // ring kernel: 0/1, or 4 = CTA b runs output phase b % 4 (`phases` must be 4 too):
+  int8_t ring_org_h[4], ring_org_w[4];   //   per-phase org_h / org_w; weights of phase ph start at B row ph*b_row_per_phase
   int32_t OH, OW, TH, TW;         // output plane and the 128-pixel tile (TH*TW == 128)
   int32_t tiles_h, tiles_w, n_img, n_blocks;
   // epilogue
@@ -68,6 +71,12 @@ struct FpropParams {
   // ReLU mask taken from a SECOND operand next to an additive aux (Gram backward + the ReLU backward of the
   // tapped feature map, losses.py:70-89 with the ReLUs of the VGG stack).
   int32_t z_mask;
+  // mask_scale / mask_shift (fp32 [image][mask_ld], both or neither): with aux_mode = AUX_RELU_MASK / AUX_LRELU_MASK
+  // the mask is act'(stat_z * scale + shift) -- recomputed from the norm INPUT z the reductions read anyway and
+  // the per-(image, channel) scale / shift of its InstanceNorm / AdaIN -- and `aux` is not read at all.
+  const float* mask_scale;
+  const float* mask_shift;
+  int32_t mask_ld;
   // m2 = 1: run on fprop_m2_kernel -- one CTA computes TWO vertically adjacent 128-pixel m-tiles (2*th, 2*th+1)
   // against the same weight tile; tmA maps then carry a {64, TW, 2*TH} box (see fprop_uses_m2).
   int32_t m2;
@@ -131,6 +140,8 @@ struct RowfoldParams {
 cudaError_t launch_fprop(const FpropParams& p, int block_n, int num_sms, cudaStream_t stream);
 cudaError_t launch_rowfold(const RowfoldParams& p, int num_sms, cudaStream_t stream);
 cudaError_t launch_fprop_ring64(const FpropParams& p, int num_sms, cudaStream_t stream);
+int ring_slots_for(int R, int S, int cbs);   // ring depth the shape gets (0: does not fit the ring kernel)
+void set_ring_slots_cap(int n);              // test hook: > 0 caps the ring depth
 cudaError_t launch_wgrad(const WgradParams& p, int block_n, cudaStream_t stream);
 bool fprop_uses_pairs(const FpropParams& p, int block_n);
 bool fprop_uses_m2(const FpropParams& p, int block_n);   // call with tiles / phases / taps / n_blocks already set

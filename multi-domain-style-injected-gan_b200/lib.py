@@ -30,7 +30,7 @@ class Epilogue(Structure):
     _fields_ = [("bias", c_void_p), ("aux", c_void_p), ("aux_mode", c_int32), ("act", c_int32),
                 ("alpha", c_float), ("alpha_ptr", c_void_p), ("slope", c_float),
                 ("out_layout", c_int32), ("stats_partial", c_void_p), ("stats_z", c_void_p),
-                ("ch_scale", c_void_p)]
+                ("ch_scale", c_void_p), ("mask_scale", c_void_p), ("mask_shift", c_void_p)]
 
 
 class WpackDesc(Structure):

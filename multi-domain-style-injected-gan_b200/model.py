@@ -259,7 +259,8 @@ class _ResBlockFn(torch.autograd.Function):
         if ops.epi_fusable(9, c):
             es = ops.epi_stats(B, g3.h, g3.w, c, dout.device)
             dh = ops.conv2d_dgrad(dzb, P["w1_d"], g3,
-                                  ops.epilogue(aux=S["ha"], aux_mode=AUX_RELU_MASK, stats=es, stats_z=S["za"]))
+                                  ops.epilogue(aux=S["ha"], aux_mode=AUX_RELU_MASK, stats=es, stats_z=S["za"],
+                                               mask_norm=S["sta"]))
             dza = ops.norm_bwd_from(es, dh, S["za"], S["sta"], dgamma=dgb[:, 0:], dbeta=dgb[:, c:], dgb_stride=2 * c2)
         else:
             dh = ops.conv2d_dgrad(dzb, P["w1_d"], g3)
@@ -496,7 +497,8 @@ class _GeneratorFn(torch.autograd.Function):
         gu2, gu1 = S["gu2"], S["gu1"]
         es = ops.epi_stats(B, gu2.h, gu2.w, gu2.c, dev)
         dy = ops.convT2d_dgrad(dzu2, P["u2_d"], gu2,
-                               ops.epilogue(aux=S["yu1"], aux_mode=AUX_RELU_MASK, stats=es, stats_z=S["zu1"]))
+                               ops.epilogue(aux=S["yu1"], aux_mode=AUX_RELU_MASK, stats=es, stats_z=S["zu1"],
+                                            mask_norm=S["stu1"]))
         del dzu2
         # ---- up 1 (ConvTranspose 256->128 + IN + ReLU)
         _trace(mod, "dyu1", dy)
@@ -524,7 +526,7 @@ class _GeneratorFn(torch.autograd.Function):
                 ops.conv2d_wgrad(ha, dzb, g3, _grad_buf(blk.conv2.weight))
             es = ops.epi_stats(B, h4, w4, 256, dev)
             dh = ops.conv2d_dgrad(dzb, P[f"r{i}1_d"], g3,
-                                  ops.epilogue(aux=ha, aux_mode=AUX_RELU_MASK, stats=es, stats_z=za))
+                                  ops.epilogue(aux=ha, aux_mode=AUX_RELU_MASK, stats=es, stats_z=za, mask_norm=sta))
             dza = ops.norm_bwd_from(es, dh, za, sta, dgamma=dgb[:, l * 512:], dbeta=dgb[:, l * 512 + 256:],
                                     dgb_stride=nl * 512)
             _trace(mod, f"res{i}", (dy, dzb, dh, dza))       # (dy into the block, dz conv2, dh, dz conv1)
@@ -548,7 +550,8 @@ class _GeneratorFn(torch.autograd.Function):
         g2, g1 = S["g2"], S["g1"]
         es = ops.epi_stats(B, g2.oh, g2.ow, g2.c, dev, phases=4)
         dy = ops.conv2d_dgrad(dz2, P["e2_d"], g2,
-                              ops.epilogue(aux=S["y1"], aux_mode=AUX_RELU_MASK, stats=es, stats_z=S["z1"]))
+                              ops.epilogue(aux=S["y1"], aux_mode=AUX_RELU_MASK, stats=es, stats_z=S["z1"],
+                                           mask_norm=S["st1"]))
         del dz2
         _trace(mod, "dy1", dy)
         dz1 = ops.norm_bwd_from(es, dy, S["z1"], S["st1"])
@@ -860,7 +863,7 @@ class _DiscriminatorFn(torch.autograd.Function):
                 es = ops.epi_stats(B, g.oh, g.ow, g.c, dev, phases=4)
                 dy = ops.conv2d_dgrad(dz, P[f"c{j}_d"], g,
                                       ops.epilogue(aux=y_in, aux_mode=AUX_LRELU_MASK, stats=es,
-                                                   stats_z=S["layers"][j - 2][2]))
+                                                   stats_z=S["layers"][j - 2][2], mask_norm=S["layers"][j - 2][3]))
             else:   # dgrad fused with LeakyReLU' of the first layer's output
                 dy = ops.conv2d_dgrad(dz, P[f"c{j}_d"], g, ops.epilogue(aux=S["y0"], aux_mode=AUX_LRELU_MASK))
             _trace(mod, f"dy{j - 1}", dy)

@@ -56,6 +56,8 @@ def ensure_init(device=None):
         import os
         if os.environ.get("MSIG_M2", "1") == "0":
             L.call("msig_debug_set_m2_mode", 0)
+        if "MSIG_RING_MODE" in os.environ:
+            L.call("msig_debug_set_ring_mode", int(os.environ["MSIG_RING_MODE"], 0))
         if "MSIG_WGRAD_MODE" in os.environ:
             L.call("msig_debug_set_wgrad_mode", int(os.environ["MSIG_WGRAD_MODE"]))
     return lib
@@ -82,13 +84,22 @@ def conv_geom(n, h, w, c, k, r, s, stride, pad_t, pad_l, oh, ow):
     return ConvGeom(n, h, w, c, k, r, s, stride, pad_t, pad_l, oh, ow)
 
 
+MASK_FROM_Z = __import__('os').environ.get('MSIG_MASK_FROM_Z', '1') != '0'     # A/B switch, default on
+
+
 def epilogue(bias=None, aux=None, aux_mode=AUX_NONE, act=ACT_NONE, alpha=1.0, alpha_ptr=None,
-             slope=0.2, out_layout=OUT_BF16_NHWC, stats=None, stats_z=None, ch_scale=None):
+             slope=0.2, out_layout=OUT_BF16_NHWC, stats=None, stats_z=None, ch_scale=None, mask_norm=None):
     """`stats`: an EpiStats buffer that receives the per-(image, channel) partial sums of the stored
-    output (sum v, sum v*v, or sum v*z when `stats_z` is given) from the GEMM epilogue."""
+    output (sum v, sum v*v, or sum v*z when `stats_z` is given) from the GEMM epilogue.
+    `mask_norm`: the NormStats of the norm whose INPUT is `stats_z`; with a ReLU / LeakyReLU mask mode the
+    mask is then act'(stats_z * scale + shift) and the saved activation `aux` is not read."""
+    if mask_norm is not None and stats_z is not None and MASK_FROM_Z and aux_mode in (AUX_RELU_MASK, AUX_LRELU_MASK):
+        return Epilogue(_p(bias), None, aux_mode, act, alpha, _p(alpha_ptr), slope, out_layout,
+                        _p(None if stats is None else stats.buf), _p(stats_z), _p(ch_scale),
+                        _p(mask_norm.scale), _p(mask_norm.shift))
     return Epilogue(_p(bias), _p(aux), aux_mode if aux is not None else AUX_NONE, act, alpha,
                     _p(alpha_ptr), slope, out_layout, _p(None if stats is None else stats.buf), _p(stats_z),
-                    _p(ch_scale))
+                    _p(ch_scale), None, None)
 
 
 # The epilogue-fused reductions cost ~900 cycles per 64 accumulator columns per tile; they are hidden

@@ -73,6 +73,36 @@ def case_conv_dgrad(n, c, h, w, k, r, stride, pad, seed=0):
     return rel_err(nchw(dx), ref), 1e-2
 
 
+def case_dgrad_mask_from_z(n, c, h, w, k, r, stride, pad, act, seed=0):
+    """dgrad epilogue with the activation mask recomputed from the norm input z (mask_scale / mask_shift) against
+    the same launch reading the saved activation: outputs and the fused reductions must be bit-identical."""
+    ops.ensure_init()
+    oh = (h + 2 * pad - r) // stride + 1
+    ow = (w + 2 * pad - r) // stride + 1
+    dy = nhwc(_bf(_rand((n, k, oh, ow), seed)).to(DEV))
+    wt = _bf(_rand((k, c, r, r), seed + 1, 1.0 / (k * r * r) ** 0.5)).to(DEV)
+    wpk = ops.wpack(L.WPACK_DGRAD_S1 if stride == 1 else L.WPACK_DGRAD_S2, wt.float().contiguous(), k, c, r, r)
+    g = ops.conv_geom(n, h, w, c, k, r, r, stride, pad, pad, oh, ow)
+    z = nhwc(_bf(_rand((n, c, h, w), seed + 2)).to(DEV))
+    st = ops.in_stats(z, gamma=_rand((n, c), seed + 3).to(DEV), beta=0.3 * _rand((n, c), seed + 4).to(DEV), gb_stride=c)
+    y = ops.norm_act_fwd(z, st, act)
+    mode = L.AUX_RELU_MASK if act == L.ACT_RELU else L.AUX_LRELU_MASK
+    outs = []
+    for use_z in (False, True):
+        es = ops.epi_stats(n, oh if stride == 2 else h, ow if stride == 2 else w, c, DEV, phases=4 if stride == 2 else 1)
+        es.buf.zero_()
+        e = ops.epilogue(aux=y, aux_mode=mode, stats=es, stats_z=z, mask_norm=st if use_z else None)
+        assert (e.mask_scale is not None) == use_z and (e.aux is None) == use_z
+        dx = ops.conv2d_dgrad(dy, wpk, g, e)
+        torch.cuda.synchronize()
+        outs.append((dx.clone(), es.buf.clone()))
+    ref = torch.nn.grad.conv2d_input((n, c, h, w), wt.float(), nchw(dy).float(), stride=stride, padding=pad)
+    yf = nchw(y).float()
+    ref = ref * torch.where(yf > 0, torch.ones_like(yf), torch.full_like(yf, 0.0 if act == L.ACT_RELU else 0.2))
+    same = torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    return (rel_err(nchw(outs[1][0]), ref) if same else 1.0), 1e-2
+
+
 def case_conv_wgrad(n, c, h, w, k, r, stride, pad, seed=0):
     ops.ensure_init()
     oh = (h + 2 * pad - r) // stride + 1
@@ -92,7 +122,7 @@ def _wgrad_mode(mask):
     L.call("msig_debug_set_wgrad_mode", mask)
 
 
-def case_convT(n, c, h, w, k, seed=0, which="fwd", wgrad_mode=3):
+def case_convT(n, c, h, w, k, seed=0, which="fwd", wgrad_mode=3, ring_mode=3):
     ops.ensure_init()
     x = _bf(_rand((n, c, h, w), seed)).to(DEV)
     wt = _bf(_rand((c, k, 4, 4), seed + 1, 1.0 / (c * 4) ** 0.5)).to(DEV)   # ConvTranspose2d layout [in, out, 4, 4]
@@ -100,7 +130,11 @@ def case_convT(n, c, h, w, k, seed=0, which="fwd", wgrad_mode=3):
     if which == "fwd":
         ref = F.conv_transpose2d(x.float(), wt.float(), None, stride=2, padding=1)
         wpk = ops.wpack(L.WPACK_CONVT_FWD, wt.float().contiguous(), k, c, 4, 4)
-        y = ops.convT2d_fwd(nhwc(x), wpk, g)
+        L.call("msig_debug_set_ring_mode", ring_mode)
+        try:
+            y = ops.convT2d_fwd(nhwc(x), wpk, g)
+        finally:
+            L.call("msig_debug_set_ring_mode", 3)
         torch.cuda.synchronize()
         return rel_err(nchw(y), ref), 1e-2
     dy = _bf(_rand((n, k, 2 * h, 2 * w), seed + 2)).to(DEV)
@@ -373,12 +407,18 @@ CASES = {
     "fwd_1x1_gemm": lambda: case_gemm(200, 256, 512),
     "fwd_gemm_small_rows_f32": lambda: case_gemm(4, 512, 2560, f32_out=True),
     "dgrad_3x3_256": lambda: case_conv_dgrad(2, 256, 64, 64, 256, 3, 1, 1),
+    "dgrad_3x3_256_mask_from_z": lambda: case_dgrad_mask_from_z(2, 256, 64, 64, 256, 3, 1, 1, L.ACT_RELU),
+    "dgrad_4x4s2_128_256_lrelu_mask_from_z": lambda: case_dgrad_mask_from_z(2, 128, 64, 64, 256, 4, 2, 1, L.ACT_LRELU, seed=4),
+    "dgrad_4x4s2_64_128_mask_from_z": lambda: case_dgrad_mask_from_z(1, 64, 128, 128, 128, 4, 2, 1, L.ACT_RELU, seed=6),
     "dgrad_4x4s2_128_256": lambda: case_conv_dgrad(2, 128, 64, 64, 256, 4, 2, 1),
     "dgrad_4x4s2_64_128_w128": lambda: case_conv_dgrad(1, 64, 256, 256, 128, 4, 2, 1),
     "convT_fwd_256_128": lambda: case_convT(2, 256, 32, 32, 128, which="fwd"),
     "convT_fwd_128_64": lambda: case_convT(1, 128, 64, 64, 64, which="fwd"),
     "convT_fwd_128_64_w128_ring": lambda: case_convT(2, 128, 24, 128, 64, which="fwd"),
     "convT_fwd_128_64_w256_ring": lambda: case_convT(1, 128, 10, 256, 64, which="fwd"),
+    "convT_fwd_128_64_ring_b5_ragged": lambda: case_convT(5, 128, 37, 200, 64, which="fwd", seed=11),
+    "convT_fwd_128_64_ring_phase_launches": lambda: case_convT(2, 128, 24, 128, 64, which="fwd", ring_mode=1),
+    "convT_fwd_128_64_ring_depth8": lambda: case_convT(2, 128, 24, 128, 64, which="fwd", ring_mode=3 | (8 << 8)),
     "dgrad_4x4s2_64_128_ring_b2": lambda: case_conv_dgrad(2, 64, 40, 256, 128, 4, 2, 1),
     "convT_dgrad_256_128": lambda: case_convT(2, 256, 32, 32, 128, which="dgrad"),
     "wgrad_3x3_256": lambda: case_conv_wgrad(2, 256, 64, 64, 256, 3, 1, 1),
