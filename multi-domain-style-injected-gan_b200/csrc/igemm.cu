@@ -366,6 +366,49 @@ __device__ __forceinline__ void fprop_epilogue_at(const FpropParams& p, int mt_f
   }
 }
 
+// Lean epilogue of the 64-wide tiles for the common case (see epilogue_is_lean): NC accumulator columns of one
+// output pixel -> alpha * acc + bias -> ReLU / LeakyReLU / none -> bf16, 32-byte stores. The accumulator stage is
+// handed back as soon as it sits in registers. `bias_r` stays in registers for the whole kernel.
+__device__ __forceinline__ bool epilogue_is_lean(const FpropParams& p, int block_n) {
+  return p.aux_mode == AUX_NONE && p.stat_out == nullptr && p.stat_z == nullptr && p.z_mask == 0 && !p.out_f32 &&
+         p.o_sc == 1 && p.fold_c == 0 && p.n_valid == block_n && p.n_blocks == 1 && p.act != ACT_TANH;
+}
+template <int NC>
+__device__ __forceinline__ void epilogue_lean(const FpropParams& p, const float (&bias_r)[NC], float alpha, uint32_t taddr,
+                                              uint64_t* tempty, bool store, __nv_bfloat16* o) {
+  static_assert(NC == 32, "one tcgen05.ld.32x32b.x32 per call");
+  tc_fence_after();
+  uint32_t r[NC];
+  tmem_ld_32x32(taddr, r);
+  tmem_ld_wait();
+  tc_fence_before();
+  mbar_arrive(tempty);                            // the accumulator is in registers
+  if (!store) return;
+  float v[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) v[j] = fmaf(__uint_as_float(r[j]), alpha, bias_r[j]);
+  if (p.act == ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
+  } else if (p.act == ACT_LRELU) {
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
+  }
+#pragma unroll
+  for (int g = 0; g < NC / 8; g += 2) {
+    uint4 a, b;
+    a.x = pack_bf16x2(v[8 * g], v[8 * g + 1]);
+    a.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
+    a.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
+    a.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
+    b.x = pack_bf16x2(v[8 * g + 8], v[8 * g + 9]);
+    b.y = pack_bf16x2(v[8 * g + 10], v[8 * g + 11]);
+    b.z = pack_bf16x2(v[8 * g + 12], v[8 * g + 13]);
+    b.w = pack_bf16x2(v[8 * g + 14], v[8 * g + 15]);
+    stg256(o + 8 * g, a, b);
+  }
+}
+
 // 12 warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 idle, 4..11 = epilogue. The two
 // epilogue warps of a TMEM lane quadrant (warp % 4) split the accumulator columns in halves.
 constexpr int kFpropThreads = 384;
@@ -493,7 +536,31 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_kernel(const __grid_co
     const int c_begin = Cfg::kAltTiles ? 0 : half * kHalfCols, c_end = c_begin + kHalfCols;
     const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
     int it = 0;
-    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+    if constexpr (BLOCK_N == 64) {
+      // 64-wide tiles with a short K (the first layers of SE / D: K = 64) are bound by the epilogue: lean path
+      if (epilogue_is_lean(p, BLOCK_N) && p.phases == 1) {
+        float bias_r[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) bias_r[j] = p.bias != nullptr ? __ldg(p.bias + c_begin + j) : 0.f;
+        const int row = q * 32 + lane;
+        const int dh = row / p.TW, dw = row % p.TW;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+          const int as = it % NACC;
+          int mt = tile;
+          const int tw = mt % p.tiles_w;
+          mt /= p.tiles_w;
+          const int th = mt % p.tiles_h;
+          const int img = mt / p.tiles_h;
+          const int oh = th * p.TH + dh, ow = tw * p.TW + dw;
+          __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + img * p.o_sn + oh * p.o_sh + ow * p.o_sw + c_begin;
+          mbar_wait(&tfull_bar[as], (it / NACC) & 1);
+          epilogue_lean<32>(p, bias_r, alpha, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c_begin,
+                            &tempty_bar[as], oh < p.OH && ow < p.OW, o);
+        }
+        it = -1;
+      }
+    }
+    for (int tile = blockIdx.x; it >= 0 && tile < total; tile += gridDim.x, ++it) {
       if (Cfg::kAltTiles && (it & 1) != half) continue;
       const int as = it % NACC;
       const uint32_t aphase = (it / NACC) & 1;
@@ -1046,6 +1113,18 @@ __global__ void __launch_bounds__(kRfThreads, 1) fprop_rowfold_kernel(const __gr
 // The ring takes whatever shared memory the resident filter leaves (ring_slots, up to 16): with R = 7 input rows
 // in use per output row (row-patch convs) the look-ahead is what hides the strip latency.
 // L2 traffic per 128-pixel tile drops from R*S*24 KiB to ~17 KiB. Epilogue = the generic one (BLOCK_N = 64).
+#ifdef MSIG_RING_PROFILE
+// Probe build only (make PROF=1 -> libmsig_prof.so): cycles per role, summed over CTAs.
+//  [0] MMA warp: wait tempty  [1] wait strips  [2] issue + commit  [3] tiles
+//  [4] epilogue warp 4: wait tfull  [5] tcgen05.ld  [6] math + stores  [7] tiles
+//  [8] producer: wait empty slot  [9] strips   [10] kernel cycles (CTA 0)
+__device__ unsigned long long g_ring_prof[16];
+#define RING_PROF_T(var) const long long var = clock64()
+#define RING_PROF_ADD(acc, a, b) acc += (b) - (a)
+#else
+#define RING_PROF_T(var)
+#define RING_PROF_ADD(acc, a, b)
+#endif
 constexpr int kRingMaxSlots = 16;
 constexpr int kRingMaxTaps = 9;                    // resident [64][64] filter tiles (R * S * channel blocks)
 constexpr int kRingWBytes = 64 * 128;              // one tap: 64 output channels x 64 K
@@ -1125,6 +1204,10 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
     }
     __syncwarp();
     uint32_t slot = 0, sphase = 0;
+#ifdef MSIG_RING_PROFILE
+    long long pw = 0, pn = 0;
+    const long long k0 = clock64();
+#endif
     for (int item = cta0; item < items; item += cta_stride) {
       int img, tw, h0, nrows;
       decode(item, img, tw, h0, nrows);
@@ -1132,7 +1215,13 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
       const int y0 = org_h + h0;
       const int nstrips = (nrows + R - 1) * CB;                    // ring entry = (input row, channel block)
       for (int j = 0; j < nstrips; ++j) {
+        RING_PROF_T(t0);
         mbar_wait(&empty_bar[slot], sphase ^ 1u);
+        RING_PROF_T(t1);
+        RING_PROF_ADD(pw, t0, t1);
+#ifdef MSIG_RING_PROFILE
+        ++pn;
+#endif
         if (elect_one()) {
           mbar_expect_tx(&full_bar[slot], strip_tx);
           tma_load_4d(ring + slot * slot_bytes, &p.tmA[1], &full_bar[slot], (j % CB) * kBlockK, x0, y0 + j / CB, img);
@@ -1141,6 +1230,13 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
         if (++slot == static_cast<uint32_t>(SLOTS)) { slot = 0; sphase ^= 1u; }
       }
     }
+#ifdef MSIG_RING_PROFILE
+    if (lane == 0) {
+      atomicAdd(&g_ring_prof[8], static_cast<unsigned long long>(pw));
+      atomicAdd(&g_ring_prof[9], static_cast<unsigned long long>(pn));
+      if (blockIdx.x == 0) atomicAdd(&g_ring_prof[10], static_cast<unsigned long long>(clock64() - k0));
+    }
+#endif
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc_bf16(kTileM, BLOCK_N, 0, 0);
     mbar_wait(wfull_bar, 0);
@@ -1150,6 +1246,9 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
     // g0 = first entry of the current item, kept as (slot, pass parity) to stay clear of divisions by SLOTS.
     uint32_t g0s = 0, g0p = 0;
     int it = 0;
+#ifdef MSIG_RING_PROFILE
+    long long m_te = 0, m_fu = 0, m_is = 0;
+#endif
     auto entry = [&](int off, uint32_t& sl, uint32_t& par) {      // entry g0 + off (off < 2 * SLOTS)
       uint32_t x = g0s + static_cast<uint32_t>(off);
       par = g0p;
@@ -1161,12 +1260,17 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
       decode(item, img, tw, h0, nrows);
       for (int i = 0; i < nrows; ++i, ++it) {
         const int as = it % NACC;
+        RING_PROF_T(t0);
         mbar_wait(&tempty_bar[as], (((it / NACC) & 1) ^ 1u));
+        RING_PROF_T(t1);
         for (int e = (i == 0 ? 0 : (R - 1) * CB); e < R * CB; ++e) {
           uint32_t sl, par;
           entry(e, sl, par);
           mbar_wait(&full_bar[sl], par);
         }
+        RING_PROF_T(t2);
+        RING_PROF_ADD(m_te, t0, t1);
+        RING_PROF_ADD(m_fu, t1, t2);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t d_tmem = tmem_base + as * BLOCK_N;
@@ -1192,6 +1296,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
           umma_commit(&tfull_bar[as]);
         }
         __syncwarp();
+        RING_PROF_T(t3);
+        RING_PROF_ADD(m_is, t2, t3);
         // the next output row starts one input row (CB entries) further
         g0s += CB;
         if (g0s >= static_cast<uint32_t>(SLOTS)) { g0s -= SLOTS; g0p ^= 1u; }
@@ -1200,24 +1306,34 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
       g0s += (R - 1) * CB;
       while (g0s >= static_cast<uint32_t>(SLOTS)) { g0s -= SLOTS; g0p ^= 1u; }
     }
+#ifdef MSIG_RING_PROFILE
+    if (lane == 0) {
+      atomicAdd(&g_ring_prof[0], static_cast<unsigned long long>(m_te));
+      atomicAdd(&g_ring_prof[1], static_cast<unsigned long long>(m_fu));
+      atomicAdd(&g_ring_prof[2], static_cast<unsigned long long>(m_is));
+      atomicAdd(&g_ring_prof[3], static_cast<unsigned long long>(it));
+    }
+#endif
   } else if (warp >= 4) {
     const int q = warp & 3;
     const int half = (warp - 4) >> 2;                 // which half of the 64 columns
     const int c_begin = half * (BLOCK_N / 2), c_end = c_begin + BLOCK_N / 2;
     const float alpha = p.alpha_ptr ? p.alpha * __ldg(p.alpha_ptr) : p.alpha;
-    // These layers are bound by the epilogue's instruction stream (ncu: the accumulator is already complete when
-    // an epilogue warp gets to it 93 % of the time, and one 32-column chunk of the generic epilogue costs ~1.9 us
-    // of dependent loads, mode dispatch and index arithmetic). The common case -- full 64-channel bf16 NHWC
-    // output, bias + ReLU / LeakyReLU / none, no second operand, no fused statistics -- gets a lean path: bias in
-    // registers for the whole kernel, pixel coordinates straight from the work item, the accumulator stage handed
-    // back as soon as it is in registers.
-    const bool lean = p.aux_mode == AUX_NONE && p.stat_out == nullptr && p.stat_z == nullptr && p.z_mask == 0 &&
-                      !p.out_f32 && p.o_sc == 1 && p.fold_c == 0 && p.n_valid == BLOCK_N && p.act != ACT_TANH;
+    // Cycle counters (make PROF=1, profiles/probe/ring_profile.py) put the bound of these layers on the MMA warp:
+    // ~60 cycles per 128 x 64 x 16 MMA (the N = 64 instruction moves 6 KiB of shared-memory operands for 32 cycles
+    // of math), 2.0-2.2 k cycles per tile against ~1 k for the lean epilogue below and ~3.4 k for the generic one.
+    // Lean path = the common case (full 64-channel bf16 NHWC output, bias + ReLU / LeakyReLU / none, no second
+    // operand, no fused statistics): bias in registers for the whole kernel, pixel coordinates straight from the
+    // work item, the accumulator stage handed back as soon as it is in registers.
+    const bool lean = epilogue_is_lean(p, BLOCK_N);
     float bias_r[BLOCK_N / 2];
 #pragma unroll
     for (int j = 0; j < BLOCK_N / 2; ++j) bias_r[j] = (lean && p.bias != nullptr) ? __ldg(p.bias + c_begin + j) : 0.f;
     __nv_bfloat16* const out_ph = reinterpret_cast<__nv_bfloat16*>(p.out) + p.o_ph[ph] + c_begin;
     int it = 0;
+#ifdef MSIG_RING_PROFILE
+    long long e_w = 0, e_ld = 0, e_m = 0;
+#endif
     for (int item = cta0; item < items; item += cta_stride) {
       int img, tw, h0, nrows;
       decode(item, img, tw, h0, nrows);
@@ -1234,40 +1350,27 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
           mbar_arrive(&tempty_bar[as]);
           continue;
         }
+        RING_PROF_T(t0);
         mbar_wait(&tfull_bar[as], aphase);
-        tc_fence_after();
-        uint32_t r[BLOCK_N / 2];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c_begin, r);
-        tmem_ld_wait();
-        tc_fence_before();
-        mbar_arrive(&tempty_bar[as]);                 // the accumulator is in registers
-        if (ow >= p.OW) continue;
-        float v[BLOCK_N / 2];
-#pragma unroll
-        for (int j = 0; j < BLOCK_N / 2; ++j) v[j] = fmaf(__uint_as_float(r[j]), alpha, bias_r[j]);
-        if (p.act == ACT_RELU) {
-#pragma unroll
-          for (int j = 0; j < BLOCK_N / 2; ++j) v[j] = v[j] > 0.f ? v[j] : 0.f;
-        } else if (p.act == ACT_LRELU) {
-#pragma unroll
-          for (int j = 0; j < BLOCK_N / 2; ++j) v[j] = v[j] > 0.f ? v[j] : v[j] * p.slope;
-        }
+        RING_PROF_T(t1);
         __nv_bfloat16* o = out_ph + img * p.o_sn + int64_t(h0 + i) * p.o_sh + int64_t(ow) * p.o_sw;
-#pragma unroll
-        for (int g = 0; g < BLOCK_N / 16; g += 2) {
-          uint4 a, b;
-          a.x = pack_bf16x2(v[8 * g], v[8 * g + 1]);
-          a.y = pack_bf16x2(v[8 * g + 2], v[8 * g + 3]);
-          a.z = pack_bf16x2(v[8 * g + 4], v[8 * g + 5]);
-          a.w = pack_bf16x2(v[8 * g + 6], v[8 * g + 7]);
-          b.x = pack_bf16x2(v[8 * g + 8], v[8 * g + 9]);
-          b.y = pack_bf16x2(v[8 * g + 10], v[8 * g + 11]);
-          b.z = pack_bf16x2(v[8 * g + 12], v[8 * g + 13]);
-          b.w = pack_bf16x2(v[8 * g + 14], v[8 * g + 15]);
-          stg256(o + 8 * g, a, b);
-        }
+        epilogue_lean<BLOCK_N / 2>(p, bias_r, alpha, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c_begin,
+                                   &tempty_bar[as], ow < p.OW, o);
+        RING_PROF_T(t2);
+        RING_PROF_ADD(e_w, t0, t1);
+        RING_PROF_ADD(e_ld, t1, t2);
+        RING_PROF_T(t3);
+        RING_PROF_ADD(e_m, t2, t3);
       }
     }
+#ifdef MSIG_RING_PROFILE
+    if (warp == 4 && lane == 0) {
+      atomicAdd(&g_ring_prof[4], static_cast<unsigned long long>(e_w));
+      atomicAdd(&g_ring_prof[5], static_cast<unsigned long long>(e_ld));
+      atomicAdd(&g_ring_prof[6], static_cast<unsigned long long>(e_m));
+      atomicAdd(&g_ring_prof[7], static_cast<unsigned long long>(it));
+    }
+#endif
   }
 
   tc_fence_before();
@@ -1777,6 +1880,15 @@ cudaError_t launch_rowfold(const RowfoldParams& p, int num_sms, cudaStream_t str
   count_launch(1);
   return cudaGetLastError();
 }
+
+#ifdef MSIG_RING_PROFILE
+extern "C" int msig_debug_ring_profile(unsigned long long* out16, int reset) {
+  unsigned long long z[16] = {0};
+  if (out16 && cudaMemcpyFromSymbol(out16, g_ring_prof, sizeof(z)) != cudaSuccess) return -1;
+  if (reset && cudaMemcpyToSymbol(g_ring_prof, z, sizeof(z)) != cudaSuccess) return -1;
+  return 0;
+}
+#endif
 
 // Ring slots that fit next to the resident filter (0: the shape does not fit the ring kernel at all).
 int ring_slots_for(int R, int S, int cbs) {

@@ -10,7 +10,7 @@ from ctypes import (POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int
                     c_size_t, c_void_p)
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmsig.so")
+LIB_PATH = os.environ.get("MSIG_LIB") or os.path.join(_HERE, "libmsig.so")   # MSIG_LIB: probe builds only
 
 # enums (mirror include/msig.h)
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_TANH = 0, 1, 2, 3
