@@ -495,14 +495,15 @@ class _GeneratorFn(torch.autograd.Function):
         # over pixels in its epilogue, so the norm backward that follows needs no reduction pass.
         dev = dout.device
         gu2, gu1 = S["gu2"], S["gu1"]
-        es = ops.epi_stats(B, gu2.h, gu2.w, gu2.c, dev)
+        es = ops.epi_stats(B, gu2.h, gu2.w, gu2.c, dev) if ops.FUSE_N128_REDUCTIONS else None
         dy = ops.convT2d_dgrad(dzu2, P["u2_d"], gu2,
                                ops.epilogue(aux=S["yu1"], aux_mode=AUX_RELU_MASK, stats=es, stats_z=S["zu1"],
                                             mask_norm=S["stu1"]))
         del dzu2
         # ---- up 1 (ConvTranspose 256->128 + IN + ReLU)
         _trace(mod, "dyu1", dy)
-        dzu1 = ops.norm_bwd_from(es, dy, S["zu1"], S["stu1"])
+        dzu1 = (ops.norm_bwd_from(es, dy, S["zu1"], S["stu1"]) if es is not None
+                else ops.norm_act_bwd(dy, S["zu1"], S["stu1"], ACT_NONE))
         _trace(mod, "dzu1", dzu1)
         if wg:
             ops.convT2d_wgrad(S["x_res"], dzu1, gu1, _grad_buf(dec[k].weight))
@@ -548,13 +549,14 @@ class _GeneratorFn(torch.autograd.Function):
         if wg:
             ops.conv2d_wgrad(S["y1"], dz2, S["g2"], _grad_buf(enc[6].weight))
         g2, g1 = S["g2"], S["g1"]
-        es = ops.epi_stats(B, g2.oh, g2.ow, g2.c, dev, phases=4)
+        es = ops.epi_stats(B, g2.oh, g2.ow, g2.c, dev, phases=4) if ops.FUSE_N128_REDUCTIONS else None
         dy = ops.conv2d_dgrad(dz2, P["e2_d"], g2,
                               ops.epilogue(aux=S["y1"], aux_mode=AUX_RELU_MASK, stats=es, stats_z=S["z1"],
                                            mask_norm=S["st1"]))
         del dz2
         _trace(mod, "dy1", dy)
-        dz1 = ops.norm_bwd_from(es, dy, S["z1"], S["st1"])
+        dz1 = (ops.norm_bwd_from(es, dy, S["z1"], S["st1"]) if es is not None
+               else ops.norm_act_bwd(dy, S["z1"], S["st1"], ACT_NONE))
         _trace(mod, "dz1", dz1)
         if wg:
             ops.conv2d_wgrad(S["y0"], dz1, g1, _grad_buf(enc[3].weight))

@@ -108,6 +108,9 @@ def epilogue(bias=None, aux=None, aux_mode=AUX_NONE, act=ACT_NONE, alpha=1.0, al
 EPI_STATS_MIN_KBLOCKS = int(__import__('os').environ.get('MSIG_EPI_MIN_KB', '11'))
 
 
+XX
+
+
 def epi_fusable(taps, c):
     return taps * c // 64 >= EPI_STATS_MIN_KBLOCKS
 
