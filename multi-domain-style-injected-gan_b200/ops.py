@@ -108,7 +108,11 @@ def epilogue(bias=None, aux=None, aux_mode=AUX_NONE, act=ACT_NONE, alpha=1.0, al
 EPI_STATS_MIN_KBLOCKS = int(__import__('os').environ.get('MSIG_EPI_MIN_KB', '11'))
 
 
-XX
+# The two 128-wide dgrads of the generator (16 K blocks per tile: model.py:133's stride-2 dgrad and model.py:140's
+# transposed-conv dgrad) are EPILOGUE bound with the fused reductions (240 us against 115 us plain), so they keep the
+# mask in the epilogue but leave the reductions to the norm backward's own pass (same-box A/B: -0.2..-0.6 ms per step).
+# MSIG_FUSE_N128=1 restores the fused form.
+FUSE_N128_REDUCTIONS = __import__('os').environ.get('MSIG_FUSE_N128', '0') != '0'
 
 
 def epi_fusable(taps, c):
