@@ -243,7 +243,7 @@ def time_hbm_kernel(torch, ops, L, batch, iters=20):
 
 def ncu_traffic():
     """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture
-    (profiles/ncu_fprop_r1.txt, first line = plain forward launch)."""
+    (profiles/ncu_fprop_r2.txt, first line = plain forward launch)."""
     try:
         path = os.path.join(ROOT, "profiles", "ncu_fprop_r2.txt")
         if not os.path.exists(path):
@@ -397,7 +397,7 @@ def run_ours(args):
                      "kernel": "fprop2_kernel (tcgen05 cta_group::2 implicit GEMM) conv3x3 256->256 @64x64, batch %d" % kb,
                      "kernel_ms": kms, "algorithmic_flops_per_launch": kflops,
                      "algorithmic_bytes_per_launch": 2.0 * (2 * kb * 4096 * 256 + 256 * 2304),
-                     "traffic_note": "dram__bytes_read+write of one launch (ncu --set full, profiles/ncu_fprop_r1.txt); "
+                     "traffic_note": "dram__bytes_read+write of one launch (ncu --set full, profiles/ncu_fprop_r2.txt); "
                                      "below the algorithmic bytes because most of the output is still in L2 when the kernel ends",
                      "peak_source": pk["source"] + " (burst, kernel timed alone, L2 flushed)"},
         "roofline_hbm": {"bound": "hbm", "achieved": hach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hach / pk["hbm_gbs"],
