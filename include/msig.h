@@ -40,6 +40,8 @@ int msig_sm_count(void);
 int msig_debug_set_ring_mode(int mode);   /* test hook: strip-ring kernel for 64-channel layers: bit 0 on, bit 1 four convT phases in one launch, bits 8..15 ring-depth cap; default 3 */
 int msig_debug_set_wgrad_mode(int mask);  /* test hook: bit 0 = M-stacked row-patch weight gradients, bit 1 = tap-grouped convT ones; default 3 */
 int msig_debug_set_m2_mode(int on);       /* test hook: two m-tiles per CTA for the 128-wide conv tiles, default on */
+int msig_debug_set_pdl(int on);           /* test hook: programmatic dependent launch of every kernel (csrc/common.h), default OFF (measured: no gain);
+                                           * the environment variable MSIG_PDL=1 turns it on */
 int msig_debug_set_pair_mode(int on);     /* test hook: CTA-pair (tcgen05 cta_group::2) kernel for 256-wide conv tiles, default on */
 long long msig_kernel_launches(void);    /* kernels launched by this library since load */
 
@@ -137,7 +139,11 @@ int msig_conv2d_fwd(const msig_conv_geom* g, const void* x, const void* w_fwd,
  * input gradient + weight gradient): no gathered patch matrix. msig_img_pad8 stores the fp32 NCHW image
  * (c <= 8) reflect- or zero-padded as bf16 [n][h+2p][w+2p+2][8]; a TMA map with a one-pixel (16-byte) W
  * stride then reads the (s, c) window of filter row r for every output pixel as one K-major 128-byte
- * row. Geometry: n,h,w,c = the UNPADDED image, pad_t = pad_l = p, stride 1, s <= 8. */
+ * row. Geometry: n,h,w,c = the UNPADDED image, pad_t = pad_l = p, stride 1, s <= 8.
+ * dst_pad8 must have room for MSIG_PAD8_SLACK_PIXELS (8) extra pixels (128 bytes) behind the last row;
+ * msig_img_pad8 zeroes them: the 8-pixel window of the last output columns of the LAST padded row reaches up to
+ * 7 - s pixels past the row (in every other row that is the start of the next row, met by zero weights). */
+#define MSIG_PAD8_SLACK_PIXELS 8
 int msig_img_pad8(const float* src_nchw, int32_t n, int32_t c, int32_t h, int32_t w, int32_t pad,
                   int32_t reflect, const float* scale /* [c] or NULL */, const float* shift /* [c] or NULL */,
                   void* dst_pad8, void* stream);   /* stores x*scale + shift (VGG renorm, losses.py:49-56); padding = 0 */
@@ -269,6 +275,21 @@ int msig_norm_bwd_from_partials(const float* partial, int32_t n, int32_t rows_pe
                                 const float* scale, const float* shift, int32_t hw, int32_t c, void* dx,
                                 float* dgamma, float* dbeta, int64_t dgb_stride, int accumulate_dgb,
                                 float* coef_workspace /* [n][2][c] fp32 */, void* stream);
+
+/* Same results in ONE launch each: every block of the apply kernel folds the partial rows of its image in its
+ * prologue (meant for few rows per image, e.g. the 32 rows of a 64x64 plane; the caller chooses), block 0 of
+ * the image writes mean / rstd / scale / shift (forward) or coef / dgamma / dbeta (backward). Replaces
+ * msig_in_stats_from_partials + msig_norm_act_fwd, and msig_norm_bwd_from_partials (model.py:16,28-36,51-55). */
+int msig_norm_act_fwd_from_partials(const float* partial, int32_t n, int32_t rows_per_img, int32_t ld,
+                                    int32_t hw, int32_t c, float eps, const float* gamma, const float* beta,
+                                    int64_t gb_stride, float* mean, float* rstd, float* scale, float* shift,
+                                    const void* x, const void* residual, int32_t act, float slope, void* y,
+                                    void* stream);
+int msig_norm_bwd_from_partials_fused(const float* partial, int32_t n, int32_t rows_per_img, int32_t ld,
+                                      const void* g, const void* x, const float* mean, const float* rstd,
+                                      const float* scale, const float* shift, int32_t hw, int32_t c, void* dx,
+                                      float* dgamma, float* dbeta, int64_t dgb_stride, int accumulate_dgb,
+                                      float* coef_workspace /* [n][2][c] fp32 */, void* stream);
 
 /* ---- small bandwidth ops ------------------------------------------------------------------ */
 /* dz = dy * act'(y) (ReLU / LeakyReLU), bf16 */

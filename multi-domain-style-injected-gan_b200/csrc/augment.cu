@@ -77,6 +77,7 @@ __device__ __forceinline__ AugBox aug_box(const int32_t* boxes, int b, int H, in
 __global__ void __launch_bounds__(256) augment_h_kernel(const uint8_t* __restrict__ src, int H, int W,
                                                         const int32_t* __restrict__ boxes, int size,
                                                         uint8_t* __restrict__ tmp, int rows_per_block) {
+  pdl_entry();
   const int b = blockIdx.y;
   const AugBox bx = aug_box(boxes, b, H, W);
   const int y0 = blockIdx.x * rows_per_block;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(256) augment_v_kernel(const uint8_t* __restric
                                                         const int32_t* __restrict__ boxes,
                                                         const int32_t* __restrict__ quarter_turns, int size,
                                                         float* __restrict__ out, int rows_per_block) {
+  pdl_entry();
   const int b = blockIdx.y;
   const AugBox bx = aug_box(boxes, b, H, W);
   const int q = quarter_turns ? (quarter_turns[b] & 3) : 0;
@@ -165,10 +167,10 @@ int msig_augment_u8(const void* src, int32_t n, int32_t h, int32_t w, const int3
   MSIG_REQUIRE(workspace_bytes >= msig_augment_workspace(n, h, w, size), "msig_augment_u8: workspace too small");
   const int rpb = 8;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  augment_h_kernel<<<dim3(static_cast<unsigned>(ceil_div(h, rpb)), n), 256, 0, st>>>(
+  MSIG_LAUNCH((augment_h_kernel), dim3(static_cast<unsigned>(ceil_div(h, rpb)), n), 256, 0, st, 
       static_cast<const uint8_t*>(src), h, w, boxes, size, static_cast<uint8_t*>(workspace), rpb);
   MSIG_CHECK_LAUNCH();
-  augment_v_kernel<<<dim3(static_cast<unsigned>(ceil_div(size, rpb)), n), 256, 0, st>>>(
+  MSIG_LAUNCH((augment_v_kernel), dim3(static_cast<unsigned>(ceil_div(size, rpb)), n), 256, 0, st, 
       static_cast<const uint8_t*>(workspace), h, w, boxes, quarter_turns, size, out, rpb);
   count_launch(2);
   MSIG_CHECK_LAUNCH();

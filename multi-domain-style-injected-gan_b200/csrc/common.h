@@ -42,6 +42,50 @@ EncodeTiledFn encode_tiled();
     if (!(cond)) return msig::set_error(MSIG_ERR_ARG, __VA_ARGS__);    \
   } while (0)
 
+// ---- launches; programmatic dependent launch (PDL) as an opt-in experiment ---------------------------------
+// Every kernel of this library is launched through launch_kernel() and starts with pdl_entry()
+// ("griddepcontrol.wait": a no-op unless the launch carries the programmatic-stream-serialization attribute,
+// in which case it holds every thread until the predecessor grid has completed and its memory is visible; no
+// kernel touches global memory before it). With MSIG_PDL=1 / msig_debug_set_pdl(1) the attribute is set and the
+// next kernel's grid is set up while the blocks of its predecessor drain (stream capture records programmatic
+// graph edges). MEASURED (profiles/probe/pdl_r2.txt, B=32 train step, same box A/B): no gain -- 79.95 / 80.05 ms
+// against 79.92 / 79.73 ms for plain launches; with an additional early "launch_dependents" trigger at kernel
+// entry the step was 0.6 ms SLOWER (81.0 vs 80.4 ms) and the graph-vs-eager bit-equality test failed once in the
+// full suite (blocks of a kernel that become resident two launches ahead can keep read-only-cache lines of a
+// buffer the allocator hands to a later producer), so the early trigger is not built and PDL stays off by default.
+bool pdl_enabled();
+void set_pdl(bool on);
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_entry() {
+#ifndef MSIG_NO_GRIDDEP
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                 Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr;
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#ifdef MSIG_LAUNCH_CHEVRON     // probe builds: the classic launch syntax
+#define MSIG_LAUNCH(kern, grid, block, smem, stream, ...) kern<<<grid, block, smem, stream>>>(__VA_ARGS__)
+#else
+#define MSIG_LAUNCH(kern, grid, block, smem, stream, ...) \
+  (void)msig::launch_kernel(kern, grid, block, smem, stream, __VA_ARGS__)
+#endif
+#endif
+
 inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

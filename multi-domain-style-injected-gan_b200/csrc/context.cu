@@ -2,6 +2,7 @@
 #include "common.h"
 #include "igemm.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -26,6 +27,16 @@ int sm_count() {                              // SM count of the CURRENT device 
   return g_sm_counts[dev];
 }
 bool context_ready() { return g_encode != nullptr; }
+
+static int g_pdl = -1;                        // -1: not decided yet (environment MSIG_PDL, default off)
+bool pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("MSIG_PDL");
+    g_pdl = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return g_pdl != 0;
+}
+void set_pdl(bool on) { g_pdl = on ? 1 : 0; }
 EncodeTiledFn encode_tiled() { return g_encode; }
 
 }  // namespace msig
@@ -38,6 +49,10 @@ int msig_version(void) { return MSIG_VERSION; }
 const char* msig_last_error(void) { return g_err; }
 int msig_sm_count(void) { return sm_count(); }
 long long msig_kernel_launches(void) { return igemm_kernel_launches(); }
+int msig_debug_set_pdl(int on) {
+  set_pdl(on != 0);
+  return MSIG_OK;
+}
 
 int msig_init(int device) {
   std::lock_guard<std::mutex> lock(g_init_mu);

@@ -116,6 +116,7 @@ __device__ __forceinline__ int64_t packed_offset(const PackGeom& g, int o, int i
 
 __global__ void wpack_kernel(PackGeom g, const float* __restrict__ w, __nv_bfloat16* __restrict__ out,
                              int64_t numel) {
+  pdl_entry();
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < numel;
        idx += int64_t(gridDim.x) * blockDim.x) {
     int o, i, t;
@@ -147,6 +148,7 @@ constexpr int kPackFwdMax = 8192;     // I * RS elements of one output channel h
 
 __global__ void __launch_bounds__(256) wpack_multi_tiled_kernel(const PackJob* __restrict__ jobs, int n_jobs,
                                                                 int64_t total_tiles) {
+  pdl_entry();
   __shared__ __align__(16) unsigned char smem_raw[kPackTile * (kPackTile + 1) * 4 > (kPackFwdMax + 64) * 2
                                                       ? kPackTile * (kPackTile + 1) * 4
                                                       : (kPackFwdMax + 64) * 2];
@@ -201,6 +203,7 @@ __global__ void __launch_bounds__(256) wpack_multi_tiled_kernel(const PackJob* _
 }
 
 __global__ void wpack_multi_kernel(const PackJob* __restrict__ jobs, int n_jobs, int64_t total) {
+  pdl_entry();
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x) {
     int lo = 0, hi = n_jobs - 1;                      // last job with start <= idx
@@ -250,6 +253,7 @@ __device__ __forceinline__ int64_t partial_offset(const PackGeom& g, int o, int 
 __global__ void wgrad_reduce_kernel(PackGeom g, const float* __restrict__ partial, int splits,
                                     int64_t split_stride, float* __restrict__ dw, int accumulate,
                                     int64_t numel) {
+  pdl_entry();
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < numel;
        idx += int64_t(gridDim.x) * blockDim.x) {
     int o, i, t;
@@ -266,6 +270,7 @@ __global__ void wgrad_reduce_kernel(PackGeom g, const float* __restrict__ partia
 __global__ void wgrad_reduce_fwd_kernel(PackGeom g, const float* __restrict__ partial, int splits,
                                         int64_t split_stride, float* __restrict__ dw, int accumulate,
                                         int64_t numel) {
+  pdl_entry();
   const int inner = g.partT ? g.O : g.I;
   for (int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; q < numel;
        q += int64_t(gridDim.x) * blockDim.x) {
@@ -287,6 +292,7 @@ __global__ void wgrad_reduce_fwd_kernel(PackGeom g, const float* __restrict__ pa
 __global__ void __launch_bounds__(256) wgrad_reduce_t_kernel(const float* __restrict__ partial, int splits,
                                                              int64_t split_stride, float* __restrict__ dw,
                                                              int accumulate, int IT, int O) {
+  pdl_entry();
   __shared__ float tile[32][33];
   const int it0 = blockIdx.x * 32, o0 = blockIdx.y * 32;
   for (int r = threadIdx.y; r < 32; r += 8) {
@@ -313,8 +319,7 @@ static int launch_wgrad_reduce(const PackGeom& g, const float* partial, int spli
   const int64_t numel = int64_t(g.O) * g.I * g.RS;
   if (g.kind == MSIG_WPACK_FWD && g.OOFF == 0 && g.OC == g.O && g.partT) {
     const int IT = g.I * g.RS;
-    wgrad_reduce_t_kernel<<<dim3(static_cast<unsigned>(ceil_div(IT, 32)), static_cast<unsigned>(ceil_div(g.O, 32))),
-                            dim3(32, 8), 0, st>>>(partial, splits, split_stride, dw, accumulate, IT, g.O);
+    MSIG_LAUNCH((wgrad_reduce_t_kernel), dim3(static_cast<unsigned>(ceil_div(IT, 32)), static_cast<unsigned>(ceil_div(g.O, 32))), dim3(32, 8), 0, st, partial, splits, split_stride, dw, accumulate, IT, g.O);
     count_launch(1);
     MSIG_CHECK_LAUNCH();
     return MSIG_OK;
@@ -322,12 +327,12 @@ static int launch_wgrad_reduce(const PackGeom& g, const float* partial, int spli
   const int threads = 256;
   const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(numel, threads), 4096));
   if (g.kind == MSIG_WPACK_FWD && g.OOFF == 0 && g.OC == g.O) {
-    wgrad_reduce_fwd_kernel<<<blocks, threads, 0, st>>>(g, partial, splits, split_stride, dw, accumulate, numel);
+    MSIG_LAUNCH((wgrad_reduce_fwd_kernel), blocks, threads, 0, st, g, partial, splits, split_stride, dw, accumulate, numel);
     count_launch(1);
     MSIG_CHECK_LAUNCH();
     return MSIG_OK;
   }
-  wgrad_reduce_kernel<<<blocks, threads, 0, st>>>(g, partial, splits, split_stride, dw, accumulate,
+  MSIG_LAUNCH((wgrad_reduce_kernel), blocks, threads, 0, st, g, partial, splits, split_stride, dw, accumulate,
                                                   numel);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
@@ -662,6 +667,7 @@ static WgradPlan plan_wgrad(int M, int N, int taps, int64_t kb_total, bool upper
 
 __global__ void sum_splits_kernel(const float* __restrict__ partial, int splits, int64_t stride,
                                   float* __restrict__ out, int64_t numel) {
+  pdl_entry();
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < numel;
        i += int64_t(gridDim.x) * blockDim.x) {
     float acc = 0.f;
@@ -728,7 +734,7 @@ int msig_wpack_part(const msig_wpack_desc* d, int32_t oc, int32_t o_off, const f
   const int64_t numel = int64_t(g.O) * g.I * g.RS;
   const int threads = 256;
   const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(numel, threads), 4096));
-  wpack_kernel<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(
+  MSIG_LAUNCH((wpack_kernel), blocks, threads, 0, static_cast<cudaStream_t>(stream), 
       g, w, reinterpret_cast<__nv_bfloat16*>(packed), numel);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
@@ -791,14 +797,14 @@ int msig_wpack_multi(const void* table_dev, int32_t n_jobs, int64_t total, int64
                "msig_wpack_multi: bad argument");
   if (total > 0) {
     const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(total, 256), 148 * 16));
-    wpack_multi_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    MSIG_LAUNCH((wpack_multi_kernel), blocks, 256, 0, static_cast<cudaStream_t>(stream), 
         reinterpret_cast<const PackJob*>(table_dev), n_jobs, total);
     count_launch(1);
     MSIG_CHECK_LAUNCH();
   }
   if (total_tiles > 0) {
     const int blocks = static_cast<int>(std::min<int64_t>(total_tiles, 148 * 8));
-    wpack_multi_tiled_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    MSIG_LAUNCH((wpack_multi_tiled_kernel), blocks, 256, 0, static_cast<cudaStream_t>(stream), 
         reinterpret_cast<const PackJob*>(table_dev), n_jobs, total_tiles);
     count_launch(1);
     MSIG_CHECK_LAUNCH();
@@ -1155,6 +1161,7 @@ size_t msig_convT2d_wgrad_workspace(const msig_conv_geom* g) {
 __global__ void __launch_bounds__(256) wgrad_reduce_convT_t_kernel(const float* __restrict__ partial, int splits,
                                                                   int64_t split_stride, float* __restrict__ dw,
                                                                   int accumulate, int O) {
+  pdl_entry();
   extern __shared__ float sm_t[];                       // [O][17]
   const int i = blockIdx.x;
   const float* pp = partial + int64_t(i) * 16 * O;
@@ -1237,7 +1244,7 @@ int msig_convT2d_wgrad(const msig_conv_geom* g, const void* x, const void* dy, f
   cudaError_t ce = launch_wgrad(p, pl.block_n, st);
   if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "convT wgrad launch: %s", cudaGetErrorString(ce));
   if (group) {
-    wgrad_reduce_convT_t_kernel<<<g->c, 256, size_t(g->k) * 17 * sizeof(float), st>>>(p.out, pl.splits, p.o_split, dw,
+    MSIG_LAUNCH((wgrad_reduce_convT_t_kernel), g->c, 256, size_t(g->k) * 17 * sizeof(float), st, p.out, pl.splits, p.o_split, dw,
                                                                                       accumulate, g->k);
     count_launch(1);
     MSIG_CHECK_LAUNCH();
@@ -1311,6 +1318,7 @@ __global__ void __launch_bounds__(256) multi_linear_grads_kernel(const float* __
                                                                  int64_t rows, int64_t ld, int layers, int O, int I,
                                                                  float* const* __restrict__ wgrads,
                                                                  float* const* __restrict__ bgrads) {
+  pdl_entry();
   const int64_t per_layer = int64_t(O) * I;
   const int64_t n_w = per_layer * layers, n_b = int64_t(O) * layers;
   for (int64_t q = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; q < n_w + n_b;
@@ -1340,7 +1348,7 @@ int msig_multi_linear_grads(const float* partial, int32_t splits, int64_t split_
                "msig_multi_linear_grads: bad argument");
   const int64_t total = int64_t(layers) * out_features * (int64_t(in_features) + 1);
   const int blocks = static_cast<int>(std::min<int64_t>(ceil_div(total, 256), 148 * 16));
-  multi_linear_grads_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  MSIG_LAUNCH((multi_linear_grads_kernel), blocks, 256, 0, static_cast<cudaStream_t>(stream), 
       partial, splits, split_stride, dy, rows, ld, layers, out_features, in_features,
       reinterpret_cast<float* const*>(wgrad_ptrs), reinterpret_cast<float* const*>(bgrad_ptrs));
   count_launch(1);
@@ -1423,7 +1431,7 @@ int msig_gram_fwd(const void* f, int32_t n, int32_t h, int32_t w, int32_t c, flo
   if (ce != cudaSuccess) return set_error(MSIG_ERR_CUDA, "gram launch: %s", cudaGetErrorString(ce));
   if (pl.splits > 1) {
     const int64_t numel = int64_t(dim) * dim;
-    sum_splits_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div(numel, 256), 4096)), 256, 0, st>>>(
+    MSIG_LAUNCH((sum_splits_kernel), static_cast<int>(std::min<int64_t>(ceil_div(numel, 256), 4096)), 256, 0, st, 
         p.out, pl.splits, p.o_split, gram, numel);
     count_launch(1);
     MSIG_CHECK_LAUNCH();

@@ -19,6 +19,7 @@
 // Reference ops these replace: every nn.Conv2d / nn.ConvTranspose2d / nn.Linear in
 // /root/reference/model.py:18,45,48,72-75,84,131-141,165,183 and the VGG convs + torch.mm Gram of
 // /root/reference/losses.py:15,76 (forward, dgrad, wgrad).
+#include "common.h"
 #include "igemm.cuh"
 #include "ptx.cuh"
 
@@ -415,6 +416,7 @@ constexpr int kFpropThreads = 384;
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kFpropThreads, 1) fprop_kernel(const __grid_constant__ FpropParams p) {
+  pdl_entry();
   using Cfg = FpropCfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -594,6 +596,7 @@ constexpr int kM2StageBytes = kM2ABytes + kM2BBytes;         // 48 KiB
 constexpr int kM2SmemBytes = kM2Stages * kM2StageBytes + 1024 + 256;
 
 __global__ void __launch_bounds__(kFpropThreads, 1) fprop_m2_kernel(const __grid_constant__ FpropParams p) {
+  pdl_entry();
   constexpr int BLOCK_N = 128;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -752,6 +755,7 @@ constexpr int k2SmemBytes = k2Stages * k2StageBytes + 1024 + 256;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kFpropThreads, 1)
     fprop2_kernel(const __grid_constant__ FpropParams p) {
+  pdl_entry();
   constexpr int BLOCK_N = 256;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
@@ -903,6 +907,7 @@ constexpr int kRfThreads = 384;                  // warps 0..3 as in the fprop k
 constexpr int kRfSmemBytes = kRfMaxR * kRfWBytes + kRfRing * kRfStripBytes + 4 * kTileM * kRfFoldLd * 4 + 1024 + 512;
 
 __global__ void __launch_bounds__(kRfThreads, 1) fprop_rowfold_kernel(const __grid_constant__ RowfoldParams p) {
+  pdl_entry();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -1133,6 +1138,7 @@ constexpr int kRingSmemMax = 232448;               // 227 KiB
 static inline int ring_slot_bytes(int S) { return ((kTileM + S - 1) * 128 + 1023) & ~1023; }
 
 __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __grid_constant__ FpropParams p) {
+  pdl_entry();
   constexpr int BLOCK_N = 64;
   constexpr int NACC = 4;                  // accumulator stages in TMEM (64 columns each)
   extern __shared__ uint8_t smem_raw[];
@@ -1394,6 +1400,7 @@ struct WgradCfg {
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(256, 1) wgrad_kernel(const __grid_constant__ WgradParams p) {
+  pdl_entry();
   using Cfg = WgradCfg<BLOCK_N>;
   const int m_blk = blockIdx.x / p.n_blocks;
   const int n_blk = blockIdx.x % p.n_blocks;
@@ -1616,6 +1623,7 @@ constexpr int kW2StageBytes = 4 * 8192;                 // A: 2 x 64 ch x 64 px,
 constexpr int kW2SmemBytes = kW2Stages * kW2StageBytes + 1024 + 256;
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1) wgrad2_kernel(const __grid_constant__ WgradParams p) {
+  pdl_entry();
   constexpr int BLOCK_N = 256;
   const uint32_t rank = cluster_ctarank();               // == m_blk
   const int m_blk = static_cast<int>(rank);
@@ -1791,7 +1799,7 @@ static cudaError_t launch_fprop_t(const FpropParams& p, int num_sms, cudaStream_
   const int total = p.n_img * p.tiles_h * p.tiles_w * p.phases * p.n_blocks;
   const int grid = total < num_sms ? total : num_sms;
   if (grid <= 0) return cudaSuccess;
-  fprop_kernel<BLOCK_N><<<grid, kFpropThreads, Cfg::kSmemBytes, stream>>>(p);
+  MSIG_LAUNCH((fprop_kernel<BLOCK_N>), grid, kFpropThreads, Cfg::kSmemBytes, stream, p);
   count_launch(1);
   return cudaGetLastError();
 }
@@ -1812,7 +1820,7 @@ static cudaError_t launch_fprop2(const FpropParams& p, int num_sms, cudaStream_t
   int clusters = num_sms / 2;
   if (pairs < clusters) clusters = pairs;
   if (clusters <= 0) return cudaSuccess;
-  fprop2_kernel<<<2 * clusters, kFpropThreads, k2SmemBytes, stream>>>(p);
+  MSIG_LAUNCH((fprop2_kernel), 2 * clusters, kFpropThreads, k2SmemBytes, stream, p);
   count_launch(1);
   return cudaGetLastError();
 }
@@ -1841,7 +1849,7 @@ static cudaError_t launch_fprop_m2(const FpropParams& p, int num_sms, cudaStream
   const int total = p.n_img * (p.tiles_h / 2) * p.tiles_w * p.phases * p.n_blocks;
   const int grid = total < num_sms ? total : num_sms;
   if (grid <= 0) return cudaSuccess;
-  fprop_m2_kernel<<<grid, kFpropThreads, kM2SmemBytes, stream>>>(p);
+  MSIG_LAUNCH((fprop_m2_kernel), grid, kFpropThreads, kM2SmemBytes, stream, p);
   count_launch(1);
   return cudaGetLastError();
 }
@@ -1876,7 +1884,7 @@ cudaError_t launch_rowfold(const RowfoldParams& p, int num_sms, cudaStream_t str
   const int items = p.n_img * p.tiles_w * p.chunks_h;
   const int grid = items < num_sms ? items : num_sms;
   if (grid <= 0) return cudaSuccess;
-  fprop_rowfold_kernel<<<grid, kRfThreads, kRfSmemBytes, stream>>>(p);
+  MSIG_LAUNCH((fprop_rowfold_kernel), grid, kRfThreads, kRfSmemBytes, stream, p);
   count_launch(1);
   return cudaGetLastError();
 }
@@ -1920,7 +1928,7 @@ cudaError_t launch_fprop_ring64(const FpropParams& p0, int num_sms, cudaStream_t
   if (grid <= 0) return cudaSuccess;
   const int smem_bytes = p.strip_r * p.strip_s * cbs * kRingWBytes + p.ring_slots * ring_slot_bytes(p.strip_s) + 1024 +
                          kRingBarBytes;
-  fprop_ring64_kernel<<<grid, kFpropThreads, smem_bytes, stream>>>(p);
+  MSIG_LAUNCH((fprop_ring64_kernel), grid, kFpropThreads, smem_bytes, stream, p);
   count_launch(1);
   return cudaGetLastError();
 }
@@ -1937,7 +1945,7 @@ static cudaError_t launch_wgrad_t(const WgradParams& p, cudaStream_t stream) {
     attr_done(attr_devs);
   }
   dim3 grid(p.m_blocks * p.n_blocks, p.taps, p.splits);
-  wgrad_kernel<BLOCK_N><<<grid, 256, Cfg::kSmemBytes, stream>>>(p);
+  MSIG_LAUNCH((wgrad_kernel<BLOCK_N>), grid, 256, Cfg::kSmemBytes, stream, p);
   count_launch(1);
   return cudaGetLastError();
 }
@@ -1950,7 +1958,7 @@ static cudaError_t launch_wgrad2(const WgradParams& p, cudaStream_t stream) {
     attr_done(attr_devs);
   }
   dim3 grid(2, p.taps, p.splits);
-  wgrad2_kernel<<<grid, 256, kW2SmemBytes, stream>>>(p);
+  MSIG_LAUNCH((wgrad2_kernel), grid, 256, kW2SmemBytes, stream, p);
   count_launch(1);
   return cudaGetLastError();
 }

@@ -58,6 +58,7 @@ static inline int lgrid(int64_t work, int threads) {
 __global__ void __launch_bounds__(256) l1_f32_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                          int64_t n, float inv_n, float* __restrict__ loss,
                                                          float* __restrict__ partial, unsigned int* ticket) {
+  pdl_entry();
   float s = 0.f;
   const int64_t n4 = n / 4;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
@@ -71,6 +72,7 @@ __global__ void __launch_bounds__(256) l1_f32_fwd_kernel(const float* __restrict
 }
 __global__ void l1_f32_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t n,
                                   float inv_n, const float* __restrict__ gscale, float* __restrict__ g) {
+  pdl_entry();
   const float k = inv_n * (gscale ? __ldg(gscale) : 1.f);
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
     g[i] = sgn(a[i] - b[i]) * k;
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(256) l1_bf16_fwd_kernel(const __nv_bfloat16* _
                                                           const __nv_bfloat16* __restrict__ b, int64_t groups,
                                                           float inv_n, float* __restrict__ loss,
                                                           float* __restrict__ partial, unsigned int* ticket) {
+  pdl_entry();
   float s = 0.f;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < groups; i += int64_t(gridDim.x) * blockDim.x) {
     const uint4 ua = reinterpret_cast<const uint4*>(a)[i];
@@ -96,6 +99,7 @@ __global__ void __launch_bounds__(256) l1_bf16_fwd_kernel(const __nv_bfloat16* _
 __global__ void l1_bf16_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b,
                                    int64_t groups, float inv_n, const float* __restrict__ gscale,
                                    const __nv_bfloat16* __restrict__ aux, __nv_bfloat16* __restrict__ g) {
+  pdl_entry();
   const float k = inv_n * (gscale ? __ldg(gscale) : 1.f);
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < groups; i += int64_t(gridDim.x) * blockDim.x) {
     const uint4 ua = reinterpret_cast<const uint4*>(a)[i];
@@ -119,6 +123,7 @@ __global__ void l1_bf16_bwd_kernel(const __nv_bfloat16* __restrict__ a, const __
 __global__ void __launch_bounds__(256) mse_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                       float t, int64_t n, float inv_n, float* __restrict__ loss,
                                                       float* __restrict__ partial, unsigned int* ticket) {
+  pdl_entry();
   float s = 0.f;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x) {
     const float d = a[i] - (b ? b[i] : t);
@@ -128,6 +133,7 @@ __global__ void __launch_bounds__(256) mse_fwd_kernel(const float* __restrict__ 
 }
 __global__ void mse_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, float t, int64_t n,
                                float inv_n, const float* __restrict__ gscale, float* __restrict__ g) {
+  pdl_entry();
   const float k = 2.f * inv_n * (gscale ? __ldg(gscale) : 1.f);
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
     g[i] = (a[i] - (b ? b[i] : t)) * k;
@@ -140,6 +146,7 @@ __global__ void __launch_bounds__(256) gram_l1_kernel(const float* __restrict__ 
                                                       int dim, float inv_n, float* __restrict__ loss, int accumulate,
                                                       __nv_bfloat16* __restrict__ ssym, float* __restrict__ partial,
                                                       unsigned int* ticket) {
+  pdl_entry();
   __shared__ float tile[32][33];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int bx = blockIdx.x * 32, by = blockIdx.y * 32;   // this block: rows by.., cols bx..
@@ -168,6 +175,7 @@ __global__ void __launch_bounds__(256) gram_l1_kernel(const float* __restrict__ 
 
 __global__ void colsum_f32_kernel(const float* __restrict__ x, int64_t rows, int c, int64_t ld,
                                   float* __restrict__ out, int accumulate) {
+  pdl_entry();
   const int ch = blockIdx.x * blockDim.x + threadIdx.x;
   if (ch >= c) return;
   float s = 0.f;
@@ -178,6 +186,7 @@ __global__ void colsum_f32_kernel(const float* __restrict__ x, int64_t rows, int
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, int64_t n, float* __restrict__ out,
                                                     int accumulate, float* __restrict__ partial,
                                                     unsigned int* ticket) {
+  pdl_entry();
   float s = 0.f;
   const int64_t n4 = n / 4;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n4; i += int64_t(gridDim.x) * blockDim.x) {
@@ -189,7 +198,8 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x,
   grid_sum_ordered(s, 1.f, out, accumulate, partial, ticket, threadIdx.x, blockIdx.x, gridDim.x);
 }
 
-__global__ void counter_inc_kernel(int32_t* c) { *c += 1; }
+__global__ void counter_inc_kernel(int32_t* c) {
+  pdl_entry(); *c += 1; }
 
 // clip_grad_norm_(max_norm) + Adam (torch defaults: no weight decay, no amsgrad) + EMA, one pass.
 // step_dev != nullptr: the step number (bias corrections) comes from device memory, so the launch can
@@ -199,6 +209,7 @@ __global__ void adam_step_kernel(float* __restrict__ p, const float* __restrict_
                                  const float* __restrict__ grad_sumsq, float max_norm, float grad_scale, float lr,
                                  float beta1, float beta2, float eps, float bc1, float bc2_sqrt, float ema_beta,
                                  const int32_t* __restrict__ step_dev) {
+  pdl_entry();
   if (step_dev != nullptr) {
     const double st = double(__ldg(step_dev));
     bc1 = float(1.0 - pow(double(beta1), st));
@@ -252,7 +263,7 @@ int msig_l1_loss_f32_fwd(const float* a, const float* b, int64_t numel, float* l
   const int blocks = lgrid(numel / 4 + 1, 256);
   MSIG_REQUIRE(REDUCE_WS_OK(blocks), "msig_l1_loss_f32_fwd: workspace too small");
   MSIG_CHECK_CUDA(cudaMemsetAsync(ws_ticket(workspace, blocks), 0, sizeof(unsigned int), ST(stream)));
-  l1_f32_fwd_kernel<<<blocks, 256, 0, ST(stream)>>>(a, b, numel, 1.f / numel, loss, ws_partial(workspace),
+  MSIG_LAUNCH((l1_f32_fwd_kernel), blocks, 256, 0, ST(stream), a, b, numel, 1.f / numel, loss, ws_partial(workspace),
                                                    ws_ticket(workspace, blocks));
   count_launch(1);
   MSIG_CHECK_LAUNCH();
@@ -261,7 +272,7 @@ int msig_l1_loss_f32_fwd(const float* a, const float* b, int64_t numel, float* l
 int msig_l1_loss_f32_bwd(const float* a, const float* b, int64_t numel, const float* gscale, float* grad_a,
                          void* stream) {
   MSIG_REQUIRE(a && b && grad_a && numel > 0, "msig_l1_loss_f32_bwd: bad argument");
-  l1_f32_bwd_kernel<<<lgrid(numel, 256), 256, 0, ST(stream)>>>(a, b, numel, 1.f / numel, gscale, grad_a);
+  MSIG_LAUNCH((l1_f32_bwd_kernel), lgrid(numel, 256), 256, 0, ST(stream), a, b, numel, 1.f / numel, gscale, grad_a);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -272,7 +283,7 @@ int msig_l1_loss_bf16_fwd(const void* a, const void* b, int64_t numel, float* lo
   const int blocks = lgrid(numel / 8, 256);
   MSIG_REQUIRE(REDUCE_WS_OK(blocks), "msig_l1_loss_bf16_fwd: workspace too small");
   MSIG_CHECK_CUDA(cudaMemsetAsync(ws_ticket(workspace, blocks), 0, sizeof(unsigned int), ST(stream)));
-  l1_bf16_fwd_kernel<<<blocks, 256, 0, ST(stream)>>>(CBF(a), CBF(b), numel / 8, 1.f / numel, loss,
+  MSIG_LAUNCH((l1_bf16_fwd_kernel), blocks, 256, 0, ST(stream), CBF(a), CBF(b), numel / 8, 1.f / numel, loss,
                                                     ws_partial(workspace), ws_ticket(workspace, blocks));
   count_launch(1);
   MSIG_CHECK_LAUNCH();
@@ -281,7 +292,7 @@ int msig_l1_loss_bf16_fwd(const void* a, const void* b, int64_t numel, float* lo
 int msig_l1_loss_bf16_bwd(const void* a, const void* b, int64_t numel, const float* gscale, const void* aux,
                           void* grad_a, void* stream) {
   MSIG_REQUIRE(a && b && grad_a && numel > 0 && numel % 8 == 0, "msig_l1_loss_bf16_bwd: bad argument");
-  l1_bf16_bwd_kernel<<<lgrid(numel / 8, 256), 256, 0, ST(stream)>>>(CBF(a), CBF(b), numel / 8, 1.f / numel, gscale,
+  MSIG_LAUNCH((l1_bf16_bwd_kernel), lgrid(numel / 8, 256), 256, 0, ST(stream), CBF(a), CBF(b), numel / 8, 1.f / numel, gscale,
                                                                    CBF(aux), BF(grad_a));
   count_launch(1);
   MSIG_CHECK_LAUNCH();
@@ -293,7 +304,7 @@ static int mse_fwd(const float* a, const float* b, float target, int64_t numel, 
   const int blocks = lgrid(numel, 256);
   MSIG_REQUIRE(REDUCE_WS_OK(blocks), "%s: workspace too small", what);
   MSIG_CHECK_CUDA(cudaMemsetAsync(ws_ticket(workspace, blocks), 0, sizeof(unsigned int), ST(stream)));
-  mse_fwd_kernel<<<blocks, 256, 0, ST(stream)>>>(a, b, target, numel, 1.f / numel, loss, ws_partial(workspace),
+  MSIG_LAUNCH((mse_fwd_kernel), blocks, 256, 0, ST(stream), a, b, target, numel, 1.f / numel, loss, ws_partial(workspace),
                                                 ws_ticket(workspace, blocks));
   count_launch(1);
   MSIG_CHECK_LAUNCH();
@@ -306,7 +317,7 @@ int msig_mse_const_fwd(const float* a, float target, int64_t numel, float* loss,
 int msig_mse_const_bwd(const float* a, float target, int64_t numel, const float* gscale, float* grad_a,
                        void* stream) {
   MSIG_REQUIRE(a && grad_a && numel > 0, "msig_mse_const_bwd: bad argument");
-  mse_bwd_kernel<<<lgrid(numel, 256), 256, 0, ST(stream)>>>(a, nullptr, target, numel, 1.f / numel, gscale, grad_a);
+  MSIG_LAUNCH((mse_bwd_kernel), lgrid(numel, 256), 256, 0, ST(stream), a, nullptr, target, numel, 1.f / numel, gscale, grad_a);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -319,7 +330,7 @@ int msig_mse_loss_fwd(const float* a, const float* target, int64_t numel, float*
 int msig_mse_loss_bwd(const float* a, const float* target, int64_t numel, const float* gscale, float* grad_a,
                       void* stream) {
   MSIG_REQUIRE(a && target && grad_a && numel > 0, "msig_mse_loss_bwd: bad argument");
-  mse_bwd_kernel<<<lgrid(numel, 256), 256, 0, ST(stream)>>>(a, target, 0.f, numel, 1.f / numel, gscale, grad_a);
+  MSIG_LAUNCH((mse_bwd_kernel), lgrid(numel, 256), 256, 0, ST(stream), a, target, 0.f, numel, 1.f / numel, gscale, grad_a);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -331,7 +342,7 @@ int msig_gram_l1(const float* ga, const float* gb, int32_t dim, float* loss, int
   const int64_t blocks = int64_t(t) * t;
   MSIG_REQUIRE(REDUCE_WS_OK(blocks), "msig_gram_l1: workspace too small");
   MSIG_CHECK_CUDA(cudaMemsetAsync(ws_ticket(workspace, blocks), 0, sizeof(unsigned int), ST(stream)));
-  gram_l1_kernel<<<dim3(t, t), dim3(32, 8), 0, ST(stream)>>>(ga, gb, dim, 1.f / (float(dim) * float(dim)), loss,
+  MSIG_LAUNCH((gram_l1_kernel), dim3(t, t), dim3(32, 8), 0, ST(stream), ga, gb, dim, 1.f / (float(dim) * float(dim)), loss,
                                                              accumulate, BF(ssym), ws_partial(workspace),
                                                              ws_ticket(workspace, blocks));
   count_launch(1);
@@ -341,7 +352,7 @@ int msig_gram_l1(const float* ga, const float* gb, int32_t dim, float* loss, int
 int msig_colsum_f32(const float* x, int64_t rows, int32_t c, int64_t ld, float* out, int accumulate,
                     void* stream) {
   MSIG_REQUIRE(x && out && c > 0, "msig_colsum_f32: bad argument");
-  colsum_f32_kernel<<<static_cast<unsigned>(ceil_div(c, 128)), 128, 0, ST(stream)>>>(x, rows, c, ld, out, accumulate);
+  MSIG_LAUNCH((colsum_f32_kernel), static_cast<unsigned>(ceil_div(c, 128)), 128, 0, ST(stream), x, rows, c, ld, out, accumulate);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -352,7 +363,7 @@ int msig_sumsq(const float* x, int64_t numel, float* out, int accumulate, void* 
   const int blocks = lgrid(numel / 4 + 1, 256);
   MSIG_REQUIRE(REDUCE_WS_OK(blocks), "msig_sumsq: workspace too small");
   MSIG_CHECK_CUDA(cudaMemsetAsync(ws_ticket(workspace, blocks), 0, sizeof(unsigned int), ST(stream)));
-  sumsq_kernel<<<blocks, 256, 0, ST(stream)>>>(x, numel, out, accumulate, ws_partial(workspace),
+  MSIG_LAUNCH((sumsq_kernel), blocks, 256, 0, ST(stream), x, numel, out, accumulate, ws_partial(workspace),
                                               ws_ticket(workspace, blocks));
   count_launch(1);
   MSIG_CHECK_LAUNCH();
@@ -364,7 +375,7 @@ int msig_adam_step(float* param, const float* grad, float* exp_avg, float* exp_a
   MSIG_REQUIRE(param && grad && exp_avg && exp_avg_sq && numel > 0 && step >= 1, "msig_adam_step: bad argument");
   const double bc1 = 1.0 - pow(double(beta1), double(step));
   const double bc2 = 1.0 - pow(double(beta2), double(step));
-  adam_step_kernel<<<lgrid(numel, 256), 256, 0, ST(stream)>>>(param, grad, exp_avg, exp_avg_sq, ema, numel,
+  MSIG_LAUNCH((adam_step_kernel), lgrid(numel, 256), 256, 0, ST(stream), param, grad, exp_avg, exp_avg_sq, ema, numel,
                                                              grad_sumsq, max_norm, grad_scale, lr, beta1, beta2, eps,
                                                              float(bc1), float(sqrt(bc2)), ema_beta, nullptr);
   count_launch(1);
@@ -375,9 +386,9 @@ int msig_adam_step_dev(float* param, const float* grad, float* exp_avg, float* e
                        const float* grad_sumsq, float max_norm, float grad_scale, float lr, float beta1, float beta2,
                        float eps, int32_t* step_counter, float ema_beta, void* stream) {
   MSIG_REQUIRE(param && grad && exp_avg && exp_avg_sq && step_counter && numel > 0, "msig_adam_step_dev: bad argument");
-  counter_inc_kernel<<<1, 1, 0, ST(stream)>>>(step_counter);
+  MSIG_LAUNCH((counter_inc_kernel), 1, 1, 0, ST(stream), step_counter);
   MSIG_CHECK_LAUNCH();
-  adam_step_kernel<<<lgrid(numel, 256), 256, 0, ST(stream)>>>(param, grad, exp_avg, exp_avg_sq, ema, numel,
+  MSIG_LAUNCH((adam_step_kernel), lgrid(numel, 256), 256, 0, ST(stream), param, grad, exp_avg, exp_avg_sq, ema, numel,
                                                              grad_sumsq, max_norm, grad_scale, lr, beta1, beta2, eps,
                                                              1.f, 1.f, ema_beta, step_counter);
   count_launch(2);

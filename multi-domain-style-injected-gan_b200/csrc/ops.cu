@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(msig_patch_geom g, co
                                                            const float* __restrict__ shift,
                                                            __nv_bfloat16* __restrict__ out, int tiles_w,
                                                            int64_t total_tiles, int win_cols) {
+  pdl_entry();
   extern __shared__ uint32_t gsm[];
   const int kgs = g.kpad / 8;
   uint32_t* tab = gsm;                                           // [8][kgs] window offsets (transposed)
@@ -138,6 +139,7 @@ __global__ void __launch_bounds__(256) patch_gather_kernel(msig_patch_geom g, co
 __global__ void patch_scatter_kernel(msig_patch_geom g, const __nv_bfloat16* __restrict__ dp,
                                      const float* __restrict__ scale, float* __restrict__ dsrc,
                                      int accumulate, int64_t total) {
+  pdl_entry();
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x) {
     const int iw = static_cast<int>(idx % g.w);
@@ -188,19 +190,23 @@ __global__ void patch_scatter_kernel(msig_patch_geom g, const __nv_bfloat16* __r
 // ---------------------------------------------------------------- padded image copies
 // fp32 NCHW [n,c,h,w] (c <= 8) -> bf16 [n][h+2p][w+2p+2][8], reflect or zero padding; channels >= c and
 // the two slack columns are zero. One thread per padded pixel (one 16-byte store).
+constexpr int kPad8Slack = 8;
 __global__ void img_pad8_kernel(const float* __restrict__ src, int c, int h, int w, int pad, int reflect,
                                 const float* __restrict__ scale, const float* __restrict__ shift,
                                 __nv_bfloat16* __restrict__ dst, int64_t total) {
+  pdl_entry();
   const int Hp = h + 2 * pad, Wp = w + 2 * pad + 2;
   const int64_t plane = int64_t(h) * w;
-  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
+  // `total` pixels plus kPad8Slack zero pixels behind the last row: the 8-pixel window of the last output
+  // columns of the last padded row reaches up to 7 - s pixels past the row (see msig_img_pad8 in msig.h)
+  for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total + kPad8Slack;
        idx += int64_t(gridDim.x) * blockDim.x) {
     const int px = static_cast<int>(idx % Wp);
     int64_t rem = idx / Wp;
     const int py = static_cast<int>(rem % Hp);
     const int64_t img = rem / Hp;
     int ih = py - pad, iw = px - pad;
-    bool ok = px < w + 2 * pad;
+    bool ok = px < w + 2 * pad && idx < total;
     if (reflect) {
       ih = reflect_idx(ih, h);
       iw = reflect_idx(iw, w);
@@ -222,6 +228,7 @@ __global__ void img_pad8_kernel(const float* __restrict__ src, int c, int h, int
 
 __global__ void reflect_fold_nchw_kernel(const float* __restrict__ dy, int h, int w, int pad,
                                          float* __restrict__ dx, int64_t total) {
+  pdl_entry();
   const int H2 = h + 2 * pad, W2 = w + 2 * pad;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < total;
        idx += int64_t(gridDim.x) * blockDim.x) {
@@ -336,6 +343,7 @@ __global__ void __launch_bounds__(256, FOLD ? 2 : 1) nc_reduce_kernel(
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
     const float* __restrict__ shift, int act, float slope, int hw, int c, int pix_per_block,
     float* __restrict__ partial, unsigned int* __restrict__ tickets, NcFinal fin, PadGeom pg = PadGeom{0, 0, 0, 0.f}) {
+  pdl_entry();
   __shared__ float red[16][256 + 1];
   __shared__ bool is_last;
   const int cg = c / 8;
@@ -469,6 +477,7 @@ __global__ void __launch_bounds__(1024) epi_stats_finalize_kernel(const float* _
                                                                   int ld, int hw, int c,
                                                                   const float* __restrict__ mean,
                                                                   const float* __restrict__ rstd, NcFinal fin) {
+  pdl_entry();
   __shared__ double red[2][32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 channels x 32 row lanes
   const int img = blockIdx.y;
@@ -531,6 +540,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_kernel(
     const __nv_bfloat16* __restrict__ x, const float* __restrict__ scale, const float* __restrict__ shift,
     const __nv_bfloat16* __restrict__ res, int act, float slope, int hw, int c, int pix_per_block,
     __nv_bfloat16* __restrict__ y, PadGeom pg = PadGeom{0, 0, 0, 0.f}) {
+  pdl_entry();
   const int cg = c / 8;
   const int lanes = 256 / cg;
   const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
@@ -597,6 +607,7 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(
     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ scale,
     const float* __restrict__ shift, const float* __restrict__ coef, int act, float slope, int hw, int c,
     int pix_per_block, __nv_bfloat16* __restrict__ dx, PadGeom pg = PadGeom{0, 0, 0, 0.f}) {
+  pdl_entry();
   const int cg = c / 8;
   const int lanes = 256 / cg;
   const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
@@ -656,6 +667,199 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(
   }
 }
 
+// ---- norm apply kernels that finish the epilogue partial sums themselves (no finalize launch) ----
+// For the 64x64 planes of the residual trunk an image has 32 partial rows, so every block can afford to fold
+// the [rows][2][c] partials of its image in its prologue (thread = channel, 32 loads in flight, double
+// accumulation in row order, so every block of an image derives bit-identical coefficients); block 0 of the
+// image also writes the per-(n,c) results the backward pass needs. The first batch of activation loads is
+// issued ahead of the fold so HBM latency overlaps it. Replaces epi_stats_finalize_kernel + the plain apply
+// (215 launches of ~7 us per training step).
+__device__ __forceinline__ void fold_partials(const float* __restrict__ pp, int rows, int ld, double& s1, double& s2) {
+  s1 = 0.0;
+  s2 = 0.0;
+  for (int r0 = 0; r0 < rows; r0 += 16) {
+    float a[16], b[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int r = min(r0 + u, rows - 1);          // clamped, unconditional: see epi_stats_finalize_kernel
+      a[u] = __ldg(pp + int64_t(r) * 2 * ld);
+      b[u] = __ldg(pp + int64_t(r) * 2 * ld + ld);
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const bool live = r0 + u < rows;
+      s1 += live ? double(a[u]) : 0.0;
+      s2 += live ? double(b[u]) : 0.0;
+    }
+  }
+}
+
+template <int U>
+__global__ void __launch_bounds__(256) norm_act_fwd_fin_kernel(
+    const __nv_bfloat16* __restrict__ x, const float* __restrict__ partial, int rows, int ld, NcFinal fin,
+    const __nv_bfloat16* __restrict__ res, int act, float slope, int hw, int c, int pix_per_block,
+    __nv_bfloat16* __restrict__ y) {
+  pdl_entry();
+  __shared__ float s_sc[512], s_sh[512];
+  const int cg = c / 8;
+  const int lanes = 256 / cg;
+  const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
+  const int img = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(p0 + pix_per_block, hw);
+  const int64_t base = int64_t(img) * hw * c + tx * 8;
+  uint4 xv[U], rv[U];
+  int p = p0 + ty;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int pp = p + u * lanes;
+    if (pp < p1) {
+      xv[u] = ldg_stream(x + base + int64_t(pp) * c);
+      if (res != nullptr) rv[u] = ldg_stream(res + base + int64_t(pp) * c);
+    }
+  }
+  for (int ch = threadIdx.x; ch < c; ch += 256) {
+    double s1, s2;
+    fold_partials(partial + int64_t(img) * rows * 2 * ld + ch, rows, ld, s1, s2);
+    const double m = s1 / hw;
+    double var = s2 / hw - m * m;
+    if (var < 0.0) var = 0.0;
+    const float r = static_cast<float>(1.0 / sqrt(var + double(fin.eps)));
+    const float gm = fin.gamma ? fin.gamma[img * fin.gb_stride + ch] : 1.f;
+    const float bt = fin.beta ? fin.beta[img * fin.gb_stride + ch] : 0.f;
+    const float scv = gm * r, shv = bt - static_cast<float>(m) * gm * r;
+    s_sc[ch] = scv;
+    s_sh[ch] = shv;
+    if (blockIdx.x == 0) {
+      const int o = img * c + ch;
+      fin.mean_out[o] = static_cast<float>(m);
+      fin.rstd_out[o] = r;
+      fin.scale_out[o] = scv;
+      fin.shift_out[o] = shv;
+    }
+  }
+  __syncthreads();
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = s_sc[tx * 8 + j];
+    sh[j] = s_sh[tx * 8 + j];
+  }
+  while (p < p1) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p1) {
+        float f[8];
+        unpack8(xv[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = act_fwd(f[j] * sc[j] + sh[j], act, slope);
+        if (res != nullptr) {
+          float rf[8];
+          unpack8(rv[u], rf);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] += rf[j];
+        }
+        store8(y + base + int64_t(pp) * c, f);
+      }
+    }
+    p += U * lanes;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p1) {
+        xv[u] = ldg_stream(x + base + int64_t(pp) * c);
+        if (res != nullptr) rv[u] = ldg_stream(res + base + int64_t(pp) * c);
+      }
+    }
+  }
+}
+
+// dx = scale*(g - c1 - xhat*c2) with c1, c2 folded from the dgrad epilogue's partials (sum g, sum g*x)
+template <int U>
+__global__ void __launch_bounds__(256, 2) norm_act_bwd_fin_kernel(
+    const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const float* __restrict__ partial,
+    int rows, int ld, const float* __restrict__ mean, const float* __restrict__ rstd,
+    const float* __restrict__ scale, const float* __restrict__ shift, NcFinal fin, int act, float slope, int hw,
+    int c, int pix_per_block, __nv_bfloat16* __restrict__ dx) {
+  pdl_entry();
+  __shared__ float s_sc[512], s_sh[512], s_k1[512], s_k2[512];
+  const int cg = c / 8;
+  const int lanes = 256 / cg;
+  const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
+  const int img = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_block;
+  const int p1 = min(p0 + pix_per_block, hw);
+  const int64_t base = int64_t(img) * hw * c + tx * 8;
+  uint4 xv[U], dv[U];
+  int p = p0 + ty;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int pp = p + u * lanes;
+    if (pp < p1) {
+      xv[u] = ldg_stream(x + base + int64_t(pp) * c);
+      dv[u] = ldg_stream(dy + base + int64_t(pp) * c);
+    }
+  }
+  for (int ch = threadIdx.x; ch < c; ch += 256) {
+    double s1, s2;
+    fold_partials(partial + int64_t(img) * rows * 2 * ld + ch, rows, ld, s1, s2);
+    const int o = img * c + ch;
+    const float mu = mean[o], rs = rstd[o], scv = scale[o];
+    const double sgx = double(rs) * (s2 - double(mu) * s1);   // sum g*xhat
+    const float c1 = static_cast<float>(s1 / hw), c2 = static_cast<float>(sgx / hw);
+    s_sc[ch] = scv;
+    s_sh[ch] = shift[o];
+    s_k1[ch] = -scv * rs * c2;
+    s_k2[ch] = -scv * (c1 - mu * rs * c2);
+    if (blockIdx.x == 0) {
+      fin.coef[(int64_t(img) * 2 + 0) * c + ch] = c1;
+      fin.coef[(int64_t(img) * 2 + 1) * c + ch] = c2;
+      if (fin.dgamma != nullptr) {
+        const int64_t oo = img * fin.dgb_stride + ch;
+        fin.dgamma[oo] = (fin.accumulate ? fin.dgamma[oo] : 0.f) + static_cast<float>(sgx);
+        fin.dbeta[oo] = (fin.accumulate ? fin.dbeta[oo] : 0.f) + static_cast<float>(s1);
+      }
+    }
+  }
+  __syncthreads();
+  float sc[8], sh[8], k1[8], k2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = s_sc[tx * 8 + j];
+    sh[j] = s_sh[tx * 8 + j];
+    k1[j] = s_k1[tx * 8 + j];
+    k2[j] = s_k2[tx * 8 + j];
+  }
+  while (p < p1) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p1) {
+        float xf[8], df[8];
+        unpack8(xv[u], xf);
+        unpack8(dv[u], df);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float uu = xf[j] * sc[j] + sh[j];
+          const float gq = df[j] * act_grad(uu, act, slope);
+          df[j] = sc[j] * gq + (k1[j] * xf[j] + k2[j]);
+        }
+        store8(dx + base + int64_t(pp) * c, df);
+      }
+    }
+    p += U * lanes;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int pp = p + u * lanes;
+      if (pp < p1) {
+        xv[u] = ldg_stream(x + base + int64_t(pp) * c);
+        dv[u] = ldg_stream(dy + base + int64_t(pp) * c);
+      }
+    }
+  }
+}
+
 // Pixels per block of the per-(n,c) kernels (grid = (chunks, n)). `bps` = resident 256-thread blocks per
 // SM of the kernel at hand (register-limited: 4 for the statistics, 3 for the forward apply, 2 for the
 // backward kernels): when the batch allows it the grid is ONE full wave of resident blocks, so no
@@ -675,6 +879,7 @@ static int pick_pix_per_block(int n, int hw, int bps = 0) {
 // ---------------------------------------------------------------- simple elementwise kernels
 __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
                                int act, float slope, int64_t groups, __nv_bfloat16* __restrict__ dz) {
+  pdl_entry();
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < groups;
        i += int64_t(gridDim.x) * blockDim.x) {
     float a[8], b[8];
@@ -686,15 +891,18 @@ __global__ void act_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_
   }
 }
 __global__ void f32_to_bf16_kernel(const float* __restrict__ x, int64_t n, __nv_bfloat16* __restrict__ y) {
+  pdl_entry();
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
     y[i] = __float2bfloat16(x[i]);
 }
 __global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ x, int64_t n, float* __restrict__ y) {
+  pdl_entry();
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
     y[i] = __bfloat162float(x[i]);
 }
 __global__ void tanh_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ y, int64_t n,
                                 float* __restrict__ dz) {
+  pdl_entry();
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < n; i += int64_t(gridDim.x) * blockDim.x)
     dz[i] = dy[i] * (1.f - y[i] * y[i]);
 }
@@ -706,6 +914,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
                                                      int c, int rows_per_block, float* __restrict__ db,
                                                      int accumulate, float* __restrict__ partial,
                                                      unsigned int* ticket) {
+  pdl_entry();
   __shared__ float red[8][256 + 1];
   __shared__ bool is_last;
   const int cg = c / 8;
@@ -753,6 +962,7 @@ __global__ void __launch_bounds__(256) nchw_chansum_kernel(const float* __restri
                                                            int64_t img_stride, float* __restrict__ out,
                                                            int accumulate, float* __restrict__ partial,
                                                            unsigned int* tickets) {
+  pdl_entry();
   const int ch = blockIdx.y;
   const int64_t total = int64_t(n) * hw;
   float s = 0.f;
@@ -786,6 +996,7 @@ __global__ void __launch_bounds__(256) nchw_chansum_kernel(const float* __restri
 // ---------------------------------------------------------------- pooling
 __global__ void maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int n, int h, int w, int c,
                                     __nv_bfloat16* __restrict__ y, int64_t groups) {
+  pdl_entry();
   const int cg = c / 8, oh = h / 2, ow = w / 2;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < groups;
        idx += int64_t(gridDim.x) * blockDim.x) {
@@ -814,6 +1025,7 @@ __global__ void maxpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, int n, 
 __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                                     int n, int h, int w, int c, __nv_bfloat16* __restrict__ dx,
                                     int64_t groups) {
+  pdl_entry();
   const int cg = c / 8, oh = h / 2, ow = w / 2;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < groups;
        idx += int64_t(gridDim.x) * blockDim.x) {
@@ -850,6 +1062,7 @@ __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const 
 // [n,hw,c] -> [n,c] mean; one block per image, (c/8) x lanes threads
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int hw, int c,
                                                           __nv_bfloat16* __restrict__ y) {
+  pdl_entry();
   __shared__ float red[8][256 + 1];
   const int img = blockIdx.x;
   for (int c0 = 0; c0 < c; c0 += 512) {   // 64 groups of 8 channels per pass
@@ -878,6 +1091,7 @@ __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const __nv_bfloat16* _
 }
 __global__ void avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int hw, int c,
                                    __nv_bfloat16* __restrict__ dx, int64_t groups) {
+  pdl_entry();
   const int cg = c / 8;
   const float inv = 1.f / hw;
   for (int64_t idx = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; idx < groups;
@@ -906,6 +1120,7 @@ __device__ __forceinline__ int wrap_head(long long k, int heads) {
 __global__ void head_gather_kernel(const float* __restrict__ all, const int64_t* __restrict__ idx, int n,
                                    int pix, int heads_ld, int heads, int per_head, int head_major,
                                    float* __restrict__ out) {
+  pdl_entry();
   const int64_t total = int64_t(n) * pix * per_head;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total;
        i += int64_t(gridDim.x) * blockDim.x) {
@@ -926,6 +1141,7 @@ __global__ void head_gather_kernel(const float* __restrict__ all, const int64_t*
 __global__ void head_scatter_kernel(const float* __restrict__ dout, const int64_t* __restrict__ idx, int n,
                                     int pix, int heads_ld, int heads, int per_head, int head_major,
                                     float* __restrict__ dall) {
+  pdl_entry();
   const int64_t total = int64_t(n) * pix * heads_ld * per_head;
   for (int64_t i = blockIdx.x * int64_t(blockDim.x) + threadIdx.x; i < total;
        i += int64_t(gridDim.x) * blockDim.x) {
@@ -960,11 +1176,11 @@ using namespace msig;
 // [32,64,64,256] (profiles/probe/norm_unroll_r2.txt): forward 4 (27.7 us; 6: 30.7), backward 6 (46.1 us; 4: 50.0).
 template <typename... Args>
 static void launch_norm_fwd(dim3 grid, cudaStream_t st, Args... args) {
-  norm_act_fwd_kernel<false, 4><<<grid, 256, 0, st>>>(args...);
+  MSIG_LAUNCH((norm_act_fwd_kernel<false, 4>), grid, 256, 0, st, args...);
 }
 template <typename... Args>
 static void launch_norm_bwd(dim3 grid, cudaStream_t st, Args... args) {
-  norm_act_bwd_kernel<false, 6><<<grid, 256, 0, st>>>(args...);
+  MSIG_LAUNCH((norm_act_bwd_kernel<false, 6>), grid, 256, 0, st, args...);
 }
 
 
@@ -982,7 +1198,7 @@ int msig_patch_gather(const msig_patch_geom* g, const float* src, const float* s
   const size_t smem = (size_t(g->kpad) + size_t(g->c) * g->r * win_cols) * 4;
   MSIG_REQUIRE(smem <= 48 * 1024, "msig_patch_gather: window too large for shared memory (%zu B)", smem);
   const int blocks = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(tiles, 148 * 6)));
-  patch_gather_kernel<<<blocks, 256, smem, ST(stream)>>>(*g, src, scale, shift, BF(patches), tiles_w, tiles,
+  MSIG_LAUNCH((patch_gather_kernel), blocks, 256, smem, ST(stream), *g, src, scale, shift, BF(patches), tiles_w, tiles,
                                                          win_cols);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
@@ -993,7 +1209,7 @@ int msig_patch_scatter(const msig_patch_geom* g, const void* dpatches, const flo
                        int accumulate, void* stream) {
   MSIG_REQUIRE(g && dpatches && dsrc, "msig_patch_scatter: null argument");
   const int64_t total = int64_t(g->n) * g->c * g->h * g->w;
-  patch_scatter_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, ST(stream)>>>(*g, CBF(dpatches), scale, dsrc,
+  MSIG_LAUNCH((patch_scatter_kernel), grid_for(total, 256, 148 * 32), 256, 0, ST(stream), *g, CBF(dpatches), scale, dsrc,
                                                                               accumulate, total);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
@@ -1006,7 +1222,7 @@ int msig_img_pad8(const float* src_nchw, int32_t n, int32_t c, int32_t h, int32_
                "msig_img_pad8: bad argument");
   MSIG_REQUIRE((scale == nullptr) == (shift == nullptr), "msig_img_pad8: scale and shift go together");
   const int64_t total = int64_t(n) * (h + 2 * pad) * (w + 2 * pad + 2);
-  img_pad8_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, ST(stream)>>>(src_nchw, c, h, w, pad, reflect, scale, shift,
+  MSIG_LAUNCH((img_pad8_kernel), grid_for(total + kPad8Slack, 256, 148 * 32), 256, 0, ST(stream), src_nchw, c, h, w, pad, reflect, scale, shift,
                                                                           BF(dst), total);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
@@ -1017,7 +1233,7 @@ int msig_reflect_fold_nchw(const float* dy_padded, int32_t n, int32_t c, int32_t
                            void* stream) {
   MSIG_REQUIRE(dy_padded && dx && pad < h && pad < w, "msig_reflect_fold_nchw: bad argument");
   const int64_t total = int64_t(n) * c * h * w;
-  reflect_fold_nchw_kernel<<<grid_for(total, 256, 148 * 32), 256, 0, ST(stream)>>>(dy_padded, h, w, pad, dx, total);
+  MSIG_LAUNCH((reflect_fold_nchw_kernel), grid_for(total, 256, 148 * 32), 256, 0, ST(stream), dy_padded, h, w, pad, dx, total);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -1046,8 +1262,8 @@ int msig_in_stats(const void* x, int32_t n, int32_t hw, int32_t c, float eps, co
   NcFinal fin{};
   fin.eps = eps; fin.gamma = gamma; fin.beta = beta; fin.gb_stride = gb_stride;
   fin.mean_out = mean; fin.rstd_out = rstd; fin.scale_out = scale; fin.shift_out = shift;
-  nc_reduce_kernel<0><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), nullptr, nullptr, nullptr, nullptr,
-                                                              nullptr, 0, 0.f, hw, c, ppb, partial, tickets, fin);
+  MSIG_LAUNCH((nc_reduce_kernel<0>), dim3(chunks, n), 256, 0, ST(stream), CBF(x), nullptr, nullptr, nullptr, nullptr,
+                                                              nullptr, 0, 0.f, hw, c, ppb, partial, tickets, fin, PadGeom{0, 0, 0, 0.f});
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -1084,8 +1300,8 @@ int msig_norm_act_bwd(const void* dy, const void* x, const float* mean, const fl
   MSIG_CHECK_CUDA(cudaMemsetAsync(tickets, 0, size_t(n) * sizeof(unsigned int), ST(stream)));
   NcFinal fin{};
   fin.coef = coef; fin.dgamma = dgamma; fin.dbeta = dbeta; fin.dgb_stride = dgb_stride; fin.accumulate = accumulate_dgb;
-  nc_reduce_kernel<1><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), CBF(dy), mean, rstd, scale, shift, act,
-                                                              slope, hw, c, ppb, partial, tickets, fin);
+  MSIG_LAUNCH((nc_reduce_kernel<1>), dim3(chunks, n), 256, 0, ST(stream), CBF(x), CBF(dy), mean, rstd, scale, shift, act,
+                                                              slope, hw, c, ppb, partial, tickets, fin, PadGeom{0, 0, 0, 0.f});
   MSIG_CHECK_LAUNCH();
   launch_norm_bwd(dim3(chunks, n), ST(stream), CBF(dy), CBF(x), mean, rstd, scale, shift,
                   static_cast<const float*>(coef), act, slope, hw, c, ppb, BF(dx), PadGeom{0, 0, 0, 0.f});
@@ -1107,7 +1323,7 @@ int msig_norm_act_fwd_pad(const void* x, const float* scale, const float* shift,
   const int hw = h * w;
   const int ppb = padnorm_ppb(n, hw);
   const int chunks = static_cast<int>(ceil_div(hw, ppb));
-  norm_act_fwd_kernel<true><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), scale, shift, nullptr, act, slope, hw, c,
+  MSIG_LAUNCH((norm_act_fwd_kernel<true>), dim3(chunks, n), 256, 0, ST(stream), CBF(x), scale, shift, nullptr, act, slope, hw, c,
                                                                     ppb, BF(y_padded), PadGeom{w, h, pad, 1.f / w});
   count_launch(1);
   MSIG_CHECK_LAUNCH();
@@ -1141,10 +1357,10 @@ int msig_norm_act_bwd_pad(const void* dy_padded, const void* x, const float* mea
   NcFinal fin{};
   fin.coef = coef;
   const PadGeom pg{w, h, pad, 1.f / w};
-  nc_reduce_kernel<1, true><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(x), CBF(dy_padded), mean, rstd, scale, shift,
+  MSIG_LAUNCH((nc_reduce_kernel<1, true>), dim3(chunks, n), 256, 0, ST(stream), CBF(x), CBF(dy_padded), mean, rstd, scale, shift,
                                                                     act, slope, hw, c, ppb, partial, tickets, fin, pg);
   MSIG_CHECK_LAUNCH();
-  norm_act_bwd_kernel<true><<<dim3(chunks, n), 256, 0, ST(stream)>>>(CBF(dy_padded), CBF(x), mean, rstd, scale, shift,
+  MSIG_LAUNCH((norm_act_bwd_kernel<true>), dim3(chunks, n), 256, 0, ST(stream), CBF(dy_padded), CBF(x), mean, rstd, scale, shift,
                                                                     coef, act, slope, hw, c, ppb, BF(dx), pg);
   count_launch(2);
   MSIG_CHECK_LAUNCH();
@@ -1159,7 +1375,7 @@ int msig_in_stats_from_partials(const float* partial, int32_t n, int32_t rows_pe
   NcFinal fin{};
   fin.eps = eps; fin.gamma = gamma; fin.beta = beta; fin.gb_stride = gb_stride;
   fin.mean_out = mean; fin.rstd_out = rstd; fin.scale_out = scale; fin.shift_out = shift;
-  epi_stats_finalize_kernel<0><<<dim3(c / 32, n), 1024, 0, ST(stream)>>>(partial, rows_per_img, ld, hw, c, nullptr,
+  MSIG_LAUNCH((epi_stats_finalize_kernel<0>), dim3(c / 32, n), 1024, 0, ST(stream), partial, rows_per_img, ld, hw, c, nullptr,
                                                                         nullptr, fin);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
@@ -1176,7 +1392,7 @@ int msig_norm_bwd_from_partials(const float* partial, int32_t n, int32_t rows_pe
   MSIG_REQUIRE((dgamma == nullptr) == (dbeta == nullptr), "msig_norm_bwd_from_partials: dgamma/dbeta go together");
   NcFinal fin{};
   fin.coef = coef; fin.dgamma = dgamma; fin.dbeta = dbeta; fin.dgb_stride = dgb_stride; fin.accumulate = accumulate_dgb;
-  epi_stats_finalize_kernel<1><<<dim3(c / 32, n), 1024, 0, ST(stream)>>>(partial, rows_per_img, ld, hw, c, mean, rstd,
+  MSIG_LAUNCH((epi_stats_finalize_kernel<1>), dim3(c / 32, n), 1024, 0, ST(stream), partial, rows_per_img, ld, hw, c, mean, rstd,
                                                                         fin);
   MSIG_CHECK_LAUNCH();
   const int ppb = pick_pix_per_block(n, hw, 2);
@@ -1189,9 +1405,49 @@ int msig_norm_bwd_from_partials(const float* partial, int32_t n, int32_t rows_pe
   return MSIG_OK;
 }
 
+int msig_norm_act_fwd_from_partials(const float* partial, int32_t n, int32_t rows_per_img, int32_t ld, int32_t hw,
+                                    int32_t c, float eps, const float* gamma, const float* beta, int64_t gb_stride,
+                                    float* mean, float* rstd, float* scale, float* shift, const void* x,
+                                    const void* residual, int32_t act, float slope, void* y, void* stream) {
+  MSIG_REQUIRE(partial && mean && rstd && scale && shift && x && y, "msig_norm_act_fwd_from_partials: null argument");
+  MSIG_REQUIRE(norm_c_ok(c) && rows_per_img > 0 && ld >= c, "msig_norm_act_fwd_from_partials: bad shape");
+  NcFinal fin{};
+  fin.eps = eps; fin.gamma = gamma; fin.beta = beta; fin.gb_stride = gb_stride;
+  fin.mean_out = mean; fin.rstd_out = rstd; fin.scale_out = scale; fin.shift_out = shift;
+  const int ppb = pick_pix_per_block(n, hw, 3);
+  const int chunks = static_cast<int>(ceil_div(hw, ppb));
+  MSIG_LAUNCH((norm_act_fwd_fin_kernel<4>), dim3(chunks, n), 256, 0, ST(stream), CBF(x), partial, rows_per_img, ld, fin,
+                                                                     CBF(residual), act, slope, hw, c, ppb, BF(y));
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
+int msig_norm_bwd_from_partials_fused(const float* partial, int32_t n, int32_t rows_per_img, int32_t ld, const void* g,
+                                      const void* x, const float* mean, const float* rstd, const float* scale,
+                                      const float* shift, int32_t hw, int32_t c, void* dx, float* dgamma,
+                                      float* dbeta, int64_t dgb_stride, int accumulate_dgb, float* coef,
+                                      void* stream) {
+  MSIG_REQUIRE(partial && g && x && mean && rstd && scale && shift && dx && coef,
+               "msig_norm_bwd_from_partials_fused: null argument");
+  MSIG_REQUIRE(norm_c_ok(c) && rows_per_img > 0 && ld >= c, "msig_norm_bwd_from_partials_fused: bad shape");
+  MSIG_REQUIRE((dgamma == nullptr) == (dbeta == nullptr),
+               "msig_norm_bwd_from_partials_fused: dgamma/dbeta go together");
+  NcFinal fin{};
+  fin.coef = coef; fin.dgamma = dgamma; fin.dbeta = dbeta; fin.dgb_stride = dgb_stride; fin.accumulate = accumulate_dgb;
+  const int ppb = pick_pix_per_block(n, hw, 2);
+  const int chunks = static_cast<int>(ceil_div(hw, ppb));
+  MSIG_LAUNCH((norm_act_bwd_fin_kernel<6>), dim3(chunks, n), 256, 0, ST(stream), 
+      CBF(g), CBF(x), partial, rows_per_img, ld, mean, rstd, scale, shift, fin, static_cast<int>(MSIG_ACT_NONE), 0.f,
+      hw, c, ppb, BF(dx));
+  count_launch(1);
+  MSIG_CHECK_LAUNCH();
+  return MSIG_OK;
+}
+
 int msig_act_bwd(const void* dy, const void* y, int32_t act, float slope, int64_t numel, void* dz, void* stream) {
   MSIG_REQUIRE(dy && y && dz && numel % 8 == 0, "msig_act_bwd: bad argument");
-  act_bwd_kernel<<<grid_for(numel / 8, 256), 256, 0, ST(stream)>>>(CBF(dy), CBF(y), act, slope, numel / 8, BF(dz));
+  MSIG_LAUNCH((act_bwd_kernel), grid_for(numel / 8, 256), 256, 0, ST(stream), CBF(dy), CBF(y), act, slope, numel / 8, BF(dz));
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -1212,7 +1468,7 @@ int msig_colsum(const void* dy, int64_t rows, int32_t c, float* db, int accumula
   float* partial = reinterpret_cast<float*>(workspace);
   unsigned int* ticket = reinterpret_cast<unsigned int*>(partial + size_t(blocks) * c);
   MSIG_CHECK_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned int), ST(stream)));
-  colsum_kernel<<<blocks, 256, 0, ST(stream)>>>(CBF(dy), rows, c, rpb, db, accumulate, partial, ticket);
+  MSIG_LAUNCH((colsum_kernel), blocks, 256, 0, ST(stream), CBF(dy), rows, c, rpb, db, accumulate, partial, ticket);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -1229,7 +1485,7 @@ int msig_nchw_chansum(const float* x, int32_t n, int32_t c, int64_t hw, int64_t 
   float* partial = reinterpret_cast<float*>(workspace);
   unsigned int* tickets = reinterpret_cast<unsigned int*>(partial + size_t(c) * blocks);
   MSIG_CHECK_CUDA(cudaMemsetAsync(tickets, 0, size_t(c) * sizeof(unsigned int), ST(stream)));
-  nchw_chansum_kernel<<<dim3(blocks, c), 256, 0, ST(stream)>>>(x, n, c, hw, img_stride, out, accumulate, partial,
+  MSIG_LAUNCH((nchw_chansum_kernel), dim3(blocks, c), 256, 0, ST(stream), x, n, c, hw, img_stride, out, accumulate, partial,
                                                               tickets);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
@@ -1239,7 +1495,7 @@ int msig_nchw_chansum(const float* x, int32_t n, int32_t c, int64_t hw, int64_t 
 int msig_maxpool2_fwd(const void* x, int32_t n, int32_t h, int32_t w, int32_t c, void* y, void* stream) {
   MSIG_REQUIRE(x && y && h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "msig_maxpool2_fwd: bad argument");
   const int64_t groups = int64_t(n) * (h / 2) * (w / 2) * (c / 8);
-  maxpool2_fwd_kernel<<<grid_for(groups, 256, 148 * 32), 256, 0, ST(stream)>>>(CBF(x), n, h, w, c, BF(y), groups);
+  MSIG_LAUNCH((maxpool2_fwd_kernel), grid_for(groups, 256, 148 * 32), 256, 0, ST(stream), CBF(x), n, h, w, c, BF(y), groups);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -1249,7 +1505,7 @@ int msig_maxpool2_bwd(const void* dy, const void* x, const void* y, int32_t n, i
   (void)y;
   MSIG_REQUIRE(dy && x && dx && h % 2 == 0 && w % 2 == 0 && c % 8 == 0, "msig_maxpool2_bwd: bad argument");
   const int64_t groups = int64_t(n) * (h / 2) * (w / 2) * (c / 8);
-  maxpool2_bwd_kernel<<<grid_for(groups, 256, 148 * 32), 256, 0, ST(stream)>>>(CBF(dy), CBF(x), n, h, w, c, BF(dx),
+  MSIG_LAUNCH((maxpool2_bwd_kernel), grid_for(groups, 256, 148 * 32), 256, 0, ST(stream), CBF(dy), CBF(x), n, h, w, c, BF(dx),
                                                                               groups);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
@@ -1257,7 +1513,7 @@ int msig_maxpool2_bwd(const void* dy, const void* x, const void* y, int32_t n, i
 }
 int msig_avgpool_fwd(const void* x, int32_t n, int32_t hw, int32_t c, void* y, void* stream) {
   MSIG_REQUIRE(x && y && c % 64 == 0, "msig_avgpool_fwd: bad argument");
-  avgpool_fwd_kernel<<<n, 256, 0, ST(stream)>>>(CBF(x), hw, c, BF(y));
+  MSIG_LAUNCH((avgpool_fwd_kernel), n, 256, 0, ST(stream), CBF(x), hw, c, BF(y));
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -1265,7 +1521,7 @@ int msig_avgpool_fwd(const void* x, int32_t n, int32_t hw, int32_t c, void* y, v
 int msig_avgpool_bwd(const void* dy, int32_t n, int32_t hw, int32_t c, void* dx, void* stream) {
   MSIG_REQUIRE(dy && dx && c % 8 == 0, "msig_avgpool_bwd: bad argument");
   const int64_t groups = int64_t(n) * hw * (c / 8);
-  avgpool_bwd_kernel<<<grid_for(groups, 256), 256, 0, ST(stream)>>>(CBF(dy), hw, c, BF(dx), groups);
+  MSIG_LAUNCH((avgpool_bwd_kernel), grid_for(groups, 256), 256, 0, ST(stream), CBF(dy), hw, c, BF(dx), groups);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
@@ -1275,7 +1531,7 @@ int msig_head_gather(const float* all, const int64_t* idx, int32_t n, int32_t pi
                      int32_t heads, int32_t per_head, int32_t head_major, float* out, void* stream) {
   MSIG_REQUIRE(all && out && heads >= 1 && heads <= heads_ld, "msig_head_gather: bad argument");
   const int64_t total = int64_t(n) * pix * per_head;
-  head_gather_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(all, idx, n, pix, heads_ld, heads, per_head,
+  MSIG_LAUNCH((head_gather_kernel), grid_for(total, 256), 256, 0, ST(stream), all, idx, n, pix, heads_ld, heads, per_head,
                                                                   head_major, out);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
@@ -1285,7 +1541,7 @@ int msig_head_scatter(const float* dout, const int64_t* idx, int32_t n, int32_t 
                       int32_t heads, int32_t per_head, int32_t head_major, float* dall, void* stream) {
   MSIG_REQUIRE(dout && dall && heads >= 1 && heads <= heads_ld, "msig_head_scatter: bad argument");
   const int64_t total = int64_t(n) * pix * heads_ld * per_head;
-  head_scatter_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(dout, idx, n, pix, heads_ld, heads, per_head,
+  MSIG_LAUNCH((head_scatter_kernel), grid_for(total, 256), 256, 0, ST(stream), dout, idx, n, pix, heads_ld, heads, per_head,
                                                                    head_major, dall);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
@@ -1294,21 +1550,21 @@ int msig_head_scatter(const float* dout, const int64_t* idx, int32_t n, int32_t 
 
 int msig_f32_to_bf16(const float* x, int64_t numel, void* y, void* stream) {
   MSIG_REQUIRE(x && y, "msig_f32_to_bf16: null argument");
-  f32_to_bf16_kernel<<<grid_for(numel, 256), 256, 0, ST(stream)>>>(x, numel, BF(y));
+  MSIG_LAUNCH((f32_to_bf16_kernel), grid_for(numel, 256), 256, 0, ST(stream), x, numel, BF(y));
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
 }
 int msig_bf16_to_f32(const void* x, int64_t numel, float* y, void* stream) {
   MSIG_REQUIRE(x && y, "msig_bf16_to_f32: null argument");
-  bf16_to_f32_kernel<<<grid_for(numel, 256), 256, 0, ST(stream)>>>(CBF(x), numel, y);
+  MSIG_LAUNCH((bf16_to_f32_kernel), grid_for(numel, 256), 256, 0, ST(stream), CBF(x), numel, y);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
 }
 int msig_tanh_bwd(const float* dy, const float* y, int64_t numel, float* dz, void* stream) {
   MSIG_REQUIRE(dy && y && dz, "msig_tanh_bwd: null argument");
-  tanh_bwd_kernel<<<grid_for(numel, 256), 256, 0, ST(stream)>>>(dy, y, numel, dz);
+  MSIG_LAUNCH((tanh_bwd_kernel), grid_for(numel, 256), 256, 0, ST(stream), dy, y, numel, dz);
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;

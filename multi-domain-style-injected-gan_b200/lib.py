@@ -55,6 +55,7 @@ _SIGS = {
     "msig_last_error": (c_char_p, []),
     "msig_sm_count": (c_int, []),
     "msig_debug_set_m2_mode": (c_int, [c_int]),
+    "msig_debug_set_pdl": (c_int, [c_int]),
     "msig_debug_set_wgrad_mode": (c_int, [c_int]),
     "msig_debug_set_pair_mode": (c_int, [c_int]),
     "msig_debug_set_ring_mode": (c_int, [c_int]),
@@ -103,6 +104,10 @@ _SIGS = {
                                             c_int64, _P, _P, _P, _P, _P]),
     "msig_norm_bwd_from_partials": (c_int, [_P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, c_int32,
                                             c_int32, _P, _P, _P, c_int64, c_int, _P, _P]),
+    "msig_norm_act_fwd_from_partials": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P,
+                                                c_int64, _P, _P, _P, _P, _P, _P, c_int32, c_float, _P, _P]),
+    "msig_norm_bwd_from_partials_fused": (c_int, [_P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, c_int32,
+                                                  c_int32, _P, _P, _P, c_int64, c_int, _P, _P]),
     "msig_act_bwd": (c_int, [_P, _P, c_int32, c_float, c_int64, _P, _P]),
     "msig_colsum_workspace": (c_size_t, [c_int64, c_int32]),
     "msig_colsum": (c_int, [_P, c_int64, c_int32, _P, c_int, _P, c_size_t, _P]),

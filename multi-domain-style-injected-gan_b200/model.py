@@ -852,6 +852,8 @@ class _DiscriminatorFn(torch.autograd.Function):
             for kx, br in enumerate(mod.domain_branches):
                 ops.wgrad_unpack(WPACK_IM2COL_FLIP, 1, 512, 4, 4, ws, splits, pgh.kpad * 512, _grad_buf(br[1].weight),
                                  oc=nd, o_off=kx)
+            # (after the last unpack: nchw_chansum takes its scratch from the same stream workspace `ws` lives in)
+            for kx, br in enumerate(mod.domain_branches):
                 ops.nchw_chansum(dall, _grad_buf(br[1].bias), n=B, c=1, hw=h * w, img_stride=nd * h * w,
                                  offset=kx * h * w)
         for j in (3, 2, 1):

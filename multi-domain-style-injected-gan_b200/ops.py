@@ -225,7 +225,9 @@ def img_pad8(src, pad, reflect, scale=None, shift=None):
     """fp32 NCHW image (c <= 8) -> bf16 [n, h+2p, w+2p+2, 8], reflect or zero padded (row-patch convs);
     with scale / shift ([c] fp32) the stored value is x*scale + shift (padding stays 0)."""
     n, c, h, w = src.shape
-    out = torch.empty((n, h + 2 * pad, w + 2 * pad + 2, 8), dtype=BF16, device=src.device)
+    numel = n * (h + 2 * pad) * (w + 2 * pad + 2) * 8
+    # + 8 zeroed slack pixels (MSIG_PAD8_SLACK_PIXELS): the last windows of the last row read past the row
+    out = torch.empty(numel + 64, dtype=BF16, device=src.device)[:numel].view(n, h + 2 * pad, w + 2 * pad + 2, 8)
     L.call("msig_img_pad8", _p(src), n, c, h, w, pad, int(reflect), _p(scale), _p(shift), _p(out), _stream())
     return out
 
@@ -388,12 +390,30 @@ def patch_wgrad(kind, o, i, r, s, rows, a, m, b, ncols, dw, accumulate=True, oc=
 
 # ------------------------------------------------------------------ InstanceNorm / AdaIN
 class NormStats:
-    """mean / rstd / scale / shift, each fp32 [n, c] (one allocation)."""
-    __slots__ = ("buf", "mean", "rstd", "scale", "shift")
+    """mean / rstd / scale / shift, each fp32 [n, c] (one allocation). `pending` holds the arguments of a
+    finalize that has not run yet: norm_act_fwd folds it into its own launch (msig_norm_act_fwd_from_partials);
+    any other consumer calls ready() first."""
+    __slots__ = ("buf", "mean", "rstd", "scale", "shift", "pending")
 
     def __init__(self, n, c, device):
         self.buf = torch.empty((4, n, c), dtype=F32, device=device)
         self.mean, self.rstd, self.scale, self.shift = self.buf[0], self.buf[1], self.buf[2], self.buf[3]
+        self.pending = None
+
+    def ready(self):
+        if self.pending is not None:
+            es, hw, c, gamma, beta, gb_stride, eps = self.pending
+            self.pending = None
+            L.call("msig_in_stats_from_partials", _p(es.buf), es.n, es.rows, es.ld, hw, c, eps, _p(gamma), _p(beta),
+                   gb_stride, _p(self.mean), _p(self.rstd), _p(self.scale), _p(self.shift), _stream())
+        return self
+
+
+# Epilogue partial sums of at most this many rows per image are folded by the apply kernels themselves
+# (one launch instead of finalize + apply); 0 = always the separate finalize kernel (A/B: MSIG_FIN_FOLD_ROWS).
+# Every block of an image repeats the fold, so it only pays for few rows: a 64x64 plane has 128 rows (32 tiles x
+# 4 accumulator quadrants), i.e. 256 KB of L2 reads per block at 256 channels -- those keep the finalize kernel.
+FIN_FOLD_ROWS = int(__import__('os').environ.get('MSIG_FIN_FOLD_ROWS', '32'))
 
 
 def in_stats(x, gamma=None, beta=None, gb_stride=0, eps=1e-5):
@@ -407,10 +427,12 @@ def in_stats(x, gamma=None, beta=None, gb_stride=0, eps=1e-5):
 
 
 def in_stats_from(es, hw, c, gamma=None, beta=None, gb_stride=0, eps=1e-5):
-    """InstanceNorm / AdaIN statistics from epilogue partial sums (no pass over the activation)."""
+    """InstanceNorm / AdaIN statistics from epilogue partial sums (no pass over the activation). With few
+    partial rows per image the finalize is deferred into the norm_act_fwd launch that consumes it."""
     st = NormStats(es.n, c, es.buf.device)
-    L.call("msig_in_stats_from_partials", _p(es.buf), es.n, es.rows, es.ld, hw, c, eps, _p(gamma), _p(beta),
-           gb_stride, _p(st.mean), _p(st.rstd), _p(st.scale), _p(st.shift), _stream())
+    st.pending = (es, hw, c, gamma, beta, gb_stride, eps)
+    if es.rows > FIN_FOLD_ROWS:
+        st.ready()
     return st
 
 
@@ -420,8 +442,10 @@ def norm_bwd_from(es, g, x, st, dgamma=None, dbeta=None, dgb_stride=0, accumulat
     n, h, w, c = x.shape
     if out is None:
         out = torch.empty_like(x)
+    st.ready()
     coef = torch.empty((n, 2, c), dtype=F32, device=x.device)
-    L.call("msig_norm_bwd_from_partials", _p(es.buf), n, es.rows, es.ld, _p(g), _p(x), _p(st.mean), _p(st.rstd),
+    fn = "msig_norm_bwd_from_partials_fused" if es.rows <= FIN_FOLD_ROWS else "msig_norm_bwd_from_partials"
+    L.call(fn, _p(es.buf), n, es.rows, es.ld, _p(g), _p(x), _p(st.mean), _p(st.rstd),
            _p(st.scale), _p(st.shift), h * w, c, _p(out), _p(dgamma), _p(dbeta), dgb_stride, int(accumulate_dgb),
            _p(coef), _stream())
     return out
@@ -431,6 +455,13 @@ def norm_act_fwd(x, st, act=ACT_NONE, residual=None, slope=0.2, out=None):
     n, h, w, c = x.shape
     if out is None:
         out = torch.empty_like(x)
+    if st.pending is not None:
+        es, hw, c_, gamma, beta, gb_stride, eps = st.pending
+        st.pending = None
+        L.call("msig_norm_act_fwd_from_partials", _p(es.buf), es.n, es.rows, es.ld, hw, c_, eps, _p(gamma),
+               _p(beta), gb_stride, _p(st.mean), _p(st.rstd), _p(st.scale), _p(st.shift), _p(x), _p(residual),
+               act, slope, _p(out), _stream())
+        return out
     L.call("msig_norm_act_fwd", _p(x), _p(st.scale), _p(st.shift), _p(residual), act, slope, n, h * w, c,
            _p(out), _stream())
     return out
@@ -440,6 +471,7 @@ def norm_act_fwd_pad(x, st, act, pad, slope=0.2):
     """norm-apply + activation written straight into the reflect-padded buffer [n, h+2p, w+2p, c]."""
     n, h, w, c = x.shape
     out = torch.empty((n, h + 2 * pad, w + 2 * pad, c), dtype=BF16, device=x.device)
+    st.ready()
     L.call("msig_norm_act_fwd_pad", _p(x), _p(st.scale), _p(st.shift), act, slope, n, h, w, c, pad, _p(out), _stream())
     return out
 
@@ -450,6 +482,7 @@ def norm_act_bwd_pad(dy_padded, x, st, act, pad, slope=0.2):
     out = torch.empty_like(x)
     nbytes = L.load().msig_norm_act_bwd_pad_workspace(n, h, w, c)
     ws = workspace(nbytes, x.device)
+    st.ready()
     L.call("msig_norm_act_bwd_pad", _p(dy_padded), _p(x), _p(st.mean), _p(st.rstd), _p(st.scale), _p(st.shift),
            act, slope, n, h, w, c, pad, _p(out), _p(ws), ws.numel(), _stream())
     return out
@@ -462,6 +495,7 @@ def norm_act_bwd(dy, x, st, act=ACT_NONE, slope=0.2, dgamma=None, dbeta=None, dg
         out = torch.empty_like(x)
     nbytes = L.load().msig_in_stats_workspace(n, h * w, c)
     ws = workspace(nbytes, x.device)
+    st.ready()
     L.call("msig_norm_act_bwd", _p(dy), _p(x), _p(st.mean), _p(st.rstd), _p(st.scale), _p(st.shift),
            None, 0, act, slope, n, h * w, c, _p(out), _p(dgamma), _p(dbeta), dgb_stride,
            int(accumulate_dgb), _p(ws), ws.numel(), _stream())

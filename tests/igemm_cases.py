@@ -103,6 +103,63 @@ def case_dgrad_mask_from_z(n, c, h, w, k, r, stride, pad, act, seed=0):
     return (rel_err(nchw(outs[1][0]), ref) if same else 1.0), 1e-2
 
 
+def case_fused_finalize(n, c, h, w, act, residual, seed=0):
+    """AdaIN forward / backward whose apply kernels fold the conv epilogue's partial sums themselves
+    (msig_norm_act_fwd_from_partials / msig_norm_bwd_from_partials_fused, model.py:28-36,51-55) against the
+    separate finalize kernel + plain apply, and against torch fp32 InstanceNorm on the same bf16 conv output."""
+    ops.ensure_init()
+    x = nhwc(_bf(_rand((n, c, h, w), seed)).to(DEV))
+    wt = _bf(_rand((c, c, 3, 3), seed + 1, 1.0 / (c * 9) ** 0.5)).to(DEV)
+    wf = ops.wpack(L.WPACK_FWD, wt.float().contiguous(), c, c, 3, 3)
+    wd = ops.wpack(L.WPACK_DGRAD_S1, wt.float().contiguous(), c, c, 3, 3)
+    g = ops.conv_geom(n, h, w, c, c, 3, 3, 1, 1, 1, h, w)
+    gb = torch.cat([1.0 + 0.3 * _rand((n, c), seed + 2), 0.3 * _rand((n, c), seed + 3)], 1).to(DEV)   # [gamma | beta]
+    dy = nhwc(_bf(_rand((n, c, h, w), seed + 4)).to(DEV))
+    keep = ops.FIN_FOLD_ROWS
+    res = {}
+    try:
+        for fold in (1 << 20, 0):
+            ops.FIN_FOLD_ROWS = fold
+            es = ops.epi_stats(n, h, w, c, torch.device(DEV))
+            assert es is not None
+            z = ops.conv2d_fwd(x, wf, g, ops.epilogue(stats=es))
+            st = ops.in_stats_from(es, h * w, c, gb[:, 0:], gb[:, c:], 2 * c)
+            assert (st.pending is not None) == (fold > 0)
+            y = ops.norm_act_fwd(z, st, act, residual=x if residual else None)
+            assert st.pending is None
+            # backward: dgrad of dy with the reductions of the norm backward in its epilogue (sum g, sum g*z)
+            es2 = ops.epi_stats(n, h, w, c, torch.device(DEV))
+            gq = ops.conv2d_dgrad(dy, wd, g, ops.epilogue(stats=es2, stats_z=z))
+            dgam = torch.zeros((n, 2 * c), device=DEV)
+            dz = ops.norm_bwd_from(es2, gq, z, st, dgamma=dgam[:, 0:], dbeta=dgam[:, c:], dgb_stride=2 * c)
+            torch.cuda.synchronize()
+            res[fold] = (z, st.buf.clone(), y, gq, dz, dgam)
+    finally:
+        ops.FIN_FOLD_ROWS = keep
+    a, b = res[1 << 20], res[0]
+    assert torch.equal(a[0], b[0]) and torch.equal(a[3], b[3])
+    errs = [rel_err(a[1][i], b[1][i]) * 1e2 for i in range(4)]          # statistics: 1e-6 (scaled to the 1e-2 bound)
+    errs += [rel_err(a[2], b[2]), rel_err(a[4], b[4]), rel_err(a[5], b[5]) * 1e2]
+    # torch fp32 on the same bf16 z / g
+    zf = nchw(a[0]).float().requires_grad_(True)
+    gamma = gb[:, :c].reshape(n, c, 1, 1)
+    beta = gb[:, c:].reshape(n, c, 1, 1)
+    yr = F.instance_norm(zf, eps=1e-5) * gamma + beta
+    if act == L.ACT_RELU:
+        yr = F.relu(yr)
+    if residual:
+        yr = yr + nchw(x).float()
+    errs.append(rel_err(nchw(a[2]), yr))
+    yn = F.instance_norm(zf, eps=1e-5) * gamma + beta                  # g already carries the mask: ACT_NONE backward
+    (dzr,) = torch.autograd.grad(yn, zf, nchw(a[3]).float())
+    errs.append(rel_err(nchw(a[4]), dzr))
+    xhat = F.instance_norm(zf.detach(), eps=1e-5)
+    gf = nchw(a[3]).float()
+    errs.append(rel_err(a[5][:, :c], (gf * xhat).sum((2, 3))) * 5)     # dgamma / dbeta: fp32 outputs, 2e-3
+    errs.append(rel_err(a[5][:, c:], gf.sum((2, 3))) * 5)
+    return max(errs), 1e-2
+
+
 def case_conv_wgrad(n, c, h, w, k, r, stride, pad, seed=0):
     ops.ensure_init()
     oh = (h + 2 * pad - r) // stride + 1
@@ -338,7 +395,7 @@ def case_repeatability(reps=12, seed=0):
     def fwd_stats():
         es = ops.epi_stats(4, 64, 64, 256, torch.device(DEV))
         y = ops.conv2d_fwd(x256h, wf, g256, ops.epilogue(stats=es))
-        st = ops.in_stats_from(es, 4096, 256)
+        st = ops.in_stats_from(es, 4096, 256).ready()
         return [y, st.buf]
 
     def dgrad_mask_red():
@@ -432,6 +489,9 @@ CASES = {
     "convT_wgrad_128_64_per_tap_plan": lambda: case_convT(2, 128, 64, 64, 64, which="wgrad", wgrad_mode=1),
     "rowpatch_first_wgrad_unstacked_plan": lambda: case_rowpatch_first(2, 64, 256, "wgrad", wgrad_mode=2),
     "rowpatch_first_wgrad_tall": lambda: case_rowpatch_first(1, 133, 64, "wgrad", seed=9),
+    "fused_finalize_adain_relu_256": lambda: case_fused_finalize(2, 256, 64, 64, L.ACT_RELU, False),
+    "fused_finalize_adain_res_256_b5": lambda: case_fused_finalize(5, 256, 64, 64, L.ACT_NONE, True, seed=3),
+    "fused_finalize_512_16x16": lambda: case_fused_finalize(3, 512, 16, 16, L.ACT_NONE, False, seed=5),
     "gram_64": lambda: case_gram(2, 64, 64, 64),
     "gram_256_b3": lambda: case_gram(3, 256, 16, 16),
     "gram_bwd_128": lambda: case_gram_bwd(2, 128, 32, 32),

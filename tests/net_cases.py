@@ -32,6 +32,7 @@ which rounds to bf16 at exactly the points where the CUDA path stores a tensor (
       noise fails (2); a defect smaller than it (3 % of one weight gradient) fails (1) / the layer-wise test.
 Measured margins of the round are committed as profiles/parity_r2.json (written by tests/test_gpu_nets.py).
 """
+import os
 import torch
 
 import msig_b200  # noqa: F401
