@@ -37,7 +37,7 @@ int msig_init(int device);               /* binds the device, resolves cuTensorM
 int msig_version(void);
 const char* msig_last_error(void);       /* thread-local */
 int msig_sm_count(void);
-int msig_debug_set_ring_mode(int mode);   /* test hook: strip-ring kernel for 64-channel layers: bit 0 on, bit 1 four convT phases in one launch, bits 8..15 ring-depth cap; default 3 */
+int msig_debug_set_ring_mode(int mode);   /* test hook: strip-ring kernel for 64-channel layers: bit 0 on, bit 1 four convT phases in one launch, bit 2 legacy per-output-row MMA order, bits 8..15 ring-depth cap; default 3 */
 int msig_debug_set_wgrad_mode(int mask);  /* test hook: bit 0 = M-stacked row-patch weight gradients, bit 1 = tap-grouped convT ones; default 3 */
 int msig_debug_set_m2_mode(int on);       /* test hook: two m-tiles per CTA for the 128-wide conv tiles, default on */
 int msig_debug_set_pdl(int on);           /* test hook: programmatic dependent launch of every kernel (csrc/common.h), default OFF (measured: no gain);

@@ -689,9 +689,11 @@ int32_t msig_epilogue_stats_rows(int32_t oh, int32_t ow, int32_t phases) {
 }
 
 // Test hook: ring kernel for the 64-channel stride-1 layers. Bit 0: on; bit 1: the four phases of a transposed
-// conv share one launch; bits 8..15: cap on the ring depth (0 = whatever fits). Default 3.
+// conv share one launch; bit 2: legacy issue order (one N = 64 MMA chain per OUTPUT row instead of the row-stacked
+// N = 64 x R MMAs per input row); bits 8..15: cap on the ring depth (0 = whatever fits). Default 3.
 int msig_debug_set_ring_mode(int mode) {
   g_ring_mode = mode & 3;
+  set_ring_legacy((mode & 4) != 0);
   set_ring_slots_cap((mode >> 8) & 0xff);
   return MSIG_OK;
 }

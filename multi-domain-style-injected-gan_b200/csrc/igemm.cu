@@ -1140,7 +1140,9 @@ static inline int ring_slot_bytes(int S) { return ((kTileM + S - 1) * 128 + 1023
 __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __grid_constant__ FpropParams p) {
   pdl_entry();
   constexpr int BLOCK_N = 64;
-  constexpr int NACC = 4;                  // accumulator stages in TMEM (64 columns each)
+  constexpr int kMaxAcc = 8;
+  const bool STACK = p.ring_stack != 0;
+  const int NACC = STACK ? 8 : 4;          // accumulator stages in TMEM (64 columns each)
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -1155,8 +1157,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + SLOTS * slot_bytes);
   uint64_t* empty_bar = full_bar + kRingMaxSlots;
   uint64_t* tfull_bar = empty_bar + kRingMaxSlots;
-  uint64_t* tempty_bar = tfull_bar + NACC;
-  uint64_t* wfull_bar = tempty_bar + NACC;
+  uint64_t* tempty_bar = tfull_bar + kMaxAcc;
+  uint64_t* wfull_bar = tempty_bar + kMaxAcc;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wfull_bar + 1);
   const uint32_t strip_tx = static_cast<uint32_t>(kTileM + S - 1) * 128u;
   // phase interleave: CTA b -> phase b % NPH, item sequence b / NPH, b / NPH + gridDim / NPH, ...
@@ -1183,7 +1185,9 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
     mbar_init(wfull_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc(tmem_slot, NACC * BLOCK_N);
+  if (warp == 2) {
+    if (STACK) tmem_alloc(tmem_slot, 512); else tmem_alloc(tmem_slot, 256);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1203,10 +1207,13 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
     if (elect_one()) {
       // resident filter, in ring order: slot (r*S + s)*CB + cb <- K block (tap(r,s)*CB + cb) of the packed matrix
       mbar_expect_tx(wfull_bar, static_cast<uint32_t>(R * S * CB) * kRingWBytes);
+      // (row-stacked mode: the R filter rows of one (s, cb) sit back to back, r descending, as ONE N = 64 R operand)
       for (int t = 0; t < R * S; ++t)
-        for (int cb = 0; cb < CB; ++cb)
-          tma_load_2d(wsm + (t * CB + cb) * kRingWBytes, &p.tmB, wfull_bar, (p.ring_tap[t] * CB + cb) * kBlockK,
+        for (int cb = 0; cb < CB; ++cb) {
+          const int dst = STACK ? ((t % S) * CB + cb) * R + (R - 1 - t / S) : t * CB + cb;
+          tma_load_2d(wsm + dst * kRingWBytes, &p.tmB, wfull_bar, (p.ring_tap[t] * CB + cb) * kBlockK,
                       ph * p.b_row_per_phase);
+        }
     }
     __syncwarp();
     uint32_t slot = 0, sphase = 0;
@@ -1261,6 +1268,108 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
       while (x >= static_cast<uint32_t>(SLOTS)) { x -= SLOTS; par ^= 1u; }
       sl = x;
     };
+    // Row-stacked issue order (ring_stack): an input-row strip feeds the R output rows y, y-1, .. y-R+1 through the
+    // filter rows r = 0 .. R-1. Their accumulators sit side by side in TMEM (output row `it` in stage it % 8), and
+    // the R filter-row tiles of one (s, cb) sit back to back in shared memory (r descending), so ONE N = 64 R MMA
+    // per (strip, s, k) replaces R N = 64 MMAs: the N = 64 instruction is bound by its 6 KiB of shared-memory
+    // operand reads (~60 cycles for 32 cycles of math); at N = 192 the A strip is read once for three rows' worth.
+    // Pieces: an MMA may not wrap around the 8 stages, N <= 256, and the first MMA into a NEW output row
+    // overwrites (accumulate = 0) that row's 64 columns only.
+    if (STACK) {
+      uint32_t gs = 0, gp = 0;               // ring cursor: strips are consumed strictly in load order
+      int it0 = 0;                           // running output-row counter at the start of the item
+      for (int item = cta0; item < items; item += cta_stride) {
+        int img, tw, h0, nrows;
+        decode(item, img, tw, h0, nrows);
+        const int nin = nrows + R - 1;
+        for (int j = 0; j < nin; ++j) {
+          const int i_lo = max(0, j - R + 1), i_hi = min(nrows - 1, j);
+          const int nb = i_hi - i_lo + 1;
+          const bool has_new = j <= nrows - 1;
+          RING_PROF_T(t0);
+          if (has_new) {
+            const int itn = it0 + j;
+            mbar_wait(&tempty_bar[itn & 7], (((itn >> 3) & 1) ^ 1u));
+          }
+          RING_PROF_T(t1);
+          {
+            uint32_t sl = gs, par = gp;
+            for (int cb = 0; cb < CB; ++cb) {
+              mbar_wait(&full_bar[sl], par);
+              if (++sl == static_cast<uint32_t>(SLOTS)) { sl = 0; par ^= 1u; }
+            }
+          }
+          RING_PROF_T(t2);
+          RING_PROF_ADD(m_te, t0, t1);
+          RING_PROF_ADD(m_fu, t1, t2);
+          tc_fence_after();
+          if (elect_one()) {
+            const int b0 = R - 1 - (j - i_lo);           // first block of the stacked filter that takes part
+            const int s0 = (it0 + i_lo) & 7;             // TMEM stage of output row i_lo
+            // MMA pieces of this input row, fixed for all its (cb, s, k): (TMEM address, descriptor offset of the
+            // first filter block, instruction descriptor). The issue loop below is a handful of integer adds per MMA
+            // -- with per-MMA descriptor construction the single issuing thread, not the tensor pipe, set the pace.
+            uint32_t d0 = 0, d1 = 0, d2 = 0, i0 = 0, i1 = 0, i2 = 0, o1 = 0, o2 = 0;   // piece 0 starts at block 0
+            int np = 0;
+            for (int b = 0; b < nb;) {
+              const int stage = (s0 + b) & 7;
+              const int len = min(min(nb - b, 4), 8 - stage);
+              const uint32_t dd = tmem_base + stage * BLOCK_N, ii = make_idesc_bf16(kTileM, BLOCK_N * len, 0, 0);
+              const uint32_t oo = static_cast<uint32_t>(b * (kRingWBytes >> 4));
+              if (np == 0) { d0 = dd; i0 = ii; }
+              else if (np == 1) { d1 = dd; i1 = ii; o1 = oo; }
+              else { d2 = dd; i2 = ii; o2 = oo; }
+              ++np;
+              b += len;
+            }
+            const uint64_t wd0 = make_smem_desc(w_addr, 0, 1024) + static_cast<uint64_t>(b0 * (kRingWBytes >> 4));
+            uint32_t sl = gs;
+            for (int cb = 0; cb < CB; ++cb) {
+              const uint32_t sa = ring_addr + sl * slot_bytes;
+              for (int s = 0; s < S; ++s) {
+                const uint64_t da = make_smem_desc(sa + s * 128, 0, 1024);      // s pixels into the strip
+                const uint64_t db = wd0 + static_cast<uint64_t>(((s * CB + cb) * R) * (kRingWBytes >> 4));
+                int k = 0;
+                if (has_new && cb == 0 && s == 0) {
+                  // first MMA into the NEW output row (last block): overwrite its 64 columns, accumulate the others
+                  for (int b = 0; b < nb - 1;) {
+                    const int stage = (s0 + b) & 7;
+                    const int len = min(min(nb - 1 - b, 4), 8 - stage);
+                    umma_bf16(tmem_base + stage * BLOCK_N, da, db + static_cast<uint64_t>(b * (kRingWBytes >> 4)),
+                              make_idesc_bf16(kTileM, BLOCK_N * len, 0, 0), 1u);
+                    b += len;
+                  }
+                  umma_bf16(tmem_base + ((s0 + nb - 1) & 7) * BLOCK_N, da,
+                            db + static_cast<uint64_t>((nb - 1) * (kRingWBytes >> 4)),
+                            make_idesc_bf16(kTileM, BLOCK_N, 0, 0), 0u);
+                  k = 1;
+                }
+                for (; k < kBlockK / 16; ++k) {
+                  const uint64_t ak = da + 2 * k, bk = db + 2 * k;
+                  umma_bf16(d0, ak, bk, i0, 1u);
+                  if (np > 1) umma_bf16(d1, ak, bk + o1, i1, 1u);
+                  if (np > 2) umma_bf16(d2, ak, bk + o2, i2, 1u);
+                }
+              }
+              if (++sl == static_cast<uint32_t>(SLOTS)) sl = 0;
+            }
+            sl = gs;
+            for (int cb = 0; cb < CB; ++cb) {                                    // this input row is dead now
+              umma_commit(&empty_bar[sl]);
+              if (++sl == static_cast<uint32_t>(SLOTS)) sl = 0;
+            }
+            if (j >= R - 1) umma_commit(&tfull_bar[(it0 + j - R + 1) & 7]);      // output row j - R + 1 is complete
+          }
+          __syncwarp();
+          RING_PROF_T(t3);
+          RING_PROF_ADD(m_is, t2, t3);
+          gs += CB;
+          if (gs >= static_cast<uint32_t>(SLOTS)) { gs -= SLOTS; gp ^= 1u; }
+        }
+        it0 += nrows;
+      }
+      it = it0;
+    } else
     for (int item = cta0; item < items; item += cta_stride) {
       int img, tw, h0, nrows;
       decode(item, img, tw, h0, nrows);
@@ -1383,7 +1492,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, NACC * BLOCK_N);
+    if (STACK) tmem_dealloc(tmem_base, 512); else tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -1807,6 +1916,8 @@ static cudaError_t launch_fprop_t(const FpropParams& p, int num_sms, cudaStream_
 static bool g_pair_mode = true;
 static int g_ring_slots_cap = 0;      // test hook: > 0 caps the ring depth (8 = the fixed depth of earlier builds)
 void set_ring_slots_cap(int n) { g_ring_slots_cap = n; }
+static bool g_ring_legacy = false;    // test hook: per-output-row N = 64 MMAs
+void set_ring_legacy(bool on) { g_ring_legacy = on; }
 void set_pair_mode(bool on) { g_pair_mode = on; }
 
 static cudaError_t launch_fprop2(const FpropParams& p, int num_sms, cudaStream_t stream) {
@@ -1921,6 +2032,7 @@ cudaError_t launch_fprop_ring64(const FpropParams& p0, int num_sms, cudaStream_t
   const int slots = ring_slots_for(p.strip_r, p.strip_s, cbs);
   if (slots == 0 || p.TW != kTileM || p.TH != 1 || p.phases != nph || (nph != 1 && nph != 4) || p.n_blocks != 1)
     return cudaErrorInvalidValue;
+  p.ring_stack = g_ring_legacy ? 0 : 1;
   p.ring_slots = g_ring_slots_cap > 0 && g_ring_slots_cap < slots ? g_ring_slots_cap : slots;
   if (p.ring_slots < (p.strip_r + 1) * cbs) p.ring_slots = (p.strip_r + 1) * cbs;
   const int items = p.n_img * p.tiles_w * p.ring_chunks;

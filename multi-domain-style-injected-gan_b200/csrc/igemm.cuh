@@ -44,6 +44,8 @@ struct FpropParams {
   int32_t ring_cb;                // ring kernel: 64-channel blocks of the input (1 or 2; 0 means 1)
   int8_t ring_tap[16];            // ring kernel: filter position (r*S + s) -> tap index in the packed weights
   int32_t ring_slots;             // ring kernel: strips resident in shared memory (set by the launcher)
+  int32_t ring_stack;             // ring kernel: 1 = one MMA per INPUT row strip over all the output rows it feeds
+                                  //   (N = 64 x rows, accumulators of consecutive rows side by side in TMEM)
   int32_t ring_phases;            // ring kernel: 0/1, or 4 = CTA b runs output phase b % 4 (`phases` must be 4 too):
   int8_t ring_org_h[4], ring_org_w[4];   //   per-phase org_h / org_w; weights of phase ph start at B row ph*b_row_per_phase
   int32_t OH, OW, TH, TW;         // output plane and the 128-pixel tile (TH*TW == 128)
@@ -142,6 +144,7 @@ cudaError_t launch_rowfold(const RowfoldParams& p, int num_sms, cudaStream_t str
 cudaError_t launch_fprop_ring64(const FpropParams& p, int num_sms, cudaStream_t stream);
 int ring_slots_for(int R, int S, int cbs);   // ring depth the shape gets (0: does not fit the ring kernel)
 void set_ring_slots_cap(int n);              // test hook: > 0 caps the ring depth
+void set_ring_legacy(bool on);               // test hook: per-output-row N = 64 MMAs (the round-1 issue order)
 cudaError_t launch_wgrad(const WgradParams& p, int block_n, cudaStream_t stream);
 bool fprop_uses_pairs(const FpropParams& p, int block_n);
 bool fprop_uses_m2(const FpropParams& p, int block_n);   // call with tiles / phases / taps / n_blocks already set

@@ -160,6 +160,35 @@ def case_fused_finalize(n, c, h, w, act, residual, seed=0):
     return max(errs), 1e-2
 
 
+def with_ring_mode(mode, fn):
+    """Runs a case under a msig_debug_set_ring_mode value (4 = legacy per-output-row N = 64 MMA order) and restores
+    the default (3: ring on, four convT phases in one launch, row-stacked N = 64 R MMAs)."""
+    ops.ensure_init()
+    L.call("msig_debug_set_ring_mode", mode)
+    try:
+        return fn()
+    finally:
+        L.call("msig_debug_set_ring_mode", 3)
+
+
+def case_ring_stack_vs_legacy(n, h, w, r, seed=0):
+    """Row-stacked ring kernel against the legacy issue order on the same 64 -> 64 stride-1 conv: the accumulation
+    order over (r, s, k) differs (input-row major instead of output-row major), so the results agree to fp32
+    rounding of the accumulator, not bit for bit; both must match torch."""
+    ops.ensure_init()
+    x = _bf(_rand((n, 64, h, w), seed)).to(DEV)
+    wt = _bf(_rand((64, 64, r, r), seed + 1, 1.0 / (64 * r * r) ** 0.5)).to(DEV)
+    b = _rand((64,), seed + 2).to(DEV)
+    ref = F.relu(F.conv2d(x.float(), wt.float(), b, padding=r // 2))
+    wpk = ops.wpack(L.WPACK_FWD, wt.float().contiguous(), 64, 64, r, r)
+    g = ops.conv_geom(n, h, w, 64, 64, r, r, 1, r // 2, r // 2, h, w)
+    run = lambda: ops.conv2d_fwd(nhwc(x), wpk, g, ops.epilogue(bias=b, act=L.ACT_RELU))   # noqa: E731
+    y_new = run()
+    y_old = with_ring_mode(3 | 4, run)
+    torch.cuda.synchronize()
+    return max(rel_err(nchw(y_new), ref), rel_err(nchw(y_old), ref), rel_err(y_new, y_old)), 1e-2
+
+
 def case_conv_wgrad(n, c, h, w, k, r, stride, pad, seed=0):
     ops.ensure_init()
     oh = (h + 2 * pad - r) // stride + 1
@@ -444,6 +473,13 @@ CASES = {
     "ring_fwd_3x3_64_ragged": lambda: case_conv_fwd(3, 64, 40, 200, 64, 3, 1, 1, act=L.ACT_RELU),
     "ring_fwd_3x3_64_tall": lambda: case_conv_fwd(2, 64, 300, 128, 64, 3, 1, 1),
     "ring_dgrad_3x3_64_256w": lambda: case_conv_dgrad(2, 64, 48, 256, 64, 3, 1, 1),
+    "ring_stack_vs_legacy_3x3": lambda: case_ring_stack_vs_legacy(3, 40, 200, 3),
+    "ring_stack_vs_legacy_3x3_b32_tall": lambda: case_ring_stack_vs_legacy(5, 300, 128, 3, seed=2),
+    "ring_stack_1row_items": lambda: case_conv_fwd(2, 64, 1, 256, 64, 3, 1, 1, act=L.ACT_RELU, seed=3),
+    "ring_stack_2row_items": lambda: case_conv_fwd(3, 64, 2, 130, 64, 3, 1, 1, seed=4),
+    "ring_legacy_fwd_3x3_64_ragged": lambda: with_ring_mode(7, lambda: case_conv_fwd(3, 64, 40, 200, 64, 3, 1, 1, act=L.ACT_RELU)),
+    "ring_legacy_rowpatch_first_fwd": lambda: with_ring_mode(7, lambda: case_rowpatch_first(2, 64, 256, "fwd")),
+    "ring_legacy_convT_fwd_128_64": lambda: with_ring_mode(7, lambda: case_convT(2, 128, 24, 128, 64, which="fwd", ring_mode=7)),
     "fwd_4x4s2_64_128": lambda: case_conv_fwd(2, 64, 64, 64, 128, 4, 2, 1, act=L.ACT_LRELU),
     "fwd_4x4s2_256_512": lambda: case_conv_fwd(2, 256, 32, 32, 512, 4, 2, 1),
     "final7x7_pertap": lambda: case_final_conv(2, 64, 256),
