@@ -56,33 +56,50 @@ def step_flops(b, s=S):
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons with nvidia-smi during the timed region."""
+    """Samples SM clocks and throttle reasons during the timed region with ONE long-running
+    `nvidia-smi --query-gpu=... -lms 200` process (the recipe's clocks line, B200_PROFILING.md): spawning a new
+    nvidia-smi every 200 ms re-initialises NVML each time and costs the step under test ~1 %."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
         self.samples, self.max_mhz, self.reasons = [], None, set()
-        self._halt = threading.Event()
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+        super().start()
 
     def run(self):
-        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        while not self._halt.is_set():
+        if self.proc is None:
+            return
+        for line in self.proc.stdout:
+            out = line.strip().split(",")
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
                 self.samples.append(float(out[0]))
                 self.max_mhz = float(out[1])
-                for n, v in zip(names, out[2:]):
+                for n, v in zip(self.NAMES, out[2:]):
                     if v.strip().lower().startswith("active"):
                         self.reasons.add(n)
-            except Exception:
+            except (ValueError, IndexError):
                 pass
-            self._halt.wait(0.2)
 
     def stop(self):
-        self._halt.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
         self.join(timeout=5)
         s = sorted(self.samples)
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}

@@ -142,4 +142,6 @@ CASES = {
     "pad8_tail_guard": case_pad8_tail,
     "pad8_tail_guard_64": lambda: case_pad8_tail(2, 64, 64, seed=2),
     "poisoned_train_step_b2_s64": case_poisoned_train_step,
+    # BASELINE.json configs[0] shape (B=1, 256x256, 10 domains): the tilings of the bench workload
+    "poisoned_train_step_b1_s256_nd10": lambda: case_poisoned_train_step(1, 256, 10),
 }
