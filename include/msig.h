@@ -82,7 +82,15 @@ typedef struct msig_epilogue {
    * from the saved activation: `aux` is ignored and one 2-byte-per-element stream leaves the epilogue. */
   const float* mask_scale;
   const float* mask_shift;
+  /* 0: stats_partial has the per-tile rows of msig_epilogue_stats_rows. > 0 (= msig_ring_stats_rows of this layer):
+   * the strip-ring kernel writes ONE partial row per (work item, phase, accumulator quadrant) -- its lean epilogue
+   * keeps a pixel column's sums in registers over the item's rows (plain statistics only: no stats_z, no aux);
+   * any other kernel refuses the call. */
+  int32_t stats_rows;
 } msig_epilogue;
+/* rows of stats_partial PER IMAGE in the ring kernel's per-item layout (msig_epilogue.stats_rows); 0 = this layer does
+ * not run on the ring kernel. kind 0: msig_conv_rowpatch_fwd, 1: msig_convT2d_fwd, 2: msig_conv2d_fwd (64 -> 64, s1) */
+int32_t msig_ring_stats_rows(int32_t kind, const msig_conv_geom* g);
 /* rows of stats_partial PER IMAGE for an output plane oh x ow produced in `phases` (1, or 4 for the
  * k4 s2 transposed conv / stride-2 dgrad, where oh x ow is the per-phase plane = the INPUT plane). */
 int32_t msig_epilogue_stats_rows(int32_t oh, int32_t ow, int32_t phases);

@@ -448,6 +448,7 @@ static int fill_epilogue(FpropParams& p, const msig_epilogue* e, const OutView& 
   p.stat_out = e ? e->stats_partial : nullptr;
   p.stat_z = e ? reinterpret_cast<const __nv_bfloat16*>(e->stats_z) : nullptr;
   p.stat_ld = static_cast<int>(round_up(n_valid, 64));
+  p.ring_item_stats = (e && e->stats_partial && e->stats_rows > 0) ? e->stats_rows : 0;   // validated by the ring launcher
   if (e && e->ch_scale != nullptr)
     return set_error(MSIG_ERR_UNSUPPORTED, "epilogue ch_scale is only implemented by msig_conv_narrow_fwd");
   if (p.stat_out != nullptr && (ov.f32 || ov.sC != 1 || n_valid < 64 || p.fold_c != 0 || p.tap_is_image))
@@ -593,7 +594,8 @@ static int run_phased(const void* in, int n, int h, int w, int c, int k, const v
   // 128 -> 64 channel layers on wide planes (model.py:140 forward, the dgrad of model.py:132): every phase is
   // a 2x2 stride-1 conv; run each through the strip-ring kernel (resident 64 KiB filter slab, input rows
   // shared by consecutive output rows) instead of re-fetching 24 KiB per K block.
-  if (g_ring_mode != 0 && c == 128 && block_n == 64 && k_pad == 64 && w >= 128 && p.stat_out == nullptr) {
+  if (g_ring_mode != 0 && c == 128 && block_n == 64 && k_pad == 64 && w >= 128 &&
+      (p.stat_out == nullptr || (p.ring_item_stats != 0 && (g_ring_mode & 2) != 0))) {
     // input rows / columns of a phase in ascending order: ring position r <-> tap 1 - r
     auto ring_taps = [](FpropParams& q) {
       q.ring_cb = 2;
@@ -686,6 +688,35 @@ int32_t msig_epilogue_stats_rows(int32_t oh, int32_t ow, int32_t phases) {
   int TW, TH;
   pick_tile(ow, TW, TH);
   return static_cast<int32_t>(ceil_div(oh, TH) * ceil_div(ow, TW) * phases * 4);
+}
+
+// Rows PER IMAGE of msig_epilogue.stats_partial when the strip-ring kernel writes one partial row per (work item,
+// phase, accumulator quadrant) (msig_epilogue.stats_rows); 0: this layer does not run on the ring kernel (use the
+// per-tile rows of msig_epilogue_stats_rows, or a separate statistics pass). kind 0: msig_conv_rowpatch_fwd,
+// kind 1: msig_convT2d_fwd, kind 2: msig_conv2d_fwd (64 -> 64 channels, stride 1).
+int32_t msig_ring_stats_rows(int32_t kind, const msig_conv_geom* g) {
+  if (!g || g_ring_mode == 0 || !context_ready()) return 0;
+  FpropParams p;
+  init_fprop(p);
+  p.n_img = g->n;
+  int nph = 1;
+  if (kind == 0) {
+    if (pad_rows(g->k) != 64 || g->k != 64 || g->r > 7 || g->ow < 128 || g->stride != 1) return 0;
+    p.OH = g->oh; p.OW = g->ow;
+  } else if (kind == 1) {
+    if (g->c != 128 || g->k != 64 || g->w < 128 || (g_ring_mode & 2) == 0) return 0;
+    p.OH = g->h; p.OW = g->w;
+    nph = 4;
+  } else if (kind == 2) {
+    if (g->stride != 1 || g->c != 64 || g->k != 64 || g->r * g->s < 2 || g->r * g->s > 9 || g->r > 7 || g->s > 8 ||
+        g->ow < 128)
+      return 0;
+    p.OH = g->oh; p.OW = g->ow;
+  } else {
+    return 0;
+  }
+  set_ring(p, 1, 1, 0, 0, nph);
+  return static_cast<int32_t>(p.tiles_w * p.ring_chunks * nph * 4);
 }
 
 // Test hook: ring kernel for the 64-channel stride-1 layers. Bit 0: on; bit 1: the four phases of a transposed

@@ -370,9 +370,9 @@ __device__ __forceinline__ void fprop_epilogue_at(const FpropParams& p, int mt_f
 // Lean epilogue of the 64-wide tiles for the common case (see epilogue_is_lean): NC accumulator columns of one
 // output pixel -> alpha * acc + bias -> ReLU / LeakyReLU / none -> bf16, 32-byte stores. The accumulator stage is
 // handed back as soon as it sits in registers. `bias_r` stays in registers for the whole kernel.
-__device__ __forceinline__ bool epilogue_is_lean(const FpropParams& p, int block_n) {
-  return p.aux_mode == AUX_NONE && p.stat_out == nullptr && p.stat_z == nullptr && p.z_mask == 0 && !p.out_f32 &&
-         p.o_sc == 1 && p.fold_c == 0 && p.n_valid == block_n && p.n_blocks == 1 && p.act != ACT_TANH;
+__device__ __forceinline__ bool epilogue_is_lean(const FpropParams& p, int block_n, bool with_stats = false) {
+  return p.aux_mode == AUX_NONE && (with_stats || p.stat_out == nullptr) && p.stat_z == nullptr && p.z_mask == 0 &&
+         !p.out_f32 && p.o_sc == 1 && p.fold_c == 0 && p.n_valid == block_n && p.n_blocks == 1 && p.act != ACT_TANH;
 }
 template <int NC>
 __device__ __forceinline__ void epilogue_lean(const FpropParams& p, const float (&bias_r)[NC], float alpha, uint32_t taddr,
@@ -407,6 +407,49 @@ __device__ __forceinline__ void epilogue_lean(const FpropParams& p, const float 
     b.z = pack_bf16x2(v[8 * g + 12], v[8 * g + 13]);
     b.w = pack_bf16x2(v[8 * g + 14], v[8 * g + 15]);
     stg256(o + 8 * g, a, b);
+  }
+}
+
+// Lean epilogue that also accumulates the InstanceNorm statistics of the values AS STORED (bf16-rounded) into
+// per-thread registers: s1 += v, s2 += v*v for this thread's pixel, NC channels. The ring kernel's work item is a
+// column of consecutive output rows, so one thread sees the same 128-pixel column position row after row and needs
+// ONE warp transpose-reduce per item instead of one per tile (ring_item_stats). Bias comes from shared memory
+// (the registers hold the 2 x NC sums instead).
+template <int NC>
+__device__ __forceinline__ void epilogue_lean_stats(const FpropParams& p, const float* bias_s, float alpha, uint32_t taddr,
+                                                    uint64_t* tempty, bool store, __nv_bfloat16* o, float (&s1)[NC],
+                                                    float (&s2)[NC]) {
+  static_assert(NC == 32, "one tcgen05.ld.32x32b.x32 per call");
+  tc_fence_after();
+  uint32_t r[NC];
+  tmem_ld_32x32(taddr, r);
+  tmem_ld_wait();
+  tc_fence_before();
+  mbar_arrive(tempty);                            // the accumulator is in registers
+  if (!store) return;
+#pragma unroll
+  for (int g = 0; g < NC / 8; g += 2) {
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float a = fmaf(__uint_as_float(r[8 * g + 2 * j]), alpha, bias_s[8 * g + 2 * j]);
+      float b = fmaf(__uint_as_float(r[8 * g + 2 * j + 1]), alpha, bias_s[8 * g + 2 * j + 1]);
+      if (p.act == ACT_RELU) {
+        a = a > 0.f ? a : 0.f;
+        b = b > 0.f ? b : 0.f;
+      } else if (p.act == ACT_LRELU) {
+        a = a > 0.f ? a : a * p.slope;
+        b = b > 0.f ? b : b * p.slope;
+      }
+      const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      const float2 f = __bfloat1622float2(h);
+      s1[8 * g + 2 * j] += f.x;
+      s2[8 * g + 2 * j] = fmaf(f.x, f.x, s2[8 * g + 2 * j]);
+      s1[8 * g + 2 * j + 1] += f.y;
+      s2[8 * g + 2 * j + 1] = fmaf(f.y, f.y, s2[8 * g + 2 * j + 1]);
+      w[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    stg256(o + 8 * g, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
   }
 }
 
@@ -1133,7 +1176,7 @@ __device__ unsigned long long g_ring_prof[16];
 constexpr int kRingMaxSlots = 16;
 constexpr int kRingMaxTaps = 9;                    // resident [64][64] filter tiles (R * S * channel blocks)
 constexpr int kRingWBytes = 64 * 128;              // one tap: 64 output channels x 64 K
-constexpr int kRingBarBytes = 512;              // 2 x 16 ring + 2 x 8 accumulator barriers + filter barrier + TMEM slot
+constexpr int kRingBarBytes = 1024;             // 2 x 16 ring + 2 x 8 accumulator barriers + filter barrier + TMEM slot; +512: bias[64] fp32
 constexpr int kRingSmemMax = 232448;               // 227 KiB
 static inline int ring_slot_bytes(int S) { return ((kTileM + S - 1) * 128 + 1023) & ~1023; }
 
@@ -1187,6 +1230,11 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
   }
   if (warp == 2) {
     if (STACK) tmem_alloc(tmem_slot, 512); else tmem_alloc(tmem_slot, 256);
+  }
+  float* const bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 512);   // item-stats epilogue
+  if (warp == 3) {
+    bias_s[lane] = (p.bias != nullptr && lane < p.n_valid) ? __ldg(p.bias + lane) : 0.f;
+    bias_s[lane + 32] = (p.bias != nullptr && lane + 32 < p.n_valid) ? __ldg(p.bias + lane + 32) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -1449,6 +1497,33 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
 #ifdef MSIG_RING_PROFILE
     long long e_w = 0, e_ld = 0, e_m = 0;
 #endif
+    if (p.ring_item_stats != 0 && p.stat_out != nullptr && epilogue_is_lean(p, BLOCK_N, true)) {
+      // InstanceNorm statistics of the stored output, one partial row per (item, phase, quadrant): this thread's
+      // pixel column over the item's rows in registers, one warp transpose-reduce per item.
+      const int rows_per_img = p.tiles_w * p.ring_chunks * NPH * 4;
+      for (int item = cta0; item < items; item += cta_stride) {
+        int img, tw, h0, nrows;
+        decode(item, img, tw, h0, nrows);
+        const int ow = tw * kTileM + q * 32 + lane;
+        float s1[BLOCK_N / 2], s2[BLOCK_N / 2];
+#pragma unroll
+        for (int j = 0; j < BLOCK_N / 2; ++j) s1[j] = s2[j] = 0.f;
+        for (int i = 0; i < nrows; ++i, ++it) {
+          const int as = it % NACC;
+          mbar_wait(&tfull_bar[as], (it / NACC) & 1);
+          __nv_bfloat16* o = out_ph + img * p.o_sn + int64_t(h0 + i) * p.o_sh + int64_t(ow) * p.o_sw;
+          epilogue_lean_stats<BLOCK_N / 2>(p, bias_s + c_begin, alpha,
+                                           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c_begin,
+                                           &tempty_bar[as], ow < p.OW, o, s1, s2);
+        }
+        const float t1 = warp_col_reduce32(s1, lane);
+        const float t2 = warp_col_reduce32(s2, lane);
+        const int li = tw * p.ring_chunks + item % p.ring_chunks;
+        float* so = p.stat_out + ((int64_t(img) * rows_per_img + (li * NPH + ph) * 4 + q) * 2) * p.stat_ld + c_begin + lane;
+        so[0] = t1;
+        so[p.stat_ld] = t2;
+      }
+    } else
     for (int item = cta0; item < items; item += cta_stride) {
       int img, tw, h0, nrows;
       decode(item, img, tw, h0, nrows);
@@ -1971,6 +2046,7 @@ bool fprop_uses_pairs(const FpropParams& p, int block_n) {
 }
 
 cudaError_t launch_fprop(const FpropParams& p, int block_n, int num_sms, cudaStream_t stream) {
+  if (p.ring_item_stats != 0) return cudaErrorInvalidValue;   // per-item statistics rows exist in the ring kernel only
   if (fprop_uses_pairs(p, block_n)) return launch_fprop2(p, num_sms, stream);
   if (p.m2 != 0) return block_n == 128 ? launch_fprop_m2(p, num_sms, stream) : cudaErrorInvalidValue;
   switch (block_n) {
@@ -2033,6 +2109,12 @@ cudaError_t launch_fprop_ring64(const FpropParams& p0, int num_sms, cudaStream_t
   if (slots == 0 || p.TW != kTileM || p.TH != 1 || p.phases != nph || (nph != 1 && nph != 4) || p.n_blocks != 1)
     return cudaErrorInvalidValue;
   p.ring_stack = g_ring_legacy ? 0 : 1;
+  if (p.ring_item_stats != 0) {         // requested rows per image (msig_epilogue.stats_rows) must be what this launch writes
+    if (p.stat_out == nullptr || p.stat_z != nullptr || p.ring_item_stats != p.tiles_w * p.ring_chunks * nph * 4 ||
+        p.aux_mode != AUX_NONE || p.n_valid != 64 || p.out_f32 || p.o_sc != 1 || p.act == ACT_TANH)
+      return cudaErrorInvalidValue;
+    p.ring_item_stats = 1;
+  }
   p.ring_slots = g_ring_slots_cap > 0 && g_ring_slots_cap < slots ? g_ring_slots_cap : slots;
   if (p.ring_slots < (p.strip_r + 1) * cbs) p.ring_slots = (p.strip_r + 1) * cbs;
   const int items = p.n_img * p.tiles_w * p.ring_chunks;

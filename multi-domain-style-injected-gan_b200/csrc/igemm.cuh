@@ -44,6 +44,8 @@ struct FpropParams {
   int32_t ring_cb;                // ring kernel: 64-channel blocks of the input (1 or 2; 0 means 1)
   int8_t ring_tap[16];            // ring kernel: filter position (r*S + s) -> tap index in the packed weights
   int32_t ring_slots;             // ring kernel: strips resident in shared memory (set by the launcher)
+  int32_t ring_item_stats;        // ring kernel: 1 = stat_out holds ONE partial row per (work item, phase, accumulator
+                                  //   quadrant): the lean epilogue sums its pixels over the item's rows in registers
   int32_t ring_stack;             // ring kernel: 1 = one MMA per INPUT row strip over all the output rows it feeds
                                   //   (N = 64 x rows, accumulators of consecutive rows side by side in TMEM)
   int32_t ring_phases;            // ring kernel: 0/1, or 4 = CTA b runs output phase b % 4 (`phases` must be 4 too):

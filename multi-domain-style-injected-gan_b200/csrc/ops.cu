@@ -674,23 +674,51 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_kernel(
 // image also writes the per-(n,c) results the backward pass needs. The first batch of activation loads is
 // issued ahead of the fold so HBM latency overlaps it. Replaces epi_stats_finalize_kernel + the plain apply
 // (215 launches of ~7 us per training step).
-__device__ __forceinline__ void fold_partials(const float* __restrict__ pp, int rows, int ld, double& s1, double& s2) {
+__device__ __forceinline__ void fold_partials(const float* __restrict__ pp, int rows, int ld, int r_first, int r_step,
+                                              double& s1, double& s2) {
   s1 = 0.0;
   s2 = 0.0;
-  for (int r0 = 0; r0 < rows; r0 += 16) {
+  for (int r0 = r_first; r0 < rows; r0 += 16 * r_step) {
     float a[16], b[16];
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
-      const int r = min(r0 + u, rows - 1);          // clamped, unconditional: see epi_stats_finalize_kernel
+      const int r = min(r0 + u * r_step, rows - 1);   // clamped, unconditional: see epi_stats_finalize_kernel
       a[u] = __ldg(pp + int64_t(r) * 2 * ld);
       b[u] = __ldg(pp + int64_t(r) * 2 * ld + ld);
     }
 #pragma unroll
     for (int u = 0; u < 16; ++u) {
-      const bool live = r0 + u < rows;
+      const bool live = r0 + u * r_step < rows;
       s1 += live ? double(a[u]) : 0.0;
       s2 += live ? double(b[u]) : 0.0;
     }
+  }
+}
+
+// Per-(image, channel) totals of the partial rows for a 256-thread block: 256 / c row lanes per channel (1 at 256
+// channels, 4 at 64), folded in lane order through shared memory, so the result does not depend on the block.
+// Calls fin(ch, s1, s2) on the thread that owns channel ch. All threads of the block must call it.
+template <typename F>
+__device__ __forceinline__ void fold_image_partials(const float* __restrict__ img_partial, int rows, int ld, int c,
+                                                    double (&s_p)[2][256], F fin) {
+  for (int c0 = 0; c0 < c; c0 += 256) {
+    const int cw = min(256, c - c0);
+    const int lanes = 256 / cw;
+    const int cl = threadIdx.x % cw, ln = threadIdx.x / cw;
+    double a = 0.0, b = 0.0;
+    if (ln < lanes) fold_partials(img_partial + c0 + cl, rows, ld, ln, lanes, a, b);
+    s_p[0][threadIdx.x] = a;
+    s_p[1][threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.x < cw) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int l = 0; l < lanes; ++l) {
+        s1 += s_p[0][l * cw + threadIdx.x];
+        s2 += s_p[1][l * cw + threadIdx.x];
+      }
+      fin(c0 + threadIdx.x, s1, s2);
+    }
+    __syncthreads();
   }
 }
 
@@ -718,9 +746,8 @@ __global__ void __launch_bounds__(256) norm_act_fwd_fin_kernel(
       if (res != nullptr) rv[u] = ldg_stream(res + base + int64_t(pp) * c);
     }
   }
-  for (int ch = threadIdx.x; ch < c; ch += 256) {
-    double s1, s2;
-    fold_partials(partial + int64_t(img) * rows * 2 * ld + ch, rows, ld, s1, s2);
+  __shared__ double s_p[2][256];
+  fold_image_partials(partial + int64_t(img) * rows * 2 * ld, rows, ld, c, s_p, [&](int ch, double s1, double s2) {
     const double m = s1 / hw;
     double var = s2 / hw - m * m;
     if (var < 0.0) var = 0.0;
@@ -737,8 +764,7 @@ __global__ void __launch_bounds__(256) norm_act_fwd_fin_kernel(
       fin.scale_out[o] = scv;
       fin.shift_out[o] = shv;
     }
-  }
-  __syncthreads();
+  });
   float sc[8], sh[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -801,9 +827,8 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_fin_kernel(
       dv[u] = ldg_stream(dy + base + int64_t(pp) * c);
     }
   }
-  for (int ch = threadIdx.x; ch < c; ch += 256) {
-    double s1, s2;
-    fold_partials(partial + int64_t(img) * rows * 2 * ld + ch, rows, ld, s1, s2);
+  __shared__ double s_p[2][256];
+  fold_image_partials(partial + int64_t(img) * rows * 2 * ld, rows, ld, c, s_p, [&](int ch, double s1, double s2) {
     const int o = img * c + ch;
     const float mu = mean[o], rs = rstd[o], scv = scale[o];
     const double sgx = double(rs) * (s2 - double(mu) * s1);   // sum g*xhat
@@ -821,8 +846,7 @@ __global__ void __launch_bounds__(256, 2) norm_act_bwd_fin_kernel(
         fin.dbeta[oo] = (fin.accumulate ? fin.dbeta[oo] : 0.f) + static_cast<float>(s1);
       }
     }
-  }
-  __syncthreads();
+  });
   float sc[8], sh[8], k1[8], k2[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {

@@ -30,7 +30,7 @@ class Epilogue(Structure):
     _fields_ = [("bias", c_void_p), ("aux", c_void_p), ("aux_mode", c_int32), ("act", c_int32),
                 ("alpha", c_float), ("alpha_ptr", c_void_p), ("slope", c_float),
                 ("out_layout", c_int32), ("stats_partial", c_void_p), ("stats_z", c_void_p),
-                ("ch_scale", c_void_p), ("mask_scale", c_void_p), ("mask_shift", c_void_p)]
+                ("ch_scale", c_void_p), ("mask_scale", c_void_p), ("mask_shift", c_void_p), ("stats_rows", c_int32)]
 
 
 class WpackDesc(Structure):
@@ -100,6 +100,7 @@ _SIGS = {
     "msig_norm_act_bwd_pad": (c_int, [_P, _P, _P, _P, _P, _P, c_int32, c_float, c_int32, c_int32, c_int32, c_int32,
                                       c_int32, _P, _P, c_size_t, _P]),
     "msig_epilogue_stats_rows": (c_int32, [c_int32, c_int32, c_int32]),
+    "msig_ring_stats_rows": (c_int32, [c_int32, _P]),
     "msig_in_stats_from_partials": (c_int, [_P, c_int32, c_int32, c_int32, c_int32, c_int32, c_float, _P, _P,
                                             c_int64, _P, _P, _P, _P, _P]),
     "msig_norm_bwd_from_partials": (c_int, [_P, c_int32, c_int32, c_int32, _P, _P, _P, _P, _P, _P, c_int32,

@@ -50,6 +50,11 @@ def _conv_stats(x, wpk, g, gamma=None, beta=None, gstride=0, transposed=False):
     """conv (or k4 s2 transposed conv) whose epilogue also emits the InstanceNorm / AdaIN statistics of
     its output: returns (z, NormStats). Replaces conv + a separate statistics pass (model.py:16,28-36)."""
     if not ops.epi_fusable(4 if transposed else g.r * g.s, g.c):   # short K: the epilogue would dominate
+        es = ops.ring_stats(ops.RING_CONVT if transposed else ops.RING_CONV, g, x.device)
+        if es is not None:      # strip-ring kernel: per-item statistics out of the lean epilogue
+            e = ops.epilogue(stats=es)
+            z = ops.convT2d_fwd(x, wpk, g, e) if transposed else ops.conv2d_fwd(x, wpk, g, e)
+            return z, ops.in_stats_from(es, g.oh * g.ow, g.k, gamma, beta, gstride)
         z = ops.convT2d_fwd(x, wpk, g) if transposed else ops.conv2d_fwd(x, wpk, g)
         return z, ops.in_stats(z, gamma, beta, gstride)
     if transposed:
@@ -414,8 +419,10 @@ class _GeneratorFn(torch.autograd.Function):
         # ---- content encoder (model.py:130-134)
         # 7x7 reflect conv on the 3-channel image: row-patch implicit GEMM over the padded bf16 copy
         g0 = ops.conv_geom(B, H, W, 3, 64, 7, 7, 1, 3, 3, H, W)
-        z0 = ops.conv_rowpatch_fwd(ops.img_pad8_cached(img, 3, True), P["e0"], g0)
-        st0 = ops.in_stats(z0)
+        es0 = ops.ring_stats(ops.RING_ROWPATCH, g0, img.device)   # (None on planes narrower than 128 pixels)
+        z0 = ops.conv_rowpatch_fwd(ops.img_pad8_cached(img, 3, True), P["e0"], g0,
+                                   None if es0 is None else ops.epilogue(stats=es0))
+        st0 = ops.in_stats(z0) if es0 is None else ops.in_stats_from(es0, H * W, 64)
         y0 = ops.norm_act_fwd(z0, st0, ACT_RELU)
         g1 = ops.conv_geom(B, H, W, 64, 128, 4, 4, 2, 1, 1, H // 2, W // 2)
         z1, st1 = _conv_stats(y0, P["e1"], g1)

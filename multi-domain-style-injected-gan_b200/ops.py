@@ -96,10 +96,10 @@ def epilogue(bias=None, aux=None, aux_mode=AUX_NONE, act=ACT_NONE, alpha=1.0, al
     if mask_norm is not None and stats_z is not None and MASK_FROM_Z and aux_mode in (AUX_RELU_MASK, AUX_LRELU_MASK):
         return Epilogue(_p(bias), None, aux_mode, act, alpha, _p(alpha_ptr), slope, out_layout,
                         _p(None if stats is None else stats.buf), _p(stats_z), _p(ch_scale),
-                        _p(mask_norm.scale), _p(mask_norm.shift))
+                        _p(mask_norm.ready().scale), _p(mask_norm.shift), 0 if stats is None else stats.item_rows)
     return Epilogue(_p(bias), _p(aux), aux_mode if aux is not None else AUX_NONE, act, alpha,
                     _p(alpha_ptr), slope, out_layout, _p(None if stats is None else stats.buf), _p(stats_z),
-                    _p(ch_scale), None, None)
+                    _p(ch_scale), None, None, 0 if stats is None else stats.item_rows)
 
 
 # The epilogue-fused reductions cost ~900 cycles per 64 accumulator columns per tile; they are hidden
@@ -120,12 +120,29 @@ def epi_fusable(taps, c):
 
 
 class EpiStats:
-    """Partial-sum buffer of the epilogue-fused reductions: [n * rows_per_img][2][ld] fp32."""
-    __slots__ = ("buf", "n", "rows", "ld")
+    """Partial-sum buffer of the epilogue-fused reductions: [n * rows_per_img][2][ld] fp32. item_rows > 0: the
+    strip-ring kernel's layout, one row per (work item, phase, accumulator quadrant) (msig_epilogue.stats_rows)."""
+    __slots__ = ("buf", "n", "rows", "ld", "item_rows")
 
-    def __init__(self, n, rows_per_img, k, device):
-        self.n, self.rows, self.ld = n, rows_per_img, (k + 63) // 64 * 64
+    def __init__(self, n, rows_per_img, k, device, item_rows=0):
+        self.n, self.rows, self.ld, self.item_rows = n, rows_per_img, (k + 63) // 64 * 64, item_rows
         self.buf = torch.empty((n * rows_per_img, 2, self.ld), dtype=F32, device=device)
+
+
+RING_ITEM_STATS = __import__('os').environ.get('MSIG_RING_ITEM_STATS', '1') != '0'     # A/B switch, default on
+RING_ROWPATCH, RING_CONVT, RING_CONV = 0, 1, 2
+
+
+def ring_stats(kind, g, device):
+    """EpiStats in the ring kernel's per-item layout for a layer that runs on the strip-ring kernel (kind:
+    RING_ROWPATCH / RING_CONVT / RING_CONV), or None when it does not (the caller then takes a separate
+    statistics pass): the kernel's lean epilogue keeps each pixel column's sums in registers over the rows of a
+    work item, so these short-K layers get their InstanceNorm statistics without a pass over the activation."""
+    if not RING_ITEM_STATS:
+        return None
+    ensure_init(device)
+    rows = int(L.load().msig_ring_stats_rows(kind, ctypes.byref(g)))
+    return EpiStats(g.n, rows, g.k, device, item_rows=rows) if rows > 0 else None
 
 
 def epi_stats(n, oh, ow, k, device, phases=1):
@@ -416,6 +433,11 @@ class NormStats:
 FIN_FOLD_ROWS = int(__import__('os').environ.get('MSIG_FIN_FOLD_ROWS', '32'))
 
 
+def _fold_ok(rows, c):
+    """rows x channels of partials every block of the apply kernel may fold itself (32 rows at 256 channels)."""
+    return rows * c <= FIN_FOLD_ROWS * 256
+
+
 def in_stats(x, gamma=None, beta=None, gb_stride=0, eps=1e-5):
     n, h, w, c = x.shape
     st = NormStats(n, c, x.device)
@@ -431,7 +453,7 @@ def in_stats_from(es, hw, c, gamma=None, beta=None, gb_stride=0, eps=1e-5):
     partial rows per image the finalize is deferred into the norm_act_fwd launch that consumes it."""
     st = NormStats(es.n, c, es.buf.device)
     st.pending = (es, hw, c, gamma, beta, gb_stride, eps)
-    if es.rows > FIN_FOLD_ROWS:
+    if not _fold_ok(es.rows, c):
         st.ready()
     return st
 
@@ -444,7 +466,7 @@ def norm_bwd_from(es, g, x, st, dgamma=None, dbeta=None, dgb_stride=0, accumulat
         out = torch.empty_like(x)
     st.ready()
     coef = torch.empty((n, 2, c), dtype=F32, device=x.device)
-    fn = "msig_norm_bwd_from_partials_fused" if es.rows <= FIN_FOLD_ROWS else "msig_norm_bwd_from_partials"
+    fn = "msig_norm_bwd_from_partials_fused" if _fold_ok(es.rows, c) else "msig_norm_bwd_from_partials"
     L.call(fn, _p(es.buf), n, es.rows, es.ld, _p(g), _p(x), _p(st.mean), _p(st.rstd),
            _p(st.scale), _p(st.shift), h * w, c, _p(out), _p(dgamma), _p(dbeta), dgb_stride, int(accumulate_dgb),
            _p(coef), _stream())

@@ -189,6 +189,50 @@ def case_ring_stack_vs_legacy(n, h, w, r, seed=0):
     return max(rel_err(nchw(y_new), ref), rel_err(nchw(y_old), ref), rel_err(y_new, y_old)), 1e-2
 
 
+def case_ring_item_stats(kind, n, h, w, seed=0):
+    """InstanceNorm statistics out of the ring kernel's lean epilogue (one partial row per work item, phase and
+    accumulator quadrant, msig_epilogue.stats_rows) against the separate statistics pass over the same stored
+    output, for the three ring-kernel entry points: the row-patch 7x7 3 -> 64 conv (model.py:131), the 128 -> 64
+    transposed conv (model.py:140), a 3x3 64 -> 64 conv. The conv output itself must not change."""
+    ops.ensure_init()
+    dev = torch.device(DEV)
+    if kind == ops.RING_ROWPATCH:
+        img = _rand((n, 3, h, w), seed).to(DEV)
+        wt = _bf(_rand((64, 3, 7, 7), seed + 1, 0.08)).to(DEV)
+        wpk = ops.wpack(L.WPACK_ROWPATCH, wt.float().contiguous(), 64, 3, 7, 7)
+        g = ops.conv_geom(n, h, w, 3, 64, 7, 7, 1, 3, 3, h, w)
+        xin = ops.img_pad8(img, 3, True)
+        run = lambda e: ops.conv_rowpatch_fwd(xin, wpk, g, e)                                   # noqa: E731
+    elif kind == ops.RING_CONVT:
+        x = nhwc(_bf(_rand((n, 128, h, w), seed)).to(DEV))
+        wt = _bf(_rand((128, 64, 4, 4), seed + 1, 0.03)).to(DEV)
+        wpk = ops.wpack(L.WPACK_CONVT_FWD, wt.float().contiguous(), 64, 128, 4, 4)
+        g = ops.conv_geom(n, h, w, 128, 64, 4, 4, 2, 1, 1, 2 * h, 2 * w)
+        run = lambda e: ops.convT2d_fwd(x, wpk, g, e)                                           # noqa: E731
+    else:
+        x = nhwc(_bf(_rand((n, 64, h, w), seed)).to(DEV))
+        wt = _bf(_rand((64, 64, 3, 3), seed + 1, 0.04)).to(DEV)
+        wpk = ops.wpack(L.WPACK_FWD, wt.float().contiguous(), 64, 64, 3, 3)
+        g = ops.conv_geom(n, h, w, 64, 64, 3, 3, 1, 1, 1, h, w)
+        run = lambda e: ops.conv2d_fwd(x, wpk, g, e)                                            # noqa: E731
+    b = _rand((64,), seed + 2).to(DEV)
+    es = ops.ring_stats(kind, g, dev)
+    assert es is not None and es.item_rows == es.rows > 0
+    es.buf.fill_(float("nan"))                       # every row must be written
+    z = run(ops.epilogue(bias=b, act=L.ACT_LRELU, stats=es))
+    z_plain = run(ops.epilogue(bias=b, act=L.ACT_LRELU))
+    st = ops.in_stats_from(es, g.oh * g.ow, 64).ready()
+    ref = ops.in_stats(z_plain)
+    torch.cuda.synchronize()
+    if not torch.equal(z, z_plain):
+        return 1.0, 1e-5
+    zf = z.float()
+    mean_t = zf.mean((1, 2))
+    rstd_t = 1.0 / torch.sqrt(zf.var((1, 2), unbiased=False) + 1e-5)
+    errs = [rel_err(st.mean, ref.mean), rel_err(st.rstd, ref.rstd), rel_err(st.mean, mean_t), rel_err(st.rstd, rstd_t)]
+    return max(errs), 1e-5
+
+
 def case_conv_wgrad(n, c, h, w, k, r, stride, pad, seed=0):
     ops.ensure_init()
     oh = (h + 2 * pad - r) // stride + 1
@@ -473,6 +517,11 @@ CASES = {
     "ring_fwd_3x3_64_ragged": lambda: case_conv_fwd(3, 64, 40, 200, 64, 3, 1, 1, act=L.ACT_RELU),
     "ring_fwd_3x3_64_tall": lambda: case_conv_fwd(2, 64, 300, 128, 64, 3, 1, 1),
     "ring_dgrad_3x3_64_256w": lambda: case_conv_dgrad(2, 64, 48, 256, 64, 3, 1, 1),
+    "ring_item_stats_rowpatch": lambda: case_ring_item_stats(ops.RING_ROWPATCH, 2, 64, 256),
+    "ring_item_stats_rowpatch_ragged_b5": lambda: case_ring_item_stats(ops.RING_ROWPATCH, 5, 37, 200, seed=2),
+    "ring_item_stats_convT": lambda: case_ring_item_stats(ops.RING_CONVT, 2, 24, 128, seed=3),
+    "ring_item_stats_convT_ragged": lambda: case_ring_item_stats(ops.RING_CONVT, 3, 37, 200, seed=4),
+    "ring_item_stats_conv3x3": lambda: case_ring_item_stats(ops.RING_CONV, 2, 40, 200, seed=5),
     "ring_stack_vs_legacy_3x3": lambda: case_ring_stack_vs_legacy(3, 40, 200, 3),
     "ring_stack_vs_legacy_3x3_b32_tall": lambda: case_ring_stack_vs_legacy(5, 300, 128, 3, seed=2),
     "ring_stack_1row_items": lambda: case_conv_fwd(2, 64, 1, 256, 64, 3, 1, 1, act=L.ACT_RELU, seed=3),
