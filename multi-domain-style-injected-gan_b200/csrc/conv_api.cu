@@ -693,7 +693,8 @@ int32_t msig_epilogue_stats_rows(int32_t oh, int32_t ow, int32_t phases) {
 // Rows PER IMAGE of msig_epilogue.stats_partial when the strip-ring kernel writes one partial row per (work item,
 // phase, accumulator quadrant) (msig_epilogue.stats_rows); 0: this layer does not run on the ring kernel (use the
 // per-tile rows of msig_epilogue_stats_rows, or a separate statistics pass). kind 0: msig_conv_rowpatch_fwd,
-// kind 1: msig_convT2d_fwd, kind 2: msig_conv2d_fwd (64 -> 64 channels, stride 1).
+// kind 1: msig_convT2d_fwd, kind 2: msig_conv2d_fwd (64 -> 64 channels, stride 1), kind 3: msig_conv2d_dgrad of a
+// 4x4 stride-2 conv 64 -> 128 (with stats_z + mask_scale / mask_shift: the norm-backward reductions).
 int32_t msig_ring_stats_rows(int32_t kind, const msig_conv_geom* g) {
   if (!g || g_ring_mode == 0 || !context_ready()) return 0;
   FpropParams p;
@@ -706,6 +707,11 @@ int32_t msig_ring_stats_rows(int32_t kind, const msig_conv_geom* g) {
   } else if (kind == 1) {
     if (g->c != 128 || g->k != 64 || g->w < 128 || (g_ring_mode & 2) == 0) return 0;
     p.OH = g->h; p.OW = g->w;
+    nph = 4;
+  } else if (kind == 3) {       // msig_conv2d_dgrad of a 4x4 stride-2 conv 64 -> 128: a phased 128 -> 64 structure over dy
+    if (g->k != 128 || g->c != 64 || g->ow < 128 || g->stride != 2 || g->r != 4 || g->s != 4 || (g_ring_mode & 2) == 0)
+      return 0;
+    p.OH = g->oh; p.OW = g->ow;
     nph = 4;
   } else if (kind == 2) {
     if (g->stride != 1 || g->c != 64 || g->k != 64 || g->r * g->s < 2 || g->r * g->s > 9 || g->r > 7 || g->s > 8 ||

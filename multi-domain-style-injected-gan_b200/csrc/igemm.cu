@@ -453,6 +453,46 @@ __device__ __forceinline__ void epilogue_lean_stats(const FpropParams& p, const 
   }
 }
 
+// Lean epilogue of a dgrad whose output feeds an InstanceNorm backward (ring_item_stats with stat_z): the activation
+// mask is recomputed from the norm input z and its per-(image, channel) scale / shift (msk = [scale[64] | shift[64]] in
+// shared memory), g = act'(z*scale + shift) * alpha * acc is stored as bf16, and the two reductions of the norm
+// backward -- sum g, sum g*z of the values as stored -- stay in this thread's registers over the rows of the work item.
+template <int NC>
+__device__ __forceinline__ void epilogue_lean_mask_stats(const FpropParams& p, const float* msk, float alpha, float off,
+                                                         uint32_t taddr, uint64_t* tempty, bool store,
+                                                         const uint4 (&zv)[NC / 8], __nv_bfloat16* o, float (&s1)[NC],
+                                                         float (&s2)[NC]) {
+  static_assert(NC == 32, "one tcgen05.ld.32x32b.x32 per call");
+  tc_fence_after();
+  uint32_t r[NC];
+  tmem_ld_32x32(taddr, r);
+  tmem_ld_wait();
+  tc_fence_before();
+  mbar_arrive(tempty);                            // the accumulator is in registers
+  if (!store) return;
+#pragma unroll
+  for (int g = 0; g < NC / 8; g += 2) {
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = 8 * g + 2 * j;
+      const __nv_bfloat162* zh = reinterpret_cast<const __nv_bfloat162*>(&zv[c / 8]);
+      const float2 z = __bfloat1622float2(zh[(c % 8) / 2]);
+      float a = __uint_as_float(r[c]) * alpha, b = __uint_as_float(r[c + 1]) * alpha;
+      a = fmaf(z.x, msk[c], msk[64 + c]) > 0.f ? a : a * off;
+      b = fmaf(z.y, msk[c + 1], msk[64 + c + 1]) > 0.f ? b : b * off;
+      const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+      const float2 f = __bfloat1622float2(h);
+      s1[c] += f.x;
+      s2[c] = fmaf(f.x, z.x, s2[c]);
+      s1[c + 1] += f.y;
+      s2[c + 1] = fmaf(f.y, z.y, s2[c + 1]);
+      w[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    stg256(o + 8 * g, make_uint4(w[0], w[1], w[2], w[3]), make_uint4(w[4], w[5], w[6], w[7]));
+  }
+}
+
 // 12 warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 idle, 4..11 = epilogue. The two
 // epilogue warps of a TMEM lane quadrant (warp % 4) split the accumulator columns in halves.
 constexpr int kFpropThreads = 384;
@@ -1176,7 +1216,7 @@ __device__ unsigned long long g_ring_prof[16];
 constexpr int kRingMaxSlots = 16;
 constexpr int kRingMaxTaps = 9;                    // resident [64][64] filter tiles (R * S * channel blocks)
 constexpr int kRingWBytes = 64 * 128;              // one tap: 64 output channels x 64 K
-constexpr int kRingBarBytes = 1024;             // 2 x 16 ring + 2 x 8 accumulator barriers + filter barrier + TMEM slot; +512: bias[64] fp32
+constexpr int kRingBarBytes = 2048;             // barriers + TMEM slot | +512: bias[64] fp32 | +1024: 2 x (mask scale[64], shift[64])
 constexpr int kRingSmemMax = 232448;               // 227 KiB
 static inline int ring_slot_bytes(int S) { return ((kTileM + S - 1) * 128 + 1023) & ~1023; }
 
@@ -1497,7 +1537,52 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
 #ifdef MSIG_RING_PROFILE
     long long e_w = 0, e_ld = 0, e_m = 0;
 #endif
-    if (p.ring_item_stats != 0 && p.stat_out != nullptr && epilogue_is_lean(p, BLOCK_N, true)) {
+    if (p.ring_item_stats != 0 && p.stat_out != nullptr && p.stat_z != nullptr) {
+      // dgrad + activation mask from z + the norm-backward reductions (sum g, sum g*z), one partial row per item
+      const int rows_per_img = p.tiles_w * p.ring_chunks * NPH * 4;
+      float* const msk_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(full_bar) + 1024);   // 2 x [scale | shift]
+      const float off = p.aux_mode == AUX_RELU_MASK ? 0.f : p.slope;
+      const __nv_bfloat16* const z_ph = p.stat_z + p.o_ph[ph] + c_begin;
+      int nitem = 0;
+      for (int item = cta0; item < items; item += cta_stride, ++nitem) {
+        int img, tw, h0, nrows;
+        decode(item, img, tw, h0, nrows);
+        const int ow = tw * kTileM + q * 32 + lane;
+        const bool valid = ow < p.OW;
+        float* const msk = msk_s + (nitem & 1) * 128;
+        if (warp == 4) {                           // this image's mask coefficients (two buffers: see the barrier below)
+          msk[lane] = __ldg(p.mask_scale + int64_t(img) * p.mask_ld + lane);
+          msk[lane + 32] = __ldg(p.mask_scale + int64_t(img) * p.mask_ld + lane + 32);
+          msk[64 + lane] = __ldg(p.mask_shift + int64_t(img) * p.mask_ld + lane);
+          msk[64 + lane + 32] = __ldg(p.mask_shift + int64_t(img) * p.mask_ld + lane + 32);
+        }
+        // all eight epilogue warps: when any of them is past this barrier, all of them have finished the previous
+        // item, so the buffer written for the item after this one is free again
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        float s1[BLOCK_N / 2], s2[BLOCK_N / 2];
+#pragma unroll
+        for (int j = 0; j < BLOCK_N / 2; ++j) s1[j] = s2[j] = 0.f;
+        for (int i = 0; i < nrows; ++i, ++it) {
+          const int as = it % NACC;
+          const int64_t off_o = img * p.o_sn + int64_t(h0 + i) * p.o_sh + int64_t(ow) * p.o_sw;
+          uint4 zv[4];
+          if (valid) {                             // issued ahead of the accumulator wait
+            ldg256(z_ph + off_o, zv[0], zv[1]);
+            ldg256(z_ph + off_o + 16, zv[2], zv[3]);
+          }
+          mbar_wait(&tfull_bar[as], (it / NACC) & 1);
+          epilogue_lean_mask_stats<BLOCK_N / 2>(p, msk + c_begin, alpha, off,
+                                                tmem_base + (static_cast<uint32_t>(q * 32) << 16) + as * BLOCK_N + c_begin,
+                                                &tempty_bar[as], valid, zv, out_ph + off_o, s1, s2);
+        }
+        const float t1 = warp_col_reduce32(s1, lane);
+        const float t2 = warp_col_reduce32(s2, lane);
+        const int li = tw * p.ring_chunks + item % p.ring_chunks;
+        float* so = p.stat_out + ((int64_t(img) * rows_per_img + (li * NPH + ph) * 4 + q) * 2) * p.stat_ld + c_begin + lane;
+        so[0] = t1;
+        so[p.stat_ld] = t2;
+      }
+    } else if (p.ring_item_stats != 0 && p.stat_out != nullptr && epilogue_is_lean(p, BLOCK_N, true)) {
       // InstanceNorm statistics of the stored output, one partial row per (item, phase, quadrant): this thread's
       // pixel column over the item's rows in registers, one warp transpose-reduce per item.
       const int rows_per_img = p.tiles_w * p.ring_chunks * NPH * 4;
@@ -2110,8 +2195,12 @@ cudaError_t launch_fprop_ring64(const FpropParams& p0, int num_sms, cudaStream_t
     return cudaErrorInvalidValue;
   p.ring_stack = g_ring_legacy ? 0 : 1;
   if (p.ring_item_stats != 0) {         // requested rows per image (msig_epilogue.stats_rows) must be what this launch writes
-    if (p.stat_out == nullptr || p.stat_z != nullptr || p.ring_item_stats != p.tiles_w * p.ring_chunks * nph * 4 ||
-        p.aux_mode != AUX_NONE || p.n_valid != 64 || p.out_f32 || p.o_sc != 1 || p.act == ACT_TANH)
+    const bool plain = p.stat_z == nullptr && p.aux_mode == AUX_NONE;                 // statistics of the output
+    const bool masked = p.stat_z != nullptr && p.mask_scale != nullptr && p.mask_shift != nullptr && p.mask_ld >= 64 &&
+                        (p.aux_mode == AUX_RELU_MASK || p.aux_mode == AUX_LRELU_MASK) && p.bias == nullptr &&
+                        p.act == ACT_NONE && p.z_mask == 0;                           // norm-backward reductions
+    if (p.stat_out == nullptr || !(plain || masked) || p.ring_item_stats != p.tiles_w * p.ring_chunks * nph * 4 ||
+        p.n_valid != 64 || p.out_f32 || p.o_sc != 1 || p.act == ACT_TANH || p.fold_c != 0)
       return cudaErrorInvalidValue;
     p.ring_item_stats = 1;
   }

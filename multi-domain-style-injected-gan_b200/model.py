@@ -567,10 +567,21 @@ class _GeneratorFn(torch.autograd.Function):
         _trace(mod, "dz1", dz1)
         if wg:
             ops.conv2d_wgrad(S["y0"], dz1, g1, _grad_buf(enc[3].weight))
-        dy = ops.conv2d_dgrad(dz1, P["e1_d"], g1)      # K = 4*128: too short to hide the fused reductions
-        del dz1
-        _trace(mod, "dy0", dy)
-        dz0 = ops.norm_act_bwd(dy, S["z0"], S["st0"], ACT_RELU)
+        es0 = ops.ring_stats(ops.RING_DGRAD_S2, g1, dev) if ops.MASK_FROM_Z else None
+        if es0 is not None:
+            # strip-ring kernel: ReLU mask from z0 and the reductions of the norm backward in the lean epilogue
+            # (per work item, in registers) -- no separate reduction pass over dy and z0
+            dy = ops.conv2d_dgrad(dz1, P["e1_d"], g1,
+                                  ops.epilogue(aux=S["y0"], aux_mode=AUX_RELU_MASK, stats=es0, stats_z=S["z0"],
+                                               mask_norm=S["st0"]))
+            del dz1
+            _trace(mod, "dy0_masked", dy)
+            dz0 = ops.norm_bwd_from(es0, dy, S["z0"], S["st0"])
+        else:
+            dy = ops.conv2d_dgrad(dz1, P["e1_d"], g1)      # K = 4*128: too short to hide per-tile reductions
+            del dz1
+            _trace(mod, "dy0", dy)
+            dz0 = ops.norm_act_bwd(dy, S["z0"], S["st0"], ACT_RELU)
         _trace(mod, "dz0", dz0)
         if wg:
             # the padded bf16 image copy is re-made (or step-cached), not saved

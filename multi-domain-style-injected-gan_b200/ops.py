@@ -130,19 +130,20 @@ class EpiStats:
 
 
 RING_ITEM_STATS = __import__('os').environ.get('MSIG_RING_ITEM_STATS', '1') != '0'     # A/B switch, default on
-RING_ROWPATCH, RING_CONVT, RING_CONV = 0, 1, 2
+RING_ROWPATCH, RING_CONVT, RING_CONV, RING_DGRAD_S2 = 0, 1, 2, 3
 
 
 def ring_stats(kind, g, device):
     """EpiStats in the ring kernel's per-item layout for a layer that runs on the strip-ring kernel (kind:
-    RING_ROWPATCH / RING_CONVT / RING_CONV), or None when it does not (the caller then takes a separate
+    RING_ROWPATCH / RING_CONVT / RING_CONV / RING_DGRAD_S2), or None when it does not (the caller then takes a separate
     statistics pass): the kernel's lean epilogue keeps each pixel column's sums in registers over the rows of a
     work item, so these short-K layers get their InstanceNorm statistics without a pass over the activation."""
     if not RING_ITEM_STATS:
         return None
     ensure_init(device)
     rows = int(L.load().msig_ring_stats_rows(kind, ctypes.byref(g)))
-    return EpiStats(g.n, rows, g.k, device, item_rows=rows) if rows > 0 else None
+    k = g.c if kind == RING_DGRAD_S2 else g.k        # channels of the tensor the launch writes
+    return EpiStats(g.n, rows, k, device, item_rows=rows) if rows > 0 else None
 
 
 def epi_stats(n, oh, ow, k, device, phases=1):

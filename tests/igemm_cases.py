@@ -233,6 +233,35 @@ def case_ring_item_stats(kind, n, h, w, seed=0):
     return max(errs), 1e-5
 
 
+def case_ring_dgrad_mask_stats(n, h, w, seed=0):
+    """dgrad of the 4x4 stride-2 conv 64 -> 128 (model.py:132) on the ring kernel with the ReLU mask of the layer
+    below recomputed from its norm input z and the norm-backward reductions (sum g, sum g*z) taken per work item in
+    the lean epilogue -- against the plain dgrad + norm backward with its own reduction pass. [n, h, w] = the
+    64-channel plane (h, w even, w/2 >= 128)."""
+    ops.ensure_init()
+    dev = torch.device(DEV)
+    z0 = nhwc(_bf(_rand((n, 64, h, w), seed)).to(DEV))
+    st0 = ops.in_stats(z0)
+    y0 = ops.norm_act_fwd(z0, st0, L.ACT_RELU)
+    dz1 = nhwc(_bf(_rand((n, 128, h // 2, w // 2), seed + 1)).to(DEV))
+    wt = _bf(_rand((128, 64, 4, 4), seed + 2, 0.03)).to(DEV)
+    wd = ops.wpack(L.WPACK_DGRAD_S2, wt.float().contiguous(), 128, 64, 4, 4)
+    g1 = ops.conv_geom(n, h, w, 64, 128, 4, 4, 2, 1, 1, h // 2, w // 2)
+    es = ops.ring_stats(ops.RING_DGRAD_S2, g1, dev)
+    assert es is not None and es.item_rows > 0
+    es.buf.fill_(float("nan"))
+    dy_a = ops.conv2d_dgrad(dz1, wd, g1, ops.epilogue(aux=y0, aux_mode=L.AUX_RELU_MASK, stats=es, stats_z=z0, mask_norm=st0))
+    dz0_a = ops.norm_bwd_from(es, dy_a, z0, st0)
+    dy_b = ops.conv2d_dgrad(dz1, wd, g1)
+    dz0_b = ops.norm_act_bwd(dy_b, z0, st0, L.ACT_RELU)
+    torch.cuda.synchronize()
+    masked_b = torch.where(y0.float() > 0, dy_b.float(), torch.zeros_like(dy_b.float()))
+    if not torch.equal(dy_a.float(), masked_b):
+        return 1.0, 1e-2
+    ref = torch.nn.grad.conv2d_input((n, 64, h, w), wt.float(), nchw(dz1).float(), stride=2, padding=1)
+    return max(rel_err(dz0_a, dz0_b), rel_err(nchw(dy_a), ref * (nchw(y0).float() > 0))), 1e-2
+
+
 def case_conv_wgrad(n, c, h, w, k, r, stride, pad, seed=0):
     ops.ensure_init()
     oh = (h + 2 * pad - r) // stride + 1
@@ -522,6 +551,8 @@ CASES = {
     "ring_item_stats_convT": lambda: case_ring_item_stats(ops.RING_CONVT, 2, 24, 128, seed=3),
     "ring_item_stats_convT_ragged": lambda: case_ring_item_stats(ops.RING_CONVT, 3, 37, 200, seed=4),
     "ring_item_stats_conv3x3": lambda: case_ring_item_stats(ops.RING_CONV, 2, 40, 200, seed=5),
+    "ring_dgrad_mask_item_stats": lambda: case_ring_dgrad_mask_stats(2, 48, 256),
+    "ring_dgrad_mask_item_stats_ragged_b3": lambda: case_ring_dgrad_mask_stats(3, 74, 400, seed=3),
     "ring_stack_vs_legacy_3x3": lambda: case_ring_stack_vs_legacy(3, 40, 200, 3),
     "ring_stack_vs_legacy_3x3_b32_tall": lambda: case_ring_stack_vs_legacy(5, 300, 128, 3, seed=2),
     "ring_stack_1row_items": lambda: case_conv_fwd(2, 64, 1, 256, 64, 3, 1, 1, act=L.ACT_RELU, seed=3),

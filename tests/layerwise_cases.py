@@ -233,14 +233,17 @@ def case_generator_layerwise(b=2, s=64, style_batch=None, seed=0):
             rep.f32(f"bwd.lin{l}.dW", grads[key + "weight"], dgb_r[:, l * 512:(l + 1) * 512].t() @ _r(style))
             rep.f32(f"bwd.lin{l}.db", grads[key + "bias"], dgb_cmp[:, l * 512:(l + 1) * 512].sum(dim=0))
         # encoder, reversed
-        dx2, dz2, dy1, dz1, dy0, dz0 = (nchw(tr[n]) for n in ("dx2", "dz2", "dy1", "dz1", "dy0", "dz0"))
+        dy0_masked = "dy0_masked" in tr           # wide planes: the e1 dgrad's ring epilogue applies the ReLU mask itself
+        dx2, dz2, dy1, dz1, dy0, dz0 = (nchw(tr[n]) for n in ("dx2", "dz2", "dy1", "dz1",
+                                                                "dy0_masked" if dy0_masked else "dy0", "dz0"))
         norm_bwd("bwd.e2", z2, dx2, dz2, relu=True)
         conv_bwd("bwd.e2", lambda x, w: O.st(F.conv2d(x, w, None, stride=2, padding=1)), y1, "content_encoder.6.weight", dz2,
                  lambda acc: rep.bf16("bwd.e2.dy", dy1, _r(acc * (y1 > 0))), "content_encoder.6.weight")
         norm_bwd("bwd.e1", z1, dy1, dz1)
         conv_bwd("bwd.e1", lambda x, w: O.st(F.conv2d(x, w, None, stride=2, padding=1)), y0, "content_encoder.3.weight", dz1,
-                 lambda acc: rep.bf16("bwd.e1.dy", dy0, _r(acc)), "content_encoder.3.weight")
-        norm_bwd("bwd.e0", z0, dy0, dz0, relu=True)
+                 lambda acc: rep.bf16("bwd.e1.dy", dy0, _r(acc * (y0 > 0)) if dy0_masked else _r(acc)),
+                 "content_encoder.3.weight")
+        norm_bwd("bwd.e0", z0, dy0, dz0, relu=not dy0_masked)
         conv_bwd("bwd.e0", lambda x, w: O.st(O.reflect_conv7(O.wq(x), w, None)), img, "content_encoder.0.weight", dz0,
                  lambda acc: rep.f32("bwd.e0.dimg", cpu(img_c.grad), acc), "content_encoder.0.weight")
     G.__dict__.pop("_msig_trace", None)
@@ -347,4 +350,7 @@ CASES = {
     "generator_layerwise_b2_s64": lambda: case_generator_layerwise(2, 64),
     "generator_layerwise_style_broadcast": lambda: case_generator_layerwise(3, 64, style_batch=1, seed=2),
     "generator_layerwise_s128": lambda: case_generator_layerwise(1, 128, seed=3),
+    # 256^2: the planes are wide enough for the strip-ring kernel's per-item statistics (first conv, last transposed
+    # conv) and its masked norm-backward reductions (dgrad of the second conv)
+    "generator_layerwise_s256": lambda: case_generator_layerwise(1, 256, seed=4),
 }
