@@ -49,10 +49,10 @@ EncodeTiledFn encode_tiled();
 // kernel touches global memory before it). With MSIG_PDL=1 / msig_debug_set_pdl(1) the attribute is set and the
 // next kernel's grid is set up while the blocks of its predecessor drain (stream capture records programmatic
 // graph edges). MEASURED (profiles/probe/pdl_r2.txt, B=32 train step, same box A/B): no gain -- 79.95 / 80.05 ms
-// against 79.92 / 79.73 ms for plain launches; with an additional early "launch_dependents" trigger at kernel
-// entry the step was 0.6 ms SLOWER (81.0 vs 80.4 ms) and the graph-vs-eager bit-equality test failed once in the
-// full suite (blocks of a kernel that become resident two launches ahead can keep read-only-cache lines of a
-// buffer the allocator hands to a later producer), so the early trigger is not built and PDL stays off by default.
+// against 79.92 / 79.73 ms for plain launches (CUPTI: the launch gaps of the replayed step total ~0.6 ms, and the
+// persistent tcgen05 kernels own a whole SM, so a dependent block becomes resident only when its predecessor's
+// block exits); with an additional early "launch_dependents" trigger at kernel entry the step was 0.6 ms SLOWER
+// (81.0 vs 80.4 ms), so the early trigger is not built and PDL stays off by default.
 bool pdl_enabled();
 void set_pdl(bool on);
 
