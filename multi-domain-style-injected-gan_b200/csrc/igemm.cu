@@ -1198,9 +1198,16 @@ __global__ void __launch_bounds__(kRfThreads, 1) fprop_rowfold_kernel(const __gr
 //   * with ring_phases = 4 (the four output phases of a stride-2 transposed conv / dgrad, each a 2x2 stride-1 conv
 //     of the SAME input) CTA b works on phase b % 4: the four phases walk the images side by side in ONE launch,
 //     so the input comes from HBM once and the other three phases hit L2.
-// The ring takes whatever shared memory the resident filter leaves (ring_slots, up to 16): with R = 7 input rows
-// in use per output row (row-patch convs) the look-ahead is what hides the strip latency.
-// L2 traffic per 128-pixel tile drops from R*S*24 KiB to ~17 KiB. Epilogue = the generic one (BLOCK_N = 64).
+// The ring takes whatever shared memory the resident filter leaves (ring_slots, up to 16) as look-ahead.
+//   * ring_stack (default): the MMA warp walks INPUT rows. A strip feeds the R output rows y .. y-R+1 through filter
+//     rows 0 .. R-1; their accumulators sit side by side in 8 TMEM stages (output row `it` in stage it % 8) and the
+//     R filter-row tiles of one (s, channel block) back to back in shared memory (r descending), so one
+//     N = 64 R MMA per (strip, s, k step) replaces R N = 64 ones and a strip is consumed exactly once. Legacy order
+//     (msig_debug_set_ring_mode bit 2): one N = 64 MMA chain per OUTPUT row over its R resident strips, 4 stages.
+//   * epilogues: lean (bias + ReLU / LeakyReLU, bf16 NHWC: the accumulator stage is handed back as soon as it is in
+//     registers); lean + per-item statistics (ring_item_stats: a thread keeps the sums of its pixel column over the
+//     rows of the work item, one warp transpose-reduce per item -- plain sum v, sum v^2, or with stat_z and
+//     mask_scale / mask_shift the masked dgrad's sum g, sum g*z); anything else goes through the generic epilogue.
 #ifdef MSIG_RING_PROFILE
 // Probe build only (make PROF=1 -> libmsig_prof.so): cycles per role, summed over CTAs.
 //  [0] MMA warp: wait tempty  [1] wait strips  [2] issue + commit  [3] tiles
