@@ -1084,33 +1084,40 @@ __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const 
 }
 
 // [n,hw,c] -> [n,c] mean; one block per image, (c/8) x lanes threads
+// grid = (n, c / 64): one block per image and 64-channel chunk, 8 channel groups x 32 pixel lanes, every lane's
+// loads independent (the first version gave an image ONE block whose threads walked hw / 4 pixels one dependent
+// L2 round trip at a time: 20 us for a 4 MB tensor at batch 16)
 __global__ void __launch_bounds__(256) avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, int hw, int c,
                                                           __nv_bfloat16* __restrict__ y) {
   pdl_entry();
   __shared__ float red[8][256 + 1];
   const int img = blockIdx.x;
-  for (int c0 = 0; c0 < c; c0 += 512) {   // 64 groups of 8 channels per pass
-    const int cw = min(512, c - c0);
-    const int cg = cw / 8, lanes = 256 / cg;
-    const int tx = threadIdx.x % cg, ty = threadIdx.x / cg;
-    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (threadIdx.x < cg * lanes)
-      for (int p = ty; p < hw; p += lanes) {
-        float f[8];
-        load8(x + (int64_t(img) * hw + p) * c + c0 + tx * 8, f);
+  const int c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x % 8, ty = threadIdx.x / 8;      // channel group, pixel lane (32)
+  float a[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const __nv_bfloat16* px = x + int64_t(img) * hw * c + c0 + tx * 8;
+  for (int p = ty; p < hw; p += 32 * 4) {
+    float f[4][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] += f[j];
-      }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) red[j][threadIdx.x] = a[j];
-    __syncthreads();
-    for (int ch = threadIdx.x; ch < cw; ch += 256) {
-      const int gx = ch / 8, j = ch % 8;
-      float s = 0.f;
-      for (int l = 0; l < lanes; ++l) s += red[j][l * cg + gx];
-      y[int64_t(img) * c + c0 + ch] = __float2bfloat16(s / hw);
+    for (int u = 0; u < 4; ++u) {
+      const int pp = min(p + 32 * u, hw - 1);                 // clamped, unconditional loads: all four in flight
+      load8(px + int64_t(pp) * c, f[u]);
     }
-    __syncthreads();
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (p + 32 * u < hw) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] += f[u][j];
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[j][threadIdx.x] = a[j];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    const int gx = threadIdx.x / 8, j = threadIdx.x % 8;
+    float s = 0.f;
+    for (int l = 0; l < 32; ++l) s += red[j][l * 8 + gx];
+    y[int64_t(img) * c + c0 + threadIdx.x] = __float2bfloat16(s / hw);
   }
 }
 __global__ void avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int hw, int c,
@@ -1537,7 +1544,7 @@ int msig_maxpool2_bwd(const void* dy, const void* x, const void* y, int32_t n, i
 }
 int msig_avgpool_fwd(const void* x, int32_t n, int32_t hw, int32_t c, void* y, void* stream) {
   MSIG_REQUIRE(x && y && c % 64 == 0, "msig_avgpool_fwd: bad argument");
-  MSIG_LAUNCH((avgpool_fwd_kernel), n, 256, 0, ST(stream), CBF(x), hw, c, BF(y));
+  MSIG_LAUNCH((avgpool_fwd_kernel), dim3(n, c / 64), 256, 0, ST(stream), CBF(x), hw, c, BF(y));
   count_launch(1);
   MSIG_CHECK_LAUNCH();
   return MSIG_OK;
