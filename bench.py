@@ -210,52 +210,63 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def time_dominant_kernel(torch, ops, L, batch, iters=20):
-    """The dominant kernel: 3x3 s1 p1 256->256 implicit GEMM at 64x64 (80% of generator FLOPs)."""
+def _time_launch(torch, launch, sets, reps=4, iters=12):
+    """Duration of one launch of a kernel timed alone, two ways, both with CUDA events on the launching stream after
+    warm-up: (a) ONE launch between two events, a 256 MB flush kernel before every timed launch; (b) the average over
+    `reps` back-to-back passes over `sets` DISTINCT operand sets whose footprint is several times the 126 MB L2 (cold
+    operands, no flush kernel in between). (a) carries the event / launch latency of a single launch (~5 us: 20 % of a
+    25 us kernel), (b) the gaps between launches; the kernel's own duration (ncu: profiles/ncu_*_r2.txt) is below
+    both, so the smaller one is reported as kernel_ms and both are listed."""
+    for k in range(sets):
+        launch(k)
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > L2 (126 MB)
+    total = 0.0
+    for i in range(iters):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        launch(i % sets)
+        e1.record()
+        e1.synchronize()
+        total += e0.elapsed_time(e1)
+    single = total / iters
+    del flush
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        for k in range(sets):
+            launch(k)
+    e1.record()
+    e1.synchronize()
+    chain = e0.elapsed_time(e1) / (reps * sets)
+    return min(single, chain), {"single_launch_l2_flushed_ms": single, "back_to_back_rotating_sets_ms": chain}
+
+
+def time_dominant_kernel(torch, ops, L, batch, sets=6):
+    """The dominant kernel: 3x3 s1 p1 256->256 implicit GEMM at 64x64 (80% of generator FLOPs); 6 rotating
+    (input, output) pairs = 6 x 134 MB at batch 32."""
     dev = torch.device("cuda")
-    x = torch.randn(batch, 64, 64, 256, device=dev).to(torch.bfloat16)
+    xs = [torch.randn(batch, 64, 64, 256, device=dev).to(torch.bfloat16) for _ in range(sets)]
+    ys = [torch.empty(batch, 64, 64, 256, device=dev, dtype=torch.bfloat16) for _ in range(sets)]
     w = torch.randn(256, 256, 3, 3, device=dev) * 0.02
     wpk = ops.wpack(L.WPACK_FWD, w, 256, 256, 3, 3)
     g = ops.conv_geom(batch, 64, 64, 256, 256, 3, 3, 1, 1, 1, 64, 64)
-    y = torch.empty(batch, 64, 64, 256, device=dev, dtype=torch.bfloat16)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > L2 (126 MB)
-    for _ in range(3):
-        ops.conv2d_fwd(x, wpk, g, out=y)
-    total = 0.0
-    for _ in range(iters):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ops.conv2d_fwd(x, wpk, g, out=y)
-        e1.record()
-        e1.synchronize()
-        total += e0.elapsed_time(e1)
-    ms = total / iters
+    ms, how = _time_launch(torch, lambda k: ops.conv2d_fwd(xs[k], wpk, g, out=ys[k]), sets)
     flops = 2.0 * batch * 4096 * 256 * 2304
-    return ms, flops
+    return ms, flops, how
 
 
-def time_hbm_kernel(torch, ops, L, batch, iters=20):
+def time_hbm_kernel(torch, ops, L, batch, sets=6):
     """The dominant HBM-bound kernel: fused norm-apply + ReLU (norm_act_fwd_kernel) on the residual-block
-    activation [B,64,64,256] bf16: 1 read + 1 write per element, L2 flushed, CUDA events."""
+    activation [B,64,64,256] bf16: 1 read + 1 write per element; 6 rotating (input, output) pairs."""
     dev = torch.device("cuda")
-    x = torch.randn(batch, 64, 64, 256, device=dev).to(torch.bfloat16)
-    y = torch.empty_like(x)
-    st = ops.in_stats(x)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for _ in range(3):
-        ops.norm_act_fwd(x, st, L.ACT_RELU, out=y)
-    total = 0.0
-    for _ in range(iters):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        ops.norm_act_fwd(x, st, L.ACT_RELU, out=y)
-        e1.record()
-        e1.synchronize()
-        total += e0.elapsed_time(e1)
-    ms = total / iters
-    return ms, 2.0 * x.numel() * 2
+    xs = [torch.randn(batch, 64, 64, 256, device=dev).to(torch.bfloat16) for _ in range(sets)]
+    ys = [torch.empty_like(x) for x in xs]
+    st = ops.in_stats(xs[0])
+    ms, how = _time_launch(torch, lambda k: ops.norm_act_fwd(xs[k], st, L.ACT_RELU, out=ys[k]), sets)
+    return ms, 2.0 * xs[0].numel() * 2, how
 
 
 def ncu_traffic():
@@ -392,9 +403,9 @@ def run_ours(args):
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     peak_mem = torch.cuda.max_memory_allocated(dev) / 2 ** 30
     kb = min(B, 32)                              # roofline kernels are timed at (up to) batch 32
-    kms, kflops = time_dominant_kernel(torch, ops, L, kb)
+    kms, kflops, khow = time_dominant_kernel(torch, ops, L, kb)
     ach = kflops / (kms * 1e-3) / 1e12
-    hms, hbytes = time_hbm_kernel(torch, ops, L, kb)
+    hms, hbytes, hhow = time_hbm_kernel(torch, ops, L, kb)
     hach = hbytes / (hms * 1e-3) / 1e9
     step_tf = step_flops(B, S) / (ms / args.steps * 1e-3) / 1e12
     line = {
@@ -416,10 +427,13 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": 2.0 * (2 * kb * 4096 * 256 + 256 * 2304),
                      "traffic_note": "dram__bytes_read+write of one launch (ncu --set full, profiles/ncu_fprop_r2.txt); "
                                      "below the algorithmic bytes because most of the output is still in L2 when the kernel ends",
-                     "peak_source": pk["source"] + " (burst, kernel timed alone, L2 flushed)"},
+                     "kernel_ms_by_method": khow,
+                     "peak_source": pk["source"] + " (burst; kernel timed alone: the smaller of a single L2-flushed launch and back-to-back launches over 6 rotating operand sets)"},
         "roofline_hbm": {"bound": "hbm", "achieved": hach, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": hach / pk["hbm_gbs"],
                          "kernel": "norm_act_fwd_kernel (IN/AdaIN apply + ReLU) [%d,64,64,256] bf16, 1R+1W" % kb,
-                         "kernel_ms": hms, "algorithmic_bytes_per_launch": hbytes, "peak_source": pk["source"]},
+                         "kernel_ms": hms, "algorithmic_bytes_per_launch": hbytes,
+                         "kernel_ms_by_method": hhow,
+                         "peak_source": pk["source"] + " (kernel timed alone: the smaller of a single L2-flushed launch and back-to-back launches over 6 rotating operand sets)"},
         "step_tflops": {"achieved": step_tf, "peak_sustained": pk["bf16_sustained"], "frac": step_tf / pk["bf16_sustained"],
                         "flops_per_step": step_flops(B, S), "note": "necessary algorithmic FLOPs (SURVEY 8d) / step time"},
     }
