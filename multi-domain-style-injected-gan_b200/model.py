@@ -7,10 +7,16 @@ Reference: /root/reference/model.py:9-214. Tensors at the module surface are fp3
 reference's; internally activations are bf16 NHWC and accumulation / statistics are fp32.
 
 Autograd contract: each network is ONE torch.autograd.Function. Its backward returns the gradients
-of the image and the style code; parameter gradients are accumulated by the wgrad kernels DIRECTLY
-into `param.grad` (allocated on demand), so flat gradient buffers (trainer / data parallel) are
-written in place. `torch.autograd.grad(out, params)` therefore reports None for parameters.
+of the image and the style code; by default ("direct" delivery) parameter gradients are accumulated by
+the wgrad kernels DIRECTLY into `param.grad` (allocated on demand), so flat gradient buffers (trainer /
+data parallel) are written in place and `torch.autograd.grad(out, params)` reports None for parameters.
+`set_param_grad_delivery("autograd")` switches to returning them from backward like any PyTorch op
+(`torch.autograd.grad`, tensor hooks, `GradScaler`, a DDP wrapper then see them; costs one extra
+accumulation pass); the drop-in trainer always runs "direct".
 """
+import contextlib
+import functools
+
 import torch
 import torch.nn as nn
 
@@ -25,11 +31,60 @@ F32 = torch.float32
 BF16 = torch.bfloat16
 
 
+_DELIVERY = "direct"     # "direct": wgrad kernels accumulate into param.grad; "autograd": backward returns the gradients
+_sink = None             # id(param) -> gradient tensor of the backward call in flight ("autograd" delivery)
+
+
+def set_param_grad_delivery(mode):
+    """How the network Functions hand out PARAMETER gradients: "direct" (default) or "autograd" (see the module
+    docstring). Process-wide; returns the previous mode."""
+    global _DELIVERY
+    if mode not in ("direct", "autograd"):
+        raise ValueError("param grad delivery must be 'direct' or 'autograd'")
+    prev, _DELIVERY = _DELIVERY, mode
+    ops.PTR_TABLE_CACHE = mode == "direct"      # the cached device pointer tables assume gradient buffers that stay put
+    return prev
+
+
+@contextlib.contextmanager
+def param_grad_delivery(mode):
+    prev = set_param_grad_delivery(mode)
+    try:
+        yield
+    finally:
+        set_param_grad_delivery(prev)
+
+
 def _grad_buf(p):
-    """param.grad as an accumulation target (zero-filled on first use)."""
+    """The accumulation target of a parameter's gradient: param.grad (zero-filled on first use), or in "autograd"
+    delivery a fresh zero tensor that the running backward returns for that parameter."""
+    if _sink is not None:
+        g = _sink.get(id(p))
+        if g is None:
+            g = _sink[id(p)] = torch.zeros_like(p)
+        return g
     if p.grad is None:
         p.grad = torch.zeros_like(p)
     return p.grad
+
+
+def _delivers_param_grads(backward):
+    """Decorator of a network Function's backward (inputs: module, two tensors, then *module.parameters()): in
+    "autograd" delivery the trailing Nones become the gradients the wgrad kernels wrote during this call."""
+    @functools.wraps(backward)
+    def wrapped(ctx, *grads):
+        global _sink
+        if _DELIVERY != "autograd":
+            return backward(ctx, *grads)
+        params = list(ctx.mod.parameters())
+        outer, _sink = _sink, {}
+        try:
+            out = backward(ctx, *grads)
+            sink = _sink
+        finally:
+            _sink = outer
+        return tuple(out[:len(out) - len(params)]) + tuple(sink.get(id(p)) for p in params)
+    return wrapped
 
 
 def _trace(mod, name, t):
@@ -244,6 +299,7 @@ class _ResBlockFn(torch.autograd.Function):
         return ops.to_f32(out).permute(0, 3, 1, 2)
 
     @staticmethod
+    @_delivers_param_grads
     @ops.dev_guard
     def backward(ctx, dout):
         mod, S = ctx.mod, ctx.saved
@@ -469,6 +525,7 @@ class _GeneratorFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_delivers_param_grads
     @ops.dev_guard
     def backward(ctx, dout):
         mod, S = ctx.mod, ctx.saved
@@ -707,6 +764,7 @@ class _StyleEncoderFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_delivers_param_grads
     @ops.dev_guard
     def backward(ctx, dout):
         mod, S = ctx.mod, ctx.saved
@@ -845,6 +903,7 @@ class _DiscriminatorFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_delivers_param_grads
     @ops.dev_guard
     def backward(ctx, dout):
         mod, S = ctx.mod, ctx.saved

@@ -566,6 +566,7 @@ def gemm_tn_partial(rows, a, m, b, ncols):
 
 
 _ptr_tables = {}
+PTR_TABLE_CACHE = True
 
 
 def grad_ptr_table(tensors):
@@ -574,6 +575,8 @@ def grad_ptr_table(tensors):
     hold the table's address). Built with a host->device copy, so the first use must be outside a CUDA-graph
     capture -- the trainer's first step is always eager."""
     ptrs = tuple(t.data_ptr() for t in tensors)
+    if not PTR_TABLE_CACHE:       # "autograd" gradient delivery (model.set_param_grad_delivery): fresh buffers every call
+        return torch.tensor(ptrs, dtype=torch.int64).to(tensors[0].device)
     key = (tensors[0].device, ptrs)
     tab = _ptr_tables.get(key)
     if tab is None:
@@ -587,8 +590,9 @@ def grad_ptr_table(tensors):
 def multi_linear_grads(ws, splits, split_stride, dy, rows, ld, layers, out_features, in_features, wgrads, bgrads):
     """dW / db of `layers` Linear layers evaluated as one batched GEMM, accumulated into their own gradient
     tensors in one launch (see msig_multi_linear_grads)."""
+    wtab, btab = grad_ptr_table(wgrads), grad_ptr_table(bgrads)     # both alive until the launch is enqueued
     L.call("msig_multi_linear_grads", _p(ws), splits, split_stride, _p(dy), rows, ld, layers, out_features,
-           in_features, _p(grad_ptr_table(wgrads)), _p(grad_ptr_table(bgrads)), _stream())
+           in_features, _p(wtab), _p(btab), _stream())
 
 
 def wgrad_unpack(kind, o, i, r, s, ws, splits, split_stride, dw, accumulate=True, oc=0, o_off=0,

@@ -24,7 +24,7 @@ import torch
 
 from . import ops
 from .losses import L1Loss, MSELoss, VGGStyleContentLoss
-from .model import MultiDomainDiscriminator, MultiDomainStyleEncoder, StyleCycleGANGenerator
+from .model import MultiDomainDiscriminator, MultiDomainStyleEncoder, StyleCycleGANGenerator, param_grad_delivery
 from .parallel import FlatAllReduce
 from .utils import EMA, DynamicWeightScheduler, FlatParams, FusedAdam
 
@@ -107,7 +107,9 @@ class MultiDomainStyleCycleGAN:
     def train_step(self, batch, epoch):
         """One G+D optimisation step (reference trainer.py:74-155). Returns the same dict of loss
         tensors: D_loss, G_loss, gan, cycle, identity, style, content."""
-        with torch.cuda.device(self.device):      # streams / workspaces of the trainer's device, whatever is current
+        # streams / workspaces of the trainer's device, whatever is current; the flat gradient buffers and the fused
+        # optimizer need the wgrad kernels to write param.grad in place ("direct" delivery)
+        with torch.cuda.device(self.device), param_grad_delivery("direct"):
             if self.use_cuda_graph:
                 return self._train_step_graphed(batch, epoch)
             return self._train_step_eager(batch, epoch)

@@ -557,6 +557,53 @@ def case_translate_vs_oracle(b=3, s=64, nd=4, seed=0):
     return res, ok
 
 
+def case_param_grads_via_autograd(seed=0):
+    """model.set_param_grad_delivery("autograd"): torch.autograd.grad(loss, params) returns the parameter gradients
+    of G / SE / D (the default "direct" delivery writes them into param.grad and reports None), a tensor hook on a
+    parameter fires, and the values are bit-identical with the "direct" ones."""
+    torch.manual_seed(seed)
+    nd = 3
+    G = M.StyleCycleGANGenerator().to(DEV)
+    SE = M.MultiDomainStyleEncoder(num_domains=nd).to(DEV)
+    D = M.MultiDomainDiscriminator(num_domains=nd).to(DEV)
+    g = torch.Generator().manual_seed(seed + 1)
+    img = (torch.rand(2, 3, 64, 64, generator=g) * 2 - 1).to(DEV)
+    ref = (torch.rand(2, 3, 64, 64, generator=g) * 2 - 1).to(DEV)
+    dom = torch.randint(0, nd, (2,), generator=g).to(DEV)
+
+    def loss():
+        fake = G(img, SE(ref, dom))
+        return D(fake, dom).square().mean() + fake.abs().mean()
+    params = list(G.parameters()) + list(SE.parameters()) + list(D.parameters())
+    for p in params:
+        p.grad = None
+    loss().backward()                                   # "direct"
+    direct = [None if p.grad is None else p.grad.clone() for p in params]
+    fired = []
+    h = G.decoder[0].conv1.weight.register_hook(lambda gr: fired.append(float(gr.abs().sum())))
+    prev = M.set_param_grad_delivery("autograd")
+    try:
+        for p in params:
+            p.grad = None
+        grads = torch.autograd.grad(loss(), params, allow_unused=True)
+        untouched = all(p.grad is None for p in params)
+        loss().backward()                               # AccumulateGrad path: param.grad filled by autograd
+        via_backward = [None if p.grad is None else p.grad.clone() for p in params]
+    finally:
+        M.set_param_grad_delivery(prev)
+        h.remove()
+    torch.cuda.synchronize()
+    res = {"params": float(len(params)), "hook_fired": float(len(fired)), "grad_left_untouched": float(untouched)}
+    bad = 0
+    for d, a, v in zip(direct, grads, via_backward):
+        if d is None or a is None or v is None:
+            bad += int(not (d is None and a is None and v is None))
+        else:
+            bad += int(not (torch.equal(d, a) and torch.equal(d, v)))
+    res["mismatching"] = float(bad)
+    return res, bad == 0 and len(fired) == 2 and untouched
+
+
 def case_graph_vs_eager(b=2, s=64, nd=3, steps=3, seed=0):
     """The CUDA-graph replay of train_step (steps 2..n) against the same steps run eagerly."""
     from msig_b200 import trainer as T
@@ -753,6 +800,7 @@ CASES = {
     "train_step_b1_s512_nd10": lambda: case_train_step(1, 512, 10, 1),
     "gd_512_b1": case_gd_512,
     "translate_vs_oracle": case_translate_vs_oracle,
+    "param_grads_via_autograd": case_param_grads_via_autograd,
     "train_step_graph_vs_eager": case_graph_vs_eager,
     "translate_graph_vs_eager": case_translate_graph,
     "translate_batches_pipeline": case_translate_batches,
