@@ -138,9 +138,35 @@ def case_pad8_tail(n=2, h=24, w=40, seed=0):
     return {"slack_zero": float(slack_zero), "nan": float(nan), "err": err}, slack_zero and not nan and err <= 1e-2
 
 
+def case_poisoned_translate(b=3, s=128, nd=4, seed=0):
+    """inference.translate (style encoder + generator forward, inference.py:119,290), eager, with every fresh buffer
+    NaN-poisoned and NaN-guarded == the clean call, bit for bit."""
+    from msig_b200 import inference as I
+    from msig_b200 import model as M
+    ops.ensure_init()
+    torch.manual_seed(seed)
+    G = M.StyleCycleGANGenerator().to(DEV).eval()
+    SE = M.MultiDomainStyleEncoder(num_domains=nd).to(DEV).eval()
+    g = torch.Generator().manual_seed(seed + 1)
+    src = (torch.rand(b, 3, s, s, generator=g) * 2 - 1).to(DEV)
+    ref = (torch.rand(b, 3, s, s, generator=g) * 2 - 1).to(DEV)
+    dom = torch.randint(0, nd, (b,), generator=g).to(DEV)
+    with poisoned() as state:
+        y0 = I.translate(G, SE, src, ref, dom, use_cuda_graph=False).clone()
+        state["on"] = True
+        y1 = I.translate(G, SE, src, ref, dom, use_cuda_graph=False).clone()
+        state["on"] = False
+    torch.cuda.synchronize()
+    nan = int(torch.isnan(y1).sum())
+    diff = int((y0 != y1).sum()) if nan == 0 else -1
+    return {"nan": float(nan), "differing": float(diff)}, nan == 0 and diff == 0
+
+
 CASES = {
     "pad8_tail_guard": case_pad8_tail,
     "pad8_tail_guard_64": lambda: case_pad8_tail(2, 64, 64, seed=2),
+    "poisoned_translate_b3_s128": case_poisoned_translate,
+    "poisoned_translate_b2_s256": lambda: case_poisoned_translate(2, 256, 10, seed=2),
     "poisoned_train_step_b2_s64": case_poisoned_train_step,
     # BASELINE.json configs[0] shape (B=1, 256x256, 10 domains): the tilings of the bench workload
     "poisoned_train_step_b1_s256_nd10": lambda: case_poisoned_train_step(1, 256, 10),
