@@ -381,6 +381,8 @@ CASES = {
     "gather_3x3_affine": lambda: case_patch_gather(1, 3, 16, 24, 3, 1, 1, False, affine=True),
     "gather_7x7_full_c3": lambda: case_patch_gather(1, 3, 20, 20, 7, 1, 6, False),
     "gather_4x4_c16": lambda: case_patch_gather(2, 16, 16, 16, 4, 1, 1, False),
+    "gather_7x7_c16_reflect": lambda: case_patch_gather(2, 16, 24, 40, 7, 1, 3, True),             # kpad 832
+    "gather_4x4s2_256": lambda: case_patch_gather(3, 3, 256, 256, 4, 2, 1, False, seed=2),         # SE / D first layer
     "scatter_7x7_reflect": lambda: case_patch_scatter(2, 3, 32, 40, 7, 1, 3, True),
     "scatter_4x4s2_zero": lambda: case_patch_scatter(2, 3, 32, 32, 4, 2, 1, False),
     "scatter_3x3_affine": lambda: case_patch_scatter(1, 3, 16, 24, 3, 1, 1, False, affine=True),
