@@ -1213,6 +1213,7 @@ __global__ void __launch_bounds__(kRfThreads, 1) fprop_rowfold_kernel(const __gr
 //  [0] MMA warp: wait tempty  [1] wait strips  [2] issue + commit  [3] tiles
 //  [4] epilogue warp 4: wait tfull  [5] tcgen05.ld  [6] math + stores  [7] tiles
 //  [8] producer: wait empty slot  [9] strips   [10] kernel cycles (CTA 0)
+//  [11] stacked MMA loop: piece setup  [12] MMA issue  [13] commits (issuing thread)
 __device__ unsigned long long g_ring_prof[16];
 #define RING_PROF_T(var) const long long var = clock64()
 #define RING_PROF_ADD(acc, a, b) acc += (b) - (a)
@@ -1355,7 +1356,7 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
     uint32_t g0s = 0, g0p = 0;
     int it = 0;
 #ifdef MSIG_RING_PROFILE
-    long long m_te = 0, m_fu = 0, m_is = 0;
+    long long m_te = 0, m_fu = 0, m_is = 0, m_setup = 0, m_mma = 0, m_commit = 0;
 #endif
     auto entry = [&](int off, uint32_t& sl, uint32_t& par) {      // entry g0 + off (off < 2 * SLOTS)
       uint32_t x = g0s + static_cast<uint32_t>(off);
@@ -1370,6 +1371,13 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
     // operand reads (~60 cycles for 32 cycles of math); at N = 192 the A strip is read once for three rows' worth.
     // Pieces: an MMA may not wrap around the 8 stages, N <= 256, and the first MMA into a NEW output row
     // overwrites (accumulate = 0) that row's 64 columns only.
+    // What bounds it now (profiles/probe/mma_rate.cu, ring_profile_r2.txt): the pipe runs these MMAs at their math
+    // floor (N >= 128: N / 2 cycles; N = 64: 48, its 6 KiB of operand reads) but queues only ~2 instructions beyond
+    // the one in flight, so whatever the issuing thread does between rows beyond ~190 cycles -- barrier waits
+    // ~350, piece setup ~290, commits ~170 per row -- drains it: ~1.3 k cycles of MMAs in a ~2.1 k cycle tile.
+    // Preparing the next row between the current row's MMAs (one thread running the whole loop, phases after every
+    // k step) measured 2-4x SLOWER, inlined (the issue loop outgrows the instruction cache: ~300 cycles per MMA)
+    // and as a non-inlined call (state in local memory): not adopted.
     if (STACK) {
       uint32_t gs = 0, gp = 0;               // ring cursor: strips are consumed strictly in load order
       int it0 = 0;                           // running output-row counter at the start of the item
@@ -1419,6 +1427,8 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
             }
             const uint64_t wd0 = make_smem_desc(w_addr, 0, 1024) + static_cast<uint64_t>(b0 * (kRingWBytes >> 4));
             uint32_t sl = gs;
+            RING_PROF_T(ts1);
+            RING_PROF_ADD(m_setup, t2, ts1);
             for (int cb = 0; cb < CB; ++cb) {
               const uint32_t sa = ring_addr + sl * slot_bytes;
               for (int s = 0; s < S; ++s) {
@@ -1448,12 +1458,16 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
               }
               if (++sl == static_cast<uint32_t>(SLOTS)) sl = 0;
             }
+            RING_PROF_T(ts2);
+            RING_PROF_ADD(m_mma, ts1, ts2);
             sl = gs;
             for (int cb = 0; cb < CB; ++cb) {                                    // this input row is dead now
               umma_commit(&empty_bar[sl]);
               if (++sl == static_cast<uint32_t>(SLOTS)) sl = 0;
             }
             if (j >= R - 1) umma_commit(&tfull_bar[(it0 + j - R + 1) & 7]);      // output row j - R + 1 is complete
+            RING_PROF_T(ts3);
+            RING_PROF_ADD(m_commit, ts2, ts3);
           }
           __syncwarp();
           RING_PROF_T(t3);
@@ -1522,6 +1536,11 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
       atomicAdd(&g_ring_prof[1], static_cast<unsigned long long>(m_fu));
       atomicAdd(&g_ring_prof[2], static_cast<unsigned long long>(m_is));
       atomicAdd(&g_ring_prof[3], static_cast<unsigned long long>(it));
+    }
+    if (elect_one()) {       // (the stacked loop's finer counters live in the issuing thread)
+      atomicAdd(&g_ring_prof[11], static_cast<unsigned long long>(m_setup));
+      atomicAdd(&g_ring_prof[12], static_cast<unsigned long long>(m_mma));
+      atomicAdd(&g_ring_prof[13], static_cast<unsigned long long>(m_commit));
     }
 #endif
   } else if (warp >= 4) {

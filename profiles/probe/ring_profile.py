@@ -51,3 +51,5 @@ for name, fn in runs:
     print(f"   MMA warp per tile: wait tempty {v[0] / tiles:.0f}  wait strips {v[1] / tiles:.0f}  issue+commit {v[2] / tiles:.0f}  cycles")
     print(f"   epilogue warp 4 per tile: wait tfull {v[4] / et:.0f}  tcgen05.ld+arrive {v[5] / et:.0f}  math+stores {v[6] / et:.0f}  cycles")
     print(f"   producer per strip: wait free slot {v[8] / strips:.0f} cycles ({strips / 148:.1f} strips/CTA)")
+    if v[12]:
+        print(f"   stacked issue loop per tile: piece setup {v[11] / tiles:.0f}  MMA issue {v[12] / tiles:.0f}  commits {v[13] / tiles:.0f}  cycles")
