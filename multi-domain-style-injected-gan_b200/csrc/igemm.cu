@@ -1390,18 +1390,21 @@ __global__ void __launch_bounds__(kFpropThreads, 1) fprop_ring64_kernel(const __
           const int nb = i_hi - i_lo + 1;
           const bool has_new = j <= nrows - 1;
           RING_PROF_T(t0);
-          if (has_new) {
-            const int itn = it0 + j;
-            mbar_wait(&tempty_bar[itn & 7], (((itn >> 3) & 1) ^ 1u));
-          }
+          // The row's barriers (accumulator stage of its new output row, its CB strips) are polled back to back
+          // before any result is looked at: a poll is a ~100-cycle round trip, and this thread's idle time between
+          // rows is exposed (the pipe queues only ~2 MMAs).
+          const int itn = it0 + j;
+          uint64_t* const te = &tempty_bar[itn & 7];
+          const uint32_t tpar = ((itn >> 3) & 1) ^ 1u;
+          uint32_t sl1 = gs + 1, par1 = gp;
+          if (sl1 == static_cast<uint32_t>(SLOTS)) { sl1 = 0; par1 ^= 1u; }
+          const bool ok_e = has_new ? mbar_try_wait(te, tpar) : true;
+          const bool ok_0 = mbar_try_wait(&full_bar[gs], gp);
+          const bool ok_1 = CB > 1 ? mbar_try_wait(&full_bar[sl1], par1) : true;
+          if (!ok_e) mbar_wait(te, tpar);
           RING_PROF_T(t1);
-          {
-            uint32_t sl = gs, par = gp;
-            for (int cb = 0; cb < CB; ++cb) {
-              mbar_wait(&full_bar[sl], par);
-              if (++sl == static_cast<uint32_t>(SLOTS)) { sl = 0; par ^= 1u; }
-            }
-          }
+          if (!ok_0) mbar_wait(&full_bar[gs], gp);
+          if (!ok_1) mbar_wait(&full_bar[sl1], par1);
           RING_PROF_T(t2);
           RING_PROF_ADD(m_te, t0, t1);
           RING_PROF_ADD(m_fu, t1, t2);
